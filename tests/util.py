@@ -1,0 +1,55 @@
+"""Shared helpers for the parity tests (recipes, golden loader, error metrics)."""
+from __future__ import annotations
+
+import functools
+import os
+
+import numpy as np
+import torch
+
+from text2speech_b200 import synthetic as syn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SIGMA = 0.666
+RECIPES = {                       # must match tests/golden/make_golden.py
+    "bench": dict(seed=1234, end_std=0.01, gain=1.0),
+    "stress": dict(seed=4321, end_std=0.01, gain=2.0),
+}
+# Tolerances (north_star): per-WN-layer relative L2 <= 2e-3 in BF16 mode, <= 1e-5 in the FP32
+# validation mode, end-to-end audio SNR >= 30 dB against reference FP32.
+TOL_LAYER_BF16 = 2e-3
+TOL_LAYER_FP32 = 1e-5
+MIN_SNR_DB = 30.0
+
+
+def load_golden():
+    out = {}
+    for name in ("waveglow_golden.npz", "stft_golden.npz"):
+        with np.load(os.path.join(HERE, "golden", name)) as f:
+            out.update({k: f[k] for k in f.files})
+    return out
+
+
+@functools.lru_cache(maxsize=4)
+def state_dict(recipe: str, weight_norm: bool = False):
+    return syn.synthetic_state_dict(syn.load_config(), weight_norm=weight_norm, **RECIPES[recipe])
+
+
+def golden_inputs(bsz=2, frames=6):
+    mel = syn.synthetic_mel(bsz, frames, seed=0)
+    z = syn.synthetic_z(bsz, frames, seed=2024)
+    g = torch.Generator().manual_seed(1)
+    wav = (0.1 * torch.randn((bsz, frames * 256), generator=g)).clamp(-1, 1)
+    return mel, z, wav
+
+
+def rel_l2(a, b) -> float:
+    a = torch.as_tensor(a, dtype=torch.float64).flatten()
+    b = torch.as_tensor(b, dtype=torch.float64).flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def snr_db(x, ref) -> float:
+    x = torch.as_tensor(x, dtype=torch.float64).flatten()
+    ref = torch.as_tensor(ref, dtype=torch.float64).flatten()
+    return float(10 * torch.log10(ref.pow(2).sum() / (x - ref).pow(2).sum().clamp_min(1e-300)))
