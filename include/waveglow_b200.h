@@ -1,0 +1,134 @@
+/* waveglow_b200 — C ABI of the B200-native vocoding path (libwaveglow_b200.so).
+ *
+ * The reference (DonggeunYu/Text2Speech) has no FFI: its hot path sits behind Python nn.Modules
+ * (waveglow/glow.py, waveglow/denoiser.py, utils/stft.py, utils/layers.py).  The drop-in Python
+ * classes in text2speech_b200/ keep that module API and state_dict layout and call ONLY the
+ * functions below (ctypes), so this header is the whole device-side contract.  Each entry point
+ * cites the reference code it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; wgb_last_error() then holds a
+ *     human-readable message (thread-local).  No CPU fallback exists anywhere: a missing GPU or
+ *     a non-sm_100 device is an error.
+ *   - all pointers are DEVICE pointers (caller-allocated, caller-owned: torch owns memory);
+ *     `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream.
+ *   - activations are channels-last: h/acts [B, T, 512], cond [B, T, 640], flow state x [B, T, 8]
+ *     (T = group steps = samples / 8).  "bf16" buffers hold __nv_bfloat16.
+ *   - safe to call concurrently from different host threads on different devices/streams.
+ */
+#ifndef WAVEGLOW_B200_H_
+#define WAVEGLOW_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WGB_ABI_VERSION 1
+#if defined(__GNUC__)
+#define WGB_API __attribute__((visibility("default")))
+#else
+#define WGB_API
+#endif
+
+WGB_API int wgb_abi_version(void);
+WGB_API const char* wgb_last_error(void);
+/* 0 iff `device` exists and is compute capability 10.x; selects nothing. */
+WGB_API int wgb_device_check(int device);
+
+/* ---------------------------------------------------------------- flow state / small convs */
+
+/* x[b,t,c] = sigma * z[b,c,t].  Replaces the noise draws + `sigma*audio` of WaveGlow.infer
+ * (glow.py:260-269, :284-289): z [B,8,T] is host-supplied noise in WaveGlow.forward's output layout. */
+WGB_API int wgb_flow_from_z(const float* z, float* x, int batch, int T, float sigma, void* stream);
+/* z[b,c,t] = x[b,t,c]: the cat(output_audio, 1) of WaveGlow.forward (glow.py:248-249). */
+WGB_API int wgb_flow_to_z(const float* x, float* z, int batch, int T, void* stream);
+/* x[:, 8-C:] <- W x[:, 8-C:], W as fp32 [8][8] row-major (top-left CxC): Invertible1x1Conv.forward
+ * (glow.py:100-101).  log|det W| is computed on the host. */
+WGB_API int wgb_flow_mix(float* x, const float* w, long long rows, int C, void* stream);
+/* WN.start 1x1 conv (glow.py:122-124,156): h[r,:] = W[512,n_half] x[r, 8-2*n_half : 8-n_half] + b.
+ * out_bf16 selects a bf16 (tensor-core path) or fp32 (validation path) h. */
+WGB_API int wgb_wn_start(const float* x, const float* w, const float* bias, void* h, int out_bf16, long long rows,
+                 int n_ch, int n_half, void* stream);
+
+/* ---------------------------------------------------------------- WN layers, BF16 tensor-core path */
+
+/* in_layers[i] (k=3, dilation) + cond_layers[i] + fused_add_tanh_sigmoid_multiply
+ * (glow.py:33-40, :159-162).  h bf16 [B,T,512], cond bf16 [B,T,640] -> acts bf16 [B,T,512].
+ * w_packed bf16 [1024][2176] and bias fp32 [1024] in the packed row order documented in
+ * text2speech_b200/packing.py (pass p: tanh rows 128p.., then sigmoid rows 512+128p..). */
+WGB_API int wgb_tc_wn_gate(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts,
+                   int batch, int T, int dilation, void* stream);
+/* residual half of res_skip_layers[i] (glow.py:164-166): h_out = h_in + W_res[512][512] acts + b. */
+WGB_API int wgb_tc_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out,
+                  int batch, int T, void* stream);
+/* skip half of all res_skip_layers (glow.py:167-174) as one K = n_layers*512 GEMM over the stored
+ * acts_all bf16 [n_layers][B][T][512], then WN.end (glow.py:175), the affine coupling and — for
+ * direction 0 (infer, glow.py:277-282) — the inverse 1x1 conv W^-1 (w_mix fp32 [8][8]); direction 1
+ * (forward, glow.py:241-246) writes log_s fp32 [B,n_half,T].  w_skip bf16 [512][n_layers*512],
+ * w_end fp32 [512][8] (transposed, zero padded), b_end fp32 [8] with the skip biases folded in. */
+WGB_API int wgb_tc_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end,
+                       const float* b_end, float* x, const float* w_mix, float* log_s, int batch, int T,
+                       int n_half, int direction, void* stream);
+
+/* Plain tcgen05 GEMM with the same TMA/TMEM pipeline: C[b,t,n] = sum_k A[b,t,k] W[n,k] + bias[n];
+ * A bf16 [B,T,K] (K % 64 == 0), W bf16 [N,K] (N % 256 == 0), C fp32 or bf16 [B,T,N]; bias may be NULL.
+ * Serves the dense-basis contractions that are 1x1 convs in the reference (cond/upsample/STFT bases,
+ * glow.py:141-143,183-185; stft.py:85-89) and the exact-arithmetic unit tests of the pipeline. */
+WGB_API int wgb_tc_gemm(const void* a, const void* w, const float* bias, void* c, int out_bf16, int batch, int T,
+                        int N, int K, void* stream);
+
+/* ---------------------------------------------------------------- FP32 validation path (CUDA cores) */
+
+/* C[b][m][n] (+)= sum_k A[b][m+shift][k] W[n][k] + bias[n]; rows outside [0,M) read as zero, so a
+ * dilated conv tap is a GEMM with a row shift (in_layers, glow.py:136-139,160), a 1x1 conv is
+ * shift 0 (cond/res_skip/end), the STFT is A = overlapping frames (lda = hop; stft.py:85-89).
+ * K, lda, ldw, a_batch must be multiples of 4.  out_bf16: C is bf16 (no accumulate). */
+WGB_API int wgb_sgemm_f32(const float* A, const float* W, const float* bias, void* C, int out_bf16, int batch, int M,
+                  int N, int K, long long lda, long long a_batch, long long ldw, long long ldc,
+                  long long c_batch, int shift, int accumulate, void* stream);
+/* acts = tanh(u[:, :C]) * sigmoid(u[:, C:]) with accurate tanhf/expf (glow.py:33-40). */
+WGB_API int wgb_gate_f32(const float* u, float* acts, long long rows, int n_ch, void* stream);
+/* has_res: h += rs[:, :C]; skip (+)= rs[:, C:]   else: skip (+)= rs   (glow.py:165-174). */
+WGB_API int wgb_res_skip_f32(const float* rs, float* h, float* skip, long long rows, int n_ch, int has_res,
+                     int first, void* stream);
+/* WN.end + coupling (+ W^-1 for infer) from an fp32 skip sum [B*T, n_ch]; same math as the
+ * epilogue of wgb_tc_wn_skip_end. */
+WGB_API int wgb_end_coupling_f32(const float* skip, const float* w_end, const float* b_end, float* x,
+                         const float* w_mix, float* log_s, int batch, int T, int n_ch, int n_half,
+                         int direction, void* stream);
+
+/* ---------------------------------------------------------------- upsample (ConvTranspose1d as GEMM) */
+
+/* A[b,q,j*ld_tap+c] = mel[b,c,q-j] (zero if q<j or c>=n_mel): the four frames feeding output samples
+ * [256q, 256q+256) of WaveGlow.upsample (glow.py:183-185,252); the GEMM against the repacked
+ * [20480][taps*ld_tap] weight then writes the regrouped cond [B, 32F, 640] directly (glow.py:254-258). */
+WGB_API int wgb_upsample_im2col(const float* mel, void* a, int out_bf16, int batch, int n_mel, int F, int taps,
+                        int ld_tap, void* stream);
+WGB_API int wgb_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+
+/* ---------------------------------------------------------------- STFT / mel / denoiser glue */
+
+/* reflect pad by `half` each side into ypad[B, ld_pad] (stft.py:79-83). */
+WGB_API int wgb_stft_reflect_pad(const float* y, float* ypad, int batch, int N, int half, long long ld_pad, void* stream);
+/* spec[B,F,2cp] -> magnitude/phase [B,cutoff,F] (stft.py:91-97), optional channels-last mag_cl[B,F,cp];
+ * any of mag / phase / mag_cl may be NULL. */
+WGB_API int wgb_stft_polar(const float* spec, float* mag, float* phase, float* mag_cl, int batch, int F, int cutoff,
+                   int cp, void* stream);
+/* out[b,m,f] = log(max(raw[b,f,m], clip))  (layers.py:77-78; audio_processing.py:70-76). */
+WGB_API int wgb_mel_log(const float* raw, float* out, int batch, int F, int n_mel, float clip, void* stream);
+/* in-place spectral subtraction on spec rows (denoiser.py:36-38 + the cos/sin recombination of
+ * stft.py:102-103, done as a magnitude ratio). */
+WGB_API int wgb_denoise_scale(float* spec, const float* bias, float strength, long long rows, int cutoff, int cp,
+                      void* stream);
+/* (magnitude, phase) [B,cutoff,F] -> spec[B,F,2cp]  (stft.py:102-103). */
+WGB_API int wgb_stft_recombine(const float* mag, const float* phase, float* spec, int batch, int F, int cutoff, int cp,
+                       void* stream);
+/* overlap-add + window-sum normalisation + xL/hop + trim (stft.py:105-128; audio_processing.py:7-48):
+ * frames [B,F,L] -> out [B, hop*(F-1)]; win_sq = fp64 squared padded window [L]. */
+WGB_API int wgb_istft_overlap_add(const float* frames, const double* win_sq, float* out, int batch, int F, int L,
+                          int hop, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAVEGLOW_B200_H_ */

@@ -24,7 +24,7 @@ cross-checked against torchaudio's independent implementation:
 "parity unpinned" for ``mel_basis`` only.
 """
 from .waveglow_oracle import (  # noqa: F401
-    fold_weight_norm, folded_state, wn_stack, waveglow_infer, waveglow_forward,
+    fold_weight_norm, folded_state, wn_layer, wn_stack, waveglow_infer, waveglow_forward,
     regroup_spect, upsample_spect, flow_channels,
 )
 from .stft_oracle import (  # noqa: F401

@@ -68,6 +68,20 @@ def regroup_spect(up: Tensor, n_group: int) -> Tensor:
     return up[:, :, : t * n_group].reshape(b, m, t, n_group).permute(0, 1, 3, 2).reshape(b, m * n_group, t)
 
 
+def wn_layer(st: Dict[str, Tensor], k: int, i: int, h: Tensor, cond: Tensor) -> Tuple[Tensor, Tensor]:
+    """Gated layer i of WN k (glow.py:159-164): returns (acts, res_skip_acts); ``st`` is folded."""
+    p = f"WN.{k}."
+    w_in = st[p + f"in_layers.{i}.weight"]
+    n_ch = w_in.shape[1]
+    d = 2 ** i                                                               # glow.py:134-137
+    pad = (w_in.shape[2] - 1) * d // 2
+    u = F.conv1d(h, w_in, st[p + f"in_layers.{i}.bias"], dilation=d, padding=pad)
+    u = u + F.conv1d(cond, st[p + f"cond_layers.{i}.weight"], st[p + f"cond_layers.{i}.bias"])
+    acts = torch.tanh(u[:, :n_ch]) * torch.sigmoid(u[:, n_ch:])              # glow.py:33-40
+    r = F.conv1d(acts, st[p + f"res_skip_layers.{i}.weight"], st[p + f"res_skip_layers.{i}.bias"])
+    return acts, r
+
+
 def wn_stack(st: Dict[str, Tensor], k: int, a0: Tensor, cond: Tensor, n_layers: int,
              taps: Optional[dict] = None) -> Tensor:
     """One WN module (glow.py:154-175) for flow k; ``st`` must be weight-norm-folded.
@@ -80,13 +94,7 @@ def wn_stack(st: Dict[str, Tensor], k: int, a0: Tensor, cond: Tensor, n_layers: 
     n_ch = h.shape[1]
     total = None
     for i in range(n_layers):
-        w_in = st[p + f"in_layers.{i}.weight"]
-        d = 2 ** i                                                           # glow.py:134-137
-        pad = (w_in.shape[2] - 1) * d // 2
-        u = F.conv1d(h, w_in, st[p + f"in_layers.{i}.bias"], dilation=d, padding=pad)
-        u = u + F.conv1d(cond, st[p + f"cond_layers.{i}.weight"], st[p + f"cond_layers.{i}.bias"])
-        acts = torch.tanh(u[:, :n_ch]) * torch.sigmoid(u[:, n_ch:])          # glow.py:33-40
-        r = F.conv1d(acts, st[p + f"res_skip_layers.{i}.weight"], st[p + f"res_skip_layers.{i}.bias"])
+        acts, r = wn_layer(st, k, i, h, cond)
         if taps is not None:
             taps[f"h{i}"] = h
             taps[f"acts{i}"] = acts

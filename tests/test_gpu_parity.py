@@ -1,0 +1,373 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors.
+
+Tolerances are north_star's: per-WN-layer relative L2 <= 2e-3 in BF16 mode, <= 1e-5 in the FP32
+validation mode, end-to-end audio SNR >= 30 dB against reference FP32.
+
+BF16 per-layer protocol: bf16's unit round-off is 2^-8, so ONE rounding to bf16 is already
+~1.6e-3 relative L2.  Kernel correctness is therefore judged with bf16-representable weights and
+inputs on both sides (the oracle runs them in fp32): what is left is fp32 accumulation order, the
+MUFU gate and the single bf16 rounding of the stored output.  The effect of quantising fp32
+weights to bf16 is covered by the end-to-end SNR tests, which use the unrounded weights in the oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests import util
+from text2speech_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def q(t):
+    """round to bf16-representable fp32"""
+    return t.bfloat16().float()
+
+
+def quantised_state(recipe):
+    sd = util.state_dict(recipe)
+    hot = (".in_layers.", ".cond_layers.", ".res_skip_layers.")
+    return {k: (q(v) if k.endswith(".weight") and any(h in k for h in hot) else v) for k, v in sd.items()}
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from text2speech_b200 import _lib
+    _lib.require_b200(torch.device(DEV))
+    return _lib
+
+
+@pytest.fixture(scope="module")
+def packed_q(lib):
+    from text2speech_b200.packing import PackedWaveGlow
+    return {r: PackedWaveGlow(quantised_state(r), 12, 8, 512, 8, "bf16", torch.device(DEV)) for r in ("stress",)}
+
+
+def cl(x):      # [B,C,T] -> channels-last [B,T,C]
+    return x.permute(0, 2, 1).contiguous()
+
+
+# ------------------------------------------------------------------------------------ primitives
+
+@pytest.mark.parametrize("shape", [(1, 200, 72, 64, 0), (3, 130, 1024, 512, -4), (2, 257, 40, 640, 9)])
+def test_sgemm_f32(lib, shape):
+    batch, m, n, k, shift = shape
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn(batch, m, k, generator=g)
+    w = torch.randn(n, k, generator=g)
+    bias = torch.randn(n, generator=g)
+    want = torch.zeros(batch, m, n, dtype=torch.float64)
+    for i in range(m):
+        if 0 <= i + shift < m:
+            want[:, i] = a[:, i + shift].double() @ w.double().t()
+    want += bias.double()
+    c = torch.empty(batch, m, n, device=DEV)
+    lib.call("wgb_sgemm_f32", a.to(DEV), w.to(DEV), bias.to(DEV), c, 0, batch, m, n, k, k, m * k, k, n, m * n, shift, 0,
+             lib.stream_ptr())
+    assert util.rel_l2(c.cpu(), want) < 1e-6
+    # accumulate on top
+    lib.call("wgb_sgemm_f32", a.to(DEV), w.to(DEV), None, c, 0, batch, m, n, k, k, m * k, k, n, m * n, shift, 1,
+             lib.stream_ptr())
+    assert util.rel_l2(c.cpu(), 2 * want - bias.double()) < 1e-6
+
+
+@pytest.mark.parametrize("dil_i,T", [(0, 128), (0, 200), (3, 200), (7, 200), (5, 1000)])
+def test_tc_gate_layer(lib, packed_q, dil_i, T):
+    """in_layers + cond_layers + fused_add_tanh_sigmoid_multiply (glow.py:159-162) on tcgen05."""
+    pk = packed_q["stress"]
+    st = oracle.folded_state(quantised_state("stress"))
+    k, B = 11, 2
+    g = torch.Generator().manual_seed(100 + dil_i)
+    h = q(1.5 * torch.randn(B, 512, T, generator=g))
+    cond = q(0.3 * torch.randn(B, 640, T, generator=g))
+    with torch.no_grad():
+        want, _ = oracle.wn_layer(st, k, dil_i, h, cond)
+    fl = pk.flows[k]
+    acts = torch.zeros(B, T, 512, device=DEV, dtype=torch.bfloat16)
+    lib.call("wgb_tc_wn_gate", cl(h).to(DEV, torch.bfloat16), cl(cond).to(DEV, torch.bfloat16), fl["w_gate"][dil_i],
+             fl["b_gate"][dil_i], acts, B, T, 2 ** dil_i, lib.stream_ptr())
+    torch.cuda.synchronize()
+    err = util.rel_l2(acts.float().cpu(), cl(want))
+    assert err <= util.TOL_LAYER_BF16, err
+
+
+def test_tc_res_layer(lib, packed_q):
+    """residual half of res_skip_layers (glow.py:164-166)."""
+    pk = packed_q["stress"]
+    st = oracle.folded_state(quantised_state("stress"))
+    k, i, B, T = 5, 2, 2, 333
+    g = torch.Generator().manual_seed(5)
+    h = q(2.0 * torch.randn(B, 512, T, generator=g))
+    acts = q(torch.rand(B, 512, T, generator=g) * 2 - 1)
+    w, b = st[f"WN.{k}.res_skip_layers.{i}.weight"], st[f"WN.{k}.res_skip_layers.{i}.bias"]
+    want = h + torch.nn.functional.conv1d(acts, w[:512], b[:512])
+    fl = pk.flows[k]
+    h_out = torch.zeros(B, T, 512, device=DEV, dtype=torch.bfloat16)
+    lib.call("wgb_tc_wn_res", cl(acts).to(DEV, torch.bfloat16), fl["w_res"][i], fl["b_res"][i],
+             cl(h).to(DEV, torch.bfloat16), h_out, B, T, lib.stream_ptr())
+    torch.cuda.synchronize()
+    err = util.rel_l2(h_out.float().cpu(), cl(want))
+    assert err <= util.TOL_LAYER_BF16, err
+
+
+@pytest.mark.parametrize("k,direction", [(11, 0), (5, 0), (0, 0), (11, 1), (4, 1), (1, 1)])
+def test_tc_skip_end_coupling(lib, packed_q, k, direction):
+    """skip sum over 8 layers + WN.end + affine coupling (+ W^-1)  (glow.py:171-175, :277-282 / :241-246)."""
+    pk = packed_q["stress"]
+    st = oracle.folded_state(quantised_state("stress"))
+    fl = pk.flows[k]
+    n_half, B, T = fl["n_half"], 2, 300
+    C, base = 2 * n_half, 8 - 2 * n_half
+    g = torch.Generator().manual_seed(11 + k)
+    acts = q(torch.rand(8, B, 512, T, generator=g) * 2 - 1)
+    x = torch.randn(B, T, 8, generator=g)
+    p = f"WN.{k}."
+    total = 0
+    for i in range(8):
+        w, b = st[p + f"res_skip_layers.{i}.weight"], st[p + f"res_skip_layers.{i}.bias"]
+        lo = 0 if i == 7 else 512
+        total = total + torch.nn.functional.conv1d(acts[i], w[lo: lo + 512], b[lo: lo + 512])
+    out = torch.nn.functional.conv1d(total, st[p + "end.weight"], st[p + "end.bias"])
+    bb, ss = cl(out[:, :n_half]), cl(out[:, n_half:])
+    want = x.clone()
+    a0, a1 = x[:, :, base: base + n_half], x[:, :, base + n_half:]
+    if direction == 0:
+        w_inv = torch.linalg.inv(st[f"convinv.{k}.conv.weight"][:, :, 0].double()).float()
+        want[:, :, base:] = torch.cat([a0, (a1 - bb) / torch.exp(ss)], 2) @ w_inv.t()
+    else:
+        want[:, :, base + n_half:] = torch.exp(ss) * a1 + bb
+    xd = x.to(DEV).contiguous()
+    log_s = torch.zeros(B, n_half, T, device=DEV) if direction == 1 else None
+    acts_all = acts.permute(0, 1, 3, 2).contiguous().to(DEV, torch.bfloat16)
+    lib.call("wgb_tc_wn_skip_end", acts_all, 8, fl["w_skip"], fl["w_end_t"], fl["b_end"], xd,
+             fl["w_mix_inv"] if direction == 0 else None, log_s, B, T, n_half, direction, lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert util.rel_l2(xd.cpu()[:, :, base:], want[:, :, base:]) <= 1e-4
+    assert torch.equal(xd.cpu()[:, :, :base], x[:, :, :base])           # early channels untouched
+    if direction == 1:
+        assert util.rel_l2(log_s.cpu(), out[:, n_half:]) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------ whole model
+
+@pytest.fixture(scope="module")
+def models(lib):
+    import text2speech_b200 as t2s
+    out = {}
+    for recipe in ("bench", "stress"):
+        m = t2s.WaveGlow(**syn.load_config())
+        m = t2s.WaveGlow.remove_weightnorm(m)
+        m.load_state_dict(util.state_dict(recipe))
+        out[recipe] = m.to(DEV).eval()
+    return out
+
+
+@pytest.mark.parametrize("recipe", ["bench", "stress"])
+def test_infer_fp32_mode_matches_reference(models, golden, recipe):
+    m = models[recipe]
+    m.mode = "fp32"
+    mel, z, _ = util.golden_inputs()
+    audio = m.infer(mel.to(DEV), sigma=util.SIGMA, z=z.to(DEV)).cpu()
+    assert audio.shape == (2, 1536)
+    err = util.rel_l2(audio, golden[f"{recipe}_infer_audio"])
+    assert err <= util.TOL_LAYER_FP32 * 3, err      # 12 flows x 8 layers of <=1e-5 layers compound slightly
+
+
+@pytest.mark.parametrize("recipe", ["bench", "stress"])
+def test_infer_bf16_mode_snr(models, golden, recipe):
+    m = models[recipe]
+    m.mode = "bf16"
+    mel, z, _ = util.golden_inputs()
+    audio = m.infer(mel.to(DEV), sigma=util.SIGMA, z=z.to(DEV)).cpu()
+    snr = util.snr_db(audio, golden[f"{recipe}_infer_audio"])
+    assert snr >= util.MIN_SNR_DB, snr
+
+
+def test_fp32_layers_match_golden_taps(models, golden, lib):
+    """FP32 validation mode per layer (<= 1e-5) against taps recorded from the reference modules."""
+    from text2speech_b200 import engine
+    m = models["bench"]
+    m.mode = "fp32"
+    pk = m._packed(torch.device(DEV))
+    fl = pk.flows[11]
+    mel, z, _ = util.golden_inputs()
+    cond = engine.upsample_cond(pk, mel.to(DEV))
+    steps = torch.from_numpy(golden["bench_tap_steps"])
+    with torch.no_grad():
+        taps = {}
+        oracle.waveglow_infer(util.state_dict("bench"), mel, z, util.SIGMA, taps)
+    sub = taps[11]
+    s = lib.stream_ptr()
+    B, T, c = 2, 192, 512
+    for i in (0, 3, 7):
+        h = cl(sub[f"h{i}"]).to(DEV)
+        u = torch.empty(B, T, 2 * c, device=DEV)
+        w_in = fl["w_in"][i]
+        for j in range(3):
+            lib.call("wgb_sgemm_f32", h, w_in[j], fl["b_in"][i] if j == 0 else None, u, 0, B, T, 2 * c, c, c, T * c, c,
+                     2 * c, T * 2 * c, (j - 1) * 2 ** i, int(j > 0), s)
+        lib.call("wgb_sgemm_f32", cond, fl["w_cond"][i], None, u, 0, B, T, 2 * c, 640, 640, T * 640, 640, 2 * c,
+                 T * 2 * c, 0, 1, s)
+        acts = torch.empty(B, T, c, device=DEV)
+        lib.call("wgb_gate_f32", u, acts, B * T, c, s)
+        got = acts[0].cpu().t()[:, steps]
+        assert util.rel_l2(got, golden[f"bench_wn11_acts{i}"]) <= util.TOL_LAYER_FP32
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_forward_matches_reference(models, golden, mode):
+    m = models["bench"]
+    m.mode = mode
+    mel, _, wav = util.golden_inputs()
+    z, log_s, log_det = m((mel.to(DEV), wav.to(DEV)))
+    assert z.shape == (2, 8, 192) and len(log_s) == 12 and len(log_det) == 12
+    if mode == "fp32":
+        assert util.rel_l2(z.cpu(), golden["bench_fwd_z"]) <= 3e-5
+        for k in (0, 5, 11):
+            assert util.rel_l2(log_s[k].cpu(), golden[f"bench_fwd_log_s{k}"]) <= 3e-5
+    else:
+        assert util.snr_db(z.cpu(), golden["bench_fwd_z"]) >= util.MIN_SNR_DB
+    got = np.array([float(v) for v in log_det])
+    assert np.allclose(got, golden["bench_fwd_log_det"], atol=1e-3)
+    # trimmed upsample branch (glow.py:216-218)
+    zs, _, _ = m((mel.to(DEV), wav[:, :-64].to(DEV)))
+    if mode == "fp32":
+        assert util.rel_l2(zs.cpu(), golden["bench_fwd_z_short"]) <= 3e-5
+    else:
+        assert util.snr_db(zs.cpu(), golden["bench_fwd_z_short"]) >= util.MIN_SNR_DB
+
+
+def test_weight_norm_layout_loads_and_matches(golden, lib):
+    import text2speech_b200 as t2s
+    m = t2s.WaveGlow(**syn.load_config())
+    m.load_state_dict(util.state_dict("bench", weight_norm=True))
+    m = m.to(DEV).eval()
+    m.mode = "fp32"
+    mel, z, _ = util.golden_inputs()
+    audio = m.infer(mel[:1, :, :4].to(DEV), sigma=util.SIGMA, z=z[:1, :, :128].to(DEV)).cpu()
+    assert util.rel_l2(audio, golden["bench_wnorm_infer_audio"]) <= 3e-5
+
+
+def test_invertibility_full_utterance(models):
+    """Size-independent property at BASELINE's single-utterance size (80x860 mel, 220160 samples):
+    infer(z = forward(x)) reproduces x (glow.py:243 vs :279)."""
+    m = models["bench"]
+    m.mode = "bf16"
+    frames = 860
+    mel = syn.synthetic_mel(1, frames, seed=3).to(DEV)
+    g = torch.Generator().manual_seed(9)
+    wav = (0.1 * torch.randn(1, frames * 256, generator=g)).clamp(-1, 1).to(DEV)
+    z, _, _ = m((mel, wav))
+    back = m.infer(mel, sigma=1.0, z=z)
+    assert back.shape == (1, 220160)
+    assert util.snr_db(back.cpu(), wav.cpu()) >= util.MIN_SNR_DB
+
+
+def test_batch_sharding_is_exact(models):
+    """Utterances are independent: a batch of 3 equals three batch-1 calls bit for bit (the multi-GPU
+    path shards by utterance)."""
+    m = models["bench"]
+    m.mode = "bf16"
+    mel = syn.synthetic_mel(3, 9, seed=4).to(DEV)
+    z = syn.synthetic_z(3, 9, seed=6).to(DEV)
+    full = m.infer(mel, sigma=util.SIGMA, z=z)
+    for i in range(3):
+        one = m.infer(mel[i:i + 1].contiguous(), sigma=util.SIGMA, z=z[i:i + 1].contiguous())
+        assert torch.equal(one[0], full[i])
+
+
+def test_no_cpu_fallback(models):
+    m = models["bench"]
+    with pytest.raises(RuntimeError):
+        m.infer(torch.zeros(1, 80, 4))
+    with pytest.raises(ValueError):
+        m.infer(torch.zeros(1, 80, 4, device=DEV), z=torch.zeros(1, 8, 5, device=DEV))
+
+
+# ------------------------------------------------------------------------------------ STFT / mel / denoiser
+
+DC = syn.DEFAULT_DATA_CONFIG
+
+
+def test_stft_transform_inverse(golden, lib):
+    import text2speech_b200 as t2s
+    stft = t2s.STFT(1024, 256, 1024).to(DEV)
+    y = syn.synthetic_waveforms(2, 4096, sr=DC["sampling_rate"], seed=5).to(DEV)
+    mag, phase = stft.transform(y)
+    assert mag.shape == (2, 513, 17)
+    assert util.rel_l2(mag.cpu(), golden["stft_mag"]) <= 1e-5
+    rec = stft.inverse(mag, phase)
+    assert rec.shape == (2, 1, 4096)
+    assert util.rel_l2(rec.cpu(), golden["stft_recon"]) <= 1e-4
+    assert util.rel_l2(stft(y).cpu(), y.cpu()[:, None]) <= 1e-4         # forward() round trip
+    with pytest.raises(RuntimeError):
+        stft.transform(torch.zeros(1, 100, device=DEV))                 # reflect pad needs N > L/2
+
+
+def test_stft_window_shorter_than_filter(golden, lib):
+    import text2speech_b200 as t2s
+    stft = t2s.STFT(64, 16, 48).to(DEV)
+    y = syn.synthetic_waveforms(2, 4096, sr=DC["sampling_rate"], seed=5)[:, :512].contiguous().to(DEV)
+    mag, phase = stft.transform(y)
+    assert util.rel_l2(mag.cpu(), golden["small_mag"]) <= 1e-5
+    assert util.rel_l2(stft.inverse(mag, phase).cpu(), golden["small_recon"]) <= 1e-4
+
+
+def test_mel_spectrogram(golden, lib):
+    import text2speech_b200 as t2s
+    taco = t2s.TacotronSTFT(1024, 256, 1024, 80, DC["sampling_rate"], DC["mel_fmin"], DC["mel_fmax"]).to(DEV)
+    y = syn.synthetic_waveforms(2, 4096, sr=DC["sampling_rate"], seed=5).to(DEV)
+    mel = taco.mel_spectrogram(y)
+    assert mel.shape == (2, 80, 17)
+    assert float((mel.cpu() - torch.from_numpy(golden["mel"])).abs().max()) <= 1e-3
+    with pytest.raises(AssertionError):
+        taco.mel_spectrogram(2 * y)                                     # layers.py:72-73 range check
+
+
+def test_denoiser(models, golden, lib):
+    import text2speech_b200 as t2s
+    m = models["bench"]
+    m.mode = "fp32"
+    den = t2s.Denoiser(m)
+    assert den.bias_spec.shape == (1, 513, 1)
+    assert util.rel_l2(den.bias_spec.cpu(), golden["denoiser_bias_spec"]) <= 1e-4
+    y = syn.synthetic_waveforms(2, 4096, sr=DC["sampling_rate"], seed=5).to(DEV)
+    for s, key in ((0.1, "denoised_s0p1"), (0.01, "denoised_s0p01")):
+        out = den(y, strength=s)
+        assert out.shape == (2, 1, 4096)
+        assert util.snr_db(out.cpu(), golden[key]) >= 60.0
+    m.mode = "bf16"
+    den16 = t2s.Denoiser(m)                                             # bias from the tensor-core path
+    assert util.rel_l2(den16.bias_spec.cpu(), golden["denoiser_bias_spec"]) <= 2e-2
+
+
+def test_denoiser_full_size_property(models, lib):
+    """BASELINE cfg5 shape (10 s waveforms): strength 0 is an STFT->ISTFT identity."""
+    import text2speech_b200 as t2s
+    m = models["bench"]
+    m.mode = "bf16"
+    den = t2s.Denoiser(m)
+    y = syn.synthetic_waveforms(4, 220160, sr=DC["sampling_rate"], seed=8).to(DEV)
+    out = den(y, strength=0.0)
+    assert out.shape == (4, 1, 220160)
+    assert util.snr_db(out.cpu()[:, 0], y.cpu()) >= 80.0
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 256, 64), (2, 300, 512, 192), (3, 1000, 1024, 2176)])
+def test_tc_gemm_exact_integers(lib, shape):
+    """TMA -> UMMA -> TMEM pipeline in exact arithmetic (small integers): bit-exact vs fp64."""
+    batch, T, N, K = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    a = torch.randint(-3, 4, (batch, T, K), generator=g).float()
+    w = torch.randint(-3, 4, (N, K), generator=g).float()
+    bias = torch.randint(-8, 9, (N,), generator=g).float()
+    want = (a.double() @ w.double().t() + bias.double()).float()
+    for out_bf16 in (0, 1):
+        c = torch.zeros((batch, T, N), device=DEV, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        lib.call("wgb_tc_gemm", a.to(DEV, torch.bfloat16), w.to(DEV, torch.bfloat16), bias.to(DEV), c, out_bf16, batch, T,
+                 N, K, lib.stream_ptr())
+        torch.cuda.synchronize()
+        ref = want.bfloat16().float() if out_bf16 else want
+        assert torch.equal(c.float().cpu(), ref)

@@ -1,0 +1,84 @@
+"""Host logic without a GPU: weight packing + the kernels' algorithmic restructuring, emulated in
+torch from the PACKED weights, must reproduce the oracle (and hence the reference)."""
+import pytest
+import torch
+
+import oracle
+from tests import emulate, util
+from text2speech_b200.packing import PackedWaveGlow, gate_row_order
+
+
+@pytest.fixture(scope="module")
+def packed():
+    sd = util.state_dict("stress")
+    return PackedWaveGlow(sd, 12, 8, 512, 8, "bf16", torch.device("cpu"))
+
+
+def test_gate_row_order_pairs_tanh_with_sigmoid():
+    order = gate_row_order(512)
+    assert order.shape == (1024,) and sorted(order.tolist()) == list(range(1024))
+    for p in range(4):
+        blk = order[p * 256:(p + 1) * 256]
+        assert torch.equal(blk[128:], blk[:128] + 512)
+
+
+def test_upsample_gemm_matches_conv_transpose(packed):
+    mel, _, _ = util.golden_inputs(2, 5)
+    sd = oracle.folded_state(util.state_dict("stress"))
+    up = oracle.upsample_spect(sd, mel)[:, :, : 5 * 256]
+    want = oracle.regroup_spect(up, 8).permute(0, 2, 1)
+    got = emulate.upsample(packed, mel)
+    assert got.shape == want.shape == (2, 160, 640)
+    assert util.rel_l2(got, want) < 1e-5
+
+
+def test_infer_emulation_fp32_matches_oracle(packed):
+    mel, z, _ = util.golden_inputs(1, 3)
+    with torch.no_grad():
+        want = oracle.waveglow_infer(util.state_dict("stress"), mel, z, util.SIGMA)
+        # bf16 weights, fp32 activations: isolates the packing from activation rounding
+        got = emulate.infer(packed, mel, z, util.SIGMA, round_bf16=False)
+    assert util.snr_db(got, want) > 40.0
+
+
+def test_infer_emulation_bf16_predicts_snr(packed):
+    mel, z, _ = util.golden_inputs(1, 3)
+    with torch.no_grad():
+        want = oracle.waveglow_infer(util.state_dict("stress"), mel, z, util.SIGMA)
+        got = emulate.infer(packed, mel, z, util.SIGMA, round_bf16=True)
+    assert util.snr_db(got, want) > util.MIN_SNR_DB
+
+
+def test_forward_emulation_matches_oracle(packed):
+    mel, _, wav = util.golden_inputs(1, 3)
+    with torch.no_grad():
+        zr, lsr, ldr = oracle.waveglow_forward(util.state_dict("stress"), mel, wav)
+        z, ls, ld = emulate.forward(packed, mel, wav, round_bf16=False)
+    assert util.snr_db(z, zr) > 40.0
+    for k in (0, 5, 11):
+        assert util.rel_l2(ls[k], lsr[k]) < 2e-2
+        assert abs(ld[k] - float(ldr[k])) < 1e-3
+
+
+def test_exact_packing_with_fp32_weights():
+    """Same emulation with the weights left in fp32: must match the oracle to fp32 round-off,
+    proving the permutations / folds are exact (not merely 'close in bf16')."""
+    sd = util.state_dict("stress")
+    pk = PackedWaveGlow(sd, 12, 8, 512, 8, "bf16", torch.device("cpu"))
+    from text2speech_b200 import packing
+    st = packing.folded(sd)
+    for k, fl in enumerate(pk.flows):           # swap bf16 tensors for their fp32 originals
+        p = f"WN.{k}."
+        w_rs = [st[p + f"res_skip_layers.{i}.weight"] for i in range(8)]
+        b_rs = [st[p + f"res_skip_layers.{i}.bias"] for i in range(8)]
+        fl["w_skip"] = packing.pack_skip(w_rs, b_rs, 512)[0]
+        for i in range(8):
+            fl["w_gate"][i] = packing.pack_gate(st[p + f"in_layers.{i}.weight"], st[p + f"in_layers.{i}.bias"],
+                                                st[p + f"cond_layers.{i}.weight"], st[p + f"cond_layers.{i}.bias"])[0]
+            if i < 7:
+                fl["w_res"][i] = w_rs[i][:512, :, 0]
+    mel, z, _ = util.golden_inputs(1, 3)
+    with torch.no_grad():
+        want = oracle.waveglow_infer(sd, mel, z, util.SIGMA)
+        got = emulate.infer(pk, mel, z, util.SIGMA, round_bf16=False)
+    assert util.rel_l2(got, want) < 2e-5

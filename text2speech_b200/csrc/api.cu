@@ -1,0 +1,134 @@
+// extern "C" surface of libwaveglow_b200.so — thin argument adapters over the kernels' host launchers.
+// Declarations (with the reference code each entry point replaces) live in include/waveglow_b200.h.
+#include "../../include/waveglow_b200.h"
+
+#include "common.cuh"
+
+namespace wgb {
+// wn_tc.cu
+int tc_wn_gate(const void*, const void*, const void*, const float*, void*, int, int, int, cudaStream_t);
+int tc_wn_res(const void*, const void*, const float*, const void*, void*, int, int, cudaStream_t);
+int tc_wn_skip_end(const void*, int, const void*, const float*, const float*, float*, const float*, float*, int, int,
+                   int, int, cudaStream_t);
+int tc_gemm_plain(const void*, const void*, const float*, void*, int, int, int, int, int, cudaStream_t);
+// ref_f32.cu
+int sgemm_nt(const float*, const float*, const float*, void*, int, int, int, int, int, long long, long long, long long,
+             long long, long long, int, int, cudaStream_t);
+int gate_f32(const float*, float*, long long, int, cudaStream_t);
+int res_skip_f32(const float*, float*, float*, long long, int, int, int, cudaStream_t);
+// flow.cu
+int flow_from_z(const float*, float*, int, int, float, cudaStream_t);
+int flow_to_z(const float*, float*, int, int, cudaStream_t);
+int flow_mix(float*, const float*, long long, int, cudaStream_t);
+int wn_start(const float*, const float*, const float*, void*, int, long long, int, int, cudaStream_t);
+int end_coupling_f32(const float*, const float*, const float*, float*, const float*, float*, int, int, int, int, int,
+                     cudaStream_t);
+int upsample_im2col(const float*, void*, int, int, int, int, int, int, cudaStream_t);
+int cast_f32_to_bf16(const float*, void*, long long, cudaStream_t);
+// stft.cu
+int stft_reflect_pad(const float*, float*, int, int, int, long long, cudaStream_t);
+int stft_polar(const float*, float*, float*, float*, int, int, int, int, cudaStream_t);
+int mel_log(const float*, float*, int, int, int, float, cudaStream_t);
+int denoise_scale(float*, const float*, float, long long, int, int, cudaStream_t);
+int stft_recombine(const float*, const float*, float*, int, int, int, int, cudaStream_t);
+int istft_overlap_add(const float*, const double*, float*, int, int, int, int, cudaStream_t);
+}  // namespace wgb
+
+using namespace wgb;
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+WGB_API int wgb_abi_version(void) { return WGB_ABI_VERSION; }
+WGB_API const char* wgb_last_error(void) { return error_buffer(); }
+
+WGB_API int wgb_device_check(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(WGB_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(WGB_ERR_DEVICE, "device %d not present (%d visible)", device, n);
+    int major = 0;
+    WGB_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(WGB_ERR_DEVICE, "device %d is sm_%d0; this library is sm_100a only", device, major);
+    return WGB_OK;
+}
+
+WGB_API int wgb_flow_from_z(const float* z, float* x, int batch, int T, float sigma, void* stream) {
+    return flow_from_z(z, x, batch, T, sigma, S(stream));
+}
+WGB_API int wgb_flow_to_z(const float* x, float* z, int batch, int T, void* stream) { return flow_to_z(x, z, batch, T, S(stream)); }
+WGB_API int wgb_flow_mix(float* x, const float* w, long long rows, int C, void* stream) { return flow_mix(x, w, rows, C, S(stream)); }
+WGB_API int wgb_wn_start(const float* x, const float* w, const float* bias, void* h, int out_bf16, long long rows, int n_ch,
+                 int n_half, void* stream) {
+    return wn_start(x, w, bias, h, out_bf16, rows, n_ch, n_half, S(stream));
+}
+
+WGB_API int wgb_tc_wn_gate(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts, int batch,
+                   int T, int dilation, void* stream) {
+    return tc_wn_gate(h, cond, w_packed, bias, acts, batch, T, dilation, S(stream));
+}
+WGB_API int wgb_tc_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch,
+                  int T, void* stream) {
+    return tc_wn_res(acts, w_res, bias, h_in, h_out, batch, T, S(stream));
+}
+WGB_API int wgb_tc_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end, const float* b_end,
+                       float* x, const float* w_mix, float* log_s, int batch, int T, int n_half, int direction,
+                       void* stream) {
+    return tc_wn_skip_end(acts_all, n_layers, w_skip, w_end, b_end, x, w_mix, log_s, batch, T, n_half, direction,
+                          S(stream));
+}
+
+WGB_API int wgb_tc_gemm(const void* a, const void* w, const float* bias, void* c, int out_bf16, int batch, int T, int N,
+                        int K, void* stream) {
+    return tc_gemm_plain(a, w, bias, c, out_bf16, batch, T, N, K, S(stream));
+}
+
+WGB_API int wgb_sgemm_f32(const float* A, const float* W, const float* bias, void* C, int out_bf16, int batch, int M, int N,
+                  int K, long long lda, long long a_batch, long long ldw, long long ldc, long long c_batch, int shift,
+                  int accumulate, void* stream) {
+    return sgemm_nt(A, W, bias, C, out_bf16, batch, M, N, K, lda, a_batch, ldw, ldc, c_batch, shift, accumulate,
+                    S(stream));
+}
+WGB_API int wgb_gate_f32(const float* u, float* acts, long long rows, int n_ch, void* stream) {
+    return gate_f32(u, acts, rows, n_ch, S(stream));
+}
+WGB_API int wgb_res_skip_f32(const float* rs, float* h, float* skip, long long rows, int n_ch, int has_res, int first,
+                     void* stream) {
+    return res_skip_f32(rs, h, skip, rows, n_ch, has_res, first, S(stream));
+}
+WGB_API int wgb_end_coupling_f32(const float* skip, const float* w_end, const float* b_end, float* x, const float* w_mix,
+                         float* log_s, int batch, int T, int n_ch, int n_half, int direction, void* stream) {
+    return end_coupling_f32(skip, w_end, b_end, x, w_mix, log_s, batch, T, n_ch, n_half, direction, S(stream));
+}
+
+WGB_API int wgb_upsample_im2col(const float* mel, void* a, int out_bf16, int batch, int n_mel, int F, int taps, int ld_tap,
+                        void* stream) {
+    return upsample_im2col(mel, a, out_bf16, batch, n_mel, F, taps, ld_tap, S(stream));
+}
+WGB_API int wgb_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+    return cast_f32_to_bf16(src, dst, n, S(stream));
+}
+
+WGB_API int wgb_stft_reflect_pad(const float* y, float* ypad, int batch, int N, int half, long long ld_pad, void* stream) {
+    return stft_reflect_pad(y, ypad, batch, N, half, ld_pad, S(stream));
+}
+WGB_API int wgb_stft_polar(const float* spec, float* mag, float* phase, float* mag_cl, int batch, int F, int cutoff, int cp,
+                   void* stream) {
+    return stft_polar(spec, mag, phase, mag_cl, batch, F, cutoff, cp, S(stream));
+}
+WGB_API int wgb_mel_log(const float* raw, float* out, int batch, int F, int n_mel, float clip, void* stream) {
+    return mel_log(raw, out, batch, F, n_mel, clip, S(stream));
+}
+WGB_API int wgb_denoise_scale(float* spec, const float* bias, float strength, long long rows, int cutoff, int cp, void* stream) {
+    return denoise_scale(spec, bias, strength, rows, cutoff, cp, S(stream));
+}
+WGB_API int wgb_stft_recombine(const float* mag, const float* phase, float* spec, int batch, int F, int cutoff, int cp,
+                       void* stream) {
+    return stft_recombine(mag, phase, spec, batch, F, cutoff, cp, S(stream));
+}
+WGB_API int wgb_istft_overlap_add(const float* frames, const double* win_sq, float* out, int batch, int F, int L, int hop,
+                          void* stream) {
+    return istft_overlap_add(frames, win_sq, out, batch, F, L, hop, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,255 @@
+// Memory-bound kernels of the flow: noise/state layout changes, WN.start 1x1 conv, invertible 1x1
+// conv (forward direction), the FP32-mode end conv + affine coupling, and the upsample im2col.
+// The flow state is one fp32 buffer x[B, T, 8] (channels-last == final audio layout, sample 8t+c);
+// flow k works on the LAST C_k = 2*n_half channels, so early outputs / noise injections
+// (reference glow.py:229-231, :284-289) never move data.
+#include "common.cuh"
+
+#include <cuda_bf16.h>
+
+namespace wgb {
+
+static inline int grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    const long long cap = 148LL * 32;
+    return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------ layout
+// x[b,t,c] = sigma * z[b,c,t]    (z is host-supplied noise laid out like WaveGlow.forward's output)
+__global__ void flow_from_z_kernel(const float* __restrict__ z, float* __restrict__ x, int T, long long total,
+                                   float sigma) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long bt = i >> 3;
+        const int c = static_cast<int>(i & 7);
+        const long long b = bt / T, t = bt - b * T;
+        x[i] = sigma * z[(b * 8 + c) * T + t];
+    }
+}
+// z[b,c,t] = x[b,t,c]
+__global__ void flow_to_z_kernel(const float* __restrict__ x, float* __restrict__ z, int T, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long t = i % T;
+        const long long bc = i / T;
+        const long long b = bc >> 3;
+        const int c = static_cast<int>(bc & 7);
+        z[i] = x[(b * T + t) * 8 + c];
+    }
+}
+
+int flow_from_z(const float* z, float* x, int batch, int T, float sigma, cudaStream_t stream) {
+    WGB_REQUIRE(z && x && batch > 0 && T > 0, "bad arguments");
+    const long long total = static_cast<long long>(batch) * T * 8;
+    flow_from_z_kernel<<<grid_for(total, 256), 256, 0, stream>>>(z, x, T, total, sigma);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+int flow_to_z(const float* x, float* z, int batch, int T, cudaStream_t stream) {
+    WGB_REQUIRE(z && x && batch > 0 && T > 0, "bad arguments");
+    const long long total = static_cast<long long>(batch) * T * 8;
+    flow_to_z_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, z, T, total);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// ------------------------------------------------------------------------------------ convinv (forward)
+// x[., 8-C:] <- W x[., 8-C:]   (Invertible1x1Conv.forward, glow.py:100-101); W as [8][8] row-major.
+__global__ void flow_mix_kernel(float* __restrict__ x, const float* __restrict__ w, long long rows, int C) {
+    __shared__ float sw[64];
+    if (threadIdx.x < 64) sw[threadIdx.x] = w[threadIdx.x];
+    __syncthreads();
+    const int base = 8 - C;
+    for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < rows;
+         r += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float v[8], o[8];
+        *reinterpret_cast<float4*>(&v[0]) = *reinterpret_cast<const float4*>(x + r * 8);
+        *reinterpret_cast<float4*>(&v[4]) = *reinterpret_cast<const float4*>(x + r * 8 + 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (i >= base && c >= base) acc = fmaf(sw[(i - base) * 8 + (c - base)], v[c], acc);
+            o[i] = i >= base ? acc : v[i];
+        }
+        *reinterpret_cast<float4*>(x + r * 8) = *reinterpret_cast<const float4*>(&o[0]);
+        *reinterpret_cast<float4*>(x + r * 8 + 4) = *reinterpret_cast<const float4*>(&o[4]);
+    }
+}
+
+int flow_mix(float* x, const float* w, long long rows, int C, cudaStream_t stream) {
+    WGB_REQUIRE(x && w && rows > 0 && C >= 2 && C <= 8, "bad arguments");
+    flow_mix_kernel<<<grid_for(rows, 256), 256, 0, stream>>>(x, w, rows, C);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// ------------------------------------------------------------------------------------ WN.start
+// h[r, c] = b[c] + sum_j W[c, j] * x[r, 8 - 2*n_half + j]   (glow.py:156); 8 channels per thread.
+template <typename OutT>
+__global__ void wn_start_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                OutT* __restrict__ h, long long rows, int n_ch, int n_half) {
+    const int groups = n_ch >> 3;
+    const long long total = rows * groups;
+    const int base = 8 - 2 * n_half;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / groups;
+        const int c0 = static_cast<int>(i - r * groups) << 3;
+        float a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = j < n_half ? x[r * 8 + base + j] : 0.f;
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float acc = bias[c0 + c];
+            for (int j = 0; j < n_half; ++j) acc = fmaf(w[(c0 + c) * n_half + j], a[j], acc);
+            o[c] = acc;
+        }
+        if constexpr (sizeof(OutT) == 4) {
+            float4* d = reinterpret_cast<float4*>(h + r * n_ch + c0);
+            d[0] = make_float4(o[0], o[1], o[2], o[3]);
+            d[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<uint32_t*>(&p2);
+            pk.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(h + r * n_ch + c0) = pk;
+        }
+    }
+}
+
+int wn_start(const float* x, const float* w, const float* bias, void* h, int out_bf16, long long rows, int n_ch,
+             int n_half, cudaStream_t stream) {
+    WGB_REQUIRE(x && w && bias && h && rows > 0, "bad arguments");
+    WGB_REQUIRE(n_ch % 8 == 0 && n_half >= 1 && n_half <= 4, "n_ch %% 8 == 0 and n_half in 1..4 required");
+    const long long total = rows * (n_ch / 8);
+    if (out_bf16)
+        wn_start_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(
+            x, w, bias, static_cast<__nv_bfloat16*>(h), rows, n_ch, n_half);
+    else
+        wn_start_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(x, w, bias, static_cast<float*>(h), rows, n_ch,
+                                                                        n_half);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// ------------------------------------------------------------------------------------ FP32 end + coupling
+// One warp per row: out = W_end * skip + b_end (glow.py:175), then the affine coupling and, for
+// infer, the inverse 1x1 conv (glow.py:277-282); forward writes log_s (glow.py:241-246).
+__global__ void end_coupling_f32_kernel(const float* __restrict__ skip, const float* __restrict__ w_end,
+                                        const float* __restrict__ b_end, float* __restrict__ x,
+                                        const float* __restrict__ w_mix, float* __restrict__ log_s, int batch, int T,
+                                        int n_ch, int n_half, int direction) {
+    const int lane = threadIdx.x & 31;
+    const long long rows = static_cast<long long>(batch) * T;
+    const long long warp_id = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long r = warp_id; r < rows; r += n_warps) {
+        float out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[j] = 0.f;
+        for (int c = lane; c < n_ch; c += 32) {
+            const float s = skip[r * n_ch + c];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) out[j] = fmaf(s, w_end[c * 8 + j], out[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) out[j] += __shfl_xor_sync(0xffffffffu, out[j], o);
+            out[j] += b_end[j];
+        }
+        if (lane == 0) {
+            const int C = 2 * n_half, base = 8 - C;
+            float xv[8], xin[8];
+            for (int i = 0; i < 8; ++i) xv[i] = x[r * 8 + i];
+            if (direction == 0) {
+                for (int j = 0; j < n_half; ++j) {
+                    xin[j] = xv[base + j];
+                    xin[n_half + j] = (xv[base + n_half + j] - out[j]) * expf(-out[n_half + j]);
+                }
+                for (int i = 0; i < C; ++i) {
+                    float acc = 0.f;
+                    for (int c = 0; c < C; ++c) acc = fmaf(w_mix[i * 8 + c], xin[c], acc);
+                    x[r * 8 + base + i] = acc;
+                }
+            } else {
+                const long long b = r / T, t = r - b * T;
+                for (int j = 0; j < n_half; ++j) {
+                    const float ls = out[n_half + j];
+                    x[r * 8 + base + n_half + j] = expf(ls) * xv[base + n_half + j] + out[j];
+                    log_s[(b * n_half + j) * T + t] = ls;
+                }
+            }
+        }
+    }
+}
+
+int end_coupling_f32(const float* skip, const float* w_end, const float* b_end, float* x, const float* w_mix,
+                     float* log_s, int batch, int T, int n_ch, int n_half, int direction, cudaStream_t stream) {
+    WGB_REQUIRE(skip && w_end && b_end && x && batch > 0 && T > 0, "bad arguments");
+    WGB_REQUIRE(n_half >= 1 && n_half <= 4, "n_half must be in 1..4");
+    WGB_REQUIRE(direction == 1 ? log_s != nullptr : w_mix != nullptr, "missing log_s / w_mix for this direction");
+    const long long rows = static_cast<long long>(batch) * T;
+    end_coupling_f32_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(skip, w_end, b_end, x, w_mix, log_s, batch, T,
+                                                                         n_ch, n_half, direction);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// ------------------------------------------------------------------------------------ upsample im2col
+// ConvTranspose1d(80,80,1024,stride 256) (glow.py:183-185) as a GEMM: row q of A holds the four
+// frames that touch output samples [256q, 256q+256):  A[b, q, j*ld_tap + c] = mel[b, c, q - j].
+template <typename OutT>
+__global__ void upsample_im2col_kernel(const float* __restrict__ mel, OutT* __restrict__ a, int n_mel, int F, int taps,
+                                       int ld_tap, long long total) {
+    const int row_len = taps * ld_tap;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long bq = i / row_len;
+        const int k = static_cast<int>(i - bq * row_len);
+        const int j = k / ld_tap, c = k - j * ld_tap;
+        const long long b = bq / F;
+        const int q = static_cast<int>(bq - b * F);
+        float v = 0.f;
+        if (c < n_mel && q - j >= 0) v = mel[(b * n_mel + c) * F + (q - j)];
+        if constexpr (sizeof(OutT) == 4) a[i] = v;
+        else a[i] = __float2bfloat16_rn(v);
+    }
+}
+
+int upsample_im2col(const float* mel, void* a, int out_bf16, int batch, int n_mel, int F, int taps, int ld_tap,
+                    cudaStream_t stream) {
+    WGB_REQUIRE(mel && a && batch > 0 && n_mel > 0 && F > 0 && taps > 0 && ld_tap >= n_mel, "bad arguments");
+    const long long total = static_cast<long long>(batch) * F * taps * ld_tap;
+    if (out_bf16)
+        upsample_im2col_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(
+            mel, static_cast<__nv_bfloat16*>(a), n_mel, F, taps, ld_tap, total);
+    else
+        upsample_im2col_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(mel, static_cast<float*>(a), n_mel, F,
+                                                                                taps, ld_tap, total);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// ------------------------------------------------------------------------------------ casts
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        dst[i] = __float2bfloat16_rn(src[i]);
+}
+int cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
+    WGB_REQUIRE(src && dst && n > 0, "bad arguments");
+    cast_bf16_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+}  // namespace wgb

@@ -1,0 +1,194 @@
+// Conv-basis STFT / mel / denoiser glue kernels (reference utils/stft.py, utils/layers.py:63-79,
+// waveglow/denoiser.py:35-40).  The two dense-basis contractions themselves run through the GEMM
+// entry points; everything here is the memory-bound work around them.
+//
+// Layouts: padded signal ypad[B, ld_pad]; spectrum spec[B, F, 2*cp] channels-last with Re in
+// [0, cutoff) and Im in [cp, cp+cutoff) (cp = cutoff rounded up to 4, pad columns are zero because
+// the packed basis rows are zero); reference-facing outputs are channels-first [B, cutoff, F].
+#include "common.cuh"
+
+namespace wgb {
+
+static inline int grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    const long long cap = 148LL * 32;
+    return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// reflect-pad L/2 samples each side (stft.py:79-83): ypad[b, i] = y[b, reflect(i - half)]
+__global__ void reflect_pad_kernel(const float* __restrict__ y, float* __restrict__ ypad, int N, int half,
+                                   long long ld_pad, long long total) {
+    const int padded = N + 2 * half;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / ld_pad;
+        const int p = static_cast<int>(i - b * ld_pad);
+        float v = 0.f;
+        if (p < padded) {
+            int s = p - half;
+            if (s < 0) s = -s;
+            if (s >= N) s = 2 * (N - 1) - s;
+            v = y[b * N + s];
+        }
+        ypad[i] = v;
+    }
+}
+
+int stft_reflect_pad(const float* y, float* ypad, int batch, int N, int half, long long ld_pad, cudaStream_t stream) {
+    WGB_REQUIRE(y && ypad && batch > 0 && N > half, "reflect padding needs N > filter_length/2 (N=%d)", N);
+    WGB_REQUIRE(ld_pad >= N + 2 * half && ld_pad % 4 == 0, "bad padded stride");
+    const long long total = static_cast<long long>(batch) * ld_pad;
+    reflect_pad_kernel<<<grid_for(total, 256), 256, 0, stream>>>(y, ypad, N, half, ld_pad, total);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// spec[B,F,2cp] -> magnitude / phase [B,cutoff,F] (stft.py:91-97) and/or channels-last mag_cl[B,F,cp]
+__global__ void stft_polar_kernel(const float* __restrict__ spec, float* __restrict__ mag, float* __restrict__ phase,
+                                  float* __restrict__ mag_cl, int F, int cutoff, int cp, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        // i enumerates (b, k, f) with f fastest so the channels-first stores coalesce
+        const int f = static_cast<int>(i % F);
+        const long long bk = i / F;
+        const int k = static_cast<int>(bk % cp);
+        const long long b = bk / cp;
+        const float* s = spec + (b * F + f) * 2 * cp;
+        const float re = s[k], im = s[cp + k];
+        const float m = sqrtf(re * re + im * im);
+        if (mag_cl) mag_cl[(b * F + f) * cp + k] = m;
+        if (k < cutoff) {
+            if (mag) mag[(b * cutoff + k) * F + f] = m;
+            if (phase) phase[(b * cutoff + k) * F + f] = atan2f(im, re);
+        }
+    }
+}
+
+int stft_polar(const float* spec, float* mag, float* phase, float* mag_cl, int batch, int F, int cutoff, int cp,
+               cudaStream_t stream) {
+    WGB_REQUIRE(spec && batch > 0 && F > 0 && cutoff > 0 && cp >= cutoff, "bad arguments");
+    const long long total = static_cast<long long>(batch) * cp * F;
+    stft_polar_kernel<<<grid_for(total, 256), 256, 0, stream>>>(spec, mag, phase, mag_cl, F, cutoff, cp, total);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// mel_out[b, m, f] = log(max(raw[b, f, m], clip))   (layers.py:77-78, audio_processing.py:70-76)
+__global__ void mel_log_kernel(const float* __restrict__ raw, float* __restrict__ out, int F, int n_mel, float clip,
+                               long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int f = static_cast<int>(i % F);
+        const long long bm = i / F;
+        const int m = static_cast<int>(bm % n_mel);
+        const long long b = bm / n_mel;
+        out[i] = logf(fmaxf(raw[(b * F + f) * n_mel + m], clip));
+    }
+}
+
+int mel_log(const float* raw, float* out, int batch, int F, int n_mel, float clip, cudaStream_t stream) {
+    WGB_REQUIRE(raw && out && batch > 0 && F > 0 && n_mel > 0, "bad arguments");
+    const long long total = static_cast<long long>(batch) * n_mel * F;
+    mel_log_kernel<<<grid_for(total, 256), 256, 0, stream>>>(raw, out, F, n_mel, clip, total);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// Spectral subtraction without trigonometry (denoiser.py:36-39 + stft.py:102-103):
+// mag' = max(mag - bias*strength, 0); Re,Im *= mag'/mag  (cos(atan2(im,re)) = re/mag; mag = 0 -> 0).
+__global__ void denoise_scale_kernel(float* __restrict__ spec, const float* __restrict__ bias, float strength,
+                                     int cutoff, int cp, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = i / cp;
+        const int k = static_cast<int>(i - row * cp);
+        if (k >= cutoff) continue;
+        float* s = spec + row * 2 * cp;
+        const float re = s[k], im = s[cp + k];
+        const float m = sqrtf(re * re + im * im);
+        const float m2 = fmaxf(m - bias[k] * strength, 0.f);
+        const float g = m > 0.f ? m2 / m : 0.f;
+        s[k] = (m > 0.f) ? re * g : m2;       // atan2(0,0) = 0 -> cos = 1, sin = 0 (m2 is 0 here anyway)
+        s[cp + k] = im * g;
+    }
+}
+
+int denoise_scale(float* spec, const float* bias, float strength, long long rows, int cutoff, int cp,
+                  cudaStream_t stream) {
+    WGB_REQUIRE(spec && bias && rows > 0 && cutoff > 0 && cp >= cutoff, "bad arguments");
+    const long long total = rows * cp;
+    denoise_scale_kernel<<<grid_for(total, 256), 256, 0, stream>>>(spec, bias, strength, cutoff, cp, total);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// (magnitude, phase) [B,cutoff,F] -> spec[B,F,2cp] = [mag cos(phase) | mag sin(phase)]  (stft.py:102-103)
+__global__ void stft_recombine_kernel(const float* __restrict__ mag, const float* __restrict__ phase,
+                                      float* __restrict__ spec, int F, int cutoff, int cp, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int f = static_cast<int>(i % F);
+        const long long bk = i / F;
+        const int k = static_cast<int>(bk % cp);
+        const long long b = bk / cp;
+        float re = 0.f, im = 0.f;
+        if (k < cutoff) {
+            const float m = mag[(b * cutoff + k) * F + f], ph = phase[(b * cutoff + k) * F + f];
+            float sn, cs;
+            sincosf(ph, &sn, &cs);
+            re = m * cs;
+            im = m * sn;
+        }
+        float* s = spec + (b * F + f) * 2 * cp;
+        s[k] = re;
+        s[cp + k] = im;
+    }
+}
+
+int stft_recombine(const float* mag, const float* phase, float* spec, int batch, int F, int cutoff, int cp,
+                   cudaStream_t stream) {
+    WGB_REQUIRE(mag && phase && spec && batch > 0 && F > 0 && cutoff > 0 && cp >= cutoff, "bad arguments");
+    const long long total = static_cast<long long>(batch) * cp * F;
+    stft_recombine_kernel<<<grid_for(total, 256), 256, 0, stream>>>(mag, phase, spec, F, cutoff, cp, total);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// Overlap-add of the per-frame inverse-basis outputs (the conv_transpose1d of stft.py:105-109),
+// window-sum normalisation where the envelope exceeds float32 tiny, x L/hop, and the L/2 trim
+// (stft.py:111-128).  The envelope is rebuilt per sample exactly like the host loop of
+// audio_processing.py:45-47 (frames ascending, float32 running sum of float64 squares).
+__global__ void istft_overlap_add_kernel(const float* __restrict__ frames, const double* __restrict__ win_sq,
+                                         float* __restrict__ out, int F, int L, int hop, int n_out, long long total) {
+    const int half = L / 2;
+    const float scale = static_cast<float>(L) / static_cast<float>(hop);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / n_out;
+        const int n = static_cast<int>(i - b * n_out) + half;     // position in the untrimmed signal
+        const int q = n / hop;
+        float acc = 0.f, env = 0.f;
+        int f_lo = (n - L + hop) / hop;                            // first frame covering n (ceil((n-L+1)/hop))
+        if (n - L + 1 <= 0) f_lo = 0;
+        const int f_hi = q < F - 1 ? q : F - 1;
+        for (int f = f_lo; f <= f_hi; ++f) {
+            const int r = n - f * hop;
+            acc += frames[(b * F + f) * L + r];
+            env = static_cast<float>(static_cast<double>(env) + win_sq[r]);
+        }
+        if (env > 1.17549435e-38f) acc /= env;
+        out[i] = acc * scale;
+    }
+}
+
+int istft_overlap_add(const float* frames, const double* win_sq, float* out, int batch, int F, int L, int hop,
+                      cudaStream_t stream) {
+    WGB_REQUIRE(frames && win_sq && out && batch > 0 && F > 1 && L > 0 && hop > 0, "bad arguments");
+    const int n_out = hop * (F - 1);
+    const long long total = static_cast<long long>(batch) * n_out;
+    istft_overlap_add_kernel<<<grid_for(total, 256), 256, 0, stream>>>(frames, win_sq, out, F, L, hop, n_out, total);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+}  // namespace wgb

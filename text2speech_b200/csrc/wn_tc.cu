@@ -1,0 +1,471 @@
+// WN-layer GEMMs on tcgen05 / TMEM, operands staged by TMA (sm_100a only).
+//
+// Activations are channels-last bf16 [B, T, C]; a tile is 128 consecutive group steps of one
+// utterance (UMMA M = 128, one TMEM lane per time step) and one pass produces 256 output columns
+// (UMMA N = 256) into one of two 256-column TMEM accumulator stages, so the epilogue of pass i
+// overlaps the MMAs of pass i+1.  K is streamed in 64-element (128 B, SWIZZLE_128B) chunks through a
+// 4-stage TMA->mbarrier->UMMA ring.  Warp roles: warp 0 = TMA producer (one elected lane),
+// warp 1 = TMEM owner + MMA issuer (one lane), warps 2..5 = epilogue (one TMEM lane quarter each).
+//
+//   MODE_GATE      in_layers[i] (k=3, dilation d) + cond_layers[i] + bias -> tanh*sigmoid -> acts
+//                  (reference glow.py:159-162).  The three taps are three TMA boxes at t0-d, t0, t0+d
+//                  (out-of-range rows zero-filled by TMA == the conv's zero padding); the cond 1x1
+//                  is 10 more K chunks into the same accumulator, so the "add" costs nothing.
+//                  Weight rows are permuted on the host so a pass holds tanh rows c..c+127 in
+//                  columns 0..127 and the matching sigmoid rows in columns 128..255.
+//   MODE_RES       res half of res_skip_layers[i]: h_out = h_in + W_res acts + b  (glow.py:164-166)
+//   MODE_SKIP_END  sum_i W_skip_i acts_i accumulated over all layers in TMEM as ONE K=8*512 GEMM
+//                  (same FLOPs as glow.py:171-174, fp32 accumulation, no HBM read-modify-write),
+//                  then end 1x1 (glow.py:175), affine coupling and invertible 1x1 conv
+//                  (glow.py:277-282 infer / :241-246 forward) in the epilogue, all fp32.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace wgb {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockN = 256;
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kStages = 4;
+constexpr int kABytes = kBlockM * kBlockK * 2;
+constexpr int kBBytes = kBlockN * kBlockK * 2;
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 192;
+constexpr int kNCh = 512;        // WN channels the tensor-core path is specialised for
+constexpr int kNCond = 640;      // n_mel_channels * n_group
+
+enum Mode { MODE_GATE = 0, MODE_RES = 1, MODE_SKIP_END = 2, MODE_PLAIN = 3 };
+
+struct TcParams {
+    int batch, T, tiles_per_b, n_tiles;
+    int n_pass, ppi, n_chunks, dilation;
+    const float* bias;            // per packed output column (GATE, RES)
+    __nv_bfloat16* acts_out;      // GATE   [B,T,512]
+    const __nv_bfloat16* h_in;    // RES    [B,T,512]
+    __nv_bfloat16* h_out;         // RES    [B,T,512]
+    const float* w_end;           // SKIP_END [512][8] fp32 (rows >= 2*n_half zero)
+    const float* b_end;           // SKIP_END [8] (skip biases already folded in)
+    float* x;                     // SKIP_END flow state [B,T,8] fp32, active channels = last 2*n_half
+    const float* w_mix;           // SKIP_END infer: W^-1 as [8][8] row-major (top-left CxC used)
+    float* log_s;                 // SKIP_END forward: [B,n_half,T]
+    void* c_out;                  // PLAIN  [B,T,N] fp32 (DIR=0) or bf16 (DIR=1); bias may be null
+    int n_total;                  // PLAIN  N (multiple of 256)
+};
+
+struct SmemLayout {
+    static constexpr int kRing = kStages * kStageBytes;
+    static constexpr int kBarOff = kRing;                    // full[4] empty[4] tfull[2] tempty[2] slot
+    static constexpr int kBarBytes = 256;
+    static constexpr int kExtraOff = kRing + kBarBytes;      // mode-specific (w_end)
+};
+
+template <int MODE, int NHALF, int DIR>
+__global__ void __launch_bounds__(kThreads, 1)
+wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+             const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SmemLayout::kBarOff);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_wend = reinterpret_cast<float*>(smem + SmemLayout::kExtraOff);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a0);
+        tma_prefetch_desc(&map_a1);
+        tma_prefetch_desc(&map_b);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    if (MODE == MODE_SKIP_END && warp >= 2) {
+        for (int i = threadIdx.x - 64; i < kNCh * 8; i += 128) s_wend[i] = p.w_end[i];
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int groups = p.n_pass / p.ppi;
+    const int n_items = p.n_tiles * groups;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int tile = item / groups;
+                const int b = tile / p.tiles_per_b;
+                const int t0 = (tile % p.tiles_per_b) * kBlockM;
+                for (int pp = 0; pp < p.ppi; ++pp) {
+                    const int pass = (item % groups) * p.ppi + pp;
+                    for (int kc = 0; kc < p.n_chunks; ++kc) {
+                        mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
+                        uint8_t* sa = smem + s * kStageBytes;
+                        uint8_t* sb = sa + kABytes;
+                        mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                        if constexpr (MODE == MODE_GATE) {
+                            if (kc < 24) {
+                                const int tap = kc >> 3;
+                                tma_load_3d(sa, &map_a0, &full_bar[s], (kc & 7) * kBlockK,
+                                            t0 + (tap - 1) * p.dilation, b);
+                            } else {
+                                tma_load_3d(sa, &map_a1, &full_bar[s], (kc - 24) * kBlockK, t0, b);
+                            }
+                        } else if constexpr (MODE == MODE_RES || MODE == MODE_PLAIN) {
+                            tma_load_3d(sa, &map_a0, &full_bar[s], kc * kBlockK, t0, b);
+                        } else {
+                            tma_load_3d(sa, &map_a0, &full_bar[s], (kc & 7) * kBlockK, t0, (kc >> 3) * p.batch + b);
+                        }
+                        tma_load_2d(sb, &map_b, &full_bar[s], kc * kBlockK, pass * kBlockN);
+                        if (++s == kStages) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM, kBlockN);
+            int s = 0;
+            uint32_t ph = 0;
+            uint32_t acc_it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                for (int pp = 0; pp < p.ppi; ++pp, ++acc_it) {
+                    const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                    mbar_wait(&tempty_bar[as], aph ^ 1, 200 + as);
+                    tc_fence_after_sync();
+                    const uint32_t d_tmem = tmem_base + as * kBlockN;
+                    for (int kc = 0; kc < p.n_chunks; ++kc) {
+                        mbar_wait(&full_bar[s], ph, 300 + s);
+                        tc_fence_after_sync();
+                        const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+                        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            umma_bf16_ss(d_tmem, umma_desc_sw128(a_addr + k * kUmmaK * 2),
+                                         umma_desc_sw128(b_addr + k * kUmmaK * 2), idesc, (kc | k) != 0);
+                        }
+                        umma_commit(&empty_bar[s]);
+                        if (++s == kStages) { s = 0; ph ^= 1; }
+                    }
+                    umma_commit(&tfull_bar[as]);
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        uint32_t acc_it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int tile = item / groups;
+            const int b = tile / p.tiles_per_b;
+            const int t = (tile % p.tiles_per_b) * kBlockM + row;
+            const bool live = t < p.T;
+            const size_t grow = static_cast<size_t>(b) * p.T + t;
+            float outv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) outv[j] = 0.f;
+
+            for (int pp = 0; pp < p.ppi; ++pp, ++acc_it) {
+                const int pass = (item % groups) * p.ppi + pp;
+                const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                mbar_wait(&tfull_bar[as], aph, 400 + as);
+                tc_fence_after_sync();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBlockN;
+
+                if constexpr (MODE == MODE_GATE) {
+                    const float* bias = p.bias + pass * kBlockN;
+                    __nv_bfloat16* dst = p.acts_out + grow * kNCh + pass * 128;
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t vt[32], vs[32];
+                        tmem_ld_32x32b_x32(taddr + ch * 32, vt);
+                        tmem_ld_32x32b_x32(taddr + 128 + ch * 32, vs);
+                        tmem_ld_wait();
+                        uint32_t packed[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int c = ch * 32 + 2 * j;
+                            const float g0 = gate_tanh_sigmoid(__uint_as_float(vt[2 * j]) + __ldg(bias + c),
+                                                               __uint_as_float(vs[2 * j]) + __ldg(bias + 128 + c));
+                            const float g1 = gate_tanh_sigmoid(__uint_as_float(vt[2 * j + 1]) + __ldg(bias + c + 1),
+                                                               __uint_as_float(vs[2 * j + 1]) + __ldg(bias + 129 + c));
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(g0, g1);
+                            packed[j] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        if (live) {
+                            uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                        }
+                    }
+                } else if constexpr (MODE == MODE_RES) {
+                    const float* bias = p.bias + pass * kBlockN;
+                    const __nv_bfloat16* src = p.h_in + grow * kNCh + pass * kBlockN;
+                    __nv_bfloat16* dst = p.h_out + grow * kNCh + pass * kBlockN;
+#pragma unroll 1
+                    for (int ch = 0; ch < 8; ++ch) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + ch * 32, v);
+                        uint4 old[4];
+                        if (live) {
+                            const uint4* s4 = reinterpret_cast<const uint4*>(src + ch * 32);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) old[j] = s4[j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) old[j] = make_uint4(0, 0, 0, 0);
+                        }
+                        tmem_ld_wait();
+                        const uint32_t* ow = reinterpret_cast<const uint32_t*>(old);
+                        uint32_t packed[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int c = ch * 32 + 2 * j;
+                            const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&ow[j]);
+                            const float r0 = __uint_as_float(v[2 * j]) + __ldg(bias + c) + __low2float(o2);
+                            const float r1 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + c + 1) + __high2float(o2);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(r0, r1);
+                            packed[j] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        if (live) {
+                            uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                        }
+                    }
+                } else if constexpr (MODE == MODE_PLAIN) {
+                    const size_t off = grow * p.n_total + pass * kBlockN;
+#pragma unroll 1
+                    for (int ch = 0; ch < 8; ++ch) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + ch * 32, v);
+                        tmem_ld_wait();
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + pass * kBlockN + ch * 32 + j) : 0.f);
+                        if (live) {
+                            if constexpr (DIR == 0) {
+                                float4* d4 = reinterpret_cast<float4*>(static_cast<float*>(p.c_out) + off + ch * 32);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) d4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                            } else {
+                                uint4* d4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.c_out) + off + ch * 32);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+                                    __nv_bfloat162 h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+                                    __nv_bfloat162 h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+                                    d4[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                       *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+                                }
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int ch = 0; ch < 8; ++ch) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + ch * 32, v);
+                        tmem_ld_wait();
+                        const float4* w4 = reinterpret_cast<const float4*>(s_wend + (pass * kBlockN + ch * 32) * 8);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float a = __uint_as_float(v[j]);
+                            const float4 w0 = w4[2 * j], w1 = w4[2 * j + 1];
+                            outv[0] = fmaf(a, w0.x, outv[0]);
+                            outv[1] = fmaf(a, w0.y, outv[1]);
+                            outv[2] = fmaf(a, w0.z, outv[2]);
+                            outv[3] = fmaf(a, w0.w, outv[3]);
+                            outv[4] = fmaf(a, w1.x, outv[4]);
+                            outv[5] = fmaf(a, w1.y, outv[5]);
+                            outv[6] = fmaf(a, w1.z, outv[6]);
+                            outv[7] = fmaf(a, w1.w, outv[7]);
+                        }
+                    }
+                }
+                // accumulator stage drained -> hand it back to the MMA warp
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            }
+
+            if constexpr (MODE == MODE_SKIP_END) if (live) {
+                constexpr int C = 2 * NHALF, BASE = 8 - C;
+                float* xr = p.x + grow * 8;
+                float xv[8];
+                *reinterpret_cast<float4*>(&xv[0]) = *reinterpret_cast<const float4*>(xr);
+                *reinterpret_cast<float4*>(&xv[4]) = *reinterpret_cast<const float4*>(xr + 4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) outv[j] += __ldg(p.b_end + j);
+                if constexpr (DIR == 0) {                        // infer (glow.py:279-282)
+                    float xin[C];
+#pragma unroll
+                    for (int j = 0; j < NHALF; ++j) {
+                        xin[j] = xv[BASE + j];
+                        xin[NHALF + j] = (xv[BASE + NHALF + j] - outv[j]) * expf(-outv[NHALF + j]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < C; ++i) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) acc = fmaf(__ldg(p.w_mix + i * 8 + c), xin[c], acc);
+                        xv[BASE + i] = acc;
+                    }
+                } else {                                         // forward (glow.py:241-246)
+#pragma unroll
+                    for (int j = 0; j < NHALF; ++j) {
+                        const float ls = outv[NHALF + j];
+                        xv[BASE + NHALF + j] = expf(ls) * xv[BASE + NHALF + j] + outv[j];
+                        p.log_s[(static_cast<size_t>(b) * NHALF + j) * p.T + t] = ls;
+                    }
+                }
+                *reinterpret_cast<float4*>(xr) = *reinterpret_cast<const float4*>(&xv[0]);
+                *reinterpret_cast<float4*>(xr + 4) = *reinterpret_cast<const float4*>(&xv[4]);
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+
+static int act_map(CUtensorMap* m, const void* base, int channels, int T, int batches) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(channels), static_cast<uint64_t>(T), static_cast<uint64_t>(batches)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(channels) * 2, static_cast<uint64_t>(channels) * 2 * T};
+    const uint32_t box[3] = {kBlockK, kBlockM, 1};
+    return make_tmap_bf16(m, base, 3, dims, strides, box);
+}
+static int weight_map(CUtensorMap* m, const void* base, int rows, int k) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(k), static_cast<uint64_t>(rows)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(k) * 2};
+    const uint32_t box[2] = {kBlockK, kBlockN};
+    return make_tmap_bf16(m, base, 2, dims, strides, box);
+}
+
+template <int MODE, int NHALF, int DIR>
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& bm, TcParams p, int extra_smem,
+                  cudaStream_t stream) {
+    const int smem = 1024 + SmemLayout::kExtraOff + extra_smem;
+    auto kern = wn_tc_kernel<MODE, NHALF, DIR>;
+    WGB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int items = p.n_tiles * (p.n_pass / p.ppi);
+    const int grid = items < sm_count() ? items : sm_count();
+    kern<<<grid, kThreads, smem, stream>>>(a0, a1, bm, p);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+static int fill_common(TcParams& p, int batch, int T) {
+    WGB_REQUIRE(batch > 0 && T > 0, "batch (%d) and T (%d) must be positive", batch, T);
+    p.batch = batch;
+    p.T = T;
+    p.tiles_per_b = ceil_div(T, kBlockM);
+    p.n_tiles = batch * p.tiles_per_b;
+    return WGB_OK;
+}
+
+int tc_wn_gate(const void* h, const void* spect, const void* w_packed, const float* bias, void* acts, int batch, int T,
+               int dilation, cudaStream_t stream) {
+    WGB_REQUIRE(h && spect && w_packed && bias && acts, "null pointer");
+    WGB_REQUIRE(dilation >= 1, "dilation must be >= 1");
+    TcParams p{};
+    if (int e = fill_common(p, batch, T)) return e;
+    p.n_pass = 4; p.ppi = 1; p.n_chunks = (3 * kNCh + kNCond) / kBlockK; p.dilation = dilation;
+    p.bias = bias;
+    p.acts_out = static_cast<__nv_bfloat16*>(acts);
+    CUtensorMap ma0, ma1, mb;
+    if (int e = act_map(&ma0, h, kNCh, T, batch)) return e;
+    if (int e = act_map(&ma1, spect, kNCond, T, batch)) return e;
+    if (int e = weight_map(&mb, w_packed, 2 * kNCh, 3 * kNCh + kNCond)) return e;
+    return launch<MODE_GATE, 0, 0>(ma0, ma1, mb, p, 0, stream);
+}
+
+int tc_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch, int T,
+              cudaStream_t stream) {
+    WGB_REQUIRE(acts && w_res && bias && h_in && h_out, "null pointer");
+    TcParams p{};
+    if (int e = fill_common(p, batch, T)) return e;
+    p.n_pass = 2; p.ppi = 1; p.n_chunks = kNCh / kBlockK;
+    p.bias = bias;
+    p.h_in = static_cast<const __nv_bfloat16*>(h_in);
+    p.h_out = static_cast<__nv_bfloat16*>(h_out);
+    CUtensorMap ma0, mb;
+    if (int e = act_map(&ma0, acts, kNCh, T, batch)) return e;
+    if (int e = weight_map(&mb, w_res, kNCh, kNCh)) return e;
+    return launch<MODE_RES, 0, 0>(ma0, ma0, mb, p, 0, stream);
+}
+
+// C[b,t,n] = sum_k A[b,t,k] W[n,k] + bias[n]; A bf16 [B,T,K] (K % 64 == 0), W bf16 [N,K] (N % 256 == 0).
+int tc_gemm_plain(const void* a, const void* w, const float* bias, void* c, int out_bf16, int batch, int T, int N, int K,
+                  cudaStream_t stream) {
+    WGB_REQUIRE(a && w && c, "null pointer");
+    WGB_REQUIRE(N > 0 && N % kBlockN == 0 && K > 0 && K % kBlockK == 0, "N must be a multiple of 256 and K of 64 (N=%d K=%d)", N, K);
+    TcParams p{};
+    if (int e = fill_common(p, batch, T)) return e;
+    p.n_pass = N / kBlockN; p.ppi = 1; p.n_chunks = K / kBlockK;
+    p.bias = bias; p.c_out = c; p.n_total = N;
+    CUtensorMap ma0, mb;
+    if (int e = act_map(&ma0, a, K, T, batch)) return e;
+    if (int e = weight_map(&mb, w, N, K)) return e;
+    return out_bf16 ? launch<MODE_PLAIN, 0, 1>(ma0, ma0, mb, p, 0, stream) : launch<MODE_PLAIN, 0, 0>(ma0, ma0, mb, p, 0, stream);
+}
+
+int tc_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end, const float* b_end,
+                   float* x, const float* w_mix, float* log_s, int batch, int T, int n_half, int direction,
+                   cudaStream_t stream) {
+    WGB_REQUIRE(acts_all && w_skip && w_end && b_end && x, "null pointer");
+    WGB_REQUIRE(n_layers == 8, "tensor-core skip GEMM is specialised for 8 layers (got %d)", n_layers);
+    WGB_REQUIRE(n_half >= 1 && n_half <= 4, "n_half must be in 1..4 (got %d)", n_half);
+    WGB_REQUIRE(direction == 0 || direction == 1, "direction must be 0 (infer) or 1 (forward)");
+    WGB_REQUIRE(direction == 1 ? log_s != nullptr : w_mix != nullptr, "missing log_s / w_mix for this direction");
+    TcParams p{};
+    if (int e = fill_common(p, batch, T)) return e;
+    p.n_pass = 2; p.ppi = 2; p.n_chunks = n_layers * kNCh / kBlockK;
+    p.w_end = w_end; p.b_end = b_end; p.x = x; p.w_mix = w_mix; p.log_s = log_s;
+    CUtensorMap ma0, mb;
+    if (int e = act_map(&ma0, acts_all, kNCh, T, batch * n_layers)) return e;
+    if (int e = weight_map(&mb, w_skip, kNCh, n_layers * kNCh)) return e;
+    const int extra = kNCh * 8 * 4;
+#define WGB_SKIP_CASE(NH)                                                                            \
+    case NH:                                                                                         \
+        return direction == 0 ? launch<MODE_SKIP_END, NH, 0>(ma0, ma0, mb, p, extra, stream)         \
+                              : launch<MODE_SKIP_END, NH, 1>(ma0, ma0, mb, p, extra, stream);
+    switch (n_half) {
+        WGB_SKIP_CASE(1)
+        WGB_SKIP_CASE(2)
+        WGB_SKIP_CASE(3)
+        WGB_SKIP_CASE(4)
+    }
+#undef WGB_SKIP_CASE
+    return fail(WGB_ERR_ARGUMENT, "unreachable");
+}
+
+}  // namespace wgb

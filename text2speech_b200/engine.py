@@ -1,0 +1,150 @@
+"""Kernel sequencing for the WaveGlow flow: which C-ABI entry point runs when, on which buffers.
+
+HBM layout (all channels-last, one allocation per call from torch's caching allocator):
+  cond      [B, T, 640]  bf16|fp32   upsampled + regrouped mel, read by all 96 layers
+  x         [B, T, 8]    fp32        flow state; flow k touches the last C_k channels; final audio layout
+  h0, h1    [B, T, 512]  bf16        residual stream ping-pong (neighbour tiles read h with a halo)
+  acts_all  [8, B, T, 512] bf16      gated activations of every layer, K operand of the skip GEMM
+No CPU path: every step is a call into libwaveglow_b200.so.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .packing import PackedWaveGlow
+
+Tensor = torch.Tensor
+
+
+def upsample_cond(pk: PackedWaveGlow, mel: Tensor) -> Tensor:
+    """mel [B, n_mel, F] fp32 -> cond [B, 32F, n_mel*n_group] (bf16 or fp32): ConvTranspose1d +
+    trim + regroup of the reference (glow.py:252-258 / :213-221) as one GEMM."""
+    b, n_mel, f = mel.shape
+    s = _lib.stream_ptr()
+    bf16 = pk.mode == "bf16"
+    k = pk.up_taps * pk.up_ld_tap
+    n_cols = pk.w_up.shape[0]
+    a = torch.empty((b, f, k), device=mel.device, dtype=torch.float32)
+    _lib.call("wgb_upsample_im2col", mel, a, 0, b, n_mel, f, pk.up_taps, pk.up_ld_tap, s)
+    cond = torch.empty((b, f, n_cols), device=mel.device, dtype=torch.bfloat16 if bf16 else torch.float32)
+    _lib.call("wgb_sgemm_f32", a, pk.w_up, pk.b_up, cond, int(bf16), 1, b * f, n_cols, k, k, 0, k, n_cols, 0, 0, 0, s)
+    t_per_frame = pk.up_stride // pk.n_group
+    return cond.view(b, f * t_per_frame, n_cols // t_per_frame)
+
+
+def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond: Tensor, bufs, direction: int, log_s: Optional[Tensor]):
+    b, t = x.shape[0], x.shape[1]
+    s = _lib.stream_ptr()
+    h0, h1, acts_all = bufs
+    _lib.call("wgb_wn_start", x, fl["w_start"], fl["b_start"], h0, 1, b * t, pk.n_ch, fl["n_half"], s)
+    cur, nxt = h0, h1
+    for i in range(pk.n_layers):
+        _lib.call("wgb_tc_wn_gate", cur, cond, fl["w_gate"][i], fl["b_gate"][i], acts_all[i], b, t, 2 ** i, s)
+        if i < pk.n_layers - 1:
+            _lib.call("wgb_tc_wn_res", acts_all[i], fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, s)
+            cur, nxt = nxt, cur
+    _lib.call("wgb_tc_wn_skip_end", acts_all, pk.n_layers, fl["w_skip"], fl["w_end_t"], fl["b_end"], x,
+              fl["w_mix_inv"] if direction == 0 else None, log_s, b, t, fl["n_half"], direction, s)
+
+
+def _wn_fp32(pk: PackedWaveGlow, fl: dict, x: Tensor, cond: Tensor, bufs, direction: int, log_s: Optional[Tensor]):
+    """Reference op order, one CUDA-core kernel per reference op (glow.py:154-175)."""
+    b, t = x.shape[0], x.shape[1]
+    s = _lib.stream_ptr()
+    h, u, acts, rs, skip = bufs
+    c, n_cond = pk.n_ch, cond.shape[2]
+    _lib.call("wgb_wn_start", x, fl["w_start"], fl["b_start"], h, 0, b * t, c, fl["n_half"], s)
+    for i in range(pk.n_layers):
+        d = 2 ** i
+        w_in = fl["w_in"][i]
+        taps = w_in.shape[0]
+        for j in range(taps):
+            shift = (j - (taps - 1) // 2) * d
+            _lib.call("wgb_sgemm_f32", h, w_in[j], fl["b_in"][i] if j == 0 else None, u, 0, b, t, 2 * c, c,
+                      c, t * c, c, 2 * c, t * 2 * c, shift, int(j > 0), s)
+        _lib.call("wgb_sgemm_f32", cond, fl["w_cond"][i], None, u, 0, b, t, 2 * c, n_cond,
+                  n_cond, t * n_cond, n_cond, 2 * c, t * 2 * c, 0, 1, s)
+        _lib.call("wgb_gate_f32", u, acts, b * t, c, s)
+        n_out = fl["w_rs"][i].shape[0]
+        _lib.call("wgb_sgemm_f32", acts, fl["w_rs"][i], fl["b_rs"][i], rs, 0, 1, b * t, n_out, c,
+                  c, 0, c, n_out, 0, 0, 0, s)
+        _lib.call("wgb_res_skip_f32", rs, h, skip, b * t, c, int(n_out == 2 * c), int(i == 0), s)
+    _lib.call("wgb_end_coupling_f32", skip, fl["w_end_t"], fl["b_end"], x,
+              fl["w_mix_inv"] if direction == 0 else None, log_s, b, t, c, fl["n_half"], direction, s)
+
+
+def _alloc(pk: PackedWaveGlow, b: int, t: int, device):
+    if pk.mode == "bf16":
+        bf = torch.bfloat16
+        return (torch.empty((b, t, pk.n_ch), device=device, dtype=bf),
+                torch.empty((b, t, pk.n_ch), device=device, dtype=bf),
+                torch.empty((pk.n_layers, b, t, pk.n_ch), device=device, dtype=bf))
+    f32 = torch.float32
+    return (torch.empty((b, t, pk.n_ch), device=device, dtype=f32),
+            torch.empty((b, t, 2 * pk.n_ch), device=device, dtype=f32),
+            torch.empty((b, t, pk.n_ch), device=device, dtype=f32),
+            torch.empty((b, t, 2 * pk.n_ch), device=device, dtype=f32),
+            torch.empty((b, t, pk.n_ch), device=device, dtype=f32))
+
+
+def run_wn(pk: PackedWaveGlow, k: int, x: Tensor, cond: Tensor, bufs, direction: int, log_s: Optional[Tensor]):
+    (_wn_bf16 if pk.mode == "bf16" else _wn_fp32)(pk, pk.flows[k], x, cond, bufs, direction, log_s)
+
+
+def infer(pk: PackedWaveGlow, mel: Tensor, z: Tensor, sigma: float) -> Tensor:
+    """WaveGlow.infer (glow.py:251-292): mel [B,80,F] fp32, z [B,8,32F] fp32 -> audio [B, 256F] fp32."""
+    b, _, f = mel.shape
+    t = f * pk.up_stride // pk.n_group
+    s = _lib.stream_ptr()
+    cond = upsample_cond(pk, mel)
+    x = torch.empty((b, t, pk.n_group), device=mel.device, dtype=torch.float32)
+    _lib.call("wgb_flow_from_z", z, x, b, t, float(sigma), s)
+    bufs = _alloc(pk, b, t, mel.device)
+    for k in reversed(range(pk.n_flows)):
+        run_wn(pk, k, x, cond, bufs, 0, None)
+    return x.view(b, t * pk.n_group)
+
+
+def forward(pk: PackedWaveGlow, mel: Tensor, audio: Tensor) -> Tuple[Tensor, List[Tensor], List[Tensor]]:
+    """WaveGlow.forward (glow.py:207-249): (mel [B,80,F], audio [B,N]) -> (z, log_s_list, log_det_W_list)."""
+    b, _, f = mel.shape
+    n = audio.shape[1]
+    up_len = (f - 1) * pk.up_stride + pk.up_stride * pk.up_taps
+    assert up_len >= n, "upsampled spectrogram shorter than audio"            # glow.py:216
+    t = n // pk.n_group
+    s = _lib.stream_ptr()
+    cond = upsample_cond(pk, mel)
+    if cond.shape[1] < t:
+        raise RuntimeError("audio longer than 256 * frames is not supported by the regrouped upsample GEMM")
+    if cond.shape[1] > t:
+        cond = cond[:, :t].contiguous()                                       # glow.py:217-218
+    x = audio[:, : t * pk.n_group].reshape(b, t, pk.n_group).float().contiguous().clone()
+    bufs = _alloc(pk, b, t, mel.device)
+    log_s_list, log_det_list = [], []
+    for k in range(pk.n_flows):
+        fl = pk.flows[k]
+        _lib.call("wgb_flow_mix", x, fl["w_mix"], b * t, 2 * fl["n_half"], s)
+        log_det_list.append(torch.tensor(b * t * fl["logdet"], device=mel.device, dtype=torch.float32))
+        log_s = torch.empty((b, fl["n_half"], t), device=mel.device, dtype=torch.float32)
+        run_wn(pk, k, x, cond, bufs, 1, log_s)
+        log_s_list.append(log_s)
+    z = torch.empty((b, pk.n_group, t), device=mel.device, dtype=torch.float32)
+    _lib.call("wgb_flow_to_z", x, z, b, t, s)
+    return z, log_s_list, log_det_list
+
+
+def wn_standalone(pk: PackedWaveGlow, k: int, audio_0: Tensor, spect: Tensor) -> Tensor:
+    """WN.forward((audio_0 [B,n_half,T], spect [B,640,T])) -> [B, 2*n_half, T] (glow.py:154-175).
+    Runs the coupling in forward direction on a zero a1, which returns (b, log_s) = WN output."""
+    b, n_half, t = audio_0.shape
+    s = _lib.stream_ptr()
+    x = torch.zeros((b, t, 8), device=audio_0.device, dtype=torch.float32)
+    x[:, :, 8 - 2 * n_half: 8 - n_half] = audio_0.permute(0, 2, 1)
+    cdt = torch.bfloat16 if pk.mode == "bf16" else torch.float32
+    cond = spect.permute(0, 2, 1).contiguous().to(cdt)
+    log_s = torch.empty((b, n_half, t), device=audio_0.device, dtype=torch.float32)
+    run_wn(pk, k, x, cond, _alloc(pk, b, t, audio_0.device), 1, log_s)
+    return torch.cat([x[:, :, 8 - n_half:].permute(0, 2, 1), log_s], dim=1)

@@ -1,0 +1,55 @@
+"""Drop-in TacotronSTFT (reference: utils/layers.py:42-79): STFT -> mel matmul -> log-clamp on the GPU.
+
+``LinearNorm`` / ``ConvNorm`` (layers.py:8-39) belong to Tacotron-2 and are out of scope.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .audio_processing import dynamic_range_compression, dynamic_range_decompression, mel_filterbank
+from .stft import STFT, _round4
+
+
+class TacotronSTFT(torch.nn.Module):
+    def __init__(self, filter_length=1024, hop_length=256, win_length=1024, n_mel_channels=80, sampling_rate=44800,
+                 mel_fmin=0.0, mel_fmax=8000.0):
+        super().__init__()
+        self.n_mel_channels = n_mel_channels
+        self.sampling_rate = sampling_rate
+        self.stft_fn = STFT(filter_length, hop_length, win_length)
+        self.register_buffer("mel_basis", mel_filterbank(sampling_rate, filter_length, n_mel_channels, mel_fmin, mel_fmax))
+        self._mel_pack = None
+
+    def spectral_normalize(self, magnitudes):
+        return dynamic_range_compression(magnitudes)
+
+    def spectral_de_normalize(self, magnitudes):
+        return dynamic_range_decompression(magnitudes)
+
+    def _mel_packed(self, device, cp):
+        key = (str(device), self.mel_basis.data_ptr(), self.mel_basis._version)
+        if self._mel_pack is None or self._mel_pack[0] != key:
+            w = torch.zeros((self.n_mel_channels, cp), dtype=torch.float32)
+            w[:, : self.mel_basis.shape[1]] = self.mel_basis.detach().float().cpu()
+            self._mel_pack = (key, w.to(device))
+        return self._mel_pack[1]
+
+    def mel_spectrogram(self, y: torch.Tensor) -> torch.Tensor:
+        """y [B, T] in [-1, 1] (CUDA) -> log-mel [B, n_mel_channels, T // hop + 1]."""
+        if not y.is_cuda:
+            raise RuntimeError("TacotronSTFT.mel_spectrogram needs a CUDA tensor on a B200; there is no CPU fallback")
+        assert torch.min(y.data) >= -1                                         # layers.py:72-73
+        assert torch.max(y.data) <= 1
+        y = y.float().contiguous()
+        spec, frames, cp = self.stft_fn._spectrum(y)
+        b = y.shape[0]
+        s = _lib.stream_ptr()
+        mag_cl = torch.empty((b, frames, cp), device=y.device, dtype=torch.float32)
+        _lib.call("wgb_stft_polar", spec, None, None, mag_cl, b, frames, self.stft_fn.cutoff, cp, s)
+        raw = torch.empty((b, frames, self.n_mel_channels), device=y.device, dtype=torch.float32)
+        _lib.call("wgb_sgemm_f32", mag_cl, self._mel_packed(y.device, cp), None, raw, 0, 1, b * frames,
+                  self.n_mel_channels, cp, cp, 0, cp, self.n_mel_channels, 0, 0, 0, s)
+        out = torch.empty((b, self.n_mel_channels, frames), device=y.device, dtype=torch.float32)
+        _lib.call("wgb_mel_log", raw, out, b, frames, self.n_mel_channels, 1e-5, s)
+        return out

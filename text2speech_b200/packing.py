@@ -1,0 +1,165 @@
+"""Host-side weight packing: reference state_dict layout -> the layouts the kernels consume.
+
+Pure tensor reshuffling (runs on CPU, unit-tested without a GPU).  Source shapes are the
+reference's: in_layers [1024,512,3], cond_layers [1024,640,1], res_skip_layers
+[1024|512,512,1], start [512,n_half,1], end [2*n_half,512,1], convinv [C,C,1], upsample [80,80,1024].
+
+BF16 tensor-core layouts
+  gate GEMM   w [1024, 2176] bf16, K index = tap*512 + c_in for the three dilated taps, then
+              1536 + c_cond for the conditioning 1x1.  Row order: pass p in 0..3 holds
+              tanh rows 128p..128p+127 followed by sigmoid rows 512+128p..512+128p+127, so one
+              256-column accumulator pass contains matching tanh/sigmoid pairs.  bias = b_in + b_cond.
+  res GEMM    w [512, 512] bf16 = rows 0..511 of res_skip_layers[i] (i < n_layers-1).
+  skip GEMM   w [512, n_layers*512] bf16 = the skip rows of every layer side by side along K
+              (rows 512..1023 for i < n_layers-1, rows 0..511 for the last layer); the skip biases are
+              folded through WN.end into b_end.
+FP32 validation layouts
+  in_layers as [3][1024][512] (tap-major), everything else as [out][in].
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+
+Tensor = torch.Tensor
+
+
+def fold_weight_norm(g: Tensor, v: Tensor) -> Tensor:
+    """w = g * v / ||v|| per output channel (torch weight_norm dim=0; reference glow.py:294-310)."""
+    norm = v.reshape(v.shape[0], -1).norm(dim=1).reshape(-1, *([1] * (v.dim() - 1)))
+    return v * (g / norm)
+
+
+def folded(state: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """fp32 ``*.weight``-only view of a reference-layout state_dict (either layout accepted)."""
+    out = {}
+    for key, val in state.items():
+        val = val.detach().float().cpu()
+        if key.endswith(".weight_g"):
+            stem = key[:-2]
+            out[stem] = fold_weight_norm(val, state[stem + "_v"].detach().float().cpu())
+        elif not key.endswith(".weight_v"):
+            out[key] = val
+    return out
+
+
+def gate_row_order(n_ch: int = 512, block: int = 128) -> Tensor:
+    """Original in/cond output-row index for each packed row of the gate GEMM."""
+    rows = []
+    for p in range(n_ch // block):
+        rows.append(torch.arange(p * block, (p + 1) * block))
+        rows.append(torch.arange(n_ch + p * block, n_ch + (p + 1) * block))
+    return torch.cat(rows)
+
+
+def pack_gate(w_in: Tensor, b_in: Tensor, w_cond: Tensor, b_cond: Tensor):
+    """-> (w [2C, taps*C + n_cond] fp32 (cast to bf16 by the caller), bias [2C] fp32)."""
+    two_c, c, taps = w_in.shape
+    order = gate_row_order(c)
+    w = torch.cat([w_in.permute(0, 2, 1).reshape(two_c, taps * c), w_cond[:, :, 0]], dim=1)
+    return w[order].contiguous(), (b_in + b_cond)[order].contiguous()
+
+
+def pack_skip(w_rs: List[Tensor], b_rs: List[Tensor], n_ch: int):
+    """-> (w_skip [C, L*C], b_skip_total [C]) from the per-layer res_skip weights."""
+    cols, bias = [], torch.zeros(n_ch, dtype=torch.float64)
+    last = len(w_rs) - 1
+    for i, (w, b) in enumerate(zip(w_rs, b_rs)):
+        lo = 0 if i == last else n_ch
+        cols.append(w[lo: lo + n_ch, :, 0])
+        bias += b[lo: lo + n_ch].double()
+    return torch.cat(cols, dim=1).contiguous(), bias
+
+
+def pack_end(w_end: Tensor, b_end: Tensor, b_skip_total: Tensor):
+    """-> (w_end_t [C, 8] fp32 zero padded, b_end_plain [8], b_end_folded [8] = b_end + W_end b_skip)."""
+    rows, n_ch = w_end.shape[0], w_end.shape[1]
+    w_t = torch.zeros(n_ch, 8, dtype=torch.float32)
+    w_t[:, :rows] = w_end[:, :, 0].t()
+    plain = torch.zeros(8, dtype=torch.float32)
+    plain[:rows] = b_end
+    fold = torch.zeros(8, dtype=torch.float64)
+    fold[:rows] = b_end.double() + w_end[:, :, 0].double() @ b_skip_total
+    return w_t.contiguous(), plain, fold.float()
+
+
+def pack_mix(w: Tensor):
+    """convinv weight [C,C,1] -> (W [8,8] fp32, W^-1 [8,8] fp32 via fp64, log|det W| python float).
+    The reference inverts in fp32 and caches (glow.py:88-95); fp64 here is strictly more accurate."""
+    c = w.shape[0]
+    w2 = w[:, :, 0].double()
+    fwd = torch.zeros(8, 8, dtype=torch.float32)
+    inv = torch.zeros(8, 8, dtype=torch.float32)
+    fwd[:c, :c] = w2.float()
+    inv[:c, :c] = torch.linalg.inv(w2).float()
+    return fwd, inv, float(torch.linalg.slogdet(w2)[1])
+
+
+def pack_upsample(w: Tensor, b: Tensor, n_group: int, ld_tap: int):
+    """ConvTranspose1d weight [c_in, c_out, K] (stride = K/4) -> GEMM weight
+    [ (K/4/n_group) * c_out * n_group, taps * ld_tap ] whose output row q, column tt*(c_out*n_group)+m*n_group+g is
+    sample 256q + 8tt + g of channel m — i.e. the regrouped cond layout of glow.py:257-258."""
+    c_in, c_out, k = w.shape
+    taps = 4
+    stride = k // taps
+    tt = stride // n_group
+    w5 = w.reshape(c_in, c_out, taps, tt, n_group)               # k = j*stride + tt*n_group + g
+    packed = torch.zeros(tt, c_out, n_group, taps, ld_tap, dtype=torch.float32)
+    packed[..., :c_in] = w5.permute(3, 1, 4, 2, 0)
+    bias_col = b.reshape(1, c_out, 1).expand(tt, c_out, n_group).reshape(-1).contiguous()
+    return packed.reshape(tt * c_out * n_group, taps * ld_tap).contiguous(), bias_col.float()
+
+
+class PackedWaveGlow:
+    """All device-side constants of one WaveGlow, for one numeric mode ('bf16' or 'fp32')."""
+
+    def __init__(self, state: Dict[str, Tensor], n_flows: int, n_layers: int, n_ch: int, n_group: int, mode: str,
+                 device: torch.device):
+        assert mode in ("bf16", "fp32")
+        st = folded(state)
+        self.mode, self.n_flows, self.n_layers, self.n_ch, self.n_group = mode, n_flows, n_layers, n_ch, n_group
+        dev = device
+        bf = torch.bfloat16
+        self.flows = []
+        for k in range(n_flows):
+            p = f"WN.{k}."
+            f: Dict[str, object] = {}
+            w_rs = [st[p + f"res_skip_layers.{i}.weight"] for i in range(n_layers)]
+            b_rs = [st[p + f"res_skip_layers.{i}.bias"] for i in range(n_layers)]
+            w_end, b_end = st[p + "end.weight"], st[p + "end.bias"]
+            f["n_half"] = w_end.shape[0] // 2
+            f["w_start"] = st[p + "start.weight"][:, :, 0].contiguous().to(dev)
+            f["b_start"] = st[p + "start.bias"].contiguous().to(dev)
+            w_skip, b_skip = pack_skip(w_rs, b_rs, n_ch)
+            w_end_t, b_plain, b_fold = pack_end(w_end, b_end, b_skip)
+            f["w_end_t"] = w_end_t.to(dev)
+            fwd, inv, logdet = pack_mix(st[f"convinv.{k}.conv.weight"])
+            f["w_mix"], f["w_mix_inv"], f["logdet"] = fwd.to(dev), inv.to(dev), logdet
+            if mode == "bf16":
+                f["b_end"] = b_fold.to(dev)
+                f["w_skip"] = w_skip.to(dev, bf)
+                f["w_gate"], f["b_gate"], f["w_res"], f["b_res"] = [], [], [], []
+                for i in range(n_layers):
+                    wg, bg = pack_gate(st[p + f"in_layers.{i}.weight"], st[p + f"in_layers.{i}.bias"],
+                                       st[p + f"cond_layers.{i}.weight"], st[p + f"cond_layers.{i}.bias"])
+                    f["w_gate"].append(wg.to(dev, bf))
+                    f["b_gate"].append(bg.to(dev))
+                    if i < n_layers - 1:
+                        f["w_res"].append(w_rs[i][:n_ch, :, 0].contiguous().to(dev, bf))
+                        f["b_res"].append(b_rs[i][:n_ch].contiguous().to(dev))
+            else:
+                f["b_end"] = b_plain.to(dev)
+                f["w_in"] = [st[p + f"in_layers.{i}.weight"].permute(2, 0, 1).contiguous().to(dev) for i in range(n_layers)]
+                f["b_in"] = [(st[p + f"in_layers.{i}.bias"] + st[p + f"cond_layers.{i}.bias"]).to(dev) for i in range(n_layers)]
+                f["w_cond"] = [st[p + f"cond_layers.{i}.weight"][:, :, 0].contiguous().to(dev) for i in range(n_layers)]
+                f["w_rs"] = [w[:, :, 0].contiguous().to(dev) for w in w_rs]
+                f["b_rs"] = [b.contiguous().to(dev) for b in b_rs]
+            self.flows.append(f)
+        up_w, up_b = st["upsample.weight"], st["upsample.bias"]
+        self.n_mel = up_w.shape[0]
+        self.up_taps = 4
+        self.up_stride = up_w.shape[2] // self.up_taps
+        self.up_ld_tap = ((self.n_mel + 3) // 4) * 4
+        w_up, b_up = pack_upsample(up_w, up_b, n_group, self.up_ld_tap)
+        self.w_up, self.b_up = w_up.to(dev), b_up.to(dev)

@@ -1,0 +1,133 @@
+"""Drop-in conv-basis STFT (reference: utils/stft.py) running on sm_100a kernels.
+
+Same constructor, buffers (``forward_basis``, ``inverse_basis`` [2*cutoff, 1, L]) and methods
+(``transform`` / ``inverse`` / ``forward``) as the reference.  Both dense-basis contractions are
+GEMMs through the C ABI (A = overlapping frames of the reflect-padded signal, row stride = hop);
+padding, magnitude/phase, recombination, overlap-add and window-sum normalisation are fused,
+coalesced CUDA kernels.  No CPU path.
+
+Conscious deviation: the reference's ``transform`` returns CPU tensors because of its own
+``.cuda()...cpu()`` round trip (stft.py:85-89); here results stay on the input's CUDA device.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .audio_processing import padded_window
+
+
+def _round4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+class STFT(torch.nn.Module):
+    def __init__(self, filter_length=800, hop_length=200, win_length=800, window="hann"):
+        super().__init__()
+        self.filter_length = filter_length
+        self.hop_length = hop_length
+        self.win_length = win_length
+        self.window = window
+        self.forward_transform = None
+        length, cutoff = filter_length, filter_length // 2 + 1
+        scale = filter_length / hop_length
+        # rows 0..cutoff-1: cos(2 pi k n / L); rows cutoff..: -sin(2 pi k n / L)   (stft.py:46-51)
+        kn = np.outer(np.arange(cutoff), np.arange(length)) * (2.0 * np.pi / length)
+        basis = np.concatenate([np.cos(kn), -np.sin(kn)], axis=0)
+        inverse = np.linalg.pinv(scale * basis).T                                  # stft.py:54-55
+        if window is not None:
+            assert filter_length >= win_length
+            win = padded_window(window, win_length, filter_length).astype(np.float32)
+        else:
+            win = np.ones(length, dtype=np.float32)
+        fwd = torch.from_numpy(basis.astype(np.float32)) * torch.from_numpy(win)
+        inv = torch.from_numpy(inverse.astype(np.float32)) * torch.from_numpy(win)
+        self.register_buffer("forward_basis", fwd[:, None, :].contiguous().float())
+        self.register_buffer("inverse_basis", inv[:, None, :].contiguous().float())
+        self._pack = None
+
+    # ------------------------------------------------------------------ packed constants
+    @property
+    def cutoff(self) -> int:
+        return self.filter_length // 2 + 1
+
+    def _packed(self, device):
+        key = (str(device), self.forward_basis.data_ptr(), self.forward_basis._version,
+               self.inverse_basis.data_ptr(), self.inverse_basis._version)
+        if self._pack is None or self._pack[0] != key:
+            cutoff, cp, length = self.cutoff, _round4(self.cutoff), self.filter_length
+            fwd = torch.zeros(2 * cp, length, dtype=torch.float32)
+            fb = self.forward_basis.detach().float().cpu()[:, 0]
+            fwd[:cutoff] = fb[:cutoff]
+            fwd[cp: cp + cutoff] = fb[cutoff:]
+            inv = torch.zeros(length, 2 * cp, dtype=torch.float32)          # W[n][k] = inverse_basis[k][n]
+            ib = self.inverse_basis.detach().float().cpu()[:, 0]
+            inv[:, :cutoff] = ib[:cutoff].t()
+            inv[:, cp: cp + cutoff] = ib[cutoff:].t()
+            if self.window is not None:
+                sq = padded_window(self.window, self.win_length, length) ** 2
+            else:
+                sq = np.zeros(length)
+            self._pack = (key, fwd.to(device), inv.to(device), torch.from_numpy(sq).double().to(device), cp)
+        return self._pack[1:]
+
+    # ------------------------------------------------------------------ device pipeline pieces
+    def _spectrum(self, y: torch.Tensor):
+        """y [B,N] fp32 cuda -> spec [B, F, 2cp] (Re | Im), F = N // hop + 1."""
+        _lib.require_b200(y.device)
+        fwd, _, _, cp = self._packed(y.device)
+        b, n = y.shape
+        length, hop = self.filter_length, self.hop_length
+        ld_pad = _round4(n + length)
+        frames = n // hop + 1
+        s = _lib.stream_ptr()
+        ypad = torch.empty((b, ld_pad), device=y.device, dtype=torch.float32)
+        _lib.call("wgb_stft_reflect_pad", y, ypad, b, n, length // 2, ld_pad, s)
+        spec = torch.empty((b, frames, 2 * cp), device=y.device, dtype=torch.float32)
+        if hop % 4 != 0 or length % 4 != 0:
+            raise RuntimeError("hop_length and filter_length must be multiples of 4")
+        _lib.call("wgb_sgemm_f32", ypad, fwd, None, spec, 0, b, frames, 2 * cp, length,
+                  hop, ld_pad, length, 2 * cp, frames * 2 * cp, 0, 0, s)
+        return spec, frames, cp
+
+    def _synthesize(self, spec: torch.Tensor, frames: int, cp: int) -> torch.Tensor:
+        """spec [B, F, 2cp] -> [B, 1, hop*(F-1)] (stft.py:105-128)."""
+        _, inv, win_sq, _ = self._packed(spec.device)
+        b = spec.shape[0]
+        length, hop = self.filter_length, self.hop_length
+        s = _lib.stream_ptr()
+        fr = torch.empty((b, frames, length), device=spec.device, dtype=torch.float32)
+        _lib.call("wgb_sgemm_f32", spec, inv, None, fr, 0, 1, b * frames, length, 2 * cp,
+                  2 * cp, 0, 2 * cp, length, 0, 0, 0, s)
+        out = torch.empty((b, 1, hop * (frames - 1)), device=spec.device, dtype=torch.float32)
+        _lib.call("wgb_istft_overlap_add", fr, win_sq, out, b, frames, length, hop, s)
+        return out
+
+    # ------------------------------------------------------------------ reference API
+    def transform(self, input_data: torch.Tensor):
+        if not input_data.is_cuda:
+            raise RuntimeError("STFT.transform needs a CUDA tensor on a B200; there is no CPU fallback")
+        self.num_samples = input_data.size(1)
+        y = input_data.float().contiguous()
+        spec, frames, cp = self._spectrum(y)
+        b = y.shape[0]
+        mag = torch.empty((b, self.cutoff, frames), device=y.device, dtype=torch.float32)
+        phase = torch.empty_like(mag)
+        _lib.call("wgb_stft_polar", spec, mag, phase, None, b, frames, self.cutoff, cp, _lib.stream_ptr())
+        return mag, phase
+
+    def inverse(self, magnitude: torch.Tensor, phase: torch.Tensor):
+        if not magnitude.is_cuda:
+            raise RuntimeError("STFT.inverse needs CUDA tensors on a B200; there is no CPU fallback")
+        _lib.require_b200(magnitude.device)
+        _, _, _, cp = self._packed(magnitude.device)
+        b, cutoff, frames = magnitude.shape
+        spec = torch.empty((b, frames, 2 * cp), device=magnitude.device, dtype=torch.float32)
+        _lib.call("wgb_stft_recombine", magnitude.float().contiguous(), phase.float().contiguous(), spec, b, frames,
+                  cutoff, cp, _lib.stream_ptr())
+        return self._synthesize(spec, frames, cp)
+
+    def forward(self, input_data):
+        self.magnitude, self.phase = self.transform(input_data)
+        return self.inverse(self.magnitude, self.phase)
