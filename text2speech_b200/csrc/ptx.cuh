@@ -48,11 +48,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 // Bounded wait: a protocol bug must trap (and surface as a CUDA error), never hang the GPU box.
+// try_wait may itself block for a system-dependent time, so the bound is wall-clock (2 s), not spins.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
-    uint32_t spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = global_timer_ns();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
+        if (global_timer_ns() - t0 > 2000000000ull) {
             printf("wgb: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
                    (int)threadIdx.x, parity);
             __trap();
