@@ -30,6 +30,8 @@ def upsample(pk: PackedWaveGlow, mel):
     a = torch.zeros(b, f, pk.up_taps, pk.up_ld_tap)
     for j in range(pk.up_taps):
         a[:, j:, j, :n_mel] = mel[:, :, : f - j].permute(0, 2, 1)
+    if pk.mode == "bf16":
+        a = a.bfloat16().float()
     out = a.reshape(b * f, -1) @ pk.w_up.float().t() + pk.b_up
     tpf = pk.up_stride // pk.n_group
     return out.reshape(b, f * tpf, -1)

@@ -27,9 +27,13 @@ def test_upsample_gemm_matches_conv_transpose(packed):
     sd = oracle.folded_state(util.state_dict("stress"))
     up = oracle.upsample_spect(sd, mel)[:, :, : 5 * 256]
     want = oracle.regroup_spect(up, 8).permute(0, 2, 1)
-    got = emulate.upsample(packed, mel)
+    pk32 = PackedWaveGlow(util.state_dict("stress"), 12, 8, 512, 8, "fp32", torch.device("cpu"))
+    got = emulate.upsample(pk32, mel)                       # fp32 layout (K = 4 x 80): exact repacking
     assert got.shape == want.shape == (2, 160, 640)
     assert util.rel_l2(got, want) < 1e-5
+    got16 = emulate.upsample(packed, mel)                   # bf16 layout (K = 4 x 128, bf16 operands)
+    assert got16.shape == want.shape
+    assert util.rel_l2(got16, want) < 5e-3
 
 
 def test_infer_emulation_fp32_matches_oracle(packed):
@@ -77,6 +81,8 @@ def test_exact_packing_with_fp32_weights():
                                                 st[p + f"cond_layers.{i}.weight"], st[p + f"cond_layers.{i}.bias"])[0]
             if i < 7:
                 fl["w_res"][i] = w_rs[i][:512, :, 0]
+    pk.w_up = packing.pack_upsample(st["upsample.weight"], st["upsample.bias"], 8, pk.up_ld_tap)[0]
+    pk.mode = "exact"                           # emulate.upsample: do not round the im2col rows
     mel, z, _ = util.golden_inputs(1, 3)
     with torch.no_grad():
         want = oracle.waveglow_infer(sd, mel, z, util.SIGMA)

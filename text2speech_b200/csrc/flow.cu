@@ -87,27 +87,43 @@ int flow_mix(float* x, const float* w, long long rows, int C, cudaStream_t strea
 }
 
 // ------------------------------------------------------------------------------------ WN.start
-// h[r, c] = b[c] + sum_j W[c, j] * x[r, 8 - 2*n_half + j]   (glow.py:156); 8 channels per thread.
+// h[r, c] = b[c] + sum_j W[c, j] * x[r, 8 - 2*n_half + j]   (glow.py:156).  HBM-bound on the 1 KB/row
+// store: each thread owns 8 fixed channels (weights + bias live in registers for the whole kernel) and
+// walks rows, so a row-lane of n_ch/8 threads writes one contiguous n_ch*sizeof(OutT) row per iteration.
 template <typename OutT>
-__global__ void wn_start_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                OutT* __restrict__ h, long long rows, int n_ch, int n_half) {
-    const int groups = n_ch >> 3;
-    const long long total = rows * groups;
+__global__ void __launch_bounds__(256) wn_start_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, OutT* __restrict__ h,
+                                                       long long rows, int n_ch, int n_half) {
+    const int groups = n_ch >> 3;                      // threads per row
+    const int lanes = blockDim.x / groups;             // rows per block iteration
+    const int g = threadIdx.x % groups, rl = threadIdx.x / groups;
+    if (rl >= lanes) return;
+    const int c0 = g << 3;
     const int base = 8 - 2 * n_half;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long r = i / groups;
-        const int c0 = static_cast<int>(i - r * groups) << 3;
+    float wr[8][4], br[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        br[c] = bias[c0 + c];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wr[c][j] = j < n_half ? w[(c0 + c) * n_half + j] : 0.f;
+    }
+    for (long long r = static_cast<long long>(blockIdx.x) * lanes + rl; r < rows;
+         r += static_cast<long long>(gridDim.x) * lanes) {
+        const float4 lo = *reinterpret_cast<const float4*>(x + r * 8);
+        const float4 hi = *reinterpret_cast<const float4*>(x + r * 8 + 4);
+        const float xv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
         float a[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) a[j] = j < n_half ? x[r * 8 + base + j] : 0.f;
+        for (int j = 0; j < 4; ++j) {
+            float v = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v = (i == base + j && j < n_half) ? xv[i] : v;
+            a[j] = v;
+        }
         float o[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float acc = bias[c0 + c];
-            for (int j = 0; j < n_half; ++j) acc = fmaf(w[(c0 + c) * n_half + j], a[j], acc);
-            o[c] = acc;
-        }
+        for (int c = 0; c < 8; ++c)
+            o[c] = fmaf(wr[c][3], a[3], fmaf(wr[c][2], a[2], fmaf(wr[c][1], a[1], fmaf(wr[c][0], a[0], br[c]))));
         if constexpr (sizeof(OutT) == 4) {
             float4* d = reinterpret_cast<float4*>(h + r * n_ch + c0);
             d[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -128,14 +144,16 @@ __global__ void wn_start_kernel(const float* __restrict__ x, const float* __rest
 int wn_start(const float* x, const float* w, const float* bias, void* h, int out_bf16, long long rows, int n_ch,
              int n_half, cudaStream_t stream) {
     WGB_REQUIRE(x && w && bias && h && rows > 0, "bad arguments");
-    WGB_REQUIRE(n_ch % 8 == 0 && n_half >= 1 && n_half <= 4, "n_ch %% 8 == 0 and n_half in 1..4 required");
-    const long long total = rows * (n_ch / 8);
+    WGB_REQUIRE(n_ch % 8 == 0 && n_ch / 8 <= 256 && n_half >= 1 && n_half <= 4,
+                "n_ch %% 8 == 0, n_ch <= 2048 and n_half in 1..4 required");
+    const int lanes = 256 / (n_ch / 8);
+    long long blocks = (rows + lanes - 1) / lanes;
+    const int grid = static_cast<int>(blocks < 148LL * 8 ? blocks : 148LL * 8);
     if (out_bf16)
-        wn_start_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(
-            x, w, bias, static_cast<__nv_bfloat16*>(h), rows, n_ch, n_half);
+        wn_start_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(h), rows, n_ch,
+                                                                 n_half);
     else
-        wn_start_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(x, w, bias, static_cast<float*>(h), rows, n_ch,
-                                                                        n_half);
+        wn_start_kernel<float><<<grid, 256, 0, stream>>>(x, w, bias, static_cast<float*>(h), rows, n_ch, n_half);
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }

@@ -218,40 +218,48 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                         }
                     }
                 } else if constexpr (MODE == MODE_RES) {
-                    const float* bias = p.bias + pass * kBlockN;
-                    const __nv_bfloat16* src = p.h_in + grow * kNCh + pass * kBlockN;
-                    __nv_bfloat16* dst = p.h_out + grow * kNCh + pass * kBlockN;
+                    // Row-per-thread TMEM fragments are transposed through a per-warp smem tile so global
+                    // traffic is one contiguous 128 B row segment per warp instruction (h_in read, h_out write).
+                    float* stg = s_wend + (warp - 2) * (32 * 66);
+                    const int warp_t0 = (tile % p.tiles_per_b) * kBlockM + q * 32;
+                    const int rows_live = min(32, p.T - warp_t0);
+                    const size_t base_el = (static_cast<size_t>(b) * p.T + warp_t0) * kNCh + pass * kBlockN + 2 * lane;
+                    const __nv_bfloat16* __restrict__ src = p.h_in + base_el;
+                    __nv_bfloat16* __restrict__ dst = p.h_out + base_el;
 #pragma unroll 1
-                    for (int ch = 0; ch < 8; ++ch) {
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(taddr + ch * 32, v);
-                        uint4 old[4];
-                        if (live) {
-                            const uint4* s4 = reinterpret_cast<const uint4*>(src + ch * 32);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) old[j] = s4[j];
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) old[j] = make_uint4(0, 0, 0, 0);
-                        }
+                    for (int step = 0; step < 4; ++step) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld_32x32b_x32(taddr + step * 64, v0);
+                        tmem_ld_32x32b_x32(taddr + step * 64 + 32, v1);
                         tmem_ld_wait();
-                        const uint32_t* ow = reinterpret_cast<const uint32_t*>(old);
-                        uint32_t packed[16];
+                        float2* srow = reinterpret_cast<float2*>(stg + lane * 66);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const int c = ch * 32 + 2 * j;
-                            const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&ow[j]);
-                            const float r0 = __uint_as_float(v[2 * j]) + __ldg(bias + c) + __low2float(o2);
-                            const float r1 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + c + 1) + __high2float(o2);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(r0, r1);
-                            packed[j] = *reinterpret_cast<uint32_t*>(&h2);
+                            srow[j] = make_float2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+                            srow[16 + j] = make_float2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
                         }
-                        if (live) {
-                            uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
+                        __syncwarp();
+                        const float2 bia = *reinterpret_cast<const float2*>(p.bias + pass * kBlockN + step * 64 + 2 * lane);
+#pragma unroll 1
+                        for (int r0 = 0; r0 < 32; r0 += 8) {
+                            uint32_t old[8];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                            for (int i = 0; i < 8; ++i)
+                                old[i] = (r0 + i < rows_live)
+                                             ? *reinterpret_cast<const uint32_t*>(src + static_cast<size_t>(r0 + i) * kNCh + step * 64)
+                                             : 0u;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float2 a = *reinterpret_cast<const float2*>(stg + (r0 + i) * 66 + 2 * lane);
+                                const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&old[i]);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(a.x + bia.x + __low2float(o2),
+                                                                          a.y + bia.y + __high2float(o2));
+                                if (r0 + i < rows_live)
+                                    *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(r0 + i) * kNCh + step * 64) =
+                                        *reinterpret_cast<uint32_t*>(&h2);
+                            }
                         }
+                        __syncwarp();
                     }
                 } else if constexpr (MODE == MODE_PLAIN) {
                     const size_t off = grow * p.n_total + pass * kBlockN;
@@ -420,7 +428,7 @@ int tc_wn_res(const void* acts, const void* w_res, const float* bias, const void
     CUtensorMap ma0, mb;
     if (int e = act_map(&ma0, acts, kNCh, T, batch)) return e;
     if (int e = weight_map(&mb, w_res, kNCh, kNCh)) return e;
-    return launch<MODE_RES, 0, 0>(ma0, ma0, mb, p, 0, stream);
+    return launch<MODE_RES, 0, 0>(ma0, ma0, mb, p, 4 * 32 * 66 * 4, stream);
 }
 
 // C[b,t,n] = sum_k A[b,t,k] W[n,k] + bias[n]; A bf16 [B,T,K] (K % 64 == 0), W bf16 [N,K] (N % 256 == 0).

@@ -27,10 +27,16 @@ def upsample_cond(pk: PackedWaveGlow, mel: Tensor) -> Tensor:
     bf16 = pk.mode == "bf16"
     k = pk.up_taps * pk.up_ld_tap
     n_cols = pk.w_up.shape[0]
-    a = torch.empty((b, f, k), device=mel.device, dtype=torch.float32)
-    _lib.call("wgb_upsample_im2col", mel, a, 0, b, n_mel, f, pk.up_taps, pk.up_ld_tap, s)
-    cond = torch.empty((b, f, n_cols), device=mel.device, dtype=torch.bfloat16 if bf16 else torch.float32)
-    _lib.call("wgb_sgemm_f32", a, pk.w_up, pk.b_up, cond, int(bf16), 1, b * f, n_cols, k, k, 0, k, n_cols, 0, 0, 0, s)
+    if bf16:            # tcgen05 GEMM: bf16 im2col rows [B, F, 4*128] x packed weight [20480, 512] -> bf16 cond
+        a = torch.empty((b, f, k), device=mel.device, dtype=torch.bfloat16)
+        _lib.call("wgb_upsample_im2col", mel, a, 1, b, n_mel, f, pk.up_taps, pk.up_ld_tap, s)
+        cond = torch.empty((b, f, n_cols), device=mel.device, dtype=torch.bfloat16)
+        _lib.call("wgb_tc_gemm", a, pk.w_up, pk.b_up, cond, 1, b, f, n_cols, k, s)
+    else:
+        a = torch.empty((b, f, k), device=mel.device, dtype=torch.float32)
+        _lib.call("wgb_upsample_im2col", mel, a, 0, b, n_mel, f, pk.up_taps, pk.up_ld_tap, s)
+        cond = torch.empty((b, f, n_cols), device=mel.device, dtype=torch.float32)
+        _lib.call("wgb_sgemm_f32", a, pk.w_up, pk.b_up, cond, 0, 1, b * f, n_cols, k, k, 0, k, n_cols, 0, 0, 0, s)
     t_per_frame = pk.up_stride // pk.n_group
     return cond.view(b, f * t_per_frame, n_cols // t_per_frame)
 

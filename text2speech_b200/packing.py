@@ -160,6 +160,9 @@ class PackedWaveGlow:
         self.n_mel = up_w.shape[0]
         self.up_taps = 4
         self.up_stride = up_w.shape[2] // self.up_taps
-        self.up_ld_tap = ((self.n_mel + 3) // 4) * 4
+        # fp32 mode: CUDA-core SGEMM, K = 4 taps x n_mel.  bf16 mode: tcgen05 GEMM, each tap padded to a
+        # multiple of 64 channels (one 128 B swizzle row per K chunk) -> K = 4 x 128 for 80 mels.
+        self.up_ld_tap = ((self.n_mel + 63) // 64) * 64 if mode == "bf16" else ((self.n_mel + 3) // 4) * 4
         w_up, b_up = pack_upsample(up_w, up_b, n_group, self.up_ld_tap)
-        self.w_up, self.b_up = w_up.to(dev), b_up.to(dev)
+        self.w_up = w_up.to(dev, bf) if mode == "bf16" else w_up.to(dev)
+        self.b_up = b_up.to(dev)
