@@ -198,9 +198,17 @@ def run_gpu_arm(args):
     raw_call = _lib.call
     profile = {"on": False}
 
+    breakdown_events = []
+
     def counted_call(name, *a):
         counter["n"] += 1
-        if profile["on"] and name == "wgb_tc_wn_gate":
+        if profile.get("all"):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            raw_call(name, *a)
+            e1.record()
+            breakdown_events.append((name, e0, e1))
+        elif profile["on"] and name == "wgb_tc_wn_gate":
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             raw_call(name, *a)
@@ -251,6 +259,18 @@ def run_gpu_arm(args):
     gate_ms = [a.elapsed_time(b) for a, b in gate_events]
     step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
+    breakdown = None
+    if args.breakdown:                       # one extra step with CUDA events around every C-ABI call
+        profile["all"] = True
+        step_resident()
+        torch.cuda.synchronize()
+        profile["all"] = False
+        agg = {}
+        for name, a, b in breakdown_events:
+            n, ms = agg.get(name, (0, 0.0))
+            agg[name] = (n + 1, ms + a.elapsed_time(b))
+        breakdown = {k: {"launches": n, "total_ms": round(ms, 3), "avg_ms": round(ms / n, 4)}
+                     for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])}
 
     ms_per_step = total_ms / args.steps
     value = samples_total / (ms_per_step * 1e-3)
@@ -287,6 +307,7 @@ def run_gpu_arm(args):
                          "launches_timed": len(gate_ms), "avg_launch_ms": gate_avg_ms,
                          "flop_per_launch": gate_flop, "traffic": None},
             "cpu_baseline": cpu,
+            "breakdown": breakdown,
             "clocks": clocks.summary(),
             "baseline_note": "vs_baseline divides by the 2750 kHz (1x V100, fp16) figure of waveglow/README.md:15-16",
         }
@@ -302,6 +323,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="add per-entry-point CUDA-event totals of one extra step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

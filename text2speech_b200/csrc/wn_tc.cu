@@ -27,7 +27,6 @@ constexpr int kBlockM = 128;
 constexpr int kBlockN = 256;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
-constexpr int kStages = 4;
 constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kBBytes = kBlockN * kBlockK * 2;
 constexpr int kStageBytes = kABytes + kBBytes;
@@ -54,25 +53,39 @@ struct TcParams {
     int n_total;                  // PLAIN  N (multiple of 256)
 };
 
+// Shared-memory carve-up (offsets from a 1024 B aligned base): [TMA ring][mode extra][barriers].
+//   RES:      3 stages + 64 KB h tile (TMA-loaded h_in, updated in place, TMA-stored as h_out)
+//   SKIP_END: 4 stages + 16 KB W_end^T
+//   others:   4 stages
+template <int MODE>
 struct SmemLayout {
+    static constexpr int kStages = MODE == MODE_RES ? 3 : 4;
     static constexpr int kRing = kStages * kStageBytes;
-    static constexpr int kBarOff = kRing;                    // full[4] empty[4] tfull[2] tempty[2] slot
-    static constexpr int kBarBytes = 256;
-    static constexpr int kExtraOff = kRing + kBarBytes;      // mode-specific (w_end)
+    static constexpr int kExtraOff = kRing;
+    static constexpr int kExtraBytes = MODE == MODE_RES ? kBlockM * kBlockN * 2 : (MODE == MODE_SKIP_END ? kNCh * 8 * 4 : 0);
+    static constexpr int kBarOff = kExtraOff + kExtraBytes;
+    static constexpr int kBarBytes = 256;     // full[4] empty[4] tfull[2] tempty[2] hfull hempty tmem_slot
+    static constexpr int kTotal = 1024 + kBarOff + kBarBytes;
 };
 
 template <int MODE, int NHALF, int DIR>
 __global__ void __launch_bounds__(kThreads, 1)
 wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-             const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+             const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_c,
+             const TcParams p) {
+    using SL = SmemLayout<MODE>;
+    constexpr int kStages = SL::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SmemLayout::kBarOff);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::kBarOff);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tfull_bar = empty_bar + kStages;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    float* s_wend = reinterpret_cast<float*>(smem + SmemLayout::kExtraOff);
+    uint64_t* hfull_bar = tempty_bar + 2;       // RES: h_in tile landed in smem
+    uint64_t* hempty_bar = hfull_bar + 1;       // RES: h tile buffer free again (TMA store has read it)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hempty_bar + 1);
+    uint8_t* s_extra = smem + SL::kExtraOff;
+    float* s_wend = reinterpret_cast<float*>(s_extra);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -81,6 +94,9 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
         tma_prefetch_desc(&map_a0);
         tma_prefetch_desc(&map_a1);
         tma_prefetch_desc(&map_b);
+        if constexpr (MODE == MODE_RES) tma_prefetch_desc(&map_c);
+        mbar_init(hfull_bar, 1);
+        mbar_init(hempty_bar, 1);
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -107,7 +123,7 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int s = 0;
-            uint32_t ph = 0;
+            uint32_t ph = 0, hph = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int tile = item / groups;
                 const int b = tile / p.tiles_per_b;
@@ -134,6 +150,17 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                         }
                         tma_load_2d(sb, &map_b, &full_bar[s], kc * kBlockK, pass * kBlockN);
                         if (++s == kStages) { s = 0; ph ^= 1; }
+                    }
+                    if constexpr (MODE == MODE_RES) {
+                        // h_in[t0:+128, pass*256:+256] -> smem as four 64-column SWIZZLE_128B boxes.  Issued AFTER
+                        // this pass's K loads: this thread is in-order, and waiting here for the previous pass's
+                        // epilogue must not hold back the operand stream that overlaps that epilogue.
+                        mbar_wait(hempty_bar, hph ^ 1, 500);
+                        mbar_arrive_expect_tx(hfull_bar, kBlockM * kBlockN * 2);
+#pragma unroll
+                        for (int j = 0; j < kBlockN / kBlockK; ++j)
+                            tma_load_3d(s_extra + j * kABytes, &map_a1, hfull_bar, pass * kBlockN + j * kBlockK, t0, b);
+                        hph ^= 1;
                     }
                 }
             }
@@ -173,6 +200,7 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;
         uint32_t acc_it = 0;
+        uint32_t hph = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int tile = item / groups;
             const int b = tile / p.tiles_per_b;
@@ -218,48 +246,38 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                         }
                     }
                 } else if constexpr (MODE == MODE_RES) {
-                    // Row-per-thread TMEM fragments are transposed through a per-warp smem tile so global
-                    // traffic is one contiguous 128 B row segment per warp instruction (h_in read, h_out write).
-                    float* stg = s_wend + (warp - 2) * (32 * 66);
-                    const int warp_t0 = (tile % p.tiles_per_b) * kBlockM + q * 32;
-                    const int rows_live = min(32, p.T - warp_t0);
-                    const size_t base_el = (static_cast<size_t>(b) * p.T + warp_t0) * kNCh + pass * kBlockN + 2 * lane;
-                    const __nv_bfloat16* __restrict__ src = p.h_in + base_el;
-                    __nv_bfloat16* __restrict__ dst = p.h_out + base_el;
+                    // h tile sits in smem in the TMA SWIZZLE_128B layout (four [128 x 64] boxes): row r of box j
+                    // is at j*16K + r*128, its 16 B chunk c at ((c ^ (r & 7)) << 4).  Each thread updates its own
+                    // row in place; the whole tile then leaves through one TMA store (coalesced, async).
+                    const float* bias = p.bias + pass * kBlockN;
+                    mbar_wait(hfull_bar, hph, 600);
+                    hph ^= 1;
 #pragma unroll 1
-                    for (int step = 0; step < 4; ++step) {
-                        uint32_t v0[32], v1[32];
-                        tmem_ld_32x32b_x32(taddr + step * 64, v0);
-                        tmem_ld_32x32b_x32(taddr + step * 64 + 32, v1);
+                    for (int ch = 0; ch < 8; ++ch) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + ch * 32, v);
+                        uint8_t* rowp = s_extra + (ch >> 1) * kABytes + row * 128;
+                        uint4 old[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            old[i] = *reinterpret_cast<const uint4*>(rowp + ((((ch & 1) * 4 + i) ^ (row & 7)) << 4));
                         tmem_ld_wait();
-                        float2* srow = reinterpret_cast<float2*>(stg + lane * 66);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            srow[j] = make_float2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
-                            srow[16 + j] = make_float2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
-                        }
-                        __syncwarp();
-                        const float2 bia = *reinterpret_cast<const float2*>(p.bias + pass * kBlockN + step * 64 + 2 * lane);
-#pragma unroll 1
-                        for (int r0 = 0; r0 < 32; r0 += 8) {
-                            uint32_t old[8];
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t* ow = reinterpret_cast<const uint32_t*>(&old[i]);
+                            uint32_t pk[4];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                old[i] = (r0 + i < rows_live)
-                                             ? *reinterpret_cast<const uint32_t*>(src + static_cast<size_t>(r0 + i) * kNCh + step * 64)
-                                             : 0u;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float2 a = *reinterpret_cast<const float2*>(stg + (r0 + i) * 66 + 2 * lane);
-                                const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&old[i]);
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(a.x + bia.x + __low2float(o2),
-                                                                          a.y + bia.y + __high2float(o2));
-                                if (r0 + i < rows_live)
-                                    *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(r0 + i) * kNCh + step * 64) =
-                                        *reinterpret_cast<uint32_t*>(&h2);
+                            for (int j = 0; j < 4; ++j) {
+                                const int c = ch * 32 + i * 8 + 2 * j;
+                                const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&ow[j]);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(
+                                    __uint_as_float(v[i * 8 + 2 * j]) + __ldg(bias + c) + __low2float(o2),
+                                    __uint_as_float(v[i * 8 + 2 * j + 1]) + __ldg(bias + c + 1) + __high2float(o2));
+                                pk[j] = *reinterpret_cast<uint32_t*>(&h2);
                             }
+                            *reinterpret_cast<uint4*>(rowp + ((((ch & 1) * 4 + i) ^ (row & 7)) << 4)) =
+                                make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
-                        __syncwarp();
                     }
                 } else if constexpr (MODE == MODE_PLAIN) {
                     const size_t off = grow * p.n_total + pass * kBlockN;
@@ -317,6 +335,19 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[as]);
+                if constexpr (MODE == MODE_RES) {
+                    fence_proxy_async_smem();                       // st.shared -> visible to the TMA store
+                    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+                    if (warp == 2 && lane == 0) {
+                        const int t0 = (tile % p.tiles_per_b) * kBlockM;
+#pragma unroll
+                        for (int j = 0; j < kBlockN / kBlockK; ++j)
+                            tma_store_3d(&map_c, s_extra + j * kABytes, pass * kBlockN + j * kBlockK, t0, b);
+                        tma_store_commit();
+                        tma_store_wait_read0();
+                        mbar_arrive(hempty_bar);
+                    }
+                }
             }
 
             if constexpr (MODE == MODE_SKIP_END) if (live) {
@@ -379,14 +410,15 @@ static int weight_map(CUtensorMap* m, const void* base, int rows, int k) {
 }
 
 template <int MODE, int NHALF, int DIR>
-static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& bm, TcParams p, int extra_smem,
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& bm, const CUtensorMap& cm, TcParams p,
                   cudaStream_t stream) {
-    const int smem = 1024 + SmemLayout::kExtraOff + extra_smem;
+    constexpr int smem = SmemLayout<MODE>::kTotal;
+    static_assert(smem <= 232448, "dynamic shared memory over the 227 KB per-CTA limit");
     auto kern = wn_tc_kernel<MODE, NHALF, DIR>;
     WGB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int items = p.n_tiles * (p.n_pass / p.ppi);
     const int grid = items < sm_count() ? items : sm_count();
-    kern<<<grid, kThreads, smem, stream>>>(a0, a1, bm, p);
+    kern<<<grid, kThreads, smem, stream>>>(a0, a1, bm, cm, p);
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }
@@ -413,7 +445,7 @@ int tc_wn_gate(const void* h, const void* spect, const void* w_packed, const flo
     if (int e = act_map(&ma0, h, kNCh, T, batch)) return e;
     if (int e = act_map(&ma1, spect, kNCond, T, batch)) return e;
     if (int e = weight_map(&mb, w_packed, 2 * kNCh, 3 * kNCh + kNCond)) return e;
-    return launch<MODE_GATE, 0, 0>(ma0, ma1, mb, p, 0, stream);
+    return launch<MODE_GATE, 0, 0>(ma0, ma1, mb, ma0, p, stream);
 }
 
 int tc_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch, int T,
@@ -425,10 +457,12 @@ int tc_wn_res(const void* acts, const void* w_res, const float* bias, const void
     p.bias = bias;
     p.h_in = static_cast<const __nv_bfloat16*>(h_in);
     p.h_out = static_cast<__nv_bfloat16*>(h_out);
-    CUtensorMap ma0, mb;
+    CUtensorMap ma0, mhi, mho, mb;
     if (int e = act_map(&ma0, acts, kNCh, T, batch)) return e;
+    if (int e = act_map(&mhi, h_in, kNCh, T, batch)) return e;
+    if (int e = act_map(&mho, h_out, kNCh, T, batch)) return e;
     if (int e = weight_map(&mb, w_res, kNCh, kNCh)) return e;
-    return launch<MODE_RES, 0, 0>(ma0, ma0, mb, p, 4 * 32 * 66 * 4, stream);
+    return launch<MODE_RES, 0, 0>(ma0, mhi, mb, mho, p, stream);
 }
 
 // C[b,t,n] = sum_k A[b,t,k] W[n,k] + bias[n]; A bf16 [B,T,K] (K % 64 == 0), W bf16 [N,K] (N % 256 == 0).
@@ -443,7 +477,7 @@ int tc_gemm_plain(const void* a, const void* w, const float* bias, void* c, int 
     CUtensorMap ma0, mb;
     if (int e = act_map(&ma0, a, K, T, batch)) return e;
     if (int e = weight_map(&mb, w, N, K)) return e;
-    return out_bf16 ? launch<MODE_PLAIN, 0, 1>(ma0, ma0, mb, p, 0, stream) : launch<MODE_PLAIN, 0, 0>(ma0, ma0, mb, p, 0, stream);
+    return out_bf16 ? launch<MODE_PLAIN, 0, 1>(ma0, ma0, mb, ma0, p, stream) : launch<MODE_PLAIN, 0, 0>(ma0, ma0, mb, ma0, p, stream);
 }
 
 int tc_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end, const float* b_end,
@@ -461,11 +495,10 @@ int tc_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const
     CUtensorMap ma0, mb;
     if (int e = act_map(&ma0, acts_all, kNCh, T, batch * n_layers)) return e;
     if (int e = weight_map(&mb, w_skip, kNCh, n_layers * kNCh)) return e;
-    const int extra = kNCh * 8 * 4;
 #define WGB_SKIP_CASE(NH)                                                                            \
     case NH:                                                                                         \
-        return direction == 0 ? launch<MODE_SKIP_END, NH, 0>(ma0, ma0, mb, p, extra, stream)         \
-                              : launch<MODE_SKIP_END, NH, 1>(ma0, ma0, mb, p, extra, stream);
+        return direction == 0 ? launch<MODE_SKIP_END, NH, 0>(ma0, ma0, mb, ma0, p, stream)           \
+                              : launch<MODE_SKIP_END, NH, 1>(ma0, ma0, mb, ma0, p, stream);
     switch (n_half) {
         WGB_SKIP_CASE(1)
         WGB_SKIP_CASE(2)
