@@ -177,9 +177,9 @@ def run_gpu_arm(args):
     import text2speech_b200 as t2s
     from text2speech_b200 import _lib, synthetic as syn
 
-    assert GLOBAL_BATCH % world == 0
-    per_rank = GLOBAL_BATCH // world
-    lo = rank * per_rank
+    from text2speech_b200.sharding import shard_bounds
+    lo, hi = shard_bounds(GLOBAL_BATCH, rank, world)       # contiguous utterance shard of this rank
+    per_rank = hi - lo
     model = t2s.WaveGlow(**syn.load_config())
     model = t2s.WaveGlow.remove_weightnorm(model)
     model.load_state_dict(syn.synthetic_state_dict(syn.load_config(), seed=1234, end_std=0.01))
@@ -208,7 +208,7 @@ def run_gpu_arm(args):
             raw_call(name, *a)
             e1.record()
             breakdown_events.append((name, e0, e1))
-        elif profile["on"] and name == "wgb_tc_wn_gate":
+        elif profile["on"] and name in ("wgb_tc_wn_gate", "wgb_tc2_wn_gate"):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             raw_call(name, *a)
@@ -218,9 +218,6 @@ def run_gpu_arm(args):
             raw_call(name, *a)
 
     _lib.call = counted_call
-    from text2speech_b200 import engine, stft as _stft, layers as _layers, denoiser as _den, glow as _glow
-    for mod in (engine, _stft, _layers, _den, _glow):
-        mod._lib.call = counted_call            # same module object; keeps every call site counted
 
     def barrier():
         if world > 1:

@@ -58,6 +58,10 @@ WGB_API int wgb_wn_start(const float* x, const float* w, const float* bias, void
  * text2speech_b200/packing.py (pass p: tanh rows 128p.., then sigmoid rows 512+128p..). */
 WGB_API int wgb_tc_wn_gate(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts,
                    int batch, int T, int dilation, void* stream);
+/* Same contract as wgb_tc_wn_gate, executed by CTA pairs (tcgen05.mma.cta_group::2, UMMA M = 256): the two
+ * CTAs of a cluster share each weight tile, halving weight traffic from L2 and shared memory. */
+WGB_API int wgb_tc2_wn_gate(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts,
+                            int batch, int T, int dilation, void* stream);
 /* residual half of res_skip_layers[i] (glow.py:164-166): h_out = h_in + W_res[512][512] acts + b. */
 WGB_API int wgb_tc_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out,
                   int batch, int T, void* stream);

@@ -1,0 +1,68 @@
+"""Multi-process host logic on CPU (gloo, world_size 2): utterance sharding, ragged gather, MAX-reduced
+timings, and the reference arm of bench.py running on rank 0 only."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from text2speech_b200.sharding import gather_utterances, max_over_ranks, shard_bounds
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_shard_bounds_cover_and_order():
+    for n in (0, 1, 5, 8, 64, 67):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert shard_bounds(64, 3, 8) == (24, 32)
+    with pytest.raises(ValueError):
+        shard_bounds(4, 4, 4)
+
+
+def _worker(rank, world, port, n_items, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_bounds(n_items, rank, world)
+    # stand-in for the per-rank audio: row u of utterance u is filled with u
+    local = torch.arange(lo, hi, dtype=torch.float32)[:, None].repeat(1, 6)
+    full = gather_utterances(local, n_items, dst=0)
+    slowest = max_over_ranks(10.0 + rank)
+    if rank == 0:
+        ok = full is not None and full.shape == (n_items, 6) and torch.equal(full[:, 0], torch.arange(n_items).float())
+        with open(os.path.join(out_dir, "r0.json"), "w") as f:
+            json.dump({"ok": bool(ok), "slowest": slowest}, f)
+    else:
+        assert full is None and slowest == 10.0 + world - 1
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_items", [5, 1, 8])
+def test_gather_and_max_world2(tmp_path, n_items):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, n_items, str(tmp_path)), nprocs=2, join=True)
+    res = json.load(open(tmp_path / "r0.json"))
+    assert res["ok"] and res["slowest"] == 11.0
+
+
+def test_reference_arm_runs_on_rank0_only():
+    """bench.py --impl reference under a 2-rank launch: rank 0 prints the JSON line, rank 1 exits 0 silently."""
+    env = dict(os.environ, WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()))
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                        env=dict(env, RANK="1", LOCAL_RANK="1"), capture_output=True, text=True, timeout=120)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""

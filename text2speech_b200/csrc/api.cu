@@ -11,6 +11,8 @@ int tc_wn_res(const void*, const void*, const float*, const void*, void*, int, i
 int tc_wn_skip_end(const void*, int, const void*, const float*, const float*, float*, const float*, float*, int, int,
                    int, int, cudaStream_t);
 int tc_gemm_plain(const void*, const void*, const float*, void*, int, int, int, int, int, cudaStream_t);
+// wn_tc2.cu
+int tc2_wn_gate(const void*, const void*, const void*, const float*, void*, int, int, int, cudaStream_t);
 // ref_f32.cu
 int sgemm_nt(const float*, const float*, const float*, void*, int, int, int, int, int, long long, long long, long long,
              long long, long long, int, int, cudaStream_t);
@@ -66,6 +68,10 @@ WGB_API int wgb_wn_start(const float* x, const float* w, const float* bias, void
 WGB_API int wgb_tc_wn_gate(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts, int batch,
                    int T, int dilation, void* stream) {
     return tc_wn_gate(h, cond, w_packed, bias, acts, batch, T, dilation, S(stream));
+}
+WGB_API int wgb_tc2_wn_gate(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts, int batch,
+                            int T, int dilation, void* stream) {
+    return tc2_wn_gate(h, cond, w_packed, bias, acts, batch, T, dilation, S(stream));
 }
 WGB_API int wgb_tc_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch,
                   int T, void* stream) {

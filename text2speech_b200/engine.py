@@ -9,6 +9,7 @@ No CPU path: every step is a call into libwaveglow_b200.so.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -17,6 +18,9 @@ from . import _lib
 from .packing import PackedWaveGlow
 
 Tensor = torch.Tensor
+
+# Which gate-GEMM kernel the BF16 path uses: "pair" = CTA pairs (tcgen05 cta_group::2), "single" = one CTA per tile.
+GATE_KERNEL = os.environ.get("WGB_GATE_KERNEL", "pair")
 
 
 def upsample_cond(pk: PackedWaveGlow, mel: Tensor) -> Tensor:
@@ -45,10 +49,11 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond: Tensor, bufs, direct
     b, t = x.shape[0], x.shape[1]
     s = _lib.stream_ptr()
     h0, h1, acts_all = bufs
+    gate = "wgb_tc2_wn_gate" if GATE_KERNEL == "pair" else "wgb_tc_wn_gate"
     _lib.call("wgb_wn_start", x, fl["w_start"], fl["b_start"], h0, 1, b * t, pk.n_ch, fl["n_half"], s)
     cur, nxt = h0, h1
     for i in range(pk.n_layers):
-        _lib.call("wgb_tc_wn_gate", cur, cond, fl["w_gate"][i], fl["b_gate"][i], acts_all[i], b, t, 2 ** i, s)
+        _lib.call(gate, cur, cond, fl["w_gate"][i], fl["b_gate"][i], acts_all[i], b, t, 2 ** i, s)
         if i < pk.n_layers - 1:
             _lib.call("wgb_tc_wn_res", acts_all[i], fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, s)
             cur, nxt = nxt, cur
