@@ -81,6 +81,15 @@ WGB_API int wgb_tc_wn_skip_end(const void* acts_all, int n_layers, const void* w
 WGB_API int wgb_tc_gemm(const void* a, const void* w, const float* bias, void* c, int out_bf16, int batch, int T,
                         int N, int K, void* stream);
 
+/* Split-bf16 GEMM (fp32-grade accuracy on tcgen05): C[b,r,n] = sum_k A[b,r,k] W[n,k] with A = a_hi + a_lo
+ * (bf16 parts, row r of batch b at element offset b*batch_stride + r*row_stride, rows may OVERLAP:
+ * row_stride = hop < K reads STFT frames straight from the padded signal) and w3 = [W_hi | W_hi | W_lo]
+ * bf16 [N][3K]; fp32 C [B,rows,N].  The dense-basis contractions of STFT.transform / STFT.inverse
+ * (stft.py:85-89, :105-109).  N % 256 == 0, K % 64 == 0, strides % 8 == 0. */
+WGB_API int wgb_tc_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, const float* bias, void* c,
+                               int batch, int rows, int N, int K, long long row_stride, long long batch_stride,
+                               void* stream);
+
 /* ---------------------------------------------------------------- FP32 validation path (CUDA cores) */
 
 /* C[b][m][n] (+)= sum_k A[b][m+shift][k] W[n][k] + bias[n]; rows outside [0,M) read as zero, so a
@@ -114,6 +123,11 @@ WGB_API int wgb_cast_f32_to_bf16(const float* src, void* dst, long long n, void*
 
 /* reflect pad by `half` each side into ypad[B, ld_pad] (stft.py:79-83). */
 WGB_API int wgb_stft_reflect_pad(const float* y, float* ypad, int batch, int N, int half, long long ld_pad, void* stream);
+/* reflect pad + split into bf16 hi/lo parts (operands of wgb_tc_gemm_split3); ld_pad % 8 == 0. */
+WGB_API int wgb_stft_reflect_pad_split(const float* y, void* hi, void* lo, int batch, int N, int half,
+                                       long long ld_pad, void* stream);
+/* hi = bf16(src), lo = bf16(src - hi). */
+WGB_API int wgb_split_bf16(const float* src, void* hi, void* lo, long long n, void* stream);
 /* spec[B,F,2cp] -> magnitude/phase [B,cutoff,F] (stft.py:91-97), optional channels-last mag_cl[B,F,cp];
  * any of mag / phase / mag_cl may be NULL. */
 WGB_API int wgb_stft_polar(const float* spec, float* mag, float* phase, float* mag_cl, int batch, int F, int cutoff,

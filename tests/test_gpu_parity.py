@@ -292,9 +292,30 @@ def test_no_cpu_fallback(models):
 DC = syn.DEFAULT_DATA_CONFIG
 
 
-def test_stft_transform_inverse(golden, lib):
+def test_tc_gemm_split3_overlapping_rows(lib):
+    """split-bf16 GEMM reading overlapping rows (row stride < K), as the STFT frames are read."""
+    g = torch.Generator().manual_seed(3)
+    batch, rows, K, N, hop = 2, 150, 256, 512, 64
+    ld = hop * (rows - 1) + K + 8
+    sig = torch.randn(batch, ld, generator=g)
+    w = torch.randn(N, K, generator=g) / 16
+    hi = sig.bfloat16()
+    lo = (sig - hi.float()).bfloat16()
+    w_hi = w.bfloat16()
+    w_lo = (w - w_hi.float()).bfloat16()
+    w3 = torch.cat([w_hi, w_hi, w_lo], 1).contiguous()
+    want = sig.double().unfold(1, K, hop)[:, :rows] @ w.double().t()
+    c = torch.zeros(batch, rows, N, device=DEV)
+    lib.call("wgb_tc_gemm_split3", hi.to(DEV), lo.to(DEV), w3.to(DEV), None, c, batch, rows, N, K, hop, ld, lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert util.rel_l2(c.cpu(), want) <= 2e-5
+
+
+@pytest.mark.parametrize("precision", ["tc", "fp32"])
+def test_stft_transform_inverse(golden, lib, precision):
     import text2speech_b200 as t2s
     stft = t2s.STFT(1024, 256, 1024).to(DEV)
+    stft.precision = precision
     y = syn.synthetic_waveforms(2, 4096, sr=DC["sampling_rate"], seed=5).to(DEV)
     mag, phase = stft.transform(y)
     assert mag.shape == (2, 513, 17)
@@ -316,9 +337,11 @@ def test_stft_window_shorter_than_filter(golden, lib):
     assert util.rel_l2(stft.inverse(mag, phase).cpu(), golden["small_recon"]) <= 1e-4
 
 
-def test_mel_spectrogram(golden, lib):
+@pytest.mark.parametrize("precision", ["tc", "fp32"])
+def test_mel_spectrogram(golden, lib, precision):
     import text2speech_b200 as t2s
     taco = t2s.TacotronSTFT(1024, 256, 1024, 80, DC["sampling_rate"], DC["mel_fmin"], DC["mel_fmax"]).to(DEV)
+    taco.stft_fn.precision = precision
     y = syn.synthetic_waveforms(2, 4096, sr=DC["sampling_rate"], seed=5).to(DEV)
     mel = taco.mel_spectrogram(y)
     assert mel.shape == (2, 80, 17)

@@ -11,6 +11,8 @@ int tc_wn_res(const void*, const void*, const float*, const void*, void*, int, i
 int tc_wn_skip_end(const void*, int, const void*, const float*, const float*, float*, const float*, float*, int, int,
                    int, int, cudaStream_t);
 int tc_gemm_plain(const void*, const void*, const float*, void*, int, int, int, int, int, cudaStream_t);
+int tc_gemm_split3(const void*, const void*, const void*, const float*, void*, int, int, int, int, long long, long long,
+                   cudaStream_t);
 // wn_tc2.cu
 int tc2_wn_gate(const void*, const void*, const void*, const float*, void*, int, int, int, cudaStream_t);
 // ref_f32.cu
@@ -29,6 +31,8 @@ int upsample_im2col(const float*, void*, int, int, int, int, int, int, cudaStrea
 int cast_f32_to_bf16(const float*, void*, long long, cudaStream_t);
 // stft.cu
 int stft_reflect_pad(const float*, float*, int, int, int, long long, cudaStream_t);
+int stft_reflect_pad_split(const float*, void*, void*, int, int, int, long long, cudaStream_t);
+int split_bf16(const float*, void*, void*, long long, cudaStream_t);
 int stft_polar(const float*, float*, float*, float*, int, int, int, int, cudaStream_t);
 int mel_log(const float*, float*, int, int, int, float, cudaStream_t);
 int denoise_scale(float*, const float*, float, long long, int, int, cudaStream_t);
@@ -89,6 +93,11 @@ WGB_API int wgb_tc_gemm(const void* a, const void* w, const float* bias, void* c
     return tc_gemm_plain(a, w, bias, c, out_bf16, batch, T, N, K, S(stream));
 }
 
+WGB_API int wgb_tc_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, const float* bias, void* c, int batch,
+                               int rows, int N, int K, long long row_stride, long long batch_stride, void* stream) {
+    return tc_gemm_split3(a_hi, a_lo, w3, bias, c, batch, rows, N, K, row_stride, batch_stride, S(stream));
+}
+
 WGB_API int wgb_sgemm_f32(const float* A, const float* W, const float* bias, void* C, int out_bf16, int batch, int M, int N,
                   int K, long long lda, long long a_batch, long long ldw, long long ldc, long long c_batch, int shift,
                   int accumulate, void* stream) {
@@ -117,6 +126,13 @@ WGB_API int wgb_cast_f32_to_bf16(const float* src, void* dst, long long n, void*
 
 WGB_API int wgb_stft_reflect_pad(const float* y, float* ypad, int batch, int N, int half, long long ld_pad, void* stream) {
     return stft_reflect_pad(y, ypad, batch, N, half, ld_pad, S(stream));
+}
+WGB_API int wgb_stft_reflect_pad_split(const float* y, void* hi, void* lo, int batch, int N, int half, long long ld_pad,
+                                       void* stream) {
+    return stft_reflect_pad_split(y, hi, lo, batch, N, half, ld_pad, S(stream));
+}
+WGB_API int wgb_split_bf16(const float* src, void* hi, void* lo, long long n, void* stream) {
+    return split_bf16(src, hi, lo, n, S(stream));
 }
 WGB_API int wgb_stft_polar(const float* spec, float* mag, float* phase, float* mag_cl, int batch, int F, int cutoff, int cp,
                    void* stream) {

@@ -7,6 +7,8 @@
 // the packed basis rows are zero); reference-facing outputs are channels-first [B, cutoff, F].
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+
 namespace wgb {
 
 static inline int grid_for(long long total, int block) {
@@ -39,6 +41,58 @@ int stft_reflect_pad(const float* y, float* ypad, int batch, int N, int half, lo
     WGB_REQUIRE(ld_pad >= N + 2 * half && ld_pad % 4 == 0, "bad padded stride");
     const long long total = static_cast<long long>(batch) * ld_pad;
     reflect_pad_kernel<<<grid_for(total, 256), 256, 0, stream>>>(y, ypad, N, half, ld_pad, total);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): operands of the split-bf16 tensor-core GEMMs
+__device__ __forceinline__ void split_store(float v, __nv_bfloat16* hi, __nv_bfloat16* lo, long long i) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+__global__ void reflect_pad_split_kernel(const float* __restrict__ y, __nv_bfloat16* __restrict__ hi,
+                                         __nv_bfloat16* __restrict__ lo, int N, int half, long long ld_pad,
+                                         long long total) {
+    const int padded = N + 2 * half;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / ld_pad;
+        const int p = static_cast<int>(i - b * ld_pad);
+        float v = 0.f;
+        if (p < padded) {
+            int s = p - half;
+            if (s < 0) s = -s;
+            if (s >= N) s = 2 * (N - 1) - s;
+            v = y[b * N + s];
+        }
+        split_store(v, hi, lo, i);
+    }
+}
+
+int stft_reflect_pad_split(const float* y, void* hi, void* lo, int batch, int N, int half, long long ld_pad,
+                           cudaStream_t stream) {
+    WGB_REQUIRE(y && hi && lo && batch > 0 && N > half, "reflect padding needs N > filter_length/2 (N=%d)", N);
+    WGB_REQUIRE(ld_pad >= N + 2 * half && ld_pad % 8 == 0, "bad padded stride");
+    const long long total = static_cast<long long>(batch) * ld_pad;
+    reflect_pad_split_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+        y, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), N, half, ld_pad, total);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+__global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        split_store(src[i], hi, lo, i);
+}
+
+int split_bf16(const float* src, void* hi, void* lo, long long n, cudaStream_t stream) {
+    WGB_REQUIRE(src && hi && lo && n > 0, "bad arguments");
+    split_bf16_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(hi),
+                                                          static_cast<__nv_bfloat16*>(lo), n);
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }

@@ -51,6 +51,8 @@ struct TcParams {
     float* log_s;                 // SKIP_END forward: [B,n_half,T]
     void* c_out;                  // PLAIN  [B,T,N] fp32 (DIR=0) or bf16 (DIR=1); bias may be null
     int n_total;                  // PLAIN  N (multiple of 256)
+    int seg_chunks, seg_mask;     // PLAIN  K is split in segments of seg_chunks chunks; bit s of seg_mask selects
+                                  //        map_a1 (else map_a0) for segment s (split-bf16 hi/lo operands)
 };
 
 // Shared-memory carve-up (offsets from a 1024 B aligned base): [TMA ring][mode extra][barriers].
@@ -143,8 +145,12 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                             } else {
                                 tma_load_3d(sa, &map_a1, &full_bar[s], (kc - 24) * kBlockK, t0, b);
                             }
-                        } else if constexpr (MODE == MODE_RES || MODE == MODE_PLAIN) {
+                        } else if constexpr (MODE == MODE_RES) {
                             tma_load_3d(sa, &map_a0, &full_bar[s], kc * kBlockK, t0, b);
+                        } else if constexpr (MODE == MODE_PLAIN) {
+                            const int seg = kc / p.seg_chunks;
+                            tma_load_3d(sa, ((p.seg_mask >> seg) & 1) ? &map_a1 : &map_a0, &full_bar[s],
+                                        (kc - seg * p.seg_chunks) * kBlockK, t0, b);
                         } else {
                             tma_load_3d(sa, &map_a0, &full_bar[s], (kc & 7) * kBlockK, t0, (kc >> 3) * p.batch + b);
                         }
@@ -474,10 +480,36 @@ int tc_gemm_plain(const void* a, const void* w, const float* bias, void* c, int 
     if (int e = fill_common(p, batch, T)) return e;
     p.n_pass = N / kBlockN; p.ppi = 1; p.n_chunks = K / kBlockK;
     p.bias = bias; p.c_out = c; p.n_total = N;
+    p.seg_chunks = p.n_chunks; p.seg_mask = 0;
     CUtensorMap ma0, mb;
     if (int e = act_map(&ma0, a, K, T, batch)) return e;
     if (int e = weight_map(&mb, w, N, K)) return e;
     return out_bf16 ? launch<MODE_PLAIN, 0, 1>(ma0, ma0, mb, ma0, p, stream) : launch<MODE_PLAIN, 0, 0>(ma0, ma0, mb, ma0, p, stream);
+}
+
+// Split-bf16 ("3x bf16") GEMM for fp32-grade accuracy on the tensor cores:
+//   C = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T,  A = A_hi + A_lo, W = W_hi + W_lo (each part bf16),
+// run as ONE K = 3*K GEMM: K segments [A_hi | A_lo | A_hi] against the packed weight [W_hi | W_hi | W_lo].
+// Rows of A may overlap in memory (row_stride < K): that is how STFT frames (hop < filter_length) are read
+// straight from the padded signal (reference stft.py:85-89 does the same with a strided conv).
+int tc_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, const float* bias, void* c, int batch, int rows,
+                   int N, int K, long long row_stride, long long batch_stride, cudaStream_t stream) {
+    WGB_REQUIRE(a_hi && a_lo && w3 && c, "null pointer");
+    WGB_REQUIRE(N > 0 && N % kBlockN == 0 && K > 0 && K % kBlockK == 0, "N must be a multiple of 256 and K of 64 (N=%d K=%d)", N, K);
+    WGB_REQUIRE(row_stride % 8 == 0 && batch_stride % 8 == 0, "row/batch strides must be multiples of 8 elements (16 B)");
+    TcParams p{};
+    if (int e = fill_common(p, batch, rows)) return e;
+    p.n_pass = N / kBlockN; p.ppi = 1; p.n_chunks = 3 * K / kBlockK;
+    p.bias = bias; p.c_out = c; p.n_total = N;
+    p.seg_chunks = K / kBlockK; p.seg_mask = 0b010;
+    CUtensorMap mhi, mlo, mb;
+    const uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(rows), static_cast<uint64_t>(batch)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(row_stride) * 2, static_cast<uint64_t>(batch_stride) * 2};
+    const uint32_t box[3] = {kBlockK, kBlockM, 1};
+    if (int e = make_tmap_bf16(&mhi, a_hi, 3, dims, strides, box)) return e;
+    if (int e = make_tmap_bf16(&mlo, a_lo, 3, dims, strides, box)) return e;
+    if (int e = weight_map(&mb, w3, N, 3 * K)) return e;
+    return launch<MODE_PLAIN, 0, 0>(mhi, mlo, mb, mhi, p, stream);
 }
 
 int tc_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end, const float* b_end,

@@ -28,7 +28,7 @@ class TacotronSTFT(torch.nn.Module):
         return dynamic_range_decompression(magnitudes)
 
     def _mel_packed(self, device, cp):
-        key = (str(device), self.mel_basis.data_ptr(), self.mel_basis._version)
+        key = (str(device), cp, self.mel_basis.data_ptr(), self.mel_basis._version)
         if self._mel_pack is None or self._mel_pack[0] != key:
             w = torch.zeros((self.n_mel_channels, cp), dtype=torch.float32)
             w[:, : self.mel_basis.shape[1]] = self.mel_basis.detach().float().cpu()

@@ -22,6 +22,17 @@ def _round4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def _split3(w: torch.Tensor) -> torch.Tensor:
+    """fp32 [N, K] -> bf16 [N, 3K] = [W_hi | W_hi | W_lo], the weight side of wgb_tc_gemm_split3."""
+    hi = w.bfloat16()
+    lo = (w - hi.float()).bfloat16()
+    return torch.cat([hi, hi, lo], dim=1).contiguous()
+
+
 class STFT(torch.nn.Module):
     def __init__(self, filter_length=800, hop_length=200, win_length=800, window="hann"):
         super().__init__()
@@ -46,17 +57,28 @@ class STFT(torch.nn.Module):
         self.register_buffer("forward_basis", fwd[:, None, :].contiguous().float())
         self.register_buffer("inverse_basis", inv[:, None, :].contiguous().float())
         self._pack = None
+        # 'tc': split-bf16 tcgen05 GEMMs (fp32-grade accuracy, needs filter_length % 256 == 0 and hop % 8 == 0);
+        # 'fp32': CUDA-core FP32 GEMM (any shape).  'auto' picks 'tc' when the shape allows.
+        self.precision = "auto"
 
     # ------------------------------------------------------------------ packed constants
     @property
     def cutoff(self) -> int:
         return self.filter_length // 2 + 1
 
+    def _use_tc(self) -> bool:
+        ok = self.filter_length % 256 == 0 and self.hop_length % 8 == 0
+        if self.precision == "tc" and not ok:
+            raise RuntimeError("tensor-core STFT needs filter_length % 256 == 0 and hop_length % 8 == 0")
+        return ok and self.precision in ("auto", "tc")
+
     def _packed(self, device):
-        key = (str(device), self.forward_basis.data_ptr(), self.forward_basis._version,
+        tc = self._use_tc()
+        key = (str(device), tc, self.forward_basis.data_ptr(), self.forward_basis._version,
                self.inverse_basis.data_ptr(), self.inverse_basis._version)
         if self._pack is None or self._pack[0] != key:
-            cutoff, cp, length = self.cutoff, _round4(self.cutoff), self.filter_length
+            cutoff, length = self.cutoff, self.filter_length
+            cp = _round_up(cutoff, 128) if tc else _round4(cutoff)
             fwd = torch.zeros(2 * cp, length, dtype=torch.float32)
             fb = self.forward_basis.detach().float().cpu()[:, 0]
             fwd[:cutoff] = fb[:cutoff]
@@ -65,6 +87,8 @@ class STFT(torch.nn.Module):
             ib = self.inverse_basis.detach().float().cpu()[:, 0]
             inv[:, :cutoff] = ib[:cutoff].t()
             inv[:, cp: cp + cutoff] = ib[cutoff:].t()
+            if tc:
+                fwd, inv = _split3(fwd), _split3(inv)
             if self.window is not None:
                 sq = padded_window(self.window, self.win_length, length) ** 2
             else:
@@ -79,14 +103,22 @@ class STFT(torch.nn.Module):
         fwd, _, _, cp = self._packed(y.device)
         b, n = y.shape
         length, hop = self.filter_length, self.hop_length
-        ld_pad = _round4(n + length)
         frames = n // hop + 1
         s = _lib.stream_ptr()
-        ypad = torch.empty((b, ld_pad), device=y.device, dtype=torch.float32)
-        _lib.call("wgb_stft_reflect_pad", y, ypad, b, n, length // 2, ld_pad, s)
         spec = torch.empty((b, frames, 2 * cp), device=y.device, dtype=torch.float32)
+        if self._use_tc():
+            # frames are overlapping rows (stride = hop) of the padded signal, read by TMA; operands split hi/lo
+            ld_pad = _round_up(n + length, 8)
+            hi = torch.empty((b, ld_pad), device=y.device, dtype=torch.bfloat16)
+            lo = torch.empty_like(hi)
+            _lib.call("wgb_stft_reflect_pad_split", y, hi, lo, b, n, length // 2, ld_pad, s)
+            _lib.call("wgb_tc_gemm_split3", hi, lo, fwd, None, spec, b, frames, 2 * cp, length, hop, ld_pad, s)
+            return spec, frames, cp
         if hop % 4 != 0 or length % 4 != 0:
             raise RuntimeError("hop_length and filter_length must be multiples of 4")
+        ld_pad = _round4(n + length)
+        ypad = torch.empty((b, ld_pad), device=y.device, dtype=torch.float32)
+        _lib.call("wgb_stft_reflect_pad", y, ypad, b, n, length // 2, ld_pad, s)
         _lib.call("wgb_sgemm_f32", ypad, fwd, None, spec, 0, b, frames, 2 * cp, length,
                   hop, ld_pad, length, 2 * cp, frames * 2 * cp, 0, 0, s)
         return spec, frames, cp
@@ -98,8 +130,15 @@ class STFT(torch.nn.Module):
         length, hop = self.filter_length, self.hop_length
         s = _lib.stream_ptr()
         fr = torch.empty((b, frames, length), device=spec.device, dtype=torch.float32)
-        _lib.call("wgb_sgemm_f32", spec, inv, None, fr, 0, 1, b * frames, length, 2 * cp,
-                  2 * cp, 0, 2 * cp, length, 0, 0, 0, s)
+        if self._use_tc():
+            hi = torch.empty((b * frames, 2 * cp), device=spec.device, dtype=torch.bfloat16)
+            lo = torch.empty_like(hi)
+            _lib.call("wgb_split_bf16", spec, hi, lo, spec.numel(), s)
+            _lib.call("wgb_tc_gemm_split3", hi, lo, inv, None, fr, 1, b * frames, length, 2 * cp, 2 * cp,
+                      b * frames * 2 * cp, s)
+        else:
+            _lib.call("wgb_sgemm_f32", spec, inv, None, fr, 0, 1, b * frames, length, 2 * cp,
+                      2 * cp, 0, 2 * cp, length, 0, 0, 0, s)
         out = torch.empty((b, 1, hop * (frames - 1)), device=spec.device, dtype=torch.float32)
         _lib.call("wgb_istft_overlap_add", fr, win_sq, out, b, frames, length, hop, s)
         return out
