@@ -41,6 +41,10 @@ SAMPLE_RATE = 22050
 CPU_SAMPLE_FRAMES = 100
 PUBLISHED_V100_SAMPLES_PER_SEC = 2.75e6      # BASELINE.md §1 (waveglow/README.md:15-16, 1x V100 fp16)
 GATE_FLOP_PER_STEP = 2 * (3 * 512 + 640) * 1024   # in_layers + cond_layers MACs*2 per group step per layer
+# dram__bytes_read.sum + dram__bytes_write.sum of one gate-GEMM launch at the full per-GPU batch of 64
+# (ncu --set full, profiles/r01c_ncu_full_summary.csv: 6.667 + 1.791 GB); algorithmic bytes are
+# h 1 KB + cond 1.25 KB read + acts 1 KB written per group step = 5.84 GB.  Scales with the per-rank batch.
+GATE_DRAM_BYTES_PER_LAUNCH_B64 = 8.458e9
 
 
 def workload_config(n_gpus):
@@ -302,7 +306,10 @@ def run_gpu_arm(args):
                          "frac": (achieved / sustained) if achieved else None, "frac_of_burst": (achieved / burst) if achieved else None,
                          "peak_source": peak_src + ", bf16_tflops_sustained (kernel timed inside a long step)",
                          "launches_timed": len(gate_ms), "avg_launch_ms": gate_avg_ms,
-                         "flop_per_launch": gate_flop, "traffic": None},
+                         "flop_per_launch": gate_flop,
+                         "traffic": GATE_DRAM_BYTES_PER_LAUNCH_B64 * per_rank / GLOBAL_BATCH,
+                         "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01c_ncu_full_summary.csv",
+                         "algorithmic_bytes_per_launch": 3328 * per_rank * t_steps},
             "cpu_baseline": cpu,
             "breakdown": breakdown,
             "clocks": clocks.summary(),

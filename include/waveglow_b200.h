@@ -119,6 +119,10 @@ WGB_API int wgb_upsample_im2col(const float* mel, void* a, int out_bf16, int bat
                         int ld_tap, void* stream);
 WGB_API int wgb_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 
+/* pcm[i] = (int16) trunc(audio[i] * scale), saturating: the `audio * MAX_WAV_VALUE` -> astype('int16') of the
+ * vocoder CLI (waveglow/inference.py:58-62) done before the device->host copy.  Buffers 16 B aligned. */
+WGB_API int wgb_audio_to_int16(const float* audio, void* pcm, long long n, float scale, void* stream);
+
 /* ---------------------------------------------------------------- STFT / mel / denoiser glue */
 
 /* reflect pad by `half` each side into ypad[B, ld_pad] (stft.py:79-83). */
@@ -138,6 +142,9 @@ WGB_API int wgb_mel_log(const float* raw, float* out, int batch, int F, int n_me
  * stft.py:102-103, done as a magnitude ratio). */
 WGB_API int wgb_denoise_scale(float* spec, const float* bias, float strength, long long rows, int cutoff, int cp,
                       void* stream);
+/* Griffin-Lim projection step (audio_processing.py:64-66): keep the phase of spec[B,F,2cp], impose the
+ * magnitude target[B,cutoff,F] (in place, no atan2/cos/sin: Re,Im *= target/|X|; |X| = 0 -> phase 0). */
+WGB_API int wgb_spec_set_magnitude(float* spec, const float* target, int batch, int F, int cutoff, int cp, void* stream);
 /* (magnitude, phase) [B,cutoff,F] -> spec[B,F,2cp]  (stft.py:102-103). */
 WGB_API int wgb_stft_recombine(const float* mag, const float* phase, float* spec, int batch, int F, int cutoff, int cp,
                        void* stream);

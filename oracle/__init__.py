@@ -29,5 +29,5 @@ from .waveglow_oracle import (  # noqa: F401
 )
 from .stft_oracle import (  # noqa: F401
     stft_bases, stft_transform, stft_inverse, window_sumsquare, mel_filterbank,
-    mel_spectrogram, denoiser_bias_spec, denoise,
+    mel_spectrogram, denoiser_bias_spec, denoise, griffin_lim, griffin_lim_initial_angles, pcm16,
 )

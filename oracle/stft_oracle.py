@@ -137,3 +137,32 @@ def denoise(audio: Tensor, bias_spec: Tensor, strength: float, forward_basis: Te
     mag, phase = stft_transform(audio.float(), forward_basis, hop_length)
     mag = torch.clamp(mag - bias_spec * strength, 0.0)
     return stft_inverse(mag, phase, inverse_basis, hop_length, win_length)
+
+
+# ----------------------------------------------------------------------------- callers
+
+
+def griffin_lim_initial_angles(shape, seed: int) -> Tensor:
+    """The reference's random initial phase (audio_processing.py:59-61) under ``np.random.seed(seed)``."""
+    np.random.seed(seed)
+    return torch.from_numpy(np.angle(np.exp(2j * np.pi * np.random.rand(*shape))).astype(np.float32))
+
+
+def griffin_lim(magnitudes: Tensor, angles: Tensor, forward_basis: Tensor, inverse_basis: Tensor, hop_length: int,
+                win_length: int, n_iters: int = 30) -> Tensor:
+    """Griffin-Lim (audio_processing.py:51-67): inverse with the given angles, then n_iters rounds of
+    transform -> keep the phase -> inverse with the target magnitudes.  Returns [B, hop*(F-1)]."""
+    signal = stft_inverse(magnitudes, angles, inverse_basis, hop_length, win_length).squeeze(1)
+    for _ in range(n_iters):
+        _, angles = stft_transform(signal, forward_basis, hop_length)
+        signal = stft_inverse(magnitudes, angles, inverse_basis, hop_length, win_length).squeeze(1)
+    return signal
+
+
+def pcm16(audio: Tensor, max_wav_value: float = 32768.0):
+    """The CLI's output conversion (waveglow/inference.py:58-62): (audio * MAX_WAV_VALUE) -> int16 by C
+    truncation.  Returns (int16 array, in_range mask); out-of-range products are undefined behaviour in
+    the reference (numpy astype), so parity is asserted on the in-range samples only."""
+    scaled = (audio.float() * max_wav_value).squeeze().numpy()
+    in_range = (scaled > -32768.0) & (scaled < 32768.0)
+    return np.trunc(np.clip(scaled, -32768.0, 32767.0)).astype(np.int16), in_range

@@ -37,6 +37,31 @@ def window_sumsquare(window, n_frames, hop_length=200, win_length=800, n_fft=800
     return env
 
 
+def griffin_lim(magnitudes, stft_fn, n_iters=30, angles=None):
+    """Griffin-Lim phase reconstruction (audio_processing.py:51-67) on the GPU STFT kernels.
+
+    magnitudes [B, cutoff, F] (CUDA); stft_fn: this package's STFT.  ``angles`` optionally supplies the
+    initial phase (the reference draws it with numpy: ``angle(exp(2j*pi*rand))``); None draws it the same
+    way on the host.  Each iteration is transform -> keep phase, impose magnitudes -> inverse; the
+    projection runs as one in-place kernel on the channels-last spectrum (no atan2 / cos / sin).
+    """
+    from . import _lib
+    if not magnitudes.is_cuda:
+        raise RuntimeError("griffin_lim needs CUDA tensors on a B200; there is no CPU fallback")
+    magnitudes = magnitudes.float().contiguous()
+    if angles is None:
+        angles = np.angle(np.exp(2j * np.pi * np.random.rand(*magnitudes.size()))).astype(np.float32)
+        angles = torch.from_numpy(angles)
+    angles = angles.to(magnitudes.device).float().contiguous()
+    b, cutoff, _ = magnitudes.shape
+    signal = stft_fn.inverse(magnitudes, angles).squeeze(1)
+    for _ in range(n_iters):
+        spec, frames, cp = stft_fn._spectrum(signal.contiguous())
+        _lib.call("wgb_spec_set_magnitude", spec, magnitudes, b, frames, cutoff, cp, _lib.stream_ptr())
+        signal = stft_fn._synthesize(spec, frames, cp).squeeze(1)
+    return signal
+
+
 def dynamic_range_compression(x, C=1, clip_val=1e-5):
     """log(clamp(x, clip_val) * C)  (audio_processing.py:70-76)."""
     return torch.log(torch.clamp(x, min=clip_val) * C)

@@ -29,6 +29,7 @@ int end_coupling_f32(const float*, const float*, const float*, float*, const flo
                      cudaStream_t);
 int upsample_im2col(const float*, void*, int, int, int, int, int, int, cudaStream_t);
 int cast_f32_to_bf16(const float*, void*, long long, cudaStream_t);
+int audio_to_int16(const float*, void*, long long, float, cudaStream_t);
 // stft.cu
 int stft_reflect_pad(const float*, float*, int, int, int, long long, cudaStream_t);
 int stft_reflect_pad_split(const float*, void*, void*, int, int, int, long long, cudaStream_t);
@@ -37,6 +38,7 @@ int stft_polar(const float*, float*, float*, float*, int, int, int, int, cudaStr
 int mel_log(const float*, float*, int, int, int, float, cudaStream_t);
 int denoise_scale(float*, const float*, float, long long, int, int, cudaStream_t);
 int stft_recombine(const float*, const float*, float*, int, int, int, int, cudaStream_t);
+int spec_set_magnitude(float*, const float*, int, int, int, int, cudaStream_t);
 int istft_overlap_add(const float*, const double*, float*, int, int, int, int, cudaStream_t);
 }  // namespace wgb
 
@@ -124,6 +126,10 @@ WGB_API int wgb_cast_f32_to_bf16(const float* src, void* dst, long long n, void*
     return cast_f32_to_bf16(src, dst, n, S(stream));
 }
 
+WGB_API int wgb_audio_to_int16(const float* audio, void* pcm, long long n, float scale, void* stream) {
+    return audio_to_int16(audio, pcm, n, scale, S(stream));
+}
+
 WGB_API int wgb_stft_reflect_pad(const float* y, float* ypad, int batch, int N, int half, long long ld_pad, void* stream) {
     return stft_reflect_pad(y, ypad, batch, N, half, ld_pad, S(stream));
 }
@@ -143,6 +149,9 @@ WGB_API int wgb_mel_log(const float* raw, float* out, int batch, int F, int n_me
 }
 WGB_API int wgb_denoise_scale(float* spec, const float* bias, float strength, long long rows, int cutoff, int cp, void* stream) {
     return denoise_scale(spec, bias, strength, rows, cutoff, cp, S(stream));
+}
+WGB_API int wgb_spec_set_magnitude(float* spec, const float* target, int batch, int F, int cutoff, int cp, void* stream) {
+    return spec_set_magnitude(spec, target, batch, F, cutoff, cp, S(stream));
 }
 WGB_API int wgb_stft_recombine(const float* mag, const float* phase, float* spec, int batch, int F, int cutoff, int cp,
                        void* stream) {

@@ -54,6 +54,34 @@ int flow_to_z(const float* x, float* z, int batch, int T, cudaStream_t stream) {
     return WGB_OK;
 }
 
+// ------------------------------------------------------------------------------------ PCM output
+// out[i] = (int16) trunc(x[i] * scale), saturating (waveglow/inference.py:58-62: audio * MAX_WAV_VALUE ->
+// astype('int16')).  HBM-bound: 4 B in, 2 B out per sample; 8 samples (32 B in, 16 B out) per thread step.
+__global__ void audio_to_int16_kernel(const float* __restrict__ x, short* __restrict__ out, long long n, float scale) {
+    const long long n8 = n >> 3;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 a = reinterpret_cast<const float4*>(x)[2 * i], b = reinterpret_cast<const float4*>(x)[2 * i + 1];
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        short s[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = static_cast<short>(__float2int_rz(fminf(fmaxf(v[j] * scale, -32768.f), 32767.f)));
+        reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<const uint4*>(s);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+        const long long i = (n8 << 3) + threadIdx.x;
+        out[i] = static_cast<short>(__float2int_rz(fminf(fmaxf(x[i] * scale, -32768.f), 32767.f)));
+    }
+}
+
+int audio_to_int16(const float* x, void* out, long long n, float scale, cudaStream_t stream) {
+    WGB_REQUIRE(x && out && n > 0, "bad arguments");
+    WGB_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0, "buffers must be 16 B aligned");
+    audio_to_int16_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, stream>>>(x, static_cast<short*>(out), n, scale);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
 // ------------------------------------------------------------------------------------ convinv (forward)
 // x[., 8-C:] <- W x[., 8-C:]   (Invertible1x1Conv.forward, glow.py:100-101); W as [8][8] row-major.
 __global__ void flow_mix_kernel(float* __restrict__ x, const float* __restrict__ w, long long rows, int C) {

@@ -176,6 +176,36 @@ int denoise_scale(float* spec, const float* bias, float strength, long long rows
     return WGB_OK;
 }
 
+// Griffin-Lim projection (audio_processing.py:64-66: `_, angles = transform(signal)` then
+// `inverse(magnitudes, angles)`): keep the phase of spec, impose the target magnitude, no trigonometry:
+// Re,Im *= target/|X|; |X| = 0 has phase atan2(0,0) = 0 -> (target, 0).  target is [B,cutoff,F].
+__global__ void spec_set_magnitude_kernel(float* __restrict__ spec, const float* __restrict__ target, int F, int cutoff,
+                                          int cp, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = i / cp;                    // row = b * F + f
+        const int k = static_cast<int>(i - row * cp);
+        if (k >= cutoff) continue;
+        const long long b = row / F;
+        const int f = static_cast<int>(row - b * F);
+        float* s = spec + row * 2 * cp;
+        const float re = s[k], im = s[cp + k];
+        const float m = sqrtf(re * re + im * im);
+        const float tgt = target[(b * cutoff + k) * F + f];
+        const float g = m > 0.f ? tgt / m : 0.f;
+        s[k] = m > 0.f ? re * g : tgt;
+        s[cp + k] = im * g;
+    }
+}
+
+int spec_set_magnitude(float* spec, const float* target, int batch, int F, int cutoff, int cp, cudaStream_t stream) {
+    WGB_REQUIRE(spec && target && batch > 0 && F > 0 && cutoff > 0 && cp >= cutoff, "bad arguments");
+    const long long total = static_cast<long long>(batch) * F * cp;
+    spec_set_magnitude_kernel<<<grid_for(total, 256), 256, 0, stream>>>(spec, target, F, cutoff, cp, total);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
 // (magnitude, phase) [B,cutoff,F] -> spec[B,F,2cp] = [mag cos(phase) | mag sin(phase)]  (stft.py:102-103)
 __global__ void stft_recombine_kernel(const float* __restrict__ mag, const float* __restrict__ phase,
                                       float* __restrict__ spec, int F, int cutoff, int cp, long long total) {

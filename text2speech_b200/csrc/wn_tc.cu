@@ -56,15 +56,17 @@ struct TcParams {
 };
 
 // Shared-memory carve-up (offsets from a 1024 B aligned base): [TMA ring][mode extra][barriers].
-//   RES:      3 stages + 64 KB h tile (TMA-loaded h_in, updated in place, TMA-stored as h_out)
+//   RES:      3 stages + 64 KB h tile (TMA-loaded h_in, updated in place, TMA-stored as h_out) + 2 KB bias
 //   SKIP_END: 4 stages + 16 KB W_end^T
+//   GATE:     4 stages + 4 KB bias (sigmoid half pre-halved)
 //   others:   4 stages
 template <int MODE>
 struct SmemLayout {
     static constexpr int kStages = MODE == MODE_RES ? 3 : 4;
     static constexpr int kRing = kStages * kStageBytes;
     static constexpr int kExtraOff = kRing;
-    static constexpr int kExtraBytes = MODE == MODE_RES ? kBlockM * kBlockN * 2 : (MODE == MODE_SKIP_END ? kNCh * 8 * 4 : 0);
+    static constexpr int kExtraBytes = MODE == MODE_RES ? kBlockM * kBlockN * 2 + kNCh * 4
+                                       : (MODE == MODE_SKIP_END ? kNCh * 8 * 4 : (MODE == MODE_GATE ? 2 * kNCh * 4 : 0));
     static constexpr int kBarOff = kExtraOff + kExtraBytes;
     static constexpr int kBarBytes = 256;     // full[4] empty[4] tfull[2] tempty[2] hfull hempty tmem_slot
     static constexpr int kTotal = 1024 + kBarOff + kBarBytes;
@@ -112,6 +114,13 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
     if (MODE == MODE_SKIP_END && warp >= 2) {
         for (int i = threadIdx.x - 64; i < kNCh * 8; i += 128) s_wend[i] = p.w_end[i];
+    }
+    if (MODE == MODE_RES && warp >= 2) {
+        float* sb = reinterpret_cast<float*>(s_extra + kBlockM * kBlockN * 2);
+        for (int i = threadIdx.x - 64; i < kNCh; i += 128) sb[i] = p.bias[i];
+    }
+    if (MODE == MODE_GATE && warp >= 2) {      // sigmoid(b) = 0.5 tanh(b/2) + 0.5: sigmoid columns carry b/2
+        for (int i = threadIdx.x - 64; i < 2 * kNCh; i += 128) s_wend[i] = p.bias[i] * ((i & 128) ? 0.5f : 1.f);
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -225,7 +234,8 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBlockN;
 
                 if constexpr (MODE == MODE_GATE) {
-                    const float* bias = p.bias + pass * kBlockN;
+                    const float4* bt4 = reinterpret_cast<const float4*>(s_wend + pass * kBlockN);
+                    const float4* bs4 = bt4 + 32;
                     __nv_bfloat16* dst = p.acts_out + grow * kNCh + pass * 128;
 #pragma unroll 1
                     for (int ch = 0; ch < 4; ++ch) {
@@ -235,14 +245,19 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                         tmem_ld_wait();
                         uint32_t packed[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int c = ch * 32 + 2 * j;
-                            const float g0 = gate_tanh_sigmoid(__uint_as_float(vt[2 * j]) + __ldg(bias + c),
-                                                               __uint_as_float(vs[2 * j]) + __ldg(bias + 128 + c));
-                            const float g1 = gate_tanh_sigmoid(__uint_as_float(vt[2 * j + 1]) + __ldg(bias + c + 1),
-                                                               __uint_as_float(vs[2 * j + 1]) + __ldg(bias + 129 + c));
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(g0, g1);
-                            packed[j] = *reinterpret_cast<uint32_t*>(&h2);
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bt = bt4[ch * 8 + j], bs = bs4[ch * 8 + j];     // warp-uniform: broadcast LDS.128
+                            const float g0 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j]) + bt.x,
+                                                                 fmaf(__uint_as_float(vs[4 * j]), 0.5f, bs.x));
+                            const float g1 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j + 1]) + bt.y,
+                                                                 fmaf(__uint_as_float(vs[4 * j + 1]), 0.5f, bs.y));
+                            const float g2 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j + 2]) + bt.z,
+                                                                 fmaf(__uint_as_float(vs[4 * j + 2]), 0.5f, bs.z));
+                            const float g3 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j + 3]) + bt.w,
+                                                                 fmaf(__uint_as_float(vs[4 * j + 3]), 0.5f, bs.w));
+                            __nv_bfloat162 h01 = __floats2bfloat162_rn(g0, g1), h23 = __floats2bfloat162_rn(g2, g3);
+                            packed[2 * j] = *reinterpret_cast<uint32_t*>(&h01);
+                            packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h23);
                         }
                         if (live) {
                             uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
@@ -255,7 +270,7 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                     // h tile sits in smem in the TMA SWIZZLE_128B layout (four [128 x 64] boxes): row r of box j
                     // is at j*16K + r*128, its 16 B chunk c at ((c ^ (r & 7)) << 4).  Each thread updates its own
                     // row in place; the whole tile then leaves through one TMA store (coalesced, async).
-                    const float* bias = p.bias + pass * kBlockN;
+                    const float4* bias4 = reinterpret_cast<const float4*>(s_extra + kBlockM * kBlockN * 2) + pass * (kBlockN / 4);
                     mbar_wait(hfull_bar, hph, 600);
                     hph ^= 1;
 #pragma unroll 1
@@ -271,14 +286,15 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const uint32_t* ow = reinterpret_cast<const uint32_t*>(&old[i]);
+                            const float4 b0 = bias4[ch * 8 + i * 2], b1 = bias4[ch * 8 + i * 2 + 1];   // broadcast LDS.128
+                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                             uint32_t pk[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const int c = ch * 32 + i * 8 + 2 * j;
                                 const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&ow[j]);
                                 __nv_bfloat162 h2 = __floats2bfloat162_rn(
-                                    __uint_as_float(v[i * 8 + 2 * j]) + __ldg(bias + c) + __low2float(o2),
-                                    __uint_as_float(v[i * 8 + 2 * j + 1]) + __ldg(bias + c + 1) + __high2float(o2));
+                                    __uint_as_float(v[i * 8 + 2 * j]) + bb[2 * j] + __low2float(o2),
+                                    __uint_as_float(v[i * 8 + 2 * j + 1]) + bb[2 * j + 1] + __high2float(o2));
                                 pk[j] = *reinterpret_cast<uint32_t*>(&h2);
                             }
                             *reinterpret_cast<uint4*>(rowp + ((((ch & 1) * 4 + i) ^ (row & 7)) << 4)) =

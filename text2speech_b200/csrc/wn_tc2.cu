@@ -31,7 +31,9 @@ constexpr int kTmemCols = 512;
 constexpr int kThreads = 192;
 constexpr int kNCh = 512;
 constexpr int kNCond = 640;
-constexpr int kBarOff = kStages * kStageBytes;
+constexpr int kBiasOff = kStages * kStageBytes;     // fp32 [1024]: tanh biases as is, sigmoid biases pre-halved
+constexpr int kBiasBytes = 2 * kNCh * 4;
+constexpr int kBarOff = kBiasOff + kBiasBytes;
 constexpr int kSmemTotal = 1024 + kBarOff + 256;
 
 struct Params {
@@ -131,6 +133,12 @@ gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_2sm(tmem_slot, kTmemCols);
+    float* s_bias = reinterpret_cast<float*>(smem + kBiasOff);
+    if (warp >= 2) {
+        // packed column c of pass p: tanh row for (c & 255) < 128, else the matching sigmoid row, whose
+        // pre-activation is halved (sigmoid(b) = 0.5 tanh(b/2) + 0.5)
+        for (int i = threadIdx.x - 64; i < 2 * kNCh; i += 128) s_bias[i] = p.bias[i] * ((i & 128) ? 0.5f : 1.f);
+    }
     tc_fence_before_sync();
     __syncthreads();
     cluster_sync_all();
@@ -214,7 +222,8 @@ gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
             mbar_wait(&tfull_bar[as], aph, 400 + as);
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBlockN;
-            const float* bias = p.bias + pass * kBlockN;
+            const float4* bt4 = reinterpret_cast<const float4*>(s_bias + pass * kBlockN);
+            const float4* bs4 = bt4 + kHalfN / 4;
             __nv_bfloat16* dst = p.acts_out + grow * kNCh + pass * 128;
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {
@@ -224,14 +233,19 @@ gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
                 tmem_ld_wait();
                 uint32_t packed[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int c = ch * 32 + 2 * j;
-                    const float g0 = gate_tanh_sigmoid(__uint_as_float(vt[2 * j]) + __ldg(bias + c),
-                                                       __uint_as_float(vs[2 * j]) + __ldg(bias + 128 + c));
-                    const float g1 = gate_tanh_sigmoid(__uint_as_float(vt[2 * j + 1]) + __ldg(bias + c + 1),
-                                                       __uint_as_float(vs[2 * j + 1]) + __ldg(bias + 129 + c));
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(g0, g1);
-                    packed[j] = *reinterpret_cast<uint32_t*>(&h2);
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bt = bt4[ch * 8 + j], bs = bs4[ch * 8 + j];      // warp-uniform: broadcast LDS.128
+                    const float g0 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j]) + bt.x,
+                                                         fmaf(__uint_as_float(vs[4 * j]), 0.5f, bs.x));
+                    const float g1 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j + 1]) + bt.y,
+                                                         fmaf(__uint_as_float(vs[4 * j + 1]), 0.5f, bs.y));
+                    const float g2 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j + 2]) + bt.z,
+                                                         fmaf(__uint_as_float(vs[4 * j + 2]), 0.5f, bs.z));
+                    const float g3 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j + 3]) + bt.w,
+                                                         fmaf(__uint_as_float(vs[4 * j + 3]), 0.5f, bs.w));
+                    __nv_bfloat162 h01 = __floats2bfloat162_rn(g0, g1), h23 = __floats2bfloat162_rn(g2, g3);
+                    packed[2 * j] = *reinterpret_cast<uint32_t*>(&h01);
+                    packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h23);
                 }
                 if (live) {
                     uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
