@@ -41,10 +41,12 @@ SAMPLE_RATE = 22050
 CPU_SAMPLE_FRAMES = 100
 PUBLISHED_V100_SAMPLES_PER_SEC = 2.75e6      # BASELINE.md §1 (waveglow/README.md:15-16, 1x V100 fp16)
 GATE_FLOP_PER_STEP = 2 * (3 * 512 + 640) * 1024   # in_layers + cond_layers MACs*2 per group step per layer
+GATE_ENTRY_POINTS = ("wgb_tc_wn_gate", "wgb_tc2_wn_gate", "wgb_tc2_wn_gate_mel")
 # dram__bytes_read.sum + dram__bytes_write.sum of one gate-GEMM launch at the full per-GPU batch of 64
 # (ncu --set full, profiles/r01c_ncu_full_summary.csv: 6.667 + 1.791 GB); algorithmic bytes are
 # h 1 KB + cond 1.25 KB read + acts 1 KB written per group step = 5.84 GB.  Scales with the per-rank batch.
-GATE_DRAM_BYTES_PER_LAUNCH_B64 = 8.458e9
+GATE_DRAM_BYTES_PER_LAUNCH_B64 = {"wgb_tc2_wn_gate": 8.458e9, "wgb_tc2_wn_gate_mel": None}
+GATE_DRAM_SOURCE = "profiles/r01c_ncu_full_summary.csv"
 
 
 def workload_config(n_gpus):
@@ -199,6 +201,7 @@ def run_gpu_arm(args):
     # ---- launch counter + per-launch CUDA events on the dominant kernel (gate GEMM)
     counter = {"n": 0}
     gate_events = []
+    gate_names = []
     raw_call = _lib.call
     profile = {"on": False}
 
@@ -212,12 +215,13 @@ def run_gpu_arm(args):
             raw_call(name, *a)
             e1.record()
             breakdown_events.append((name, e0, e1))
-        elif profile["on"] and name in ("wgb_tc_wn_gate", "wgb_tc2_wn_gate"):
+        elif profile["on"] and name in GATE_ENTRY_POINTS:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             raw_call(name, *a)
             e1.record()
             gate_events.append((e0, e1))
+            gate_names.append(name)
         else:
             raw_call(name, *a)
 
@@ -284,6 +288,31 @@ def run_gpu_arm(args):
     wn_flop_total = 522190848 * GLOBAL_BATCH * t_steps       # WN GEMM FLOPs per group step
     overall_tflops = wn_flop_total / (ms_per_step * 1e-3) / 1e12 / world
 
+    # The gate GEMM runs either on the [B,T,640] cond tensor (K = 2176, 128 group steps per tile) or with the
+    # conditioning composed with the upsampler (K = 1856, 128 frames x 1 phase per tile; engine.use_mel_path).
+    # `achieved` is ALGORITHMIC FLOPs (the reference's in_layers + cond_layers convs) / time; `executed_*` is what
+    # the tensor pipe really ran (fewer K chunks, but whole 128-frame tiles).
+    gate_name = gate_names[0] if gate_names else None
+    if gate_name == "wgb_tc2_wn_gate_mel":
+        gate_exec = 2 * (3 * 512 + 320) * 1024 * per_rank * (-(-FRAMES // 128) * 128) * 32
+        kernel_desc = ("tc2::pair_kernel<GATE_MEL>: in_layers k=3 dilated + (cond_layers o upsample) composed, K = 1856, "
+                       "+ gate epilogue; tcgen05 cta_group::2")
+    else:
+        gate_exec = gate_flop
+        kernel_desc = "in_layers k=3 dilated + cond 1x1 (K = 2176) + gate epilogue; tcgen05"
+    achieved_exec = gate_exec / (gate_avg_ms * 1e-3) / 1e12 if gate_ms else None
+    traffic = GATE_DRAM_BYTES_PER_LAUNCH_B64.get(gate_name)
+    roofline = {"kernel": kernel_desc, "entry_point": gate_name,
+                "bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                "frac": (achieved / sustained) if achieved else None, "frac_of_burst": (achieved / burst) if achieved else None,
+                "peak_source": peak_src + ", bf16_tflops_sustained (kernel timed inside a long step)",
+                "launches_timed": len(gate_ms), "avg_launch_ms": gate_avg_ms,
+                "flop_per_launch": gate_flop, "executed_flop_per_launch": gate_exec,
+                "executed_tflops": achieved_exec, "frac_executed": (achieved_exec / sustained) if achieved_exec else None,
+                "traffic": traffic * per_rank / GLOBAL_BATCH if traffic else None,
+                "traffic_source": "ncu dram__bytes_read+write per launch at batch 64, " + GATE_DRAM_SOURCE,
+                "algorithmic_bytes_per_launch": 3328 * per_rank * t_steps}
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -301,15 +330,7 @@ def run_gpu_arm(args):
                     "h2d_bytes_per_step": (mel_host.numel() + z_host.numel()) * 4 * world,
                     "d2h_bytes_per_step": out_host.numel() * 4 * world},
             "gpu_launches": launches,
-            "roofline": {"kernel": "wn_tc_kernel<GATE> (in_layers k=3 dilated + cond 1x1 + gate, tcgen05)",
-                         "bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                         "frac": (achieved / sustained) if achieved else None, "frac_of_burst": (achieved / burst) if achieved else None,
-                         "peak_source": peak_src + ", bf16_tflops_sustained (kernel timed inside a long step)",
-                         "launches_timed": len(gate_ms), "avg_launch_ms": gate_avg_ms,
-                         "flop_per_launch": gate_flop,
-                         "traffic": GATE_DRAM_BYTES_PER_LAUNCH_B64 * per_rank / GLOBAL_BATCH,
-                         "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01c_ncu_full_summary.csv",
-                         "algorithmic_bytes_per_launch": 3328 * per_rank * t_steps},
+            "roofline": roofline,
             "cpu_baseline": cpu,
             "breakdown": breakdown,
             "clocks": clocks.summary(),

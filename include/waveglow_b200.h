@@ -74,6 +74,25 @@ WGB_API int wgb_tc_wn_skip_end(const void* acts_all, int n_layers, const void* w
                        const float* b_end, float* x, const float* w_mix, float* log_s, int batch, int T,
                        int n_half, int direction, void* stream);
 
+/* The gate layer with cond_layers[i] composed with WaveGlow.upsample (glow.py:183-185,252-258 + :141-143,161):
+ * cond_layers[i](regroup(upsample(mel)))[t] is linear in the 4 x 80 mel values reaching group step t, with a
+ * weight that depends only on t mod 32, so the kernel tiles rows phase-major (128 frames at one phase) and the
+ * conditioning costs K = 320 instead of 640 (K = 1856 per layer instead of 2176); the [B,T,640] cond tensor is
+ * not needed.  h bf16 [B,T,512], T = 32 * frames; mel_stack bf16 [B,frames,320] (wgb_upsample_im2col with
+ * ld_tap = 80); w_packed as for wgb_tc_wn_gate (its 640 cond columns are not read); w_mel bf16 [32][1024][320] and
+ * bias fp32 [1024] from text2speech_b200/packing.py:pack_cond_mel.  Same output as wgb_tc2_wn_gate up to bf16
+ * rounding of the composed weight. */
+WGB_API int wgb_tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, const void* w_mel,
+                                const float* bias, void* acts, int batch, int T, int dilation, void* stream);
+
+/* CTA-pair (cta_group::2) forms of the two entry points above, same contracts: each CTA loads half of every
+ * weight tile, the pair issues one M = 256 MMA (half the weight traffic from L2 / shared memory per FLOP). */
+WGB_API int wgb_tc2_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out,
+                           int batch, int T, void* stream);
+WGB_API int wgb_tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end,
+                                const float* b_end, float* x, const float* w_mix, float* log_s, int batch, int T,
+                                int n_half, int direction, void* stream);
+
 /* Plain tcgen05 GEMM with the same TMA/TMEM pipeline: C[b,t,n] = sum_k A[b,t,k] W[n,k] + bias[n];
  * A bf16 [B,T,K] (K % 64 == 0), W bf16 [N,K] (N % 256 == 0), C fp32 or bf16 [B,T,N]; bias may be NULL.
  * Serves the dense-basis contractions that are 1x1 convs in the reference (cond/upsample/STFT bases,

@@ -94,11 +94,13 @@ def test_tc_gate_layer(lib, packed_q, dil_i, T, entry):
     assert err <= util.TOL_LAYER_BF16, err
 
 
-def test_tc_res_layer(lib, packed_q):
+@pytest.mark.parametrize("entry", ["wgb_tc_wn_res", "wgb_tc2_wn_res"])
+@pytest.mark.parametrize("B,T", [(2, 333), (3, 128), (1, 27520)])
+def test_tc_res_layer(lib, packed_q, entry, B, T):
     """residual half of res_skip_layers (glow.py:164-166)."""
     pk = packed_q["stress"]
     st = oracle.folded_state(quantised_state("stress"))
-    k, i, B, T = 5, 2, 2, 333
+    k, i = 5, 2
     g = torch.Generator().manual_seed(5)
     h = q(2.0 * torch.randn(B, 512, T, generator=g))
     acts = q(torch.rand(B, 512, T, generator=g) * 2 - 1)
@@ -106,20 +108,21 @@ def test_tc_res_layer(lib, packed_q):
     want = h + torch.nn.functional.conv1d(acts, w[:512], b[:512])
     fl = pk.flows[k]
     h_out = torch.zeros(B, T, 512, device=DEV, dtype=torch.bfloat16)
-    lib.call("wgb_tc_wn_res", cl(acts).to(DEV, torch.bfloat16), fl["w_res"][i], fl["b_res"][i],
+    lib.call(entry, cl(acts).to(DEV, torch.bfloat16), fl["w_res"][i], fl["b_res"][i],
              cl(h).to(DEV, torch.bfloat16), h_out, B, T, lib.stream_ptr())
     torch.cuda.synchronize()
     err = util.rel_l2(h_out.float().cpu(), cl(want))
     assert err <= util.TOL_LAYER_BF16, err
 
 
+@pytest.mark.parametrize("entry", ["wgb_tc_wn_skip_end", "wgb_tc2_wn_skip_end"])
 @pytest.mark.parametrize("k,direction", [(11, 0), (5, 0), (0, 0), (11, 1), (4, 1), (1, 1)])
-def test_tc_skip_end_coupling(lib, packed_q, k, direction):
+def test_tc_skip_end_coupling(lib, packed_q, k, direction, entry):
     """skip sum over 8 layers + WN.end + affine coupling (+ W^-1)  (glow.py:171-175, :277-282 / :241-246)."""
     pk = packed_q["stress"]
     st = oracle.folded_state(quantised_state("stress"))
     fl = pk.flows[k]
-    n_half, B, T = fl["n_half"], 2, 300
+    n_half, B, T = fl["n_half"], (2 if k != 5 else 3), (300 if k != 0 else 128)
     C, base = 2 * n_half, 8 - 2 * n_half
     g = torch.Generator().manual_seed(11 + k)
     acts = q(torch.rand(8, B, 512, T, generator=g) * 2 - 1)
@@ -142,7 +145,7 @@ def test_tc_skip_end_coupling(lib, packed_q, k, direction):
     xd = x.to(DEV).contiguous()
     log_s = torch.zeros(B, n_half, T, device=DEV) if direction == 1 else None
     acts_all = acts.permute(0, 1, 3, 2).contiguous().to(DEV, torch.bfloat16)
-    lib.call("wgb_tc_wn_skip_end", acts_all, 8, fl["w_skip"], fl["w_end_t"], fl["b_end"], xd,
+    lib.call(entry, acts_all, 8, fl["w_skip"], fl["w_end_t"], fl["b_end"], xd,
              fl["w_mix_inv"] if direction == 0 else None, log_s, B, T, n_half, direction, lib.stream_ptr())
     torch.cuda.synchronize()
     assert util.rel_l2(xd.cpu()[:, :, base:], want[:, :, base:]) <= 1e-4
@@ -152,6 +155,44 @@ def test_tc_skip_end_coupling(lib, packed_q, k, direction):
 
 
 # ------------------------------------------------------------------------------------ whole model
+
+@pytest.mark.parametrize("dil_i,B,F", [(0, 2, 130), (3, 3, 40), (4, 1, 129), (5, 1, 200), (7, 2, 130), (6, 1, 860)])
+def test_tc2_gate_mel_layer(lib, packed_q, dil_i, B, F):
+    """Gate layer with cond_layers composed with the upsampler (wgb_tc2_wn_gate_mel): in_layers taps read through
+    the phase-major 4-D map of h, conditioning as K = 320 against the per-phase weight.  Both sides use the packed
+    (bf16) operands; the composition itself is pinned on the CPU (tests/test_packing.py)."""
+    from text2speech_b200 import engine
+    pk = packed_q["stress"]
+    st = oracle.folded_state(quantised_state("stress"))
+    k, T = 9, 32 * F
+    fl = pk.flows[k]
+    g = torch.Generator().manual_seed(300 + dil_i)
+    h = q(1.5 * torch.randn(B, 512, T, generator=g))
+    mel = syn.synthetic_mel(B, F, seed=17 + dil_i)
+    stack = engine.mel_stack(pk, mel.to(DEV))                                  # bf16 [B, F, 320]
+    assert stack.shape == (B, F, 320)
+    ref_stack = torch.zeros(B, F, 4, 80)
+    for j in range(4):
+        ref_stack[:, j:, j] = mel[:, :, : F - j].permute(0, 2, 1)
+    assert torch.equal(stack.float().cpu(), q(ref_stack.reshape(B, F, 320)))
+    # reference pre-activation: dilated in_layers conv on h (fp32, quantised weights) + packed per-phase conditioning
+    w_in = st[f"WN.{k}.in_layers.{dil_i}.weight"]
+    d = 2 ** dil_i
+    u_in = torch.nn.functional.conv1d(h, w_in, None, dilation=d, padding=d)                      # [B, 1024, T]
+    from text2speech_b200.packing import gate_row_order
+    u_in = u_in[:, gate_row_order(512)].permute(0, 2, 1)                                         # packed order [B,T,1024]
+    v = fl["w_mel"][dil_i].float().cpu().double()                                                # [32, 1024, 320]
+    u_c = torch.einsum("pok,bfk->bfpo", v, stack.float().cpu().double()).reshape(B, T, 1024)
+    u = u_in.double() + u_c + fl["b_mel"][dil_i].cpu().double()
+    want = torch.cat([torch.tanh(u[:, :, p * 256: p * 256 + 128]) * torch.sigmoid(u[:, :, p * 256 + 128: (p + 1) * 256])
+                      for p in range(4)], dim=2)
+    acts = torch.zeros(B, T, 512, device=DEV, dtype=torch.bfloat16)
+    lib.call("wgb_tc2_wn_gate_mel", cl(h).to(DEV, torch.bfloat16), stack, fl["w_gate"][dil_i], fl["w_mel"][dil_i],
+             fl["b_mel"][dil_i], acts, B, T, d, lib.stream_ptr())
+    torch.cuda.synchronize()
+    err = util.rel_l2(acts.float().cpu(), want)
+    assert err <= util.TOL_LAYER_BF16, err
+
 
 @pytest.fixture(scope="module")
 def models(lib):
@@ -184,6 +225,37 @@ def test_infer_bf16_mode_snr(models, golden, recipe):
     audio = m.infer(mel.to(DEV), sigma=util.SIGMA, z=z.to(DEV)).cpu()
     snr = util.snr_db(audio, golden[f"{recipe}_infer_audio"])
     assert snr >= util.MIN_SNR_DB, snr
+
+
+@pytest.mark.parametrize("recipe", ["bench", "stress"])
+def test_infer_bf16_composed_conditioning_path(models, golden, recipe):
+    """Forced 'mel' path (conditioning composed with the upsampler) vs the reference, and vs the 'cond' path."""
+    m = models[recipe]
+    m.mode = "bf16"
+    mel, z, _ = util.golden_inputs()
+    try:
+        m.cond_path = "mel"
+        a_mel = m.infer(mel.to(DEV), sigma=util.SIGMA, z=z.to(DEV)).cpu()
+        m.cond_path = "cond"
+        a_cond = m.infer(mel.to(DEV), sigma=util.SIGMA, z=z.to(DEV)).cpu()
+    finally:
+        m.cond_path = "auto"
+    assert util.snr_db(a_mel, golden[f"{recipe}_infer_audio"]) >= util.MIN_SNR_DB
+    assert util.snr_db(a_mel, a_cond) >= util.MIN_SNR_DB
+    assert not torch.equal(a_mel, a_cond)            # really two different kernels
+
+
+def test_forward_bf16_composed_conditioning_path(models, golden):
+    m = models["bench"]
+    m.mode = "bf16"
+    mel, _, wav = util.golden_inputs()
+    try:
+        m.cond_path = "mel"
+        z, log_s, log_det = m((mel.to(DEV), wav.to(DEV)))
+    finally:
+        m.cond_path = "auto"
+    assert util.snr_db(z.cpu(), golden["bench_fwd_z"]) >= util.MIN_SNR_DB
+    assert util.rel_l2(log_s[5].cpu(), golden["bench_fwd_log_s5"]) < 0.05
 
 
 def test_fp32_layers_match_golden_taps(models, golden, lib):

@@ -88,3 +88,27 @@ def test_exact_packing_with_fp32_weights():
         want = oracle.waveglow_infer(sd, mel, z, util.SIGMA)
         got = emulate.infer(pk, mel, z, util.SIGMA, round_bf16=False)
     assert util.rel_l2(got, want) < 2e-5
+
+
+def test_cond_mel_composition_matches_cond_layer_of_upsampled_mel():
+    """pack_cond_mel: cond_layers[i](regroup(upsample(mel))) == per-phase (W_cond U_phase) . stack(mel[f-j]) + bias
+    (the algebra behind wgb_tc2_wn_gate_mel; glow.py:252-258 + :161)."""
+    from text2speech_b200.packing import pack_cond_mel, pack_gate
+    st = oracle.folded_state(util.state_dict("stress"))
+    k, i, bsz, frames = 7, 3, 2, 5
+    p = f"WN.{k}."
+    wg, bg = pack_gate(st[p + f"in_layers.{i}.weight"], st[p + f"in_layers.{i}.bias"],
+                       st[p + f"cond_layers.{i}.weight"], st[p + f"cond_layers.{i}.bias"])
+    v, b_add = pack_cond_mel(wg[:, 1536:], st["upsample.weight"], st["upsample.bias"], 8)
+    assert v.shape == (32, 1024, 320) and b_add.shape == (1024,)
+    mel, _, _ = util.golden_inputs(bsz, frames)
+    stack = torch.zeros(bsz, frames, 4, 80)
+    for j in range(4):
+        stack[:, j:, j] = mel[:, :, : frames - j].permute(0, 2, 1)
+    stack = stack.reshape(bsz, frames, 320)
+    got = torch.einsum("pok,bfk->bfpo", v, stack).reshape(bsz, frames * 32, 1024) + (bg + b_add)
+    up = oracle.upsample_spect(st, mel)[:, :, : frames * 256]
+    cond = oracle.regroup_spect(up, 8)
+    want = torch.nn.functional.conv1d(cond, st[p + f"cond_layers.{i}.weight"], st[p + f"cond_layers.{i}.bias"])
+    want = (want + st[p + f"in_layers.{i}.bias"][None, :, None])[:, gate_row_order(512)].permute(0, 2, 1)
+    assert util.rel_l2(got, want) < 1e-5

@@ -15,6 +15,10 @@ int tc_gemm_split3(const void*, const void*, const void*, const float*, void*, i
                    cudaStream_t);
 // wn_tc2.cu
 int tc2_wn_gate(const void*, const void*, const void*, const float*, void*, int, int, int, cudaStream_t);
+int tc2_wn_res(const void*, const void*, const float*, const void*, void*, int, int, cudaStream_t);
+int tc2_wn_gate_mel(const void*, const void*, const void*, const void*, const float*, void*, int, int, int, cudaStream_t);
+int tc2_wn_skip_end(const void*, int, const void*, const float*, const float*, float*, const float*, float*, int, int,
+                    int, int, cudaStream_t);
 // ref_f32.cu
 int sgemm_nt(const float*, const float*, const float*, void*, int, int, int, int, int, long long, long long, long long,
              long long, long long, int, int, cudaStream_t);
@@ -78,6 +82,20 @@ WGB_API int wgb_tc_wn_gate(const void* h, const void* cond, const void* w_packed
 WGB_API int wgb_tc2_wn_gate(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts, int batch,
                             int T, int dilation, void* stream) {
     return tc2_wn_gate(h, cond, w_packed, bias, acts, batch, T, dilation, S(stream));
+}
+WGB_API int wgb_tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, const void* w_mel,
+                                const float* bias, void* acts, int batch, int T, int dilation, void* stream) {
+    return tc2_wn_gate_mel(h, mel_stack, w_packed, w_mel, bias, acts, batch, T, dilation, S(stream));
+}
+WGB_API int wgb_tc2_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch,
+                           int T, void* stream) {
+    return tc2_wn_res(acts, w_res, bias, h_in, h_out, batch, T, S(stream));
+}
+WGB_API int wgb_tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end,
+                                const float* b_end, float* x, const float* w_mix, float* log_s, int batch, int T,
+                                int n_half, int direction, void* stream) {
+    return tc2_wn_skip_end(acts_all, n_layers, w_skip, w_end, b_end, x, w_mix, log_s, batch, T, n_half, direction,
+                           S(stream));
 }
 WGB_API int wgb_tc_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch,
                   int T, void* stream) {

@@ -1,16 +1,29 @@
-// WN gate GEMM on CTA pairs: tcgen05.mma.cta_group::2 (UMMA M = 256 over two SMs).
+// WN-layer GEMMs on CTA pairs: tcgen05.mma.cta_group::2 (UMMA M = 256 over two SMs).
 //
-// Same math as MODE_GATE in wn_tc.cu (in_layers k=3 dilated + cond 1x1 + bias -> tanh*sigmoid, reference
-// glow.py:159-162), but two CTAs of a cluster share every weight tile: each CTA TMA-loads its own 128
-// time rows of the activation operand and only HALF (128 of 256 rows) of the weight tile, and the
-// leader CTA issues one M=256 x N=256 MMA that reads both halves.  Per CTA and K chunk that is
-// 16 KB + 16 KB instead of 16 KB + 32 KB from L2, and the tensor core reads each weight byte from
-// shared memory once per pair instead of once per CTA -- the point on a power-capped part.
+// Same math as the one-CTA kernels in wn_tc.cu, but the two CTAs of a cluster share every weight tile:
+// each CTA TMA-loads its own 128 time rows of the activation operand and only HALF (128 of 256 rows) of
+// the weight tile, and the leader CTA issues one M=256 x N=256 MMA that reads both halves.  Per CTA and
+// K chunk that is 16 KB + 16 KB instead of 16 KB + 32 KB from L2, and the tensor core reads each weight
+// byte from shared memory once per pair instead of once per CTA -- the point on a power-capped part.
 //
-// Protocol (per pair): both CTAs run a TMA producer; all loads complete_tx on the LEADER's full barrier,
-// which the leader's producer arms with the byte count of both CTAs.  The leader's MMA thread commits
-// with .multicast::cluster to the empty / tmem-full barriers of both CTAs; the epilogue warps of both
-// CTAs arrive (the peer remotely) on the leader's tmem-empty barrier.
+//   GATE      in_layers[i] (k=3, dilation d) + cond_layers[i] + bias -> tanh*sigmoid -> acts   (glow.py:159-162)
+//   GATE_MEL  the same layer with the conditioning path composed with the upsampler: cond_layers[i](upsample(mel))
+//             is linear in the 4 x 80 mel values that reach a group step, with a weight that depends only on the
+//             step's phase inside its frame (t mod 32), so rows are tiled PHASE-MAJOR (128 consecutive frames at
+//             one phase, read through a 4-D tensor map of h) and the conditioning costs K = 320 instead of 640:
+//             K = 1856 per layer instead of 2176, and the [B,T,640] cond tensor is never read (glow.py:252-258 + :161)
+//   RES       res half of res_skip_layers[i]: h_out = h_in + W_res acts + b                   (glow.py:164-166)
+//   SKIP_END  sum_i W_skip_i acts_i as ONE K = 8*512 GEMM, then end 1x1, affine coupling and the
+//             invertible 1x1 conv in the fp32 epilogue                     (glow.py:167-175, :277-282 / :241-246)
+//
+// Protocol (per pair): both CTAs run a TMA producer; all operand loads complete_tx on the LEADER's full
+// barrier, which the leader's producer arms with the byte count of both CTAs.  The leader's MMA thread
+// commits with .multicast::cluster to the empty / tmem-full barriers of both CTAs; the epilogue warps of
+// both CTAs arrive (the peer remotely) on the leader's tmem-empty barrier.  RES additionally stages its
+// own 128 x 256 h tile per CTA in two 128-column halves (TMA load -> in-place update in the swizzled layout
+// -> TMA store), driven by a seventh warp behind CTA-local barriers: while the epilogue works on one half,
+// the other half's store drains and the next pass's h_in streams in, so the HBM latency of the residual
+// stream never sits between two epilogues.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -23,24 +36,44 @@ constexpr int kBlockN = 256;
 constexpr int kHalfN = 128;           // weight rows each CTA loads
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
-constexpr int kStages = 6;
 constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
 constexpr int kBBytes = kHalfN * kBlockK * 2;       // 16 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 192;
+constexpr int kThreadsRes = 224;      // + warp 6: h-tile loader / storer
 constexpr int kNCh = 512;
 constexpr int kNCond = 640;
-constexpr int kBiasOff = kStages * kStageBytes;     // fp32 [1024]: tanh biases as is, sigmoid biases pre-halved
-constexpr int kBiasBytes = 2 * kNCh * 4;
-constexpr int kBarOff = kBiasOff + kBiasBytes;
-constexpr int kSmemTotal = 1024 + kBarOff + 256;
+
+enum Mode { GATE = 0, RES = 1, SKIP_END = 2, GATE_MEL = 3 };
+constexpr int kPhases = 32;          // group steps per mel frame (hop 256 / n_group 8)
+constexpr int kMelK = 320;           // 4 upsample taps x 80 mel channels
+
+// Shared memory (offsets from a 1024 B aligned base): [TMA ring][mode extra][barriers]
+//   GATE      6 stages + 4 KB bias (sigmoid half pre-halved)
+//   RES       4 stages + 64 KB h tile + 2 KB bias
+//   SKIP_END  6 stages + 16 KB W_end^T
+template <int MODE>
+struct Smem {
+    static constexpr int kStages = MODE == RES ? 4 : 6;
+    static constexpr int kExtraOff = kStages * kStageBytes;
+    static constexpr int kExtraBytes =
+        (MODE == GATE || MODE == GATE_MEL) ? 2 * kNCh * 4 : (MODE == RES ? kBlockM * kBlockN * 2 + kNCh * 4 : kNCh * 8 * 4);
+    static constexpr int kBarOff = kExtraOff + kExtraBytes;
+    static constexpr int kTotal = 1024 + kBarOff + 256;
+};
 
 struct Params {
     int batch, T, tiles_per_b, n_tiles;
-    int n_pass, n_chunks, dilation;
-    const float* bias;
-    __nv_bfloat16* acts_out;
+    int n_pass, ppi, n_chunks, dilation;
+    int frames, n_fblk;           // GATE_MEL: mel frames per utterance (T = 32 frames), 128-frame blocks per utterance
+    const float* bias;            // GATE [1024] packed order, RES [512]
+    __nv_bfloat16* acts_out;      // GATE [B,T,512]
+    const float* w_end;           // SKIP_END [512][8] fp32 (rows >= 2*n_half zero)
+    const float* b_end;           // SKIP_END [8] (skip biases folded in)
+    float* x;                     // SKIP_END flow state [B,T,8]
+    const float* w_mix;           // SKIP_END infer: W^-1 [8][8]
+    float* log_s;                 // SKIP_END forward: [B,n_half,T]
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -84,6 +117,14 @@ __device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* m,
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1,
+                                                int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                  uint32_t accumulate) {
     asm volatile(
@@ -102,16 +143,24 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                  : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_cond,
-            const __grid_constant__ CUtensorMap map_w, const Params p) {
+template <int MODE, int NHALF, int DIR>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsRes, 1)
+pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+            const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c, const Params p) {
+    using SL = Smem<MODE>;
+    constexpr int kStages = SL::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBarOff);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::kBarOff);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tfull_bar = empty_bar + kStages;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* hfull_bar = tempty_bar + 2;        // RES [2]: h_in half-tile landed in smem
+    uint64_t* hready_bar = hfull_bar + 2;        // RES [2]: half-tile updated in place by the epilogue, ready to store
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hready_bar + 2);
+    uint8_t* s_extra = smem + SL::kExtraOff;
+    float* s_f32 = reinterpret_cast<float*>(s_extra);                                    // GATE bias / SKIP_END W_end^T
+    float* s_rbias = reinterpret_cast<float*>(s_extra + kBlockM * kBlockN * 2);           // RES bias
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -119,9 +168,14 @@ gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
     const bool leader = rank == 0;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&map_h);
-        tma_prefetch_desc(&map_cond);
+        tma_prefetch_desc(&map_a0);
+        tma_prefetch_desc(&map_a1);
         tma_prefetch_desc(&map_w);
+        if constexpr (MODE == RES || MODE == GATE_MEL) tma_prefetch_desc(&map_c);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&hfull_bar[i], 1);
+            mbar_init(&hready_bar[i], 4);      // the four epilogue warps
+        }
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -133,11 +187,17 @@ gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_2sm(tmem_slot, kTmemCols);
-    float* s_bias = reinterpret_cast<float*>(smem + kBiasOff);
-    if (warp >= 2) {
-        // packed column c of pass p: tanh row for (c & 255) < 128, else the matching sigmoid row, whose
-        // pre-activation is halved (sigmoid(b) = 0.5 tanh(b/2) + 0.5)
-        for (int i = threadIdx.x - 64; i < 2 * kNCh; i += 128) s_bias[i] = p.bias[i] * ((i & 128) ? 0.5f : 1.f);
+    if (warp >= 2 && warp < 6) {
+        const int i0 = threadIdx.x - 64;
+        if constexpr (MODE == GATE || MODE == GATE_MEL) {
+            // packed column c of pass p: tanh row for (c & 255) < 128, else the matching sigmoid row, whose
+            // pre-activation is halved (sigmoid(b) = 0.5 tanh(b/2) + 0.5)
+            for (int i = i0; i < 2 * kNCh; i += 128) s_f32[i] = p.bias[i] * ((i & 128) ? 0.5f : 1.f);
+        } else if constexpr (MODE == RES) {
+            for (int i = i0; i < kNCh; i += 128) s_rbias[i] = p.bias[i];
+        } else {
+            for (int i = i0; i < kNCh * 8; i += 128) s_f32[i] = p.w_end[i];
+        }
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -148,7 +208,8 @@ gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
     const int n_pairs = gridDim.x >> 1;
     const int pair_id = blockIdx.x >> 1;
     const int n_pair_tiles = (p.n_tiles + 1) >> 1;
-    const int n_items = n_pair_tiles * p.n_pass;
+    const int groups = p.n_pass / p.ppi;
+    const int n_items = n_pair_tiles * groups;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -156,25 +217,51 @@ gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
             int s = 0;
             uint32_t ph = 0;
             for (int item = pair_id; item < n_items; item += n_pairs) {
-                const int tile = 2 * (item / p.n_pass) + static_cast<int>(rank);
-                const int pass = item % p.n_pass;
+                const int tile = 2 * (item / groups) + static_cast<int>(rank);
                 const bool valid = tile < p.n_tiles;
                 const int b = valid ? tile / p.tiles_per_b : 0;
-                const int t0 = valid ? (tile % p.tiles_per_b) * kBlockM : p.T + 4 * kBlockM;   // all rows OOB -> zeros
-                for (int kc = 0; kc < p.n_chunks; ++kc) {
-                    mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
-                    uint8_t* sa = smem + s * kStageBytes;
-                    uint8_t* sb = sa + kABytes;
-                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * kStageBytes);
-                    const uint32_t bar = mapa_u32(&full_bar[s], 0);
-                    if (kc < 24) {
-                        const int tap = kc >> 3;
-                        tma_load_3d_2sm(sa, &map_h, bar, (kc & 7) * kBlockK, t0 + (tap - 1) * p.dilation, b);
-                    } else {
-                        tma_load_3d_2sm(sa, &map_cond, bar, (kc - 24) * kBlockK, t0, b);
+                // first row (GATE_MEL: first frame) of this CTA's tile; an absent second tile reads all-OOB rows = zeros
+                const int t0 = valid ? (tile % p.tiles_per_b) * kBlockM : (MODE == GATE_MEL ? p.frames : p.T) + 4 * kBlockM;
+                for (int pp = 0; pp < p.ppi; ++pp) {
+                    const int vpass = (item % groups) * p.ppi + pp;
+                    // GATE_MEL enumerates (phase, pass) as 128 virtual passes: pass fastest, then the phase
+                    const int pass = MODE == GATE_MEL ? (vpass & 3) : vpass;
+                    const int phase = vpass >> 2;
+                    for (int kc = 0; kc < p.n_chunks; ++kc) {
+                        mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
+                        uint8_t* sa = smem + s * kStageBytes;
+                        uint8_t* sb = sa + kABytes;
+                        if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * kStageBytes);
+                        const uint32_t bar = mapa_u32(&full_bar[s], 0);
+                        if constexpr (MODE == GATE) {
+                            if (kc < 24) {
+                                const int tap = kc >> 3;
+                                tma_load_3d_2sm(sa, &map_a0, bar, (kc & 7) * kBlockK, t0 + (tap - 1) * p.dilation, b);
+                            } else {
+                                tma_load_3d_2sm(sa, &map_a1, bar, (kc - 24) * kBlockK, t0, b);
+                            }
+                        } else if constexpr (MODE == GATE_MEL) {
+                            if (kc < 24) {
+                                // row (f, phase) of the tile needs h at group step 32 f + phase + (tap-1) d = frame
+                                // f + (q >> 5), phase q & 31 with q = phase + (tap-1) d (floor / mod, q may be < 0);
+                                // frames outside [0, F) are zero-filled by TMA = the conv's zero padding
+                                const int q = phase + ((kc >> 3) - 1) * p.dilation;
+                                tma_load_4d_2sm(sa, &map_a0, bar, (kc & 7) * kBlockK, q & (kPhases - 1), t0 + (q >> 5), b);
+                            } else {
+                                tma_load_3d_2sm(sa, &map_a1, bar, (kc - 24) * kBlockK, t0, b);
+                            }
+                        } else if constexpr (MODE == RES) {
+                            tma_load_3d_2sm(sa, &map_a0, bar, kc * kBlockK, t0, b);
+                        } else {
+                            tma_load_3d_2sm(sa, &map_a0, bar, (kc & 7) * kBlockK, t0, (kc >> 3) * p.batch + b);
+                        }
+                        const int w_row = pass * kBlockN + static_cast<int>(rank) * kHalfN;
+                        if (MODE == GATE_MEL && kc >= 24)      // phase-specific composed conditioning weight [32*1024][320]
+                            tma_load_2d_2sm(sb, &map_c, bar, (kc - 24) * kBlockK, phase * (2 * kNCh) + w_row);
+                        else
+                            tma_load_2d_2sm(sb, &map_w, bar, kc * kBlockK, w_row);
+                        if (++s == kStages) { s = 0; ph ^= 1; }
                     }
-                    tma_load_2d_2sm(sb, &map_w, bar, kc * kBlockK, pass * kBlockN + static_cast<int>(rank) * kHalfN);
-                    if (++s == kStages) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -184,79 +271,240 @@ gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
             constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * kBlockM, kBlockN);
             int s = 0;
             uint32_t ph = 0, acc_it = 0;
-            for (int item = pair_id; item < n_items; item += n_pairs, ++acc_it) {
-                const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-                mbar_wait(&tempty_bar[as], aph ^ 1, 200 + as);
-                tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + as * kBlockN;
-                for (int kc = 0; kc < p.n_chunks; ++kc) {
-                    mbar_wait(&full_bar[s], ph, 300 + s);
+            for (int item = pair_id; item < n_items; item += n_pairs) {
+                for (int pp = 0; pp < p.ppi; ++pp, ++acc_it) {
+                    const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                    mbar_wait(&tempty_bar[as], aph ^ 1, 200 + as);
                     tc_fence_after_sync();
-                    const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
-                    const uint32_t b_addr = a_addr + kABytes;
+                    const uint32_t d_tmem = tmem_base + as * kBlockN;
+                    for (int kc = 0; kc < p.n_chunks; ++kc) {
+                        mbar_wait(&full_bar[s], ph, 300 + s);
+                        tc_fence_after_sync();
+                        const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+                        const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        umma_bf16_ss_2sm(d_tmem, umma_desc_sw128(a_addr + k * kUmmaK * 2),
-                                         umma_desc_sw128(b_addr + k * kUmmaK * 2), idesc, (kc | k) != 0);
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            umma_bf16_ss_2sm(d_tmem, umma_desc_sw128(a_addr + k * kUmmaK * 2),
+                                             umma_desc_sw128(b_addr + k * kUmmaK * 2), idesc, (kc | k) != 0);
+                        }
+                        umma_commit_2sm(&empty_bar[s]);
+                        if (++s == kStages) { s = 0; ph ^= 1; }
                     }
-                    umma_commit_2sm(&empty_bar[s]);
-                    if (++s == kStages) { s = 0; ph ^= 1; }
+                    umma_commit_2sm(&tfull_bar[as]);
                 }
-                umma_commit_2sm(&tfull_bar[as]);
+            }
+        }
+    } else if (warp == 6) {
+        // ------------------------------------------------------------------ RES: h-tile loader / storer (both CTAs)
+        if constexpr (MODE == RES) {
+            if (lane == 0) {
+                // step k of this CTA = (item pair_id + k*n_pairs, its single pass); half hf = columns hf*128..+127 of
+                // the pass = boxes 2hf, 2hf+1 of the 64 KB tile buffer
+                auto coords = [&](int item, int& pass, int& t0, int& b) {
+                    const int tile = 2 * (item / groups) + static_cast<int>(rank);
+                    const bool valid = tile < p.n_tiles;
+                    pass = item % groups;
+                    b = valid ? tile / p.tiles_per_b : 0;
+                    t0 = valid ? (tile % p.tiles_per_b) * kBlockM : p.T + 4 * kBlockM;      // OOB: zeros in, nothing out
+                };
+                auto load_half = [&](int hf, int pass, int t0, int b) {
+                    mbar_arrive_expect_tx(&hfull_bar[hf], kBlockM * kHalfN * 2);
+#pragma unroll
+                    for (int j = 2 * hf; j < 2 * hf + 2; ++j)
+                        tma_load_3d(s_extra + j * kABytes, &map_a1, &hfull_bar[hf], pass * kBlockN + j * kBlockK, t0, b);
+                };
+                int pass, t0, b;
+                if (pair_id < n_items) {
+                    coords(pair_id, pass, t0, b);
+                    load_half(0, pass, t0, b);
+                    load_half(1, pass, t0, b);
+                }
+                uint32_t it = 0;
+                for (int item = pair_id; item < n_items; item += n_pairs, ++it) {
+                    coords(item, pass, t0, b);
+                    const bool has_next = item + n_pairs < n_items;
+                    int npass = 0, nt0 = 0, nb = 0;
+                    if (has_next) {
+                        coords(item + n_pairs, npass, nt0, nb);
+#pragma unroll
+                        for (int j = 0; j < kBlockN / kBlockK; ++j)      // pull the next h_in tile into L2 a whole pass early
+                            tma_prefetch_3d(&map_a1, npass * kBlockN + j * kBlockK, nt0, nb);
+                    }
+                    for (int hf = 0; hf < 2; ++hf) {
+                        mbar_wait(&hready_bar[hf], it & 1, 700 + hf);
+#pragma unroll
+                        for (int j = 2 * hf; j < 2 * hf + 2; ++j)
+                            tma_store_3d(&map_c, s_extra + j * kABytes, pass * kBlockN + j * kBlockK, t0, b);
+                        tma_store_commit();
+                        tma_store_wait_read0();                          // smem half free again
+                        if (has_next) load_half(hf, npass, nt0, nb);
+                    }
+                }
+                tma_store_wait_all0();                                   // h_out globally visible before the kernel ends
             }
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        uint32_t acc_it = 0;
-        for (int item = pair_id; item < n_items; item += n_pairs, ++acc_it) {
-            const int tile = 2 * (item / p.n_pass) + static_cast<int>(rank);
-            const int pass = item % p.n_pass;
+        uint32_t acc_it = 0, hph = 0;
+        for (int item = pair_id; item < n_items; item += n_pairs) {
+            const int tile = 2 * (item / groups) + static_cast<int>(rank);
             const bool valid = tile < p.n_tiles;
             const int b = valid ? tile / p.tiles_per_b : 0;
-            const int t = valid ? (tile % p.tiles_per_b) * kBlockM + row : p.T;
-            const bool live = t < p.T;
-            const size_t grow = static_cast<size_t>(b) * p.T + t;
-            const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-            mbar_wait(&tfull_bar[as], aph, 400 + as);
-            tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBlockN;
-            const float4* bt4 = reinterpret_cast<const float4*>(s_bias + pass * kBlockN);
-            const float4* bs4 = bt4 + kHalfN / 4;
-            __nv_bfloat16* dst = p.acts_out + grow * kNCh + pass * 128;
-#pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t vt[32], vs[32];
-                tmem_ld_32x32b_x32(taddr + ch * 32, vt);
-                tmem_ld_32x32b_x32(taddr + 128 + ch * 32, vs);
-                tmem_ld_wait();
-                uint32_t packed[16];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 bt = bt4[ch * 8 + j], bs = bs4[ch * 8 + j];      // warp-uniform: broadcast LDS.128
-                    const float g0 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j]) + bt.x,
-                                                         fmaf(__uint_as_float(vs[4 * j]), 0.5f, bs.x));
-                    const float g1 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j + 1]) + bt.y,
-                                                         fmaf(__uint_as_float(vs[4 * j + 1]), 0.5f, bs.y));
-                    const float g2 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j + 2]) + bt.z,
-                                                         fmaf(__uint_as_float(vs[4 * j + 2]), 0.5f, bs.z));
-                    const float g3 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j + 3]) + bt.w,
-                                                         fmaf(__uint_as_float(vs[4 * j + 3]), 0.5f, bs.w));
-                    __nv_bfloat162 h01 = __floats2bfloat162_rn(g0, g1), h23 = __floats2bfloat162_rn(g2, g3);
-                    packed[2 * j] = *reinterpret_cast<uint32_t*>(&h01);
-                    packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h23);
-                }
-                if (live) {
-                    uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                }
+            int t = valid ? (tile % p.tiles_per_b) * kBlockM + row : p.T;
+            bool live = t < p.T;
+            if constexpr (MODE == GATE_MEL) {                 // phase-major tile: row = frame, t = 32 frame + phase
+                live = valid && t < p.frames;
+                t = t * kPhases + ((item % groups) >> 2);
             }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[as], 0));
+            const size_t grow = static_cast<size_t>(b) * p.T + t;
+            float outv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) outv[j] = 0.f;
+
+            for (int pp = 0; pp < p.ppi; ++pp, ++acc_it) {
+                const int vpass = (item % groups) * p.ppi + pp;
+                const int pass = MODE == GATE_MEL ? (vpass & 3) : vpass;
+                const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                mbar_wait(&tfull_bar[as], aph, 400 + as);
+                tc_fence_after_sync();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBlockN;
+
+                if constexpr (MODE == GATE || MODE == GATE_MEL) {
+                    const float4* bt4 = reinterpret_cast<const float4*>(s_f32 + pass * kBlockN);
+                    const float4* bs4 = bt4 + kHalfN / 4;
+                    __nv_bfloat16* dst = p.acts_out + grow * kNCh + pass * 128;
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t vt[32], vs[32];
+                        tmem_ld_32x32b_x32(taddr + ch * 32, vt);
+                        tmem_ld_32x32b_x32(taddr + 128 + ch * 32, vs);
+                        tmem_ld_wait();
+                        uint32_t packed[16];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bt = bt4[ch * 8 + j], bs = bs4[ch * 8 + j];      // warp-uniform: broadcast LDS.128
+                            const float g0 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j]) + bt.x,
+                                                                 fmaf(__uint_as_float(vs[4 * j]), 0.5f, bs.x));
+                            const float g1 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j + 1]) + bt.y,
+                                                                 fmaf(__uint_as_float(vs[4 * j + 1]), 0.5f, bs.y));
+                            const float g2 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j + 2]) + bt.z,
+                                                                 fmaf(__uint_as_float(vs[4 * j + 2]), 0.5f, bs.z));
+                            const float g3 = gate_tanh_sigmoid_h(__uint_as_float(vt[4 * j + 3]) + bt.w,
+                                                                 fmaf(__uint_as_float(vs[4 * j + 3]), 0.5f, bs.w));
+                            __nv_bfloat162 h01 = __floats2bfloat162_rn(g0, g1), h23 = __floats2bfloat162_rn(g2, g3);
+                            packed[2 * j] = *reinterpret_cast<uint32_t*>(&h01);
+                            packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h23);
+                        }
+                        if (live) {
+                            uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                        }
+                    }
+                } else if constexpr (MODE == RES) {
+                    // h tile sits in smem in the TMA SWIZZLE_128B layout (four [128 x 64] boxes): row r of box j is
+                    // at j*16K + r*128, its 16 B chunk c at ((c ^ (r & 7)) << 4).  Each thread updates its own row
+                    // in place; the whole tile then leaves through one TMA store (coalesced, asynchronous).
+                    const float4* bias4 = reinterpret_cast<const float4*>(s_rbias) + pass * (kBlockN / 4);
+#pragma unroll 1
+                    for (int ch = 0; ch < 8; ++ch) {
+                        if ((ch & 3) == 0) mbar_wait(&hfull_bar[ch >> 2], hph, 600 + (ch >> 2));
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + ch * 32, v);
+                        uint8_t* rowp = s_extra + (ch >> 1) * kABytes + row * 128;
+                        uint4 old[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            old[i] = *reinterpret_cast<const uint4*>(rowp + ((((ch & 1) * 4 + i) ^ (row & 7)) << 4));
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t* ow = reinterpret_cast<const uint32_t*>(&old[i]);
+                            const float4 b0 = bias4[ch * 8 + i * 2], b1 = bias4[ch * 8 + i * 2 + 1];   // broadcast LDS.128
+                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&ow[j]);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(
+                                    __uint_as_float(v[i * 8 + 2 * j]) + bb[2 * j] + __low2float(o2),
+                                    __uint_as_float(v[i * 8 + 2 * j + 1]) + bb[2 * j + 1] + __high2float(o2));
+                                pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                            }
+                            *reinterpret_cast<uint4*>(rowp + ((((ch & 1) * 4 + i) ^ (row & 7)) << 4)) =
+                                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                        if ((ch & 3) == 3) {                            // half-tile done: hand it to the storer warp
+                            fence_proxy_async_smem();                   // st.shared -> visible to the TMA store
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&hready_bar[ch >> 2]);
+                        }
+                    }
+                    hph ^= 1;
+                } else {
+#pragma unroll 1
+                    for (int ch = 0; ch < 8; ++ch) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + ch * 32, v);
+                        tmem_ld_wait();
+                        const float4* w4 = reinterpret_cast<const float4*>(s_f32 + (pass * kBlockN + ch * 32) * 8);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float a = __uint_as_float(v[j]);
+                            const float4 w0 = w4[2 * j], w1 = w4[2 * j + 1];
+                            outv[0] = fmaf(a, w0.x, outv[0]);
+                            outv[1] = fmaf(a, w0.y, outv[1]);
+                            outv[2] = fmaf(a, w0.z, outv[2]);
+                            outv[3] = fmaf(a, w0.w, outv[3]);
+                            outv[4] = fmaf(a, w1.x, outv[4]);
+                            outv[5] = fmaf(a, w1.y, outv[5]);
+                            outv[6] = fmaf(a, w1.z, outv[6]);
+                            outv[7] = fmaf(a, w1.w, outv[7]);
+                        }
+                    }
+                }
+                // accumulator stage drained -> hand it back to the leader's MMA thread
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[as], 0));
+            }
+
+            if constexpr (MODE == SKIP_END) if (live) {
+                constexpr int C = 2 * NHALF, BASE = 8 - C;
+                float* xr = p.x + grow * 8;
+                float xv[8];
+                *reinterpret_cast<float4*>(&xv[0]) = *reinterpret_cast<const float4*>(xr);
+                *reinterpret_cast<float4*>(&xv[4]) = *reinterpret_cast<const float4*>(xr + 4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) outv[j] += __ldg(p.b_end + j);
+                if constexpr (DIR == 0) {                        // infer (glow.py:279-282)
+                    float xin[C];
+#pragma unroll
+                    for (int j = 0; j < NHALF; ++j) {
+                        xin[j] = xv[BASE + j];
+                        xin[NHALF + j] = (xv[BASE + NHALF + j] - outv[j]) * expf(-outv[NHALF + j]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < C; ++i) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) acc = fmaf(__ldg(p.w_mix + i * 8 + c), xin[c], acc);
+                        xv[BASE + i] = acc;
+                    }
+                } else {                                         // forward (glow.py:241-246)
+#pragma unroll
+                    for (int j = 0; j < NHALF; ++j) {
+                        const float ls = outv[NHALF + j];
+                        xv[BASE + NHALF + j] = expf(ls) * xv[BASE + NHALF + j] + outv[j];
+                        p.log_s[(static_cast<size_t>(b) * NHALF + j) * p.T + t] = ls;
+                    }
+                }
+                *reinterpret_cast<float4*>(xr) = *reinterpret_cast<const float4*>(&xv[0]);
+                *reinterpret_cast<float4*>(xr + 4) = *reinterpret_cast<const float4*>(&xv[4]);
+            }
         }
     }
 
@@ -270,47 +518,138 @@ gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
     }
 }
 
+// ------------------------------------------------------------------------------------ host side
+
+static int act_map(CUtensorMap* m, const void* base, int channels, int T, int batches) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(channels), static_cast<uint64_t>(T), static_cast<uint64_t>(batches)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(channels) * 2, static_cast<uint64_t>(channels) * 2 * T};
+    const uint32_t box[3] = {kBlockK, kBlockM, 1};
+    return make_tmap_bf16(m, base, 3, dims, strides, box);
+}
+static int weight_half_map(CUtensorMap* m, const void* base, int rows, int k) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(k), static_cast<uint64_t>(rows)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(k) * 2};
+    const uint32_t box[2] = {kBlockK, kHalfN};
+    return make_tmap_bf16(m, base, 2, dims, strides, box);
+}
+
+static int fill_common(Params& p, int batch, int T) {
+    WGB_REQUIRE(batch > 0 && T > 0, "batch (%d) and T (%d) must be positive", batch, T);
+    p.batch = batch;
+    p.T = T;
+    p.tiles_per_b = ceil_div(T, kBlockM);
+    p.n_tiles = batch * p.tiles_per_b;
+    return WGB_OK;
+}
+
+template <int MODE, int NHALF, int DIR>
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& c, const Params& p,
+                  cudaStream_t stream) {
+    constexpr int smem = Smem<MODE>::kTotal;
+    static_assert(smem <= 232448, "dynamic shared memory over the 227 KB per-CTA limit");
+    auto kern = pair_kernel<MODE, NHALF, DIR>;
+    WGB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int n_items = ((p.n_tiles + 1) / 2) * (p.n_pass / p.ppi);
+    int pairs = sm_count() / 2;
+    if (n_items < pairs) pairs = n_items;
+    kern<<<2 * pairs, MODE == RES ? kThreadsRes : kThreads, smem, stream>>>(a0, a1, w, c, p);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
 }  // namespace tc2
 
 int tc2_wn_gate(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts, int batch, int T,
                 int dilation, cudaStream_t stream) {
     using namespace tc2;
     WGB_REQUIRE(h && cond && w_packed && bias && acts, "null pointer");
-    WGB_REQUIRE(batch > 0 && T > 0 && dilation >= 1, "bad shape");
+    WGB_REQUIRE(dilation >= 1, "dilation must be >= 1");
+    Params p{};
+    if (int e = fill_common(p, batch, T)) return e;
+    p.n_pass = 4; p.ppi = 1; p.n_chunks = (3 * kNCh + kNCond) / kBlockK; p.dilation = dilation;
+    p.bias = bias; p.acts_out = static_cast<__nv_bfloat16*>(acts);
+    CUtensorMap mh, mc, mw;
+    if (int e = act_map(&mh, h, kNCh, T, batch)) return e;
+    if (int e = act_map(&mc, cond, kNCond, T, batch)) return e;
+    if (int e = weight_half_map(&mw, w_packed, 2 * kNCh, 3 * kNCh + kNCond)) return e;
+    return launch<GATE, 0, 0>(mh, mc, mw, mh, p, stream);
+}
+
+// Gate layer with the conditioning composed with the upsampler (see GATE_MEL above).  h bf16 [B,T,512] with
+// T = 32 * frames; mel_stack bf16 [B, frames, 320] = the four mel frames feeding each frame's group steps (the
+// upsample im2col); w_packed bf16 [1024][2176] (only the 1536 in_layers columns are read); w_mel bf16
+// [32][1024][320] = per-phase W_cond U_phase in the packed row order; bias fp32 [1024] = b_in + b_cond + W_cond b_up.
+int tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, const void* w_mel, const float* bias,
+                    void* acts, int batch, int T, int dilation, cudaStream_t stream) {
+    using namespace tc2;
+    WGB_REQUIRE(h && mel_stack && w_packed && w_mel && bias && acts, "null pointer");
+    WGB_REQUIRE(dilation >= 1, "dilation must be >= 1");
+    WGB_REQUIRE(batch > 0 && T > 0 && T % kPhases == 0, "T (%d) must be a positive multiple of %d group steps", T, kPhases);
     Params p{};
     p.batch = batch; p.T = T;
-    p.tiles_per_b = ceil_div(T, kBlockM);
-    p.n_tiles = batch * p.tiles_per_b;
-    p.n_pass = 4; p.n_chunks = (3 * kNCh + kNCond) / kBlockK; p.dilation = dilation;
+    p.frames = T / kPhases;
+    p.n_fblk = ceil_div(p.frames, kBlockM);
+    p.tiles_per_b = p.n_fblk;                       // "tiles" = 128-frame blocks; each is visited once per phase and pass
+    p.n_tiles = batch * p.n_fblk;
+    p.n_pass = 4 * kPhases; p.ppi = 1; p.n_chunks = (3 * kNCh + kMelK) / kBlockK; p.dilation = dilation;
     p.bias = bias; p.acts_out = static_cast<__nv_bfloat16*>(acts);
+    CUtensorMap mh, mm, mw, mv;
+    {
+        const uint64_t dims[4] = {kNCh, kPhases, static_cast<uint64_t>(p.frames), static_cast<uint64_t>(batch)};
+        const uint64_t strides[3] = {kNCh * 2, static_cast<uint64_t>(kNCh) * 2 * kPhases, static_cast<uint64_t>(kNCh) * 2 * T};
+        const uint32_t box[4] = {kBlockK, 1, kBlockM, 1};
+        if (int e = make_tmap_bf16(&mh, h, 4, dims, strides, box)) return e;
+    }
+    if (int e = act_map(&mm, mel_stack, kMelK, p.frames, batch)) return e;
+    if (int e = weight_half_map(&mw, w_packed, 2 * kNCh, 3 * kNCh + kNCond)) return e;
+    if (int e = weight_half_map(&mv, w_mel, kPhases * 2 * kNCh, kMelK)) return e;
+    return launch<GATE_MEL, 0, 0>(mh, mm, mw, mv, p, stream);
+}
 
-    CUtensorMap mh, mc, mw;
-    {
-        const uint64_t dims[3] = {kNCh, static_cast<uint64_t>(T), static_cast<uint64_t>(batch)};
-        const uint64_t strides[2] = {kNCh * 2, static_cast<uint64_t>(kNCh) * 2 * T};
-        const uint32_t box[3] = {kBlockK, kBlockM, 1};
-        if (int e = make_tmap_bf16(&mh, h, 3, dims, strides, box)) return e;
+int tc2_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch, int T,
+               cudaStream_t stream) {
+    using namespace tc2;
+    WGB_REQUIRE(acts && w_res && bias && h_in && h_out, "null pointer");
+    Params p{};
+    if (int e = fill_common(p, batch, T)) return e;
+    p.n_pass = 2; p.ppi = 1; p.n_chunks = kNCh / kBlockK;
+    p.bias = bias;
+    CUtensorMap ma, mhi, mho, mw;
+    if (int e = act_map(&ma, acts, kNCh, T, batch)) return e;
+    if (int e = act_map(&mhi, h_in, kNCh, T, batch)) return e;
+    if (int e = act_map(&mho, h_out, kNCh, T, batch)) return e;
+    if (int e = weight_half_map(&mw, w_res, kNCh, kNCh)) return e;
+    return launch<RES, 0, 0>(ma, mhi, mw, mho, p, stream);
+}
+
+int tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end, const float* b_end,
+                    float* x, const float* w_mix, float* log_s, int batch, int T, int n_half, int direction,
+                    cudaStream_t stream) {
+    using namespace tc2;
+    WGB_REQUIRE(acts_all && w_skip && w_end && b_end && x, "null pointer");
+    WGB_REQUIRE(n_layers == 8, "tensor-core skip GEMM is specialised for 8 layers (got %d)", n_layers);
+    WGB_REQUIRE(n_half >= 1 && n_half <= 4, "n_half must be in 1..4 (got %d)", n_half);
+    WGB_REQUIRE(direction == 0 || direction == 1, "direction must be 0 (infer) or 1 (forward)");
+    WGB_REQUIRE(direction == 1 ? log_s != nullptr : w_mix != nullptr, "missing log_s / w_mix for this direction");
+    Params p{};
+    if (int e = fill_common(p, batch, T)) return e;
+    p.n_pass = 2; p.ppi = 2; p.n_chunks = n_layers * kNCh / kBlockK;
+    p.w_end = w_end; p.b_end = b_end; p.x = x; p.w_mix = w_mix; p.log_s = log_s;
+    CUtensorMap ma, mw;
+    if (int e = act_map(&ma, acts_all, kNCh, T, batch * n_layers)) return e;
+    if (int e = weight_half_map(&mw, w_skip, kNCh, n_layers * kNCh)) return e;
+#define WGB_SKIP_CASE(NH)                                                                      \
+    case NH:                                                                                   \
+        return direction == 0 ? launch<SKIP_END, NH, 0>(ma, ma, mw, ma, p, stream)             \
+                              : launch<SKIP_END, NH, 1>(ma, ma, mw, ma, p, stream);
+    switch (n_half) {
+        WGB_SKIP_CASE(1)
+        WGB_SKIP_CASE(2)
+        WGB_SKIP_CASE(3)
+        WGB_SKIP_CASE(4)
     }
-    {
-        const uint64_t dims[3] = {kNCond, static_cast<uint64_t>(T), static_cast<uint64_t>(batch)};
-        const uint64_t strides[2] = {kNCond * 2, static_cast<uint64_t>(kNCond) * 2 * T};
-        const uint32_t box[3] = {kBlockK, kBlockM, 1};
-        if (int e = make_tmap_bf16(&mc, cond, 3, dims, strides, box)) return e;
-    }
-    {
-        const uint64_t k = 3 * kNCh + kNCond;
-        const uint64_t dims[2] = {k, 2 * kNCh};
-        const uint64_t strides[1] = {k * 2};
-        const uint32_t box[2] = {kBlockK, kHalfN};
-        if (int e = make_tmap_bf16(&mw, w_packed, 2, dims, strides, box)) return e;
-    }
-    WGB_CUDA_TRY(cudaFuncSetAttribute(gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    const int n_items = ((p.n_tiles + 1) / 2) * p.n_pass;
-    int pairs = sm_count() / 2;
-    if (n_items < pairs) pairs = n_items;
-    gate_kernel<<<2 * pairs, kThreads, kSmemTotal, stream>>>(mh, mc, mw, p);
-    WGB_LAUNCH_CHECK();
-    return WGB_OK;
+#undef WGB_SKIP_CASE
+    return fail(WGB_ERR_ARGUMENT, "unreachable");
 }
 
 }  // namespace wgb

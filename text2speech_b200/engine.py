@@ -19,8 +19,10 @@ from .packing import PackedWaveGlow
 
 Tensor = torch.Tensor
 
-# Which gate-GEMM kernel the BF16 path uses: "pair" = CTA pairs (tcgen05 cta_group::2), "single" = one CTA per tile.
+# Which tcgen05 kernels the BF16 path uses: "pair" = CTA pairs (cta_group::2, UMMA M = 256), "single" = one CTA per tile.
 GATE_KERNEL = os.environ.get("WGB_GATE_KERNEL", "pair")
+RES_KERNEL = os.environ.get("WGB_RES_KERNEL", "pair")
+SKIP_KERNEL = os.environ.get("WGB_SKIP_KERNEL", "pair")
 
 
 def upsample_cond(pk: PackedWaveGlow, mel: Tensor) -> Tensor:
@@ -45,19 +47,46 @@ def upsample_cond(pk: PackedWaveGlow, mel: Tensor) -> Tensor:
     return cond.view(b, f * t_per_frame, n_cols // t_per_frame)
 
 
-def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond: Tensor, bufs, direction: int, log_s: Optional[Tensor]):
+def mel_stack(pk: PackedWaveGlow, mel: Tensor) -> Tensor:
+    """mel [B, n_mel, F] fp32 -> bf16 [B, F, 4*n_mel]: the four frames feeding each frame's group steps (the A operand
+    of the upsample GEMM without channel padding), K operand of the composed conditioning in wgb_tc2_wn_gate_mel."""
+    b, n_mel, f = mel.shape
+    a = torch.empty((b, f, pk.up_taps * n_mel), device=mel.device, dtype=torch.bfloat16)
+    _lib.call("wgb_upsample_im2col", mel, a, 1, b, n_mel, f, pk.up_taps, n_mel, _lib.stream_ptr())
+    return a
+
+
+def use_mel_path(pk: PackedWaveGlow, frames: int, t: int) -> bool:
+    """Composed conditioning (K = 1856, rows tiled 128 frames x 1 phase) vs the cond tensor (K = 2176, rows tiled
+    128 group steps): pick the one that executes fewer MMA chunks for this length ('auto'), or as forced."""
+    if pk.mode != "bf16" or not pk.has_mel or pk.cond_path == "cond" or GATE_KERNEL != "pair":
+        return False
+    if t != frames * 32:                      # forward() with audio shorter than 256 * frames
+        return False
+    if pk.cond_path == "mel":
+        return True
+    return -(-frames // 128) * 32 * 29 < -(-t // 128) * 34
+
+
+def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int, log_s: Optional[Tensor]):
     b, t = x.shape[0], x.shape[1]
     s = _lib.stream_ptr()
     h0, h1, acts_all = bufs
     gate = "wgb_tc2_wn_gate" if GATE_KERNEL == "pair" else "wgb_tc_wn_gate"
+    res = "wgb_tc2_wn_res" if RES_KERNEL == "pair" else "wgb_tc_wn_res"
+    skip_end = "wgb_tc2_wn_skip_end" if SKIP_KERNEL == "pair" else "wgb_tc_wn_skip_end"
     _lib.call("wgb_wn_start", x, fl["w_start"], fl["b_start"], h0, 1, b * t, pk.n_ch, fl["n_half"], s)
     cur, nxt = h0, h1
     for i in range(pk.n_layers):
-        _lib.call(gate, cur, cond, fl["w_gate"][i], fl["b_gate"][i], acts_all[i], b, t, 2 ** i, s)
+        if isinstance(cond, tuple):           # ("mel", mel_stack): conditioning composed with the upsampler
+            _lib.call("wgb_tc2_wn_gate_mel", cur, cond[1], fl["w_gate"][i], fl["w_mel"][i], fl["b_mel"][i], acts_all[i],
+                      b, t, 2 ** i, s)
+        else:
+            _lib.call(gate, cur, cond, fl["w_gate"][i], fl["b_gate"][i], acts_all[i], b, t, 2 ** i, s)
         if i < pk.n_layers - 1:
-            _lib.call("wgb_tc_wn_res", acts_all[i], fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, s)
+            _lib.call(res, acts_all[i], fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, s)
             cur, nxt = nxt, cur
-    _lib.call("wgb_tc_wn_skip_end", acts_all, pk.n_layers, fl["w_skip"], fl["w_end_t"], fl["b_end"], x,
+    _lib.call(skip_end, acts_all, pk.n_layers, fl["w_skip"], fl["w_end_t"], fl["b_end"], x,
               fl["w_mix_inv"] if direction == 0 else None, log_s, b, t, fl["n_half"], direction, s)
 
 
@@ -110,7 +139,7 @@ def infer(pk: PackedWaveGlow, mel: Tensor, z: Tensor, sigma: float) -> Tensor:
     b, _, f = mel.shape
     t = f * pk.up_stride // pk.n_group
     s = _lib.stream_ptr()
-    cond = upsample_cond(pk, mel)
+    cond = ("mel", mel_stack(pk, mel)) if use_mel_path(pk, f, t) else upsample_cond(pk, mel)
     x = torch.empty((b, t, pk.n_group), device=mel.device, dtype=torch.float32)
     _lib.call("wgb_flow_from_z", z, x, b, t, float(sigma), s)
     bufs = _alloc(pk, b, t, mel.device)
@@ -127,11 +156,14 @@ def forward(pk: PackedWaveGlow, mel: Tensor, audio: Tensor) -> Tuple[Tensor, Lis
     assert up_len >= n, "upsampled spectrogram shorter than audio"            # glow.py:216
     t = n // pk.n_group
     s = _lib.stream_ptr()
-    cond = upsample_cond(pk, mel)
-    if cond.shape[1] < t:
+    if t > f * pk.up_stride // pk.n_group:
         raise RuntimeError("audio longer than 256 * frames is not supported by the regrouped upsample GEMM")
-    if cond.shape[1] > t:
-        cond = cond[:, :t].contiguous()                                       # glow.py:217-218
+    if use_mel_path(pk, f, t):
+        cond = ("mel", mel_stack(pk, mel))
+    else:
+        cond = upsample_cond(pk, mel)
+        if cond.shape[1] > t:
+            cond = cond[:, :t].contiguous()                                   # glow.py:217-218
     x = audio[:, : t * pk.n_group].reshape(b, t, pk.n_group).float().contiguous().clone()
     bufs = _alloc(pk, b, t, mel.device)
     log_s_list, log_det_list = [], []

@@ -130,6 +130,8 @@ class WaveGlow(torch.nn.Module):
             self.WN.append(WN(n_half, n_mel_channels * n_group, **WN_config))
         self.n_remaining_channels = n_remaining_channels
         self.mode = "bf16"
+        # 'auto' | 'mel' | 'cond': how the bf16 gate GEMM gets its conditioning (engine.use_mel_path)
+        self.cond_path = "auto"
         self._pack_cache = {}
         self._attach()
 
@@ -141,6 +143,7 @@ class WaveGlow(torch.nn.Module):
     def __setstate__(self, state):          # pickled-module checkpoints (waveglow/inference.py:37)
         super().__setstate__(state)
         self.__dict__.setdefault("mode", "bf16")
+        self.__dict__.setdefault("cond_path", "auto")
         self.__dict__["_pack_cache"] = {}
         self._attach()
 
@@ -170,6 +173,7 @@ class WaveGlow(torch.nn.Module):
                                 self.mode, device)
             self._pack_cache = {key: (sig, pk)}
             hit = self._pack_cache[key]
+        hit[1].cond_path = self.cond_path
         return hit[1]
 
     def repack(self):

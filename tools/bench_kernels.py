@@ -1,0 +1,137 @@
+"""A/B timing of the WN kernels on ONE GPU in ONE process (box-to-box clock variance is +-5 %, so variants
+must be compared inside the same run).  Each variant is looped for ~`--seconds` back to back (steady state
+under the power cap), timed with CUDA events; board power and SM clock are sampled through NVML meanwhile.
+
+    python tools/bench_kernels.py [--batch 64] [--frames 860] [--seconds 1.5] [--out gpurun_out/kernels.json]
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from text2speech_b200 import _lib, synthetic as syn          # noqa: E402
+from text2speech_b200.packing import PackedWaveGlow          # noqa: E402
+
+DEV = torch.device("cuda:0")
+
+
+class Nvml:
+    def __init__(self):
+        self.rows, self.stop, self.h = [], False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+        except Exception:                                     # noqa: BLE001
+            self.nv = None
+
+    def __enter__(self):
+        self.rows, self.stop = [], False
+        if self.nv:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def _run(self):
+        while not self.stop:
+            try:
+                self.rows.append((self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                  self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            except Exception:                                 # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def __exit__(self, *exc):
+        self.stop = True
+        if self.nv:
+            self.t.join()
+
+    def summary(self):
+        rows = self.rows[len(self.rows) // 3:]                # steady state: drop the first third
+        if not rows:
+            return {"power_w": None, "sm_mhz": None}
+        return {"power_w": round(sum(r[0] for r in rows) / len(rows), 1),
+                "sm_mhz": round(sum(r[1] for r in rows) / len(rows), 1)}
+
+
+def loop(fn, seconds):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        fn()
+    e1.record()
+    e1.synchronize()
+    n = max(5, int(seconds * 1e3 / (e0.elapsed_time(e1) / 3)))
+    with Nvml() as nv:
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        e1.synchronize()
+    return e0.elapsed_time(e1) / n, n, nv.summary()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=860)
+    ap.add_argument("--seconds", type=float, default=1.5)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernels.json"))
+    args = ap.parse_args()
+    b, t = args.batch, args.frames * 32
+    cfg = syn.load_config()
+    pk = PackedWaveGlow(syn.synthetic_state_dict(cfg, seed=1234, end_std=0.01), 12, 8, 512, 8, "bf16", DEV)
+    fl = pk.flows[3]
+    s = _lib.stream_ptr()
+    bf = torch.bfloat16
+    h0 = torch.randn((b, t, 512), device=DEV).to(bf)
+    h1 = torch.empty_like(h0)
+    cond = torch.randn((b, t, 640), device=DEV).to(bf)
+    acts_all = (torch.rand((8, b, t, 512), device=DEV) * 2 - 1).to(bf)
+    x = torch.randn((b, t, 8), device=DEV)
+    steps = b * t
+    gate_flop, res_flop, skip_flop = 2 * 2176 * 1024 * steps, 2 * 512 * 512 * steps, 2 * 4096 * 512 * steps
+    variants = []
+    for name in ("wgb_tc_wn_gate", "wgb_tc2_wn_gate"):
+        for d in (1, 128):
+            variants.append((f"{name} d={d}", gate_flop, 3328 * steps,
+                             lambda name=name, d=d: _lib.call(name, h0, cond, fl["w_gate"][2], fl["b_gate"][2], acts_all[2], b, t, d, s)))
+    for name in ("wgb_tc_wn_res", "wgb_tc2_wn_res"):
+        variants.append((name, res_flop, 3072 * steps,
+                         lambda name=name: _lib.call(name, acts_all[2], fl["w_res"][2], fl["b_res"][2], h0, h1, b, t, s)))
+    for name in ("wgb_tc_wn_skip_end", "wgb_tc2_wn_skip_end"):
+        variants.append((name, skip_flop, (8 * 1024 + 64) * steps,
+                         lambda name=name: _lib.call(name, acts_all, 8, fl["w_skip"], fl["w_end_t"], fl["b_end"], x,
+                                                     fl["w_mix_inv"], None, b, t, fl["n_half"], 0, s)))
+    variants.append(("wgb_wn_start", 0, (32 + 1024) * steps,
+                     lambda: _lib.call("wgb_wn_start", x, fl["w_start"], fl["b_start"], h0, 1, b * t, 512, fl["n_half"], s)))
+    out = []
+    for name, flop, bytes_, fn in variants:
+        if args.only and args.only not in name:
+            continue
+        ms, n, nv = loop(fn, args.seconds)
+        rec = {"kernel": name, "ms": round(ms, 4), "iters": n, "tflops": round(flop / ms / 1e9, 1) if flop else None,
+               "algorithmic_gb_s": round(bytes_ / ms / 1e6, 1), **nv}
+        if nv["power_w"]:
+            rec["joule_per_launch"] = round(nv["power_w"] * ms * 1e-3, 3)
+            if flop and nv["sm_mhz"]:
+                rec["frac_of_clock_peak"] = round(flop / (ms * 1e-3) / (148 * 8192 * nv["sm_mhz"] * 1e6), 3)
+        out.append(rec)
+        print(json.dumps(rec), flush=True)
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
