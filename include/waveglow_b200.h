@@ -86,12 +86,26 @@ WGB_API int wgb_tc2_wn_gate_mel(const void* h, const void* mel_stack, const void
                                 const float* bias, void* acts, int batch, int T, int dilation, void* stream);
 
 /* CTA-pair (cta_group::2) forms of the two entry points above, same contracts: each CTA loads half of every
- * weight tile, the pair issues one M = 256 MMA (half the weight traffic from L2 / shared memory per FLOP). */
+ * weight tile, the pair issues one M = 256 MMA (half the weight traffic from L2 / shared memory per FLOP).
+ * wgb_tc2_wn_skip_end can also run WN.start of the NEXT flow of WaveGlow.infer (glow.py:156 for flow k-1) on the
+ * rows it has just updated: h_next bf16 [B,T,512] = next_w_start fp32 [512][next_n_half] applied to that flow's
+ * audio_0 channels + next_b_start fp32 [512]; pass h_next = NULL (and NULL / 0 for the rest) to skip it. */
 WGB_API int wgb_tc2_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out,
                            int batch, int T, void* stream);
 WGB_API int wgb_tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end,
                                 const float* b_end, float* x, const float* w_mix, float* log_s, int batch, int T,
-                                int n_half, int direction, void* stream);
+                                int n_half, int direction, const float* next_w_start, const float* next_b_start,
+                                int next_n_half, void* h_next, void* stream);
+
+/* Skip path and WN.end composed (glow.py:167-175 are linear with nothing in between): one skinny tcgen05 GEMM of
+ * acts_all bf16 [n_layers][B][T][512] against w16 bf16 [16][n_layers*512] = the bf16 hi (rows 0..7) and lo (rows 8..15)
+ * parts of W_end [W_skip_0 | ... | W_skip_7] (zero rows beyond 2*n_half), b_end fp32 [8] with the skip biases folded
+ * in; then the same coupling / W^-1 / log_s / optional next-flow WN.start epilogue as wgb_tc2_wn_skip_end.
+ * HBM-bound: 8 KB of activations per group step, 2*4096*16 tensor FLOPs instead of 2*4096*512. */
+WGB_API int wgb_tc_wn_skip16_end(const void* acts_all, int n_layers, const void* w16, const float* b_end, float* x,
+                                 const float* w_mix, float* log_s, int batch, int T, int n_half, int direction,
+                                 const float* next_w_start, const float* next_b_start, int next_n_half, void* h_next,
+                                 void* stream);
 
 /* Plain tcgen05 GEMM with the same TMA/TMEM pipeline: C[b,t,n] = sum_k A[b,t,k] W[n,k] + bias[n];
  * A bf16 [B,T,K] (K % 64 == 0), W bf16 [N,K] (N % 256 == 0), C fp32 or bf16 [B,T,N]; bias may be NULL.

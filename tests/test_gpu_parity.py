@@ -115,7 +115,7 @@ def test_tc_res_layer(lib, packed_q, entry, B, T):
     assert err <= util.TOL_LAYER_BF16, err
 
 
-@pytest.mark.parametrize("entry", ["wgb_tc_wn_skip_end", "wgb_tc2_wn_skip_end"])
+@pytest.mark.parametrize("entry", ["wgb_tc_wn_skip_end", "wgb_tc2_wn_skip_end", "wgb_tc_wn_skip16_end"])
 @pytest.mark.parametrize("k,direction", [(11, 0), (5, 0), (0, 0), (11, 1), (4, 1), (1, 1)])
 def test_tc_skip_end_coupling(lib, packed_q, k, direction, entry):
     """skip sum over 8 layers + WN.end + affine coupling (+ W^-1)  (glow.py:171-175, :277-282 / :241-246)."""
@@ -145,9 +145,29 @@ def test_tc_skip_end_coupling(lib, packed_q, k, direction, entry):
     xd = x.to(DEV).contiguous()
     log_s = torch.zeros(B, n_half, T, device=DEV) if direction == 1 else None
     acts_all = acts.permute(0, 1, 3, 2).contiguous().to(DEV, torch.bfloat16)
-    lib.call(entry, acts_all, 8, fl["w_skip"], fl["w_end_t"], fl["b_end"], xd,
-             fl["w_mix_inv"] if direction == 0 else None, log_s, B, T, n_half, direction, lib.stream_ptr())
+    args = (acts_all, 8, fl["w_skip"], fl["w_end_t"], fl["b_end"], xd,
+            fl["w_mix_inv"] if direction == 0 else None, log_s, B, T, n_half, direction)
+    h_next = None
+    if entry == "wgb_tc_wn_skip16_end":          # WN.end composed with the skip GEMM (hi/lo bf16 split of the product)
+        args = (acts_all, 8, fl["w_skip16"], fl["b_end"], xd, fl["w_mix_inv"] if direction == 0 else None, log_s, B, T,
+                n_half, direction)
+    if entry != "wgb_tc_wn_skip_end":
+        if direction == 0 and k > 0:             # also run WN.start of flow k-1 on the updated rows (glow.py:156)
+            nf = pk.flows[k - 1]
+            h_next = torch.zeros(B, T, 512, device=DEV, dtype=torch.bfloat16)
+            lib.call(entry, *args, nf["w_start"], nf["b_start"], nf["n_half"], h_next, lib.stream_ptr())
+        else:
+            lib.call(entry, *args, None, None, 0, None, lib.stream_ptr())
+    else:
+        lib.call(entry, *args, lib.stream_ptr())
     torch.cuda.synchronize()
+    if h_next is not None:
+        nh = pk.flows[k - 1]["n_half"]
+        nb = 8 - 2 * nh
+        a0 = xd.cpu()[:, :, nb: nb + nh]                                        # the kernel's own updated x
+        w, bias = st[f"WN.{k - 1}.start.weight"][:, :, 0], st[f"WN.{k - 1}.start.bias"]
+        want_h = a0 @ w.t() + bias
+        assert util.rel_l2(h_next.float().cpu(), want_h) <= util.TOL_LAYER_BF16
     assert util.rel_l2(xd.cpu()[:, :, base:], want[:, :, base:]) <= 1e-4
     assert torch.equal(xd.cpu()[:, :, :base], x[:, :, :base])           # early channels untouched
     if direction == 1:

@@ -112,3 +112,32 @@ def test_cond_mel_composition_matches_cond_layer_of_upsampled_mel():
     want = torch.nn.functional.conv1d(cond, st[p + f"cond_layers.{i}.weight"], st[p + f"cond_layers.{i}.bias"])
     want = (want + st[p + f"in_layers.{i}.bias"][None, :, None])[:, gate_row_order(512)].permute(0, 2, 1)
     assert util.rel_l2(got, want) < 1e-5
+
+
+def test_skip_end_composition_matches_skip_sum_then_end():
+    """pack_skip_end16: end(sum_i skip_i) == (W_end W_skip) . acts + folded bias, hi + lo parts sum to the product."""
+    from text2speech_b200.packing import pack_end, pack_skip, pack_skip_end16
+    st = oracle.folded_state(util.state_dict("stress"))
+    k, bsz, t = 6, 2, 40
+    p = f"WN.{k}."
+    w_rs = [st[p + f"res_skip_layers.{i}.weight"] for i in range(8)]
+    b_rs = [st[p + f"res_skip_layers.{i}.bias"] for i in range(8)]
+    w_skip, b_skip = pack_skip(w_rs, b_rs, 512)
+    w_end, b_end = st[p + "end.weight"], st[p + "end.bias"]
+    _, _, b_fold = pack_end(w_end, b_end, b_skip)
+    w16 = pack_skip_end16(w_skip, w_end)
+    assert w16.shape == (16, 4096) and w16.dtype == torch.bfloat16
+    comp = (w16[:8].double() + w16[8:].double())
+    rows = w_end.shape[0]
+    exact = w_end[:, :, 0].double() @ w_skip.double()
+    assert float((comp[:rows] - exact).abs().max() / exact.abs().max()) < 2e-5 and float(comp[rows:].abs().max()) == 0.0
+    g = torch.Generator().manual_seed(3)
+    acts = torch.rand(8, bsz, 512, t, generator=g) * 2 - 1
+    total = 0
+    for i in range(8):
+        lo = 0 if i == 7 else 512
+        total = total + torch.nn.functional.conv1d(acts[i], w_rs[i][lo: lo + 512], b_rs[i][lo: lo + 512])
+    want = torch.nn.functional.conv1d(total, w_end, b_end)                                   # [B, 2n_half, T]
+    a_cat = acts.permute(1, 3, 0, 2).reshape(bsz, t, 4096).double()                          # K index = layer*512 + c
+    got = (a_cat @ comp.t())[:, :, :rows] + b_fold[:rows].double()
+    assert util.rel_l2(got.permute(0, 2, 1), want) < 1e-5

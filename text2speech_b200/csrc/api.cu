@@ -18,7 +18,10 @@ int tc2_wn_gate(const void*, const void*, const void*, const float*, void*, int,
 int tc2_wn_res(const void*, const void*, const float*, const void*, void*, int, int, cudaStream_t);
 int tc2_wn_gate_mel(const void*, const void*, const void*, const void*, const float*, void*, int, int, int, cudaStream_t);
 int tc2_wn_skip_end(const void*, int, const void*, const float*, const float*, float*, const float*, float*, int, int,
-                    int, int, cudaStream_t);
+                    int, int, const float*, const float*, int, void*, cudaStream_t);
+// wn_skip16.cu
+int tc_wn_skip16_end(const void*, int, const void*, const float*, float*, const float*, float*, int, int, int, int,
+                     const float*, const float*, int, void*, cudaStream_t);
 // ref_f32.cu
 int sgemm_nt(const float*, const float*, const float*, void*, int, int, int, int, int, long long, long long, long long,
              long long, long long, int, int, cudaStream_t);
@@ -93,9 +96,17 @@ WGB_API int wgb_tc2_wn_res(const void* acts, const void* w_res, const float* bia
 }
 WGB_API int wgb_tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end,
                                 const float* b_end, float* x, const float* w_mix, float* log_s, int batch, int T,
-                                int n_half, int direction, void* stream) {
+                                int n_half, int direction, const float* next_w_start, const float* next_b_start,
+                                int next_n_half, void* h_next, void* stream) {
     return tc2_wn_skip_end(acts_all, n_layers, w_skip, w_end, b_end, x, w_mix, log_s, batch, T, n_half, direction,
-                           S(stream));
+                           next_w_start, next_b_start, next_n_half, h_next, S(stream));
+}
+WGB_API int wgb_tc_wn_skip16_end(const void* acts_all, int n_layers, const void* w16, const float* b_end, float* x,
+                                 const float* w_mix, float* log_s, int batch, int T, int n_half, int direction,
+                                 const float* next_w_start, const float* next_b_start, int next_n_half, void* h_next,
+                                 void* stream) {
+    return tc_wn_skip16_end(acts_all, n_layers, w16, b_end, x, w_mix, log_s, batch, T, n_half, direction, next_w_start,
+                            next_b_start, next_n_half, h_next, S(stream));
 }
 WGB_API int wgb_tc_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch,
                   int T, void* stream) {

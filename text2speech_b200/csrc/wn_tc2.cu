@@ -52,13 +52,14 @@ constexpr int kMelK = 320;           // 4 upsample taps x 80 mel channels
 // Shared memory (offsets from a 1024 B aligned base): [TMA ring][mode extra][barriers]
 //   GATE      6 stages + 4 KB bias (sigmoid half pre-halved)
 //   RES       4 stages + 64 KB h tile + 2 KB bias
-//   SKIP_END  6 stages + 16 KB W_end^T
+//   SKIP_END  6 stages + 16 KB W_end^T + 10 KB WN.start weights of the next flow
 template <int MODE>
 struct Smem {
     static constexpr int kStages = MODE == RES ? 4 : 6;
     static constexpr int kExtraOff = kStages * kStageBytes;
     static constexpr int kExtraBytes =
-        (MODE == GATE || MODE == GATE_MEL) ? 2 * kNCh * 4 : (MODE == RES ? kBlockM * kBlockN * 2 + kNCh * 4 : kNCh * 8 * 4);
+        (MODE == GATE || MODE == GATE_MEL) ? 2 * kNCh * 4
+                                           : (MODE == RES ? kBlockM * kBlockN * 2 + kNCh * 4 : kNCh * 8 * 4 + kNCh * 5 * 4);
     static constexpr int kBarOff = kExtraOff + kExtraBytes;
     static constexpr int kTotal = 1024 + kBarOff + 256;
 };
@@ -74,6 +75,12 @@ struct Params {
     float* x;                     // SKIP_END flow state [B,T,8]
     const float* w_mix;           // SKIP_END infer: W^-1 [8][8]
     float* log_s;                 // SKIP_END forward: [B,n_half,T]
+    // SKIP_END infer, optional: WN.start of the NEXT flow to run (glow.py:156 of flow k-1) fused behind the
+    // coupling: h_next[b,t,:] = W[512][n_half_next] x_new[a0 channels of that flow] + b
+    const float* next_w_start;
+    const float* next_b_start;
+    __nv_bfloat16* h_next;
+    int next_n_half;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -197,6 +204,12 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             for (int i = i0; i < kNCh; i += 128) s_rbias[i] = p.bias[i];
         } else {
             for (int i = i0; i < kNCh * 8; i += 128) s_f32[i] = p.w_end[i];
+            if (p.h_next) {                       // [512][4] zero-padded weight rows, then [512] bias
+                float* s_ws = s_f32 + kNCh * 8;
+                for (int i = i0; i < kNCh * 4; i += 128)
+                    s_ws[i] = (i & 3) < p.next_n_half ? p.next_w_start[(i >> 2) * p.next_n_half + (i & 3)] : 0.f;
+                for (int i = i0; i < kNCh; i += 128) s_ws[kNCh * 4 + i] = p.next_b_start[i];
+            }
         }
     }
     tc_fence_before_sync();
@@ -504,6 +517,37 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 }
                 *reinterpret_cast<float4*>(xr) = *reinterpret_cast<const float4*>(&xv[0]);
                 *reinterpret_cast<float4*>(xr + 4) = *reinterpret_cast<const float4*>(&xv[4]);
+                if constexpr (DIR == 0) if (p.h_next) {
+                    // WN.start of the next flow on the freshly updated row: its a0 = the first next_n_half of its
+                    // last 2*next_n_half channels.  Overlaps the MMAs of the next tile (both TMEM stages are free).
+                    const int nb = 8 - 2 * p.next_n_half;
+                    float a0[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v = (i == nb + j) ? xv[i] : v;
+                        a0[j] = v;                                  // weight columns >= next_n_half are zero
+                    }
+                    const float4* ws4 = reinterpret_cast<const float4*>(s_f32 + kNCh * 8);
+                    const float4* bs4 = ws4 + kNCh;
+                    uint4* dst = reinterpret_cast<uint4*>(p.h_next + grow * kNCh);
+#pragma unroll 2
+                    for (int c8 = 0; c8 < kNCh / 8; ++c8) {
+                        const float4 b0 = bs4[2 * c8], b1 = bs4[2 * c8 + 1];
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 w0 = ws4[c8 * 8 + 2 * j], w1 = ws4[c8 * 8 + 2 * j + 1];
+                            const float v0 = fmaf(w0.w, a0[3], fmaf(w0.z, a0[2], fmaf(w0.y, a0[1], fmaf(w0.x, a0[0], bb[2 * j]))));
+                            const float v1 = fmaf(w1.w, a0[3], fmaf(w1.z, a0[2], fmaf(w1.y, a0[1], fmaf(w1.x, a0[0], bb[2 * j + 1]))));
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        dst[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
             }
         }
     }
@@ -624,6 +668,7 @@ int tc2_wn_res(const void* acts, const void* w_res, const float* bias, const voi
 
 int tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end, const float* b_end,
                     float* x, const float* w_mix, float* log_s, int batch, int T, int n_half, int direction,
+                    const float* next_w_start, const float* next_b_start, int next_n_half, void* h_next,
                     cudaStream_t stream) {
     using namespace tc2;
     WGB_REQUIRE(acts_all && w_skip && w_end && b_end && x, "null pointer");
@@ -635,6 +680,12 @@ int tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, cons
     if (int e = fill_common(p, batch, T)) return e;
     p.n_pass = 2; p.ppi = 2; p.n_chunks = n_layers * kNCh / kBlockK;
     p.w_end = w_end; p.b_end = b_end; p.x = x; p.w_mix = w_mix; p.log_s = log_s;
+    if (h_next) {
+        WGB_REQUIRE(direction == 0, "the fused WN.start of the next flow exists for the infer direction only");
+        WGB_REQUIRE(next_w_start && next_b_start && next_n_half >= 1 && next_n_half <= 4, "bad next-flow start arguments");
+        p.next_w_start = next_w_start; p.next_b_start = next_b_start; p.next_n_half = next_n_half;
+        p.h_next = static_cast<__nv_bfloat16*>(h_next);
+    }
     CUtensorMap ma, mw;
     if (int e = act_map(&ma, acts_all, kNCh, T, batch * n_layers)) return e;
     if (int e = weight_half_map(&mw, w_skip, kNCh, n_layers * kNCh)) return e;

@@ -22,7 +22,11 @@ Tensor = torch.Tensor
 # Which tcgen05 kernels the BF16 path uses: "pair" = CTA pairs (cta_group::2, UMMA M = 256), "single" = one CTA per tile.
 GATE_KERNEL = os.environ.get("WGB_GATE_KERNEL", "pair")
 RES_KERNEL = os.environ.get("WGB_RES_KERNEL", "pair")
-SKIP_KERNEL = os.environ.get("WGB_SKIP_KERNEL", "pair")
+# skip path: "skip16" = WN.end composed with the skip GEMM (one N = 16 sweep, HBM-bound); "pair" / "single" = the
+# K = 4096 x N = 512 GEMM with WN.end in the epilogue
+SKIP_KERNEL = os.environ.get("WGB_SKIP_KERNEL", "skip16")
+# infer: run WN.start of flow k-1 inside the skip+end kernel of flow k (one launch and one pass over x less per flow)
+FUSE_START = os.environ.get("WGB_FUSE_START", "1") == "1"
 
 
 def upsample_cond(pk: PackedWaveGlow, mel: Tensor) -> Tensor:
@@ -68,14 +72,19 @@ def use_mel_path(pk: PackedWaveGlow, frames: int, t: int) -> bool:
     return -(-frames // 128) * 32 * 29 < -(-t // 128) * 34
 
 
-def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int, log_s: Optional[Tensor]):
+def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int, log_s: Optional[Tensor],
+             start_done: bool = False, next_fl: Optional[dict] = None) -> bool:
+    """One WN + coupling.  start_done: h0 already holds WN.start(x) (written by the previous flow's skip+end kernel);
+    next_fl: the flow that runs next in infer order, whose WN.start the pair skip+end kernel fuses behind the
+    coupling.  Returns True when that fused start was issued."""
     b, t = x.shape[0], x.shape[1]
     s = _lib.stream_ptr()
     h0, h1, acts_all = bufs
     gate = "wgb_tc2_wn_gate" if GATE_KERNEL == "pair" else "wgb_tc_wn_gate"
     res = "wgb_tc2_wn_res" if RES_KERNEL == "pair" else "wgb_tc_wn_res"
     skip_end = "wgb_tc2_wn_skip_end" if SKIP_KERNEL == "pair" else "wgb_tc_wn_skip_end"
-    _lib.call("wgb_wn_start", x, fl["w_start"], fl["b_start"], h0, 1, b * t, pk.n_ch, fl["n_half"], s)
+    if not start_done:
+        _lib.call("wgb_wn_start", x, fl["w_start"], fl["b_start"], h0, 1, b * t, pk.n_ch, fl["n_half"], s)
     cur, nxt = h0, h1
     for i in range(pk.n_layers):
         if isinstance(cond, tuple):           # ("mel", mel_stack): conditioning composed with the upsampler
@@ -86,8 +95,21 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int
         if i < pk.n_layers - 1:
             _lib.call(res, acts_all[i], fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, s)
             cur, nxt = nxt, cur
-    _lib.call(skip_end, acts_all, pk.n_layers, fl["w_skip"], fl["w_end_t"], fl["b_end"], x,
-              fl["w_mix_inv"] if direction == 0 else None, log_s, b, t, fl["n_half"], direction, s)
+    args = (acts_all, pk.n_layers, fl["w_skip"], fl["w_end_t"], fl["b_end"], x,
+            fl["w_mix_inv"] if direction == 0 else None, log_s, b, t, fl["n_half"], direction)
+    if SKIP_KERNEL == "single":
+        _lib.call(skip_end, *args, s)
+        return False
+    fuse = direction == 0 and next_fl is not None and FUSE_START
+    if SKIP_KERNEL == "skip16":
+        skip_end = "wgb_tc_wn_skip16_end"
+        args = (acts_all, pk.n_layers, fl["w_skip16"], fl["b_end"], x,
+                fl["w_mix_inv"] if direction == 0 else None, log_s, b, t, fl["n_half"], direction)
+    if fuse:
+        _lib.call(skip_end, *args, next_fl["w_start"], next_fl["b_start"], next_fl["n_half"], h0, s)
+    else:
+        _lib.call(skip_end, *args, None, None, 0, None, s)
+    return fuse
 
 
 def _wn_fp32(pk: PackedWaveGlow, fl: dict, x: Tensor, cond: Tensor, bufs, direction: int, log_s: Optional[Tensor]):
@@ -130,8 +152,13 @@ def _alloc(pk: PackedWaveGlow, b: int, t: int, device):
             torch.empty((b, t, pk.n_ch), device=device, dtype=f32))
 
 
-def run_wn(pk: PackedWaveGlow, k: int, x: Tensor, cond: Tensor, bufs, direction: int, log_s: Optional[Tensor]):
-    (_wn_bf16 if pk.mode == "bf16" else _wn_fp32)(pk, pk.flows[k], x, cond, bufs, direction, log_s)
+def run_wn(pk: PackedWaveGlow, k: int, x: Tensor, cond: Tensor, bufs, direction: int, log_s: Optional[Tensor],
+           start_done: bool = False, next_k: Optional[int] = None) -> bool:
+    if pk.mode == "bf16":
+        return _wn_bf16(pk, pk.flows[k], x, cond, bufs, direction, log_s, start_done,
+                        pk.flows[next_k] if next_k is not None else None)
+    _wn_fp32(pk, pk.flows[k], x, cond, bufs, direction, log_s)
+    return False
 
 
 def infer(pk: PackedWaveGlow, mel: Tensor, z: Tensor, sigma: float) -> Tensor:
@@ -143,8 +170,9 @@ def infer(pk: PackedWaveGlow, mel: Tensor, z: Tensor, sigma: float) -> Tensor:
     x = torch.empty((b, t, pk.n_group), device=mel.device, dtype=torch.float32)
     _lib.call("wgb_flow_from_z", z, x, b, t, float(sigma), s)
     bufs = _alloc(pk, b, t, mel.device)
+    start_done = False
     for k in reversed(range(pk.n_flows)):
-        run_wn(pk, k, x, cond, bufs, 0, None)
+        start_done = run_wn(pk, k, x, cond, bufs, 0, None, start_done, k - 1 if k > 0 else None)
     return x.view(b, t * pk.n_group)
 
 

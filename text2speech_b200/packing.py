@@ -84,6 +84,19 @@ def pack_end(w_end: Tensor, b_end: Tensor, b_skip_total: Tensor):
     return w_t.contiguous(), plain, fold.float()
 
 
+def pack_skip_end16(w_skip: Tensor, w_end: Tensor):
+    """Compose WN.end with the skip GEMM (both linear, glow.py:167-175): W_end [2n_half,512] @ W_skip [512, L*512]
+    -> [8, L*512] (zero rows beyond 2*n_half), computed in fp64 and split into bf16 hi / lo parts stacked as
+    [16, L*512] (rows 0..7 hi, 8..15 lo): the N = 16 operand of wgb_tc_wn_skip16_end."""
+    rows = w_end.shape[0]
+    comp = torch.zeros(8, w_skip.shape[1], dtype=torch.float64)
+    comp[:rows] = w_end[:, :, 0].double() @ w_skip.double()
+    comp = comp.float()
+    hi = comp.bfloat16()
+    lo = (comp - hi.float()).bfloat16()
+    return torch.cat([hi, lo], dim=0).contiguous()
+
+
 def pack_mix(w: Tensor):
     """convinv weight [C,C,1] -> (W [8,8] fp32, W^-1 [8,8] fp32 via fp64, log|det W| python float).
     The reference inverts in fp32 and caches (glow.py:88-95); fp64 here is strictly more accurate."""
@@ -162,6 +175,7 @@ class PackedWaveGlow:
             if mode == "bf16":
                 f["b_end"] = b_fold.to(dev)
                 f["w_skip"] = w_skip.to(dev, bf)
+                f["w_skip16"] = pack_skip_end16(w_skip, w_end).to(dev)
                 f["w_gate"], f["b_gate"], f["w_res"], f["b_res"], f["w_mel"], f["b_mel"] = [], [], [], [], [], []
                 for i in range(n_layers):
                     wg, bg = pack_gate(st[p + f"in_layers.{i}.weight"], st[p + f"in_layers.{i}.bias"],

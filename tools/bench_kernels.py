@@ -109,10 +109,25 @@ def main():
     for name in ("wgb_tc_wn_res", "wgb_tc2_wn_res"):
         variants.append((name, res_flop, 3072 * steps,
                          lambda name=name: _lib.call(name, acts_all[2], fl["w_res"][2], fl["b_res"][2], h0, h1, b, t, s)))
-    for name in ("wgb_tc_wn_skip_end", "wgb_tc2_wn_skip_end"):
-        variants.append((name, skip_flop, (8 * 1024 + 64) * steps,
-                         lambda name=name: _lib.call(name, acts_all, 8, fl["w_skip"], fl["w_end_t"], fl["b_end"], x,
-                                                     fl["w_mix_inv"], None, b, t, fl["n_half"], 0, s)))
+    skip_args = (acts_all, 8, fl["w_skip"], fl["w_end_t"], fl["b_end"], x, fl["w_mix_inv"], None, b, t, fl["n_half"], 0)
+    nf = pk.flows[2]
+    variants.append(("wgb_tc_wn_skip_end", skip_flop, (8 * 1024 + 64) * steps,
+                     lambda: _lib.call("wgb_tc_wn_skip_end", *skip_args, s)))
+    variants.append(("wgb_tc2_wn_skip_end", skip_flop, (8 * 1024 + 64) * steps,
+                     lambda: _lib.call("wgb_tc2_wn_skip_end", *skip_args, None, None, 0, None, s)))
+    variants.append(("wgb_tc2_wn_skip_end + next start", skip_flop, (9 * 1024 + 64) * steps,
+                     lambda: _lib.call("wgb_tc2_wn_skip_end", *skip_args, nf["w_start"], nf["b_start"], nf["n_half"], h1, s)))
+    s16 = (acts_all, 8, fl["w_skip16"], fl["b_end"], x, fl["w_mix_inv"], None, b, t, fl["n_half"], 0)
+    variants.append(("wgb_tc_wn_skip16_end", skip_flop, (8 * 1024 + 64) * steps,
+                     lambda: _lib.call("wgb_tc_wn_skip16_end", *s16, None, None, 0, None, s)))
+    variants.append(("wgb_tc_wn_skip16_end + next start", skip_flop, (9 * 1024 + 64) * steps,
+                     lambda: _lib.call("wgb_tc_wn_skip16_end", *s16, nf["w_start"], nf["b_start"], nf["n_half"], h1, s)))
+    if pk.has_mel:
+        stack = torch.randn((b, args.frames, 320), device=DEV).to(bf)
+        for d in (1, 128):
+            variants.append((f"wgb_tc2_wn_gate_mel d={d}", gate_flop, (2048 + 20) * steps,
+                             lambda d=d: _lib.call("wgb_tc2_wn_gate_mel", h0, stack, fl["w_gate"][2], fl["w_mel"][2],
+                                                   fl["b_mel"][2], acts_all[2], b, t, d, s)))
     variants.append(("wgb_wn_start", 0, (32 + 1024) * steps,
                      lambda: _lib.call("wgb_wn_start", x, fl["w_start"], fl["b_start"], h0, 1, b * t, 512, fl["n_half"], s)))
     out = []
