@@ -294,7 +294,7 @@ def run_gpu_arm(args):
     # the tensor pipe really ran (fewer K chunks, but whole 128-frame tiles).
     gate_name = gate_names[0] if gate_names else None
     if gate_name == "wgb_tc2_wn_gate_mel":
-        gate_exec = 2 * (3 * 512 + 320) * 1024 * per_rank * (-(-FRAMES // 128) * 128) * 32
+        gate_exec = 2 * (3 * 512 + 320) * 1024 * (-(-per_rank * (FRAMES + 4) // 128) * 128) * 32   # padded frame axis
         kernel_desc = ("tc2::pair_kernel<GATE_MEL>: in_layers k=3 dilated + (cond_layers o upsample) composed, K = 1856, "
                        "+ gate epilogue; tcgen05 cta_group::2")
     else:

@@ -49,6 +49,10 @@ WGB_API int wgb_flow_mix(float* x, const float* w, long long rows, int C, void* 
  * out_bf16 selects a bf16 (tensor-core path) or fp32 (validation path) h. */
 WGB_API int wgb_wn_start(const float* x, const float* w, const float* bias, void* h, int out_bf16, long long rows,
                  int n_ch, int n_half, void* stream);
+/* Same, x [B,T,8] dense but h with a row pitch of h_batch_rows >= T per utterance (the padded layout of
+ * wgb_tc2_wn_gate_mel: rows T.. of every utterance are guard rows that stay zero). */
+WGB_API int wgb_wn_start_padded(const float* x, const float* w, const float* bias, void* h, int out_bf16, int batch, int T,
+                                long long h_batch_rows, int n_ch, int n_half, void* stream);
 
 /* ---------------------------------------------------------------- WN layers, BF16 tensor-core path */
 
@@ -81,21 +85,28 @@ WGB_API int wgb_tc_wn_skip_end(const void* acts_all, int n_layers, const void* w
  * not needed.  h bf16 [B,T,512], T = 32 * frames; mel_stack bf16 [B,frames,320] (wgb_upsample_im2col with
  * ld_tap = 80); w_packed as for wgb_tc_wn_gate (its 640 cond columns are not read); w_mel bf16 [32][1024][320] and
  * bias fp32 [1024] from text2speech_b200/packing.py:pack_cond_mel.  Same output as wgb_tc2_wn_gate up to bf16
- * rounding of the composed weight. */
+ * rounding of the composed weight.
+ *
+ * frames_pad == T/32: h and mel_stack are dense and every utterance is tiled on its own (ceil(frames/128) tiles per
+ * phase).  frames_pad > T/32 (by at least dilation/32): PADDED layout: h [B, 32*frames_pad, 512] and mel_stack
+ * [B, frames_pad, 320], the guard rows of h (rows >= T of each utterance) are zero and stay zero, and the kernel tiles
+ * all utterances as one sequence of B*frames_pad frames (no partial tile per utterance); acts stays dense [B,T,512]. */
 WGB_API int wgb_tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, const void* w_mel,
-                                const float* bias, void* acts, int batch, int T, int dilation, void* stream);
+                                const float* bias, void* acts, int batch, int T, int frames_pad, int dilation,
+                                void* stream);
 
 /* CTA-pair (cta_group::2) forms of the two entry points above, same contracts: each CTA loads half of every
  * weight tile, the pair issues one M = 256 MMA (half the weight traffic from L2 / shared memory per FLOP).
  * wgb_tc2_wn_skip_end can also run WN.start of the NEXT flow of WaveGlow.infer (glow.py:156 for flow k-1) on the
- * rows it has just updated: h_next bf16 [B,T,512] = next_w_start fp32 [512][next_n_half] applied to that flow's
- * audio_0 channels + next_b_start fp32 [512]; pass h_next = NULL (and NULL / 0 for the rest) to skip it. */
+ * rows it has just updated: h_next bf16 [B,T,512] (row pitch h_next_batch_rows >= T per utterance) = next_w_start
+ * fp32 [512][next_n_half] applied to that flow's audio_0 channels + next_b_start fp32 [512]; pass h_next = NULL
+ * (and NULL / 0 for the rest) to skip it.  wgb_tc2_wn_res takes the same row pitch for h_in / h_out. */
 WGB_API int wgb_tc2_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out,
-                           int batch, int T, void* stream);
+                           int batch, int T, long long h_batch_rows, void* stream);
 WGB_API int wgb_tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end,
                                 const float* b_end, float* x, const float* w_mix, float* log_s, int batch, int T,
                                 int n_half, int direction, const float* next_w_start, const float* next_b_start,
-                                int next_n_half, void* h_next, void* stream);
+                                int next_n_half, void* h_next, long long h_next_batch_rows, void* stream);
 
 /* Skip path and WN.end composed (glow.py:167-175 are linear with nothing in between): one skinny tcgen05 GEMM of
  * acts_all bf16 [n_layers][B][T][512] against w16 bf16 [16][n_layers*512] = the bf16 hi (rows 0..7) and lo (rows 8..15)
@@ -105,7 +116,7 @@ WGB_API int wgb_tc2_wn_skip_end(const void* acts_all, int n_layers, const void* 
 WGB_API int wgb_tc_wn_skip16_end(const void* acts_all, int n_layers, const void* w16, const float* b_end, float* x,
                                  const float* w_mix, float* log_s, int batch, int T, int n_half, int direction,
                                  const float* next_w_start, const float* next_b_start, int next_n_half, void* h_next,
-                                 void* stream);
+                                 long long h_next_batch_rows, void* stream);
 
 /* Plain tcgen05 GEMM with the same TMA/TMEM pipeline: C[b,t,n] = sum_k A[b,t,k] W[n,k] + bias[n];
  * A bf16 [B,T,K] (K % 64 == 0), W bf16 [N,K] (N % 256 == 0), C fp32 or bf16 [B,T,N]; bias may be NULL.

@@ -108,11 +108,21 @@ def test_tc_res_layer(lib, packed_q, entry, B, T):
     want = h + torch.nn.functional.conv1d(acts, w[:512], b[:512])
     fl = pk.flows[k]
     h_out = torch.zeros(B, T, 512, device=DEV, dtype=torch.bfloat16)
+    extra = (T,) if entry == "wgb_tc2_wn_res" else ()
     lib.call(entry, cl(acts).to(DEV, torch.bfloat16), fl["w_res"][i], fl["b_res"][i],
-             cl(h).to(DEV, torch.bfloat16), h_out, B, T, lib.stream_ptr())
+             cl(h).to(DEV, torch.bfloat16), h_out, B, T, *extra, lib.stream_ptr())
     torch.cuda.synchronize()
     err = util.rel_l2(h_out.float().cpu(), cl(want))
     assert err <= util.TOL_LAYER_BF16, err
+    if entry == "wgb_tc2_wn_res":                 # padded rows per utterance: guard rows neither read nor written
+        rows = T + 128
+        h_in = torch.full((B, rows, 512), 7.0, device=DEV, dtype=torch.bfloat16)
+        h_in[:, :T] = cl(h).to(DEV, torch.bfloat16)
+        h_out2 = torch.full((B, rows, 512), -3.0, device=DEV, dtype=torch.bfloat16)
+        lib.call(entry, cl(acts).to(DEV, torch.bfloat16), fl["w_res"][i], fl["b_res"][i], h_in, h_out2, B, T, rows,
+                 lib.stream_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(h_out2[:, :T], h_out) and bool((h_out2[:, T:] == -3.0).all())
 
 
 @pytest.mark.parametrize("entry", ["wgb_tc_wn_skip_end", "wgb_tc2_wn_skip_end", "wgb_tc_wn_skip16_end"])
@@ -155,9 +165,9 @@ def test_tc_skip_end_coupling(lib, packed_q, k, direction, entry):
         if direction == 0 and k > 0:             # also run WN.start of flow k-1 on the updated rows (glow.py:156)
             nf = pk.flows[k - 1]
             h_next = torch.zeros(B, T, 512, device=DEV, dtype=torch.bfloat16)
-            lib.call(entry, *args, nf["w_start"], nf["b_start"], nf["n_half"], h_next, lib.stream_ptr())
+            lib.call(entry, *args, nf["w_start"], nf["b_start"], nf["n_half"], h_next, T, lib.stream_ptr())
         else:
-            lib.call(entry, *args, None, None, 0, None, lib.stream_ptr())
+            lib.call(entry, *args, None, None, 0, None, 0, lib.stream_ptr())
     else:
         lib.call(entry, *args, lib.stream_ptr())
     torch.cuda.synchronize()
@@ -208,10 +218,21 @@ def test_tc2_gate_mel_layer(lib, packed_q, dil_i, B, F):
                       for p in range(4)], dim=2)
     acts = torch.zeros(B, T, 512, device=DEV, dtype=torch.bfloat16)
     lib.call("wgb_tc2_wn_gate_mel", cl(h).to(DEV, torch.bfloat16), stack, fl["w_gate"][dil_i], fl["w_mel"][dil_i],
-             fl["b_mel"][dil_i], acts, B, T, d, lib.stream_ptr())
+             fl["b_mel"][dil_i], acts, B, T, F, d, lib.stream_ptr())
     torch.cuda.synchronize()
     err = util.rel_l2(acts.float().cpu(), want)
     assert err <= util.TOL_LAYER_BF16, err
+    # padded layout: guard frames of zeros between the utterances, all of them tiled as one frame sequence
+    fp = F + 4
+    h_pad = torch.zeros(B, 32 * fp, 512, device=DEV, dtype=torch.bfloat16)
+    h_pad[:, :T] = cl(h).to(DEV, torch.bfloat16)
+    stack_pad = engine.mel_stack(pk, mel.to(DEV), fp)
+    assert stack_pad.shape == (B, fp, 320) and torch.equal(stack_pad[:, :F], stack)
+    acts2 = torch.zeros_like(acts)
+    lib.call("wgb_tc2_wn_gate_mel", h_pad, stack_pad, fl["w_gate"][dil_i], fl["w_mel"][dil_i], fl["b_mel"][dil_i], acts2,
+             B, T, fp, d, lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(acts2, acts)               # same math, different tiling
 
 
 @pytest.fixture(scope="module")

@@ -15,13 +15,13 @@ int tc_gemm_split3(const void*, const void*, const void*, const float*, void*, i
                    cudaStream_t);
 // wn_tc2.cu
 int tc2_wn_gate(const void*, const void*, const void*, const float*, void*, int, int, int, cudaStream_t);
-int tc2_wn_res(const void*, const void*, const float*, const void*, void*, int, int, cudaStream_t);
-int tc2_wn_gate_mel(const void*, const void*, const void*, const void*, const float*, void*, int, int, int, cudaStream_t);
+int tc2_wn_res(const void*, const void*, const float*, const void*, void*, int, int, long long, cudaStream_t);
+int tc2_wn_gate_mel(const void*, const void*, const void*, const void*, const float*, void*, int, int, int, int, cudaStream_t);
 int tc2_wn_skip_end(const void*, int, const void*, const float*, const float*, float*, const float*, float*, int, int,
-                    int, int, const float*, const float*, int, void*, cudaStream_t);
+                    int, int, const float*, const float*, int, void*, long long, cudaStream_t);
 // wn_skip16.cu
 int tc_wn_skip16_end(const void*, int, const void*, const float*, float*, const float*, float*, int, int, int, int,
-                     const float*, const float*, int, void*, cudaStream_t);
+                     const float*, const float*, int, void*, long long, cudaStream_t);
 // ref_f32.cu
 int sgemm_nt(const float*, const float*, const float*, void*, int, int, int, int, int, long long, long long, long long,
              long long, long long, int, int, cudaStream_t);
@@ -31,7 +31,7 @@ int res_skip_f32(const float*, float*, float*, long long, int, int, int, cudaStr
 int flow_from_z(const float*, float*, int, int, float, cudaStream_t);
 int flow_to_z(const float*, float*, int, int, cudaStream_t);
 int flow_mix(float*, const float*, long long, int, cudaStream_t);
-int wn_start(const float*, const float*, const float*, void*, int, long long, int, int, cudaStream_t);
+int wn_start(const float*, const float*, const float*, void*, int, long long, int, int, int, long long, cudaStream_t);
 int end_coupling_f32(const float*, const float*, const float*, float*, const float*, float*, int, int, int, int, int,
                      cudaStream_t);
 int upsample_im2col(const float*, void*, int, int, int, int, int, int, cudaStream_t);
@@ -75,7 +75,11 @@ WGB_API int wgb_flow_to_z(const float* x, float* z, int batch, int T, void* stre
 WGB_API int wgb_flow_mix(float* x, const float* w, long long rows, int C, void* stream) { return flow_mix(x, w, rows, C, S(stream)); }
 WGB_API int wgb_wn_start(const float* x, const float* w, const float* bias, void* h, int out_bf16, long long rows, int n_ch,
                  int n_half, void* stream) {
-    return wn_start(x, w, bias, h, out_bf16, rows, n_ch, n_half, S(stream));
+    return wn_start(x, w, bias, h, out_bf16, rows, n_ch, n_half, 0, 0, S(stream));
+}
+WGB_API int wgb_wn_start_padded(const float* x, const float* w, const float* bias, void* h, int out_bf16, int batch, int T,
+                                long long h_batch_rows, int n_ch, int n_half, void* stream) {
+    return wn_start(x, w, bias, h, out_bf16, static_cast<long long>(batch) * T, n_ch, n_half, T, h_batch_rows, S(stream));
 }
 
 WGB_API int wgb_tc_wn_gate(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts, int batch,
@@ -87,26 +91,27 @@ WGB_API int wgb_tc2_wn_gate(const void* h, const void* cond, const void* w_packe
     return tc2_wn_gate(h, cond, w_packed, bias, acts, batch, T, dilation, S(stream));
 }
 WGB_API int wgb_tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, const void* w_mel,
-                                const float* bias, void* acts, int batch, int T, int dilation, void* stream) {
-    return tc2_wn_gate_mel(h, mel_stack, w_packed, w_mel, bias, acts, batch, T, dilation, S(stream));
+                                const float* bias, void* acts, int batch, int T, int frames_pad, int dilation,
+                                void* stream) {
+    return tc2_wn_gate_mel(h, mel_stack, w_packed, w_mel, bias, acts, batch, T, frames_pad, dilation, S(stream));
 }
 WGB_API int wgb_tc2_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch,
-                           int T, void* stream) {
-    return tc2_wn_res(acts, w_res, bias, h_in, h_out, batch, T, S(stream));
+                           int T, long long h_batch_rows, void* stream) {
+    return tc2_wn_res(acts, w_res, bias, h_in, h_out, batch, T, h_batch_rows, S(stream));
 }
 WGB_API int wgb_tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end,
                                 const float* b_end, float* x, const float* w_mix, float* log_s, int batch, int T,
                                 int n_half, int direction, const float* next_w_start, const float* next_b_start,
-                                int next_n_half, void* h_next, void* stream) {
+                                int next_n_half, void* h_next, long long h_next_batch_rows, void* stream) {
     return tc2_wn_skip_end(acts_all, n_layers, w_skip, w_end, b_end, x, w_mix, log_s, batch, T, n_half, direction,
-                           next_w_start, next_b_start, next_n_half, h_next, S(stream));
+                           next_w_start, next_b_start, next_n_half, h_next, h_next_batch_rows, S(stream));
 }
 WGB_API int wgb_tc_wn_skip16_end(const void* acts_all, int n_layers, const void* w16, const float* b_end, float* x,
                                  const float* w_mix, float* log_s, int batch, int T, int n_half, int direction,
                                  const float* next_w_start, const float* next_b_start, int next_n_half, void* h_next,
-                                 void* stream) {
+                                 long long h_next_batch_rows, void* stream) {
     return tc_wn_skip16_end(acts_all, n_layers, w16, b_end, x, w_mix, log_s, batch, T, n_half, direction, next_w_start,
-                            next_b_start, next_n_half, h_next, S(stream));
+                            next_b_start, next_n_half, h_next, h_next_batch_rows, S(stream));
 }
 WGB_API int wgb_tc_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch,
                   int T, void* stream) {

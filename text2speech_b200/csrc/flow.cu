@@ -121,7 +121,8 @@ int flow_mix(float* x, const float* w, long long rows, int C, cudaStream_t strea
 template <typename OutT>
 __global__ void __launch_bounds__(256) wn_start_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ bias, OutT* __restrict__ h,
-                                                       long long rows, int n_ch, int n_half) {
+                                                       long long rows, int n_ch, int n_half, int T,
+                                                       long long h_batch_rows) {
     const int groups = n_ch >> 3;                      // threads per row
     const int lanes = blockDim.x / groups;             // rows per block iteration
     const int g = threadIdx.x % groups, rl = threadIdx.x / groups;
@@ -152,8 +153,10 @@ __global__ void __launch_bounds__(256) wn_start_kernel(const float* __restrict__
 #pragma unroll
         for (int c = 0; c < 8; ++c)
             o[c] = fmaf(wr[c][3], a[3], fmaf(wr[c][2], a[2], fmaf(wr[c][1], a[1], fmaf(wr[c][0], a[0], br[c]))));
+        const long long hb = r / T;
+        const long long hr = hb * h_batch_rows + (r - hb * T);           // row of h: utterances h_batch_rows apart
         if constexpr (sizeof(OutT) == 4) {
-            float4* d = reinterpret_cast<float4*>(h + r * n_ch + c0);
+            float4* d = reinterpret_cast<float4*>(h + hr * n_ch + c0);
             d[0] = make_float4(o[0], o[1], o[2], o[3]);
             d[1] = make_float4(o[4], o[5], o[6], o[7]);
         } else {
@@ -164,14 +167,16 @@ __global__ void __launch_bounds__(256) wn_start_kernel(const float* __restrict__
             pk.y = *reinterpret_cast<uint32_t*>(&p1);
             pk.z = *reinterpret_cast<uint32_t*>(&p2);
             pk.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(h + r * n_ch + c0) = pk;
+            *reinterpret_cast<uint4*>(h + hr * n_ch + c0) = pk;
         }
     }
 }
 
 int wn_start(const float* x, const float* w, const float* bias, void* h, int out_bf16, long long rows, int n_ch,
-             int n_half, cudaStream_t stream) {
+             int n_half, int T, long long h_batch_rows, cudaStream_t stream) {
     WGB_REQUIRE(x && w && bias && h && rows > 0, "bad arguments");
+    if (T <= 0) { T = static_cast<int>(rows < 0x7fffffffLL ? rows : 0x7fffffffLL); h_batch_rows = T; }   // dense h
+    WGB_REQUIRE(h_batch_rows >= T, "h_batch_rows must be >= T");
     WGB_REQUIRE(n_ch % 8 == 0 && n_ch / 8 <= 256 && n_half >= 1 && n_half <= 4,
                 "n_ch %% 8 == 0, n_ch <= 2048 and n_half in 1..4 required");
     const int lanes = 256 / (n_ch / 8);
@@ -179,9 +184,10 @@ int wn_start(const float* x, const float* w, const float* bias, void* h, int out
     const int grid = static_cast<int>(blocks < 148LL * 8 ? blocks : 148LL * 8);
     if (out_bf16)
         wn_start_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(h), rows, n_ch,
-                                                                 n_half);
+                                                                 n_half, T, h_batch_rows);
     else
-        wn_start_kernel<float><<<grid, 256, 0, stream>>>(x, w, bias, static_cast<float*>(h), rows, n_ch, n_half);
+        wn_start_kernel<float><<<grid, 256, 0, stream>>>(x, w, bias, static_cast<float*>(h), rows, n_ch, n_half, T,
+                                                         h_batch_rows);
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }

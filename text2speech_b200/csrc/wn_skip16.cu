@@ -43,6 +43,7 @@ struct Params {
     const float* next_b_start;
     __nv_bfloat16* h_next;
     int next_n_half;
+    long long h_next_batch_rows;  // row pitch per utterance of h_next (T, or more in the padded layout)
 };
 
 template <int NHALF, int DIR>
@@ -196,7 +197,7 @@ skip16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 }
                 const float4* ws4 = reinterpret_cast<const float4*>(s_ws);
                 const float4* bs4 = ws4 + kNCh;
-                uint4* dst = reinterpret_cast<uint4*>(p.h_next + grow * kNCh);
+                uint4* dst = reinterpret_cast<uint4*>(p.h_next + (static_cast<size_t>(b) * p.h_next_batch_rows + t) * kNCh);
 #pragma unroll 2
                 for (int c8 = 0; c8 < kNCh / 8; ++c8) {
                     const float4 b0 = bs4[2 * c8], b1 = bs4[2 * c8 + 1];
@@ -239,7 +240,8 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p,
 
 int tc_wn_skip16_end(const void* acts_all, int n_layers, const void* w16, const float* b_end, float* x, const float* w_mix,
                      float* log_s, int batch, int T, int n_half, int direction, const float* next_w_start,
-                     const float* next_b_start, int next_n_half, void* h_next, cudaStream_t stream) {
+                     const float* next_b_start, int next_n_half, void* h_next, long long h_next_batch_rows,
+                     cudaStream_t stream) {
     using namespace skip16;
     WGB_REQUIRE(acts_all && w16 && b_end && x, "null pointer");
     WGB_REQUIRE(n_layers >= 1 && batch > 0 && T > 0, "bad shape");
@@ -255,8 +257,10 @@ int tc_wn_skip16_end(const void* acts_all, int n_layers, const void* w16, const 
     if (h_next) {
         WGB_REQUIRE(direction == 0, "the fused WN.start of the next flow exists for the infer direction only");
         WGB_REQUIRE(next_w_start && next_b_start && next_n_half >= 1 && next_n_half <= 4, "bad next-flow start arguments");
+        WGB_REQUIRE(h_next_batch_rows >= T, "h_next_batch_rows must be >= T");
         p.next_w_start = next_w_start; p.next_b_start = next_b_start; p.next_n_half = next_n_half;
         p.h_next = static_cast<__nv_bfloat16*>(h_next);
+        p.h_next_batch_rows = h_next_batch_rows;
     }
     CUtensorMap ma, mw;
     {

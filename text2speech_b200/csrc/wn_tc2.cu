@@ -67,7 +67,10 @@ struct Smem {
 struct Params {
     int batch, T, tiles_per_b, n_tiles;
     int n_pass, ppi, n_chunks, dilation;
-    int frames, n_fblk;           // GATE_MEL: mel frames per utterance (T = 32 frames), 128-frame blocks per utterance
+    int frames, n_fblk;           // GATE_MEL: frames per tiled sequence (one utterance, or all of them in the padded
+                                  // layout), 128-frame blocks per sequence
+    int f_pad, f_real;            // GATE_MEL padded layout: frame pitch per utterance (> f_real: guard frames of zeros
+                                  // separate the utterances) and real frames per utterance; f_pad = 0: per-utterance tiles
     const float* bias;            // GATE [1024] packed order, RES [512]
     __nv_bfloat16* acts_out;      // GATE [B,T,512]
     const float* w_end;           // SKIP_END [512][8] fp32 (rows >= 2*n_half zero)
@@ -81,6 +84,7 @@ struct Params {
     const float* next_b_start;
     __nv_bfloat16* h_next;
     int next_n_half;
+    long long h_next_batch_rows;  // row pitch per utterance of h_next (T, or more in the padded layout)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -367,11 +371,17 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             const int b = valid ? tile / p.tiles_per_b : 0;
             int t = valid ? (tile % p.tiles_per_b) * kBlockM + row : p.T;
             bool live = t < p.T;
+            int bb = b;
             if constexpr (MODE == GATE_MEL) {                 // phase-major tile: row = frame, t = 32 frame + phase
                 live = valid && t < p.frames;
+                if (p.f_pad) {                                // padded layout: one frame axis over all utterances
+                    bb = t / p.f_pad;
+                    t -= bb * p.f_pad;
+                    live = live && t < p.f_real;
+                }
                 t = t * kPhases + ((item % groups) >> 2);
             }
-            const size_t grow = static_cast<size_t>(b) * p.T + t;
+            const size_t grow = static_cast<size_t>(bb) * p.T + t;
             float outv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) outv[j] = 0.f;
@@ -531,7 +541,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                     }
                     const float4* ws4 = reinterpret_cast<const float4*>(s_f32 + kNCh * 8);
                     const float4* bs4 = ws4 + kNCh;
-                    uint4* dst = reinterpret_cast<uint4*>(p.h_next + grow * kNCh);
+                    uint4* dst = reinterpret_cast<uint4*>(p.h_next + (static_cast<size_t>(b) * p.h_next_batch_rows + t) * kNCh);
 #pragma unroll 2
                     for (int c8 = 0; c8 < kNCh / 8; ++c8) {
                         const float4 b0 = bs4[2 * c8], b1 = bs4[2 * c8 + 1];
@@ -624,44 +634,64 @@ int tc2_wn_gate(const void* h, const void* cond, const void* w_packed, const flo
 // upsample im2col); w_packed bf16 [1024][2176] (only the 1536 in_layers columns are read); w_mel bf16
 // [32][1024][320] = per-phase W_cond U_phase in the packed row order; bias fp32 [1024] = b_in + b_cond + W_cond b_up.
 int tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, const void* w_mel, const float* bias,
-                    void* acts, int batch, int T, int dilation, cudaStream_t stream) {
+                    void* acts, int batch, int T, int frames_pad, int dilation, cudaStream_t stream) {
     using namespace tc2;
     WGB_REQUIRE(h && mel_stack && w_packed && w_mel && bias && acts, "null pointer");
     WGB_REQUIRE(dilation >= 1, "dilation must be >= 1");
     WGB_REQUIRE(batch > 0 && T > 0 && T % kPhases == 0, "T (%d) must be a positive multiple of %d group steps", T, kPhases);
+    const int frames = T / kPhases;
+    WGB_REQUIRE(frames_pad == frames || frames_pad >= frames + ceil_div(dilation, kPhases),
+                "frames_pad (%d) must equal frames (%d) or leave >= dilation/32 guard frames", frames_pad, frames);
     Params p{};
-    p.batch = batch; p.T = T;
-    p.frames = T / kPhases;
+    p.T = T;
+    const bool padded = frames_pad > frames;
+    // padded layout: h [B, 32*frames_pad, 512] and mel_stack [B, frames_pad, 320] with the guard frames of h zero, tiled
+    // as ONE sequence of B*frames_pad frames (the guards are the conv's zero padding between utterances)
+    p.batch = padded ? 1 : batch;
+    p.frames = padded ? batch * frames_pad : frames;
+    p.f_pad = padded ? frames_pad : 0;
+    p.f_real = frames;
     p.n_fblk = ceil_div(p.frames, kBlockM);
     p.tiles_per_b = p.n_fblk;                       // "tiles" = 128-frame blocks; each is visited once per phase and pass
-    p.n_tiles = batch * p.n_fblk;
+    p.n_tiles = p.batch * p.n_fblk;
     p.n_pass = 4 * kPhases; p.ppi = 1; p.n_chunks = (3 * kNCh + kMelK) / kBlockK; p.dilation = dilation;
     p.bias = bias; p.acts_out = static_cast<__nv_bfloat16*>(acts);
     CUtensorMap mh, mm, mw, mv;
     {
-        const uint64_t dims[4] = {kNCh, kPhases, static_cast<uint64_t>(p.frames), static_cast<uint64_t>(batch)};
-        const uint64_t strides[3] = {kNCh * 2, static_cast<uint64_t>(kNCh) * 2 * kPhases, static_cast<uint64_t>(kNCh) * 2 * T};
+        const uint64_t seq_rows = static_cast<uint64_t>(kPhases) * (padded ? frames_pad : frames);
+        const uint64_t dims[4] = {kNCh, kPhases, static_cast<uint64_t>(p.frames), static_cast<uint64_t>(p.batch)};
+        const uint64_t strides[3] = {kNCh * 2, static_cast<uint64_t>(kNCh) * 2 * kPhases, static_cast<uint64_t>(kNCh) * 2 * seq_rows};
         const uint32_t box[4] = {kBlockK, 1, kBlockM, 1};
         if (int e = make_tmap_bf16(&mh, h, 4, dims, strides, box)) return e;
     }
-    if (int e = act_map(&mm, mel_stack, kMelK, p.frames, batch)) return e;
+    if (int e = act_map(&mm, mel_stack, kMelK, p.frames, p.batch)) return e;
     if (int e = weight_half_map(&mw, w_packed, 2 * kNCh, 3 * kNCh + kNCond)) return e;
     if (int e = weight_half_map(&mv, w_mel, kPhases * 2 * kNCh, kMelK)) return e;
     return launch<GATE_MEL, 0, 0>(mh, mm, mw, mv, p, stream);
 }
 
+static int h_map(CUtensorMap* m, const void* base, int T, int batch, long long batch_rows) {
+    const uint64_t dims[3] = {tc2::kNCh, static_cast<uint64_t>(T), static_cast<uint64_t>(batch)};
+    const uint64_t strides[2] = {tc2::kNCh * 2, static_cast<uint64_t>(tc2::kNCh) * 2 * static_cast<uint64_t>(batch_rows)};
+    const uint32_t box[3] = {tc2::kBlockK, tc2::kBlockM, 1};
+    return make_tmap_bf16(m, base, 3, dims, strides, box);
+}
+
+// h_batch_rows: row pitch per utterance of h_in / h_out (T for dense buffers; more in the padded layout, whose guard
+// rows are never loaded nor stored because the tensor maps end at row T)
 int tc2_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch, int T,
-               cudaStream_t stream) {
+               long long h_batch_rows, cudaStream_t stream) {
     using namespace tc2;
     WGB_REQUIRE(acts && w_res && bias && h_in && h_out, "null pointer");
+    WGB_REQUIRE(h_batch_rows >= T, "h_batch_rows (%lld) must be >= T (%d)", h_batch_rows, T);
     Params p{};
     if (int e = fill_common(p, batch, T)) return e;
     p.n_pass = 2; p.ppi = 1; p.n_chunks = kNCh / kBlockK;
     p.bias = bias;
     CUtensorMap ma, mhi, mho, mw;
     if (int e = act_map(&ma, acts, kNCh, T, batch)) return e;
-    if (int e = act_map(&mhi, h_in, kNCh, T, batch)) return e;
-    if (int e = act_map(&mho, h_out, kNCh, T, batch)) return e;
+    if (int e = h_map(&mhi, h_in, T, batch, h_batch_rows)) return e;
+    if (int e = h_map(&mho, h_out, T, batch, h_batch_rows)) return e;
     if (int e = weight_half_map(&mw, w_res, kNCh, kNCh)) return e;
     return launch<RES, 0, 0>(ma, mhi, mw, mho, p, stream);
 }
@@ -669,7 +699,7 @@ int tc2_wn_res(const void* acts, const void* w_res, const float* bias, const voi
 int tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end, const float* b_end,
                     float* x, const float* w_mix, float* log_s, int batch, int T, int n_half, int direction,
                     const float* next_w_start, const float* next_b_start, int next_n_half, void* h_next,
-                    cudaStream_t stream) {
+                    long long h_next_batch_rows, cudaStream_t stream) {
     using namespace tc2;
     WGB_REQUIRE(acts_all && w_skip && w_end && b_end && x, "null pointer");
     WGB_REQUIRE(n_layers == 8, "tensor-core skip GEMM is specialised for 8 layers (got %d)", n_layers);
@@ -683,8 +713,10 @@ int tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, cons
     if (h_next) {
         WGB_REQUIRE(direction == 0, "the fused WN.start of the next flow exists for the infer direction only");
         WGB_REQUIRE(next_w_start && next_b_start && next_n_half >= 1 && next_n_half <= 4, "bad next-flow start arguments");
+        WGB_REQUIRE(h_next_batch_rows >= T, "h_next_batch_rows must be >= T");
         p.next_w_start = next_w_start; p.next_b_start = next_b_start; p.next_n_half = next_n_half;
         p.h_next = static_cast<__nv_bfloat16*>(h_next);
+        p.h_next_batch_rows = h_next_batch_rows;
     }
     CUtensorMap ma, mw;
     if (int e = act_map(&ma, acts_all, kNCh, T, batch * n_layers)) return e;

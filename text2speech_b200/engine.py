@@ -51,25 +51,35 @@ def upsample_cond(pk: PackedWaveGlow, mel: Tensor) -> Tensor:
     return cond.view(b, f * t_per_frame, n_cols // t_per_frame)
 
 
-def mel_stack(pk: PackedWaveGlow, mel: Tensor) -> Tensor:
-    """mel [B, n_mel, F] fp32 -> bf16 [B, F, 4*n_mel]: the four frames feeding each frame's group steps (the A operand
-    of the upsample GEMM without channel padding), K operand of the composed conditioning in wgb_tc2_wn_gate_mel."""
+GUARD_FRAMES = 4          # >= max dilation (128 group steps) / 32 steps per frame
+
+
+def mel_stack(pk: PackedWaveGlow, mel: Tensor, frames_pad: Optional[int] = None) -> Tensor:
+    """mel [B, n_mel, F] fp32 -> bf16 [B, frames_pad, 4*n_mel]: the four frames feeding each frame's group steps (the A
+    operand of the upsample GEMM without channel padding), K operand of the composed conditioning in
+    wgb_tc2_wn_gate_mel.  Rows >= F (guard frames of the padded layout) are never used."""
     b, n_mel, f = mel.shape
-    a = torch.empty((b, f, pk.up_taps * n_mel), device=mel.device, dtype=torch.bfloat16)
-    _lib.call("wgb_upsample_im2col", mel, a, 1, b, n_mel, f, pk.up_taps, n_mel, _lib.stream_ptr())
+    fp = f if frames_pad is None else frames_pad
+    if fp != f:
+        padded = torch.zeros((b, n_mel, fp), device=mel.device, dtype=torch.float32)
+        padded[:, :, :f] = mel
+        mel = padded
+    a = torch.empty((b, fp, pk.up_taps * n_mel), device=mel.device, dtype=torch.bfloat16)
+    _lib.call("wgb_upsample_im2col", mel, a, 1, b, n_mel, fp, pk.up_taps, n_mel, _lib.stream_ptr())
     return a
 
 
-def use_mel_path(pk: PackedWaveGlow, frames: int, t: int) -> bool:
-    """Composed conditioning (K = 1856, rows tiled 128 frames x 1 phase) vs the cond tensor (K = 2176, rows tiled
-    128 group steps): pick the one that executes fewer MMA chunks for this length ('auto'), or as forced."""
-    if pk.mode != "bf16" or not pk.has_mel or pk.cond_path == "cond" or GATE_KERNEL != "pair":
+def use_mel_path(pk: PackedWaveGlow, batch: int, frames: int, t: int) -> bool:
+    """Composed conditioning (K = 1856, rows tiled 128 frames x 1 phase over the padded frame axis of the whole batch)
+    vs the cond tensor (K = 2176, rows tiled 128 group steps per utterance): pick the one that executes fewer MMA
+    chunks for this shape ('auto'), or as forced by model.cond_path."""
+    if pk.mode != "bf16" or not pk.has_mel or pk.cond_path == "cond" or GATE_KERNEL != "pair" or RES_KERNEL != "pair":
         return False
     if t != frames * 32:                      # forward() with audio shorter than 256 * frames
         return False
     if pk.cond_path == "mel":
         return True
-    return -(-frames // 128) * 32 * 29 < -(-t // 128) * 34
+    return -(-batch * (frames + GUARD_FRAMES) // 128) * 32 * 29 < batch * -(-t // 128) * 34
 
 
 def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int, log_s: Optional[Tensor],
@@ -80,20 +90,24 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int
     b, t = x.shape[0], x.shape[1]
     s = _lib.stream_ptr()
     h0, h1, acts_all = bufs
+    h_rows = h0.shape[1]                      # row pitch per utterance: t, or 32 * frames_pad in the padded layout
     gate = "wgb_tc2_wn_gate" if GATE_KERNEL == "pair" else "wgb_tc_wn_gate"
     res = "wgb_tc2_wn_res" if RES_KERNEL == "pair" else "wgb_tc_wn_res"
     skip_end = "wgb_tc2_wn_skip_end" if SKIP_KERNEL == "pair" else "wgb_tc_wn_skip_end"
     if not start_done:
-        _lib.call("wgb_wn_start", x, fl["w_start"], fl["b_start"], h0, 1, b * t, pk.n_ch, fl["n_half"], s)
+        _lib.call("wgb_wn_start_padded", x, fl["w_start"], fl["b_start"], h0, 1, b, t, h_rows, pk.n_ch, fl["n_half"], s)
     cur, nxt = h0, h1
     for i in range(pk.n_layers):
         if isinstance(cond, tuple):           # ("mel", mel_stack): conditioning composed with the upsampler
             _lib.call("wgb_tc2_wn_gate_mel", cur, cond[1], fl["w_gate"][i], fl["w_mel"][i], fl["b_mel"][i], acts_all[i],
-                      b, t, 2 ** i, s)
+                      b, t, h_rows // 32, 2 ** i, s)
         else:
             _lib.call(gate, cur, cond, fl["w_gate"][i], fl["b_gate"][i], acts_all[i], b, t, 2 ** i, s)
         if i < pk.n_layers - 1:
-            _lib.call(res, acts_all[i], fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, s)
+            if RES_KERNEL == "pair":
+                _lib.call(res, acts_all[i], fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, h_rows, s)
+            else:
+                _lib.call(res, acts_all[i], fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, s)
             cur, nxt = nxt, cur
     args = (acts_all, pk.n_layers, fl["w_skip"], fl["w_end_t"], fl["b_end"], x,
             fl["w_mix_inv"] if direction == 0 else None, log_s, b, t, fl["n_half"], direction)
@@ -106,9 +120,9 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int
         args = (acts_all, pk.n_layers, fl["w_skip16"], fl["b_end"], x,
                 fl["w_mix_inv"] if direction == 0 else None, log_s, b, t, fl["n_half"], direction)
     if fuse:
-        _lib.call(skip_end, *args, next_fl["w_start"], next_fl["b_start"], next_fl["n_half"], h0, s)
+        _lib.call(skip_end, *args, next_fl["w_start"], next_fl["b_start"], next_fl["n_half"], h0, h_rows, s)
     else:
-        _lib.call(skip_end, *args, None, None, 0, None, s)
+        _lib.call(skip_end, *args, None, None, 0, None, 0, s)
     return fuse
 
 
@@ -138,12 +152,16 @@ def _wn_fp32(pk: PackedWaveGlow, fl: dict, x: Tensor, cond: Tensor, bufs, direct
               fl["w_mix_inv"] if direction == 0 else None, log_s, b, t, c, fl["n_half"], direction, s)
 
 
-def _alloc(pk: PackedWaveGlow, b: int, t: int, device):
+def _alloc(pk: PackedWaveGlow, b: int, t: int, device, h_rows: Optional[int] = None):
     if pk.mode == "bf16":
         bf = torch.bfloat16
-        return (torch.empty((b, t, pk.n_ch), device=device, dtype=bf),
-                torch.empty((b, t, pk.n_ch), device=device, dtype=bf),
-                torch.empty((pk.n_layers, b, t, pk.n_ch), device=device, dtype=bf))
+        if h_rows is not None and h_rows != t:     # padded layout: guard rows are zero and no kernel ever writes them
+            h0 = torch.zeros((b, h_rows, pk.n_ch), device=device, dtype=bf)
+            h1 = torch.zeros((b, h_rows, pk.n_ch), device=device, dtype=bf)
+        else:
+            h0 = torch.empty((b, t, pk.n_ch), device=device, dtype=bf)
+            h1 = torch.empty((b, t, pk.n_ch), device=device, dtype=bf)
+        return (h0, h1, torch.empty((pk.n_layers, b, t, pk.n_ch), device=device, dtype=bf))
     f32 = torch.float32
     return (torch.empty((b, t, pk.n_ch), device=device, dtype=f32),
             torch.empty((b, t, 2 * pk.n_ch), device=device, dtype=f32),
@@ -166,10 +184,15 @@ def infer(pk: PackedWaveGlow, mel: Tensor, z: Tensor, sigma: float) -> Tensor:
     b, _, f = mel.shape
     t = f * pk.up_stride // pk.n_group
     s = _lib.stream_ptr()
-    cond = ("mel", mel_stack(pk, mel)) if use_mel_path(pk, f, t) else upsample_cond(pk, mel)
+    h_rows = None
+    if use_mel_path(pk, b, f, t):
+        h_rows = 32 * (f + GUARD_FRAMES)
+        cond = ("mel", mel_stack(pk, mel, f + GUARD_FRAMES))
+    else:
+        cond = upsample_cond(pk, mel)
     x = torch.empty((b, t, pk.n_group), device=mel.device, dtype=torch.float32)
     _lib.call("wgb_flow_from_z", z, x, b, t, float(sigma), s)
-    bufs = _alloc(pk, b, t, mel.device)
+    bufs = _alloc(pk, b, t, mel.device, h_rows)
     start_done = False
     for k in reversed(range(pk.n_flows)):
         start_done = run_wn(pk, k, x, cond, bufs, 0, None, start_done, k - 1 if k > 0 else None)
@@ -186,14 +209,16 @@ def forward(pk: PackedWaveGlow, mel: Tensor, audio: Tensor) -> Tuple[Tensor, Lis
     s = _lib.stream_ptr()
     if t > f * pk.up_stride // pk.n_group:
         raise RuntimeError("audio longer than 256 * frames is not supported by the regrouped upsample GEMM")
-    if use_mel_path(pk, f, t):
-        cond = ("mel", mel_stack(pk, mel))
+    h_rows = None
+    if use_mel_path(pk, b, f, t):
+        h_rows = 32 * (f + GUARD_FRAMES)
+        cond = ("mel", mel_stack(pk, mel, f + GUARD_FRAMES))
     else:
         cond = upsample_cond(pk, mel)
         if cond.shape[1] > t:
             cond = cond[:, :t].contiguous()                                   # glow.py:217-218
     x = audio[:, : t * pk.n_group].reshape(b, t, pk.n_group).float().contiguous().clone()
-    bufs = _alloc(pk, b, t, mel.device)
+    bufs = _alloc(pk, b, t, mel.device, h_rows)
     log_s_list, log_det_list = [], []
     for k in range(pk.n_flows):
         fl = pk.flows[k]

@@ -108,26 +108,34 @@ def main():
                              lambda name=name, d=d: _lib.call(name, h0, cond, fl["w_gate"][2], fl["b_gate"][2], acts_all[2], b, t, d, s)))
     for name in ("wgb_tc_wn_res", "wgb_tc2_wn_res"):
         variants.append((name, res_flop, 3072 * steps,
-                         lambda name=name: _lib.call(name, acts_all[2], fl["w_res"][2], fl["b_res"][2], h0, h1, b, t, s)))
+                         lambda name=name: _lib.call(name, acts_all[2], fl["w_res"][2], fl["b_res"][2], h0, h1, b, t,
+                                                     *((t,) if name == "wgb_tc2_wn_res" else ()), s)))
     skip_args = (acts_all, 8, fl["w_skip"], fl["w_end_t"], fl["b_end"], x, fl["w_mix_inv"], None, b, t, fl["n_half"], 0)
     nf = pk.flows[2]
     variants.append(("wgb_tc_wn_skip_end", skip_flop, (8 * 1024 + 64) * steps,
                      lambda: _lib.call("wgb_tc_wn_skip_end", *skip_args, s)))
     variants.append(("wgb_tc2_wn_skip_end", skip_flop, (8 * 1024 + 64) * steps,
-                     lambda: _lib.call("wgb_tc2_wn_skip_end", *skip_args, None, None, 0, None, s)))
+                     lambda: _lib.call("wgb_tc2_wn_skip_end", *skip_args, None, None, 0, None, 0, s)))
     variants.append(("wgb_tc2_wn_skip_end + next start", skip_flop, (9 * 1024 + 64) * steps,
-                     lambda: _lib.call("wgb_tc2_wn_skip_end", *skip_args, nf["w_start"], nf["b_start"], nf["n_half"], h1, s)))
+                     lambda: _lib.call("wgb_tc2_wn_skip_end", *skip_args, nf["w_start"], nf["b_start"], nf["n_half"], h1, t, s)))
     s16 = (acts_all, 8, fl["w_skip16"], fl["b_end"], x, fl["w_mix_inv"], None, b, t, fl["n_half"], 0)
     variants.append(("wgb_tc_wn_skip16_end", skip_flop, (8 * 1024 + 64) * steps,
-                     lambda: _lib.call("wgb_tc_wn_skip16_end", *s16, None, None, 0, None, s)))
+                     lambda: _lib.call("wgb_tc_wn_skip16_end", *s16, None, None, 0, None, 0, s)))
     variants.append(("wgb_tc_wn_skip16_end + next start", skip_flop, (9 * 1024 + 64) * steps,
-                     lambda: _lib.call("wgb_tc_wn_skip16_end", *s16, nf["w_start"], nf["b_start"], nf["n_half"], h1, s)))
+                     lambda: _lib.call("wgb_tc_wn_skip16_end", *s16, nf["w_start"], nf["b_start"], nf["n_half"], h1, t, s)))
     if pk.has_mel:
         stack = torch.randn((b, args.frames, 320), device=DEV).to(bf)
         for d in (1, 128):
             variants.append((f"wgb_tc2_wn_gate_mel d={d}", gate_flop, (2048 + 20) * steps,
                              lambda d=d: _lib.call("wgb_tc2_wn_gate_mel", h0, stack, fl["w_gate"][2], fl["w_mel"][2],
-                                                   fl["b_mel"][2], acts_all[2], b, t, d, s)))
+                                                   fl["b_mel"][2], acts_all[2], b, t, args.frames, d, s)))
+        fp = args.frames + 4
+        h_pad = torch.zeros((b, 32 * fp, 512), device=DEV, dtype=bf)
+        h_pad[:, :t] = h0
+        stack_pad = torch.randn((b, fp, 320), device=DEV).to(bf)
+        variants.append(("wgb_tc2_wn_gate_mel padded d=128", gate_flop, (2048 + 20) * steps,
+                         lambda: _lib.call("wgb_tc2_wn_gate_mel", h_pad, stack_pad, fl["w_gate"][2], fl["w_mel"][2],
+                                           fl["b_mel"][2], acts_all[2], b, t, fp, 128, s)))
     variants.append(("wgb_wn_start", 0, (32 + 1024) * steps,
                      lambda: _lib.call("wgb_wn_start", x, fl["w_start"], fl["b_start"], h0, 1, b * t, 512, fl["n_half"], s)))
     out = []
