@@ -90,10 +90,23 @@ WGB_API int wgb_tc_wn_skip_end(const void* acts_all, int n_layers, const void* w
  * frames_pad == T/32: h and mel_stack are dense and every utterance is tiled on its own (ceil(frames/128) tiles per
  * phase).  frames_pad > T/32 (by at least dilation/32): PADDED layout: h [B, 32*frames_pad, 512] and mel_stack
  * [B, frames_pad, 320], the guard rows of h (rows >= T of each utterance) are zero and stay zero, and the kernel tiles
- * all utterances as one sequence of B*frames_pad frames (no partial tile per utterance); acts stays dense [B,T,512]. */
+ * all utterances as one sequence of B*frames_pad frames (no partial tile per utterance); acts stays dense [B,T,512].
+ *
+ * Optional skip accumulation (w_comp, skip_acc both non-NULL): the skip halves of res_skip_layers and WN.end are
+ * linear with nothing in between (glow.py:167-175), so this layer's contribution to WN.end's output is
+ * (W_end W_skip_i) acts_i.  w_comp fp32 [512][8] is that product transposed; each epilogue thread adds (stores, when
+ * skip_first) the partial product over its pass's 128 channels, taken from the un-rounded fp32 activations, into its
+ * own slot of skip_acc fp32 [4][B*T][8].  wgb_end_from_acc then finishes the flow, and acts need not be kept. */
 WGB_API int wgb_tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, const void* w_mel,
                                 const float* bias, void* acts, int batch, int T, int frames_pad, int dilation,
-                                void* stream);
+                                const float* w_comp, float* skip_acc, int skip_first, void* stream);
+/* WN.end output = sum of the 4 slots of skip_acc + b_end (skip biases folded in), then the affine coupling and W^-1
+ * (direction 0, glow.py:277-282) or forward coupling + log_s (direction 1, :241-246), and optionally WN.start of the
+ * next flow (as wgb_tc2_wn_skip_end).  Memory-bound: 160 B in, 32 B (+ 1 KB h_next) out per group step. */
+WGB_API int wgb_end_from_acc(const float* skip_acc, const float* b_end, float* x, const float* w_mix, float* log_s,
+                             int batch, int T, int n_half, int direction, const float* next_w_start,
+                             const float* next_b_start, int next_n_half, void* h_next, long long h_next_batch_rows,
+                             void* stream);
 
 /* CTA-pair (cta_group::2) forms of the two entry points above, same contracts: each CTA loads half of every
  * weight tile, the pair issues one M = 256 MMA (half the weight traffic from L2 / shared memory per FLOP).

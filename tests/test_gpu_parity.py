@@ -184,6 +184,48 @@ def test_tc_skip_end_coupling(lib, packed_q, k, direction, entry):
         assert util.rel_l2(log_s.cpu(), out[:, n_half:]) <= 1e-4
 
 
+@pytest.mark.parametrize("k,direction", [(11, 0), (5, 0), (0, 0), (11, 1), (4, 1)])
+def test_end_from_acc(lib, packed_q, k, direction):
+    """WN.end output from the four skip-accumulator slots, coupling (+ W^-1, + next-flow WN.start)."""
+    pk = packed_q["stress"]
+    st = oracle.folded_state(quantised_state("stress"))
+    fl = pk.flows[k]
+    n_half, B, T = fl["n_half"], 3, 777
+    base = 8 - 2 * n_half
+    g = torch.Generator().manual_seed(40 + k)
+    acc = 0.1 * torch.randn(4, B * T, 8, generator=g)
+    x = torch.randn(B, T, 8, generator=g)
+    out = acc.sum(0).reshape(B, T, 8) + fl["b_end"].cpu()
+    bb, ss = out[:, :, :n_half], out[:, :, n_half: 2 * n_half]
+    want = x.clone()
+    a0, a1 = x[:, :, base: base + n_half], x[:, :, base + n_half:]
+    if direction == 0:
+        w_inv = torch.linalg.inv(st[f"convinv.{k}.conv.weight"][:, :, 0].double()).float()
+        want[:, :, base:] = torch.cat([a0, (a1 - bb) / torch.exp(ss)], 2) @ w_inv.t()
+    else:
+        want[:, :, base + n_half:] = torch.exp(ss) * a1 + bb
+    xd = x.to(DEV).contiguous()
+    log_s = torch.zeros(B, n_half, T, device=DEV) if direction == 1 else None
+    rows = T + 64
+    h_next = torch.full((B, rows, 512), 5.0, device=DEV, dtype=torch.bfloat16) if (direction == 0 and k > 0) else None
+    nf = pk.flows[k - 1] if h_next is not None else None
+    lib.call("wgb_end_from_acc", acc.to(DEV), fl["b_end"], xd, fl["w_mix_inv"] if direction == 0 else None, log_s, B, T,
+             n_half, direction, *((nf["w_start"], nf["b_start"], nf["n_half"], h_next, rows) if nf else (None, None, 0, None, 0)),
+             lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert util.rel_l2(xd.cpu()[:, :, base:], want[:, :, base:]) <= 1e-5
+    assert torch.equal(xd.cpu()[:, :, :base], x[:, :, :base])
+    if direction == 1:
+        assert util.rel_l2(log_s.cpu(), ss.permute(0, 2, 1)) <= 1e-6
+    if nf:
+        nh = nf["n_half"]
+        nb = 8 - 2 * nh
+        w, bias = st[f"WN.{k - 1}.start.weight"][:, :, 0], st[f"WN.{k - 1}.start.bias"]
+        want_h = xd.cpu()[:, :, nb: nb + nh] @ w.t() + bias
+        assert util.rel_l2(h_next[:, :T].float().cpu(), want_h) <= util.TOL_LAYER_BF16
+        assert bool((h_next[:, T:] == 5.0).all())                 # guard rows untouched
+
+
 # ------------------------------------------------------------------------------------ whole model
 
 @pytest.mark.parametrize("dil_i,B,F", [(0, 2, 130), (3, 3, 40), (4, 1, 129), (5, 1, 200), (7, 2, 130), (6, 1, 860)])
@@ -218,7 +260,7 @@ def test_tc2_gate_mel_layer(lib, packed_q, dil_i, B, F):
                       for p in range(4)], dim=2)
     acts = torch.zeros(B, T, 512, device=DEV, dtype=torch.bfloat16)
     lib.call("wgb_tc2_wn_gate_mel", cl(h).to(DEV, torch.bfloat16), stack, fl["w_gate"][dil_i], fl["w_mel"][dil_i],
-             fl["b_mel"][dil_i], acts, B, T, F, d, lib.stream_ptr())
+             fl["b_mel"][dil_i], acts, B, T, F, d, None, None, 0, lib.stream_ptr())
     torch.cuda.synchronize()
     err = util.rel_l2(acts.float().cpu(), want)
     assert err <= util.TOL_LAYER_BF16, err
@@ -229,10 +271,17 @@ def test_tc2_gate_mel_layer(lib, packed_q, dil_i, B, F):
     stack_pad = engine.mel_stack(pk, mel.to(DEV), fp)
     assert stack_pad.shape == (B, fp, 320) and torch.equal(stack_pad[:, :F], stack)
     acts2 = torch.zeros_like(acts)
-    lib.call("wgb_tc2_wn_gate_mel", h_pad, stack_pad, fl["w_gate"][dil_i], fl["w_mel"][dil_i], fl["b_mel"][dil_i], acts2,
-             B, T, fp, d, lib.stream_ptr())
+    # ... and with the skip path accumulated in the epilogue: slots (pass, row) hold W_end W_skip_i applied to the
+    # fp32 activations of that pass's 128 channels; a second call with skip_first = 0 adds on top
+    w_comp = fl["w_comp"][dil_i]
+    skip_acc = torch.full((4, B * T, 8), 99.0, device=DEV)
+    for first in (1, 0):
+        lib.call("wgb_tc2_wn_gate_mel", h_pad, stack_pad, fl["w_gate"][dil_i], fl["w_mel"][dil_i], fl["b_mel"][dil_i],
+                 acts2, B, T, fp, d, w_comp, skip_acc, first, lib.stream_ptr())
     torch.cuda.synchronize()
     assert torch.equal(acts2, acts)               # same math, different tiling
+    want_skip = 2 * torch.einsum("rpc,pcm->prm", want.reshape(B * T, 4, 128), w_comp.cpu().double().reshape(4, 128, 8))
+    assert util.rel_l2(skip_acc.cpu(), want_skip) <= util.TOL_LAYER_BF16
 
 
 @pytest.fixture(scope="module")
@@ -284,6 +333,28 @@ def test_infer_bf16_composed_conditioning_path(models, golden, recipe):
     assert util.snr_db(a_mel, golden[f"{recipe}_infer_audio"]) >= util.MIN_SNR_DB
     assert util.snr_db(a_mel, a_cond) >= util.MIN_SNR_DB
     assert not torch.equal(a_mel, a_cond)            # really two different kernels
+
+
+def test_skip_paths_agree(models, golden, monkeypatch):
+    """Composed-conditioning path with the skip product accumulated in the gate epilogue ('acc', default) vs the
+    N = 16 sweep over stored activations ('skip16') vs the un-composed K = 4096 GEMM ('pair')."""
+    from text2speech_b200 import engine
+    m = models["stress"]
+    m.mode = "bf16"
+    mel, z, _ = util.golden_inputs()
+    out = {}
+    try:
+        m.cond_path = "mel"
+        for kind in ("acc", "skip16", "pair"):
+            monkeypatch.setattr(engine, "SKIP_KERNEL", kind)
+            out[kind] = m.infer(mel.to(DEV), sigma=util.SIGMA, z=z.to(DEV)).cpu()
+    finally:
+        m.cond_path = "auto"
+    for kind, audio in out.items():
+        assert util.snr_db(audio, golden["stress_infer_audio"]) >= util.MIN_SNR_DB, kind
+    # the variants differ only in where bf16 rounding enters, so they agree with each other as well as with the reference
+    assert util.snr_db(out["acc"], out["skip16"]) >= util.MIN_SNR_DB
+    assert util.snr_db(out["skip16"], out["pair"]) >= util.MIN_SNR_DB
 
 
 def test_forward_bf16_composed_conditioning_path(models, golden):

@@ -16,7 +16,11 @@ int tc_gemm_split3(const void*, const void*, const void*, const float*, void*, i
 // wn_tc2.cu
 int tc2_wn_gate(const void*, const void*, const void*, const float*, void*, int, int, int, cudaStream_t);
 int tc2_wn_res(const void*, const void*, const float*, const void*, void*, int, int, long long, cudaStream_t);
-int tc2_wn_gate_mel(const void*, const void*, const void*, const void*, const float*, void*, int, int, int, int, cudaStream_t);
+int tc2_wn_gate_mel(const void*, const void*, const void*, const void*, const float*, void*, int, int, int, int,
+                    const float*, float*, int, cudaStream_t);
+// flow.cu
+int end_from_acc(const float*, const float*, float*, const float*, float*, int, int, int, int, const float*, const float*,
+                 int, void*, long long, cudaStream_t);
 int tc2_wn_skip_end(const void*, int, const void*, const float*, const float*, float*, const float*, float*, int, int,
                     int, int, const float*, const float*, int, void*, long long, cudaStream_t);
 // wn_skip16.cu
@@ -92,8 +96,15 @@ WGB_API int wgb_tc2_wn_gate(const void* h, const void* cond, const void* w_packe
 }
 WGB_API int wgb_tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, const void* w_mel,
                                 const float* bias, void* acts, int batch, int T, int frames_pad, int dilation,
-                                void* stream) {
-    return tc2_wn_gate_mel(h, mel_stack, w_packed, w_mel, bias, acts, batch, T, frames_pad, dilation, S(stream));
+                                const float* w_comp, float* skip_acc, int skip_first, void* stream) {
+    return tc2_wn_gate_mel(h, mel_stack, w_packed, w_mel, bias, acts, batch, T, frames_pad, dilation, w_comp, skip_acc,
+                           skip_first, S(stream));
+}
+WGB_API int wgb_end_from_acc(const float* skip_acc, const float* b_end, float* x, const float* w_mix, float* log_s, int batch,
+                             int T, int n_half, int direction, const float* next_w_start, const float* next_b_start,
+                             int next_n_half, void* h_next, long long h_next_batch_rows, void* stream) {
+    return end_from_acc(skip_acc, b_end, x, w_mix, log_s, batch, T, n_half, direction, next_w_start, next_b_start,
+                        next_n_half, h_next, h_next_batch_rows, S(stream));
 }
 WGB_API int wgb_tc2_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch,
                            int T, long long h_batch_rows, void* stream) {

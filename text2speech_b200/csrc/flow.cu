@@ -192,6 +192,151 @@ int wn_start(const float* x, const float* w, const float* bias, void* h, int out
     return WGB_OK;
 }
 
+// ------------------------------------------------------------------------------------ end from the skip accumulator
+// out = sum of the four per-pass slots of skip_acc + b_end  (= WN.end(sum_i skip_i), accumulated by the gate kernels),
+// then the affine coupling + W^-1 (infer, glow.py:277-282) or the forward coupling + log_s (:241-246), then -- infer
+// only, optional -- WN.start of the next flow (glow.py:156) on the updated row.  Each row is handled by a lane group of
+// n_ch/8 = 64 threads: all of them evaluate the (tiny) coupling redundantly from broadcast loads, the first one writes
+// x / log_s, and every thread writes its 8 channels of h_next, so the 1 KB row store is contiguous.
+template <int NHALF, int DIR>
+__global__ void __launch_bounds__(256, 3) end_from_acc_kernel(const float* __restrict__ acc, const float* __restrict__ b_end,
+                                                           float* __restrict__ x, const float* __restrict__ w_mix,
+                                                           float* __restrict__ log_s, long long rows, int T,
+                                                           const float* __restrict__ nw, const float* __restrict__ nbias,
+                                                           int next_n_half, __nv_bfloat16* __restrict__ h_next,
+                                                           long long h_batch_rows) {
+    constexpr int kCh = 512, kGroups = kCh / 8, kLanes = 256 / kGroups;
+    constexpr int C = 2 * NHALF, BASE = 8 - C;
+    const int g = threadIdx.x % kGroups, rl = threadIdx.x / kGroups;
+    const int c0 = g << 3;
+    __shared__ float s_wm[64], s_be[8];                 // W^-1 and b_end: broadcast reads, keeps registers for wr/br
+    if (threadIdx.x < 64) s_wm[threadIdx.x] = (DIR == 0) ? w_mix[threadIdx.x] : 0.f;
+    if (threadIdx.x < 8) s_be[threadIdx.x] = b_end[threadIdx.x];
+    __syncthreads();
+    float wr[8][4], br[8];
+    if (h_next) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            br[c] = nbias[c0 + c];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wr[c][j] = j < next_n_half ? nw[(c0 + c) * next_n_half + j] : 0.f;
+        }
+    }
+    const int nb = 8 - 2 * next_n_half;
+    for (long long r0 = static_cast<long long>(blockIdx.x) * kLanes; r0 < rows;
+         r0 += static_cast<long long>(gridDim.x) * kLanes) {           // block-uniform trip count (barrier inside)
+        const bool valid = r0 + rl < rows;
+        const long long r = valid ? r0 + rl : rows - 1;
+        float out[8];
+        {
+            const float4 a0 = *reinterpret_cast<const float4*>(acc + r * 8), a1 = *reinterpret_cast<const float4*>(acc + r * 8 + 4);
+            out[0] = a0.x; out[1] = a0.y; out[2] = a0.z; out[3] = a0.w;
+            out[4] = a1.x; out[5] = a1.y; out[6] = a1.z; out[7] = a1.w;
+        }
+#pragma unroll
+        for (int s = 1; s < 4; ++s) {
+            const float* ap = acc + (static_cast<long long>(s) * rows + r) * 8;
+            const float4 a0 = *reinterpret_cast<const float4*>(ap), a1 = *reinterpret_cast<const float4*>(ap + 4);
+            out[0] += a0.x; out[1] += a0.y; out[2] += a0.z; out[3] += a0.w;
+            out[4] += a1.x; out[5] += a1.y; out[6] += a1.z; out[7] += a1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[j] += s_be[j];
+        float xv[8];
+        *reinterpret_cast<float4*>(&xv[0]) = *reinterpret_cast<const float4*>(x + r * 8);
+        *reinterpret_cast<float4*>(&xv[4]) = *reinterpret_cast<const float4*>(x + r * 8 + 4);
+        const long long b = r / T;
+        const long long t = r - b * T;
+        __syncthreads();          // every thread of the row's lane group has read the old x before its first thread writes
+        if constexpr (DIR == 0) {
+            float xin[C];
+#pragma unroll
+            for (int j = 0; j < NHALF; ++j) {
+                xin[j] = xv[BASE + j];
+                xin[NHALF + j] = (xv[BASE + NHALF + j] - out[j]) * expf(-out[NHALF + j]);
+            }
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                float a = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) a = fmaf(s_wm[i * 8 + c], xin[c], a);
+                xv[BASE + i] = a;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NHALF; ++j) {
+                const float ls = out[NHALF + j];
+                xv[BASE + NHALF + j] = expf(ls) * xv[BASE + NHALF + j] + out[j];
+                if (g == 0 && valid) log_s[(b * NHALF + j) * T + t] = ls;
+            }
+        }
+        if (g == 0 && valid) {
+            *reinterpret_cast<float4*>(x + r * 8) = *reinterpret_cast<const float4*>(&xv[0]);
+            *reinterpret_cast<float4*>(x + r * 8 + 4) = *reinterpret_cast<const float4*>(&xv[4]);
+        }
+        if (DIR == 0 && h_next && valid) {
+            float a[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v = (i == nb + j) ? xv[i] : v;
+                a[j] = v;
+            }
+            float o[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                o[c] = fmaf(wr[c][3], a[3], fmaf(wr[c][2], a[2], fmaf(wr[c][1], a[1], fmaf(wr[c][0], a[0], br[c]))));
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<uint32_t*>(&p2);
+            pk.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(h_next + (b * h_batch_rows + t) * kCh + c0) = pk;
+        }
+    }
+}
+
+int end_from_acc(const float* skip_acc, const float* b_end, float* x, const float* w_mix, float* log_s, int batch, int T,
+                 int n_half, int direction, const float* next_w_start, const float* next_b_start, int next_n_half,
+                 void* h_next, long long h_next_batch_rows, cudaStream_t stream) {
+    WGB_REQUIRE(skip_acc && b_end && x && batch > 0 && T > 0, "bad arguments");
+    WGB_REQUIRE(n_half >= 1 && n_half <= 4, "n_half must be in 1..4 (got %d)", n_half);
+    WGB_REQUIRE(direction == 0 || direction == 1, "direction must be 0 (infer) or 1 (forward)");
+    WGB_REQUIRE(direction == 1 ? log_s != nullptr : w_mix != nullptr, "missing log_s / w_mix for this direction");
+    if (h_next) {
+        WGB_REQUIRE(direction == 0, "the fused WN.start of the next flow exists for the infer direction only");
+        WGB_REQUIRE(next_w_start && next_b_start && next_n_half >= 1 && next_n_half <= 4 && h_next_batch_rows >= T,
+                    "bad next-flow start arguments");
+    } else {
+        next_n_half = 1;
+    }
+    const long long rows = static_cast<long long>(batch) * T;
+    const long long blocks = (rows + 3) / 4;
+    const int grid = static_cast<int>(blocks < 148LL * 8 ? blocks : 148LL * 8);
+    __nv_bfloat16* hn = static_cast<__nv_bfloat16*>(h_next);
+#define WGB_EFA_CASE(NH)                                                                                              \
+    case NH:                                                                                                          \
+        if (direction == 0)                                                                                           \
+            end_from_acc_kernel<NH, 0><<<grid, 256, 0, stream>>>(skip_acc, b_end, x, w_mix, log_s, rows, T, next_w_start, \
+                                                                 next_b_start, next_n_half, hn, h_next_batch_rows);  \
+        else                                                                                                          \
+            end_from_acc_kernel<NH, 1><<<grid, 256, 0, stream>>>(skip_acc, b_end, x, w_mix, log_s, rows, T, next_w_start, \
+                                                                 next_b_start, next_n_half, hn, h_next_batch_rows);  \
+        break;
+    switch (n_half) {
+        WGB_EFA_CASE(1)
+        WGB_EFA_CASE(2)
+        WGB_EFA_CASE(3)
+        WGB_EFA_CASE(4)
+    }
+#undef WGB_EFA_CASE
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
 // ------------------------------------------------------------------------------------ FP32 end + coupling
 // One warp per row: out = W_end * skip + b_end (glow.py:175), then the affine coupling and, for
 // infer, the inverse 1x1 conv (glow.py:277-282); forward writes log_s (glow.py:241-246).

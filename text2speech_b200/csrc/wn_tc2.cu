@@ -45,12 +45,14 @@ constexpr int kThreadsRes = 224;      // + warp 6: h-tile loader / storer
 constexpr int kNCh = 512;
 constexpr int kNCond = 640;
 
-enum Mode { GATE = 0, RES = 1, SKIP_END = 2, GATE_MEL = 3 };
+enum Mode { GATE = 0, RES = 1, SKIP_END = 2, GATE_MEL = 3, GATE_MEL_ACC = 4 };   // _ACC: + skip accumulation in the epilogue
+__host__ __device__ constexpr bool is_mel(int mode) { return mode == GATE_MEL || mode == GATE_MEL_ACC; }
 constexpr int kPhases = 32;          // group steps per mel frame (hop 256 / n_group 8)
 constexpr int kMelK = 320;           // 4 upsample taps x 80 mel channels
 
 // Shared memory (offsets from a 1024 B aligned base): [TMA ring][mode extra][barriers]
 //   GATE      6 stages + 4 KB bias (sigmoid half pre-halved)
+//   GATE_MEL  6 stages + 4 KB bias + 16 KB W_end W_skip_i (fp32 [512][8]) for the skip accumulation in the epilogue
 //   RES       4 stages + 64 KB h tile + 2 KB bias
 //   SKIP_END  6 stages + 16 KB W_end^T + 10 KB WN.start weights of the next flow
 template <int MODE>
@@ -58,7 +60,7 @@ struct Smem {
     static constexpr int kStages = MODE == RES ? 4 : 6;
     static constexpr int kExtraOff = kStages * kStageBytes;
     static constexpr int kExtraBytes =
-        (MODE == GATE || MODE == GATE_MEL) ? 2 * kNCh * 4
+        (MODE == GATE || MODE == GATE_MEL) ? 2 * kNCh * 4 : MODE == GATE_MEL_ACC ? 2 * kNCh * 4 + kNCh * 8 * 4
                                            : (MODE == RES ? kBlockM * kBlockN * 2 + kNCh * 4 : kNCh * 8 * 4 + kNCh * 5 * 4);
     static constexpr int kBarOff = kExtraOff + kExtraBytes;
     static constexpr int kTotal = 1024 + kBarOff + 256;
@@ -71,6 +73,13 @@ struct Params {
                                   // layout), 128-frame blocks per sequence
     int f_pad, f_real;            // GATE_MEL padded layout: frame pitch per utterance (> f_real: guard frames of zeros
                                   // separate the utterances) and real frames per utterance; f_pad = 0: per-utterance tiles
+    // GATE_MEL, optional: skip path accumulated in the epilogue.  w_comp fp32 [512][8] = (W_end W_skip_i)^T of THIS
+    // layer; skip_acc fp32 [4 passes][rows_total][8]: slot (pass, row) += sum over the pass's 128 channels of
+    // acts * w_comp (stored instead of added when skip_first).  One thread owns a slot: deterministic.
+    const float* w_comp;
+    float* skip_acc;
+    long long rows_total;
+    int skip_first;
     const float* bias;            // GATE [1024] packed order, RES [512]
     __nv_bfloat16* acts_out;      // GATE [B,T,512]
     const float* w_end;           // SKIP_END [512][8] fp32 (rows >= 2*n_half zero)
@@ -182,7 +191,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         tma_prefetch_desc(&map_a0);
         tma_prefetch_desc(&map_a1);
         tma_prefetch_desc(&map_w);
-        if constexpr (MODE == RES || MODE == GATE_MEL) tma_prefetch_desc(&map_c);
+        if constexpr (MODE == RES || is_mel(MODE)) tma_prefetch_desc(&map_c);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&hfull_bar[i], 1);
             mbar_init(&hready_bar[i], 4);      // the four epilogue warps
@@ -200,10 +209,13 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     if (warp == 1) tmem_alloc_2sm(tmem_slot, kTmemCols);
     if (warp >= 2 && warp < 6) {
         const int i0 = threadIdx.x - 64;
-        if constexpr (MODE == GATE || MODE == GATE_MEL) {
+        if constexpr (MODE == GATE || is_mel(MODE)) {
             // packed column c of pass p: tanh row for (c & 255) < 128, else the matching sigmoid row, whose
             // pre-activation is halved (sigmoid(b) = 0.5 tanh(b/2) + 0.5)
             for (int i = i0; i < 2 * kNCh; i += 128) s_f32[i] = p.bias[i] * ((i & 128) ? 0.5f : 1.f);
+            if constexpr (MODE == GATE_MEL_ACC) {
+                for (int i = i0; i < kNCh * 8; i += 128) s_f32[2 * kNCh + i] = p.w_comp[i];
+            }
         } else if constexpr (MODE == RES) {
             for (int i = i0; i < kNCh; i += 128) s_rbias[i] = p.bias[i];
         } else {
@@ -238,11 +250,11 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 const bool valid = tile < p.n_tiles;
                 const int b = valid ? tile / p.tiles_per_b : 0;
                 // first row (GATE_MEL: first frame) of this CTA's tile; an absent second tile reads all-OOB rows = zeros
-                const int t0 = valid ? (tile % p.tiles_per_b) * kBlockM : (MODE == GATE_MEL ? p.frames : p.T) + 4 * kBlockM;
+                const int t0 = valid ? (tile % p.tiles_per_b) * kBlockM : (is_mel(MODE) ? p.frames : p.T) + 4 * kBlockM;
                 for (int pp = 0; pp < p.ppi; ++pp) {
                     const int vpass = (item % groups) * p.ppi + pp;
                     // GATE_MEL enumerates (phase, pass) as 128 virtual passes: pass fastest, then the phase
-                    const int pass = MODE == GATE_MEL ? (vpass & 3) : vpass;
+                    const int pass = is_mel(MODE) ? (vpass & 3) : vpass;
                     const int phase = vpass >> 2;
                     for (int kc = 0; kc < p.n_chunks; ++kc) {
                         mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
@@ -257,7 +269,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             } else {
                                 tma_load_3d_2sm(sa, &map_a1, bar, (kc - 24) * kBlockK, t0, b);
                             }
-                        } else if constexpr (MODE == GATE_MEL) {
+                        } else if constexpr (is_mel(MODE)) {
                             if (kc < 24) {
                                 // row (f, phase) of the tile needs h at group step 32 f + phase + (tap-1) d = frame
                                 // f + (q >> 5), phase q & 31 with q = phase + (tap-1) d (floor / mod, q may be < 0);
@@ -273,7 +285,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             tma_load_3d_2sm(sa, &map_a0, bar, (kc & 7) * kBlockK, t0, (kc >> 3) * p.batch + b);
                         }
                         const int w_row = pass * kBlockN + static_cast<int>(rank) * kHalfN;
-                        if (MODE == GATE_MEL && kc >= 24)      // phase-specific composed conditioning weight [32*1024][320]
+                        if (is_mel(MODE) && kc >= 24)      // phase-specific composed conditioning weight [32*1024][320]
                             tma_load_2d_2sm(sb, &map_c, bar, (kc - 24) * kBlockK, phase * (2 * kNCh) + w_row);
                         else
                             tma_load_2d_2sm(sb, &map_w, bar, kc * kBlockK, w_row);
@@ -372,7 +384,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             int t = valid ? (tile % p.tiles_per_b) * kBlockM + row : p.T;
             bool live = t < p.T;
             int bb = b;
-            if constexpr (MODE == GATE_MEL) {                 // phase-major tile: row = frame, t = 32 frame + phase
+            if constexpr (is_mel(MODE)) {                     // phase-major tile: row = frame, t = 32 frame + phase
                 live = valid && t < p.frames;
                 if (p.f_pad) {                                // padded layout: one frame axis over all utterances
                     bb = t / p.f_pad;
@@ -388,13 +400,30 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 
             for (int pp = 0; pp < p.ppi; ++pp, ++acc_it) {
                 const int vpass = (item % groups) * p.ppi + pp;
-                const int pass = MODE == GATE_MEL ? (vpass & 3) : vpass;
+                const int pass = is_mel(MODE) ? (vpass & 3) : vpass;
                 const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                // GATE_MEL skip accumulation: fetch this thread's slot before waiting for the accumulator
+                float sk[8];
+                float4 prev0 = make_float4(0.f, 0.f, 0.f, 0.f), prev1 = prev0;
+                float* slot = nullptr;
+                bool do_skip = false;
+                if constexpr (MODE == GATE_MEL_ACC) {
+                    do_skip = true;
+                    {
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) sk[m] = 0.f;
+                        slot = p.skip_acc + (static_cast<size_t>(pass) * p.rows_total + grow) * 8;
+                        if (live && !p.skip_first) {
+                            prev0 = *reinterpret_cast<const float4*>(slot);
+                            prev1 = *reinterpret_cast<const float4*>(slot + 4);
+                        }
+                    }
+                }
                 mbar_wait(&tfull_bar[as], aph, 400 + as);
                 tc_fence_after_sync();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBlockN;
 
-                if constexpr (MODE == GATE || MODE == GATE_MEL) {
+                if constexpr (MODE == GATE || is_mel(MODE)) {
                     const float4* bt4 = reinterpret_cast<const float4*>(s_f32 + pass * kBlockN);
                     const float4* bs4 = bt4 + kHalfN / 4;
                     __nv_bfloat16* dst = p.acts_out + grow * kNCh + pass * 128;
@@ -419,12 +448,39 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             __nv_bfloat162 h01 = __floats2bfloat162_rn(g0, g1), h23 = __floats2bfloat162_rn(g2, g3);
                             packed[2 * j] = *reinterpret_cast<uint32_t*>(&h01);
                             packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h23);
+                            if constexpr (MODE == GATE_MEL_ACC) {
+                                {                                      // 4 channels x [8] composed skip/end weights
+                                    const float4* wc = reinterpret_cast<const float4*>(s_f32 + 2 * kNCh) +
+                                                       (pass * 128 + ch * 32 + 4 * j) * 2;
+                                    const float gv[4] = {g0, g1, g2, g3};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float4 w0 = wc[2 * e], w1 = wc[2 * e + 1];
+                                        sk[0] = fmaf(gv[e], w0.x, sk[0]);
+                                        sk[1] = fmaf(gv[e], w0.y, sk[1]);
+                                        sk[2] = fmaf(gv[e], w0.z, sk[2]);
+                                        sk[3] = fmaf(gv[e], w0.w, sk[3]);
+                                        sk[4] = fmaf(gv[e], w1.x, sk[4]);
+                                        sk[5] = fmaf(gv[e], w1.y, sk[5]);
+                                        sk[6] = fmaf(gv[e], w1.z, sk[6]);
+                                        sk[7] = fmaf(gv[e], w1.w, sk[7]);
+                                    }
+                                }
+                            }
                         }
                         if (live) {
                             uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                        }
+                    }
+                    if constexpr (MODE == GATE_MEL_ACC) {
+                        if (live) {
+                            *reinterpret_cast<float4*>(slot) =
+                                make_float4(prev0.x + sk[0], prev0.y + sk[1], prev0.z + sk[2], prev0.w + sk[3]);
+                            *reinterpret_cast<float4*>(slot + 4) =
+                                make_float4(prev1.x + sk[4], prev1.y + sk[5], prev1.z + sk[6], prev1.w + sk[7]);
                         }
                     }
                 } else if constexpr (MODE == RES) {
@@ -634,7 +690,8 @@ int tc2_wn_gate(const void* h, const void* cond, const void* w_packed, const flo
 // upsample im2col); w_packed bf16 [1024][2176] (only the 1536 in_layers columns are read); w_mel bf16
 // [32][1024][320] = per-phase W_cond U_phase in the packed row order; bias fp32 [1024] = b_in + b_cond + W_cond b_up.
 int tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, const void* w_mel, const float* bias,
-                    void* acts, int batch, int T, int frames_pad, int dilation, cudaStream_t stream) {
+                    void* acts, int batch, int T, int frames_pad, int dilation, const float* w_comp, float* skip_acc,
+                    int skip_first, cudaStream_t stream) {
     using namespace tc2;
     WGB_REQUIRE(h && mel_stack && w_packed && w_mel && bias && acts, "null pointer");
     WGB_REQUIRE(dilation >= 1, "dilation must be >= 1");
@@ -656,6 +713,9 @@ int tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, 
     p.n_tiles = p.batch * p.n_fblk;
     p.n_pass = 4 * kPhases; p.ppi = 1; p.n_chunks = (3 * kNCh + kMelK) / kBlockK; p.dilation = dilation;
     p.bias = bias; p.acts_out = static_cast<__nv_bfloat16*>(acts);
+    WGB_REQUIRE((w_comp == nullptr) == (skip_acc == nullptr), "w_comp and skip_acc go together");
+    p.w_comp = w_comp; p.skip_acc = skip_acc; p.skip_first = skip_first;
+    p.rows_total = static_cast<long long>(batch) * T;
     CUtensorMap mh, mm, mw, mv;
     {
         const uint64_t seq_rows = static_cast<uint64_t>(kPhases) * (padded ? frames_pad : frames);
@@ -667,7 +727,7 @@ int tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, 
     if (int e = act_map(&mm, mel_stack, kMelK, p.frames, p.batch)) return e;
     if (int e = weight_half_map(&mw, w_packed, 2 * kNCh, 3 * kNCh + kNCond)) return e;
     if (int e = weight_half_map(&mv, w_mel, kPhases * 2 * kNCh, kMelK)) return e;
-    return launch<GATE_MEL, 0, 0>(mh, mm, mw, mv, p, stream);
+    return skip_acc ? launch<GATE_MEL_ACC, 0, 0>(mh, mm, mw, mv, p, stream) : launch<GATE_MEL, 0, 0>(mh, mm, mw, mv, p, stream);
 }
 
 static int h_map(CUtensorMap* m, const void* base, int T, int batch, long long batch_rows) {

@@ -22,8 +22,11 @@ Tensor = torch.Tensor
 # Which tcgen05 kernels the BF16 path uses: "pair" = CTA pairs (cta_group::2, UMMA M = 256), "single" = one CTA per tile.
 GATE_KERNEL = os.environ.get("WGB_GATE_KERNEL", "pair")
 RES_KERNEL = os.environ.get("WGB_RES_KERNEL", "pair")
-# skip path: "skip16" = WN.end composed with the skip GEMM (one N = 16 sweep, HBM-bound); "pair" / "single" = the
-# K = 4096 x N = 512 GEMM with WN.end in the epilogue
+# skip path: "skip16" (default) = WN.end composed with the skip GEMM, one N = 16 tcgen05 sweep over the stored
+# activations (HBM-bound); "acc" = the same product accumulated in the gate kernel's epilogue (composed-conditioning
+# path only, elsewhere it means "skip16"; measured SLOWER: +0.3 ms per gate launch, 671 vs 647 ms per step, kept as a
+# tested variant because it needs no acts_all buffer); "pair" / "single" = the K = 4096 x N = 512 GEMM with WN.end in
+# the epilogue
 SKIP_KERNEL = os.environ.get("WGB_SKIP_KERNEL", "skip16")
 # infer: run WN.start of flow k-1 inside the skip+end kernel of flow k (one launch and one pass over x less per flow)
 FUSE_START = os.environ.get("WGB_FUSE_START", "1") == "1"
@@ -89,7 +92,8 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int
     coupling.  Returns True when that fused start was issued."""
     b, t = x.shape[0], x.shape[1]
     s = _lib.stream_ptr()
-    h0, h1, acts_all = bufs
+    h0, h1, acts_all = bufs[:3]
+    skip_acc = bufs[3] if len(bufs) > 3 else None     # "acc" skip path: [4, B*T, 8] fp32, one acts buffer
     h_rows = h0.shape[1]                      # row pitch per utterance: t, or 32 * frames_pad in the padded layout
     gate = "wgb_tc2_wn_gate" if GATE_KERNEL == "pair" else "wgb_tc_wn_gate"
     res = "wgb_tc2_wn_res" if RES_KERNEL == "pair" else "wgb_tc_wn_res"
@@ -98,16 +102,18 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int
         _lib.call("wgb_wn_start_padded", x, fl["w_start"], fl["b_start"], h0, 1, b, t, h_rows, pk.n_ch, fl["n_half"], s)
     cur, nxt = h0, h1
     for i in range(pk.n_layers):
+        acts = acts_all[i if skip_acc is None else 0]
         if isinstance(cond, tuple):           # ("mel", mel_stack): conditioning composed with the upsampler
-            _lib.call("wgb_tc2_wn_gate_mel", cur, cond[1], fl["w_gate"][i], fl["w_mel"][i], fl["b_mel"][i], acts_all[i],
-                      b, t, h_rows // 32, 2 ** i, s)
+            _lib.call("wgb_tc2_wn_gate_mel", cur, cond[1], fl["w_gate"][i], fl["w_mel"][i], fl["b_mel"][i], acts,
+                      b, t, h_rows // 32, 2 ** i, fl["w_comp"][i] if skip_acc is not None else None, skip_acc,
+                      int(i == 0), s)
         else:
-            _lib.call(gate, cur, cond, fl["w_gate"][i], fl["b_gate"][i], acts_all[i], b, t, 2 ** i, s)
+            _lib.call(gate, cur, cond, fl["w_gate"][i], fl["b_gate"][i], acts, b, t, 2 ** i, s)
         if i < pk.n_layers - 1:
             if RES_KERNEL == "pair":
-                _lib.call(res, acts_all[i], fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, h_rows, s)
+                _lib.call(res, acts, fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, h_rows, s)
             else:
-                _lib.call(res, acts_all[i], fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, s)
+                _lib.call(res, acts, fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, s)
             cur, nxt = nxt, cur
     args = (acts_all, pk.n_layers, fl["w_skip"], fl["w_end_t"], fl["b_end"], x,
             fl["w_mix_inv"] if direction == 0 else None, log_s, b, t, fl["n_half"], direction)
@@ -115,7 +121,12 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int
         _lib.call(skip_end, *args, s)
         return False
     fuse = direction == 0 and next_fl is not None and FUSE_START
-    if SKIP_KERNEL == "skip16":
+    if skip_acc is not None:
+        _lib.call("wgb_end_from_acc", skip_acc, fl["b_end"], x, fl["w_mix_inv"] if direction == 0 else None, log_s, b, t,
+                  fl["n_half"], direction, *((next_fl["w_start"], next_fl["b_start"], next_fl["n_half"], h0, h_rows)
+                                             if fuse else (None, None, 0, None, 0)), s)
+        return fuse
+    if SKIP_KERNEL in ("skip16", "acc"):
         skip_end = "wgb_tc_wn_skip16_end"
         args = (acts_all, pk.n_layers, fl["w_skip16"], fl["b_end"], x,
                 fl["w_mix_inv"] if direction == 0 else None, log_s, b, t, fl["n_half"], direction)
@@ -155,12 +166,16 @@ def _wn_fp32(pk: PackedWaveGlow, fl: dict, x: Tensor, cond: Tensor, bufs, direct
 def _alloc(pk: PackedWaveGlow, b: int, t: int, device, h_rows: Optional[int] = None):
     if pk.mode == "bf16":
         bf = torch.bfloat16
+        acc = h_rows is not None and SKIP_KERNEL == "acc"     # composed-conditioning path: skip accumulated by the gate kernel
         if h_rows is not None and h_rows != t:     # padded layout: guard rows are zero and no kernel ever writes them
             h0 = torch.zeros((b, h_rows, pk.n_ch), device=device, dtype=bf)
             h1 = torch.zeros((b, h_rows, pk.n_ch), device=device, dtype=bf)
         else:
             h0 = torch.empty((b, t, pk.n_ch), device=device, dtype=bf)
             h1 = torch.empty((b, t, pk.n_ch), device=device, dtype=bf)
+        if acc:
+            return (h0, h1, torch.empty((1, b, t, pk.n_ch), device=device, dtype=bf),
+                    torch.empty((4, b * t, 8), device=device, dtype=torch.float32))
         return (h0, h1, torch.empty((pk.n_layers, b, t, pk.n_ch), device=device, dtype=bf))
     f32 = torch.float32
     return (torch.empty((b, t, pk.n_ch), device=device, dtype=f32),

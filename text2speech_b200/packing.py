@@ -97,6 +97,16 @@ def pack_skip_end16(w_skip: Tensor, w_end: Tensor):
     return torch.cat([hi, lo], dim=0).contiguous()
 
 
+def pack_skip_end_layers(w_skip: Tensor, w_end: Tensor, n_ch: int):
+    """Per-layer fp32 [L][n_ch][8] = (W_end W_skip_i)^T (zero columns beyond 2*n_half): the weights the gate kernel's
+    epilogue applies to its fp32 activations when it accumulates the skip path (wgb_tc2_wn_gate_mel)."""
+    rows = w_end.shape[0]
+    comp = torch.zeros(8, w_skip.shape[1], dtype=torch.float64)
+    comp[:rows] = w_end[:, :, 0].double() @ w_skip.double()
+    layers = w_skip.shape[1] // n_ch
+    return comp.float().reshape(8, layers, n_ch).permute(1, 2, 0).contiguous()
+
+
 def pack_mix(w: Tensor):
     """convinv weight [C,C,1] -> (W [8,8] fp32, W^-1 [8,8] fp32 via fp64, log|det W| python float).
     The reference inverts in fp32 and caches (glow.py:88-95); fp64 here is strictly more accurate."""
@@ -176,6 +186,7 @@ class PackedWaveGlow:
                 f["b_end"] = b_fold.to(dev)
                 f["w_skip"] = w_skip.to(dev, bf)
                 f["w_skip16"] = pack_skip_end16(w_skip, w_end).to(dev)
+                f["w_comp"] = pack_skip_end_layers(w_skip, w_end, n_ch).to(dev)
                 f["w_gate"], f["b_gate"], f["w_res"], f["b_res"], f["w_mel"], f["b_mel"] = [], [], [], [], [], []
                 for i in range(n_layers):
                     wg, bg = pack_gate(st[p + f"in_layers.{i}.weight"], st[p + f"in_layers.{i}.bias"],

@@ -128,14 +128,21 @@ def main():
         for d in (1, 128):
             variants.append((f"wgb_tc2_wn_gate_mel d={d}", gate_flop, (2048 + 20) * steps,
                              lambda d=d: _lib.call("wgb_tc2_wn_gate_mel", h0, stack, fl["w_gate"][2], fl["w_mel"][2],
-                                                   fl["b_mel"][2], acts_all[2], b, t, args.frames, d, s)))
+                                                   fl["b_mel"][2], acts_all[2], b, t, args.frames, d, None, None, 0, s)))
         fp = args.frames + 4
         h_pad = torch.zeros((b, 32 * fp, 512), device=DEV, dtype=bf)
         h_pad[:, :t] = h0
         stack_pad = torch.randn((b, fp, 320), device=DEV).to(bf)
         variants.append(("wgb_tc2_wn_gate_mel padded d=128", gate_flop, (2048 + 20) * steps,
                          lambda: _lib.call("wgb_tc2_wn_gate_mel", h_pad, stack_pad, fl["w_gate"][2], fl["w_mel"][2],
-                                           fl["b_mel"][2], acts_all[2], b, t, fp, 128, s)))
+                                           fl["b_mel"][2], acts_all[2], b, t, fp, 128, None, None, 0, s)))
+        skip_acc = torch.zeros((4, b * t, 8), device=DEV)
+        variants.append(("wgb_tc2_wn_gate_mel padded + skip acc d=128", gate_flop, (2048 + 20 + 256) * steps,
+                         lambda: _lib.call("wgb_tc2_wn_gate_mel", h_pad, stack_pad, fl["w_gate"][2], fl["w_mel"][2],
+                                           fl["b_mel"][2], acts_all[2], b, t, fp, 128, fl["w_comp"][2], skip_acc, 0, s)))
+        variants.append(("wgb_end_from_acc + next start", 0, (160 + 32 + 1024) * steps,
+                         lambda: _lib.call("wgb_end_from_acc", skip_acc, fl["b_end"], x, fl["w_mix_inv"], None, b, t,
+                                           fl["n_half"], 0, nf["w_start"], nf["b_start"], nf["n_half"], h_pad, 32 * fp, s)))
     variants.append(("wgb_wn_start", 0, (32 + 1024) * steps,
                      lambda: _lib.call("wgb_wn_start", x, fl["w_start"], fl["b_start"], h0, 1, b * t, 512, fl["n_half"], s)))
     out = []
