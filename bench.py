@@ -45,8 +45,9 @@ GATE_ENTRY_POINTS = ("wgb_tc_wn_gate", "wgb_tc2_wn_gate", "wgb_tc2_wn_gate_mel")
 # dram__bytes_read.sum + dram__bytes_write.sum of one gate-GEMM launch at the full per-GPU batch of 64
 # (ncu --set full, profiles/r01c_ncu_full_summary.csv: 6.667 + 1.791 GB); algorithmic bytes are
 # h 1 KB + cond 1.25 KB read + acts 1 KB written per group step = 5.84 GB.  Scales with the per-rank batch.
-GATE_DRAM_BYTES_PER_LAUNCH_B64 = {"wgb_tc2_wn_gate": 8.458e9, "wgb_tc2_wn_gate_mel": None}
-GATE_DRAM_SOURCE = "profiles/r01c_ncu_full_summary.csv"
+GATE_DRAM_BYTES_PER_LAUNCH_B64 = {"wgb_tc2_wn_gate": 8.458e9,         # profiles/r01c_ncu_full_summary.csv
+                                  "wgb_tc2_wn_gate_mel": 5.272e9}     # profiles/r01h_ncu_full_summary.csv (3.489 + 1.783 GB)
+GATE_DRAM_SOURCE = "profiles/r01h_ncu_full_summary.csv (composed gate) / r01c (cond-tensor gate)"
 
 
 def workload_config(n_gpus):

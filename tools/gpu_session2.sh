@@ -13,8 +13,8 @@ CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 timeout 600 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv \
     --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_list.log 2>&1
-# per WN the tcgen05 launches are g r g r ... g s (16): skip 13 -> residual, gate, skip+end
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gate_kernel|wn_tc_kernel' -s 13 -c 3 \
+# per WN the tcgen05 launches are g r g r ... g s (16 per flow): skip 12 -> gate, residual, gate, skip+end, gate
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'pair_kernel|skip16_kernel' -s 12 -c 5 \
     -f -o gpurun_out/${TAG}_prof $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -4 gpurun_out/${TAG}_pytest_gpu.log; tail -3 gpurun_out/${TAG}_smoke.log
 tail -1 gpurun_out/${TAG}_bench_reference.log; tail -1 gpurun_out/${TAG}_bench.log; tail -3 gpurun_out/${TAG}_ncu_full.log
