@@ -226,6 +226,17 @@ def test_end_from_acc(lib, packed_q, k, direction):
         assert bool((h_next[:, T:] == 5.0).all())                 # guard rows untouched
 
 
+def test_cond_mel_packing_on_gpu_matches_cpu(lib):
+    """The composed conditioning weight packed on the GPU (wgb_sgemm_f32, fp32) equals the CPU fp64 composition."""
+    from text2speech_b200.packing import gate_row_order, pack_cond_mel
+    st = oracle.folded_state(util.state_dict("stress"))
+    w_rows = st["WN.4.cond_layers.6.weight"][:, :, 0][gate_row_order(512)].contiguous()
+    v_cpu, b_cpu = pack_cond_mel(w_rows, st["upsample.weight"], st["upsample.bias"], 8)
+    v_gpu, b_gpu = pack_cond_mel(w_rows, st["upsample.weight"], st["upsample.bias"], 8, torch.device(DEV))
+    assert v_gpu.shape == (32, 1024, 320) and v_gpu.is_cuda
+    assert util.rel_l2(v_gpu.cpu(), v_cpu) < 1e-6 and util.rel_l2(b_gpu.cpu(), b_cpu) < 1e-6
+
+
 # ------------------------------------------------------------------------------------ whole model
 
 @pytest.mark.parametrize("dil_i,B,F", [(0, 2, 130), (3, 3, 40), (4, 1, 129), (5, 1, 200), (7, 2, 130), (6, 1, 860)])

@@ -134,23 +134,46 @@ def pack_upsample(w: Tensor, b: Tensor, n_group: int, ld_tap: int):
     return packed.reshape(tt * c_out * n_group, taps * ld_tap).contiguous(), bias_col.float()
 
 
-def pack_cond_mel(w_cond_rows: Tensor, w_up: Tensor, b_up: Tensor, n_group: int, device=None):
+def upsample_phase_operand(w_up: Tensor, b_up: Tensor, n_group: int):
+    """(U^T [32, 4*n_mel, n_mel*n_group] fp32, bias column [n_mel*n_group] fp32): U_phase maps the stacked mel frames
+    (mel[f], mel[f-1], mel[f-2], mel[f-3]) to the regrouped upsampled mel at group step 32 f + phase
+    (glow.py:183-185,252-258); it is the phase's slice of ``pack_upsample``."""
+    c_in = w_up.shape[0]
+    u, b_col = pack_upsample(w_up, b_up, n_group, c_in)          # [32 * 640, 4 * 80], [32 * 640]
+    n_cond = w_up.shape[1] * n_group
+    phases = u.shape[0] // n_cond
+    return u.reshape(phases, n_cond, u.shape[1]).transpose(1, 2).contiguous(), b_col[:n_cond].contiguous()
+
+
+def pack_cond_mel(w_cond_rows: Tensor, w_up: Tensor, b_up: Tensor, n_group: int, device=None, u_t: Tensor = None,
+                  b_col: Tensor = None):
     """Compose cond_layers[i] with WaveGlow.upsample (glow.py:183-185,252-258 + :141-143,161).
 
     For group step t = 32 f + phase, the regrouped upsampled mel is cond[t] = U_phase . stack(mel[f], mel[f-1],
-    mel[f-2], mel[f-3]) + b_up (U_phase [640, 320] = the rows of ``pack_upsample`` belonging to that phase), so
-    W_cond cond[t] = (W_cond U_phase) . stack + W_cond b_up.  ``w_cond_rows`` [2C, 640] is W_cond in whatever
-    row order the caller wants (the gate GEMM's packed order).  Returns (V [32, 2C, 320] fp32, bias_add [2C] fp32),
-    computed in fp64."""
-    c_in = w_up.shape[0]
-    u, b_col = pack_upsample(w_up, b_up, n_group, c_in)          # [32 * 640, 4 * 80], [32 * 640]
-    n_cond = w_cond_rows.shape[1]
-    phases = u.shape[0] // n_cond
-    dev = device if device is not None else w_cond_rows.device
-    w64 = w_cond_rows.to(dev, torch.float64)
-    v = torch.matmul(w64[None], u.to(dev, torch.float64).reshape(phases, n_cond, u.shape[1]))
-    bias_add = w64 @ b_col[:n_cond].to(dev, torch.float64)
-    return v.float(), bias_add.float()
+    mel[f-2], mel[f-3]) + b_up, so W_cond cond[t] = (W_cond U_phase) . stack + W_cond b_up.  ``w_cond_rows`` [2C, 640]
+    is W_cond in whatever row order the caller wants (the gate GEMM's packed order).  Returns
+    (V [32, 2C, 320] fp32, bias_add [2C] fp32).  On a CUDA device the 32 products run through this library's own FP32
+    GEMM (wgb_sgemm_f32); on the CPU (unit tests) in torch fp64.  ``u_t`` / ``b_col`` = a cached
+    ``upsample_phase_operand`` (on ``device``)."""
+    dev = torch.device(device) if device is not None else w_cond_rows.device
+    if u_t is None:
+        u_t, b_col = upsample_phase_operand(w_up, b_up, n_group)
+        u_t, b_col = u_t.to(dev), b_col.to(dev)
+    phases, k_mel, n_cond = u_t.shape
+    rows = w_cond_rows.shape[0]
+    if dev.type != "cuda":
+        w64 = w_cond_rows.to(dev, torch.float64)
+        v = torch.matmul(w64[None], u_t.to(torch.float64).transpose(1, 2))
+        return v.float(), (w64 @ b_col.to(torch.float64)).float()
+    from . import _lib
+    wc = w_cond_rows.to(dev, torch.float32).contiguous()
+    v_t = torch.empty((phases, k_mel, rows), device=dev, dtype=torch.float32)    # V^T: [phase][k][row]
+    with torch.cuda.device(dev):
+        # C[phase][m = k][n = row] = sum_c U^T[phase][k][c] W_cond[row][c]
+        _lib.call("wgb_sgemm_f32", u_t, wc, None, v_t, 0, phases, k_mel, rows, n_cond, n_cond, k_mel * n_cond, n_cond,
+                  rows, k_mel * rows, 0, 0, _lib.stream_ptr())
+    bias_add = (w_cond_rows.double() @ b_col.cpu().double()).float().to(dev)
+    return v_t.transpose(1, 2).contiguous(), bias_add
 
 
 class PackedWaveGlow:
@@ -168,6 +191,9 @@ class PackedWaveGlow:
         dev = device
         bf = torch.bfloat16
         self.flows = []
+        if self.has_mel:
+            u_t, b_col = upsample_phase_operand(st["upsample.weight"], st["upsample.bias"], n_group)
+            u_t, b_col = u_t.to(dev), b_col.to(dev)
         for k in range(n_flows):
             p = f"WN.{k}."
             f: Dict[str, object] = {}
@@ -195,7 +221,8 @@ class PackedWaveGlow:
                     f["b_gate"].append(bg.to(dev))
                     if self.has_mel:
                         taps_k = st[p + f"in_layers.{i}.weight"].shape[1] * st[p + f"in_layers.{i}.weight"].shape[2]
-                        v, b_add = pack_cond_mel(wg[:, taps_k:], st["upsample.weight"], st["upsample.bias"], n_group, dev)
+                        v, b_add = pack_cond_mel(wg[:, taps_k:].contiguous(), st["upsample.weight"], st["upsample.bias"],
+                                                 n_group, dev, u_t, b_col)
                         f["w_mel"].append(v.to(bf).contiguous())
                         f["b_mel"].append((bg.to(dev) + b_add).contiguous())
                     if i < n_layers - 1:
