@@ -199,6 +199,10 @@ WGB_API int wgb_mel_log(const float* raw, float* out, int batch, int F, int n_me
  * stft.py:102-103, done as a magnitude ratio). */
 WGB_API int wgb_denoise_scale(float* spec, const float* bias, float strength, long long rows, int cutoff, int cp,
                       void* stream);
+/* The same spectral subtraction, but writing the result as the bf16 hi / lo operands of the inverse-basis
+ * wgb_tc_gemm_split3 (spec is read once and not modified). */
+WGB_API int wgb_denoise_scale_split(const float* spec, const float* bias, float strength, void* hi, void* lo,
+                                    long long rows, int cutoff, int cp, void* stream);
 /* Griffin-Lim projection step (audio_processing.py:64-66): keep the phase of spec[B,F,2cp], impose the
  * magnitude target[B,cutoff,F] (in place, no atan2/cos/sin: Re,Im *= target/|X|; |X| = 0 -> phase 0). */
 WGB_API int wgb_spec_set_magnitude(float* spec, const float* target, int batch, int F, int cutoff, int cp, void* stream);

@@ -48,6 +48,7 @@ int split_bf16(const float*, void*, void*, long long, cudaStream_t);
 int stft_polar(const float*, float*, float*, float*, int, int, int, int, cudaStream_t);
 int mel_log(const float*, float*, int, int, int, float, cudaStream_t);
 int denoise_scale(float*, const float*, float, long long, int, int, cudaStream_t);
+int denoise_scale_split(const float*, const float*, float, void*, void*, long long, int, int, cudaStream_t);
 int stft_recombine(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 int spec_set_magnitude(float*, const float*, int, int, int, int, cudaStream_t);
 int istft_overlap_add(const float*, const double*, float*, int, int, int, int, cudaStream_t);
@@ -197,6 +198,10 @@ WGB_API int wgb_denoise_scale(float* spec, const float* bias, float strength, lo
 }
 WGB_API int wgb_spec_set_magnitude(float* spec, const float* target, int batch, int F, int cutoff, int cp, void* stream) {
     return spec_set_magnitude(spec, target, batch, F, cutoff, cp, S(stream));
+}
+WGB_API int wgb_denoise_scale_split(const float* spec, const float* bias, float strength, void* hi, void* lo, long long rows,
+                                    int cutoff, int cp, void* stream) {
+    return denoise_scale_split(spec, bias, strength, hi, lo, rows, cutoff, cp, S(stream));
 }
 WGB_API int wgb_stft_recombine(const float* mag, const float* phase, float* spec, int batch, int F, int cutoff, int cp,
                        void* stream) {

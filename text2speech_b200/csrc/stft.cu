@@ -118,9 +118,31 @@ __global__ void stft_polar_kernel(const float* __restrict__ spec, float* __restr
     }
 }
 
+// channels-last only (the mel path): mag_cl[row, k] = |spec[row, k] + i spec[row, cp + k]|, k fastest so that both the
+// reads and the writes are contiguous; 4 bins per thread (cp % 4 == 0)
+__global__ void stft_mag_cl_kernel(const float* __restrict__ spec, float* __restrict__ mag_cl, int cp, long long total4) {
+    const int cp4 = cp >> 2;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = i / cp4;
+        const int k4 = static_cast<int>(i - row * cp4);
+        const float4 re = reinterpret_cast<const float4*>(spec + row * 2 * cp)[k4];
+        const float4 im = reinterpret_cast<const float4*>(spec + row * 2 * cp + cp)[k4];
+        reinterpret_cast<float4*>(mag_cl + row * cp)[k4] =
+            make_float4(sqrtf(re.x * re.x + im.x * im.x), sqrtf(re.y * re.y + im.y * im.y),
+                        sqrtf(re.z * re.z + im.z * im.z), sqrtf(re.w * re.w + im.w * im.w));
+    }
+}
+
 int stft_polar(const float* spec, float* mag, float* phase, float* mag_cl, int batch, int F, int cutoff, int cp,
                cudaStream_t stream) {
     WGB_REQUIRE(spec && batch > 0 && F > 0 && cutoff > 0 && cp >= cutoff, "bad arguments");
+    if (mag_cl && !mag && !phase && cp % 4 == 0) {
+        const long long total4 = static_cast<long long>(batch) * F * (cp >> 2);
+        stft_mag_cl_kernel<<<grid_for(total4, 256), 256, 0, stream>>>(spec, mag_cl, cp, total4);
+        WGB_LAUNCH_CHECK();
+        return WGB_OK;
+    }
     const long long total = static_cast<long long>(batch) * cp * F;
     stft_polar_kernel<<<grid_for(total, 256), 256, 0, stream>>>(spec, mag, phase, mag_cl, F, cutoff, cp, total);
     WGB_LAUNCH_CHECK();
@@ -202,6 +224,39 @@ int spec_set_magnitude(float* spec, const float* target, int batch, int F, int c
     WGB_REQUIRE(spec && target && batch > 0 && F > 0 && cutoff > 0 && cp >= cutoff, "bad arguments");
     const long long total = static_cast<long long>(batch) * F * cp;
     spec_set_magnitude_kernel<<<grid_for(total, 256), 256, 0, stream>>>(spec, target, F, cutoff, cp, total);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// Spectral subtraction fused with the hi/lo split that feeds the inverse-basis tensor-core GEMM: spec is read once and
+// never written back (denoiser.py:36-39 + stft.py:102-103 + the operand split of wgb_tc_gemm_split3).
+__global__ void denoise_scale_split_kernel(const float* __restrict__ spec, const float* __restrict__ bias, float strength,
+                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int cutoff,
+                                           int cp, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = i / cp;
+        const int k = static_cast<int>(i - row * cp);
+        const float* s = spec + row * 2 * cp;
+        float re = s[k], im = s[cp + k];
+        if (k < cutoff) {
+            const float m = sqrtf(re * re + im * im);
+            const float m2 = fmaxf(m - bias[k] * strength, 0.f);
+            const float g = m > 0.f ? m2 / m : 0.f;
+            re = (m > 0.f) ? re * g : m2;
+            im = im * g;
+        }
+        split_store(re, hi, lo, row * 2 * cp + k);
+        split_store(im, hi, lo, row * 2 * cp + cp + k);
+    }
+}
+
+int denoise_scale_split(const float* spec, const float* bias, float strength, void* hi, void* lo, long long rows, int cutoff,
+                        int cp, cudaStream_t stream) {
+    WGB_REQUIRE(spec && bias && hi && lo && rows > 0 && cutoff > 0 && cp >= cutoff, "bad arguments");
+    const long long total = rows * cp;
+    denoise_scale_split_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+        spec, bias, strength, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), cutoff, cp, total);
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }

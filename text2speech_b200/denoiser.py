@@ -38,7 +38,4 @@ class Denoiser(torch.nn.Module):
         """audio [B, N] -> denoised [B, 1, N'] with N' = hop * (N // hop)  (denoiser.py:35-40)."""
         audio = audio.to(self.bias_spec.device).float().contiguous()
         spec, frames, cp = self.stft._spectrum(audio)
-        b = audio.shape[0]
-        _lib.call("wgb_denoise_scale", spec, self.bias_spec.reshape(-1).contiguous(), float(strength), b * frames,
-                  self.stft.cutoff, cp, _lib.stream_ptr())
-        return self.stft._synthesize(spec, frames, cp)
+        return self.stft._synthesize(spec, frames, cp, denoise=(self.bias_spec.reshape(-1).contiguous(), strength))

@@ -28,12 +28,18 @@ class TacotronSTFT(torch.nn.Module):
         return dynamic_range_decompression(magnitudes)
 
     def _mel_packed(self, device, cp):
+        """(mel basis [n_mel, k_used] fp32 on device, k_used): only the leading bins that carry any weight take part
+        in the matmul (bins above mel_fmax are exactly zero: 372 of 513 at 22.05 kHz / 8 kHz)."""
         key = (str(device), cp, self.mel_basis.data_ptr(), self.mel_basis._version)
         if self._mel_pack is None or self._mel_pack[0] != key:
-            w = torch.zeros((self.n_mel_channels, cp), dtype=torch.float32)
-            w[:, : self.mel_basis.shape[1]] = self.mel_basis.detach().float().cpu()
-            self._mel_pack = (key, w.to(device))
-        return self._mel_pack[1]
+            basis = self.mel_basis.detach().float().cpu()
+            nz = torch.nonzero(basis.abs().sum(0))
+            k_used = min(cp, _round4(int(nz.max()) + 1 if nz.numel() else 4))
+            w = torch.zeros((self.n_mel_channels, k_used), dtype=torch.float32)
+            n = min(k_used, basis.shape[1])
+            w[:, :n] = basis[:, :n]
+            self._mel_pack = (key, w.to(device), k_used)
+        return self._mel_pack[1], self._mel_pack[2]
 
     def mel_spectrogram(self, y: torch.Tensor) -> torch.Tensor:
         """y [B, T] in [-1, 1] (CUDA) -> log-mel [B, n_mel_channels, T // hop + 1]."""
@@ -48,8 +54,9 @@ class TacotronSTFT(torch.nn.Module):
         mag_cl = torch.empty((b, frames, cp), device=y.device, dtype=torch.float32)
         _lib.call("wgb_stft_polar", spec, None, None, mag_cl, b, frames, self.stft_fn.cutoff, cp, s)
         raw = torch.empty((b, frames, self.n_mel_channels), device=y.device, dtype=torch.float32)
-        _lib.call("wgb_sgemm_f32", mag_cl, self._mel_packed(y.device, cp), None, raw, 0, 1, b * frames,
-                  self.n_mel_channels, cp, cp, 0, cp, self.n_mel_channels, 0, 0, 0, s)
+        w_mel, k_used = self._mel_packed(y.device, cp)
+        _lib.call("wgb_sgemm_f32", mag_cl, w_mel, None, raw, 0, 1, b * frames,
+                  self.n_mel_channels, k_used, cp, 0, k_used, self.n_mel_channels, 0, 0, 0, s)
         out = torch.empty((b, self.n_mel_channels, frames), device=y.device, dtype=torch.float32)
         _lib.call("wgb_mel_log", raw, out, b, frames, self.n_mel_channels, 1e-5, s)
         return out

@@ -123,17 +123,24 @@ class STFT(torch.nn.Module):
                   hop, ld_pad, length, 2 * cp, frames * 2 * cp, 0, 0, s)
         return spec, frames, cp
 
-    def _synthesize(self, spec: torch.Tensor, frames: int, cp: int) -> torch.Tensor:
-        """spec [B, F, 2cp] -> [B, 1, hop*(F-1)] (stft.py:105-128)."""
+    def _synthesize(self, spec: torch.Tensor, frames: int, cp: int, denoise=None) -> torch.Tensor:
+        """spec [B, F, 2cp] -> [B, 1, hop*(F-1)] (stft.py:105-128).  denoise = (bias_spec [cutoff], strength): apply
+        the Denoiser's spectral subtraction on the way (denoiser.py:36-38), fused with the operand split."""
         _, inv, win_sq, _ = self._packed(spec.device)
         b = spec.shape[0]
         length, hop = self.filter_length, self.hop_length
         s = _lib.stream_ptr()
         fr = torch.empty((b, frames, length), device=spec.device, dtype=torch.float32)
+        if denoise is not None and not self._use_tc():
+            _lib.call("wgb_denoise_scale", spec, denoise[0], float(denoise[1]), b * frames, self.cutoff, cp, s)
         if self._use_tc():
             hi = torch.empty((b * frames, 2 * cp), device=spec.device, dtype=torch.bfloat16)
             lo = torch.empty_like(hi)
-            _lib.call("wgb_split_bf16", spec, hi, lo, spec.numel(), s)
+            if denoise is not None:
+                _lib.call("wgb_denoise_scale_split", spec, denoise[0], float(denoise[1]), hi, lo, b * frames, self.cutoff,
+                          cp, s)
+            else:
+                _lib.call("wgb_split_bf16", spec, hi, lo, spec.numel(), s)
             _lib.call("wgb_tc_gemm_split3", hi, lo, inv, None, fr, 1, b * frames, length, 2 * cp, 2 * cp,
                       b * frames * 2 * cp, s)
         else:

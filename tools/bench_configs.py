@@ -38,6 +38,31 @@ def timeit(fn, warmup=3, iters=5):
     return statistics.median(ms), min(ms)
 
 
+def breakdown(fn):
+    """Per-C-ABI-entry-point CUDA-event totals of one call of fn (after it has been warmed up)."""
+    from text2speech_b200 import _lib
+    raw, events = _lib.call, []
+
+    def timed_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        raw(name, *a)
+        e1.record()
+        events.append((name, e0, e1))
+
+    _lib.call = timed_call
+    try:
+        fn()
+        torch.cuda.synchronize()
+    finally:
+        _lib.call = raw
+    agg = {}
+    for name, a, b in events:
+        n, ms = agg.get(name, (0, 0.0))
+        agg[name] = (n + 1, ms + a.elapsed_time(b))
+    return {k: {"launches": n, "ms": round(ms, 3)} for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.json"))
@@ -97,12 +122,15 @@ def main():
                 "samples_per_s": n / (med * 1e-3), "algorithmic_gb_s": n * 5.25 / (med * 1e-3) / 1e9,
                 "frac_hbm": n * 5.25 / (med * 1e-3) / 1e9 / peaks["hbm_gbs"],
                 "dense_basis_tflops": frames * (STFT_FLOP_PER_FRAME + 2 * 80 * 513) / (med * 1e-3) / 1e12})
+    out[-1]["breakdown"] = breakdown(lambda: taco.mel_spectrogram(y))
     den = t2s.Denoiser(model)
     med, best = timeit(lambda: den(y, strength=0.01))
     out.append({"config": "cfg5b: Denoiser(strength 0.01) 256 x 220160 samples", "ms_median": med, "ms_best": best,
                 "samples_per_s": n / (med * 1e-3), "algorithmic_gb_s": n * 8 / (med * 1e-3) / 1e9,
                 "frac_hbm": n * 8 / (med * 1e-3) / 1e9 / peaks["hbm_gbs"],
                 "dense_basis_tflops": frames * 2 * STFT_FLOP_PER_FRAME / (med * 1e-3) / 1e12})
+
+    out[-1]["breakdown"] = breakdown(lambda: den(y, strength=0.01))
 
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
