@@ -100,6 +100,17 @@ WGB_API int wgb_tc_wn_skip_end(const void* acts_all, int n_layers, const void* w
 WGB_API int wgb_tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, const void* w_mel,
                                 const float* bias, void* acts, int batch, int T, int frames_pad, int dilation,
                                 const float* w_comp, float* skip_acc, int skip_first, void* stream);
+/* First WN layer with WN.start folded into in_layers[0] (both linear, glow.py:156 + :160, dilation 1):
+ *   in_layers[0](start(a0))[t] = sum_tap (W_in0,tap W_start) a0[t+tap-1] + sum_tap (W_in0,tap b_start) [t+tap-1 in range]
+ * wgb_x_stack writes, per group step, the K = 64 operand row (bf16 hi / lo split of the three a0 taps of the flow state
+ * x [B,T,8] and the in-range indicators; layout in csrc/flow.cu) into out bf16 [B, out_batch_rows, 64];
+ * wgb_tc2_wn_gate_mel0 is wgb_tc2_wn_gate_mel with that operand (x_stack, w0 bf16 [1024][64] from
+ * packing.py:pack_gate0) in place of the three dilated taps of h: K = 64 + 320 instead of 1536 + 320.  The first
+ * layer's in-conv becomes fp32-grade accurate (hi/lo on both sides) instead of reading a bf16-rounded h. */
+WGB_API int wgb_x_stack(const float* x, void* out, int batch, int T, long long out_batch_rows, int n_half, void* stream);
+WGB_API int wgb_tc2_wn_gate_mel0(const void* x_stack, const void* mel_stack, const void* w0, const void* w_mel,
+                                 const float* bias, void* acts, int batch, int T, int frames_pad, const float* w_comp,
+                                 float* skip_acc, int skip_first, void* stream);
 /* WN.end output = sum of the 4 slots of skip_acc + b_end (skip biases folded in), then the affine coupling and W^-1
  * (direction 0, glow.py:277-282) or forward coupling + log_s (direction 1, :241-246), and optionally WN.start of the
  * next flow (as wgb_tc2_wn_skip_end).  Memory-bound: 160 B in, 32 B (+ 1 KB h_next) out per group step. */

@@ -184,6 +184,44 @@ def test_tc_skip_end_coupling(lib, packed_q, k, direction, entry):
         assert util.rel_l2(log_s.cpu(), out[:, n_half:]) <= 1e-4
 
 
+@pytest.mark.parametrize("k,B,F", [(10, 2, 130), (6, 3, 40), (1, 1, 129)])
+def test_tc2_gate_mel0_first_layer_fold(lib, packed_q, k, B, F):
+    """First WN layer with WN.start folded into in_layers[0]: wgb_x_stack + wgb_tc2_wn_gate_mel0 against
+    gate(in_layers[0](start(a0)) + composed conditioning), start and conv in fp32 on the host."""
+    from tests.test_packing import _x_stack_rows
+    from text2speech_b200 import engine
+    from text2speech_b200.packing import gate_row_order
+    pk = packed_q["stress"]
+    st = oracle.folded_state(quantised_state("stress"))
+    fl = pk.flows[k]
+    n_half, T, fp = fl["n_half"], 32 * F, F + 4
+    g = torch.Generator().manual_seed(500 + k)
+    x = torch.randn(B, T, 8, generator=g)
+    mel = syn.synthetic_mel(B, F, seed=23 + k)
+    xs = torch.full((B, 32 * fp, 64), 3.0, device=DEV, dtype=torch.bfloat16)
+    lib.call("wgb_x_stack", x.to(DEV), xs, B, T, 32 * fp, n_half, lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(xs[:, :T].float().cpu(), _x_stack_rows(x, n_half))
+    assert bool((xs[:, T:] == 3.0).all())                       # guard rows untouched
+    stack = engine.mel_stack(pk, mel.to(DEV), fp)
+    base = 8 - 2 * n_half
+    a0 = x[:, :, base: base + n_half].permute(0, 2, 1)
+    h0 = torch.nn.functional.conv1d(a0, st[f"WN.{k}.start.weight"], st[f"WN.{k}.start.bias"])
+    u_in = torch.nn.functional.conv1d(h0, st[f"WN.{k}.in_layers.0.weight"], None, padding=1)
+    u_in = u_in[:, gate_row_order(512)].permute(0, 2, 1)
+    v = fl["w_mel"][0].float().cpu().double()
+    u_c = torch.einsum("pok,bfk->bfpo", v, stack[:, :F].float().cpu().double()).reshape(B, T, 1024)
+    u = u_in.double() + u_c + fl["b_mel"][0].cpu().double()
+    want = torch.cat([torch.tanh(u[:, :, p * 256: p * 256 + 128]) * torch.sigmoid(u[:, :, p * 256 + 128: (p + 1) * 256])
+                      for p in range(4)], dim=2)
+    acts = torch.zeros(B, T, 512, device=DEV, dtype=torch.bfloat16)
+    lib.call("wgb_tc2_wn_gate_mel0", xs, stack, fl["w_gate0"], fl["w_mel"][0], fl["b_mel"][0], acts, B, T, fp,
+             None, None, 0, lib.stream_ptr())
+    torch.cuda.synchronize()
+    err = util.rel_l2(acts.float().cpu(), want)
+    assert err <= util.TOL_LAYER_BF16, err
+
+
 @pytest.mark.parametrize("k,direction", [(11, 0), (5, 0), (0, 0), (11, 1), (4, 1)])
 def test_end_from_acc(lib, packed_q, k, direction):
     """WN.end output from the four skip-accumulator slots, coupling (+ W^-1, + next-flow WN.start)."""
@@ -344,6 +382,26 @@ def test_infer_bf16_composed_conditioning_path(models, golden, recipe):
     assert util.snr_db(a_mel, golden[f"{recipe}_infer_audio"]) >= util.MIN_SNR_DB
     assert util.snr_db(a_mel, a_cond) >= util.MIN_SNR_DB
     assert not torch.equal(a_mel, a_cond)            # really two different kernels
+
+
+def test_first_layer_fold_agrees(models, golden, monkeypatch):
+    """Composed path with and without WN.start folded into in_layers[0]."""
+    from text2speech_b200 import engine
+    m = models["stress"]
+    m.mode = "bf16"
+    mel, z, _ = util.golden_inputs()
+    out = {}
+    try:
+        m.cond_path = "mel"
+        for fold in (True, False):
+            monkeypatch.setattr(engine, "FOLD_START", fold)
+            out[fold] = m.infer(mel.to(DEV), sigma=util.SIGMA, z=z.to(DEV)).cpu()
+    finally:
+        m.cond_path = "auto"
+    assert not torch.equal(out[True], out[False])
+    for audio in out.values():
+        assert util.snr_db(audio, golden["stress_infer_audio"]) >= util.MIN_SNR_DB
+    assert util.snr_db(out[True], out[False]) >= util.MIN_SNR_DB
 
 
 def test_skip_paths_agree(models, golden, monkeypatch):

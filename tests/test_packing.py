@@ -141,3 +141,46 @@ def test_skip_end_composition_matches_skip_sum_then_end():
     a_cat = acts.permute(1, 3, 0, 2).reshape(bsz, t, 4096).double()                          # K index = layer*512 + c
     got = (a_cat @ comp.t())[:, :, :rows] + b_fold[:rows].double()
     assert util.rel_l2(got.permute(0, 2, 1), want) < 1e-5
+
+
+def _x_stack_rows(x, n_half):
+    """Host restatement of wgb_x_stack's row layout (fp32 values of the bf16 entries)."""
+    bsz, t, _ = x.shape
+    base = 8 - 2 * n_half
+    a0 = torch.zeros(bsz, t, 4)
+    a0[:, :, :n_half] = x[:, :, base: base + n_half]
+    taps = torch.zeros(bsz, t, 3, 4)
+    ind = torch.zeros(bsz, t, 3)
+    for tap in range(3):
+        s = tap - 1
+        lo, hi = max(0, -s), min(t, t - s)
+        taps[:, lo:hi, tap] = a0[:, lo + s: hi + s]
+        ind[:, lo:hi, tap] = 1.0
+    flat = taps.reshape(bsz, t, 12)
+    a_hi = flat.bfloat16().float()
+    a_lo = (flat - a_hi).bfloat16().float()
+    rows = torch.zeros(bsz, t, 64)
+    rows[:, :, 0:12], rows[:, :, 12:24], rows[:, :, 24:36] = a_hi, a_lo, a_hi
+    rows[:, :, 36:39], rows[:, :, 39:42] = ind, ind
+    return rows
+
+
+def test_start_folded_into_first_in_layer():
+    """pack_gate0 + the x_stack layout: in_layers[0](start(a0)) == W0 . x_stack row (edges included), packed order."""
+    from text2speech_b200.packing import pack_gate0
+    st = oracle.folded_state(util.state_dict("stress"))
+    for k in (10, 6, 1):                                           # n_half 2, 3, 4
+        p = f"WN.{k}."
+        w_in0, b_in0 = st[p + "in_layers.0.weight"], st[p + "in_layers.0.bias"]
+        w_start, b_start = st[p + "start.weight"][:, :, 0], st[p + "start.bias"]
+        n_half = w_start.shape[1]
+        g = torch.Generator().manual_seed(k)
+        x = torch.randn(2, 37, 8, generator=g)
+        base = 8 - 2 * n_half
+        a0 = x[:, :, base: base + n_half].permute(0, 2, 1)                                   # [B, n_half, T]
+        h0 = torch.nn.functional.conv1d(a0, w_start[:, :, None], b_start)
+        want = torch.nn.functional.conv1d(h0, w_in0, None, padding=1)[:, gate_row_order(512)].permute(0, 2, 1)
+        w0 = pack_gate0(w_in0, w_start, b_start)
+        assert w0.shape == (1024, 64) and w0.dtype == torch.bfloat16
+        got = _x_stack_rows(x, n_half).double() @ w0.double().t()
+        assert util.rel_l2(got, want) < 3e-5, k

@@ -18,7 +18,10 @@ int tc2_wn_gate(const void*, const void*, const void*, const float*, void*, int,
 int tc2_wn_res(const void*, const void*, const float*, const void*, void*, int, int, long long, cudaStream_t);
 int tc2_wn_gate_mel(const void*, const void*, const void*, const void*, const float*, void*, int, int, int, int,
                     const float*, float*, int, cudaStream_t);
+int tc2_wn_gate_mel0(const void*, const void*, const void*, const void*, const float*, void*, int, int, int, const float*,
+                     float*, int, cudaStream_t);
 // flow.cu
+int x_stack(const float*, void*, int, int, long long, int, cudaStream_t);
 int end_from_acc(const float*, const float*, float*, const float*, float*, int, int, int, int, const float*, const float*,
                  int, void*, long long, cudaStream_t);
 int tc2_wn_skip_end(const void*, int, const void*, const float*, const float*, float*, const float*, float*, int, int,
@@ -100,6 +103,15 @@ WGB_API int wgb_tc2_wn_gate_mel(const void* h, const void* mel_stack, const void
                                 const float* w_comp, float* skip_acc, int skip_first, void* stream) {
     return tc2_wn_gate_mel(h, mel_stack, w_packed, w_mel, bias, acts, batch, T, frames_pad, dilation, w_comp, skip_acc,
                            skip_first, S(stream));
+}
+WGB_API int wgb_tc2_wn_gate_mel0(const void* x_stack_, const void* mel_stack, const void* w0, const void* w_mel, const float* bias,
+                                 void* acts, int batch, int T, int frames_pad, const float* w_comp, float* skip_acc,
+                                 int skip_first, void* stream) {
+    return tc2_wn_gate_mel0(x_stack_, mel_stack, w0, w_mel, bias, acts, batch, T, frames_pad, w_comp, skip_acc, skip_first,
+                            S(stream));
+}
+WGB_API int wgb_x_stack(const float* x, void* out, int batch, int T, long long out_batch_rows, int n_half, void* stream) {
+    return x_stack(x, out, batch, T, out_batch_rows, n_half, S(stream));
 }
 WGB_API int wgb_end_from_acc(const float* skip_acc, const float* b_end, float* x, const float* w_mix, float* log_s, int batch,
                              int T, int n_half, int direction, const float* next_w_start, const float* next_b_start,

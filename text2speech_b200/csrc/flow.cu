@@ -114,6 +114,63 @@ int flow_mix(float* x, const float* w, long long rows, int C, cudaStream_t strea
     return WGB_OK;
 }
 
+// ------------------------------------------------------------------------------------ x_stack (first-layer operand)
+// Row t of utterance b (pitch out_batch_rows): 64 bf16 =
+//   [ 0..11] hi(a0[t-1][0..3]), hi(a0[t][0..3]), hi(a0[t+1][0..3])      a0 = x[., 8-2*n_half .. 8-n_half), zero beyond n_half
+//   [12..23] lo parts of the same 12 values (x = hi + lo, both bf16)
+//   [24..35] hi parts again (they meet the lo part of the weight)
+//   [36..38] 1.0 where tap t-1 / t / t+1 lies inside [0, T) (carries W_in0,tap b_start), [39..41] the same again
+//   [42..63] zero
+// the K = 64 operand of wgb_tc2_wn_gate_mel0: WN.start folded into in_layers[0] (glow.py:156,160).
+__global__ void x_stack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int T, long long rows,
+                               long long out_batch_rows, int n_half) {
+    const int base = 8 - 2 * n_half;
+    for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < rows;
+         r += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = r / T;
+        const int t = static_cast<int>(r - b * T);
+        __align__(16) __nv_bfloat16 row[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) row[i] = __float2bfloat16_rn(0.f);
+#pragma unroll
+        for (int tap = 0; tap < 3; ++tap) {
+            const int tt = t + tap - 1;
+            const bool in = tt >= 0 && tt < T;
+            float xv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xv[i] = 0.f;
+            if (in) {
+                *reinterpret_cast<float4*>(&xv[0]) = *reinterpret_cast<const float4*>(x + (r + tap - 1) * 8);
+                *reinterpret_cast<float4*>(&xv[4]) = *reinterpret_cast<const float4*>(x + (r + tap - 1) * 8 + 4);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float v = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v = (i == base + c && c < n_half) ? xv[i] : v;
+                const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                row[tap * 4 + c] = hi;
+                row[12 + tap * 4 + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+                row[24 + tap * 4 + c] = hi;
+            }
+            row[36 + tap] = __float2bfloat16_rn(in ? 1.f : 0.f);
+            row[39 + tap] = row[36 + tap];
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + (b * out_batch_rows + t) * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = reinterpret_cast<const uint4*>(row)[i];
+    }
+}
+
+int x_stack(const float* x, void* out, int batch, int T, long long out_batch_rows, int n_half, cudaStream_t stream) {
+    WGB_REQUIRE(x && out && batch > 0 && T > 0 && out_batch_rows >= T && n_half >= 1 && n_half <= 4, "bad arguments");
+    const long long rows = static_cast<long long>(batch) * T;
+    x_stack_kernel<<<grid_for(rows, 128), 128, 0, stream>>>(x, static_cast<__nv_bfloat16*>(out), T, rows, out_batch_rows,
+                                                           n_half);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
 // ------------------------------------------------------------------------------------ WN.start
 // h[r, c] = b[c] + sum_j W[c, j] * x[r, 8 - 2*n_half + j]   (glow.py:156).  HBM-bound on the 1 KB/row
 // store: each thread owns 8 fixed channels (weights + bias live in registers for the whole kernel) and

@@ -71,6 +71,8 @@ struct Params {
     int n_pass, ppi, n_chunks, dilation;
     int frames, n_fblk;           // GATE_MEL: frames per tiled sequence (one utterance, or all of them in the padded
                                   // layout), 128-frame blocks per sequence
+    int n_tap_chunks;             // GATE_MEL: K chunks of the in_layers part: 24 (three dilated taps of h), or 1 when the
+                                  // first layer reads the pre-stacked flow state instead (x_stack, see tc2_wn_gate_mel0)
     int f_pad, f_real;            // GATE_MEL padded layout: frame pitch per utterance (> f_real: guard frames of zeros
                                   // separate the utterances) and real frames per utterance; f_pad = 0: per-utterance tiles
     // GATE_MEL, optional: skip path accumulated in the epilogue.  w_comp fp32 [512][8] = (W_end W_skip_i)^T of THIS
@@ -270,14 +272,15 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                                 tma_load_3d_2sm(sa, &map_a1, bar, (kc - 24) * kBlockK, t0, b);
                             }
                         } else if constexpr (is_mel(MODE)) {
-                            if (kc < 24) {
+                            if (kc < p.n_tap_chunks) {
                                 // row (f, phase) of the tile needs h at group step 32 f + phase + (tap-1) d = frame
                                 // f + (q >> 5), phase q & 31 with q = phase + (tap-1) d (floor / mod, q may be < 0);
-                                // frames outside [0, F) are zero-filled by TMA = the conv's zero padding
-                                const int q = phase + ((kc >> 3) - 1) * p.dilation;
+                                // frames outside [0, F) are zero-filled by TMA = the conv's zero padding.  With one tap
+                                // chunk (pre-stacked first layer) q = phase: the row itself.
+                                const int q = phase + (p.n_tap_chunks == 1 ? 0 : ((kc >> 3) - 1) * p.dilation);
                                 tma_load_4d_2sm(sa, &map_a0, bar, (kc & 7) * kBlockK, q & (kPhases - 1), t0 + (q >> 5), b);
                             } else {
-                                tma_load_3d_2sm(sa, &map_a1, bar, (kc - 24) * kBlockK, t0, b);
+                                tma_load_3d_2sm(sa, &map_a1, bar, (kc - p.n_tap_chunks) * kBlockK, t0, b);
                             }
                         } else if constexpr (MODE == RES) {
                             tma_load_3d_2sm(sa, &map_a0, bar, kc * kBlockK, t0, b);
@@ -285,8 +288,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             tma_load_3d_2sm(sa, &map_a0, bar, (kc & 7) * kBlockK, t0, (kc >> 3) * p.batch + b);
                         }
                         const int w_row = pass * kBlockN + static_cast<int>(rank) * kHalfN;
-                        if (is_mel(MODE) && kc >= 24)      // phase-specific composed conditioning weight [32*1024][320]
-                            tma_load_2d_2sm(sb, &map_c, bar, (kc - 24) * kBlockK, phase * (2 * kNCh) + w_row);
+                        if (is_mel(MODE) && kc >= p.n_tap_chunks)      // phase-specific composed conditioning weight [32*1024][320]
+                            tma_load_2d_2sm(sb, &map_c, bar, (kc - p.n_tap_chunks) * kBlockK, phase * (2 * kNCh) + w_row);
                         else
                             tma_load_2d_2sm(sb, &map_w, bar, kc * kBlockK, w_row);
                         if (++s == kStages) { s = 0; ph ^= 1; }
@@ -689,11 +692,11 @@ int tc2_wn_gate(const void* h, const void* cond, const void* w_packed, const flo
 // T = 32 * frames; mel_stack bf16 [B, frames, 320] = the four mel frames feeding each frame's group steps (the
 // upsample im2col); w_packed bf16 [1024][2176] (only the 1536 in_layers columns are read); w_mel bf16
 // [32][1024][320] = per-phase W_cond U_phase in the packed row order; bias fp32 [1024] = b_in + b_cond + W_cond b_up.
-int tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, const void* w_mel, const float* bias,
-                    void* acts, int batch, int T, int frames_pad, int dilation, const float* w_comp, float* skip_acc,
-                    int skip_first, cudaStream_t stream) {
+static int gate_mel_launch(const void* a_taps, int tap_channels, int n_tap_chunks, const void* mel_stack, const void* w_taps,
+                           int w_taps_k, const void* w_mel, const float* bias, void* acts, int batch, int T, int frames_pad,
+                           int dilation, const float* w_comp, float* skip_acc, int skip_first, cudaStream_t stream) {
     using namespace tc2;
-    WGB_REQUIRE(h && mel_stack && w_packed && w_mel && bias && acts, "null pointer");
+    WGB_REQUIRE(a_taps && mel_stack && w_taps && w_mel && bias && acts, "null pointer");
     WGB_REQUIRE(dilation >= 1, "dilation must be >= 1");
     WGB_REQUIRE(batch > 0 && T > 0 && T % kPhases == 0, "T (%d) must be a positive multiple of %d group steps", T, kPhases);
     const int frames = T / kPhases;
@@ -711,23 +714,47 @@ int tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, 
     p.n_fblk = ceil_div(p.frames, kBlockM);
     p.tiles_per_b = p.n_fblk;                       // "tiles" = 128-frame blocks; each is visited once per phase and pass
     p.n_tiles = p.batch * p.n_fblk;
-    p.n_pass = 4 * kPhases; p.ppi = 1; p.n_chunks = (3 * kNCh + kMelK) / kBlockK; p.dilation = dilation;
+    p.n_tap_chunks = n_tap_chunks;
+    p.n_pass = 4 * kPhases; p.ppi = 1; p.n_chunks = n_tap_chunks + kMelK / kBlockK; p.dilation = dilation;
     p.bias = bias; p.acts_out = static_cast<__nv_bfloat16*>(acts);
     WGB_REQUIRE((w_comp == nullptr) == (skip_acc == nullptr), "w_comp and skip_acc go together");
     p.w_comp = w_comp; p.skip_acc = skip_acc; p.skip_first = skip_first;
     p.rows_total = static_cast<long long>(batch) * T;
     CUtensorMap mh, mm, mw, mv;
     {
+        const uint64_t row_bytes = static_cast<uint64_t>(tap_channels) * 2;
         const uint64_t seq_rows = static_cast<uint64_t>(kPhases) * (padded ? frames_pad : frames);
-        const uint64_t dims[4] = {kNCh, kPhases, static_cast<uint64_t>(p.frames), static_cast<uint64_t>(p.batch)};
-        const uint64_t strides[3] = {kNCh * 2, static_cast<uint64_t>(kNCh) * 2 * kPhases, static_cast<uint64_t>(kNCh) * 2 * seq_rows};
+        const uint64_t dims[4] = {static_cast<uint64_t>(tap_channels), kPhases, static_cast<uint64_t>(p.frames),
+                                  static_cast<uint64_t>(p.batch)};
+        const uint64_t strides[3] = {row_bytes, row_bytes * kPhases, row_bytes * seq_rows};
         const uint32_t box[4] = {kBlockK, 1, kBlockM, 1};
-        if (int e = make_tmap_bf16(&mh, h, 4, dims, strides, box)) return e;
+        if (int e = make_tmap_bf16(&mh, a_taps, 4, dims, strides, box)) return e;
     }
     if (int e = act_map(&mm, mel_stack, kMelK, p.frames, p.batch)) return e;
-    if (int e = weight_half_map(&mw, w_packed, 2 * kNCh, 3 * kNCh + kNCond)) return e;
+    if (int e = weight_half_map(&mw, w_taps, 2 * kNCh, w_taps_k)) return e;
     if (int e = weight_half_map(&mv, w_mel, kPhases * 2 * kNCh, kMelK)) return e;
     return skip_acc ? launch<GATE_MEL_ACC, 0, 0>(mh, mm, mw, mv, p, stream) : launch<GATE_MEL, 0, 0>(mh, mm, mw, mv, p, stream);
+}
+
+int tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, const void* w_mel, const float* bias,
+                    void* acts, int batch, int T, int frames_pad, int dilation, const float* w_comp, float* skip_acc,
+                    int skip_first, cudaStream_t stream) {
+    using namespace tc2;
+    return gate_mel_launch(h, kNCh, 3 * kNCh / kBlockK, mel_stack, w_packed, 3 * kNCh + kNCond, w_mel, bias, acts, batch, T,
+                           frames_pad, dilation, w_comp, skip_acc, skip_first, stream);
+}
+
+// First WN layer with WN.start folded into its in_layers conv (both linear, glow.py:156 + :160, dilation 1):
+// in_layers[0](start(a0))[t] = sum_tap (W_in0,tap W_start) a0[t+tap-1] + sum_tap (W_in0,tap b_start) [t+tap-1 in range].
+// x_stack bf16 [B, 32*frames_pad, 64] holds, per group step, the hi/lo split of the three a0 taps and the in-range
+// indicators (wgb_x_stack); w0 bf16 [1024][64] the matching composed weights (packing.py:pack_gate0).  The layer then
+// costs K = 64 + 320 instead of 1536 + 320.
+int tc2_wn_gate_mel0(const void* x_stack, const void* mel_stack, const void* w0, const void* w_mel, const float* bias,
+                     void* acts, int batch, int T, int frames_pad, const float* w_comp, float* skip_acc, int skip_first,
+                     cudaStream_t stream) {
+    using namespace tc2;
+    return gate_mel_launch(x_stack, kBlockK, 1, mel_stack, w0, kBlockK, w_mel, bias, acts, batch, T, frames_pad, 1, w_comp,
+                           skip_acc, skip_first, stream);
 }
 
 static int h_map(CUtensorMap* m, const void* base, int T, int batch, long long batch_rows) {

@@ -28,6 +28,8 @@ RES_KERNEL = os.environ.get("WGB_RES_KERNEL", "pair")
 # tested variant because it needs no acts_all buffer); "pair" / "single" = the K = 4096 x N = 512 GEMM with WN.end in
 # the epilogue
 SKIP_KERNEL = os.environ.get("WGB_SKIP_KERNEL", "skip16")
+# composed-conditioning path: fold WN.start into in_layers[0] (first layer reads the stacked flow state, K = 64 + 320)
+FOLD_START = os.environ.get("WGB_FOLD_START", "1") == "1"
 # infer: run WN.start of flow k-1 inside the skip+end kernel of flow k (one launch and one pass over x less per flow)
 FUSE_START = os.environ.get("WGB_FUSE_START", "1") == "1"
 
@@ -92,8 +94,8 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int
     coupling.  Returns True when that fused start was issued."""
     b, t = x.shape[0], x.shape[1]
     s = _lib.stream_ptr()
-    h0, h1, acts_all = bufs[:3]
-    skip_acc = bufs[3] if len(bufs) > 3 else None     # "acc" skip path: [4, B*T, 8] fp32, one acts buffer
+    h0, h1, acts_all = bufs["h0"], bufs["h1"], bufs["acts"]
+    skip_acc = bufs.get("skip_acc")           # "acc" skip path: [4, B*T, 8] fp32, one acts buffer
     h_rows = h0.shape[1]                      # row pitch per utterance: t, or 32 * frames_pad in the padded layout
     gate = "wgb_tc2_wn_gate" if GATE_KERNEL == "pair" else "wgb_tc_wn_gate"
     res = "wgb_tc2_wn_res" if RES_KERNEL == "pair" else "wgb_tc_wn_res"
@@ -103,7 +105,16 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int
     cur, nxt = h0, h1
     for i in range(pk.n_layers):
         acts = acts_all[i if skip_acc is None else 0]
-        if isinstance(cond, tuple):           # ("mel", mel_stack): conditioning composed with the upsampler
+        if i == 0 and isinstance(cond, tuple) and FOLD_START and "w_gate0" in fl:
+            # WN.start folded into in_layers[0]: the operand is the stacked flow state, not h0 (h0 still feeds the
+            # residual GEMM)
+            xs = bufs.get("x_stack")
+            if xs is None:
+                xs = bufs["x_stack"] = torch.empty((b, h_rows, 64), device=x.device, dtype=torch.bfloat16)
+            _lib.call("wgb_x_stack", x, xs, b, t, h_rows, fl["n_half"], s)
+            _lib.call("wgb_tc2_wn_gate_mel0", xs, cond[1], fl["w_gate0"], fl["w_mel"][0], fl["b_mel"][0], acts, b, t,
+                      h_rows // 32, fl["w_comp"][0] if skip_acc is not None else None, skip_acc, 1, s)
+        elif isinstance(cond, tuple):         # ("mel", mel_stack): conditioning composed with the upsampler
             _lib.call("wgb_tc2_wn_gate_mel", cur, cond[1], fl["w_gate"][i], fl["w_mel"][i], fl["b_mel"][i], acts,
                       b, t, h_rows // 32, 2 ** i, fl["w_comp"][i] if skip_acc is not None else None, skip_acc,
                       int(i == 0), s)
@@ -174,9 +185,9 @@ def _alloc(pk: PackedWaveGlow, b: int, t: int, device, h_rows: Optional[int] = N
             h0 = torch.empty((b, t, pk.n_ch), device=device, dtype=bf)
             h1 = torch.empty((b, t, pk.n_ch), device=device, dtype=bf)
         if acc:
-            return (h0, h1, torch.empty((1, b, t, pk.n_ch), device=device, dtype=bf),
-                    torch.empty((4, b * t, 8), device=device, dtype=torch.float32))
-        return (h0, h1, torch.empty((pk.n_layers, b, t, pk.n_ch), device=device, dtype=bf))
+            return {"h0": h0, "h1": h1, "acts": torch.empty((1, b, t, pk.n_ch), device=device, dtype=bf),
+                    "skip_acc": torch.empty((4, b * t, 8), device=device, dtype=torch.float32)}
+        return {"h0": h0, "h1": h1, "acts": torch.empty((pk.n_layers, b, t, pk.n_ch), device=device, dtype=bf)}
     f32 = torch.float32
     return (torch.empty((b, t, pk.n_ch), device=device, dtype=f32),
             torch.empty((b, t, 2 * pk.n_ch), device=device, dtype=f32),

@@ -61,6 +61,30 @@ def pack_gate(w_in: Tensor, b_in: Tensor, w_cond: Tensor, b_cond: Tensor):
     return w[order].contiguous(), (b_in + b_cond)[order].contiguous()
 
 
+def pack_gate0(w_in0: Tensor, w_start: Tensor, b_start: Tensor) -> Tensor:
+    """WN.start folded into in_layers[0] (glow.py:156 + :160; both linear, dilation 1):
+        in_layers[0](start(a0))[t] = sum_tap (W_in0[:,:,tap] W_start) a0[t+tap-1] + (W_in0[:,:,tap] b_start) [t+tap-1 in range]
+    -> bf16 [2C, 64] in the gate GEMM's packed row order, columns matching the rows written by wgb_x_stack:
+    [0..11] hi(W_tap W_start) (meets hi(a0)), [12..23] the same (meets lo(a0)), [24..35] lo(W_tap W_start) (meets hi(a0)),
+    [36..38] hi(W_tap b_start), [39..41] lo(W_tap b_start) (meet the in-range indicators), rest zero."""
+    two_c, c, taps = w_in0.shape
+    assert taps == 3, "the fold is written for kernel_size 3"
+    n_half = w_start.shape[1]
+    w = torch.zeros(two_c, 64, dtype=torch.float32)
+    for tap in range(taps):
+        comp = (w_in0[:, :, tap].double() @ w_start[:, :n_half].double()).float()
+        wb = (w_in0[:, :, tap].double() @ b_start.double()).float()
+        hi = comp.bfloat16().float()
+        lo = (comp - hi).bfloat16().float()
+        w[:, tap * 4: tap * 4 + n_half] = hi
+        w[:, 12 + tap * 4: 12 + tap * 4 + n_half] = hi
+        w[:, 24 + tap * 4: 24 + tap * 4 + n_half] = lo
+        wbh = wb.bfloat16().float()
+        w[:, 36 + tap] = wbh
+        w[:, 39 + tap] = (wb - wbh).bfloat16().float()
+    return w[gate_row_order(c)].bfloat16().contiguous()
+
+
 def pack_skip(w_rs: List[Tensor], b_rs: List[Tensor], n_ch: int):
     """-> (w_skip [C, L*C], b_skip_total [C]) from the per-layer res_skip weights."""
     cols, bias = [], torch.zeros(n_ch, dtype=torch.float64)
@@ -213,6 +237,9 @@ class PackedWaveGlow:
                 f["w_skip"] = w_skip.to(dev, bf)
                 f["w_skip16"] = pack_skip_end16(w_skip, w_end).to(dev)
                 f["w_comp"] = pack_skip_end_layers(w_skip, w_end, n_ch).to(dev)
+                if st[p + "in_layers.0.weight"].shape[2] == 3:
+                    f["w_gate0"] = pack_gate0(st[p + "in_layers.0.weight"], st[p + "start.weight"][:, :, 0],
+                                              st[p + "start.bias"]).to(dev)
                 f["w_gate"], f["b_gate"], f["w_res"], f["b_res"], f["w_mel"], f["b_mel"] = [], [], [], [], [], []
                 for i in range(n_layers):
                     wg, bg = pack_gate(st[p + f"in_layers.{i}.weight"], st[p + f"in_layers.{i}.bias"],
