@@ -124,9 +124,14 @@ WGB_API int wgb_end_from_acc(const float* skip_acc, const float* b_end, float* x
  * wgb_tc2_wn_skip_end can also run WN.start of the NEXT flow of WaveGlow.infer (glow.py:156 for flow k-1) on the
  * rows it has just updated: h_next bf16 [B,T,512] (row pitch h_next_batch_rows >= T per utterance) = next_w_start
  * fp32 [512][next_n_half] applied to that flow's audio_0 channels + next_b_start fp32 [512]; pass h_next = NULL
- * (and NULL / 0 for the rest) to skip it.  wgb_tc2_wn_res takes the same row pitch for h_in / h_out. */
+ * (and NULL / 0 for the rest) to skip it.  wgb_tc2_wn_res takes the same row pitch for h_in / h_out.
+ *
+ * wgb_tc2_wn_res can also accumulate the layer's share of WN.end's output while the activations are on chip
+ * (w16_layer, skip_acc both non-NULL): a third, N = 16 pass per tile against w16_layer bf16 [16][512] (hi rows 0..7 /
+ * lo rows 8..15 of W_end W_skip_i), added (stored when skip_first) into skip_acc fp32 [B*T][8]. */
 WGB_API int wgb_tc2_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out,
-                           int batch, int T, long long h_batch_rows, void* stream);
+                           int batch, int T, long long h_batch_rows, const void* w16_layer, float* skip_acc,
+                           int skip_first, void* stream);
 WGB_API int wgb_tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end,
                                 const float* b_end, float* x, const float* w_mix, float* log_s, int batch, int T,
                                 int n_half, int direction, const float* next_w_start, const float* next_b_start,
@@ -136,11 +141,13 @@ WGB_API int wgb_tc2_wn_skip_end(const void* acts_all, int n_layers, const void* 
  * acts_all bf16 [n_layers][B][T][512] against w16 bf16 [16][n_layers*512] = the bf16 hi (rows 0..7) and lo (rows 8..15)
  * parts of W_end [W_skip_0 | ... | W_skip_7] (zero rows beyond 2*n_half), b_end fp32 [8] with the skip biases folded
  * in; then the same coupling / W^-1 / log_s / optional next-flow WN.start epilogue as wgb_tc2_wn_skip_end.
- * HBM-bound: 8 KB of activations per group step, 2*4096*16 tensor FLOPs instead of 2*4096*512. */
+ * HBM-bound: 8 KB of activations per group step, 2*4096*16 tensor FLOPs instead of 2*4096*512.
+ * skip_acc (optional) fp32 [B*T][8] is added to the product: with the first n-1 layers accumulated by
+ * wgb_tc2_wn_res, call this with n_layers = 1 on the last layer's activations and its [16][512] weight slice. */
 WGB_API int wgb_tc_wn_skip16_end(const void* acts_all, int n_layers, const void* w16, const float* b_end, float* x,
                                  const float* w_mix, float* log_s, int batch, int T, int n_half, int direction,
                                  const float* next_w_start, const float* next_b_start, int next_n_half, void* h_next,
-                                 long long h_next_batch_rows, void* stream);
+                                 long long h_next_batch_rows, const float* skip_acc, void* stream);
 
 /* Plain tcgen05 GEMM with the same TMA/TMEM pipeline: C[b,t,n] = sum_k A[b,t,k] W[n,k] + bias[n];
  * A bf16 [B,T,K] (K % 64 == 0), W bf16 [N,K] (N % 256 == 0), C fp32 or bf16 [B,T,N]; bias may be NULL.

@@ -108,7 +108,7 @@ def test_tc_res_layer(lib, packed_q, entry, B, T):
     want = h + torch.nn.functional.conv1d(acts, w[:512], b[:512])
     fl = pk.flows[k]
     h_out = torch.zeros(B, T, 512, device=DEV, dtype=torch.bfloat16)
-    extra = (T,) if entry == "wgb_tc2_wn_res" else ()
+    extra = (T, None, None, 0) if entry == "wgb_tc2_wn_res" else ()
     lib.call(entry, cl(acts).to(DEV, torch.bfloat16), fl["w_res"][i], fl["b_res"][i],
              cl(h).to(DEV, torch.bfloat16), h_out, B, T, *extra, lib.stream_ptr())
     torch.cuda.synchronize()
@@ -120,9 +120,21 @@ def test_tc_res_layer(lib, packed_q, entry, B, T):
         h_in[:, :T] = cl(h).to(DEV, torch.bfloat16)
         h_out2 = torch.full((B, rows, 512), -3.0, device=DEV, dtype=torch.bfloat16)
         lib.call(entry, cl(acts).to(DEV, torch.bfloat16), fl["w_res"][i], fl["b_res"][i], h_in, h_out2, B, T, rows,
-                 lib.stream_ptr())
+                 None, None, 0, lib.stream_ptr())
         torch.cuda.synchronize()
         assert torch.equal(h_out2[:, :T], h_out) and bool((h_out2[:, T:] == -3.0).all())
+        # third pass: this layer's share of WN.end's output, (W_end W_skip_i) acts, stored then accumulated
+        skip_row = torch.full((B * T, 8), 9.0, device=DEV)
+        h_out3 = torch.zeros_like(h_out)
+        for first in (1, 0):
+            lib.call(entry, cl(acts).to(DEV, torch.bfloat16), fl["w_res"][i], fl["b_res"][i],
+                     cl(h).to(DEV, torch.bfloat16), h_out3, B, T, T, fl["w_skip16_layers"][i], skip_row, first,
+                     lib.stream_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(h_out3, h_out)
+        w_comp = fl["w_comp"][i].cpu().double()                                  # [512][8] fp32 = (W_end W_skip_i)^T
+        want_skip = 2 * (cl(acts).double().reshape(B * T, 512) @ w_comp)
+        assert util.rel_l2(skip_row.cpu(), want_skip) <= 1e-4
 
 
 @pytest.mark.parametrize("entry", ["wgb_tc_wn_skip_end", "wgb_tc2_wn_skip_end", "wgb_tc_wn_skip16_end"])
@@ -158,16 +170,24 @@ def test_tc_skip_end_coupling(lib, packed_q, k, direction, entry):
     args = (acts_all, 8, fl["w_skip"], fl["w_end_t"], fl["b_end"], xd,
             fl["w_mix_inv"] if direction == 0 else None, log_s, B, T, n_half, direction)
     h_next = None
+    tail = ()
     if entry == "wgb_tc_wn_skip16_end":          # WN.end composed with the skip GEMM (hi/lo bf16 split of the product)
         args = (acts_all, 8, fl["w_skip16"], fl["b_end"], xd, fl["w_mix_inv"] if direction == 0 else None, log_s, B, T,
                 n_half, direction)
+        tail = (None,)
+        if k == 5:                               # layers 0..6 pre-accumulated (as wgb_tc2_wn_res does), last layer here
+            w_comp = fl["w_comp"].cpu().double()                                # [8][512][8]
+            pre = sum(acts[i].permute(0, 2, 1).double().reshape(B * T, 512) @ w_comp[i] for i in range(7))
+            args = (acts_all[7].contiguous(), 1, fl["w_skip16_layers"][7], fl["b_end"], xd,
+                    fl["w_mix_inv"] if direction == 0 else None, log_s, B, T, n_half, direction)
+            tail = (pre.float().to(DEV).contiguous(),)
     if entry != "wgb_tc_wn_skip_end":
         if direction == 0 and k > 0:             # also run WN.start of flow k-1 on the updated rows (glow.py:156)
             nf = pk.flows[k - 1]
             h_next = torch.zeros(B, T, 512, device=DEV, dtype=torch.bfloat16)
-            lib.call(entry, *args, nf["w_start"], nf["b_start"], nf["n_half"], h_next, T, lib.stream_ptr())
+            lib.call(entry, *args, nf["w_start"], nf["b_start"], nf["n_half"], h_next, T, *tail, lib.stream_ptr())
         else:
-            lib.call(entry, *args, None, None, 0, None, 0, lib.stream_ptr())
+            lib.call(entry, *args, None, None, 0, None, 0, *tail, lib.stream_ptr())
     else:
         lib.call(entry, *args, lib.stream_ptr())
     torch.cuda.synchronize()
@@ -414,7 +434,7 @@ def test_skip_paths_agree(models, golden, monkeypatch):
     out = {}
     try:
         m.cond_path = "mel"
-        for kind in ("acc", "skip16", "pair"):
+        for kind in ("res16", "acc", "skip16", "pair"):
             monkeypatch.setattr(engine, "SKIP_KERNEL", kind)
             out[kind] = m.infer(mel.to(DEV), sigma=util.SIGMA, z=z.to(DEV)).cpu()
     finally:
@@ -423,6 +443,7 @@ def test_skip_paths_agree(models, golden, monkeypatch):
         assert util.snr_db(audio, golden["stress_infer_audio"]) >= util.MIN_SNR_DB, kind
     # the variants differ only in where bf16 rounding enters, so they agree with each other as well as with the reference
     assert util.snr_db(out["acc"], out["skip16"]) >= util.MIN_SNR_DB
+    assert util.snr_db(out["res16"], out["skip16"]) >= util.MIN_SNR_DB
     assert util.snr_db(out["skip16"], out["pair"]) >= util.MIN_SNR_DB
 
 

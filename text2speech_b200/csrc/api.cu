@@ -15,7 +15,8 @@ int tc_gemm_split3(const void*, const void*, const void*, const float*, void*, i
                    cudaStream_t);
 // wn_tc2.cu
 int tc2_wn_gate(const void*, const void*, const void*, const float*, void*, int, int, int, cudaStream_t);
-int tc2_wn_res(const void*, const void*, const float*, const void*, void*, int, int, long long, cudaStream_t);
+int tc2_wn_res(const void*, const void*, const float*, const void*, void*, int, int, long long, const void*, float*, int,
+               cudaStream_t);
 int tc2_wn_gate_mel(const void*, const void*, const void*, const void*, const float*, void*, int, int, int, int,
                     const float*, float*, int, cudaStream_t);
 int tc2_wn_gate_mel0(const void*, const void*, const void*, const void*, const float*, void*, int, int, int, const float*,
@@ -28,7 +29,7 @@ int tc2_wn_skip_end(const void*, int, const void*, const float*, const float*, f
                     int, int, const float*, const float*, int, void*, long long, cudaStream_t);
 // wn_skip16.cu
 int tc_wn_skip16_end(const void*, int, const void*, const float*, float*, const float*, float*, int, int, int, int,
-                     const float*, const float*, int, void*, long long, cudaStream_t);
+                     const float*, const float*, int, void*, long long, const float*, cudaStream_t);
 // ref_f32.cu
 int sgemm_nt(const float*, const float*, const float*, void*, int, int, int, int, int, long long, long long, long long,
              long long, long long, int, int, cudaStream_t);
@@ -120,8 +121,9 @@ WGB_API int wgb_end_from_acc(const float* skip_acc, const float* b_end, float* x
                         next_n_half, h_next, h_next_batch_rows, S(stream));
 }
 WGB_API int wgb_tc2_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch,
-                           int T, long long h_batch_rows, void* stream) {
-    return tc2_wn_res(acts, w_res, bias, h_in, h_out, batch, T, h_batch_rows, S(stream));
+                           int T, long long h_batch_rows, const void* w16_layer, float* skip_acc, int skip_first,
+                           void* stream) {
+    return tc2_wn_res(acts, w_res, bias, h_in, h_out, batch, T, h_batch_rows, w16_layer, skip_acc, skip_first, S(stream));
 }
 WGB_API int wgb_tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end,
                                 const float* b_end, float* x, const float* w_mix, float* log_s, int batch, int T,
@@ -133,9 +135,9 @@ WGB_API int wgb_tc2_wn_skip_end(const void* acts_all, int n_layers, const void* 
 WGB_API int wgb_tc_wn_skip16_end(const void* acts_all, int n_layers, const void* w16, const float* b_end, float* x,
                                  const float* w_mix, float* log_s, int batch, int T, int n_half, int direction,
                                  const float* next_w_start, const float* next_b_start, int next_n_half, void* h_next,
-                                 long long h_next_batch_rows, void* stream) {
+                                 long long h_next_batch_rows, const float* skip_acc, void* stream) {
     return tc_wn_skip16_end(acts_all, n_layers, w16, b_end, x, w_mix, log_s, batch, T, n_half, direction, next_w_start,
-                            next_b_start, next_n_half, h_next, h_next_batch_rows, S(stream));
+                            next_b_start, next_n_half, h_next, h_next_batch_rows, skip_acc, S(stream));
 }
 WGB_API int wgb_tc_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch,
                   int T, void* stream) {

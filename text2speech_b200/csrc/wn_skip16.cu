@@ -36,6 +36,7 @@ constexpr int kSmemTotal = 1024 + kBarOff + 256;
 struct Params {
     int batch, T, tiles_per_b, n_tiles, n_chunks;
     const float* b_end;           // [8], skip biases folded through W_end
+    const float* skip_acc;        // optional [B*T][8]: contributions of the layers accumulated by wgb_tc2_wn_res
     float* x;                     // flow state [B,T,8]
     const float* w_mix;           // infer: W^-1 [8][8]
     float* log_s;                 // forward: [B,n_half,T]
@@ -155,6 +156,12 @@ skip16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             float outv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) outv[j] = __uint_as_float(v[j]) + __uint_as_float(v[8 + j]) + __ldg(p.b_end + j);   // hi + lo
+            if (p.skip_acc) {
+                const float4 s0 = *reinterpret_cast<const float4*>(p.skip_acc + grow * 8);
+                const float4 s1 = *reinterpret_cast<const float4*>(p.skip_acc + grow * 8 + 4);
+                outv[0] += s0.x; outv[1] += s0.y; outv[2] += s0.z; outv[3] += s0.w;
+                outv[4] += s1.x; outv[5] += s1.y; outv[6] += s1.z; outv[7] += s1.w;
+            }
             constexpr int C = 2 * NHALF, BASE = 8 - C;
             float* xr = p.x + grow * 8;
             float xv[8];
@@ -241,7 +248,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p,
 int tc_wn_skip16_end(const void* acts_all, int n_layers, const void* w16, const float* b_end, float* x, const float* w_mix,
                      float* log_s, int batch, int T, int n_half, int direction, const float* next_w_start,
                      const float* next_b_start, int next_n_half, void* h_next, long long h_next_batch_rows,
-                     cudaStream_t stream) {
+                     const float* skip_acc, cudaStream_t stream) {
     using namespace skip16;
     WGB_REQUIRE(acts_all && w16 && b_end && x, "null pointer");
     WGB_REQUIRE(n_layers >= 1 && batch > 0 && T > 0, "bad shape");
@@ -253,7 +260,7 @@ int tc_wn_skip16_end(const void* acts_all, int n_layers, const void* w16, const 
     p.tiles_per_b = ceil_div(T, kBlockM);
     p.n_tiles = batch * p.tiles_per_b;
     p.n_chunks = n_layers * kNCh / kBlockK;
-    p.b_end = b_end; p.x = x; p.w_mix = w_mix; p.log_s = log_s;
+    p.b_end = b_end; p.x = x; p.w_mix = w_mix; p.log_s = log_s; p.skip_acc = skip_acc;
     if (h_next) {
         WGB_REQUIRE(direction == 0, "the fused WN.start of the next flow exists for the infer direction only");
         WGB_REQUIRE(next_w_start && next_b_start && next_n_half >= 1 && next_n_half <= 4, "bad next-flow start arguments");

@@ -23,7 +23,9 @@
 // own 128 x 256 h tile per CTA in two 128-column halves (TMA load -> in-place update in the swizzled layout
 // -> TMA store), driven by a seventh warp behind CTA-local barriers: while the epilogue works on one half,
 // the other half's store drains and the next pass's h_in streams in, so the HBM latency of the residual
-// stream never sits between two epilogues.
+// stream never sits between two epilogues.  RES can also run a third, skinny pass per tile over the same activations:
+// N = 16 against the bf16 hi/lo rows of W_end W_skip_i, added into a per-row fp32 accumulator (skip_acc [B*T][8]) --
+// the layer's contribution to WN.end's output (glow.py:167-175), so the skip path never re-reads the activations.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -78,6 +80,8 @@ struct Params {
     // GATE_MEL, optional: skip path accumulated in the epilogue.  w_comp fp32 [512][8] = (W_end W_skip_i)^T of THIS
     // layer; skip_acc fp32 [4 passes][rows_total][8]: slot (pass, row) += sum over the pass's 128 channels of
     // acts * w_comp (stored instead of added when skip_first).  One thread owns a slot: deterministic.
+    // RES, optional (skip_acc non-NULL): third pass, N = 16 rows of map_x (hi / lo of W_end W_skip_i), result added
+    // (stored when skip_first) into skip_acc fp32 [B*T][8]
     const float* w_comp;
     float* skip_acc;
     long long rows_total;
@@ -168,7 +172,8 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 template <int MODE, int NHALF, int DIR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsRes, 1)
 pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-            const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c, const Params p) {
+            const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
+            const __grid_constant__ CUtensorMap map_x, const Params p) {
     using SL = Smem<MODE>;
     constexpr int kStages = SL::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -262,7 +267,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                         mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
                         uint8_t* sa = smem + s * kStageBytes;
                         uint8_t* sb = sa + kABytes;
-                        if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * kStageBytes);
+                        const bool skinny = MODE == RES && pass == 2;          // N = 16: 8 weight rows (1 KB) per CTA
+                        if (leader) mbar_arrive_expect_tx(&full_bar[s], skinny ? 2 * (kABytes + 1024) : 2 * kStageBytes);
                         const uint32_t bar = mapa_u32(&full_bar[s], 0);
                         if constexpr (MODE == GATE) {
                             if (kc < 24) {
@@ -290,6 +296,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                         const int w_row = pass * kBlockN + static_cast<int>(rank) * kHalfN;
                         if (is_mel(MODE) && kc >= p.n_tap_chunks)      // phase-specific composed conditioning weight [32*1024][320]
                             tma_load_2d_2sm(sb, &map_c, bar, (kc - p.n_tap_chunks) * kBlockK, phase * (2 * kNCh) + w_row);
+                        else if (skinny)
+                            tma_load_2d_2sm(sb, &map_x, bar, kc * kBlockK, static_cast<int>(rank) * 8);
                         else
                             tma_load_2d_2sm(sb, &map_w, bar, kc * kBlockK, w_row);
                         if (++s == kStages) { s = 0; ph ^= 1; }
@@ -300,10 +308,12 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * kBlockM, kBlockN);
+            constexpr uint32_t idesc256 = umma_idesc_bf16_f32(2 * kBlockM, kBlockN);
+            constexpr uint32_t idesc16 = umma_idesc_bf16_f32(2 * kBlockM, 16);
             int s = 0;
             uint32_t ph = 0, acc_it = 0;
             for (int item = pair_id; item < n_items; item += n_pairs) {
+                const uint32_t idesc = (MODE == RES && item % groups == 2) ? idesc16 : idesc256;
                 for (int pp = 0; pp < p.ppi; ++pp, ++acc_it) {
                     const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
                     mbar_wait(&tempty_bar[as], aph ^ 1, 200 + as);
@@ -345,19 +355,26 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                     for (int j = 2 * hf; j < 2 * hf + 2; ++j)
                         tma_load_3d(s_extra + j * kABytes, &map_a1, &hfull_bar[hf], pass * kBlockN + j * kBlockK, t0, b);
                 };
+                // items whose pass is 2 (the skinny skip pass) have no h tile: step over them
+                auto next_h_item = [&](int item) {
+                    do item += n_pairs; while (item < n_items && item % groups == 2);
+                    return item;
+                };
                 int pass, t0, b;
-                if (pair_id < n_items) {
-                    coords(pair_id, pass, t0, b);
+                const int first = (pair_id < n_items && pair_id % groups == 2) ? next_h_item(pair_id) : pair_id;
+                if (first < n_items) {
+                    coords(first, pass, t0, b);
                     load_half(0, pass, t0, b);
                     load_half(1, pass, t0, b);
                 }
                 uint32_t it = 0;
-                for (int item = pair_id; item < n_items; item += n_pairs, ++it) {
+                for (int item = first; item < n_items; ++it) {
                     coords(item, pass, t0, b);
-                    const bool has_next = item + n_pairs < n_items;
+                    const int nitem = next_h_item(item);
+                    const bool has_next = nitem < n_items;
                     int npass = 0, nt0 = 0, nb = 0;
                     if (has_next) {
-                        coords(item + n_pairs, npass, nt0, nb);
+                        coords(nitem, npass, nt0, nb);
 #pragma unroll
                         for (int j = 0; j < kBlockN / kBlockK; ++j)      // pull the next h_in tile into L2 a whole pass early
                             tma_prefetch_3d(&map_a1, npass * kBlockN + j * kBlockK, nt0, nb);
@@ -371,6 +388,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                         tma_store_wait_read0();                          // smem half free again
                         if (has_next) load_half(hf, npass, nt0, nb);
                     }
+                    item = nitem;
                 }
                 tma_store_wait_all0();                                   // h_out globally visible before the kernel ends
             }
@@ -485,6 +503,29 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             *reinterpret_cast<float4*>(slot + 4) =
                                 make_float4(prev1.x + sk[4], prev1.y + sk[5], prev1.z + sk[6], prev1.w + sk[7]);
                         }
+                    }
+                } else if (MODE == RES && pass == 2) {
+                    // skinny skip pass: columns 0..7 = hi rows, 8..15 = lo rows of W_end W_skip_i applied to this row
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(taddr, v);
+                    tmem_ld_wait();
+                    if (live) {
+                        float* slot = p.skip_acc + grow * 8;
+                        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+                        if (!p.skip_first) {
+                            o0 = *reinterpret_cast<const float4*>(slot);
+                            o1 = *reinterpret_cast<const float4*>(slot + 4);
+                        }
+                        o0.x += __uint_as_float(v[0]) + __uint_as_float(v[8]);
+                        o0.y += __uint_as_float(v[1]) + __uint_as_float(v[9]);
+                        o0.z += __uint_as_float(v[2]) + __uint_as_float(v[10]);
+                        o0.w += __uint_as_float(v[3]) + __uint_as_float(v[11]);
+                        o1.x += __uint_as_float(v[4]) + __uint_as_float(v[12]);
+                        o1.y += __uint_as_float(v[5]) + __uint_as_float(v[13]);
+                        o1.z += __uint_as_float(v[6]) + __uint_as_float(v[14]);
+                        o1.w += __uint_as_float(v[7]) + __uint_as_float(v[15]);
+                        *reinterpret_cast<float4*>(slot) = o0;
+                        *reinterpret_cast<float4*>(slot + 4) = o1;
                     }
                 } else if constexpr (MODE == RES) {
                     // h tile sits in smem in the TMA SWIZZLE_128B layout (four [128 x 64] boxes): row r of box j is
@@ -657,7 +698,7 @@ static int fill_common(Params& p, int batch, int T) {
 
 template <int MODE, int NHALF, int DIR>
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& c, const Params& p,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const CUtensorMap* x = nullptr) {
     constexpr int smem = Smem<MODE>::kTotal;
     static_assert(smem <= 232448, "dynamic shared memory over the 227 KB per-CTA limit");
     auto kern = pair_kernel<MODE, NHALF, DIR>;
@@ -665,7 +706,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     const int n_items = ((p.n_tiles + 1) / 2) * (p.n_pass / p.ppi);
     int pairs = sm_count() / 2;
     if (n_items < pairs) pairs = n_items;
-    kern<<<2 * pairs, MODE == RES ? kThreadsRes : kThreads, smem, stream>>>(a0, a1, w, c, p);
+    kern<<<2 * pairs, MODE == RES ? kThreadsRes : kThreads, smem, stream>>>(a0, a1, w, c, x ? *x : a0, p);
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }
@@ -767,20 +808,28 @@ static int h_map(CUtensorMap* m, const void* base, int T, int batch, long long b
 // h_batch_rows: row pitch per utterance of h_in / h_out (T for dense buffers; more in the padded layout, whose guard
 // rows are never loaded nor stored because the tensor maps end at row T)
 int tc2_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch, int T,
-               long long h_batch_rows, cudaStream_t stream) {
+               long long h_batch_rows, const void* w16_layer, float* skip_acc, int skip_first, cudaStream_t stream) {
     using namespace tc2;
     WGB_REQUIRE(acts && w_res && bias && h_in && h_out, "null pointer");
     WGB_REQUIRE(h_batch_rows >= T, "h_batch_rows (%lld) must be >= T (%d)", h_batch_rows, T);
+    WGB_REQUIRE((w16_layer == nullptr) == (skip_acc == nullptr), "w16_layer and skip_acc go together");
     Params p{};
     if (int e = fill_common(p, batch, T)) return e;
-    p.n_pass = 2; p.ppi = 1; p.n_chunks = kNCh / kBlockK;
+    p.n_pass = skip_acc ? 3 : 2; p.ppi = 1; p.n_chunks = kNCh / kBlockK;
     p.bias = bias;
-    CUtensorMap ma, mhi, mho, mw;
+    p.skip_acc = skip_acc; p.skip_first = skip_first;
+    CUtensorMap ma, mhi, mho, mw, mx;
+    if (skip_acc) {                      // [16 rows][512] bf16: hi rows 0..7, lo rows 8..15; each CTA loads 8 rows per chunk
+        const uint64_t dims[2] = {kNCh, 16};
+        const uint64_t strides[1] = {kNCh * 2};
+        const uint32_t box[2] = {kBlockK, 8};
+        if (int e = make_tmap_bf16(&mx, w16_layer, 2, dims, strides, box)) return e;
+    }
     if (int e = act_map(&ma, acts, kNCh, T, batch)) return e;
     if (int e = h_map(&mhi, h_in, T, batch, h_batch_rows)) return e;
     if (int e = h_map(&mho, h_out, T, batch, h_batch_rows)) return e;
     if (int e = weight_half_map(&mw, w_res, kNCh, kNCh)) return e;
-    return launch<RES, 0, 0>(ma, mhi, mw, mho, p, stream);
+    return launch<RES, 0, 0>(ma, mhi, mw, mho, p, stream, skip_acc ? &mx : nullptr);
 }
 
 int tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end, const float* b_end,

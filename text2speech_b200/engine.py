@@ -22,11 +22,14 @@ Tensor = torch.Tensor
 # Which tcgen05 kernels the BF16 path uses: "pair" = CTA pairs (cta_group::2, UMMA M = 256), "single" = one CTA per tile.
 GATE_KERNEL = os.environ.get("WGB_GATE_KERNEL", "pair")
 RES_KERNEL = os.environ.get("WGB_RES_KERNEL", "pair")
-# skip path: "skip16" (default) = WN.end composed with the skip GEMM, one N = 16 tcgen05 sweep over the stored
-# activations (HBM-bound); "acc" = the same product accumulated in the gate kernel's epilogue (composed-conditioning
-# path only, elsewhere it means "skip16"; measured SLOWER: +0.3 ms per gate launch, 671 vs 647 ms per step, kept as a
-# tested variant because it needs no acts_all buffer); "pair" / "single" = the K = 4096 x N = 512 GEMM with WN.end in
-# the epilogue
+# skip path (WN.end composed with the skip GEMM in all but "pair" / "single"):
+#   "skip16" (default) one N = 16 tcgen05 sweep over the stored activations of all layers (HBM-bound, 8 KB per group step)
+#   "res16"  the residual kernel adds each layer's [16 x 512] product into a per-row accumulator while the activations
+#            are on chip (third, N = 16 pass); the last layer + coupling run in wgb_tc_wn_skip16_end.  One activation
+#            buffer instead of eight (-12.6 GB at batch 64), but measured 2 % SLOWER: every extra accumulator pass pays
+#            the TMEM drain and pipeline hand-off of a full pass (+0.14 ms per residual launch vs -1.2 ms per flow).
+#   "acc"    the product accumulated in the gate kernel's epilogue (composed-conditioning path only; also slower)
+#   "pair" / "single"  the K = 4096 x N = 512 GEMM with WN.end in the epilogue
 SKIP_KERNEL = os.environ.get("WGB_SKIP_KERNEL", "skip16")
 # composed-conditioning path: fold WN.start into in_layers[0] (first layer reads the stacked flow state, K = 64 + 320)
 FOLD_START = os.environ.get("WGB_FOLD_START", "1") == "1"
@@ -96,6 +99,7 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int
     s = _lib.stream_ptr()
     h0, h1, acts_all = bufs["h0"], bufs["h1"], bufs["acts"]
     skip_acc = bufs.get("skip_acc")           # "acc" skip path: [4, B*T, 8] fp32, one acts buffer
+    skip_row = bufs.get("skip_row")           # "res16" skip path: [B*T, 8] fp32, one acts buffer
     h_rows = h0.shape[1]                      # row pitch per utterance: t, or 32 * frames_pad in the padded layout
     gate = "wgb_tc2_wn_gate" if GATE_KERNEL == "pair" else "wgb_tc_wn_gate"
     res = "wgb_tc2_wn_res" if RES_KERNEL == "pair" else "wgb_tc_wn_res"
@@ -104,7 +108,7 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int
         _lib.call("wgb_wn_start_padded", x, fl["w_start"], fl["b_start"], h0, 1, b, t, h_rows, pk.n_ch, fl["n_half"], s)
     cur, nxt = h0, h1
     for i in range(pk.n_layers):
-        acts = acts_all[i if skip_acc is None else 0]
+        acts = acts_all[i if (skip_acc is None and skip_row is None) else 0]
         if i == 0 and isinstance(cond, tuple) and FOLD_START and "w_gate0" in fl:
             # WN.start folded into in_layers[0]: the operand is the stacked flow state, not h0 (h0 still feeds the
             # residual GEMM)
@@ -122,7 +126,8 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int
             _lib.call(gate, cur, cond, fl["w_gate"][i], fl["b_gate"][i], acts, b, t, 2 ** i, s)
         if i < pk.n_layers - 1:
             if RES_KERNEL == "pair":
-                _lib.call(res, acts, fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, h_rows, s)
+                _lib.call(res, acts, fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, h_rows,
+                          fl["w_skip16_layers"][i] if skip_row is not None else None, skip_row, int(i == 0), s)
             else:
                 _lib.call(res, acts, fl["w_res"][i], fl["b_res"][i], cur, nxt, b, t, s)
             cur, nxt = nxt, cur
@@ -137,14 +142,21 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int
                   fl["n_half"], direction, *((next_fl["w_start"], next_fl["b_start"], next_fl["n_half"], h0, h_rows)
                                              if fuse else (None, None, 0, None, 0)), s)
         return fuse
-    if SKIP_KERNEL in ("skip16", "acc"):
+    tail = ()
+    if skip_row is not None:                  # layers 0..L-2 are in skip_row; the last layer's activations are in acts
+        skip_end = "wgb_tc_wn_skip16_end"
+        args = (acts_all[0], 1, fl["w_skip16_layers"][pk.n_layers - 1], fl["b_end"], x,
+                fl["w_mix_inv"] if direction == 0 else None, log_s, b, t, fl["n_half"], direction)
+        tail = (skip_row,)
+    elif SKIP_KERNEL in ("skip16", "acc", "res16"):
         skip_end = "wgb_tc_wn_skip16_end"
         args = (acts_all, pk.n_layers, fl["w_skip16"], fl["b_end"], x,
                 fl["w_mix_inv"] if direction == 0 else None, log_s, b, t, fl["n_half"], direction)
+        tail = (None,)
     if fuse:
-        _lib.call(skip_end, *args, next_fl["w_start"], next_fl["b_start"], next_fl["n_half"], h0, h_rows, s)
+        _lib.call(skip_end, *args, next_fl["w_start"], next_fl["b_start"], next_fl["n_half"], h0, h_rows, *tail, s)
     else:
-        _lib.call(skip_end, *args, None, None, 0, None, 0, s)
+        _lib.call(skip_end, *args, None, None, 0, None, 0, *tail, s)
     return fuse
 
 
@@ -178,6 +190,12 @@ def _alloc(pk: PackedWaveGlow, b: int, t: int, device, h_rows: Optional[int] = N
     if pk.mode == "bf16":
         bf = torch.bfloat16
         acc = h_rows is not None and SKIP_KERNEL == "acc"     # composed-conditioning path: skip accumulated by the gate kernel
+        if SKIP_KERNEL == "res16" and RES_KERNEL == "pair" and pk.n_layers > 1:
+            hr = t if h_rows is None else h_rows
+            mk = torch.zeros if hr != t else torch.empty
+            return {"h0": mk((b, hr, pk.n_ch), device=device, dtype=bf), "h1": mk((b, hr, pk.n_ch), device=device, dtype=bf),
+                    "acts": torch.empty((1, b, t, pk.n_ch), device=device, dtype=bf),
+                    "skip_row": torch.empty((b * t, 8), device=device, dtype=torch.float32)}
         if h_rows is not None and h_rows != t:     # padded layout: guard rows are zero and no kernel ever writes them
             h0 = torch.zeros((b, h_rows, pk.n_ch), device=device, dtype=bf)
             h1 = torch.zeros((b, h_rows, pk.n_ch), device=device, dtype=bf)

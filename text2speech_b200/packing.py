@@ -235,7 +235,11 @@ class PackedWaveGlow:
             if mode == "bf16":
                 f["b_end"] = b_fold.to(dev)
                 f["w_skip"] = w_skip.to(dev, bf)
-                f["w_skip16"] = pack_skip_end16(w_skip, w_end).to(dev)
+                w16 = pack_skip_end16(w_skip, w_end)
+                f["w_skip16"] = w16.to(dev)
+                # the same product per layer, [16][n_ch] contiguous: wgb_tc2_wn_res accumulates layers 0..L-2 while the
+                # activations are on chip, wgb_tc_wn_skip16_end adds the last layer
+                f["w_skip16_layers"] = [w16[:, i * n_ch:(i + 1) * n_ch].contiguous().to(dev) for i in range(n_layers)]
                 f["w_comp"] = pack_skip_end_layers(w_skip, w_end, n_ch).to(dev)
                 if st[p + "in_layers.0.weight"].shape[2] == 3:
                     f["w_gate0"] = pack_gate0(st[p + "in_layers.0.weight"], st[p + "start.weight"][:, :, 0],
