@@ -404,6 +404,27 @@ def test_infer_bf16_composed_conditioning_path(models, golden, recipe):
     assert not torch.equal(a_mel, a_cond)            # really two different kernels
 
 
+@pytest.mark.parametrize("B,F", [(1, 1), (5, 2), (2, 33)])
+def test_infer_ragged_small_shapes(models, B, F):
+    """Shapes far below one tile (T = 32 F < 128) and odd batches, all three paths against the CPU oracle."""
+    m = models["bench"]
+    sd = util.state_dict("bench")
+    mel, z = syn.synthetic_mel(B, F, seed=70 + F), syn.synthetic_z(B, F, seed=80 + F)
+    with torch.no_grad():
+        want = oracle.waveglow_infer(sd, mel, z, util.SIGMA)
+    m.mode = "fp32"
+    got = m.infer(mel.to(DEV), sigma=util.SIGMA, z=z.to(DEV)).cpu()
+    assert got.shape == (B, 256 * F) and util.rel_l2(got, want) <= 3e-5
+    m.mode = "bf16"
+    try:
+        for path in ("cond", "mel"):
+            m.cond_path = path
+            got = m.infer(mel.to(DEV), sigma=util.SIGMA, z=z.to(DEV)).cpu()
+            assert util.snr_db(got, want) >= util.MIN_SNR_DB, (path, B, F)
+    finally:
+        m.cond_path = "auto"
+
+
 def test_first_layer_fold_agrees(models, golden, monkeypatch):
     """Composed path with and without WN.start folded into in_layers[0]."""
     from text2speech_b200 import engine
