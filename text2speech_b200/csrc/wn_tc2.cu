@@ -413,6 +413,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                     live = live && t < p.f_real;
                 }
                 t = t * kPhases + ((item % groups) >> 2);
+                live = live && t < p.T;                       // partial last frame
             }
             const size_t grow = static_cast<size_t>(bb) * p.T + t;
             float outv[8];
@@ -739,10 +740,12 @@ static int gate_mel_launch(const void* a_taps, int tap_channels, int n_tap_chunk
     using namespace tc2;
     WGB_REQUIRE(a_taps && mel_stack && w_taps && w_mel && bias && acts, "null pointer");
     WGB_REQUIRE(dilation >= 1, "dilation must be >= 1");
-    WGB_REQUIRE(batch > 0 && T > 0 && T % kPhases == 0, "T (%d) must be a positive multiple of %d group steps", T, kPhases);
-    const int frames = T / kPhases;
-    WGB_REQUIRE(frames_pad == frames || frames_pad >= frames + ceil_div(dilation, kPhases),
-                "frames_pad (%d) must equal frames (%d) or leave >= dilation/32 guard frames", frames_pad, frames);
+    WGB_REQUIRE(batch > 0 && T > 0, "batch and T must be positive");
+    const int frames = ceil_div(T, kPhases);        // the last frame may be partial (forward() on audio that is not a
+                                                    // multiple of 256 samples): its missing rows are guard rows
+    WGB_REQUIRE((frames_pad == frames && T % kPhases == 0) || frames_pad >= frames + ceil_div(dilation, kPhases),
+                "frames_pad (%d) must equal frames (%d, T a multiple of 32) or leave >= dilation/32 guard frames",
+                frames_pad, frames);
     Params p{};
     p.T = T;
     const bool padded = frames_pad > frames;

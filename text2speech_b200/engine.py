@@ -83,11 +83,12 @@ def use_mel_path(pk: PackedWaveGlow, batch: int, frames: int, t: int) -> bool:
     chunks for this shape ('auto'), or as forced by model.cond_path."""
     if pk.mode != "bf16" or not pk.has_mel or pk.cond_path == "cond" or GATE_KERNEL != "pair" or RES_KERNEL != "pair":
         return False
-    if t != frames * 32:                      # forward() with audio shorter than 256 * frames
+    if t > frames * 32:
         return False
     if pk.cond_path == "mel":
         return True
-    return -(-batch * (frames + GUARD_FRAMES) // 128) * 32 * 29 < batch * -(-t // 128) * 34
+    used = -(-t // 32)                        # forward() may use fewer (and a partial last) frame than the mel has
+    return -(-batch * (used + GUARD_FRAMES) // 128) * 32 * 29 < batch * -(-t // 128) * 34
 
 
 def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int, log_s: Optional[Tensor],
@@ -255,8 +256,9 @@ def forward(pk: PackedWaveGlow, mel: Tensor, audio: Tensor) -> Tuple[Tensor, Lis
         raise RuntimeError("audio longer than 256 * frames is not supported by the regrouped upsample GEMM")
     h_rows = None
     if use_mel_path(pk, b, f, t):
-        h_rows = 32 * (f + GUARD_FRAMES)
-        cond = ("mel", mel_stack(pk, mel, f + GUARD_FRAMES))
+        used = -(-t // 32)                    # frames that carry audio; the mel may have more (glow.py:216-218)
+        h_rows = 32 * (used + GUARD_FRAMES)
+        cond = ("mel", mel_stack(pk, mel[:, :, :used].contiguous(), used + GUARD_FRAMES))
     else:
         cond = upsample_cond(pk, mel)
         if cond.shape[1] > t:
