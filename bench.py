@@ -203,6 +203,7 @@ def run_gpu_arm(args):
     counter = {"n": 0}
     gate_events = []
     gate_names = []
+    seen_entry_points = set()
     raw_call = _lib.call
     profile = {"on": False}
 
@@ -210,6 +211,7 @@ def run_gpu_arm(args):
 
     def counted_call(name, *a):
         counter["n"] += 1
+        seen_entry_points.add(name)
         if profile.get("all"):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -314,6 +316,24 @@ def run_gpu_arm(args):
                 "traffic_source": "ncu dram__bytes_read+write per launch at batch 64, " + GATE_DRAM_SOURCE,
                 "algorithmic_bytes_per_launch": 3328 * per_rank * t_steps}
 
+    # Tensor-pipe FLOPs actually executed per infer on this rank (three exact algebraic
+    # compositions execute fewer FLOPs than the reference's convs, which is what `wn_gemm_tflops_per_gpu` counts)
+    n_flows, n_layers = 12, 8
+    rows = per_rank * t_steps
+    if gate_name == "wgb_tc2_wn_gate_mel":
+        tiled_rows = (-(-per_rank * (FRAMES + 4) // 128) * 128) * 32
+        fold = 1 if "wgb_tc2_wn_gate_mel0" in seen_entry_points else 0
+        exec_flop = n_flows * ((n_layers - fold) * 2 * 1856 * 1024 * tiled_rows + fold * 2 * 384 * 1024 * tiled_rows)
+    else:
+        exec_flop = n_flows * n_layers * GATE_FLOP_PER_STEP * rows
+    exec_flop += n_flows * (n_layers - 1) * 2 * 512 * 512 * rows
+    exec_flop += n_flows * (2 * 4096 * 16 * rows if "wgb_tc_wn_skip16_end" in seen_entry_points else 2 * 4096 * 512 * rows)
+    exec_tflops = exec_flop / (ms_per_step * 1e-3) / 1e12
+    executed = {"tflop_per_step_per_gpu": exec_flop / 1e12, "tflops_per_gpu": exec_tflops,
+                "frac_of_bf16_sustained": exec_tflops / sustained,
+                "note": "conditioning composed with the upsampler, WN.end composed with the skip sum, WN.start folded "
+                        "into in_layers[0] (exact; DESIGN.md section 4)"}
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -327,6 +347,7 @@ def run_gpu_arm(args):
             "rtf": (ms_per_step * 1e-3) / (samples_total / SAMPLE_RATE),
             "wn_gemm_tflops_per_gpu": overall_tflops,
             "wn_gemm_frac_of_bf16_peak": {"sustained": overall_tflops / sustained, "burst": overall_tflops / burst},
+            "wn_gemm_executed": executed,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": (mel_host.numel() + z_host.numel()) * 4 * world,
                     "d2h_bytes_per_step": out_host.numel() * 4 * world},
