@@ -46,8 +46,9 @@ GATE_ENTRY_POINTS = ("wgb_tc_wn_gate", "wgb_tc2_wn_gate", "wgb_tc2_wn_gate_mel")
 # (ncu --set full, profiles/r01c_ncu_full_summary.csv: 6.667 + 1.791 GB); algorithmic bytes are
 # h 1 KB + cond 1.25 KB read + acts 1 KB written per group step = 5.84 GB.  Scales with the per-rank batch.
 GATE_DRAM_BYTES_PER_LAUNCH_B64 = {"wgb_tc2_wn_gate": 8.458e9,         # profiles/r01c_ncu_full_summary.csv
-                                  "wgb_tc2_wn_gate_mel": 5.272e9}     # profiles/r01h_ncu_full_summary.csv (3.489 + 1.783 GB)
-GATE_DRAM_SOURCE = "profiles/r01h_ncu_full_summary.csv (composed gate) / r01c (cond-tensor gate)"
+                                  "wgb_tc2_wn_gate_mel": 4.02e9}      # profiles/r01l_ncu_full_summary.csv (2.24 + 1.78 GB;
+                                                                      # 3.49 + 1.78 GB for the launch captured in r01h)
+GATE_DRAM_SOURCE = "profiles/r01l_ncu_full_summary.csv (composed gate) / r01c (cond-tensor gate)"
 
 
 def workload_config(n_gpus):
@@ -314,7 +315,9 @@ def run_gpu_arm(args):
                 "executed_tflops": achieved_exec, "frac_executed": (achieved_exec / sustained) if achieved_exec else None,
                 "traffic": traffic * per_rank / GLOBAL_BATCH if traffic else None,
                 "traffic_source": "ncu dram__bytes_read+write per launch at batch 64, " + GATE_DRAM_SOURCE,
-                "algorithmic_bytes_per_launch": 3328 * per_rank * t_steps}
+                "algorithmic_bytes_per_launch": 3328 * per_rank * t_steps,      # reference op: h + cond in, acts out
+                "min_bytes_per_launch_as_executed": 2048 * per_rank * t_steps + 640 * per_rank * (FRAMES + 4)
+                if gate_name == "wgb_tc2_wn_gate_mel" else 3328 * per_rank * t_steps}
 
     # Tensor-pipe FLOPs actually executed per infer on this rank (three exact algebraic
     # compositions execute fewer FLOPs than the reference's convs, which is what `wn_gemm_tflops_per_gpu` counts)
