@@ -165,6 +165,18 @@ WGB_API int wgb_tc_gemm_split3(const void* a_hi, const void* a_lo, const void* w
                                int batch, int rows, int N, int K, long long row_stride, long long batch_stride,
                                void* stream);
 
+/* The forward STFT GEMM with its consumer fused into the epilogue.  w3_paired = the split-bf16 forward basis
+ * [2cp][3K] with rows in Re/Im-PAIRED order (rows 256p..256p+127 = Re of bins 128p..128p+127, the next 128 rows their
+ * Im; cp % 128 == 0), so each accumulator pass holds both parts of its bins:
+ *   wgb_tc_stft_mag      |X| fp32 channels-last [B, rows, cp]   (stft.py:85-97; all TacotronSTFT.mel_spectrogram needs)
+ *   wgb_tc_stft_denoise  Denoiser.forward's max(|X| - bias*strength, 0) e^{j arg X} (denoiser.py:36-38, stft.py:102-103)
+ *                        written as the bf16 hi / lo operands [B*rows][2cp] (Re | Im) of the inverse-basis GEMM. */
+WGB_API int wgb_tc_stft_mag(const void* a_hi, const void* a_lo, const void* w3_paired, void* mag_cl, int batch, int rows,
+                            int cp, int K, long long row_stride, long long batch_stride, void* stream);
+WGB_API int wgb_tc_stft_denoise(const void* a_hi, const void* a_lo, const void* w3_paired, const float* bias_spec,
+                                float strength, void* hi_out, void* lo_out, int batch, int rows, int cutoff, int cp, int K,
+                                long long row_stride, long long batch_stride, void* stream);
+
 /* ---------------------------------------------------------------- FP32 validation path (CUDA cores) */
 
 /* C[b][m][n] (+)= sum_k A[b][m+shift][k] W[n][k] + bias[n]; rows outside [0,M) read as zero, so a

@@ -13,6 +13,9 @@ int tc_wn_skip_end(const void*, int, const void*, const float*, const float*, fl
 int tc_gemm_plain(const void*, const void*, const float*, void*, int, int, int, int, int, cudaStream_t);
 int tc_gemm_split3(const void*, const void*, const void*, const float*, void*, int, int, int, int, long long, long long,
                    cudaStream_t);
+int tc_stft_mag(const void*, const void*, const void*, void*, int, int, int, int, long long, long long, cudaStream_t);
+int tc_stft_denoise(const void*, const void*, const void*, const float*, float, void*, void*, int, int, int, int, int,
+                    long long, long long, cudaStream_t);
 // wn_tc2.cu
 int tc2_wn_gate(const void*, const void*, const void*, const float*, void*, int, int, int, cudaStream_t);
 int tc2_wn_res(const void*, const void*, const float*, const void*, void*, int, int, long long, const void*, float*, int,
@@ -158,6 +161,17 @@ WGB_API int wgb_tc_gemm(const void* a, const void* w, const float* bias, void* c
 WGB_API int wgb_tc_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, const float* bias, void* c, int batch,
                                int rows, int N, int K, long long row_stride, long long batch_stride, void* stream) {
     return tc_gemm_split3(a_hi, a_lo, w3, bias, c, batch, rows, N, K, row_stride, batch_stride, S(stream));
+}
+
+WGB_API int wgb_tc_stft_mag(const void* a_hi, const void* a_lo, const void* w3_paired, void* mag_cl, int batch, int rows,
+                            int cp, int K, long long row_stride, long long batch_stride, void* stream) {
+    return tc_stft_mag(a_hi, a_lo, w3_paired, mag_cl, batch, rows, cp, K, row_stride, batch_stride, S(stream));
+}
+WGB_API int wgb_tc_stft_denoise(const void* a_hi, const void* a_lo, const void* w3_paired, const float* bias_spec,
+                                float strength, void* hi_out, void* lo_out, int batch, int rows, int cutoff, int cp, int K,
+                                long long row_stride, long long batch_stride, void* stream) {
+    return tc_stft_denoise(a_hi, a_lo, w3_paired, bias_spec, strength, hi_out, lo_out, batch, rows, cutoff, cp, K,
+                           row_stride, batch_stride, S(stream));
 }
 
 WGB_API int wgb_sgemm_f32(const float* A, const float* W, const float* bias, void* C, int out_bf16, int batch, int M, int N,

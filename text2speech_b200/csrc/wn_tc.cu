@@ -50,6 +50,12 @@ struct TcParams {
     const float* w_mix;           // SKIP_END infer: W^-1 as [8][8] row-major (top-left CxC used)
     float* log_s;                 // SKIP_END forward: [B,n_half,T]
     void* c_out;                  // PLAIN  [B,T,N] fp32 (DIR=0) or bf16 (DIR=1); bias may be null
+                                  //        DIR=2 (paired Re/Im columns): magnitudes fp32 [B,T,N/2]
+                                  //        DIR=3 (paired): spectral subtraction, bf16 hi part [B,T,N] (Re | Im halves)
+    void* c_out2;                 // PLAIN  DIR=3: bf16 lo part
+    const float* spec_bias;       // PLAIN  DIR=3: denoiser bias spectrum [cutoff]
+    float strength;               // PLAIN  DIR=3
+    int cutoff;                   // PLAIN  DIR=3: bins < cutoff are real spectrum bins, the rest padding
     int n_total;                  // PLAIN  N (multiple of 256)
     int seg_chunks, seg_mask;     // PLAIN  K is split in segments of seg_chunks chunks; bit s of seg_mask selects
                                   //        map_a1 (else map_a0) for segment s (split-bf16 hi/lo operands)
@@ -301,6 +307,69 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                                 make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
                     }
+                } else if constexpr (MODE == MODE_PLAIN && DIR >= 2) {
+                    // STFT with Re/Im-paired basis rows: columns 0..127 of the pass are Re of bins 128 pass .. +127,
+                    // columns 128..255 the matching Im (stft.py:85-97), so |X| and the Denoiser's spectral
+                    // subtraction (denoiser.py:36-38 + stft.py:102-103) happen here instead of in extra passes over HBM
+                    const int cp = p.n_total >> 1;
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t vr[32], vi[32];
+                        tmem_ld_32x32b_x32(taddr + ch * 32, vr);
+                        tmem_ld_32x32b_x32(taddr + 128 + ch * 32, vi);
+                        tmem_ld_wait();
+                        const int k0 = pass * 128 + ch * 32;
+                        if constexpr (DIR == 2) {
+                            float m[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float re = __uint_as_float(vr[j]), im = __uint_as_float(vi[j]);
+                                m[j] = sqrtf(re * re + im * im);
+                            }
+                            if (live) {
+                                float4* d4 = reinterpret_cast<float4*>(static_cast<float*>(p.c_out) + grow * cp + k0);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) d4[j] = make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
+                            }
+                        } else {
+                            uint32_t hr[16], lr[16], hi_[16], li[16];
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                float o[4];
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    float re = __uint_as_float(vr[j + e]), im = __uint_as_float(vi[j + e]);
+                                    if (k0 + j + e < p.cutoff) {
+                                        const float mag = sqrtf(re * re + im * im);
+                                        const float m2 = fmaxf(mag - __ldg(p.spec_bias + k0 + j + e) * p.strength, 0.f);
+                                        const float g = mag > 0.f ? m2 / mag : 0.f;
+                                        re = mag > 0.f ? re * g : m2;      // atan2(0,0) = 0 -> cos = 1, sin = 0
+                                        im = im * g;
+                                    }
+                                    o[e] = re;
+                                    o[2 + e] = im;
+                                }
+                                const __nv_bfloat162 rh = __floats2bfloat162_rn(o[0], o[1]), ih = __floats2bfloat162_rn(o[2], o[3]);
+                                const __nv_bfloat162 rl = __floats2bfloat162_rn(o[0] - __low2float(rh), o[1] - __high2float(rh));
+                                const __nv_bfloat162 il = __floats2bfloat162_rn(o[2] - __low2float(ih), o[3] - __high2float(ih));
+                                hr[j >> 1] = *reinterpret_cast<const uint32_t*>(&rh);
+                                lr[j >> 1] = *reinterpret_cast<const uint32_t*>(&rl);
+                                hi_[j >> 1] = *reinterpret_cast<const uint32_t*>(&ih);
+                                li[j >> 1] = *reinterpret_cast<const uint32_t*>(&il);
+                            }
+                            if (live) {
+                                __nv_bfloat16* hp = static_cast<__nv_bfloat16*>(p.c_out) + grow * p.n_total + k0;
+                                __nv_bfloat16* lp = static_cast<__nv_bfloat16*>(p.c_out2) + grow * p.n_total + k0;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    reinterpret_cast<uint4*>(hp)[j] = make_uint4(hr[4 * j], hr[4 * j + 1], hr[4 * j + 2], hr[4 * j + 3]);
+                                    reinterpret_cast<uint4*>(lp)[j] = make_uint4(lr[4 * j], lr[4 * j + 1], lr[4 * j + 2], lr[4 * j + 3]);
+                                    reinterpret_cast<uint4*>(hp + cp)[j] = make_uint4(hi_[4 * j], hi_[4 * j + 1], hi_[4 * j + 2], hi_[4 * j + 3]);
+                                    reinterpret_cast<uint4*>(lp + cp)[j] = make_uint4(li[4 * j], li[4 * j + 1], li[4 * j + 2], li[4 * j + 3]);
+                                }
+                            }
+                        }
+                    }
                 } else if constexpr (MODE == MODE_PLAIN) {
                     const size_t off = grow * p.n_total + pass * kBlockN;
 #pragma unroll 1
@@ -508,8 +577,9 @@ int tc_gemm_plain(const void* a, const void* w, const float* bias, void* c, int 
 // run as ONE K = 3*K GEMM: K segments [A_hi | A_lo | A_hi] against the packed weight [W_hi | W_hi | W_lo].
 // Rows of A may overlap in memory (row_stride < K): that is how STFT frames (hop < filter_length) are read
 // straight from the padded signal (reference stft.py:85-89 does the same with a strided conv).
-int tc_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, const float* bias, void* c, int batch, int rows,
-                   int N, int K, long long row_stride, long long batch_stride, cudaStream_t stream) {
+static int gemm_split3(const void* a_hi, const void* a_lo, const void* w3, const float* bias, void* c, int batch, int rows,
+                       int N, int K, long long row_stride, long long batch_stride, int epilogue, void* c2,
+                       const float* spec_bias, float strength, int cutoff, cudaStream_t stream) {
     WGB_REQUIRE(a_hi && a_lo && w3 && c, "null pointer");
     WGB_REQUIRE(N > 0 && N % kBlockN == 0 && K > 0 && K % kBlockK == 0, "N must be a multiple of 256 and K of 64 (N=%d K=%d)", N, K);
     WGB_REQUIRE(row_stride % 8 == 0 && batch_stride % 8 == 0, "row/batch strides must be multiples of 8 elements (16 B)");
@@ -525,7 +595,38 @@ int tc_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, const flo
     if (int e = make_tmap_bf16(&mhi, a_hi, 3, dims, strides, box)) return e;
     if (int e = make_tmap_bf16(&mlo, a_lo, 3, dims, strides, box)) return e;
     if (int e = weight_map(&mb, w3, N, 3 * K)) return e;
+    p.c_out2 = c2; p.spec_bias = spec_bias; p.strength = strength; p.cutoff = cutoff;
+    if (epilogue == 2) return launch<MODE_PLAIN, 0, 2>(mhi, mlo, mb, mhi, p, stream);
+    if (epilogue == 3) return launch<MODE_PLAIN, 0, 3>(mhi, mlo, mb, mhi, p, stream);
     return launch<MODE_PLAIN, 0, 0>(mhi, mlo, mb, mhi, p, stream);
+}
+
+int tc_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, const float* bias, void* c, int batch, int rows,
+                   int N, int K, long long row_stride, long long batch_stride, cudaStream_t stream) {
+    return gemm_split3(a_hi, a_lo, w3, bias, c, batch, rows, N, K, row_stride, batch_stride, 0, nullptr, nullptr, 0.f, 0,
+                       stream);
+}
+
+// STFT with the forward basis packed in Re/Im-paired order (pass p = Re rows of bins 128p..128p+127, then their Im
+// rows): |X| straight from the GEMM epilogue, channels-last [B, rows, cp] (stft.py:85-97; the mel path never needs
+// Re / Im / phase).
+int tc_stft_mag(const void* a_hi, const void* a_lo, const void* w3_paired, void* mag_cl, int batch, int rows, int cp, int K,
+                long long row_stride, long long batch_stride, cudaStream_t stream) {
+    WGB_REQUIRE(cp > 0 && cp % 128 == 0, "cp (%d) must be a multiple of 128", cp);
+    return gemm_split3(a_hi, a_lo, w3_paired, nullptr, mag_cl, batch, rows, 2 * cp, K, row_stride, batch_stride, 2, nullptr,
+                       nullptr, 0.f, 0, stream);
+}
+
+// Same GEMM with the Denoiser's spectral subtraction in the epilogue (denoiser.py:36-38 + the cos/sin recombination
+// of stft.py:102-103 as a magnitude ratio); writes the bf16 hi / lo operands [B*rows, 2cp] (Re | Im) of the
+// inverse-basis GEMM directly.
+int tc_stft_denoise(const void* a_hi, const void* a_lo, const void* w3_paired, const float* bias_spec, float strength,
+                    void* hi_out, void* lo_out, int batch, int rows, int cutoff, int cp, int K, long long row_stride,
+                    long long batch_stride, cudaStream_t stream) {
+    WGB_REQUIRE(cp > 0 && cp % 128 == 0 && cutoff > 0 && cutoff <= cp, "cp (%d) must be a multiple of 128 and >= cutoff", cp);
+    WGB_REQUIRE(bias_spec && lo_out, "null pointer");
+    return gemm_split3(a_hi, a_lo, w3_paired, nullptr, hi_out, batch, rows, 2 * cp, K, row_stride, batch_stride, 3, lo_out,
+                       bias_spec, strength, cutoff, stream);
 }
 
 int tc_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end, const float* b_end,

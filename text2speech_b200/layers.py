@@ -48,11 +48,14 @@ class TacotronSTFT(torch.nn.Module):
         assert torch.min(y.data) >= -1                                         # layers.py:72-73
         assert torch.max(y.data) <= 1
         y = y.float().contiguous()
-        spec, frames, cp = self.stft_fn._spectrum(y)
         b = y.shape[0]
         s = _lib.stream_ptr()
-        mag_cl = torch.empty((b, frames, cp), device=y.device, dtype=torch.float32)
-        _lib.call("wgb_stft_polar", spec, None, None, mag_cl, b, frames, self.stft_fn.cutoff, cp, s)
+        if self.stft_fn._use_tc():            # |X| straight from the STFT GEMM's epilogue
+            mag_cl, frames, cp = self.stft_fn._magnitude_cl(y)
+        else:
+            spec, frames, cp = self.stft_fn._spectrum(y)
+            mag_cl = torch.empty((b, frames, cp), device=y.device, dtype=torch.float32)
+            _lib.call("wgb_stft_polar", spec, None, None, mag_cl, b, frames, self.stft_fn.cutoff, cp, s)
         raw = torch.empty((b, frames, self.n_mel_channels), device=y.device, dtype=torch.float32)
         w_mel, k_used = self._mel_packed(y.device, cp)
         _lib.call("wgb_sgemm_f32", mag_cl, w_mel, None, raw, 0, 1, b * frames,

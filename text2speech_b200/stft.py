@@ -87,14 +87,23 @@ class STFT(torch.nn.Module):
             ib = self.inverse_basis.detach().float().cpu()[:, 0]
             inv[:, :cutoff] = ib[:cutoff].t()
             inv[:, cp: cp + cutoff] = ib[cutoff:].t()
+            fwd_paired = None
             if tc:
+                # Re/Im-paired row order for the fused-epilogue GEMMs: pass p = Re rows of bins 128p..128p+127, then Im
+                order = torch.cat([torch.cat([torch.arange(128 * p, 128 * (p + 1)), cp + torch.arange(128 * p, 128 * (p + 1))])
+                                   for p in range(cp // 128)])
+                fwd_paired = _split3(fwd[order]).to(device)
                 fwd, inv = _split3(fwd), _split3(inv)
             if self.window is not None:
                 sq = padded_window(self.window, self.win_length, length) ** 2
             else:
                 sq = np.zeros(length)
-            self._pack = (key, fwd.to(device), inv.to(device), torch.from_numpy(sq).double().to(device), cp)
-        return self._pack[1:]
+            self._pack = (key, fwd.to(device), inv.to(device), torch.from_numpy(sq).double().to(device), cp, fwd_paired)
+        return self._pack[1:5]
+
+    def _paired_basis(self, device):
+        self._packed(device)
+        return self._pack[5]
 
     # ------------------------------------------------------------------ device pipeline pieces
     def _spectrum(self, y: torch.Tensor):
@@ -108,10 +117,7 @@ class STFT(torch.nn.Module):
         spec = torch.empty((b, frames, 2 * cp), device=y.device, dtype=torch.float32)
         if self._use_tc():
             # frames are overlapping rows (stride = hop) of the padded signal, read by TMA; operands split hi/lo
-            ld_pad = _round_up(n + length, 8)
-            hi = torch.empty((b, ld_pad), device=y.device, dtype=torch.bfloat16)
-            lo = torch.empty_like(hi)
-            _lib.call("wgb_stft_reflect_pad_split", y, hi, lo, b, n, length // 2, ld_pad, s)
+            hi, lo, ld_pad = self._padded_split(y)
             _lib.call("wgb_tc_gemm_split3", hi, lo, fwd, None, spec, b, frames, 2 * cp, length, hop, ld_pad, s)
             return spec, frames, cp
         if hop % 4 != 0 or length % 4 != 0:
@@ -122,6 +128,48 @@ class STFT(torch.nn.Module):
         _lib.call("wgb_sgemm_f32", ypad, fwd, None, spec, 0, b, frames, 2 * cp, length,
                   hop, ld_pad, length, 2 * cp, frames * 2 * cp, 0, 0, s)
         return spec, frames, cp
+
+    def _padded_split(self, y: torch.Tensor):
+        """reflect-padded signal as bf16 hi / lo parts [B, ld_pad] (operands of the tensor-core STFT GEMMs)."""
+        b, n = y.shape
+        ld_pad = _round_up(n + self.filter_length, 8)
+        hi = torch.empty((b, ld_pad), device=y.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi)
+        _lib.call("wgb_stft_reflect_pad_split", y, hi, lo, b, n, self.filter_length // 2, ld_pad, _lib.stream_ptr())
+        return hi, lo, ld_pad
+
+    def _magnitude_cl(self, y: torch.Tensor):
+        """y [B,N] -> |STFT| channels-last fp32 [B, F, cp] straight from the GEMM epilogue (tensor-core path only)."""
+        _lib.require_b200(y.device)
+        _, _, _, cp = self._packed(y.device)
+        b, n = y.shape
+        frames = n // self.hop_length + 1
+        hi, lo, ld_pad = self._padded_split(y)
+        mag = torch.empty((b, frames, cp), device=y.device, dtype=torch.float32)
+        _lib.call("wgb_tc_stft_mag", hi, lo, self._paired_basis(y.device), mag, b, frames, cp, self.filter_length,
+                  self.hop_length, ld_pad, _lib.stream_ptr())
+        return mag, frames, cp
+
+    def _denoised(self, y: torch.Tensor, bias_spec: torch.Tensor, strength: float) -> torch.Tensor:
+        """Denoiser.forward on the tensor-core path: STFT GEMM with the spectral subtraction in its epilogue (writes
+        the inverse GEMM's bf16 hi / lo operands), inverse GEMM, overlap-add."""
+        _lib.require_b200(y.device)
+        _, inv, win_sq, cp = self._packed(y.device)
+        b, n = y.shape
+        length, hop = self.filter_length, self.hop_length
+        frames = n // hop + 1
+        s = _lib.stream_ptr()
+        hi, lo, ld_pad = self._padded_split(y)
+        shi = torch.empty((b * frames, 2 * cp), device=y.device, dtype=torch.bfloat16)
+        slo = torch.empty_like(shi)
+        _lib.call("wgb_tc_stft_denoise", hi, lo, self._paired_basis(y.device), bias_spec, float(strength), shi, slo, b,
+                  frames, self.cutoff, cp, length, hop, ld_pad, s)
+        fr = torch.empty((b, frames, length), device=y.device, dtype=torch.float32)
+        _lib.call("wgb_tc_gemm_split3", shi, slo, inv, None, fr, 1, b * frames, length, 2 * cp, 2 * cp,
+                  b * frames * 2 * cp, s)
+        out = torch.empty((b, 1, hop * (frames - 1)), device=y.device, dtype=torch.float32)
+        _lib.call("wgb_istft_overlap_add", fr, win_sq, out, b, frames, length, hop, s)
+        return out
 
     def _synthesize(self, spec: torch.Tensor, frames: int, cp: int, denoise=None) -> torch.Tensor:
         """spec [B, F, 2cp] -> [B, 1, hop*(F-1)] (stft.py:105-128).  denoise = (bias_spec [cutoff], strength): apply
