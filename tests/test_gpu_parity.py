@@ -425,6 +425,18 @@ def test_infer_ragged_small_shapes(models, B, F):
         m.cond_path = "auto"
 
 
+def test_graphed_infer_matches_eager(models):
+    m = models["bench"]
+    m.mode = "bf16"
+    B, F = 2, 40
+    run = m.graphed_infer(B, F, sigma=util.SIGMA)
+    for seed in (1, 2):
+        mel, z = syn.synthetic_mel(B, F, seed=seed).to(DEV), syn.synthetic_z(B, F, seed=10 + seed).to(DEV)
+        want = m.infer(mel, sigma=util.SIGMA, z=z)
+        got = run(mel, z).clone()
+        assert torch.equal(got, want)
+
+
 def test_first_layer_fold_agrees(models, golden, monkeypatch):
     """Composed path with and without WN.start folded into in_layers[0]."""
     from text2speech_b200 import engine
