@@ -143,11 +143,14 @@ WGB_API int wgb_tc2_wn_skip_end(const void* acts_all, int n_layers, const void* 
  * in; then the same coupling / W^-1 / log_s / optional next-flow WN.start epilogue as wgb_tc2_wn_skip_end.
  * HBM-bound: 8 KB of activations per group step, 2*4096*16 tensor FLOPs instead of 2*4096*512.
  * skip_acc (optional) fp32 [B*T][8] is added to the product: with the first n-1 layers accumulated by
- * wgb_tc2_wn_res, call this with n_layers = 1 on the last layer's activations and its [16][512] weight slice. */
+ * wgb_tc2_wn_res, call this with n_layers = 1 on the last layer's activations and its [16][512] weight slice.
+ * next_w_mix (direction 1 only, with a fused next-flow start): fp32 [8][8] W of the NEXT flow's Invertible1x1Conv,
+ * applied to the updated row first (WaveGlow.forward runs convinv[k+1] before WN[k+1], glow.py:233). */
 WGB_API int wgb_tc_wn_skip16_end(const void* acts_all, int n_layers, const void* w16, const float* b_end, float* x,
                                  const float* w_mix, float* log_s, int batch, int T, int n_half, int direction,
                                  const float* next_w_start, const float* next_b_start, int next_n_half, void* h_next,
-                                 long long h_next_batch_rows, const float* skip_acc, void* stream);
+                                 long long h_next_batch_rows, const float* skip_acc, const float* next_w_mix,
+                                 void* stream);
 
 /* Plain tcgen05 GEMM with the same TMA/TMEM pipeline: C[b,t,n] = sum_k A[b,t,k] W[n,k] + bias[n];
  * A bf16 [B,T,K] (K % 64 == 0), W bf16 [N,K] (N % 256 == 0), C fp32 or bf16 [B,T,N]; bias may be NULL.

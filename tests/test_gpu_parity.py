@@ -174,13 +174,28 @@ def test_tc_skip_end_coupling(lib, packed_q, k, direction, entry):
     if entry == "wgb_tc_wn_skip16_end":          # WN.end composed with the skip GEMM (hi/lo bf16 split of the product)
         args = (acts_all, 8, fl["w_skip16"], fl["b_end"], xd, fl["w_mix_inv"] if direction == 0 else None, log_s, B, T,
                 n_half, direction)
-        tail = (None,)
+        tail = (None, None)
         if k == 5:                               # layers 0..6 pre-accumulated (as wgb_tc2_wn_res does), last layer here
             w_comp = fl["w_comp"].cpu().double()                                # [8][512][8]
             pre = sum(acts[i].permute(0, 2, 1).double().reshape(B * T, 512) @ w_comp[i] for i in range(7))
             args = (acts_all[7].contiguous(), 1, fl["w_skip16_layers"][7], fl["b_end"], xd,
                     fl["w_mix_inv"] if direction == 0 else None, log_s, B, T, n_half, direction)
-            tail = (pre.float().to(DEV).contiguous(),)
+            tail = (pre.float().to(DEV).contiguous(), None)
+    fwd_next = entry == "wgb_tc_wn_skip16_end" and direction == 1 and k < 11 and k != 5
+    if fwd_next:                                 # forward: next flow's 1x1 conv (glow.py:233) then its WN.start, fused
+        nf = pk.flows[k + 1]
+        h_next = torch.zeros(B, T, 512, device=DEV, dtype=torch.bfloat16)
+        lib.call(entry, *args, nf["w_start"], nf["b_start"], nf["n_half"], h_next, T, None, nf["w_mix"], lib.stream_ptr())
+        torch.cuda.synchronize()
+        cn = 2 * nf["n_half"]
+        w_next = st[f"convinv.{k + 1}.conv.weight"][:, :, 0]
+        want[:, :, 8 - cn:] = want[:, :, 8 - cn:] @ w_next.t()
+        assert util.rel_l2(xd.cpu(), want) <= 1e-4
+        a0 = xd.cpu()[:, :, 8 - cn: 8 - cn + nf["n_half"]]
+        want_h = a0 @ st[f"WN.{k + 1}.start.weight"][:, :, 0].t() + st[f"WN.{k + 1}.start.bias"]
+        assert util.rel_l2(h_next.float().cpu(), want_h) <= util.TOL_LAYER_BF16
+        assert util.rel_l2(log_s.cpu(), out[:, n_half:]) <= 1e-4
+        return
     if entry != "wgb_tc_wn_skip_end":
         if direction == 0 and k > 0:             # also run WN.start of flow k-1 on the updated rows (glow.py:156)
             nf = pk.flows[k - 1]

@@ -32,7 +32,7 @@ int tc2_wn_skip_end(const void*, int, const void*, const float*, const float*, f
                     int, int, const float*, const float*, int, void*, long long, cudaStream_t);
 // wn_skip16.cu
 int tc_wn_skip16_end(const void*, int, const void*, const float*, float*, const float*, float*, int, int, int, int,
-                     const float*, const float*, int, void*, long long, const float*, cudaStream_t);
+                     const float*, const float*, int, void*, long long, const float*, const float*, cudaStream_t);
 // ref_f32.cu
 int sgemm_nt(const float*, const float*, const float*, void*, int, int, int, int, int, long long, long long, long long,
              long long, long long, int, int, cudaStream_t);
@@ -138,9 +138,10 @@ WGB_API int wgb_tc2_wn_skip_end(const void* acts_all, int n_layers, const void* 
 WGB_API int wgb_tc_wn_skip16_end(const void* acts_all, int n_layers, const void* w16, const float* b_end, float* x,
                                  const float* w_mix, float* log_s, int batch, int T, int n_half, int direction,
                                  const float* next_w_start, const float* next_b_start, int next_n_half, void* h_next,
-                                 long long h_next_batch_rows, const float* skip_acc, void* stream) {
+                                 long long h_next_batch_rows, const float* skip_acc, const float* next_w_mix,
+                                 void* stream) {
     return tc_wn_skip16_end(acts_all, n_layers, w16, b_end, x, w_mix, log_s, batch, T, n_half, direction, next_w_start,
-                            next_b_start, next_n_half, h_next, h_next_batch_rows, skip_acc, S(stream));
+                            next_b_start, next_n_half, h_next, h_next_batch_rows, skip_acc, next_w_mix, S(stream));
 }
 WGB_API int wgb_tc_wn_res(const void* acts, const void* w_res, const float* bias, const void* h_in, void* h_out, int batch,
                   int T, void* stream) {

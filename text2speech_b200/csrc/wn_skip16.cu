@@ -37,6 +37,8 @@ struct Params {
     int batch, T, tiles_per_b, n_tiles, n_chunks;
     const float* b_end;           // [8], skip biases folded through W_end
     const float* skip_acc;        // optional [B*T][8]: contributions of the layers accumulated by wgb_tc2_wn_res
+    const float* next_w_mix;      // forward, optional: W of the NEXT flow's Invertible1x1Conv ([8][8], top-left C'xC'),
+                                  // applied to the updated row before its fused WN.start (glow.py:233 of flow k+1)
     float* x;                     // flow state [B,T,8]
     const float* w_mix;           // infer: W^-1 [8][8]
     float* log_s;                 // forward: [B,n_half,T]
@@ -189,9 +191,25 @@ skip16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     p.log_s[(static_cast<size_t>(b) * NHALF + j) * p.T + t] = ls;
                 }
             }
+            if constexpr (DIR == 1) {
+                if (p.next_w_mix) {                          // the next flow's 1x1 conv on its last C' = 2 n_half' channels
+                    const int cn = 2 * p.next_n_half, bn = 8 - cn;
+                    float xo[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (i >= bn && c >= bn) acc = fmaf(__ldg(p.next_w_mix + (i - bn) * 8 + (c - bn)), xv[c], acc);
+                        xo[i] = i >= bn ? acc : xv[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) xv[i] = xo[i];
+                }
+            }
             *reinterpret_cast<float4*>(xr) = *reinterpret_cast<const float4*>(&xv[0]);
             *reinterpret_cast<float4*>(xr + 4) = *reinterpret_cast<const float4*>(&xv[4]);
-            if constexpr (DIR == 0) if (p.h_next) {
+            if (p.h_next) {
                 // WN.start of the next flow (glow.py:156) on the freshly updated row
                 const int nb = 8 - 2 * p.next_n_half;
                 float a0[4];
@@ -248,7 +266,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p,
 int tc_wn_skip16_end(const void* acts_all, int n_layers, const void* w16, const float* b_end, float* x, const float* w_mix,
                      float* log_s, int batch, int T, int n_half, int direction, const float* next_w_start,
                      const float* next_b_start, int next_n_half, void* h_next, long long h_next_batch_rows,
-                     const float* skip_acc, cudaStream_t stream) {
+                     const float* skip_acc, const float* next_w_mix, cudaStream_t stream) {
     using namespace skip16;
     WGB_REQUIRE(acts_all && w16 && b_end && x, "null pointer");
     WGB_REQUIRE(n_layers >= 1 && batch > 0 && T > 0, "bad shape");
@@ -261,9 +279,11 @@ int tc_wn_skip16_end(const void* acts_all, int n_layers, const void* w16, const 
     p.n_tiles = batch * p.tiles_per_b;
     p.n_chunks = n_layers * kNCh / kBlockK;
     p.b_end = b_end; p.x = x; p.w_mix = w_mix; p.log_s = log_s; p.skip_acc = skip_acc;
+    WGB_REQUIRE(!next_w_mix || (direction == 1 && h_next), "next_w_mix goes with direction 1 and a fused next-flow start");
+    p.next_w_mix = next_w_mix;
     if (h_next) {
-        WGB_REQUIRE(direction == 0, "the fused WN.start of the next flow exists for the infer direction only");
         WGB_REQUIRE(next_w_start && next_b_start && next_n_half >= 1 && next_n_half <= 4, "bad next-flow start arguments");
+        WGB_REQUIRE(direction == 0 || next_w_mix, "forward: the next flow's 1x1 conv must run before its WN.start (pass next_w_mix)");
         WGB_REQUIRE(h_next_batch_rows >= T, "h_next_batch_rows must be >= T");
         p.next_w_start = next_w_start; p.next_b_start = next_b_start; p.next_n_half = next_n_half;
         p.h_next = static_cast<__nv_bfloat16*>(h_next);

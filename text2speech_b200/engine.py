@@ -137,7 +137,8 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int
     if SKIP_KERNEL == "single":
         _lib.call(skip_end, *args, s)
         return False
-    fuse = direction == 0 and next_fl is not None and FUSE_START
+    # infer: the next flow (k-1) starts from the row as updated here; forward: flow k+1 first applies its 1x1 conv
+    fuse = next_fl is not None and FUSE_START and (direction == 0 or skip_acc is None)
     if skip_acc is not None:
         _lib.call("wgb_end_from_acc", skip_acc, fl["b_end"], x, fl["w_mix_inv"] if direction == 0 else None, log_s, b, t,
                   fl["n_half"], direction, *((next_fl["w_start"], next_fl["b_start"], next_fl["n_half"], h0, h_rows)
@@ -154,6 +155,10 @@ def _wn_bf16(pk: PackedWaveGlow, fl: dict, x: Tensor, cond, bufs, direction: int
         args = (acts_all, pk.n_layers, fl["w_skip16"], fl["b_end"], x,
                 fl["w_mix_inv"] if direction == 0 else None, log_s, b, t, fl["n_half"], direction)
         tail = (None,)
+    if SKIP_KERNEL == "pair":                 # K = 4096 x N = 512 variant: fused start for infer only, no fused mix
+        fuse = fuse and direction == 0
+    elif tail:
+        tail = tail + ((next_fl["w_mix"] if (fuse and direction == 1) else None),)
     if fuse:
         _lib.call(skip_end, *args, next_fl["w_start"], next_fl["b_start"], next_fl["n_half"], h0, h_rows, *tail, s)
     else:
@@ -266,12 +271,14 @@ def forward(pk: PackedWaveGlow, mel: Tensor, audio: Tensor) -> Tuple[Tensor, Lis
     x = audio[:, : t * pk.n_group].reshape(b, t, pk.n_group).float().contiguous().clone()
     bufs = _alloc(pk, b, t, mel.device, h_rows)
     log_s_list, log_det_list = [], []
+    started = False                           # flow k's 1x1 conv + WN.start already done by flow k-1's skip+end kernel
     for k in range(pk.n_flows):
         fl = pk.flows[k]
-        _lib.call("wgb_flow_mix", x, fl["w_mix"], b * t, 2 * fl["n_half"], s)
+        if not started:
+            _lib.call("wgb_flow_mix", x, fl["w_mix"], b * t, 2 * fl["n_half"], s)
         log_det_list.append(torch.tensor(b * t * fl["logdet"], device=mel.device, dtype=torch.float32))
         log_s = torch.empty((b, fl["n_half"], t), device=mel.device, dtype=torch.float32)
-        run_wn(pk, k, x, cond, bufs, 1, log_s)
+        started = run_wn(pk, k, x, cond, bufs, 1, log_s, started, k + 1 if k + 1 < pk.n_flows else None)
         log_s_list.append(log_s)
     z = torch.empty((b, pk.n_group, t), device=mel.device, dtype=torch.float32)
     _lib.call("wgb_flow_to_z", x, z, b, t, s)

@@ -124,13 +124,13 @@ def main():
                      lambda: _lib.call("wgb_tc2_wn_skip_end", *skip_args, nf["w_start"], nf["b_start"], nf["n_half"], h1, t, s)))
     s16 = (acts_all, 8, fl["w_skip16"], fl["b_end"], x, fl["w_mix_inv"], None, b, t, fl["n_half"], 0)
     variants.append(("wgb_tc_wn_skip16_end", skip_flop, (8 * 1024 + 64) * steps,
-                     lambda: _lib.call("wgb_tc_wn_skip16_end", *s16, None, None, 0, None, 0, None, s)))
+                     lambda: _lib.call("wgb_tc_wn_skip16_end", *s16, None, None, 0, None, 0, None, None, s)))
     variants.append(("wgb_tc_wn_skip16_end + next start", skip_flop, (9 * 1024 + 64) * steps,
-                     lambda: _lib.call("wgb_tc_wn_skip16_end", *s16, nf["w_start"], nf["b_start"], nf["n_half"], h1, t, None, s)))
+                     lambda: _lib.call("wgb_tc_wn_skip16_end", *s16, nf["w_start"], nf["b_start"], nf["n_half"], h1, t, None, None, s)))
     s16l = (acts_all[7], 1, fl["w_skip16_layers"][7], fl["b_end"], x, fl["w_mix_inv"], None, b, t, fl["n_half"], 0)
     variants.append(("wgb_tc_wn_skip16_end last layer + acc + next start", 0, (1024 + 96 + 1024) * steps,
                      lambda: _lib.call("wgb_tc_wn_skip16_end", *s16l, nf["w_start"], nf["b_start"], nf["n_half"], h1, t,
-                                       skip_row, s)))
+                                       skip_row, None, s)))
     if pk.has_mel:
         stack = torch.randn((b, args.frames, 320), device=DEV).to(bf)
         for d in (1, 128):
