@@ -440,6 +440,38 @@ def test_infer_ragged_small_shapes(models, B, F):
         m.cond_path = "auto"
 
 
+def test_full_size_batch_rows_equal_single_utterance_calls(models):
+    """BASELINE configs[2] shape (64 x 80x860): rows of the batched call equal batch-1 calls bit for bit (the padded
+    tiling mixes utterances inside a tile, the arithmetic per row must not depend on it)."""
+    m = models["bench"]
+    m.mode = "bf16"
+    B, F = 64, 860
+    mel, z = syn.synthetic_mel(B, F, seed=0).to(DEV), syn.synthetic_z(B, F, seed=2024).to(DEV)
+    full = m.infer(mel, sigma=util.SIGMA, z=z)
+    assert full.shape == (B, 256 * F) and bool(torch.isfinite(full).all())
+    for i in (0, 17, 63):
+        one = m.infer(mel[i: i + 1].contiguous(), sigma=util.SIGMA, z=z[i: i + 1].contiguous())
+        assert torch.equal(one[0], full[i]), i
+
+
+def test_full_utterance_snr_against_reference(models):
+    """One 10 s utterance (80x860, T = 27 520) end to end against the audio the UNMODIFIED reference produced for the
+    same weights, mel and noise (tests/golden/make_golden_full.py): BF16 mode SNR >= 30 dB, FP32 mode <= 3e-5."""
+    import os
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full_utterance_golden.npz")) as f:
+        want = torch.from_numpy(f["bench_full_infer_audio"])
+    m = models["bench"]
+    F = 860
+    mel, z = syn.synthetic_mel(1, F, seed=0).to(DEV), syn.synthetic_z(1, F, seed=2024).to(DEV)
+    m.mode = "bf16"
+    snr = util.snr_db(m.infer(mel, sigma=util.SIGMA, z=z).cpu(), want)
+    assert snr >= util.MIN_SNR_DB, snr
+    m.mode = "fp32"
+    err = util.rel_l2(m.infer(mel, sigma=util.SIGMA, z=z).cpu(), want)
+    m.mode = "bf16"
+    assert err <= 3e-5, err
+
+
 def test_graphed_infer_matches_eager(models):
     m = models["bench"]
     m.mode = "bf16"

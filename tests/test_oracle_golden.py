@@ -117,3 +117,18 @@ def test_denoiser(golden):
         out = oracle.denoise(y, torch.from_numpy(golden["denoiser_bias_spec"]), s, fwd, inv, 256, 1024)
         assert out.shape == (2, 1, 4096)
         assert util.rel_l2(out, golden[key]) < 1e-5
+
+
+def test_oracle_full_utterance_matches_reference():
+    """The oracle at BASELINE configs[1] size (80x860 mel, T = 27 520) against the unmodified reference's audio
+    (tests/golden/make_golden_full.py)."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full_utterance_golden.npz")
+    with np.load(path) as f:
+        want = f["bench_full_infer_audio"]
+    torch.set_num_threads(os.cpu_count() or 1)
+    mel, z = syn.synthetic_mel(1, 860, seed=0), syn.synthetic_z(1, 860, seed=2024)
+    with torch.no_grad():
+        got = oracle.waveglow_infer(util.state_dict("bench"), mel, z, util.SIGMA)
+    assert got.shape == (1, 220160)
+    assert util.rel_l2(got, want) < 1e-5
