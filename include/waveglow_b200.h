@@ -191,6 +191,10 @@ WGB_API int wgb_sgemm_f32(const float* A, const float* W, const float* bias, voi
                   long long c_batch, int shift, int accumulate, void* stream);
 /* acts = tanh(u[:, :C]) * sigmoid(u[:, C:]) with accurate tanhf/expf (glow.py:33-40). */
 WGB_API int wgb_gate_f32(const float* u, float* acts, long long rows, int n_ch, void* stream);
+/* fused_add_tanh_sigmoid_multiply(input_a, input_b, n_channels) of the reference on ITS layout (glow.py:33-40):
+ * input_a, input_b fp32 [B, 2*n_ch, T] channels-first -> acts fp32 [B, n_ch, T]. */
+WGB_API int wgb_fused_add_tanh_sigmoid_multiply(const float* input_a, const float* input_b, float* acts, int batch,
+                                                int n_ch, int T, void* stream);
 /* has_res: h += rs[:, :C]; skip (+)= rs[:, C:]   else: skip (+)= rs   (glow.py:165-174). */
 WGB_API int wgb_res_skip_f32(const float* rs, float* h, float* skip, long long rows, int n_ch, int has_res,
                      int first, void* stream);

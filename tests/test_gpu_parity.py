@@ -73,6 +73,19 @@ def test_sgemm_f32(lib, shape):
     assert util.rel_l2(c.cpu(), 2 * want - bias.double()) < 1e-6
 
 
+def test_fused_add_tanh_sigmoid_multiply_function(lib):
+    """The reference's module-level op on its own [B, 2C, T] layout (glow.py:33-40)."""
+    import text2speech_b200 as t2s
+    g = torch.Generator().manual_seed(3)
+    a, b = 2 * torch.randn(3, 64, 77, generator=g), 2 * torch.randn(3, 64, 77, generator=g)
+    u = a + b
+    want = torch.tanh(u[:, :32]) * torch.sigmoid(u[:, 32:])
+    got = t2s.fused_add_tanh_sigmoid_multiply(a.to(DEV), b.to(DEV), torch.IntTensor([32]))
+    assert got.shape == (3, 32, 77) and util.rel_l2(got.cpu(), want) < 1e-6
+    with pytest.raises(ValueError):
+        t2s.fused_add_tanh_sigmoid_multiply(a.to(DEV), b.to(DEV), 16)
+
+
 @pytest.mark.parametrize("entry", ["wgb_tc_wn_gate", "wgb_tc2_wn_gate"])
 @pytest.mark.parametrize("dil_i,T", [(0, 128), (0, 200), (3, 200), (7, 200), (5, 1000), (6, 27520)])
 def test_tc_gate_layer(lib, packed_q, dil_i, T, entry):

@@ -8,7 +8,8 @@ Drop-in module API (same names / signatures / state_dict layout as the reference
 All compute runs in hand-written CUDA behind the C ABI in include/waveglow_b200.h; there is no CPU
 fallback.  Importing the package does not need a GPU (the library is loaded on first use).
 """
-from .glow import WaveGlow, WN, Invertible1x1Conv, WaveGlowLoss, remove      # noqa: F401
+from .glow import (WaveGlow, WN, Invertible1x1Conv, WaveGlowLoss, remove,      # noqa: F401
+                   fused_add_tanh_sigmoid_multiply)
 from .denoiser import Denoiser                                                # noqa: F401
 from .stft import STFT                                                        # noqa: F401
 from .layers import TacotronSTFT                                              # noqa: F401

@@ -37,6 +37,7 @@ int tc_wn_skip16_end(const void*, int, const void*, const float*, float*, const 
 int sgemm_nt(const float*, const float*, const float*, void*, int, int, int, int, int, long long, long long, long long,
              long long, long long, int, int, cudaStream_t);
 int gate_f32(const float*, float*, long long, int, cudaStream_t);
+int fused_add_tanh_sigmoid_multiply(const float*, const float*, float*, int, int, int, cudaStream_t);
 int res_skip_f32(const float*, float*, float*, long long, int, int, int, cudaStream_t);
 // flow.cu
 int flow_from_z(const float*, float*, int, int, float, cudaStream_t);
@@ -183,6 +184,10 @@ WGB_API int wgb_sgemm_f32(const float* A, const float* W, const float* bias, voi
 }
 WGB_API int wgb_gate_f32(const float* u, float* acts, long long rows, int n_ch, void* stream) {
     return gate_f32(u, acts, rows, n_ch, S(stream));
+}
+WGB_API int wgb_fused_add_tanh_sigmoid_multiply(const float* input_a, const float* input_b, float* acts, int batch, int n_ch,
+                                                int T, void* stream) {
+    return fused_add_tanh_sigmoid_multiply(input_a, input_b, acts, batch, n_ch, T, S(stream));
 }
 WGB_API int wgb_res_skip_f32(const float* rs, float* h, float* skip, long long rows, int n_ch, int has_res, int first,
                      void* stream) {

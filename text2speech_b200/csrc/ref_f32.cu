@@ -131,6 +131,32 @@ int gate_f32(const float* u, float* acts, long long rows, int n_ch, cudaStream_t
     return WGB_OK;
 }
 
+// The reference's module-level function on its own layout: input_a, input_b [B, 2C, T] channels-first,
+// out[b, c, t] = tanh((a+b)[b, c, t]) * sigmoid((a+b)[b, C + c, t])   (glow.py:33-40).  t is the fastest index for
+// reads and writes alike, so a flat loop over (b, c, t) is fully coalesced.
+__global__ void fused_add_tanh_sigmoid_multiply_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                       float* __restrict__ out, int n_ch, int T, long long total) {
+    const long long ct = static_cast<long long>(n_ch) * T;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long bi = i / ct;
+        const long long rem = i - bi * ct;                  // c * T + t
+        const long long it = bi * 2 * ct + rem, is = it + ct;
+        const float ut = a[it] + b[it], us = a[is] + b[is];
+        out[i] = tanhf(ut) * (1.f / (1.f + expf(-us)));
+    }
+}
+
+int fused_add_tanh_sigmoid_multiply(const float* a, const float* b, float* out, int batch, int n_ch, int T,
+                                    cudaStream_t stream) {
+    WGB_REQUIRE(a && b && out && batch > 0 && n_ch > 0 && T > 0, "bad arguments");
+    const long long total = static_cast<long long>(batch) * n_ch * T;
+    const int grid = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
+    fused_add_tanh_sigmoid_multiply_kernel<<<grid, 256, 0, stream>>>(a, b, out, n_ch, T, total);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
 // has_res: h += rs[:, :C], skip (+)= rs[:, C:]; else skip (+)= rs (last layer)   (glow.py:165-174)
 __global__ void res_skip_f32_kernel(const float* __restrict__ rs, float* __restrict__ h, float* __restrict__ skip,
                                     long long rows, int n_ch, int has_res, int first) {

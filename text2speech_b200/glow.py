@@ -28,6 +28,23 @@ from . import _lib, engine
 from .packing import PackedWaveGlow
 
 
+def fused_add_tanh_sigmoid_multiply(input_a: torch.Tensor, input_b: torch.Tensor, n_channels) -> torch.Tensor:
+    """Reference glow.py:33-40 as a standalone op: tanh((a+b)[:, :C]) * sigmoid((a+b)[:, C:]) for [B, 2C, T] CUDA
+    tensors (``n_channels`` may be an int or the reference's one-element IntTensor).  Inside the drop-in WaveGlow this
+    is the epilogue of the gate GEMM; this entry exists for callers that use the function on its own."""
+    if not input_a.is_cuda:
+        raise RuntimeError("fused_add_tanh_sigmoid_multiply needs CUDA tensors on a B200; there is no CPU fallback")
+    _lib.require_b200(input_a.device)
+    c = int(n_channels[0]) if isinstance(n_channels, torch.Tensor) else int(n_channels)
+    b, two_c, t = input_a.shape
+    if two_c != 2 * c or input_b.shape != input_a.shape:
+        raise ValueError(f"expected two [B, {2 * c}, T] tensors, got {tuple(input_a.shape)} and {tuple(input_b.shape)}")
+    out = torch.empty((b, c, t), device=input_a.device, dtype=torch.float32)
+    _lib.call("wgb_fused_add_tanh_sigmoid_multiply", input_a.float().contiguous(), input_b.float().contiguous(), out,
+              b, c, t, _lib.stream_ptr())
+    return out.to(input_a.dtype)
+
+
 class WaveGlowLoss(torch.nn.Module):
     """Reference glow.py:43-59 (training-side scalar; plain tensor ops on whatever device z lives)."""
 
