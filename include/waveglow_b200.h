@@ -174,6 +174,13 @@ WGB_API int wgb_tc_gemm_split3(const void* a_hi, const void* a_lo, const void* w
  *   wgb_tc_stft_mag      |X| fp32 channels-last [B, rows, cp]   (stft.py:85-97; all TacotronSTFT.mel_spectrogram needs)
  *   wgb_tc_stft_denoise  Denoiser.forward's max(|X| - bias*strength, 0) e^{j arg X} (denoiser.py:36-38, stft.py:102-103)
  *                        written as the bf16 hi / lo operands [B*rows][2cp] (Re | Im) of the inverse-basis GEMM. */
+/*   wgb_tc_stft_mel      all of TacotronSTFT.mel_spectrogram (layers.py:63-79): |X|, the mel filterbank and
+ *                        log(max(., clip)) in the epilogue; out fp32 [B, n_mel, rows].  mel_table: cp x {first filter
+ *                        index, weight in it, weight in the next filter, 0} (fp32 x 4): the triangular filters overlap
+ *                        pairwise, so a bin feeds at most two adjacent filters (checked by the packer). */
+WGB_API int wgb_tc_stft_mel(const void* a_hi, const void* a_lo, const void* w3_paired, const void* mel_table, float* out,
+                            int batch, int rows, int cp, int K, long long row_stride, long long batch_stride, int n_mel,
+                            float clip, void* stream);
 WGB_API int wgb_tc_stft_mag(const void* a_hi, const void* a_lo, const void* w3_paired, void* mag_cl, int batch, int rows,
                             int cp, int K, long long row_stride, long long batch_stride, void* stream);
 WGB_API int wgb_tc_stft_denoise(const void* a_hi, const void* a_lo, const void* w3_paired, const float* bias_spec,

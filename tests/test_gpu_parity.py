@@ -721,6 +721,19 @@ def test_mel_spectrogram(golden, lib, precision):
     mel = taco.mel_spectrogram(y)
     assert mel.shape == (2, 80, 17)
     assert float((mel.cpu() - torch.from_numpy(golden["mel"])).abs().max()) <= 1e-3
+    if precision == "tc":                     # fused single-kernel path (default) vs separate mel matmul / log kernels
+        assert taco._mel_table(torch.device(DEV), 640) is not None
+        taco.fused = False
+        mel_sep = taco.mel_spectrogram(y)
+        taco.fused = True
+        assert float((mel_sep - mel).abs().max()) <= 2e-5
+        # many frames (several tiles, ragged tail) and 3 waveforms
+        y2 = syn.synthetic_waveforms(3, 256 * 300 + 77, sr=DC["sampling_rate"], seed=8).to(DEV)
+        a = taco.mel_spectrogram(y2)
+        taco.fused = False
+        b = taco.mel_spectrogram(y2)
+        taco.fused = True
+        assert a.shape == b.shape == (3, 80, 301) and float((a - b).abs().max()) <= 2e-5
     with pytest.raises(AssertionError):
         taco.mel_spectrogram(2 * y)                                     # layers.py:72-73 range check
 

@@ -14,6 +14,8 @@ int tc_gemm_plain(const void*, const void*, const float*, void*, int, int, int, 
 int tc_gemm_split3(const void*, const void*, const void*, const float*, void*, int, int, int, int, long long, long long,
                    cudaStream_t);
 int tc_stft_mag(const void*, const void*, const void*, void*, int, int, int, int, long long, long long, cudaStream_t);
+int tc_stft_mel(const void*, const void*, const void*, const void*, void*, int, int, int, int, long long, long long, int, float,
+                cudaStream_t);
 int tc_stft_denoise(const void*, const void*, const void*, const float*, float, void*, void*, int, int, int, int, int,
                     long long, long long, cudaStream_t);
 // wn_tc2.cu
@@ -168,6 +170,12 @@ WGB_API int wgb_tc_gemm_split3(const void* a_hi, const void* a_lo, const void* w
 WGB_API int wgb_tc_stft_mag(const void* a_hi, const void* a_lo, const void* w3_paired, void* mag_cl, int batch, int rows,
                             int cp, int K, long long row_stride, long long batch_stride, void* stream) {
     return tc_stft_mag(a_hi, a_lo, w3_paired, mag_cl, batch, rows, cp, K, row_stride, batch_stride, S(stream));
+}
+WGB_API int wgb_tc_stft_mel(const void* a_hi, const void* a_lo, const void* w3_paired, const void* mel_table, float* out,
+                            int batch, int rows, int cp, int K, long long row_stride, long long batch_stride, int n_mel,
+                            float clip, void* stream) {
+    return tc_stft_mel(a_hi, a_lo, w3_paired, mel_table, out, batch, rows, cp, K, row_stride, batch_stride, n_mel, clip,
+                       S(stream));
 }
 WGB_API int wgb_tc_stft_denoise(const void* a_hi, const void* a_lo, const void* w3_paired, const float* bias_spec,
                                 float strength, void* hi_out, void* lo_out, int batch, int rows, int cutoff, int cp, int K,

@@ -35,7 +35,8 @@ constexpr int kThreads = 192;
 constexpr int kNCh = 512;        // WN channels the tensor-core path is specialised for
 constexpr int kNCond = 640;      // n_mel_channels * n_group
 
-enum Mode { MODE_GATE = 0, MODE_RES = 1, MODE_SKIP_END = 2, MODE_PLAIN = 3 };
+enum Mode { MODE_GATE = 0, MODE_RES = 1, MODE_SKIP_END = 2, MODE_PLAIN = 3, MODE_STFT_MEL = 4 };
+constexpr int kMelMax = 80;          // mel channels the fused STFT->mel epilogue keeps per row (+1 pad column)
 
 struct TcParams {
     int batch, T, tiles_per_b, n_tiles;
@@ -56,6 +57,10 @@ struct TcParams {
     const float* spec_bias;       // PLAIN  DIR=3: denoiser bias spectrum [cutoff]
     float strength;               // PLAIN  DIR=3
     int cutoff;                   // PLAIN  DIR=3: bins < cutoff are real spectrum bins, the rest padding
+    const float4* mel_table;      // STFT_MEL [cp]: {first filter index (as float), weight in that filter, weight in the
+                                  //          next filter, 0}: every bin lies in at most two adjacent triangular filters
+    int n_mel;                    // STFT_MEL (<= 80)
+    float mel_clip;               // STFT_MEL log(max(., clip))
     int n_total;                  // PLAIN  N (multiple of 256)
     int seg_chunks, seg_mask;     // PLAIN  K is split in segments of seg_chunks chunks; bit s of seg_mask selects
                                   //        map_a1 (else map_a0) for segment s (split-bf16 hi/lo operands)
@@ -65,14 +70,17 @@ struct TcParams {
 //   RES:      3 stages + 64 KB h tile (TMA-loaded h_in, updated in place, TMA-stored as h_out) + 2 KB bias
 //   SKIP_END: 4 stages + 16 KB W_end^T
 //   GATE:     4 stages + 4 KB bias (sigmoid half pre-halved)
+//   STFT_MEL: 3 stages + 41.5 KB per-row mel accumulators [128][81] + the sparse mel table [cp] float4
 //   others:   4 stages
 template <int MODE>
 struct SmemLayout {
-    static constexpr int kStages = MODE == MODE_RES ? 3 : 4;
+    static constexpr int kStages = (MODE == MODE_RES || MODE == MODE_STFT_MEL) ? 3 : 4;
     static constexpr int kRing = kStages * kStageBytes;
     static constexpr int kExtraOff = kRing;
     static constexpr int kExtraBytes = MODE == MODE_RES ? kBlockM * kBlockN * 2 + kNCh * 4
-                                       : (MODE == MODE_SKIP_END ? kNCh * 8 * 4 : (MODE == MODE_GATE ? 2 * kNCh * 4 : 0));
+                                       : (MODE == MODE_SKIP_END ? kNCh * 8 * 4
+                                          : (MODE == MODE_GATE ? 2 * kNCh * 4
+                                             : (MODE == MODE_STFT_MEL ? kBlockM * (kMelMax + 1) * 4 + 1024 * 16 : 0)));
     static constexpr int kBarOff = kExtraOff + kExtraBytes;
     static constexpr int kBarBytes = 256;     // full[4] empty[4] tfull[2] tempty[2] hfull hempty tmem_slot
     static constexpr int kTotal = 1024 + kBarOff + kBarBytes;
@@ -125,6 +133,10 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
         float* sb = reinterpret_cast<float*>(s_extra + kBlockM * kBlockN * 2);
         for (int i = threadIdx.x - 64; i < kNCh; i += 128) sb[i] = p.bias[i];
     }
+    if (MODE == MODE_STFT_MEL && warp >= 2) {
+        float4* tab = reinterpret_cast<float4*>(s_extra + kBlockM * (kMelMax + 1) * 4);
+        for (int i = threadIdx.x - 64; i < (p.n_total >> 1); i += 128) tab[i] = p.mel_table[i];
+    }
     if (MODE == MODE_GATE && warp >= 2) {      // sigmoid(b) = 0.5 tanh(b/2) + 0.5: sigmoid columns carry b/2
         for (int i = threadIdx.x - 64; i < 2 * kNCh; i += 128) s_wend[i] = p.bias[i] * ((i & 128) ? 0.5f : 1.f);
     }
@@ -162,7 +174,7 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                             }
                         } else if constexpr (MODE == MODE_RES) {
                             tma_load_3d(sa, &map_a0, &full_bar[s], kc * kBlockK, t0, b);
-                        } else if constexpr (MODE == MODE_PLAIN) {
+                        } else if constexpr (MODE == MODE_PLAIN || MODE == MODE_STFT_MEL) {
                             const int seg = kc / p.seg_chunks;
                             tma_load_3d(sa, ((p.seg_mask >> seg) & 1) ? &map_a1 : &map_a0, &full_bar[s],
                                         (kc - seg * p.seg_chunks) * kBlockK, t0, b);
@@ -306,6 +318,36 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                             *reinterpret_cast<uint4*>(rowp + ((((ch & 1) * 4 + i) ^ (row & 7)) << 4)) =
                                 make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
+                    }
+                } else if constexpr (MODE == MODE_STFT_MEL) {
+                    // TacotronSTFT.mel_spectrogram in one kernel (stft.py:85-97, layers.py:77-78, audio_processing.py:76):
+                    // Re/Im-paired basis rows -> |X| per bin -> scattered into this row's <= 80 mel accumulators in
+                    // shared memory (a bin feeds at most two adjacent filters) -> log(max(., clip)) after the last pass
+                    float* acc = reinterpret_cast<float*>(s_extra) + row * (kMelMax + 1);     // stride 81: conflict-free
+                    const float4* tab = reinterpret_cast<const float4*>(s_extra + kBlockM * (kMelMax + 1) * 4);
+                    if (pp == 0) {
+                        for (int m = 0; m <= kMelMax; ++m) acc[m] = 0.f;
+                    }
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t vr[32], vi[32];
+                        tmem_ld_32x32b_x32(taddr + ch * 32, vr);
+                        tmem_ld_32x32b_x32(taddr + 128 + ch * 32, vi);
+                        tmem_ld_wait();
+                        const int k0 = pass * 128 + ch * 32;
+#pragma unroll 8
+                        for (int j = 0; j < 32; ++j) {
+                            const float re = __uint_as_float(vr[j]), im = __uint_as_float(vi[j]);
+                            const float mag = sqrtf(re * re + im * im);
+                            const float4 e = tab[k0 + j];                                      // warp-uniform: broadcast
+                            const int m0 = static_cast<int>(e.x);
+                            acc[m0] = fmaf(e.y, mag, acc[m0]);
+                            acc[m0 + 1] = fmaf(e.z, mag, acc[m0 + 1]);
+                        }
+                    }
+                    if (pp == p.ppi - 1 && live) {
+                        float* out = static_cast<float*>(p.c_out) + (static_cast<size_t>(b) * p.n_mel) * p.T + t;
+                        for (int m = 0; m < p.n_mel; ++m) out[static_cast<size_t>(m) * p.T] = logf(fmaxf(acc[m], p.mel_clip));
                     }
                 } else if constexpr (MODE == MODE_PLAIN && DIR >= 2) {
                     // STFT with Re/Im-paired basis rows: columns 0..127 of the pass are Re of bins 128 pass .. +127,
@@ -615,6 +657,34 @@ int tc_stft_mag(const void* a_hi, const void* a_lo, const void* w3_paired, void*
     WGB_REQUIRE(cp > 0 && cp % 128 == 0, "cp (%d) must be a multiple of 128", cp);
     return gemm_split3(a_hi, a_lo, w3_paired, nullptr, mag_cl, batch, rows, 2 * cp, K, row_stride, batch_stride, 2, nullptr,
                        nullptr, 0.f, 0, stream);
+}
+
+// TacotronSTFT.mel_spectrogram as ONE kernel: the paired-basis STFT GEMM with the magnitude, the mel filterbank (as a
+// sparse per-bin table: every bin lies in at most two adjacent triangular filters) and log(clamp) in the epilogue.
+// out fp32 [B, n_mel, rows] (the reference's layout); mel_table [cp] float4 {first filter, w_first, w_next, 0}.
+int tc_stft_mel(const void* a_hi, const void* a_lo, const void* w3_paired, const void* mel_table, void* out, int batch,
+                int rows, int cp, int K, long long row_stride, long long batch_stride, int n_mel, float clip,
+                cudaStream_t stream) {
+    WGB_REQUIRE(a_hi && a_lo && w3_paired && mel_table && out, "null pointer");
+    WGB_REQUIRE(cp > 0 && cp % 128 == 0 && cp <= 1024, "cp (%d) must be a multiple of 128 and <= 1024", cp);
+    WGB_REQUIRE(n_mel >= 1 && n_mel <= kMelMax, "n_mel (%d) must be in 1..%d", n_mel, kMelMax);
+    WGB_REQUIRE(K > 0 && K % kBlockK == 0, "K must be a multiple of 64");
+    WGB_REQUIRE(row_stride % 8 == 0 && batch_stride % 8 == 0, "row/batch strides must be multiples of 8 elements (16 B)");
+    TcParams p{};
+    if (int e = fill_common(p, batch, rows)) return e;
+    const int N = 2 * cp;
+    p.n_pass = N / kBlockN; p.ppi = p.n_pass; p.n_chunks = 3 * K / kBlockK;       // one CTA runs all passes of a tile
+    p.c_out = out; p.n_total = N;
+    p.seg_chunks = K / kBlockK; p.seg_mask = 0b010;
+    p.mel_table = static_cast<const float4*>(mel_table); p.n_mel = n_mel; p.mel_clip = clip;
+    CUtensorMap mhi, mlo, mb;
+    const uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(rows), static_cast<uint64_t>(batch)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(row_stride) * 2, static_cast<uint64_t>(batch_stride) * 2};
+    const uint32_t box[3] = {kBlockK, kBlockM, 1};
+    if (int e = make_tmap_bf16(&mhi, a_hi, 3, dims, strides, box)) return e;
+    if (int e = make_tmap_bf16(&mlo, a_lo, 3, dims, strides, box)) return e;
+    if (int e = weight_map(&mb, w3_paired, N, 3 * K)) return e;
+    return launch<MODE_STFT_MEL, 0, 0>(mhi, mlo, mb, mhi, p, stream);
 }
 
 // Same GEMM with the Denoiser's spectral subtraction in the epilogue (denoiser.py:36-38 + the cos/sin recombination

@@ -20,6 +20,7 @@ class TacotronSTFT(torch.nn.Module):
         self.stft_fn = STFT(filter_length, hop_length, win_length)
         self.register_buffer("mel_basis", mel_filterbank(sampling_rate, filter_length, n_mel_channels, mel_fmin, mel_fmax))
         self._mel_pack = None
+        self.fused = True          # False: keep the mel matmul / log as separate kernels (A/B and validation)
 
     def spectral_normalize(self, magnitudes):
         return dynamic_range_compression(magnitudes)
@@ -41,6 +42,31 @@ class TacotronSTFT(torch.nn.Module):
             self._mel_pack = (key, w.to(device), k_used)
         return self._mel_pack[1], self._mel_pack[2]
 
+    def _mel_table(self, device, cp):
+        """Sparse form of mel_basis for the fused kernel: per bin {first filter index, weight in it, weight in the next
+        filter, 0}.  Triangular filters overlap pairwise, so a bin feeds at most two ADJACENT filters; returns None if
+        this basis does not have that structure (a hand-edited mel_basis) or has more than 80 filters."""
+        key = (str(device), cp, self.mel_basis.data_ptr(), self.mel_basis._version)
+        cached = getattr(self, "_mel_tab", None)
+        if cached is None or cached[0] != key:
+            basis = self.mel_basis.detach().float().cpu()
+            n_mel, n_bins = basis.shape
+            tab = torch.zeros((cp, 4), dtype=torch.float32)
+            ok = n_mel <= 80 and n_bins <= cp
+            for k in range(min(n_bins, cp)) if ok else ():
+                nz = torch.nonzero(basis[:, k]).flatten()
+                if nz.numel() == 0:
+                    continue
+                m0 = int(nz[0])
+                if nz.numel() > 2 or (nz.numel() == 2 and int(nz[1]) != m0 + 1):
+                    ok = False
+                    break
+                tab[k, 0], tab[k, 1] = float(m0), basis[m0, k]
+                if nz.numel() == 2:
+                    tab[k, 2] = basis[m0 + 1, k]
+            self._mel_tab = (key, tab.to(device) if ok else None)
+        return self._mel_tab[1]
+
     def mel_spectrogram(self, y: torch.Tensor) -> torch.Tensor:
         """y [B, T] in [-1, 1] (CUDA) -> log-mel [B, n_mel_channels, T // hop + 1]."""
         if not y.is_cuda:
@@ -50,8 +76,12 @@ class TacotronSTFT(torch.nn.Module):
         y = y.float().contiguous()
         b = y.shape[0]
         s = _lib.stream_ptr()
-        if self.stft_fn._use_tc():            # |X| straight from the STFT GEMM's epilogue
-            mag_cl, frames, cp = self.stft_fn._magnitude_cl(y)
+        if self.stft_fn._use_tc():
+            cp = self.stft_fn._packed(y.device)[3]
+            table = self._mel_table(y.device, cp) if self.fused else None
+            if table is not None:             # STFT GEMM with |X|, the mel filterbank and log-clamp in its epilogue
+                return self.stft_fn._mel_fused(y, table, self.n_mel_channels, 1e-5)
+            mag_cl, frames, cp = self.stft_fn._magnitude_cl(y)   # |X| straight from the STFT GEMM's epilogue
         else:
             spec, frames, cp = self.stft_fn._spectrum(y)
             mag_cl = torch.empty((b, frames, cp), device=y.device, dtype=torch.float32)

@@ -150,6 +150,18 @@ class STFT(torch.nn.Module):
                   self.hop_length, ld_pad, _lib.stream_ptr())
         return mag, frames, cp
 
+    def _mel_fused(self, y: torch.Tensor, mel_table: torch.Tensor, n_mel: int, clip: float) -> torch.Tensor:
+        """y [B,N] -> log-mel [B, n_mel, F] in one GEMM kernel (TacotronSTFT.mel_spectrogram, layers.py:63-79)."""
+        _lib.require_b200(y.device)
+        _, _, _, cp = self._packed(y.device)
+        b, n = y.shape
+        frames = n // self.hop_length + 1
+        hi, lo, ld_pad = self._padded_split(y)
+        out = torch.empty((b, n_mel, frames), device=y.device, dtype=torch.float32)
+        _lib.call("wgb_tc_stft_mel", hi, lo, self._paired_basis(y.device), mel_table, out, b, frames, cp,
+                  self.filter_length, self.hop_length, ld_pad, n_mel, float(clip), _lib.stream_ptr())
+        return out
+
     def _denoised(self, y: torch.Tensor, bias_spec: torch.Tensor, strength: float) -> torch.Tensor:
         """Denoiser.forward on the tensor-core path: STFT GEMM with the spectral subtraction in its epilogue (writes
         the inverse GEMM's bf16 hi / lo operands), inverse GEMM, overlap-add."""
