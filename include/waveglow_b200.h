@@ -159,6 +159,14 @@ WGB_API int wgb_tc_wn_skip16_end(const void* acts_all, int n_layers, const void*
 WGB_API int wgb_tc_gemm(const void* a, const void* w, const float* bias, void* c, int out_bf16, int batch, int T,
                         int N, int K, void* stream);
 
+/* conv1d (stride 1, zero "same" padding) as an implicit GEMM on the same pipeline:
+ *   c[b,t,n] = act(bias[n] + sum_tap sum_ch w[n][tap*C + ch] * a[b, t + (tap - (taps-1)/2)*dilation, ch])
+ * a bf16 channels-last [B,T,C] (C % 64 == 0), w bf16 [N][taps*C] (N % 256 == 0), c fp32 or bf16 [B,T,N]; act 0 none,
+ * 1 tanh, 2 relu.  Every tap is a K segment whose TMA box is shifted in time (out-of-range rows zero-filled).  Serves
+ * the Tacotron-2 Postnet (tacotron/modules.py:94-137) with BatchNorm folded into w / bias. */
+WGB_API int wgb_tc_conv1d(const void* a, const void* w, const float* bias, void* c, int out_bf16, int batch, int T, int N,
+                          int C, int taps, int dilation, int act, void* stream);
+
 /* Split-bf16 GEMM (fp32-grade accuracy on tcgen05): C[b,r,n] = sum_k A[b,r,k] W[n,k] with A = a_hi + a_lo
  * (bf16 parts, row r of batch b at element offset b*batch_stride + r*row_stride, rows may OVERLAP:
  * row_stride = hop < K reads STFT frames straight from the padded signal) and w3 = [W_hi | W_hi | W_lo]
@@ -202,6 +210,8 @@ WGB_API int wgb_gate_f32(const float* u, float* acts, long long rows, int n_ch, 
  * input_a, input_b fp32 [B, 2*n_ch, T] channels-first -> acts fp32 [B, n_ch, T]. */
 WGB_API int wgb_fused_add_tanh_sigmoid_multiply(const float* input_a, const float* input_b, float* acts, int batch,
                                                 int n_ch, int T, void* stream);
+/* in-place tanh (act 1) / relu (act 2), accurate libm versions: FP32 validation path of the Postnet. */
+WGB_API int wgb_act_f32(float* x, long long n, int act, void* stream);
 /* has_res: h += rs[:, :C]; skip (+)= rs[:, C:]   else: skip (+)= rs   (glow.py:165-174). */
 WGB_API int wgb_res_skip_f32(const float* rs, float* h, float* skip, long long rows, int n_ch, int has_res,
                      int first, void* stream);

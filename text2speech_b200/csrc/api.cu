@@ -13,6 +13,7 @@ int tc_wn_skip_end(const void*, int, const void*, const float*, const float*, fl
 int tc_gemm_plain(const void*, const void*, const float*, void*, int, int, int, int, int, cudaStream_t);
 int tc_gemm_split3(const void*, const void*, const void*, const float*, void*, int, int, int, int, long long, long long,
                    cudaStream_t);
+int tc_conv1d_taps(const void*, const void*, const float*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
 int tc_stft_mag(const void*, const void*, const void*, void*, int, int, int, int, long long, long long, cudaStream_t);
 int tc_stft_mel(const void*, const void*, const void*, const void*, void*, int, int, int, int, long long, long long, int, float,
                 cudaStream_t);
@@ -39,6 +40,7 @@ int tc_wn_skip16_end(const void*, int, const void*, const float*, float*, const 
 int sgemm_nt(const float*, const float*, const float*, void*, int, int, int, int, int, long long, long long, long long,
              long long, long long, int, int, cudaStream_t);
 int gate_f32(const float*, float*, long long, int, cudaStream_t);
+int act_f32(float*, long long, int, cudaStream_t);
 int fused_add_tanh_sigmoid_multiply(const float*, const float*, float*, int, int, int, cudaStream_t);
 int res_skip_f32(const float*, float*, float*, long long, int, int, int, cudaStream_t);
 // flow.cu
@@ -171,6 +173,10 @@ WGB_API int wgb_tc_stft_mag(const void* a_hi, const void* a_lo, const void* w3_p
                             int cp, int K, long long row_stride, long long batch_stride, void* stream) {
     return tc_stft_mag(a_hi, a_lo, w3_paired, mag_cl, batch, rows, cp, K, row_stride, batch_stride, S(stream));
 }
+WGB_API int wgb_tc_conv1d(const void* a, const void* w, const float* bias, void* c, int out_bf16, int batch, int T, int N,
+                          int C, int taps, int dilation, int act, void* stream) {
+    return tc_conv1d_taps(a, w, bias, c, out_bf16, batch, T, N, C, taps, dilation, act, S(stream));
+}
 WGB_API int wgb_tc_stft_mel(const void* a_hi, const void* a_lo, const void* w3_paired, const void* mel_table, float* out,
                             int batch, int rows, int cp, int K, long long row_stride, long long batch_stride, int n_mel,
                             float clip, void* stream) {
@@ -197,6 +203,7 @@ WGB_API int wgb_fused_add_tanh_sigmoid_multiply(const float* input_a, const floa
                                                 int T, void* stream) {
     return fused_add_tanh_sigmoid_multiply(input_a, input_b, acts, batch, n_ch, T, S(stream));
 }
+WGB_API int wgb_act_f32(float* x, long long n, int act, void* stream) { return act_f32(x, n, act, S(stream)); }
 WGB_API int wgb_res_skip_f32(const float* rs, float* h, float* skip, long long rows, int n_ch, int has_res, int first,
                      void* stream) {
     return res_skip_f32(rs, h, skip, rows, n_ch, has_res, first, S(stream));

@@ -157,6 +157,21 @@ int fused_add_tanh_sigmoid_multiply(const float* a, const float* b, float* out, 
     return WGB_OK;
 }
 
+// in-place tanh (act 1) / relu (act 2) with the accurate libm functions: FP32 validation path of the Postnet
+__global__ void act_f32_kernel(float* __restrict__ x, long long n, int act) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        x[i] = act == 1 ? tanhf(x[i]) : fmaxf(x[i], 0.f);
+}
+
+int act_f32(float* x, long long n, int act, cudaStream_t stream) {
+    WGB_REQUIRE(x && n > 0 && (act == 1 || act == 2), "bad arguments");
+    const int grid = static_cast<int>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
+    act_f32_kernel<<<grid, 256, 0, stream>>>(x, n, act);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
 // has_res: h += rs[:, :C], skip (+)= rs[:, C:]; else skip (+)= rs (last layer)   (glow.py:165-174)
 __global__ void res_skip_f32_kernel(const float* __restrict__ rs, float* __restrict__ h, float* __restrict__ skip,
                                     long long rows, int n_ch, int has_res, int first) {

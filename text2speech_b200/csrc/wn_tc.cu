@@ -64,6 +64,9 @@ struct TcParams {
     int n_total;                  // PLAIN  N (multiple of 256)
     int seg_chunks, seg_mask;     // PLAIN  K is split in segments of seg_chunks chunks; bit s of seg_mask selects
                                   //        map_a1 (else map_a0) for segment s (split-bf16 hi/lo operands)
+    int seg_shift0, seg_dshift;   // PLAIN  segment s reads A rows t + seg_shift0 + s*seg_dshift (conv taps; rows outside
+                                  //        [0,T) are zero-filled by TMA = zero padding); 0, 0 for a plain GEMM
+    int act;                      // PLAIN  DIR 0/1 epilogue: 0 none, 1 tanh, 2 relu
 };
 
 // Shared-memory carve-up (offsets from a 1024 B aligned base): [TMA ring][mode extra][barriers].
@@ -177,7 +180,7 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                         } else if constexpr (MODE == MODE_PLAIN || MODE == MODE_STFT_MEL) {
                             const int seg = kc / p.seg_chunks;
                             tma_load_3d(sa, ((p.seg_mask >> seg) & 1) ? &map_a1 : &map_a0, &full_bar[s],
-                                        (kc - seg * p.seg_chunks) * kBlockK, t0, b);
+                                        (kc - seg * p.seg_chunks) * kBlockK, t0 + p.seg_shift0 + seg * p.seg_dshift, b);
                         } else {
                             tma_load_3d(sa, &map_a0, &full_bar[s], (kc & 7) * kBlockK, t0, (kc >> 3) * p.batch + b);
                         }
@@ -421,8 +424,11 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                         tmem_ld_wait();
                         float f[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
+                        for (int j = 0; j < 32; ++j) {
                             f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + pass * kBlockN + ch * 32 + j) : 0.f);
+                            if (p.act == 1) f[j] = tanhf(f[j]);
+                            else if (p.act == 2) f[j] = fmaxf(f[j], 0.f);
+                        }
                         if (live) {
                             if constexpr (DIR == 0) {
                                 float4* d4 = reinterpret_cast<float4*>(static_cast<float*>(p.c_out) + off + ch * 32);
@@ -611,6 +617,29 @@ int tc_gemm_plain(const void* a, const void* w, const float* bias, void* c, int 
     CUtensorMap ma0, mb;
     if (int e = act_map(&ma0, a, K, T, batch)) return e;
     if (int e = weight_map(&mb, w, N, K)) return e;
+    return out_bf16 ? launch<MODE_PLAIN, 0, 1>(ma0, ma0, mb, ma0, p, stream) : launch<MODE_PLAIN, 0, 0>(ma0, ma0, mb, ma0, p, stream);
+}
+
+// conv1d (stride 1, "same" zero padding) as an implicit GEMM: out[b,t,n] = act(bias[n] + sum_tap sum_c W[n][tap*C+c]
+// A[b, t + (tap - (taps-1)/2) * dilation, c]).  A bf16 channels-last [B,T,C] (C % 64 == 0), W bf16 [N][taps*C]
+// (N % 256 == 0), out fp32 or bf16 [B,T,N].  Every tap is a K segment whose TMA box is shifted in time; rows outside
+// the sequence are zero-filled by TMA.  Serves the Tacotron-2 Postnet (tacotron/modules.py:94-137: five k = 5 convs
+// with BatchNorm folded into W / bias, tanh between them).
+int tc_conv1d_taps(const void* a, const void* w, const float* bias, void* c, int out_bf16, int batch, int T, int N, int C,
+                   int taps, int dilation, int act, cudaStream_t stream) {
+    WGB_REQUIRE(a && w && c, "null pointer");
+    WGB_REQUIRE(N > 0 && N % kBlockN == 0 && C > 0 && C % kBlockK == 0, "N must be a multiple of 256 and C of 64 (N=%d C=%d)", N, C);
+    WGB_REQUIRE(taps >= 1 && taps % 2 == 1 && taps <= 31 && dilation >= 1, "taps must be odd (got %d), dilation >= 1", taps);
+    WGB_REQUIRE(act >= 0 && act <= 2, "act must be 0 (none), 1 (tanh) or 2 (relu)");
+    TcParams p{};
+    if (int e = fill_common(p, batch, T)) return e;
+    p.n_pass = N / kBlockN; p.ppi = 1; p.n_chunks = taps * C / kBlockK;
+    p.bias = bias; p.c_out = c; p.n_total = N;
+    p.seg_chunks = C / kBlockK; p.seg_mask = 0;
+    p.seg_shift0 = -((taps - 1) / 2) * dilation; p.seg_dshift = dilation; p.act = act;
+    CUtensorMap ma0, mb;
+    if (int e = act_map(&ma0, a, C, T, batch)) return e;
+    if (int e = weight_map(&mb, w, N, taps * C)) return e;
     return out_bf16 ? launch<MODE_PLAIN, 0, 1>(ma0, ma0, mb, ma0, p, stream) : launch<MODE_PLAIN, 0, 0>(ma0, ma0, mb, ma0, p, stream);
 }
 

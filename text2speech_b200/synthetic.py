@@ -128,3 +128,31 @@ def synthetic_waveforms(batch: int, samples: int, sr: int = 22050, seed: int = 5
     tone = 0.5 * torch.sin(2 * math.pi * f0 * n / sr)
     noise = 0.05 * torch.randn((batch, samples), generator=g, dtype=torch.float64)
     return torch.clamp(tone + noise, -1.0, 1.0).float()
+
+
+DEFAULT_POSTNET_HPARAMS = {          # == hparams.py:18,146-148 of the reference
+    "n_mel_channels": 80, "postnet_embedding_dim": 512, "postnet_kernel_size": 5, "postnet_n_convolutions": 5,
+}
+
+
+def synthetic_postnet_state_dict(hparams: Optional[Dict] = None, seed: int = 77) -> "OrderedDict[str, torch.Tensor]":
+    """Random Postnet ``state_dict`` in the reference layout (tacotron/modules.py:94-130): xavier-uniform conv weights
+    (gain 5/3 before a tanh, 1 for the last layer), and NON-trivial BatchNorm affine parameters / running statistics so
+    that folding the BatchNorm is exercised."""
+    hp = hparams or DEFAULT_POSTNET_HPARAMS
+    n_mel, dim, k, n = hp["n_mel_channels"], hp["postnet_embedding_dim"], hp["postnet_kernel_size"], hp["postnet_n_convolutions"]
+    chans = [n_mel] + [dim] * (n - 1) + [n_mel]
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for i in range(n):
+        c_in, c_out = chans[i], chans[i + 1]
+        gain = 5.0 / 3.0 if i < n - 1 else 1.0
+        bound = gain * math.sqrt(6.0 / (c_in * k + c_out * k))
+        p = f"convolutions.{i}."
+        sd[p + "0.conv.weight"] = _uniform((c_out, c_in, k), bound, seed, p + "w")
+        sd[p + "0.conv.bias"] = _uniform((c_out,), 1.0 / math.sqrt(c_in * k), seed, p + "b")
+        sd[p + "1.weight"] = 0.5 + torch.rand((c_out,), generator=_gen(seed, p + "g"))
+        sd[p + "1.bias"] = 0.1 * torch.randn((c_out,), generator=_gen(seed, p + "beta"))
+        sd[p + "1.running_mean"] = 0.1 * torch.randn((c_out,), generator=_gen(seed, p + "mean"))
+        sd[p + "1.running_var"] = 0.5 + torch.rand((c_out,), generator=_gen(seed, p + "var"))
+        sd[p + "1.num_batches_tracked"] = torch.tensor(1, dtype=torch.long)
+    return sd
