@@ -37,7 +37,8 @@ class Denoiser(torch.nn.Module):
         """audio [B, N] -> denoised [B, 1, N'] with N' = hop * (N // hop)  (denoiser.py:35-40)."""
         audio = audio.to(self.bias_spec.device).float().contiguous()
         bias = self.bias_spec.reshape(-1).contiguous()
-        if self.stft._use_tc():               # subtraction inside the STFT GEMM's epilogue
-            return self.stft._denoised(audio, bias, strength)
-        spec, frames, cp = self.stft._spectrum(audio)
-        return self.stft._synthesize(spec, frames, cp, denoise=(bias, strength))
+        with torch.cuda.device(audio.device):
+            if self.stft._use_tc():           # subtraction inside the STFT GEMM's epilogue
+                return self.stft._denoised(audio, bias, strength)
+            spec, frames, cp = self.stft._spectrum(audio)
+            return self.stft._synthesize(spec, frames, cp, denoise=(bias, strength))

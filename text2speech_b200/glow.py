@@ -203,21 +203,21 @@ class WaveGlow(torch.nn.Module):
         spect, audio = forward_input
         if not spect.is_cuda:
             raise RuntimeError("WaveGlow.forward needs CUDA tensors on a B200; there is no CPU fallback")
-        pk = self._packed(spect.device)
-        with torch.no_grad():
+        with torch.cuda.device(spect.device), torch.no_grad():      # kernels launch on the tensors' device / its current stream
+            pk = self._packed(spect.device)
             return engine.forward(pk, spect.float().contiguous(), audio.float().contiguous())
 
     def infer(self, spect: torch.Tensor, sigma: float = 1.0, z: Optional[torch.Tensor] = None) -> torch.Tensor:
         if not spect.is_cuda:
             raise RuntimeError("WaveGlow.infer needs CUDA tensors on a B200; there is no CPU fallback")
-        pk = self._packed(spect.device)
         b, _, f = spect.shape
         t = f * self.upsample.stride[0] // self.n_group
         if z is None:
             z = torch.randn((b, self.n_group, t), device=spect.device, dtype=torch.float32)
         if tuple(z.shape) != (b, self.n_group, t):
             raise ValueError(f"z must be [{b}, {self.n_group}, {t}], got {tuple(z.shape)}")
-        with torch.no_grad():
+        with torch.cuda.device(spect.device), torch.no_grad():      # kernels launch on the tensors' device / its current stream
+            pk = self._packed(spect.device)
             audio = engine.infer(pk, spect.float().contiguous(), z.to(spect.device).float().contiguous(), sigma)
         return audio.to(spect.dtype) if spect.dtype in (torch.float16, torch.bfloat16) else audio
 

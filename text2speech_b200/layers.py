@@ -73,6 +73,10 @@ class TacotronSTFT(torch.nn.Module):
             raise RuntimeError("TacotronSTFT.mel_spectrogram needs a CUDA tensor on a B200; there is no CPU fallback")
         assert torch.min(y.data) >= -1                                         # layers.py:72-73
         assert torch.max(y.data) <= 1
+        with torch.cuda.device(y.device):
+            return self._mel_spectrogram(y)
+
+    def _mel_spectrogram(self, y: torch.Tensor) -> torch.Tensor:
         y = y.float().contiguous()
         b = y.shape[0]
         s = _lib.stream_ptr()

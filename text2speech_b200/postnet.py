@@ -95,6 +95,10 @@ class Postnet(torch.nn.Module):
         if not x.is_cuda:
             raise RuntimeError("Postnet needs a CUDA tensor on a B200; there is no CPU fallback")
         _lib.require_b200(x.device)
+        with torch.cuda.device(x.device):
+            return self._forward(x)
+
+    def _forward(self, x: torch.Tensor) -> torch.Tensor:
         layers = self._packed(x.device)
         b, c, f = x.shape
         s = _lib.stream_ptr()

@@ -216,23 +216,25 @@ class STFT(torch.nn.Module):
             raise RuntimeError("STFT.transform needs a CUDA tensor on a B200; there is no CPU fallback")
         self.num_samples = input_data.size(1)
         y = input_data.float().contiguous()
-        spec, frames, cp = self._spectrum(y)
-        b = y.shape[0]
-        mag = torch.empty((b, self.cutoff, frames), device=y.device, dtype=torch.float32)
-        phase = torch.empty_like(mag)
-        _lib.call("wgb_stft_polar", spec, mag, phase, None, b, frames, self.cutoff, cp, _lib.stream_ptr())
+        with torch.cuda.device(y.device):
+            spec, frames, cp = self._spectrum(y)
+            b = y.shape[0]
+            mag = torch.empty((b, self.cutoff, frames), device=y.device, dtype=torch.float32)
+            phase = torch.empty_like(mag)
+            _lib.call("wgb_stft_polar", spec, mag, phase, None, b, frames, self.cutoff, cp, _lib.stream_ptr())
         return mag, phase
 
     def inverse(self, magnitude: torch.Tensor, phase: torch.Tensor):
         if not magnitude.is_cuda:
             raise RuntimeError("STFT.inverse needs CUDA tensors on a B200; there is no CPU fallback")
         _lib.require_b200(magnitude.device)
-        _, _, _, cp = self._packed(magnitude.device)
-        b, cutoff, frames = magnitude.shape
-        spec = torch.empty((b, frames, 2 * cp), device=magnitude.device, dtype=torch.float32)
-        _lib.call("wgb_stft_recombine", magnitude.float().contiguous(), phase.float().contiguous(), spec, b, frames,
-                  cutoff, cp, _lib.stream_ptr())
-        return self._synthesize(spec, frames, cp)
+        with torch.cuda.device(magnitude.device):
+            _, _, _, cp = self._packed(magnitude.device)
+            b, cutoff, frames = magnitude.shape
+            spec = torch.empty((b, frames, 2 * cp), device=magnitude.device, dtype=torch.float32)
+            _lib.call("wgb_stft_recombine", magnitude.float().contiguous(), phase.float().contiguous(), spec, b, frames,
+                      cutoff, cp, _lib.stream_ptr())
+            return self._synthesize(spec, frames, cp)
 
     def forward(self, input_data):
         self.magnitude, self.phase = self.transform(input_data)
