@@ -54,11 +54,12 @@ def griffin_lim(magnitudes, stft_fn, n_iters=30, angles=None):
         angles = torch.from_numpy(angles)
     angles = angles.to(magnitudes.device).float().contiguous()
     b, cutoff, _ = magnitudes.shape
-    signal = stft_fn.inverse(magnitudes, angles).squeeze(1)
-    for _ in range(n_iters):
-        spec, frames, cp = stft_fn._spectrum(signal.contiguous())
-        _lib.call("wgb_spec_set_magnitude", spec, magnitudes, b, frames, cutoff, cp, _lib.stream_ptr())
-        signal = stft_fn._synthesize(spec, frames, cp).squeeze(1)
+    with torch.cuda.device(magnitudes.device):
+        signal = stft_fn.inverse(magnitudes, angles).squeeze(1)
+        for _ in range(n_iters):
+            spec, frames, cp = stft_fn._spectrum(signal.contiguous())
+            _lib.call("wgb_spec_set_magnitude", spec, magnitudes, b, frames, cutoff, cp, _lib.stream_ptr())
+            signal = stft_fn._synthesize(spec, frames, cp).squeeze(1)
     return signal
 
 

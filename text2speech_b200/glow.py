@@ -40,8 +40,9 @@ def fused_add_tanh_sigmoid_multiply(input_a: torch.Tensor, input_b: torch.Tensor
     if two_c != 2 * c or input_b.shape != input_a.shape:
         raise ValueError(f"expected two [B, {2 * c}, T] tensors, got {tuple(input_a.shape)} and {tuple(input_b.shape)}")
     out = torch.empty((b, c, t), device=input_a.device, dtype=torch.float32)
-    _lib.call("wgb_fused_add_tanh_sigmoid_multiply", input_a.float().contiguous(), input_b.float().contiguous(), out,
-              b, c, t, _lib.stream_ptr())
+    with torch.cuda.device(input_a.device):
+        _lib.call("wgb_fused_add_tanh_sigmoid_multiply", input_a.float().contiguous(), input_b.float().contiguous(), out,
+                  b, c, t, _lib.stream_ptr())
     return out.to(input_a.dtype)
 
 
@@ -79,7 +80,8 @@ class Invertible1x1Conv(torch.nn.Module):
         fwd, inv, logdet = pack_mix(self.conv.weight.detach().float().cpu())
         x = torch.zeros((b, t, 8), device=z.device, dtype=torch.float32)
         x[:, :, 8 - c:] = z.float().permute(0, 2, 1)
-        _lib.call("wgb_flow_mix", x, (inv if reverse else fwd).to(z.device), b * t, c, _lib.stream_ptr())
+        with torch.cuda.device(z.device):
+            _lib.call("wgb_flow_mix", x, (inv if reverse else fwd).to(z.device), b * t, c, _lib.stream_ptr())
         out = x[:, :, 8 - c:].permute(0, 2, 1).contiguous().to(z.dtype)
         if reverse:
             return out
@@ -120,8 +122,9 @@ class WN(torch.nn.Module):
         if self._owner is None:
             raise RuntimeError("WN.forward needs its owning WaveGlow (kernels are packed per model)")
         model, k = self._owner
-        pk = model._packed(audio.device)
-        return engine.wn_standalone(pk, k, audio.float().contiguous(), spect.float().contiguous())
+        with torch.cuda.device(audio.device), torch.no_grad():
+            pk = model._packed(audio.device)
+            return engine.wn_standalone(pk, k, audio.float().contiguous(), spect.float().contiguous())
 
 
 class WaveGlow(torch.nn.Module):

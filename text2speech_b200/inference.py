@@ -72,7 +72,8 @@ def audio_to_int16(audio: torch.Tensor, scale: float = MAX_WAV_VALUE) -> torch.T
     """trunc(audio * scale) as int16 on the GPU (inference.py:58-62), saturating."""
     flat = audio.float().contiguous()
     out = torch.empty(flat.shape, device=flat.device, dtype=torch.int16)
-    _lib.call("wgb_audio_to_int16", flat, out, flat.numel(), float(scale), _lib.stream_ptr())
+    with torch.cuda.device(flat.device):
+        _lib.call("wgb_audio_to_int16", flat, out, flat.numel(), float(scale), _lib.stream_ptr())
     return out
 
 
