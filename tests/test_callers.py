@@ -234,3 +234,28 @@ def test_gpu_mel2samp_batch(tmp_path):
     assert float((mel.cpu() - want).abs().max()) < 2e-3
     batch = ds.mel_batch(torch.stack([audio, audio]) * 32768.0)
     assert torch.allclose(batch[0], mel, atol=1e-5) and torch.equal(batch[0], batch[1])
+
+
+@pytest.mark.gpu
+def test_gpu_mel2samp_cli_writes_reference_format(tmp_path):
+    """python -m text2speech_b200.mel2samp (mel2samp.py:110-142): wav list -> <name>.pt mel files, batched by length."""
+    import json
+    from scipy.io.wavfile import write
+    from text2speech_b200 import mel2samp
+    y = syn.synthetic_waveforms(3, 9000, sr=22050, seed=12)
+    names = []
+    for i, n in enumerate((9000, 7000, 9000)):
+        write(tmp_path / f"a{i}.wav", 22050, (y[i, :n] * 32767).numpy().astype(np.int16))
+        names.append(str(tmp_path / f"a{i}.wav"))
+    (tmp_path / "files.txt").write_text("\n".join(names) + "\n")
+    cfg = {"data_config": dict(training_files=str(tmp_path / "files.txt"), **DC)}
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    written = mel2samp.main(str(tmp_path / "files.txt"), str(tmp_path / "config.json"), str(tmp_path / "mels"), batch=8)
+    assert sorted(os.path.basename(p) for p in written) == ["a0.wav.pt", "a1.wav.pt", "a2.wav.pt"]
+    fwd, _ = oracle.stft_bases(1024, 256, 1024)
+    mb = torch.from_numpy(oracle.mel_filterbank(22050, 1024, 80, 0.0, 8000.0)).float()
+    for i, n in enumerate((9000, 7000, 9000)):
+        mel = torch.load(tmp_path / "mels" / f"a{i}.wav.pt")
+        audio = torch.from_numpy((y[i, :n] * 32767).numpy().astype(np.int16)).float() / 32768.0
+        want = oracle.mel_spectrogram(audio[None], fwd, mb, 256)[0]
+        assert mel.shape == (80, n // 256 + 1) and float((mel - want).abs().max()) < 2e-3

@@ -72,3 +72,50 @@ class Mel2Samp(torch.utils.data.Dataset):
 
     def __len__(self):
         return len(self.audio_files)
+
+
+# ===================================================================
+# Takes a list of clean audio files and writes their mel spectrograms (mel2samp.py:110-142)
+#   python -m text2speech_b200.mel2samp -f files.txt -c config.json -o mels/ [--batch 32]
+# Same outputs as the reference (<output_dir>/<wav name>.pt holding a [80, frames] float tensor); files of equal
+# length are batched through one mel_spectrogram call.
+# ===================================================================
+def main(filelist_path, config, output_dir, batch=32):
+    import json
+    import os
+    with open(config) as f:
+        data_config = json.loads(f.read())["data_config"]
+    mel2samp = Mel2Samp(**data_config)
+    filepaths = files_to_list(filelist_path)
+    if not os.path.isdir(output_dir):
+        os.makedirs(output_dir)
+        os.chmod(output_dir, 0o775)
+    audios = [load_wav_to_torch(p)[0] for p in filepaths]
+    order = sorted(range(len(audios)), key=lambda i: audios[i].shape[0])
+    written = []
+    pos = 0
+    while pos < len(order):
+        group = [order[pos]]
+        while (len(group) < max(1, batch) and pos + len(group) < len(order)
+               and audios[order[pos + len(group)]].shape[0] == audios[group[0]].shape[0]):
+            group.append(order[pos + len(group)])
+        pos += len(group)
+        mels = mel2samp.mel_batch(torch.stack([audios[i] for i in group])).cpu()
+        for row, i in enumerate(group):
+            new_filepath = output_dir + "/" + os.path.basename(filepaths[i]) + ".pt"
+            torch.save(mels[row].clone(), new_filepath)
+            written.append(new_filepath)
+    for p in sorted(written, key=written.index):
+        print(p)
+    return written
+
+
+if __name__ == "__main__":
+    import argparse
+    parser = argparse.ArgumentParser()
+    parser.add_argument("-f", "--filelist_path", required=True)
+    parser.add_argument("-c", "--config", type=str, help="JSON file for configuration")
+    parser.add_argument("-o", "--output_dir", type=str, help="Output directory")
+    parser.add_argument("--batch", type=int, default=32, help="equal-length files per mel_spectrogram call")
+    args = parser.parse_args()
+    main(args.filelist_path, args.config, args.output_dir, args.batch)
