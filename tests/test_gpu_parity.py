@@ -497,6 +497,48 @@ def test_graphed_infer_matches_eager(models):
         assert torch.equal(got, want)
 
 
+@pytest.mark.parametrize("B,F", [(1, 7), (3, 13), (2, 64), (5, 31), (1, 129), (4, 128)])
+def test_infer_shape_sweep_all_paths_agree(models, B, F):
+    """Prime / power-of-two / tile-boundary lengths and odd batches: the FP32 validation path against the CPU oracle
+    (small shapes) and every BF16 path against the FP32 path."""
+    m = models["stress"]
+    mel, z = syn.synthetic_mel(B, F, seed=900 + F), syn.synthetic_z(B, F, seed=901 + F)
+    m.mode = "fp32"
+    ref = m.infer(mel.to(DEV), sigma=util.SIGMA, z=z.to(DEV)).cpu()
+    assert bool(torch.isfinite(ref).all())
+    if B * F <= 64:
+        with torch.no_grad():
+            want = oracle.waveglow_infer(util.state_dict("stress"), mel, z, util.SIGMA)
+        assert util.rel_l2(ref, want) <= 3e-5
+    m.mode = "bf16"
+    try:
+        for path in ("cond", "mel", "auto"):
+            m.cond_path = path
+            got = m.infer(mel.to(DEV), sigma=util.SIGMA, z=z.to(DEV)).cpu()
+            assert util.snr_db(got, ref) >= util.MIN_SNR_DB, (path, B, F)
+    finally:
+        m.cond_path = "auto"
+
+
+@pytest.mark.parametrize("n", [513, 1000, 4096 + 17, 22050])
+def test_stft_mel_denoiser_length_sweep(models, lib, n):
+    """Lengths that are not multiples of the hop: tensor-core STFT paths against the FP32 CUDA-core paths."""
+    import text2speech_b200 as t2s
+    y = syn.synthetic_waveforms(3, n, sr=22050, seed=n).to(DEV)
+    taco = t2s.TacotronSTFT(1024, 256, 1024, 80, 22050, 0.0, 8000.0).to(DEV)
+    a = taco.mel_spectrogram(y)
+    taco.stft_fn.precision = "fp32"
+    b = taco.mel_spectrogram(y)
+    assert a.shape == b.shape == (3, 80, n // 256 + 1) and float((a - b).abs().max()) <= 1e-3
+    m = models["bench"]
+    m.mode = "bf16"
+    den = t2s.Denoiser(m)
+    d_tc = den(y, 0.05)
+    den.stft.precision = "fp32"
+    d_32 = den(y, 0.05)
+    assert d_tc.shape == d_32.shape == (3, 1, 256 * (n // 256)) and util.rel_l2(d_tc.cpu(), d_32.cpu()) <= 1e-4
+
+
 def test_first_layer_fold_agrees(models, golden, monkeypatch):
     """Composed path with and without WN.start folded into in_layers[0]."""
     from text2speech_b200 import engine
