@@ -66,3 +66,11 @@ def test_reference_arm_runs_on_rank0_only():
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                         env=dict(env, RANK="1", LOCAL_RANK="1"), capture_output=True, text=True, timeout=120)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_multi_gpu_vocoder_refuses_cpu_only_hosts():
+    from text2speech_b200.sharding import MultiGpuVocoder
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        MultiGpuVocoder(torch.nn.Identity())

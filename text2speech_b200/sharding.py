@@ -47,3 +47,55 @@ def gather_utterances(local: torch.Tensor, n_items: int, dst: int = 0) -> Option
         lo, hi = shard_bounds(n_items, r, world)
         parts.append(bucket[r][: hi - lo])
     return torch.cat(parts, dim=0)
+
+
+class MultiGpuVocoder:
+    """Single-process form of the utterance sharding: one WaveGlow replica per visible GPU, one host thread per replica.
+
+    ``bench.py`` / torchrun use one PROCESS per GPU; this class is the convenience for callers that want one Python
+    process (a server, a notebook): ``infer(mel [B,80,F], sigma, z)`` splits the batch with ``shard_bounds``, runs the
+    shards concurrently (the C ABI is safe to call from different host threads on different devices) and concatenates
+    the audio on the host.  No inter-GPU traffic: utterances are independent.
+    """
+
+    def __init__(self, model, devices=None):
+        import copy
+        if devices is None:
+            devices = [torch.device("cuda", i) for i in range(torch.cuda.device_count())]
+        if not devices:
+            raise RuntimeError("MultiGpuVocoder needs at least one CUDA device; there is no CPU fallback")
+        self.devices = [torch.device(d) for d in devices]
+        self.replicas = []
+        for i, d in enumerate(self.devices):
+            replica = model if i == 0 else copy.deepcopy(model)
+            self.replicas.append(replica.to(d).eval())
+
+    def infer(self, spect: torch.Tensor, sigma: float = 1.0, z: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """spect [B, n_mel, F] (host or any device) -> audio [B, 256 F] on the host."""
+        import threading
+        n = spect.shape[0]
+        world = len(self.devices)
+        out = [None] * world
+        errors = []
+
+        def work(r):
+            try:
+                lo, hi = shard_bounds(n, r, world)
+                if hi == lo:
+                    return
+                d = self.devices[r]
+                with torch.cuda.device(d), torch.no_grad():
+                    zz = None if z is None else z[lo:hi].to(d, non_blocking=True)
+                    audio = self.replicas[r].infer(spect[lo:hi].to(d, non_blocking=True), sigma=sigma, z=zz)
+                    out[r] = audio.cpu()
+            except Exception as e:      # noqa: BLE001  (re-raised on the caller's thread)
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return torch.cat([o for o in out if o is not None], dim=0)
