@@ -71,10 +71,57 @@ __global__ void reflect_pad_split_kernel(const float* __restrict__ y, __nv_bfloa
     }
 }
 
+// 8 outputs per thread: two float4 loads in the interior (16 B aligned when N % 4 == 0 and half % 8 == 0), scalar
+// reflected reads at the two edges, one 16 B store per output array
+__global__ void reflect_pad_split8_kernel(const float* __restrict__ y, __nv_bfloat16* __restrict__ hi,
+                                          __nv_bfloat16* __restrict__ lo, int N, int half, long long ld_pad,
+                                          long long total8) {
+    const int padded = N + 2 * half;
+    const long long per_row = ld_pad >> 3;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / per_row;
+        const int p0 = static_cast<int>(i - b * per_row) << 3;
+        const float* row = y + b * N;
+        float v[8];
+        const int s0 = p0 - half;
+        if (s0 >= 0 && s0 + 7 < N) {
+            const float4 a = *reinterpret_cast<const float4*>(row + s0), c = *reinterpret_cast<const float4*>(row + s0 + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int p = p0 + j;
+                int sidx = p - half;
+                if (sidx < 0) sidx = -sidx;
+                if (sidx >= N) sidx = 2 * (N - 1) - sidx;
+                v[j] = p < padded ? row[sidx] : 0.f;
+            }
+        }
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - __low2float(hh), v[2 * j + 1] - __high2float(hh));
+            h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        *reinterpret_cast<uint4*>(hi + b * ld_pad + p0) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(lo + b * ld_pad + p0) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
 int stft_reflect_pad_split(const float* y, void* hi, void* lo, int batch, int N, int half, long long ld_pad,
                            cudaStream_t stream) {
     WGB_REQUIRE(y && hi && lo && batch > 0 && N > half, "reflect padding needs N > filter_length/2 (N=%d)", N);
     WGB_REQUIRE(ld_pad >= N + 2 * half && ld_pad % 8 == 0, "bad padded stride");
+    if (N % 4 == 0 && half % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+        const long long total8 = static_cast<long long>(batch) * (ld_pad >> 3);
+        reflect_pad_split8_kernel<<<grid_for(total8, 256), 256, 0, stream>>>(
+            y, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), N, half, ld_pad, total8);
+        WGB_LAUNCH_CHECK();
+        return WGB_OK;
+    }
     const long long total = static_cast<long long>(batch) * ld_pad;
     reflect_pad_split_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
         y, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), N, half, ld_pad, total);
@@ -320,10 +367,47 @@ __global__ void istft_overlap_add_kernel(const float* __restrict__ frames, const
     }
 }
 
+// 4 consecutive samples per thread (hop % 4 == 0, L % 4 == 0): the same frames cover all four, so each covering frame
+// contributes one float4 load and the envelope terms are read once per frame; same summation order as the scalar kernel
+__global__ void istft_overlap_add4_kernel(const float* __restrict__ frames, const double* __restrict__ win_sq,
+                                          float* __restrict__ out, int F, int L, int hop, int n_out, long long total4) {
+    const int half = L / 2;
+    const float scale = static_cast<float>(L) / static_cast<float>(hop);
+    const int per_row = n_out >> 2;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / per_row;
+        const int n = (static_cast<int>(i - b * per_row) << 2) + half;      // first of 4 positions, untrimmed signal
+        const int q = n / hop;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, env[4] = {0.f, 0.f, 0.f, 0.f};
+        int f_lo = (n - L + hop) / hop;
+        if (n - L + 1 <= 0) f_lo = 0;
+        const int f_hi = q < F - 1 ? q : F - 1;
+        // n .. n+3 lie in the same hop interval and the same set of frames (n % 4 == 0, hop % 4 == 0, L % 4 == 0)
+        for (int f = f_lo; f <= f_hi; ++f) {
+            const int r = n - f * hop;
+            const float4 v = *reinterpret_cast<const float4*>(frames + (b * F + f) * L + r);
+            acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) env[j] = static_cast<float>(static_cast<double>(env[j]) + win_sq[r + j]);
+        }
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = (env[j] > 1.17549435e-38f ? acc[j] / env[j] : acc[j]) * scale;
+        *reinterpret_cast<float4*>(out + b * n_out + (n - half)) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 int istft_overlap_add(const float* frames, const double* win_sq, float* out, int batch, int F, int L, int hop,
                       cudaStream_t stream) {
     WGB_REQUIRE(frames && win_sq && out && batch > 0 && F > 1 && L > 0 && hop > 0, "bad arguments");
     const int n_out = hop * (F - 1);
+    if (hop % 4 == 0 && L % 8 == 0 && (reinterpret_cast<uintptr_t>(frames) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        const long long total4 = static_cast<long long>(batch) * (n_out >> 2);
+        istft_overlap_add4_kernel<<<grid_for(total4, 256), 256, 0, stream>>>(frames, win_sq, out, F, L, hop, n_out, total4);
+        WGB_LAUNCH_CHECK();
+        return WGB_OK;
+    }
     const long long total = static_cast<long long>(batch) * n_out;
     istft_overlap_add_kernel<<<grid_for(total, 256), 256, 0, stream>>>(frames, win_sq, out, F, L, hop, n_out, total);
     WGB_LAUNCH_CHECK();
