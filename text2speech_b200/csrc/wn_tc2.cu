@@ -55,15 +55,15 @@ constexpr int kMelK = 320;           // 4 upsample taps x 80 mel channels
 // Shared memory (offsets from a 1024 B aligned base): [TMA ring][mode extra][barriers]
 //   GATE      6 stages + 4 KB bias (sigmoid half pre-halved)
 //   GATE_MEL  6 stages + 4 KB bias + 16 KB W_end W_skip_i (fp32 [512][8]) for the skip accumulation in the epilogue
-//   RES       4 stages + 64 KB h tile + 2 KB bias
+//   RES       5 stages + 64 KB h tile (the ring depth bounds this latency-bound kernel; the bias is read through L1)
 //   SKIP_END  6 stages + 16 KB W_end^T + 10 KB WN.start weights of the next flow
 template <int MODE>
 struct Smem {
-    static constexpr int kStages = MODE == RES ? 4 : 6;
+    static constexpr int kStages = MODE == RES ? 5 : 6;
     static constexpr int kExtraOff = kStages * kStageBytes;
     static constexpr int kExtraBytes =
         (MODE == GATE || MODE == GATE_MEL) ? 2 * kNCh * 4 : MODE == GATE_MEL_ACC ? 2 * kNCh * 4 + kNCh * 8 * 4
-                                           : (MODE == RES ? kBlockM * kBlockN * 2 + kNCh * 4 : kNCh * 8 * 4 + kNCh * 5 * 4);
+                                           : (MODE == RES ? kBlockM * kBlockN * 2 : kNCh * 8 * 4 + kNCh * 5 * 4);
     static constexpr int kBarOff = kExtraOff + kExtraBytes;
     static constexpr int kTotal = 1024 + kBarOff + 256;
 };
@@ -187,7 +187,6 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hready_bar + 2);
     uint8_t* s_extra = smem + SL::kExtraOff;
     float* s_f32 = reinterpret_cast<float*>(s_extra);                                    // GATE bias / SKIP_END W_end^T
-    float* s_rbias = reinterpret_cast<float*>(s_extra + kBlockM * kBlockN * 2);           // RES bias
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -224,7 +223,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 for (int i = i0; i < kNCh * 8; i += 128) s_f32[2 * kNCh + i] = p.w_comp[i];
             }
         } else if constexpr (MODE == RES) {
-            for (int i = i0; i < kNCh; i += 128) s_rbias[i] = p.bias[i];
+            // bias stays in global memory (__ldg): the 2 KB would cost the fifth ring stage
         } else {
             for (int i = i0; i < kNCh * 8; i += 128) s_f32[i] = p.w_end[i];
             if (p.h_next) {                       // [512][4] zero-padded weight rows, then [512] bias
@@ -532,7 +531,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                     // h tile sits in smem in the TMA SWIZZLE_128B layout (four [128 x 64] boxes): row r of box j is
                     // at j*16K + r*128, its 16 B chunk c at ((c ^ (r & 7)) << 4).  Each thread updates its own row
                     // in place; the whole tile then leaves through one TMA store (coalesced, asynchronous).
-                    const float4* bias4 = reinterpret_cast<const float4*>(s_rbias) + pass * (kBlockN / 4);
+                    const float4* bias4 = reinterpret_cast<const float4*>(p.bias) + pass * (kBlockN / 4);
 #pragma unroll 1
                     for (int ch = 0; ch < 8; ++ch) {
                         if ((ch & 3) == 0) mbar_wait(&hfull_bar[ch >> 2], hph, 600 + (ch >> 2));
@@ -547,7 +546,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const uint32_t* ow = reinterpret_cast<const uint32_t*>(&old[i]);
-                            const float4 b0 = bias4[ch * 8 + i * 2], b1 = bias4[ch * 8 + i * 2 + 1];   // broadcast LDS.128
+                            const float4 b0 = __ldg(bias4 + ch * 8 + i * 2), b1 = __ldg(bias4 + ch * 8 + i * 2 + 1);
                             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                             uint32_t pk[4];
 #pragma unroll
