@@ -268,6 +268,57 @@ WGB_API int wgb_stft_recombine(const float* mag, const float* phase, float* spec
 WGB_API int wgb_istft_overlap_add(const float* frames, const double* win_sq, float* out, int batch, int F, int L,
                           int hop, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Training direction: what torch autograd + torch.optim.Adam run for
+ * waveglow/train.py:116-124 (`outputs = model((mel, audio)); loss = criterion(outputs); loss.backward();
+ * optimizer.step()`), restated as explicit kernels over the tensors the forward kernels already hold.
+ * All activations channels-last; "rows" = B*T group steps.
+ * --------------------------------------------------------------------------------------------------------------- */
+/* wgb_tc2_wn_gate that also stores tanh | sigmoid of the pre-activations as bf16 [B,T,1024] (original channel order):
+ * the tensors autograd would save for glow.py:33-40. */
+WGB_API int wgb_tc2_wn_gate_train(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts,
+                                  void* ts, int batch, int T, int dilation, void* stream);
+/* out[b,t,n] = act(bias[n] + sum_s sum_c W[n][s*C+c] A_s[b, t + shift0 + s*dshift, c]) + res[b,t,n] on tcgen05.
+ * A_s = a1 if bit s of seg_mask else a0 (bf16 [B,T,C], C % 64 == 0); W bf16 [N][n_seg*C] (N % 256 == 0); out / res fp32
+ * (out_bf16 = 0) or bf16; res may be NULL or alias out.  The data gradients of in_layers (dilated taps + residual
+ * stream), res_skip_layers (segments [g_h | g_skip]) and cond_layers (accumulating) of glow.py:159-166. */
+WGB_API int wgb_tc_gemm_seg(const void* a0, const void* a1, int n_seg, int seg_mask, const void* w, const float* bias,
+                            const void* res, void* c, int out_bf16, int batch, int T, int N, int C, int shift0, int dshift,
+                            int act, void* stream);
+/* dw[tap][m][n] (+)= sum_{b,t} g[b,t,m] x[b, t + (tap - (taps-1)/2)*dilation, n] on tcgen05 with both operands
+ * MN-major (no transposed copies).  g bf16 [B,T,ca] (ca % 64 == 0), x bf16 [B,T,cb] (cb % 8 == 0), dw fp32
+ * [taps][ca][cb]; accumulate = 0 clears dw first.  Weight gradients of in_layers / cond_layers / res_skip_layers. */
+WGB_API int wgb_tc_wgrad(const void* g, const void* x, float* dw, int batch, int T, int ca, int cb, int taps, int dilation,
+                         int accumulate, void* stream);
+/* ts (tanh | sigmoid, bf16 [rows, 2 n_ch]) <- gradient w.r.t. the gate pre-activations given g_acts bf16 [rows, n_ch]. */
+WGB_API int wgb_gate_bwd(const void* g_acts, void* ts, long long rows, int n_ch, void* stream);
+/* Affine coupling + WN.end backward (glow.py:241-246): see csrc/train.cu.  g_x fp32 [rows,8] in/out, x_mix = flow state
+ * before the coupling, log_s / g_log_s fp32 [B,n_half,T] (g_log_s may be NULL), w_end_t fp32 [n_ch][8];
+ * g_out fp32 [rows,8], g_skip bf16 [rows,n_ch]. */
+WGB_API int wgb_coupling_bwd(float* g_x, const float* x_mix, const float* log_s, const float* g_log_s, const float* w_end_t,
+                             float* g_out, void* g_skip, int batch, int T, int n_ch, int n_half, void* stream);
+/* g_x[a0 channels] += g_h0 W_start (glow.py:156); w_start fp32 [n_ch][n_half]. */
+WGB_API int wgb_start_bwd(float* g_x, const void* g_h0, const float* w_start, long long rows, int n_ch, int n_half,
+                          void* stream);
+/* out[j][c] (+)= sum_r a[r][j] b[r][c]; a fp32 [rows,8], b bf16 [rows,n_ch], out fp32 [8][n_ch]. */
+WGB_API int wgb_skinny_wgrad(const float* a, const void* b, float* out, long long rows, int n_ch, int accumulate,
+                             void* stream);
+/* out[c] (+)= sum_r b[r][c] (bias gradients); b bf16 [rows,n_ch]. */
+WGB_API int wgb_colsum_bf16(const void* b, float* out, long long rows, int n_ch, int accumulate, void* stream);
+/* out[j] (+)= sum_r a[r][j]; a fp32 [rows,8]. */
+WGB_API int wgb_colsum8_f32(const float* a, float* out, long long rows, int accumulate, void* stream);
+/* Invertible 1x1 conv backward (glow.py:97-102): g_x <- W^T g_y on the last C channels (in place),
+ * dw[i][j] = sum_r g_y[i] x_pre[j] (fp32 [8][8]; the log-det term is the caller's). */
+WGB_API int wgb_mix_bwd(float* g_x, const float* x_pre, const float* w, float* dw, long long rows, int C, void* stream);
+/* ConvTranspose1d upsample weight / bias gradient (glow.py:183-185,213-221) from the gradient of the regrouped
+ * conditioning tensor g_cond fp32 [B,T,ld]; mel fp32 [B,n_mel,frames]; dw fp32 [n_mel][n_mel][ksize], db [n_mel]. */
+WGB_API int wgb_upsample_wgrad(const float* mel, const float* g_cond, float* dw, float* db, int batch, int n_mel, int frames,
+                               int T, int ld, int ksize, int stride, int n_group, void* stream);
+/* torch.optim.Adam step (train.py:79,124; no weight decay / amsgrad) over one flat fp32 buffer of n (% 4 == 0) values;
+ * the gradient is multiplied by grad_scale first (1 / world_size after a sum all-reduce). */
+WGB_API int wgb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                          float eps, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,364 @@
+"""Training direction: gradients of WaveGlowLoss(WaveGlow.forward) w.r.t. every reference
+parameter, pinned to the UNMODIFIED reference's autograd (tests/golden/train_grads_golden.npz, written by
+tests/golden/make_golden_grads.py), plus the kernels behind them, the fused Adam step and the flat-bucket all-reduce.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+from tests.golden.make_golden_grads import SIGMA, sample_index, train_config, train_inputs
+from text2speech_b200 import synthetic as syn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def golden_grads():
+    with np.load(os.path.join(HERE, "golden", "train_grads_golden.npz")) as f:
+        return {k: f[k] for k in f.files}
+
+
+def _train_state():
+    return syn.synthetic_state_dict(train_config(), seed=777, end_std=0.05, weight_norm=True)
+
+
+def _compare(named_grads, golden, tol_big, tol_small, min_fraction=1.0):
+    """Sampled entries of every gradient vs the reference's.  Returns the worst relative error per parameter kind."""
+    worst = {}
+    bad = []
+    for name, g in named_grads:
+        g = g.detach().float().cpu().flatten()
+        ref = torch.from_numpy(golden[name + "|samples"])
+        got = g[torch.from_numpy(sample_index(name, g.numel()))]
+        scale = float(golden[name + "|norm"]) / max(g.numel(), 1) ** 0.5        # rms of the whole gradient
+        err = float((got - ref).norm() / max(float(ref.norm()), 1e-3 * scale * len(ref) ** 0.5, 1e-30))
+        kind = name.split(".")[-2] + "." + name.split(".")[-1] if name.startswith("WN") else name
+        worst[kind] = max(worst.get(kind, 0.0), err)
+        tol = tol_small if g.numel() <= 4096 else tol_big
+        if err > tol:
+            bad.append((name, err))
+    return worst, bad
+
+
+def test_oracle_gradients_match_reference(golden_grads):
+    """The CPU oracle under torch autograd reproduces the reference's parameter gradients (pins the checker)."""
+    from oracle import waveglow_oracle as wo
+    sd = {k: v.clone().requires_grad_(True) for k, v in _train_state().items()}
+    mel, wav = train_inputs()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        z, log_s, log_det = wo.waveglow_forward(sd, mel, wav)
+        loss = wo.waveglow_loss(z, log_s, log_det, SIGMA)
+        loss.backward()
+    assert abs(float(loss) - float(golden_grads["loss"])) <= 1e-5 * abs(float(golden_grads["loss"])) + 1e-6
+    worst, bad = _compare([(k, v.grad) for k, v in sd.items()], golden_grads, 2e-4, 2e-4)
+    assert not bad, f"oracle gradients differ from the reference's: {bad[:5]} (worst per kind: {worst})"
+
+
+def test_allreduce_gradients_is_identity_without_process_group():
+    from text2speech_b200 import training
+
+    class Fake:
+        def gather_grads(self):
+            return torch.ones(8)
+
+    assert training.allreduce_gradients(Fake()) == 1.0
+
+
+# ---------------------------------------------------------------------------------------------------- GPU
+@pytest.fixture(scope="module")
+def lib():
+    from text2speech_b200 import _lib
+    _lib.require_b200(torch.device(DEV))
+    return _lib
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ca,cb,taps,dil,b,t", [(1024, 512, 3, 4, 3, 200), (512, 512, 1, 1, 2, 333), (1024, 640, 1, 1, 2, 128),
+                                                (1024, 512, 3, 128, 2, 300)])
+def test_tc_wgrad_matches_torch(lib, ca, cb, taps, dil, b, t):
+    g = torch.Generator().manual_seed(ca + cb + taps)
+    gy = torch.randn((b, t, ca), generator=g).bfloat16()
+    x = torch.randn((b, t, cb), generator=g).bfloat16()
+    want = torch.zeros(taps, ca, cb, dtype=torch.float64)
+    for tap in range(taps):
+        sh = (tap - (taps - 1) // 2) * dil
+        xs = torch.zeros_like(x, dtype=torch.float64)
+        if sh >= 0:
+            xs[:, : t - sh] = x[:, sh:].double() if sh < t else 0
+        else:
+            xs[:, -sh:] = x[:, : t + sh].double()
+        want[tap] = torch.einsum("btm,btn->mn", gy.double(), xs)
+    dw = torch.full((taps, ca, cb), 7.0, device=DEV)
+    lib.call("wgb_tc_wgrad", gy.to(DEV), x.to(DEV), dw, b, t, ca, cb, taps, dil, 0, lib.stream_ptr())
+    assert util.rel_l2(dw.cpu(), want) <= 1e-4
+    lib.call("wgb_tc_wgrad", gy.to(DEV), x.to(DEV), dw, b, t, ca, cb, taps, dil, 1, lib.stream_ptr())
+    assert util.rel_l2(dw.cpu(), 2 * want) <= 1e-4
+
+
+@pytest.mark.gpu
+def test_tc_gemm_seg_taps_residual_and_two_operands(lib):
+    g = torch.Generator().manual_seed(5)
+    b, t, c, n, d = 2, 300, 1024, 512, 8
+    a = torch.randn((b, t, c), generator=g).bfloat16()
+    w = (torch.randn((n, 3 * c), generator=g) / 40).bfloat16()
+    res = torch.randn((b, t, n), generator=g).bfloat16()
+    want = res.double().clone()
+    for s in range(3):
+        sh = (s - 1) * d
+        a_s = torch.zeros((b, t, c), dtype=torch.float64)
+        if sh >= 0:
+            a_s[:, : t - sh] = a[:, sh:].double()
+        else:
+            a_s[:, -sh:] = a[:, : t + sh].double()
+        want += a_s @ w[:, s * c:(s + 1) * c].double().t()
+    out = res.to(DEV).clone()
+    lib.call("wgb_tc_gemm_seg", a.to(DEV), None, 3, 0, w.to(DEV), None, out, out, 1, b, t, n, c, -d, d, 0, lib.stream_ptr())
+    assert util.rel_l2(out.float().cpu(), want) <= 4e-3                     # bf16 output rounding
+    # two operands (segments [a0 | a1]), fp32 output accumulated in place
+    a1 = torch.randn((b, t, c), generator=g).bfloat16()
+    w2 = (torch.randn((256, 2 * c), generator=g) / 40).bfloat16()
+    acc0 = torch.randn((b, t, 256), generator=g)
+    want2 = acc0.double() + a.double() @ w2[:, :c].double().t() + a1.double() @ w2[:, c:].double().t()
+    acc = acc0.to(DEV).clone()
+    lib.call("wgb_tc_gemm_seg", a.to(DEV), a1.to(DEV), 2, 0b10, w2.to(DEV), None, acc, acc, 0, b, t, 256, c, 0, 0, 0,
+             lib.stream_ptr())
+    assert util.rel_l2(acc.cpu(), want2) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_gate_train_stores_tanh_and_sigmoid(lib):
+    from text2speech_b200.packing import gate_row_order
+    g = torch.Generator().manual_seed(6)
+    b, t = 2, 200
+    h = torch.randn((b, t, 512), generator=g).bfloat16()
+    cond = torch.randn((b, t, 640), generator=g).bfloat16()
+    w = (torch.randn((1024, 2176), generator=g) / 50).bfloat16()
+    bias = torch.randn(1024, generator=g) * 0.1
+    order = gate_row_order(512)
+    acts = torch.empty((b, t, 512), device=DEV, dtype=torch.bfloat16)
+    acts2 = torch.empty_like(acts)
+    ts = torch.empty((b, t, 1024), device=DEV, dtype=torch.bfloat16)
+    args = (h.to(DEV), cond.to(DEV), w[order].contiguous().to(DEV), bias[order].contiguous().to(DEV))
+    lib.call("wgb_tc2_wn_gate_train", *args, acts, ts, b, t, 2, lib.stream_ptr())
+    lib.call("wgb_tc2_wn_gate", *args, acts2, b, t, 2, lib.stream_ptr())
+    assert torch.equal(acts, acts2)
+    hp = torch.zeros((b, t + 4, 512), dtype=torch.float64)
+    hp[:, 2:-2] = h.double()
+    u = bias.double() + cond.double() @ w[:, 1536:].double().t()
+    for tap in range(3):
+        u = u + hp[:, 2 * tap: 2 * tap + t] @ w[:, tap * 512:(tap + 1) * 512].double().t()
+    want = torch.cat([torch.tanh(u[..., :512]), torch.sigmoid(u[..., 512:])], dim=-1)
+    assert util.rel_l2(ts.float().cpu(), want) <= 4e-3
+
+
+@pytest.mark.gpu
+def test_pointwise_backward_kernels(lib):
+    g = torch.Generator().manual_seed(8)
+    rows, nh = 1000, 3
+    c, base = 2 * nh, 8 - 2 * nh
+    s = lib.stream_ptr()
+    # gate backward
+    ga = torch.randn((rows, 512), generator=g).bfloat16()
+    tt = torch.tanh(torch.randn((rows, 512), generator=g)).bfloat16()
+    ss = torch.sigmoid(torch.randn((rows, 512), generator=g)).bfloat16()
+    ts = torch.cat([tt, ss], dim=1).to(DEV).contiguous()
+    lib.call("wgb_gate_bwd", ga.to(DEV), ts, rows, 512, s)
+    want = torch.cat([ga.float() * ss.float() * (1 - tt.float() ** 2), ga.float() * tt.float() * ss.float() * (1 - ss.float())], 1)
+    assert util.rel_l2(ts.float().cpu(), want) <= 4e-3
+    # coupling backward
+    b, t = 2, 500
+    g_x = torch.randn((rows, 8), generator=g)
+    x_mix = torch.randn((rows, 8), generator=g)
+    log_s = 0.3 * torch.randn((b, nh, t), generator=g)
+    g_ls = torch.randn((b, nh, t), generator=g)
+    w_end_t = torch.zeros(512, 8)
+    w_end_t[:, :c] = torch.randn((512, c), generator=g)
+    gx = g_x.to(DEV).clone()
+    g_out = torch.empty((rows, 8), device=DEV)
+    g_skip = torch.empty((rows, 512), device=DEV, dtype=torch.bfloat16)
+    lib.call("wgb_coupling_bwd", gx, x_mix.to(DEV), log_s.to(DEV), g_ls.to(DEV), w_end_t.to(DEV), g_out, g_skip, b, t, 512, nh, s)
+    ls_rows = log_s.permute(0, 2, 1).reshape(rows, nh)
+    gls_rows = g_ls.permute(0, 2, 1).reshape(rows, nh)
+    ga1p = g_x[:, base + nh:]
+    want_out = torch.zeros(rows, 8)
+    want_out[:, :nh] = ga1p
+    want_out[:, nh:c] = ga1p * x_mix[:, base + nh:] * ls_rows.exp() + gls_rows
+    want_gx = g_x.clone()
+    want_gx[:, base + nh:] = ga1p * ls_rows.exp()
+    assert util.rel_l2(g_out.cpu(), want_out) <= 1e-6
+    assert util.rel_l2(gx.cpu(), want_gx) <= 1e-6
+    assert util.rel_l2(g_skip.float().cpu(), want_out @ w_end_t.t()) <= 4e-3
+    # skinny reductions
+    bb = torch.randn((rows, 512), generator=g).bfloat16()
+    out = torch.empty((8, 512), device=DEV)
+    lib.call("wgb_skinny_wgrad", g_out, bb.to(DEV), out, rows, 512, 0, s)
+    assert util.rel_l2(out.cpu(), want_out.double().t() @ bb.double()) <= 1e-5
+    cs = torch.empty(512, device=DEV)
+    lib.call("wgb_colsum_bf16", bb.to(DEV), cs, rows, 512, 0, s)
+    assert util.rel_l2(cs.cpu(), bb.double().sum(0)) <= 1e-5
+    c8 = torch.empty(8, device=DEV)
+    lib.call("wgb_colsum8_f32", g_out, c8, rows, 0, s)
+    assert util.rel_l2(c8.cpu(), want_out.double().sum(0)) <= 1e-5
+    # WN.start backward
+    w_start = torch.randn((512, nh), generator=g)
+    gx2 = g_x.to(DEV).clone()
+    lib.call("wgb_start_bwd", gx2, bb.to(DEV), w_start.to(DEV), rows, 512, nh, s)
+    want2 = g_x.clone()
+    want2[:, base: base + nh] += (bb.double() @ w_start.double()).float()
+    assert util.rel_l2(gx2.cpu(), want2) <= 1e-5
+    # 1x1 mix backward
+    w = torch.zeros(8, 8)
+    w[:c, :c] = torch.randn((c, c), generator=g)
+    gx3 = g_x.to(DEV).clone()
+    dw = torch.empty((8, 8), device=DEV)
+    lib.call("wgb_mix_bwd", gx3, x_mix.to(DEV), w.to(DEV), dw, rows, c, s)
+    want3 = g_x.clone()
+    want3[:, base:] = g_x[:, base:] @ w[:c, :c]
+    assert util.rel_l2(gx3.cpu(), want3) <= 1e-5
+    assert util.rel_l2(dw[:c, :c].cpu(), g_x[:, base:].double().t() @ x_mix[:, base:].double()) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_upsample_wgrad_matches_autograd(lib):
+    g = torch.Generator().manual_seed(9)
+    b, f, t = 2, 5, 150                                   # t < 32 f: the trimmed branch (glow.py:216-218)
+    mel = torch.randn((b, 80, f), generator=g)
+    w = torch.randn((80, 80, 1024), generator=g, requires_grad=True)
+    bias = torch.zeros(80, requires_grad=True)
+    g_cond = torch.zeros((b, t, 768))
+    g_cond[:, :, :640] = torch.randn((b, t, 640), generator=g)
+    up = torch.nn.functional.conv_transpose1d(mel, w, bias, stride=256)[:, :, : t * 8]
+    cond = up.reshape(b, 80, t, 8).permute(0, 2, 1, 3).reshape(b, t, 640)
+    (cond * g_cond[:, :, :640]).sum().backward()
+    dw = torch.empty((80, 80, 1024), device=DEV)
+    db = torch.empty(80, device=DEV)
+    lib.call("wgb_upsample_wgrad", mel.to(DEV), g_cond.to(DEV), dw, db, b, 80, f, t, 768, 1024, 256, 8, lib.stream_ptr())
+    assert util.rel_l2(dw.cpu(), w.grad) <= 1e-5
+    assert util.rel_l2(db.cpu(), bias.grad) <= 1e-5
+
+
+@pytest.fixture(scope="module")
+def train_model(lib):
+    import text2speech_b200 as t2s
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = t2s.WaveGlow(**train_config())
+    m.load_state_dict(_train_state())
+    return m.to(DEV).train()
+
+
+@pytest.mark.gpu
+def test_parameter_gradients_match_reference(train_model, golden_grads):
+    """criterion(model((mel, audio))).backward() on the drop-in model vs the unmodified reference's autograd."""
+    import text2speech_b200 as t2s
+    m = train_model
+    m.zero_grad()
+    mel, wav = train_inputs()
+    outputs = m((mel.to(DEV), wav.to(DEV)))
+    loss = t2s.WaveGlowLoss(SIGMA)(outputs)
+    loss.backward()
+    assert abs(float(loss) - float(golden_grads["loss"])) <= 2e-3 * abs(float(golden_grads["loss"]))
+    named = [(n, p.grad) for n, p in m.named_parameters()]
+    assert all(g is not None for _, g in named), [n for n, g in named if g is None][:5]
+    worst, bad = _compare(named, golden_grads, 1.5e-2, 1.5e-2)
+    print("worst relative error per parameter kind:", {k: round(v, 4) for k, v in sorted(worst.items())})
+    assert not bad, f"{len(bad)} gradients off: {bad[:8]} (worst per kind: {worst})"
+
+
+@pytest.mark.gpu
+def test_eval_forward_is_unchanged_and_train_forward_agrees(train_model):
+    m = train_model
+    mel, wav = train_inputs()
+    z_train, log_s_train, log_det_train = m((mel.to(DEV), wav.to(DEV)))
+    m.eval()
+    with torch.no_grad():
+        z_eval, log_s_eval, log_det_eval = m((mel.to(DEV), wav.to(DEV)))
+    m.train()
+    assert not z_eval.requires_grad and z_train.requires_grad
+    assert util.snr_db(z_train.detach().cpu(), z_eval.cpu()) >= 40.0
+    assert util.snr_db(log_s_train[-1].detach().cpu(), log_s_eval[-1].cpu()) >= 40.0
+    assert abs(float(log_det_train[0]) - float(log_det_eval[0])) <= 1e-3
+
+
+@pytest.mark.gpu
+def test_fused_adam_matches_torch_adam(lib):
+    from text2speech_b200.training import FusedAdam
+    g = torch.Generator().manual_seed(10)
+    shapes = [(7, 3), (130,), (5, 5, 5)]
+    a = [torch.randn(s, generator=g).to(DEV).requires_grad_(True) for s in shapes]
+    b = [p.detach().clone().requires_grad_(True) for p in a]
+    opt_a = FusedAdam(a, lr=1e-2)
+    opt_b = torch.optim.Adam(b, lr=1e-2)
+    for step in range(5):
+        for pa, pb in zip(a, b):
+            gr = torch.randn(pa.shape, generator=g).to(DEV)
+            pa.grad = gr.clone()
+            pb.grad = gr.clone()
+        opt_a.step()
+        opt_b.step()
+    for pa, pb in zip(a, b):
+        assert util.rel_l2(pa.detach().cpu(), pb.detach().cpu()) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_step_along_the_gradient_lowers_the_loss_as_predicted(lib):
+    """Size-independent property: loss(theta - eps g) - loss(theta) = -eps |g|^2 to first order.  eps is chosen so
+    that the predicted drop is 3 % of the loss; the realised drop must be 0.5x .. 1.5x of it."""
+    import text2speech_b200 as t2s
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = t2s.WaveGlow(**train_config())
+    m.load_state_dict(_train_state())
+    m = m.to(DEV).train()
+    crit = t2s.WaveGlowLoss(SIGMA)
+    mel, wav = train_inputs()
+    mel, wav = mel.to(DEV), wav.to(DEV)
+    loss0 = crit(m((mel, wav)))
+    loss0.backward()
+    g2 = sum(float(p.grad.double().pow(2).sum()) for p in m.parameters())
+    predicted = 0.03 * abs(float(loss0.detach()))
+    eps = predicted / g2
+    with torch.no_grad():
+        for p in m.parameters():
+            p -= eps * p.grad
+    loss1 = crit(m((mel, wav)))
+    drop = float(loss0.detach()) - float(loss1.detach())
+    assert 0.5 * predicted <= drop <= 1.5 * predicted, (float(loss0), float(loss1), predicted)
+
+
+@pytest.mark.gpu
+def test_training_loop_with_fused_adam_and_flat_allreduce(lib):
+    """train.py:108-124 in miniature (zero_grad / forward / loss / backward / all-reduce / step): every parameter
+    moves by at most lr per step (Adam's bound) and the loss stays finite."""
+    import text2speech_b200 as t2s
+    from text2speech_b200.training import FusedAdam, allreduce_gradients
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = t2s.WaveGlow(**train_config())
+    m.load_state_dict(_train_state())
+    m = m.to(DEV).train()
+    before = [p.detach().clone() for p in m.parameters()]
+    lr = 1e-6
+    opt = FusedAdam(m.parameters(), lr=lr)
+    crit = t2s.WaveGlowLoss(SIGMA)
+    mel, wav = train_inputs()
+    mel, wav = mel.to(DEV), wav.to(DEV)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = crit(m((mel, wav)))
+        loss.backward()
+        scale = allreduce_gradients(opt)
+        opt.step(grad_scale=scale, gathered=True)
+        losses.append(float(loss.detach()))
+    assert all(np.isfinite(losses)) and abs(losses[-1] - losses[0]) <= 0.5 * abs(losses[0]), losses
+    moved = max(float((p.detach() - q).abs().max()) for p, q in zip(m.parameters(), before))
+    assert 0.5 * lr <= moved <= 3.2 * lr, moved

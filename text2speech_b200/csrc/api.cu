@@ -20,7 +20,7 @@ int tc_stft_mel(const void*, const void*, const void*, const void*, void*, int, 
 int tc_stft_denoise(const void*, const void*, const void*, const float*, float, void*, void*, int, int, int, int, int,
                     long long, long long, cudaStream_t);
 // wn_tc2.cu
-int tc2_wn_gate(const void*, const void*, const void*, const float*, void*, int, int, int, cudaStream_t);
+int tc2_wn_gate(const void*, const void*, const void*, const float*, void*, void*, int, int, int, cudaStream_t);
 int tc2_wn_res(const void*, const void*, const float*, const void*, void*, int, int, long long, const void*, float*, int,
                cudaStream_t);
 int tc2_wn_gate_mel(const void*, const void*, const void*, const void*, const float*, void*, int, int, int, int,
@@ -53,6 +53,20 @@ int end_coupling_f32(const float*, const float*, const float*, float*, const flo
 int upsample_im2col(const float*, void*, int, int, int, int, int, int, cudaStream_t);
 int cast_f32_to_bf16(const float*, void*, long long, cudaStream_t);
 int audio_to_int16(const float*, void*, long long, float, cudaStream_t);
+// training direction: wn_tc.cu, wn_wgrad.cu, train.cu
+int tc_gemm_seg(const void*, const void*, int, int, const void*, const float*, const void*, void*, int, int, int, int, int,
+                int, int, int, cudaStream_t);
+int tc_wgrad(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
+int gate_bwd(const void*, void*, long long, int, cudaStream_t);
+int coupling_bwd(float*, const float*, const float*, const float*, const float*, float*, void*, int, int, int, int,
+                 cudaStream_t);
+int start_bwd(float*, const void*, const float*, long long, int, int, cudaStream_t);
+int skinny_wgrad(const float*, const void*, float*, long long, int, int, cudaStream_t);
+int colsum_bf16(const void*, float*, long long, int, int, cudaStream_t);
+int colsum8_f32(const float*, float*, long long, int, cudaStream_t);
+int mix_bwd(float*, const float*, const float*, float*, long long, int, cudaStream_t);
+int upsample_wgrad(const float*, const float*, float*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
+int adam_step(float*, const float*, float*, float*, long long, float, float, float, float, int, float, cudaStream_t);
 // stft.cu
 int stft_reflect_pad(const float*, float*, int, int, int, long long, cudaStream_t);
 int stft_reflect_pad_split(const float*, void*, void*, int, int, int, long long, cudaStream_t);
@@ -105,7 +119,12 @@ WGB_API int wgb_tc_wn_gate(const void* h, const void* cond, const void* w_packed
 }
 WGB_API int wgb_tc2_wn_gate(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts, int batch,
                             int T, int dilation, void* stream) {
-    return tc2_wn_gate(h, cond, w_packed, bias, acts, batch, T, dilation, S(stream));
+    return tc2_wn_gate(h, cond, w_packed, bias, acts, nullptr, batch, T, dilation, S(stream));
+}
+WGB_API int wgb_tc2_wn_gate_train(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts,
+                                  void* ts, int batch, int T, int dilation, void* stream) {
+    WGB_REQUIRE(ts != nullptr, "ts is null");
+    return tc2_wn_gate(h, cond, w_packed, bias, acts, ts, batch, T, dilation, S(stream));
 }
 WGB_API int wgb_tc2_wn_gate_mel(const void* h, const void* mel_stack, const void* w_packed, const void* w_mel,
                                 const float* bias, void* acts, int batch, int T, int frames_pad, int dilation,
@@ -262,3 +281,46 @@ WGB_API int wgb_istft_overlap_add(const float* frames, const double* win_sq, flo
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ training direction
+WGB_API int wgb_tc_gemm_seg(const void* a0, const void* a1, int n_seg, int seg_mask, const void* w, const float* bias,
+                            const void* res, void* c, int out_bf16, int batch, int T, int N, int C, int shift0, int dshift,
+                            int act, void* stream) {
+    return tc_gemm_seg(a0, a1, n_seg, seg_mask, w, bias, res, c, out_bf16, batch, T, N, C, shift0, dshift, act, S(stream));
+}
+WGB_API int wgb_tc_wgrad(const void* g, const void* x, float* dw, int batch, int T, int ca, int cb, int taps, int dilation,
+                         int accumulate, void* stream) {
+    return tc_wgrad(g, x, dw, batch, T, ca, cb, taps, dilation, accumulate, S(stream));
+}
+WGB_API int wgb_gate_bwd(const void* g_acts, void* ts, long long rows, int n_ch, void* stream) {
+    return gate_bwd(g_acts, ts, rows, n_ch, S(stream));
+}
+WGB_API int wgb_coupling_bwd(float* g_x, const float* x_mix, const float* log_s, const float* g_log_s, const float* w_end_t,
+                             float* g_out, void* g_skip, int batch, int T, int n_ch, int n_half, void* stream) {
+    return coupling_bwd(g_x, x_mix, log_s, g_log_s, w_end_t, g_out, g_skip, batch, T, n_ch, n_half, S(stream));
+}
+WGB_API int wgb_start_bwd(float* g_x, const void* g_h0, const float* w_start, long long rows, int n_ch, int n_half,
+                          void* stream) {
+    return start_bwd(g_x, g_h0, w_start, rows, n_ch, n_half, S(stream));
+}
+WGB_API int wgb_skinny_wgrad(const float* a, const void* b, float* out, long long rows, int n_ch, int accumulate,
+                             void* stream) {
+    return skinny_wgrad(a, b, out, rows, n_ch, accumulate, S(stream));
+}
+WGB_API int wgb_colsum_bf16(const void* b, float* out, long long rows, int n_ch, int accumulate, void* stream) {
+    return colsum_bf16(b, out, rows, n_ch, accumulate, S(stream));
+}
+WGB_API int wgb_colsum8_f32(const float* a, float* out, long long rows, int accumulate, void* stream) {
+    return colsum8_f32(a, out, rows, accumulate, S(stream));
+}
+WGB_API int wgb_mix_bwd(float* g_x, const float* x_pre, const float* w, float* dw, long long rows, int C, void* stream) {
+    return mix_bwd(g_x, x_pre, w, dw, rows, C, S(stream));
+}
+WGB_API int wgb_upsample_wgrad(const float* mel, const float* g_cond, float* dw, float* db, int batch, int n_mel, int frames,
+                               int T, int ld, int ksize, int stride, int n_group, void* stream) {
+    return upsample_wgrad(mel, g_cond, dw, db, batch, n_mel, frames, T, ld, ksize, stride, n_group, S(stream));
+}
+WGB_API int wgb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                          float eps, int step, float grad_scale, void* stream) {
+    return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step, grad_scale, S(stream));
+}

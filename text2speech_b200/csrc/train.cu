@@ -1,0 +1,436 @@
+// Training direction: the memory-bound pieces of the backward pass through one flow
+// (glow.py:207-249 under autograd, as driven by waveglow/train.py:116-124) and the optimiser step (train.py:79,124).
+// The GEMM-shaped pieces are in wn_tc.cu (data gradients: tc_gemm_seg) and wn_wgrad.cu (weight gradients: tc_wgrad).
+// Everything here is channels-last, fp32 for the flow state and its gradient ([rows, 8]), bf16 for the 512-channel
+// residual-stream tensors.
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace wgb {
+
+// ------------------------------------------------------------------------------------------------ gate backward
+// acts = tanh(a) * sigmoid(b)  ->  g_a = g * s * (1 - t^2), g_b = g * t * s * (1 - s).  ts holds (t | s) on entry and
+// (g_a | g_b) on exit (the gradient w.r.t. the gate pre-activations, original channel order).
+__global__ void gate_bwd_kernel(const uint4* __restrict__ g_acts, uint4* __restrict__ ts, long long rows, int c8) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= rows * c8) return;
+    const long long r = i / c8;
+    const int c = static_cast<int>(i - r * c8);
+    const uint4 g4 = g_acts[i];
+    uint4* tp = ts + r * (2 * c8) + c;
+    uint4* sp = tp + c8;
+    const uint4 t4 = *tp, s4 = *sp;
+    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, tw[4] = {t4.x, t4.y, t4.z, t4.w}, sw[4] = {s4.x, s4.y, s4.z, s4.w};
+    uint32_t ga[4], gb[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]));
+        const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tw[e]));
+        const float2 s = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&sw[e]));
+        __nv_bfloat162 a2 = __floats2bfloat162_rn(g.x * s.x * (1.f - t.x * t.x), g.y * s.y * (1.f - t.y * t.y));
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(g.x * t.x * s.x * (1.f - s.x), g.y * t.y * s.y * (1.f - s.y));
+        ga[e] = *reinterpret_cast<uint32_t*>(&a2);
+        gb[e] = *reinterpret_cast<uint32_t*>(&b2);
+    }
+    *tp = make_uint4(ga[0], ga[1], ga[2], ga[3]);
+    *sp = make_uint4(gb[0], gb[1], gb[2], gb[3]);
+}
+
+int gate_bwd(const void* g_acts, void* ts, long long rows, int n_ch, cudaStream_t stream) {
+    WGB_REQUIRE(g_acts && ts, "null pointer");
+    WGB_REQUIRE(rows > 0 && n_ch > 0 && n_ch % 8 == 0, "rows must be positive and n_ch a multiple of 8");
+    const long long n = rows * (n_ch / 8);
+    gate_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(static_cast<const uint4*>(g_acts),
+                                                                                static_cast<uint4*>(ts), rows, n_ch / 8);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ coupling backward
+// Forward (glow.py:241-246): a1' = exp(log_s) a1 + b, (b, log_s) = WN.end(skip).  Given g_x (gradient w.r.t. the flow
+// state after the coupling), the state before it (x_mix: a0 | a1 in the last 2 n_half channels) and the upstream
+// gradient of log_s itself (g_ls [B,n_half,T], e.g. -1/N from WaveGlowLoss), writes
+//   g_out  [rows, 8] fp32: columns 0..n_half-1 = g_b, n_half..2n_half-1 = g_log_s (the gradient of WN.end's output)
+//   g_skip [rows, 512] bf16 = g_out W_end (gradient of the skip sum; w_end_t is [512][8], zero beyond 2 n_half)
+// and replaces g_x's a1 channels by g_a1 = g_a1' exp(log_s).  One warp per row.
+template <int NHALF>
+__global__ void coupling_bwd_kernel(float* __restrict__ g_x, const float* __restrict__ x_mix, const float* __restrict__ log_s,
+                                    const float* __restrict__ g_ls, const float* __restrict__ w_end_t,
+                                    float* __restrict__ g_out, __nv_bfloat16* __restrict__ g_skip, int batch, int T, int n_ch) {
+    constexpr int C = 2 * NHALF, BASE = 8 - C;
+    const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= static_cast<long long>(batch) * T) return;
+    const int b = static_cast<int>(row / T), t = static_cast<int>(row - static_cast<long long>(b) * T);
+    float go[8], ga1[NHALF];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) go[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NHALF; ++j) {
+        const float ga1p = g_x[row * 8 + BASE + NHALF + j];
+        const float a1 = x_mix[row * 8 + BASE + NHALF + j];
+        const size_t li = (static_cast<size_t>(b) * NHALF + j) * T + t;
+        const float e = expf(log_s[li]);
+        go[j] = ga1p;
+        go[NHALF + j] = ga1p * a1 * e + (g_ls ? g_ls[li] : 0.f);
+        ga1[j] = ga1p * e;
+    }
+    __syncwarp();                                            // every lane has read g_x before lane 0 overwrites it
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < NHALF; ++j) g_x[row * 8 + BASE + NHALF + j] = ga1[j];
+    }
+    if (lane == 0) {
+        *reinterpret_cast<float4*>(g_out + row * 8) = make_float4(go[0], go[1], go[2], go[3]);
+        *reinterpret_cast<float4*>(g_out + row * 8 + 4) = make_float4(go[4], go[5], go[6], go[7]);
+    }
+    for (int c = lane * 2; c < n_ch; c += 64) {
+        const float4* w0 = reinterpret_cast<const float4*>(w_end_t + static_cast<size_t>(c) * 8);
+        float acc[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float4 wa = w0[2 * e], wb = w0[2 * e + 1];
+            acc[e] = go[0] * wa.x + go[1] * wa.y + go[2] * wa.z + go[3] * wa.w + go[4] * wb.x + go[5] * wb.y + go[6] * wb.z +
+                     go[7] * wb.w;
+        }
+        *reinterpret_cast<__nv_bfloat162*>(g_skip + row * n_ch + c) = __floats2bfloat162_rn(acc[0], acc[1]);
+    }
+}
+
+int coupling_bwd(float* g_x, const float* x_mix, const float* log_s, const float* g_ls, const float* w_end_t, float* g_out,
+                 void* g_skip, int batch, int T, int n_ch, int n_half, cudaStream_t stream) {
+    WGB_REQUIRE(g_x && x_mix && log_s && w_end_t && g_out && g_skip, "null pointer");
+    WGB_REQUIRE(batch > 0 && T > 0 && n_ch % 64 == 0, "bad shape");
+    WGB_REQUIRE(n_half >= 1 && n_half <= 4, "n_half must be in 1..4 (got %d)", n_half);
+    const long long rows = static_cast<long long>(batch) * T;
+    const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+    __nv_bfloat16* gs = static_cast<__nv_bfloat16*>(g_skip);
+    switch (n_half) {
+        case 1: coupling_bwd_kernel<1><<<grid, 256, 0, stream>>>(g_x, x_mix, log_s, g_ls, w_end_t, g_out, gs, batch, T, n_ch); break;
+        case 2: coupling_bwd_kernel<2><<<grid, 256, 0, stream>>>(g_x, x_mix, log_s, g_ls, w_end_t, g_out, gs, batch, T, n_ch); break;
+        case 3: coupling_bwd_kernel<3><<<grid, 256, 0, stream>>>(g_x, x_mix, log_s, g_ls, w_end_t, g_out, gs, batch, T, n_ch); break;
+        default: coupling_bwd_kernel<4><<<grid, 256, 0, stream>>>(g_x, x_mix, log_s, g_ls, w_end_t, g_out, gs, batch, T, n_ch); break;
+    }
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ WN.start backward
+// h0 = W_start a0 + b (glow.py:156): g_x[a0 channels] += g_h0 W_start.  w_start fp32 [512][n_half]; one warp per row.
+__global__ void start_bwd_kernel(float* __restrict__ g_x, const __nv_bfloat16* __restrict__ g_h0,
+                                 const float* __restrict__ w_start, long long rows, int n_ch, int n_half) {
+    const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane * 2; c < n_ch; c += 64) {
+        const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(g_h0 + row * n_ch + c));
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < n_half)
+                acc[j] += g.x * __ldg(w_start + static_cast<size_t>(c) * n_half + j) +
+                          g.y * __ldg(w_start + static_cast<size_t>(c + 1) * n_half + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    if (lane == 0) {
+        const int base = 8 - 2 * n_half;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < n_half) g_x[row * 8 + base + j] += acc[j];
+    }
+}
+
+int start_bwd(float* g_x, const void* g_h0, const float* w_start, long long rows, int n_ch, int n_half, cudaStream_t stream) {
+    WGB_REQUIRE(g_x && g_h0 && w_start, "null pointer");
+    WGB_REQUIRE(rows > 0 && n_ch % 64 == 0 && n_half >= 1 && n_half <= 4, "bad shape");
+    start_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(g_x, static_cast<const __nv_bfloat16*>(g_h0),
+                                                                                w_start, rows, n_ch, n_half);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ skinny reductions
+// out[j][c] += sum_r a[r][j] * b[r][c]   (a fp32 [rows, 8], b bf16 [rows, n_ch]; out fp32 [8][n_ch]).
+// Weight gradients whose one side has <= 8 channels: WN.start (a = flow state, b = g_h0), WN.end composed with the
+// skip rows (a = g_out, b = the layer's gated activations).  One thread per 8 columns, 256 rows per block.
+__global__ void skinny_wgrad_kernel(const float* __restrict__ a, const uint4* __restrict__ b, float* __restrict__ out,
+                                    long long rows, int c8, int rows_per_block) {
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= c8) return;
+    const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+    const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float acc[8][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+        const uint4 v = b[r * c8 + c];
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(a + r * 8));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(a + r * 8) + 1);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        float bv[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+            bv[2 * e] = f.x;
+            bv[2 * e + 1] = f.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(av[j], bv[e], acc[j][e]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(out + static_cast<size_t>(j) * c8 * 8 + c * 8 + e, acc[j][e]);
+}
+
+int skinny_wgrad(const float* a, const void* b, float* out, long long rows, int n_ch, int accumulate, cudaStream_t stream) {
+    WGB_REQUIRE(a && b && out, "null pointer");
+    WGB_REQUIRE(rows > 0 && n_ch > 0 && n_ch % 8 == 0, "bad shape");
+    if (!accumulate) WGB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * 8 * n_ch, stream));
+    const int c8 = n_ch / 8;
+    const int rpb = 256;
+    dim3 grid(static_cast<unsigned>((rows + rpb - 1) / rpb), (c8 + 63) / 64);
+    skinny_wgrad_kernel<<<grid, 64, 0, stream>>>(a, static_cast<const uint4*>(b), out, rows, c8, rpb);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// out[c] += sum_r b[r][c]  (bias gradients; b bf16 [rows, n_ch])
+__global__ void colsum_bf16_kernel(const uint4* __restrict__ b, float* __restrict__ out, long long rows, int c8,
+                                   int rows_per_block) {
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= c8) return;
+    const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+    const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long long r = r0; r < r1; ++r) {
+        const uint4 v = b[r * c8 + c];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+            acc[2 * e] += f.x;
+            acc[2 * e + 1] += f.y;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(out + c * 8 + e, acc[e]);
+}
+
+int colsum_bf16(const void* b, float* out, long long rows, int n_ch, int accumulate, cudaStream_t stream) {
+    WGB_REQUIRE(b && out, "null pointer");
+    WGB_REQUIRE(rows > 0 && n_ch > 0 && n_ch % 8 == 0, "bad shape");
+    if (!accumulate) WGB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * n_ch, stream));
+    const int c8 = n_ch / 8;
+    const int rpb = 128;
+    dim3 grid(static_cast<unsigned>((rows + rpb - 1) / rpb), (c8 + 127) / 128);
+    colsum_bf16_kernel<<<grid, 128, 0, stream>>>(static_cast<const uint4*>(b), out, rows, c8, rpb);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// out[j] += sum_r a[r][j]  (a fp32 [rows, 8]; gradient of WN.end's bias)
+__global__ void colsum8_f32_kernel(const float* __restrict__ a, float* __restrict__ out, long long rows) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < rows;
+         r += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 a0 = *reinterpret_cast<const float4*>(a + r * 8), a1 = *reinterpret_cast<const float4*>(a + r * 8 + 4);
+        acc[0] += a0.x; acc[1] += a0.y; acc[2] += a0.z; acc[3] += a0.w;
+        acc[4] += a1.x; acc[5] += a1.y; acc[6] += a1.z; acc[7] += a1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(out + j, acc[j]);
+    }
+}
+
+int colsum8_f32(const float* a, float* out, long long rows, int accumulate, cudaStream_t stream) {
+    WGB_REQUIRE(a && out && rows > 0, "bad argument");
+    if (!accumulate) WGB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * 8, stream));
+    long long blocks = (rows + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    colsum8_f32_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(a, out, rows);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ 1x1 mix backward
+// y = W x on the last C channels (glow.py:97-102 forward).  g_x <- W^T g_y in place; dW[i][j] += sum_r g_y[i] x_pre[j]
+// (dw fp32 [8][8], top-left CxC used; the log-det term is added by the caller).
+template <int C>
+__global__ void mix_bwd_kernel(float* __restrict__ g_x, const float* __restrict__ x_pre, const float* __restrict__ w,
+                               float* __restrict__ dw, long long rows) {
+    constexpr int BASE = 8 - C;
+    __shared__ float s_dw[64];
+    if (threadIdx.x < 64) s_dw[threadIdx.x] = 0.f;
+    __syncthreads();
+    float acc[C * C];
+#pragma unroll
+    for (int i = 0; i < C * C; ++i) acc[i] = 0.f;
+    float wr[C * C];
+#pragma unroll
+    for (int i = 0; i < C; ++i)
+#pragma unroll
+        for (int j = 0; j < C; ++j) wr[i * C + j] = __ldg(w + i * 8 + j);
+    for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < rows;
+         r += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float gy[8], xp[8], gx[8];
+        *reinterpret_cast<float4*>(&gy[0]) = *reinterpret_cast<const float4*>(g_x + r * 8);
+        *reinterpret_cast<float4*>(&gy[4]) = *reinterpret_cast<const float4*>(g_x + r * 8 + 4);
+        *reinterpret_cast<float4*>(&xp[0]) = *reinterpret_cast<const float4*>(x_pre + r * 8);
+        *reinterpret_cast<float4*>(&xp[4]) = *reinterpret_cast<const float4*>(x_pre + r * 8 + 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gx[j] = gy[j];
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < C; ++i) s = fmaf(wr[i * C + j], gy[BASE + i], s);
+            gx[BASE + j] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < C; ++i)
+#pragma unroll
+            for (int j = 0; j < C; ++j) acc[i * C + j] = fmaf(gy[BASE + i], xp[BASE + j], acc[i * C + j]);
+        *reinterpret_cast<float4*>(g_x + r * 8) = *reinterpret_cast<const float4*>(&gx[0]);
+        *reinterpret_cast<float4*>(g_x + r * 8 + 4) = *reinterpret_cast<const float4*>(&gx[4]);
+    }
+#pragma unroll
+    for (int i = 0; i < C; ++i)
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            float v = acc[i * C + j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&s_dw[i * 8 + j], v);
+        }
+    __syncthreads();
+    if (threadIdx.x < 64 && s_dw[threadIdx.x] != 0.f) atomicAdd(dw + threadIdx.x, s_dw[threadIdx.x]);
+}
+
+int mix_bwd(float* g_x, const float* x_pre, const float* w, float* dw, long long rows, int C, cudaStream_t stream) {
+    WGB_REQUIRE(g_x && x_pre && w && dw, "null pointer");
+    WGB_REQUIRE(rows > 0 && C >= 2 && C <= 8 && C % 2 == 0, "C must be 2, 4, 6 or 8 (got %d)", C);
+    WGB_CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(float) * 64, stream));
+    long long blocks = (rows + 127) / 128;
+    if (blocks > 296) blocks = 296;
+    const unsigned g = static_cast<unsigned>(blocks);
+    switch (C) {
+        case 2: mix_bwd_kernel<2><<<g, 128, 0, stream>>>(g_x, x_pre, w, dw, rows); break;
+        case 4: mix_bwd_kernel<4><<<g, 128, 0, stream>>>(g_x, x_pre, w, dw, rows); break;
+        case 6: mix_bwd_kernel<6><<<g, 128, 0, stream>>>(g_x, x_pre, w, dw, rows); break;
+        default: mix_bwd_kernel<8><<<g, 128, 0, stream>>>(g_x, x_pre, w, dw, rows); break;
+    }
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ upsample backward
+// cond[b, t, m*8 + g] = up[b, m, 8t + g], up[b, m, n] = bias[m] + sum_{ci, f} mel[b, ci, f] w[ci, m, n - stride f]
+// (ConvTranspose1d, glow.py:183-185,213-221).  Given g_cond fp32 [B, T, ld] (ld >= n_mel*8):
+//   dw[ci][m][k] = sum_{b,f} mel[b,ci,f] g_up[b, m, stride f + k],    db[m] = sum_{b,n} g_up[b,m,n]
+// One block per (m, 128 taps k); each thread owns one k and all ci (<= 80) accumulators.
+constexpr int kUpMaxMel = 80;
+__global__ void upsample_wgrad_kernel(const float* __restrict__ mel, const float* __restrict__ g_cond, float* __restrict__ dw,
+                                      float* __restrict__ db, int batch, int n_mel, int frames, int T, int ld, int ksize,
+                                      int stride, int n_group) {
+    extern __shared__ float s_mel[];                           // [frames chunk][n_mel]
+    const int m = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc[kUpMaxMel];
+#pragma unroll
+    for (int i = 0; i < kUpMaxMel; ++i) acc[i] = 0.f;
+    float bsum = 0.f;
+    const int n_total = T * n_group;
+    constexpr int kFChunk = 32;
+    for (int b = blockIdx.z; b < batch; b += gridDim.z)
+    for (int f0 = 0; f0 < frames; f0 += kFChunk) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kFChunk * n_mel; i += blockDim.x) {
+            const int ff = i / n_mel, ci = i - ff * n_mel;
+            s_mel[i] = (f0 + ff < frames) ? mel[(static_cast<size_t>(b) * n_mel + ci) * frames + f0 + ff] : 0.f;
+        }
+        __syncthreads();
+        for (int ff = 0; ff < kFChunk && f0 + ff < frames; ++ff) {
+            const int n = stride * (f0 + ff) + k;
+            if (k < ksize && n < n_total) {
+                const float g = g_cond[(static_cast<size_t>(b) * T + n / n_group) * ld + m * n_group + n % n_group];
+                if (k < stride) bsum += g;                     // every sample n is counted once (k < stride covers n = stride f + k)
+                const float* sm = s_mel + ff * n_mel;
+#pragma unroll
+                for (int ci = 0; ci < kUpMaxMel; ++ci)
+                    if (ci < n_mel) acc[ci] = fmaf(sm[ci], g, acc[ci]);
+            }
+        }
+    }
+    if (k < ksize) {
+        for (int ci = 0; ci < n_mel; ++ci) atomicAdd(dw + (static_cast<size_t>(ci) * n_mel + m) * ksize + k, acc[ci]);
+    }
+    // db: block reduction of bsum
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+    if ((threadIdx.x & 31) == 0 && bsum != 0.f) atomicAdd(db + m, bsum);
+}
+
+int upsample_wgrad(const float* mel, const float* g_cond, float* dw, float* db, int batch, int n_mel, int frames, int T,
+                   int ld, int ksize, int stride, int n_group, cudaStream_t stream) {
+    WGB_REQUIRE(mel && g_cond && dw && db, "null pointer");
+    WGB_REQUIRE(n_mel >= 1 && n_mel <= kUpMaxMel, "n_mel (%d) must be in 1..%d", n_mel, kUpMaxMel);
+    WGB_REQUIRE(batch > 0 && frames > 0 && T > 0 && ld >= n_mel * n_group && ksize > 0 && stride > 0, "bad shape");
+    WGB_CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(float) * n_mel * n_mel * ksize, stream));
+    WGB_CUDA_TRY(cudaMemsetAsync(db, 0, sizeof(float) * n_mel, stream));
+    dim3 grid((ksize + 127) / 128, n_mel, batch < 4 ? batch : 4);
+    upsample_wgrad_kernel<<<grid, 128, 32 * n_mel * sizeof(float), stream>>>(mel, g_cond, dw, db, batch, n_mel, frames, T, ld,
+                                                                             ksize, stride, n_group);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ Adam
+// torch.optim.Adam (train.py:79; no weight decay, no amsgrad) over one flat fp32 buffer:
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+__global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                            long long n4, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+        float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float gr = ga[e] * grad_scale;
+            ma[e] = b1 * ma[e] + (1.f - b1) * gr;
+            va[e] = b2 * va[e] + (1.f - b2) * gr * gr;
+            const float denom = sqrtf(va[e]) / bc2_sqrt + eps;
+            pa[e] -= (lr / bc1) * (ma[e] / denom);
+        }
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+}
+
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+              int step, float grad_scale, cudaStream_t stream) {
+    WGB_REQUIRE(p && g && m && v, "null pointer");
+    WGB_REQUIRE(n > 0 && n % 4 == 0, "n (%lld) must be a positive multiple of 4 (pad the flat buffer)", n);
+    WGB_REQUIRE(step >= 1, "step counts from 1");
+    const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+    const float bc2 = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    adam_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g),
+                                                                   reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
+                                                                   n / 4, lr, beta1, beta2, eps, bc1, bc2, grad_scale);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+}  // namespace wgb

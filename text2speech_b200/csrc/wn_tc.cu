@@ -67,6 +67,8 @@ struct TcParams {
     int seg_shift0, seg_dshift;   // PLAIN  segment s reads A rows t + seg_shift0 + s*seg_dshift (conv taps; rows outside
                                   //        [0,T) are zero-filled by TMA = zero padding); 0, 0 for a plain GEMM
     int act;                      // PLAIN  DIR 0/1 epilogue: 0 none, 1 tanh, 2 relu
+    const void* res;              // PLAIN  DIR 0/1: optional [B,T,N] tensor (fp32 for DIR 0, bf16 for DIR 1) added to the
+                                  //        result before the store; may alias c_out (accumulate / residual update in place)
 };
 
 // Shared-memory carve-up (offsets from a 1024 B aligned base): [TMA ring][mode extra][barriers].
@@ -429,6 +431,29 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                             if (p.act == 1) f[j] = tanhf(f[j]);
                             else if (p.act == 2) f[j] = fmaxf(f[j], 0.f);
                         }
+                        if (p.res && live) {
+                            if constexpr (DIR == 0) {
+                                const float4* r4 = reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + off + ch * 32);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 r = r4[j];
+                                    f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+                                }
+                            } else {
+                                const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res) + off + ch * 32);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint4 r = r4[j];
+                                    const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
+                                        f[8 * j + 2 * e] += __low2float(h2);
+                                        f[8 * j + 2 * e + 1] += __high2float(h2);
+                                    }
+                                }
+                            }
+                        }
                         if (live) {
                             if constexpr (DIR == 0) {
                                 float4* d4 = reinterpret_cast<float4*>(static_cast<float*>(p.c_out) + off + ch * 32);
@@ -641,6 +666,32 @@ int tc_conv1d_taps(const void* a, const void* w, const float* bias, void* c, int
     if (int e = act_map(&ma0, a, C, T, batch)) return e;
     if (int e = weight_map(&mb, w, N, taps * C)) return e;
     return out_bf16 ? launch<MODE_PLAIN, 0, 1>(ma0, ma0, mb, ma0, p, stream) : launch<MODE_PLAIN, 0, 0>(ma0, ma0, mb, ma0, p, stream);
+}
+
+// General segmented GEMM behind the backward pass of the WN layers (training direction):
+//   out[b,t,n] = act(bias[n] + sum_s sum_c W[n][s*C + c] A_s[b, t + shift0 + s*dshift, c]) + res[b,t,n]
+// A_s = a1 when bit s of seg_mask is set, else a0 (both bf16 [B,T,C], C % 64 == 0); W bf16 [N][n_seg*C] (N % 256 == 0);
+// out / res fp32 (out_bf16 = 0) or bf16 [B,T,N]; res may be null or alias out.  Uses: data gradient of the dilated
+// conv (taps as shifted segments + residual stream), of res_skip (segments [g_h | g_skip]), of cond (accumulating).
+int tc_gemm_seg(const void* a0, const void* a1, int n_seg, int seg_mask, const void* w, const float* bias, const void* res,
+                void* c, int out_bf16, int batch, int T, int N, int C, int shift0, int dshift, int act,
+                cudaStream_t stream) {
+    WGB_REQUIRE(a0 && w && c, "null pointer");
+    WGB_REQUIRE(n_seg >= 1 && n_seg <= 31, "n_seg must be in 1..31 (got %d)", n_seg);
+    WGB_REQUIRE(seg_mask == 0 || a1 != nullptr, "seg_mask selects a1, which is null");
+    WGB_REQUIRE(N > 0 && N % kBlockN == 0 && C > 0 && C % kBlockK == 0, "N must be a multiple of 256 and C of 64 (N=%d C=%d)", N, C);
+    WGB_REQUIRE(act >= 0 && act <= 2, "act must be 0 (none), 1 (tanh) or 2 (relu)");
+    TcParams p{};
+    if (int e = fill_common(p, batch, T)) return e;
+    p.n_pass = N / kBlockN; p.ppi = 1; p.n_chunks = n_seg * C / kBlockK;
+    p.bias = bias; p.c_out = c; p.n_total = N; p.res = res;
+    p.seg_chunks = C / kBlockK; p.seg_mask = seg_mask;
+    p.seg_shift0 = shift0; p.seg_dshift = dshift; p.act = act;
+    CUtensorMap ma0, ma1, mb;
+    if (int e = act_map(&ma0, a0, C, T, batch)) return e;
+    if (int e = act_map(&ma1, a1 ? a1 : a0, C, T, batch)) return e;
+    if (int e = weight_map(&mb, w, N, n_seg * C)) return e;
+    return out_bf16 ? launch<MODE_PLAIN, 0, 1>(ma0, ma1, mb, ma0, p, stream) : launch<MODE_PLAIN, 0, 0>(ma0, ma1, mb, ma0, p, stream);
 }
 
 // Split-bf16 ("3x bf16") GEMM for fp32-grade accuracy on the tensor cores:

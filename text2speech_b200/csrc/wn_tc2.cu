@@ -88,6 +88,8 @@ struct Params {
     int skip_first;
     const float* bias;            // GATE [1024] packed order, RES [512]
     __nv_bfloat16* acts_out;      // GATE [B,T,512]
+    __nv_bfloat16* ts_out;        // GATE, training forward (optional): [B,T,1024] = tanh half | sigmoid half, original
+                                  //       channel order (what the gate's backward needs; glow.py:33-40 under autograd)
     const float* w_end;           // SKIP_END [512][8] fp32 (rows >= 2*n_half zero)
     const float* b_end;           // SKIP_END [8] (skip biases folded in)
     float* x;                     // SKIP_END flow state [B,T,8]
@@ -495,6 +497,36 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             for (int j = 0; j < 4; ++j)
                                 d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                         }
+                        if constexpr (MODE == GATE) {
+                            if (p.ts_out != nullptr && live) {     // training forward: keep tanh and sigmoid for the backward
+                                __nv_bfloat16* tdst = p.ts_out + grow * (2 * kNCh) + pass * 128 + ch * 32;
+#pragma unroll
+                                for (int half = 0; half < 2; ++half) {
+                                    uint32_t pk[16];
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) {
+                                        float v0, v1;
+                                        if (half == 0) {
+                                            const float4 bt = bt4[ch * 8 + (j >> 1)];
+                                            const float b0 = (j & 1) ? bt.z : bt.x, b1 = (j & 1) ? bt.w : bt.y;
+                                            v0 = tanh_approx(__uint_as_float(vt[2 * j]) + b0);
+                                            v1 = tanh_approx(__uint_as_float(vt[2 * j + 1]) + b1);
+                                        } else {
+                                            const float4 bs = bs4[ch * 8 + (j >> 1)];
+                                            const float b0 = (j & 1) ? bs.z : bs.x, b1 = (j & 1) ? bs.w : bs.y;
+                                            v0 = fmaf(tanh_approx(fmaf(__uint_as_float(vs[2 * j]), 0.5f, b0)), 0.5f, 0.5f);
+                                            v1 = fmaf(tanh_approx(fmaf(__uint_as_float(vs[2 * j + 1]), 0.5f, b1)), 0.5f, 0.5f);
+                                        }
+                                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                                        pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                                    }
+                                    uint4* t4 = reinterpret_cast<uint4*>(tdst + half * kNCh);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        t4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                                }
+                            }
+                        }
                     }
                     if constexpr (MODE == GATE_MEL_ACC) {
                         if (live) {
@@ -713,15 +745,16 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
 
 }  // namespace tc2
 
-int tc2_wn_gate(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts, int batch, int T,
-                int dilation, cudaStream_t stream) {
+// ts (optional, training forward): bf16 [B,T,1024] receiving tanh | sigmoid of the pre-activations (original order)
+int tc2_wn_gate(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts, void* ts, int batch,
+                int T, int dilation, cudaStream_t stream) {
     using namespace tc2;
     WGB_REQUIRE(h && cond && w_packed && bias && acts, "null pointer");
     WGB_REQUIRE(dilation >= 1, "dilation must be >= 1");
     Params p{};
     if (int e = fill_common(p, batch, T)) return e;
     p.n_pass = 4; p.ppi = 1; p.n_chunks = (3 * kNCh + kNCond) / kBlockK; p.dilation = dilation;
-    p.bias = bias; p.acts_out = static_cast<__nv_bfloat16*>(acts);
+    p.bias = bias; p.acts_out = static_cast<__nv_bfloat16*>(acts); p.ts_out = static_cast<__nv_bfloat16*>(ts);
     CUtensorMap mh, mc, mw;
     if (int e = act_map(&mh, h, kNCh, T, batch)) return e;
     if (int e = act_map(&mc, cond, kNCond, T, batch)) return e;

@@ -206,6 +206,11 @@ class WaveGlow(torch.nn.Module):
         spect, audio = forward_input
         if not spect.is_cuda:
             raise RuntimeError("WaveGlow.forward needs CUDA tensors on a B200; there is no CPU fallback")
+        if self.training and torch.is_grad_enabled():
+            # training direction (waveglow/train.py:116-124): the same outputs, wired into autograd so that
+            # criterion(outputs).backward() fills every parameter's .grad through this package's backward kernels
+            from . import training
+            return training.forward_autograd(self, spect, audio)
         with torch.cuda.device(spect.device), torch.no_grad():      # kernels launch on the tensors' device / its current stream
             pk = self._packed(spect.device)
             return engine.forward(pk, spect.float().contiguous(), audio.float().contiguous())

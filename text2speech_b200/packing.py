@@ -152,7 +152,7 @@ def pack_upsample(w: Tensor, b: Tensor, n_group: int, ld_tap: int):
     stride = k // taps
     tt = stride // n_group
     w5 = w.reshape(c_in, c_out, taps, tt, n_group)               # k = j*stride + tt*n_group + g
-    packed = torch.zeros(tt, c_out, n_group, taps, ld_tap, dtype=torch.float32)
+    packed = torch.zeros(tt, c_out, n_group, taps, ld_tap, dtype=torch.float32, device=w.device)
     packed[..., :c_in] = w5.permute(3, 1, 4, 2, 0)
     bias_col = b.reshape(1, c_out, 1).expand(tt, c_out, n_group).reshape(-1).contiguous()
     return packed.reshape(tt * c_out * n_group, taps * ld_tap).contiguous(), bias_col.float()

@@ -1,0 +1,383 @@
+"""Training direction of the vocoder (reference waveglow/train.py:55-56,72,116-124).
+
+``model.train(); outputs = model((mel, audio)); loss = criterion(outputs); loss.backward(); optimizer.step()`` works on
+the drop-in ``WaveGlow`` exactly as on the reference: ``WaveGlow.forward`` routes here whenever autograd is recording,
+and returns tensors wired into one ``torch.autograd.Function`` whose forward and backward are sequences of C-ABI
+kernel calls (no torch op touches an activation):
+
+  forward   the inference kernels of engine.py in their un-composed form (tcgen05 gate / residual / skip GEMMs), the
+            gate kernel additionally storing tanh | sigmoid; every layer's h, acts and (tanh | sigmoid) are kept in
+            bf16, the flow state before / after each 1x1 conv in fp32  (~2.1 GB per flow at 32 x 16000 samples)
+  backward  per flow, last to first: coupling + WN.end (wgb_coupling_bwd), then per layer, last to first:
+              g_acts  = [g_h | g_skip] W_rs          wgb_tc_gemm_seg   (tcgen05, K = 1024)
+              g_in    = gate'(g_acts, tanh, sigmoid) wgb_gate_bwd
+              g_h     = g_h + conv_in^T(g_in)        wgb_tc_gemm_seg   (three shifted taps + residual, K = 3072)
+              g_cond += g_in W_cond                  wgb_tc_gemm_seg   (fp32 accumulate)
+              dW_in, dW_cond, dW_res                 wgb_tc_wgrad      (tcgen05, MN-major operands, K = B*T)
+              biases, WN.end / skip / start weights  wgb_colsum_* / wgb_skinny_wgrad (+ 8 x 512 parameter algebra)
+            then WN.start (wgb_start_bwd), the 1x1 conv (wgb_mix_bwd) and finally the upsampler (wgb_upsample_wgrad).
+
+Weight norm (g, v) and log|det W| stay ordinary torch autograd on parameter-sized tensors around the Function, so the
+``.grad`` of every reference parameter (weight_g / weight_v / bias / convinv weight / upsample) is filled.
+``FusedAdam`` is train.py:79's optimiser as one kernel over a flat buffer; ``allreduce_gradients`` is the flat-bucket
+data-parallel reduction of waveglow/distributed.py:90-142.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .packing import gate_row_order, pack_upsample
+
+Tensor = torch.Tensor
+N_CH, N_COND, N_LAYERS = 512, 640, 8
+N_COND_PAD = 768          # g_cond leading dimension: the cond dgrad GEMM writes 256-column passes
+
+
+# ------------------------------------------------------------------------------------------------ parameters
+def _effective(conv: torch.nn.Module) -> Tensor:
+    """conv.weight with weight norm applied by autograd-visible torch ops (glow.py:123,138,142,151)."""
+    if hasattr(conv, "weight_g"):
+        return torch._weight_norm(conv.weight_v, conv.weight_g, 0)
+    return conv.weight
+
+
+def effective_weights(model) -> Tuple[List[str], List[Tensor]]:
+    """Flat (names, tensors) of every effective weight / bias of the model in the order ``_Flow`` expects."""
+    names, tensors = [], []
+
+    def add(name, t):
+        names.append(name)
+        tensors.append(t)
+
+    add("upsample.weight", model.upsample.weight)
+    add("upsample.bias", model.upsample.bias)
+    for k, wn in enumerate(model.WN):
+        add(f"convinv.{k}.conv.weight", model.convinv[k].conv.weight)
+        add(f"WN.{k}.start.weight", _effective(wn.start))
+        add(f"WN.{k}.start.bias", wn.start.bias)
+        for i in range(wn.n_layers):
+            add(f"WN.{k}.in_layers.{i}.weight", _effective(wn.in_layers[i]))
+            add(f"WN.{k}.in_layers.{i}.bias", wn.in_layers[i].bias)
+            add(f"WN.{k}.cond_layers.{i}.weight", _effective(wn.cond_layers[i]))
+            add(f"WN.{k}.cond_layers.{i}.bias", wn.cond_layers[i].bias)
+            add(f"WN.{k}.res_skip_layers.{i}.weight", _effective(wn.res_skip_layers[i]))
+            add(f"WN.{k}.res_skip_layers.{i}.bias", wn.res_skip_layers[i].bias)
+        add(f"WN.{k}.end.weight", wn.end.weight)
+        add(f"WN.{k}.end.bias", wn.end.bias)
+    return names, tensors
+
+
+class _UpsampleOperands:
+    """The attributes engine.upsample_cond reads from a PackedWaveGlow, built from live weights on the device."""
+
+    def __init__(self, w_up: Tensor, b_up: Tensor, n_group: int):
+        self.mode = "bf16"
+        self.n_group = n_group
+        self.n_mel = w_up.shape[0]
+        self.up_taps = 4
+        self.up_stride = w_up.shape[2] // self.up_taps
+        self.up_ld_tap = ((self.n_mel + 63) // 64) * 64
+        w, b = pack_upsample(w_up, b_up, n_group, self.up_ld_tap)
+        self.w_up, self.b_up = w.to(torch.bfloat16), b
+
+
+def _pack_flow(st: Dict[str, Tensor], k: int) -> Dict[str, object]:
+    """bf16 / fp32 kernel operands of flow k from the live fp32 weights (all on the device; runs every step)."""
+    p = f"WN.{k}."
+    dev = st[p + "start.weight"].device
+    bf = torch.bfloat16
+    order = gate_row_order(N_CH).to(dev)
+    f: Dict[str, object] = {}
+    w_end = st[p + "end.weight"][:, :, 0]                                   # [2 n_half, 512]
+    n_half = w_end.shape[0] // 2
+    f["n_half"] = n_half
+    f["w_start"] = st[p + "start.weight"][:, :, 0].contiguous()             # [512, n_half]
+    f["b_start"] = st[p + "start.bias"].contiguous()
+    mix = torch.zeros(8, 8, device=dev)
+    c = 2 * n_half
+    mix[:c, :c] = st[f"convinv.{k}.conv.weight"][:, :, 0]
+    f["w_mix"] = mix
+    w_in = torch.stack([st[p + f"in_layers.{i}.weight"] for i in range(N_LAYERS)])              # [8, 1024, 512, 3]
+    w_cond = torch.stack([st[p + f"cond_layers.{i}.weight"][:, :, 0] for i in range(N_LAYERS)])  # [8, 1024, 640]
+    b_gate = torch.stack([st[p + f"in_layers.{i}.bias"] + st[p + f"cond_layers.{i}.bias"] for i in range(N_LAYERS)])
+    w_gate = torch.cat([w_in.permute(0, 1, 3, 2).reshape(N_LAYERS, 2 * N_CH, 3 * N_CH), w_cond], dim=2)
+    f["w_gate"] = w_gate[:, order].to(bf).contiguous()                      # [8, 1024, 2176] packed row order
+    f["b_gate"] = b_gate[:, order].contiguous()
+    # data-gradient operands: W^T with the taps mirrored (tap' = 2 - tap)
+    f["wt_in"] = w_in.flip(3).permute(0, 2, 3, 1).reshape(N_LAYERS, N_CH, 3 * 2 * N_CH).to(bf).contiguous()
+    wt_cond = torch.zeros(N_LAYERS, N_COND_PAD, 2 * N_CH, device=dev, dtype=bf)
+    wt_cond[:, :N_COND] = w_cond.transpose(1, 2)
+    f["wt_cond"] = wt_cond
+    w_rs = [st[p + f"res_skip_layers.{i}.weight"][:, :, 0] for i in range(N_LAYERS)]             # [1024|512, 512]
+    b_rs = [st[p + f"res_skip_layers.{i}.bias"] for i in range(N_LAYERS)]
+    f["w_res"] = [w_rs[i][:N_CH].to(bf).contiguous() for i in range(N_LAYERS - 1)]
+    f["b_res"] = [b_rs[i][:N_CH].contiguous() for i in range(N_LAYERS - 1)]
+    f["wt_rs"] = [w_rs[i].t().to(bf).contiguous() for i in range(N_LAYERS)]                      # [512, 1024|512]
+    w_skip = [w_rs[i][N_CH:] if i < N_LAYERS - 1 else w_rs[i] for i in range(N_LAYERS)]          # [512, 512] each
+    b_skip = sum(b_rs[i][N_CH:] if i < N_LAYERS - 1 else b_rs[i] for i in range(N_LAYERS))
+    f["w_skip_f32"] = w_skip
+    f["b_skip_total"] = b_skip
+    f["w_skip"] = torch.cat(w_skip, dim=1).to(bf).contiguous()              # [512, 8*512]
+    w_end_t = torch.zeros(N_CH, 8, device=dev)
+    w_end_t[:, :c] = w_end.t()
+    f["w_end_t"] = w_end_t
+    f["w_end"] = w_end
+    b_end = torch.zeros(8, device=dev)
+    b_end[:c] = st[p + "end.bias"] + w_end @ b_skip
+    f["b_end"] = b_end
+    return f
+
+
+# ------------------------------------------------------------------------------------------------ forward
+class _Saved:
+    pass
+
+
+def _forward(st: Dict[str, Tensor], n_flows: int, n_group: int, mel: Tensor, audio: Tensor):
+    from . import engine
+    b, _, frames = mel.shape
+    n = audio.shape[1]
+    s = _lib.stream_ptr()
+    up = _UpsampleOperands(st["upsample.weight"], st["upsample.bias"], n_group)
+    up_len = (frames - 1) * up.up_stride + up.up_stride * up.up_taps
+    assert up_len >= n, "upsampled spectrogram shorter than audio"            # glow.py:216
+    t = n // n_group
+    if t > frames * up.up_stride // n_group:
+        raise RuntimeError("audio longer than 256 * frames is not supported by the regrouped upsample GEMM")
+    cond = engine.upsample_cond(up, mel)
+    if cond.shape[1] > t:
+        cond = cond[:, :t].contiguous()                                       # glow.py:217-218
+    dev = mel.device
+    bf = torch.bfloat16
+    x = audio[:, : t * n_group].reshape(b, t, n_group).float().contiguous().clone()
+    sv = _Saved()
+    sv.b, sv.t, sv.frames, sv.cond, sv.mel, sv.up = b, t, frames, cond, mel, up
+    sv.flows, sv.packs = [], []
+    log_s_list = []
+    for k in range(n_flows):
+        f = _pack_flow(st, k)
+        nh = f["n_half"]
+        fs = _Saved()
+        fs.x_pre = x.clone()
+        _lib.call("wgb_flow_mix", x, f["w_mix"], b * t, 2 * nh, s)
+        fs.x_mix = x.clone()
+        fs.h = torch.empty((N_LAYERS, b, t, N_CH), device=dev, dtype=bf)
+        fs.acts = torch.empty((N_LAYERS, b, t, N_CH), device=dev, dtype=bf)
+        fs.ts = torch.empty((N_LAYERS, b, t, 2 * N_CH), device=dev, dtype=bf)
+        _lib.call("wgb_wn_start_padded", x, f["w_start"], f["b_start"], fs.h[0], 1, b, t, t, N_CH, nh, s)
+        for i in range(N_LAYERS):
+            _lib.call("wgb_tc2_wn_gate_train", fs.h[i], cond, f["w_gate"][i], f["b_gate"][i], fs.acts[i], fs.ts[i], b, t,
+                      2 ** i, s)
+            if i < N_LAYERS - 1:
+                _lib.call("wgb_tc2_wn_res", fs.acts[i], f["w_res"][i], f["b_res"][i], fs.h[i], fs.h[i + 1], b, t, t,
+                          None, None, 0, s)
+        fs.log_s = torch.empty((b, nh, t), device=dev, dtype=torch.float32)
+        _lib.call("wgb_tc2_wn_skip_end", fs.acts, N_LAYERS, f["w_skip"], f["w_end_t"], f["b_end"], x, None, fs.log_s, b, t,
+                  nh, 1, None, None, 0, None, 0, s)
+        log_s_list.append(fs.log_s)
+        sv.flows.append(fs)
+        sv.packs.append(f)
+    z = torch.empty((b, n_group, t), device=dev, dtype=torch.float32)
+    _lib.call("wgb_flow_to_z", x, z, b, t, s)
+    return z, log_s_list, sv
+
+
+# ------------------------------------------------------------------------------------------------ backward
+def _backward(st: Dict[str, Tensor], sv: _Saved, n_flows: int, n_group: int, g_z: Tensor,
+              g_log_s: Sequence[Optional[Tensor]]) -> Dict[str, Tensor]:
+    b, t, cond = sv.b, sv.t, sv.cond
+    rows = b * t
+    dev = cond.device
+    s = _lib.stream_ptr()
+    bf, f32 = torch.bfloat16, torch.float32
+    grads: Dict[str, Tensor] = {}
+    g_x = g_z.permute(0, 2, 1).contiguous().float()                            # [B, T, 8], the layout of x
+    g_cond = torch.zeros((b, t, N_COND_PAD), device=dev, dtype=f32)
+    g_out = torch.empty((rows, 8), device=dev, dtype=f32)
+    g_skip = torch.empty((b, t, N_CH), device=dev, dtype=bf)
+    g_h = torch.empty((b, t, N_CH), device=dev, dtype=bf)
+    g_acts = torch.empty((b, t, N_CH), device=dev, dtype=bf)
+    for k in reversed(range(n_flows)):
+        f, fs = sv.packs[k], sv.flows[k]
+        p = f"WN.{k}."
+        nh = f["n_half"]
+        c = 2 * nh
+        base = 8 - c
+        gls = g_log_s[k]
+        gls = None if gls is None else gls.float().contiguous()
+        _lib.call("wgb_coupling_bwd", g_x, fs.x_mix, fs.log_s, gls, f["w_end_t"], g_out, g_skip, b, t, N_CH, nh, s)
+        g_out_sum = torch.empty(8, device=dev, dtype=f32)
+        _lib.call("wgb_colsum8_f32", g_out, g_out_sum, rows, 0, s)
+        grads[p + "end.bias"] = g_out_sum[:c].clone()
+        w_end = f["w_end"]                                                     # [c, 512]
+        d_w_end = torch.outer(g_out_sum[:c], f["b_skip_total"])
+        db_skip = w_end.t() @ g_out_sum[:c]                                    # the same for every layer's skip bias
+        for i in reversed(range(N_LAYERS)):
+            d = 2 ** i
+            last = i == N_LAYERS - 1
+            # skip rows of res_skip and WN.end through the 8 x 512 product G_i = g_out^T acts_i
+            g_i = torch.empty((8, N_CH), device=dev, dtype=f32)
+            _lib.call("wgb_skinny_wgrad", g_out, fs.acts[i], g_i, rows, N_CH, 0, s)
+            d_w_end = d_w_end + g_i[:c] @ f["w_skip_f32"][i].t()
+            d_w_skip = w_end.t() @ g_i[:c]                                     # [512, 512]
+            if last:
+                _lib.call("wgb_tc_gemm_seg", g_skip, None, 1, 0, f["wt_rs"][i], None, None, g_acts, 1, b, t, N_CH, N_CH,
+                          0, 0, 0, s)
+                grads[p + f"res_skip_layers.{i}.weight"] = d_w_skip.unsqueeze(2)
+                grads[p + f"res_skip_layers.{i}.bias"] = db_skip.clone()
+            else:
+                _lib.call("wgb_tc_gemm_seg", g_h, g_skip, 2, 0b10, f["wt_rs"][i], None, None, g_acts, 1, b, t, N_CH, N_CH,
+                          0, 0, 0, s)
+                d_w_res = torch.empty((1, N_CH, N_CH), device=dev, dtype=f32)
+                _lib.call("wgb_tc_wgrad", g_h, fs.acts[i], d_w_res, b, t, N_CH, N_CH, 1, 1, 0, s)
+                db_res = torch.empty(N_CH, device=dev, dtype=f32)
+                _lib.call("wgb_colsum_bf16", g_h, db_res, rows, N_CH, 0, s)
+                grads[p + f"res_skip_layers.{i}.weight"] = torch.cat([d_w_res[0], d_w_skip], dim=0).unsqueeze(2)
+                grads[p + f"res_skip_layers.{i}.bias"] = torch.cat([db_res, db_skip])
+            g_in = fs.ts[i]                                                    # (tanh | sigmoid) -> gradient, in place
+            _lib.call("wgb_gate_bwd", g_acts, g_in, rows, N_CH, s)
+            db_in = torch.empty(2 * N_CH, device=dev, dtype=f32)
+            _lib.call("wgb_colsum_bf16", g_in, db_in, rows, 2 * N_CH, 0, s)
+            grads[p + f"in_layers.{i}.bias"] = db_in
+            grads[p + f"cond_layers.{i}.bias"] = db_in.clone()
+            d_w_in = torch.empty((3, 2 * N_CH, N_CH), device=dev, dtype=f32)
+            _lib.call("wgb_tc_wgrad", g_in, fs.h[i], d_w_in, b, t, 2 * N_CH, N_CH, 3, d, 0, s)
+            grads[p + f"in_layers.{i}.weight"] = d_w_in.permute(1, 2, 0).contiguous()
+            d_w_cond = torch.empty((1, 2 * N_CH, N_COND), device=dev, dtype=f32)
+            _lib.call("wgb_tc_wgrad", g_in, cond, d_w_cond, b, t, 2 * N_CH, N_COND, 1, 1, 0, s)
+            grads[p + f"cond_layers.{i}.weight"] = d_w_cond[0].unsqueeze(2)
+            _lib.call("wgb_tc_gemm_seg", g_in, None, 1, 0, f["wt_cond"][i], None, g_cond, g_cond, 0, b, t, N_COND_PAD,
+                      2 * N_CH, 0, 0, 0, s)
+            _lib.call("wgb_tc_gemm_seg", g_in, None, 3, 0, f["wt_in"][i], None, None if last else g_h, g_h, 1, b, t, N_CH,
+                      2 * N_CH, -d, d, 0, s)
+        grads[p + "end.weight"] = d_w_end.unsqueeze(2)
+        # WN.start (g_h is now the gradient of h_0)
+        db_start = torch.empty(N_CH, device=dev, dtype=f32)
+        _lib.call("wgb_colsum_bf16", g_h, db_start, rows, N_CH, 0, s)
+        grads[p + "start.bias"] = db_start
+        d_start = torch.empty((8, N_CH), device=dev, dtype=f32)
+        _lib.call("wgb_skinny_wgrad", fs.x_mix, g_h, d_start, rows, N_CH, 0, s)
+        grads[p + "start.weight"] = d_start[base: base + nh].t().contiguous().unsqueeze(2)
+        _lib.call("wgb_start_bwd", g_x, g_h, f["w_start"], rows, N_CH, nh, s)
+        # invertible 1x1 conv
+        d_mix = torch.empty((8, 8), device=dev, dtype=f32)
+        _lib.call("wgb_mix_bwd", g_x, fs.x_pre, f["w_mix"], d_mix, rows, c, s)
+        grads[f"convinv.{k}.conv.weight"] = d_mix[:c, :c].contiguous().unsqueeze(2)
+        fs.h = fs.acts = fs.ts = None                                          # release this flow's activations
+    up = sv.up
+    ksize = up.up_stride * up.up_taps
+    d_up = torch.empty((up.n_mel, up.n_mel, ksize), device=dev, dtype=f32)
+    db_up = torch.empty(up.n_mel, device=dev, dtype=f32)
+    _lib.call("wgb_upsample_wgrad", sv.mel, g_cond, d_up, db_up, b, up.n_mel, sv.frames, t, N_COND_PAD, ksize, up.up_stride,
+              n_group, s)
+    grads["upsample.weight"] = d_up
+    grads["upsample.bias"] = db_up
+    return grads
+
+
+class _Flow(torch.autograd.Function):
+    """(mel, audio, *effective weights) -> (z, *log_s): the whole flow as one autograd node."""
+
+    @staticmethod
+    def forward(ctx, names, n_flows, n_group, mel, audio, *weights):
+        st = {n: w.detach().float() for n, w in zip(names, weights)}
+        with torch.cuda.device(mel.device):
+            z, log_s_list, sv = _forward(st, n_flows, n_group, mel.detach().float().contiguous(),
+                                         audio.detach().float().contiguous())
+        ctx.names, ctx.n_flows, ctx.n_group, ctx.st, ctx.sv = names, n_flows, n_group, st, sv
+        return (z, *log_s_list)
+
+    @staticmethod
+    def backward(ctx, g_z, *g_log_s):
+        sv = ctx.sv
+        if sv is None:
+            raise RuntimeError("the flow's saved activations were already consumed (backward twice?)")
+        if g_z is None:
+            g_z = torch.zeros((sv.b, ctx.n_group, sv.t), device=sv.cond.device)
+        with torch.cuda.device(sv.cond.device):
+            grads = _backward(ctx.st, sv, ctx.n_flows, ctx.n_group, g_z, g_log_s)
+        ctx.sv = None
+        out = []
+        for n, need in zip(ctx.names, ctx.needs_input_grad[5:]):
+            out.append(grads[n] if need else None)
+        return (None, None, None, None, None, *out)
+
+
+def forward_autograd(model, spect: Tensor, audio: Tensor):
+    """WaveGlow.forward under autograd (glow.py:207-249): returns (z, log_s_list, log_det_W_list) whose backward fills
+    the ``.grad`` of every model parameter."""
+    if model.mode != "bf16":
+        raise RuntimeError("the training direction exists for the bf16 tensor-core path only")
+    model._check_supported()
+    _lib.require_b200(spect.device)
+    names, weights = effective_weights(model)
+    outs = _Flow.apply(names, model.n_flows, model.n_group, spect, audio, *weights)
+    z, log_s_list = outs[0], list(outs[1:])
+    bt = z.shape[0] * z.shape[2]
+    log_det = [bt * torch.logdet(model.convinv[k].conv.weight.squeeze(-1).float()) for k in range(model.n_flows)]   # glow.py:100
+    return z, log_s_list, log_det
+
+
+# ------------------------------------------------------------------------------------------------ optimiser / DP
+class FusedAdam:
+    """torch.optim.Adam(model.parameters(), lr) of train.py:79 as ONE kernel per step over a flat fp32 buffer.
+    Parameters are re-pointed at views of the flat buffer (their values are preserved); gradients are gathered into a
+    flat buffer each step (that copy is the only per-parameter work)."""
+
+    def __init__(self, params, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no parameters to optimise")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedAdam needs parameters on a CUDA device (there is no CPU path)")
+        self.lr, self.betas, self.eps, self.step_count = lr, betas, eps, 0
+        sizes = [p.numel() for p in self.params]
+        pitch = [(sz + 63) // 64 * 64 for sz in sizes]          # every parameter starts 256 B aligned (vector loads)
+        self.n = sum(pitch)
+        self.flat = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        off = 0
+        self.views = []
+        for p, sz, pt in zip(self.params, sizes, pitch):
+            self.flat[off: off + sz].copy_(p.data.reshape(-1))
+            p.data = self.flat[off: off + sz].view_as(p.data)
+            self.views.append(self.grad[off: off + sz].view_as(p.data))
+            off += pt
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    def gather_grads(self) -> Tensor:
+        """Copy every .grad into the flat gradient buffer (missing grads count as zero); returns that buffer."""
+        for p, gv in zip(self.params, self.views):
+            if p.grad is None:
+                gv.zero_()
+            else:
+                gv.copy_(p.grad)
+        return self.grad
+
+    def step(self, grad_scale: float = 1.0, gathered: bool = False):
+        if not gathered:
+            self.gather_grads()
+        self.step_count += 1
+        with torch.cuda.device(self.flat.device):
+            _lib.call("wgb_adam_step", self.flat, self.grad, self.m, self.v, self.n, float(self.lr), float(self.betas[0]),
+                      float(self.betas[1]), float(self.eps), self.step_count, float(grad_scale), _lib.stream_ptr())
+
+
+def allreduce_gradients(optimizer: FusedAdam, group=None) -> float:
+    """Data-parallel gradient reduction of waveglow/distributed.py:90-142 (flatten -> all_reduce -> divide by world
+    size) on the optimiser's flat buffer: ONE collective per step; returns the scale to hand to ``step``."""
+    import torch.distributed as dist
+    flat = optimizer.gather_grads()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 1.0
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / dist.get_world_size(group)

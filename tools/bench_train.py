@@ -1,0 +1,80 @@
+"""Training-step timing: WaveGlow.forward + WaveGlowLoss + backward + Adam on BASELINE.json
+configs[3]'s shape (batch 32 x 16000-sample segments, 63 mel frames, config.json architecture, weight-norm layout).
+
+    python tools/bench_train.py [--batch 32] [--samples 16000] [--steps 5] [--warmup 2]
+
+Prints one JSON line: ms per step (CUDA events), split into forward / backward / optimiser, audio samples per second,
+and the tensor-core GEMM rate (algorithmic FLOPs: forward 522.19 MFLOP per group step, backward 2x that).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import warnings
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import text2speech_b200 as t2s                                   # noqa: E402
+from text2speech_b200 import synthetic as syn                    # noqa: E402
+from text2speech_b200.training import FusedAdam, allreduce_gradients   # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--samples", type=int, default=16000)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    cfg = syn.load_config()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = t2s.WaveGlow(**cfg)
+    model.load_state_dict(syn.synthetic_state_dict(cfg, seed=1234, end_std=0.01, weight_norm=True))
+    model = model.to(dev).train()
+    opt = FusedAdam(model.parameters(), lr=1e-4)
+    crit = t2s.WaveGlowLoss(1.0)
+    frames = args.samples // 256 + 1
+    g = torch.Generator().manual_seed(1)
+    audio = (0.1 * torch.randn((args.batch, args.samples), generator=g)).clamp(-1, 1).to(dev)
+    mel = syn.synthetic_mel(args.batch, frames, seed=0).to(dev)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    losses = []
+    for it in range(args.warmup + args.steps):
+        e = ev[it - args.warmup] if it >= args.warmup else None
+        opt.zero_grad()
+        if e: e[0].record()
+        loss = crit(model((mel, audio)))
+        if e: e[1].record()
+        loss.backward()
+        if e: e[2].record()
+        scale = allreduce_gradients(opt)
+        opt.step(grad_scale=scale, gathered=True)
+        if e: e[3].record()
+        losses.append(float(loss.detach()))
+    torch.cuda.synchronize()
+    fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    optim = sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps
+    total = fwd + bwd + optim
+    t = args.samples // 8
+    flop_fwd = 522_190_848 * t * args.batch
+    print(json.dumps({
+        "metric": "waveglow_train_step_ms", "value": total, "unit": "ms", "higher_is_better": False,
+        "config": {"workload": f"WaveGlow train step, batch {args.batch} x {args.samples} samples ({frames} frames), "
+                               "config.json arch, weight norm, Adam"},
+        "forward_ms": fwd, "backward_ms": bwd, "optimizer_ms": optim,
+        "samples_per_s": args.batch * args.samples / (total * 1e-3),
+        "wn_gemm_tflops": {"forward": flop_fwd / (fwd * 1e-3) / 1e12, "backward": 2 * flop_fwd / (bwd * 1e-3) / 1e12,
+                           "step": 3 * flop_fwd / (total * 1e-3) / 1e12},
+        "loss_first_last": [losses[0], losses[-1]], "steps": args.steps, "warmup": args.warmup,
+        "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+    }))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,11 @@
+#!/bin/bash
+# GPU check of the training direction: kernel tests + gradient parity (tests/test_training.py), optional step timing.
+mkdir -p gpurun_out
+TAG=${1:-train}
+KEXPR=${2:-""}
+timeout 1200 python -m pytest tests/test_training.py -m gpu -q --timeout 900 -p no:cacheprovider -s ${KEXPR:+-k "$KEXPR"} > gpurun_out/${TAG}_pytest.log 2>&1
+echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
+tail -40 gpurun_out/${TAG}_pytest.log
+if [ -f tools/bench_train.py ] && [ "${3:-}" = "bench" ]; then
+  timeout 900 python tools/bench_train.py > gpurun_out/${TAG}_bench.log 2>&1; tail -3 gpurun_out/${TAG}_bench.log
+fi
