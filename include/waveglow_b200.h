@@ -279,19 +279,26 @@ WGB_API int wgb_istft_overlap_add(const float* frames, const double* win_sq, flo
 WGB_API int wgb_tc2_wn_gate_train(const void* h, const void* cond, const void* w_packed, const float* bias, void* acts,
                                   void* ts, int batch, int T, int dilation, void* stream);
 /* out[b,t,n] = act(bias[n] + sum_s sum_c W[n][s*C+c] A_s[b, t + shift0 + s*dshift, c]) + res[b,t,n] on tcgen05.
- * A_s = a1 if bit s of seg_mask else a0 (bf16 [B,T,C], C % 64 == 0); W bf16 [N][n_seg*C] (N % 256 == 0); out / res fp32
- * (out_bf16 = 0) or bf16; res may be NULL or alias out.  The data gradients of in_layers (dilated taps + residual
+ * A_s = a1 if bit s of seg_mask else a0 (bf16 [B,T,C], C % 64 == 0); stacked = 1: a0 is [n_seg,B,T,C] and A_s = plane s.
+ * W bf16 [N][n_seg*C] (N % 256 == 0); out / res fp32 (out_bf16 = 0) or bf16; res may be NULL or alias out.  The data gradients of in_layers (dilated taps + residual
  * stream), res_skip_layers (segments [g_h | g_skip]) and cond_layers (accumulating) of glow.py:159-166. */
 WGB_API int wgb_tc_gemm_seg(const void* a0, const void* a1, int n_seg, int seg_mask, const void* w, const float* bias,
                             const void* res, void* c, int out_bf16, int batch, int T, int N, int C, int shift0, int dshift,
-                            int act, void* stream);
+                            int act, int stacked, void* stream);
+/* h_out[b,t,:] = h_in[b,t,:] + bias + sum_tap W[:, tap*C:(tap+1)*C] a[b, t + (tap - (taps-1)/2) dilation, :] with the CTA-pair
+ * residual kernel (cta_group::2, h tile updated in shared memory and TMA-stored): the data gradient of in_layers
+ * flowing into the residual stream's gradient.  a bf16 [B,T,C], w bf16 [512][taps*C], bias fp32 [512], h bf16
+ * [B,h_batch_rows,512] (h_in may alias h_out). */
+WGB_API int wgb_tc2_wn_res_taps(const void* a, const void* w, const float* bias, const void* h_in, void* h_out, int batch,
+                                int T, long long h_batch_rows, int C, int taps, int dilation, void* stream);
 /* dw[tap][m][n] (+)= sum_{b,t} g[b,t,m] x[b, t + (tap - (taps-1)/2)*dilation, n] on tcgen05 with both operands
  * MN-major (no transposed copies).  g bf16 [B,T,ca] (ca % 64 == 0), x bf16 [B,T,cb] (cb % 8 == 0), dw fp32
  * [taps][ca][cb]; accumulate = 0 clears dw first.  Weight gradients of in_layers / cond_layers / res_skip_layers. */
 WGB_API int wgb_tc_wgrad(const void* g, const void* x, float* dw, int batch, int T, int ca, int cb, int taps, int dilation,
                          int accumulate, void* stream);
-/* ts (tanh | sigmoid, bf16 [rows, 2 n_ch]) <- gradient w.r.t. the gate pre-activations given g_acts bf16 [rows, n_ch]. */
-WGB_API int wgb_gate_bwd(const void* g_acts, void* ts, long long rows, int n_ch, void* stream);
+/* ts (tanh | sigmoid, bf16 [rows, 2 n_ch]) <- gradient w.r.t. the gate pre-activations given g_acts bf16 [rows, n_ch];
+ * db (optional, fp32 [2 n_ch]) <- its column sums = the gradient of the in_layers / cond_layers biases. */
+WGB_API int wgb_gate_bwd(const void* g_acts, void* ts, float* db, long long rows, int n_ch, void* stream);
 /* Affine coupling + WN.end backward (glow.py:241-246): see csrc/train.cu.  g_x fp32 [rows,8] in/out, x_mix = flow state
  * before the coupling, log_s / g_log_s fp32 [B,n_half,T] (g_log_s may be NULL), w_end_t fp32 [n_ch][8];
  * g_out fp32 [rows,8], g_skip bf16 [rows,n_ch]. */

@@ -120,7 +120,7 @@ def test_tc_gemm_seg_taps_residual_and_two_operands(lib):
             a_s[:, -sh:] = a[:, : t + sh].double()
         want += a_s @ w[:, s * c:(s + 1) * c].double().t()
     out = res.to(DEV).clone()
-    lib.call("wgb_tc_gemm_seg", a.to(DEV), None, 3, 0, w.to(DEV), None, out, out, 1, b, t, n, c, -d, d, 0, lib.stream_ptr())
+    lib.call("wgb_tc_gemm_seg", a.to(DEV), None, 3, 0, w.to(DEV), None, out, out, 1, b, t, n, c, -d, d, 0, 0, lib.stream_ptr())
     assert util.rel_l2(out.float().cpu(), want) <= 4e-3                     # bf16 output rounding
     # two operands (segments [a0 | a1]), fp32 output accumulated in place
     a1 = torch.randn((b, t, c), generator=g).bfloat16()
@@ -128,7 +128,12 @@ def test_tc_gemm_seg_taps_residual_and_two_operands(lib):
     acc0 = torch.randn((b, t, 256), generator=g)
     want2 = acc0.double() + a.double() @ w2[:, :c].double().t() + a1.double() @ w2[:, c:].double().t()
     acc = acc0.to(DEV).clone()
-    lib.call("wgb_tc_gemm_seg", a.to(DEV), a1.to(DEV), 2, 0b10, w2.to(DEV), None, acc, acc, 0, b, t, 256, c, 0, 0, 0,
+    lib.call("wgb_tc_gemm_seg", a.to(DEV), a1.to(DEV), 2, 0b10, w2.to(DEV), None, acc, acc, 0, b, t, 256, c, 0, 0, 0, 0,
+             lib.stream_ptr())
+    assert util.rel_l2(acc.cpu(), want2) <= 1e-5
+    # the same product with the two operands stacked as planes of one tensor
+    acc = acc0.to(DEV).clone()
+    lib.call("wgb_tc_gemm_seg", torch.stack([a, a1]).to(DEV), None, 2, 0, w2.to(DEV), None, acc, acc, 0, b, t, 256, c, 0, 0, 0, 1,
              lib.stream_ptr())
     assert util.rel_l2(acc.cpu(), want2) <= 1e-5
 
@@ -170,9 +175,11 @@ def test_pointwise_backward_kernels(lib):
     tt = torch.tanh(torch.randn((rows, 512), generator=g)).bfloat16()
     ss = torch.sigmoid(torch.randn((rows, 512), generator=g)).bfloat16()
     ts = torch.cat([tt, ss], dim=1).to(DEV).contiguous()
-    lib.call("wgb_gate_bwd", ga.to(DEV), ts, rows, 512, s)
+    db = torch.empty(1024, device=DEV)
+    lib.call("wgb_gate_bwd", ga.to(DEV), ts, db, rows, 512, s)
     want = torch.cat([ga.float() * ss.float() * (1 - tt.float() ** 2), ga.float() * tt.float() * ss.float() * (1 - ss.float())], 1)
     assert util.rel_l2(ts.float().cpu(), want) <= 4e-3
+    assert util.rel_l2(db.cpu(), ts.float().cpu().double().sum(0)) <= 1e-5
     # coupling backward
     b, t = 2, 500
     g_x = torch.randn((rows, 8), generator=g)
@@ -359,6 +366,6 @@ def test_training_loop_with_fused_adam_and_flat_allreduce(lib):
         scale = allreduce_gradients(opt)
         opt.step(grad_scale=scale, gathered=True)
         losses.append(float(loss.detach()))
-    assert all(np.isfinite(losses)) and abs(losses[-1] - losses[0]) <= 0.5 * abs(losses[0]), losses
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses      # a small enough step lowers the NLL
     moved = max(float((p.detach() - q).abs().max()) for p, q in zip(m.parameters(), before))
     assert 0.5 * lr <= moved <= 3.2 * lr, moved

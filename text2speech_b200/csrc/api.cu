@@ -53,11 +53,13 @@ int end_coupling_f32(const float*, const float*, const float*, float*, const flo
 int upsample_im2col(const float*, void*, int, int, int, int, int, int, cudaStream_t);
 int cast_f32_to_bf16(const float*, void*, long long, cudaStream_t);
 int audio_to_int16(const float*, void*, long long, float, cudaStream_t);
-// training direction: wn_tc.cu, wn_wgrad.cu, train.cu
+// training direction: wn_tc2.cu, wn_tc.cu, wn_wgrad.cu, train.cu
+int tc2_wn_res_taps(const void*, const void*, const float*, const void*, void*, int, int, long long, int, int, int,
+                    cudaStream_t);
 int tc_gemm_seg(const void*, const void*, int, int, const void*, const float*, const void*, void*, int, int, int, int, int,
-                int, int, int, cudaStream_t);
+                int, int, int, int, cudaStream_t);
 int tc_wgrad(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
-int gate_bwd(const void*, void*, long long, int, cudaStream_t);
+int gate_bwd(const void*, void*, float*, long long, int, cudaStream_t);
 int coupling_bwd(float*, const float*, const float*, const float*, const float*, float*, void*, int, int, int, int,
                  cudaStream_t);
 int start_bwd(float*, const void*, const float*, long long, int, int, cudaStream_t);
@@ -285,15 +287,16 @@ WGB_API int wgb_istft_overlap_add(const float* frames, const double* win_sq, flo
 // ------------------------------------------------------------------------------------------------ training direction
 WGB_API int wgb_tc_gemm_seg(const void* a0, const void* a1, int n_seg, int seg_mask, const void* w, const float* bias,
                             const void* res, void* c, int out_bf16, int batch, int T, int N, int C, int shift0, int dshift,
-                            int act, void* stream) {
-    return tc_gemm_seg(a0, a1, n_seg, seg_mask, w, bias, res, c, out_bf16, batch, T, N, C, shift0, dshift, act, S(stream));
+                            int act, int stacked, void* stream) {
+    return tc_gemm_seg(a0, a1, n_seg, seg_mask, w, bias, res, c, out_bf16, batch, T, N, C, shift0, dshift, act, stacked,
+                       S(stream));
 }
 WGB_API int wgb_tc_wgrad(const void* g, const void* x, float* dw, int batch, int T, int ca, int cb, int taps, int dilation,
                          int accumulate, void* stream) {
     return tc_wgrad(g, x, dw, batch, T, ca, cb, taps, dilation, accumulate, S(stream));
 }
-WGB_API int wgb_gate_bwd(const void* g_acts, void* ts, long long rows, int n_ch, void* stream) {
-    return gate_bwd(g_acts, ts, rows, n_ch, S(stream));
+WGB_API int wgb_gate_bwd(const void* g_acts, void* ts, float* db, long long rows, int n_ch, void* stream) {
+    return gate_bwd(g_acts, ts, db, rows, n_ch, S(stream));
 }
 WGB_API int wgb_coupling_bwd(float* g_x, const float* x_mix, const float* log_s, const float* g_log_s, const float* w_end_t,
                              float* g_out, void* g_skip, int batch, int T, int n_ch, int n_half, void* stream) {
@@ -323,4 +326,8 @@ WGB_API int wgb_upsample_wgrad(const float* mel, const float* g_cond, float* dw,
 WGB_API int wgb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                           float eps, int step, float grad_scale, void* stream) {
     return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step, grad_scale, S(stream));
+}
+WGB_API int wgb_tc2_wn_res_taps(const void* a, const void* w, const float* bias, const void* h_in, void* h_out, int batch,
+                                int T, long long h_batch_rows, int C, int taps, int dilation, void* stream) {
+    return tc2_wn_res_taps(a, w, bias, h_in, h_out, batch, T, h_batch_rows, C, taps, dilation, S(stream));
 }

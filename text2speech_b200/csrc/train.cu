@@ -11,37 +11,84 @@ namespace wgb {
 // ------------------------------------------------------------------------------------------------ gate backward
 // acts = tanh(a) * sigmoid(b)  ->  g_a = g * s * (1 - t^2), g_b = g * t * s * (1 - s).  ts holds (t | s) on entry and
 // (g_a | g_b) on exit (the gradient w.r.t. the gate pre-activations, original channel order).
-__global__ void gate_bwd_kernel(const uint4* __restrict__ g_acts, uint4* __restrict__ ts, long long rows, int c8) {
-    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (i >= rows * c8) return;
-    const long long r = i / c8;
-    const int c = static_cast<int>(i - r * c8);
-    const uint4 g4 = g_acts[i];
-    uint4* tp = ts + r * (2 * c8) + c;
-    uint4* sp = tp + c8;
-    const uint4 t4 = *tp, s4 = *sp;
-    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, tw[4] = {t4.x, t4.y, t4.z, t4.w}, sw[4] = {s4.x, s4.y, s4.z, s4.w};
-    uint32_t ga[4], gb[4];
+// Block = 64 column groups (8 channels each) x 4 row lanes, grid-stride over 16-row groups; db[2 n_ch] (optional) accumulates the
+// column sums of the result = the gradient of the in_layers / cond_layers biases.
+__global__ void __launch_bounds__(256)
+gate_bwd_kernel(const uint4* __restrict__ g_acts, uint4* ts, float* __restrict__ db, long long rows, int c8) {
+    __shared__ float s_sum[3][64][16];
+    const int col = threadIdx.x & 63, lane_r = threadIdx.x >> 6;
+    const int c = blockIdx.y * 64 + col;
+    float sa[8], sb[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]));
-        const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tw[e]));
-        const float2 s = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&sw[e]));
-        __nv_bfloat162 a2 = __floats2bfloat162_rn(g.x * s.x * (1.f - t.x * t.x), g.y * s.y * (1.f - t.y * t.y));
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(g.x * t.x * s.x * (1.f - s.x), g.y * t.y * s.y * (1.f - s.y));
-        ga[e] = *reinterpret_cast<uint32_t*>(&a2);
-        gb[e] = *reinterpret_cast<uint32_t*>(&b2);
+    for (int e = 0; e < 8; ++e) sa[e] = sb[e] = 0.f;
+    if (c < c8) {
+        constexpr int kBatch = 4;                               // rows in flight per thread (12 independent 16 B loads)
+#pragma unroll 1
+        for (long long rb = static_cast<long long>(blockIdx.x) * (4 * kBatch) + lane_r; rb < rows;
+             rb += static_cast<long long>(gridDim.x) * (4 * kBatch)) {
+            uint4 g4[kBatch], t4[kBatch], s4[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const long long r = rb + 4 * u;
+                if (r < rows) {
+                    g4[u] = g_acts[r * c8 + c];
+                    t4[u] = ts[r * (2 * c8) + c];
+                    s4[u] = ts[r * (2 * c8) + c8 + c];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const long long r = rb + 4 * u;
+                if (r >= rows) continue;
+                const uint32_t gw[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w}, tw[4] = {t4[u].x, t4[u].y, t4[u].z, t4[u].w},
+                               sw[4] = {s4[u].x, s4[u].y, s4[u].z, s4[u].w};
+                uint32_t ga[4], gb[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]));
+                    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tw[e]));
+                    const float2 sg = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&sw[e]));
+                    __nv_bfloat162 a2 = __floats2bfloat162_rn(g.x * sg.x * (1.f - t.x * t.x), g.y * sg.y * (1.f - t.y * t.y));
+                    __nv_bfloat162 b2 = __floats2bfloat162_rn(g.x * t.x * sg.x * (1.f - sg.x), g.y * t.y * sg.y * (1.f - sg.y));
+                    ga[e] = *reinterpret_cast<uint32_t*>(&a2);
+                    gb[e] = *reinterpret_cast<uint32_t*>(&b2);
+                    sa[2 * e] += __low2float(a2);  sa[2 * e + 1] += __high2float(a2);      // sums of what was stored
+                    sb[2 * e] += __low2float(b2);  sb[2 * e + 1] += __high2float(b2);
+                }
+                ts[r * (2 * c8) + c] = make_uint4(ga[0], ga[1], ga[2], ga[3]);
+                ts[r * (2 * c8) + c8 + c] = make_uint4(gb[0], gb[1], gb[2], gb[3]);
+            }
+        }
     }
-    *tp = make_uint4(ga[0], ga[1], ga[2], ga[3]);
-    *sp = make_uint4(gb[0], gb[1], gb[2], gb[3]);
+    if (db == nullptr) return;
+    if (lane_r > 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            s_sum[lane_r - 1][col][e] = sa[e];
+            s_sum[lane_r - 1][col][8 + e] = sb[e];
+        }
+    }
+    __syncthreads();
+    if (lane_r == 0 && c < c8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float va = sa[e] + s_sum[0][col][e] + s_sum[1][col][e] + s_sum[2][col][e];
+            const float vb = sb[e] + s_sum[0][col][8 + e] + s_sum[1][col][8 + e] + s_sum[2][col][8 + e];
+            atomicAdd(db + c * 8 + e, va);
+            atomicAdd(db + c8 * 8 + c * 8 + e, vb);
+        }
+    }
 }
 
-int gate_bwd(const void* g_acts, void* ts, long long rows, int n_ch, cudaStream_t stream) {
+int gate_bwd(const void* g_acts, void* ts, float* db, long long rows, int n_ch, cudaStream_t stream) {
     WGB_REQUIRE(g_acts && ts, "null pointer");
     WGB_REQUIRE(rows > 0 && n_ch > 0 && n_ch % 8 == 0, "rows must be positive and n_ch a multiple of 8");
-    const long long n = rows * (n_ch / 8);
-    gate_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(static_cast<const uint4*>(g_acts),
-                                                                                static_cast<uint4*>(ts), rows, n_ch / 8);
+    if (db) WGB_CUDA_TRY(cudaMemsetAsync(db, 0, sizeof(float) * 2 * n_ch, stream));
+    const int c8 = n_ch / 8;
+    long long blocks = (rows + 15) / 16;                    // few, long-lived blocks: one set of bias atomics per block
+    if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
+    dim3 grid(static_cast<unsigned>(blocks), (c8 + 63) / 64);
+    gate_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(g_acts), static_cast<uint4*>(ts), db, rows, c8);
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }
@@ -156,39 +203,60 @@ int start_bwd(float* g_x, const void* g_h0, const float* w_start, long long rows
 // out[j][c] += sum_r a[r][j] * b[r][c]   (a fp32 [rows, 8], b bf16 [rows, n_ch]; out fp32 [8][n_ch]).
 // Weight gradients whose one side has <= 8 channels: WN.start (a = flow state, b = g_h0), WN.end composed with the
 // skip rows (a = g_out, b = the layer's gated activations).  One thread per 8 columns, 256 rows per block.
-__global__ void skinny_wgrad_kernel(const float* __restrict__ a, const uint4* __restrict__ b, float* __restrict__ out,
-                                    long long rows, int c8, int rows_per_block) {
-    const int c = blockIdx.y * blockDim.x + threadIdx.x;
-    if (c >= c8) return;
-    const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
-    const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+__global__ void __launch_bounds__(256)
+skinny_wgrad_kernel(const float* __restrict__ a, const uint4* __restrict__ b, float* __restrict__ out, long long rows, int c8) {
+    __shared__ float s_acc[8][64 * 8];                         // [j][column within this block's 512-column slab]
+    const int col = threadIdx.x & 63, lane_r = threadIdx.x >> 6;
+    const int c = blockIdx.y * 64 + col;
+    for (int i = threadIdx.x; i < 8 * 512; i += 256) (&s_acc[0][0])[i] = 0.f;
+    __syncthreads();
     float acc[8][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
-    for (long long r = r0; r < r1; ++r) {
-        const uint4 v = b[r * c8 + c];
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(a + r * 8));
-        const float4 a1 = __ldg(reinterpret_cast<const float4*>(a + r * 8) + 1);
-        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        float bv[8];
+    if (c < c8) {
+        constexpr int kBatch = 4;
+#pragma unroll 1
+        for (long long rb = static_cast<long long>(blockIdx.x) * (4 * kBatch) + lane_r; rb < rows;
+             rb += static_cast<long long>(gridDim.x) * (4 * kBatch)) {
+            uint4 v[kBatch];
+            float4 a0[kBatch], a1[kBatch];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-            bv[2 * e] = f.x;
-            bv[2 * e + 1] = f.y;
+            for (int u = 0; u < kBatch; ++u) {
+                const long long r = rb + 4 * u;
+                const bool ok = r < rows;
+                v[u] = ok ? b[r * c8 + c] : make_uint4(0u, 0u, 0u, 0u);
+                a0[u] = ok ? __ldg(reinterpret_cast<const float4*>(a + r * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                a1[u] = ok ? __ldg(reinterpret_cast<const float4*>(a + r * 8) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const float av[8] = {a0[u].x, a0[u].y, a0[u].z, a0[u].w, a1[u].x, a1[u].y, a1[u].z, a1[u].w};
+                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                float bv[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                    bv[2 * e] = f.x;
+                    bv[2 * e + 1] = f.y;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(av[j], bv[e], acc[j][e]);
+            }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(av[j], bv[e], acc[j][e]);
+            for (int e = 0; e < 8; ++e) atomicAdd(&s_acc[j][col * 8 + e], acc[j][e]);       // 4-way (the row lanes)
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(out + static_cast<size_t>(j) * c8 * 8 + c * 8 + e, acc[j][e]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * 512; i += 256) {
+        const int j = i >> 9, cc = blockIdx.y * 512 + (i & 511);
+        if (cc < c8 * 8) atomicAdd(out + static_cast<size_t>(j) * c8 * 8 + cc, s_acc[j][i & 511]);
+    }
 }
 
 int skinny_wgrad(const float* a, const void* b, float* out, long long rows, int n_ch, int accumulate, cudaStream_t stream) {
@@ -196,33 +264,53 @@ int skinny_wgrad(const float* a, const void* b, float* out, long long rows, int 
     WGB_REQUIRE(rows > 0 && n_ch > 0 && n_ch % 8 == 0, "bad shape");
     if (!accumulate) WGB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * 8 * n_ch, stream));
     const int c8 = n_ch / 8;
-    const int rpb = 256;
-    dim3 grid(static_cast<unsigned>((rows + rpb - 1) / rpb), (c8 + 63) / 64);
-    skinny_wgrad_kernel<<<grid, 64, 0, stream>>>(a, static_cast<const uint4*>(b), out, rows, c8, rpb);
+    long long blocks = (rows + 15) / 16;
+    if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
+    dim3 grid(static_cast<unsigned>(blocks), (c8 + 63) / 64);
+    skinny_wgrad_kernel<<<grid, 256, 0, stream>>>(a, static_cast<const uint4*>(b), out, rows, c8);
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }
 
-// out[c] += sum_r b[r][c]  (bias gradients; b bf16 [rows, n_ch])
-__global__ void colsum_bf16_kernel(const uint4* __restrict__ b, float* __restrict__ out, long long rows, int c8,
-                                   int rows_per_block) {
-    const int c = blockIdx.y * blockDim.x + threadIdx.x;
-    if (c >= c8) return;
-    const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
-    const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+// out[c] += sum_r b[r][c]  (bias gradients; b bf16 [rows, n_ch]).  Block = 64 column groups x 4 row lanes, grid-stride.
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const uint4* __restrict__ b, float* __restrict__ out, long long rows, int c8) {
+    __shared__ float s_sum[3][64][8];
+    const int col = threadIdx.x & 63, lane_r = threadIdx.x >> 6;
+    const int c = blockIdx.y * 64 + col;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (long long r = r0; r < r1; ++r) {
-        const uint4 v = b[r * c8 + c];
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (c < c8) {
+        constexpr int kBatch = 8;
+#pragma unroll 1
+        for (long long rb = static_cast<long long>(blockIdx.x) * (4 * kBatch) + lane_r; rb < rows;
+             rb += static_cast<long long>(gridDim.x) * (4 * kBatch)) {
+            uint4 v[kBatch];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-            acc[2 * e] += f.x;
-            acc[2 * e + 1] += f.y;
+            for (int u = 0; u < kBatch; ++u) {
+                const long long r = rb + 4 * u;
+                v[u] = r < rows ? b[r * c8 + c] : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                    acc[2 * e] += f.x;
+                    acc[2 * e + 1] += f.y;
+                }
+            }
         }
     }
+    if (lane_r > 0) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) atomicAdd(out + c * 8 + e, acc[e]);
+        for (int e = 0; e < 8; ++e) s_sum[lane_r - 1][col][e] = acc[e];
+    }
+    __syncthreads();
+    if (lane_r == 0 && c < c8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(out + c * 8 + e, acc[e] + s_sum[0][col][e] + s_sum[1][col][e] + s_sum[2][col][e]);
+    }
 }
 
 int colsum_bf16(const void* b, float* out, long long rows, int n_ch, int accumulate, cudaStream_t stream) {
@@ -230,9 +318,10 @@ int colsum_bf16(const void* b, float* out, long long rows, int n_ch, int accumul
     WGB_REQUIRE(rows > 0 && n_ch > 0 && n_ch % 8 == 0, "bad shape");
     if (!accumulate) WGB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * n_ch, stream));
     const int c8 = n_ch / 8;
-    const int rpb = 128;
-    dim3 grid(static_cast<unsigned>((rows + rpb - 1) / rpb), (c8 + 127) / 128);
-    colsum_bf16_kernel<<<grid, 128, 0, stream>>>(static_cast<const uint4*>(b), out, rows, c8, rpb);
+    long long blocks = (rows + 31) / 32;
+    if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
+    dim3 grid(static_cast<unsigned>(blocks), (c8 + 63) / 64);
+    colsum_bf16_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(b), out, rows, c8);
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }
@@ -341,42 +430,54 @@ int mix_bwd(float* g_x, const float* x_pre, const float* w, float* dw, long long
 //   dw[ci][m][k] = sum_{b,f} mel[b,ci,f] g_up[b, m, stride f + k],    db[m] = sum_{b,n} g_up[b,m,n]
 // One block per (m, 128 taps k); each thread owns one k and all ci (<= 80) accumulators.
 constexpr int kUpMaxMel = 80;
-__global__ void upsample_wgrad_kernel(const float* __restrict__ mel, const float* __restrict__ g_cond, float* __restrict__ dw,
-                                      float* __restrict__ db, int batch, int n_mel, int frames, int T, int ld, int ksize,
-                                      int stride, int n_group) {
-    extern __shared__ float s_mel[];                           // [frames chunk][n_mel]
+// One block per (m, 256 taps): 128 threads, each owning taps k and k + 128 and all ci accumulators (mel values come as
+// broadcast LDS.128, one per 8 FMAs).
+__global__ void __launch_bounds__(128)
+upsample_wgrad_kernel(const float* __restrict__ mel, const float* __restrict__ g_cond, float* __restrict__ dw,
+                      float* __restrict__ db, int batch, int n_mel, int frames, int T, int ld, int ksize, int stride,
+                      int n_group) {
+    constexpr int kFChunk = 32;
+    __shared__ __align__(16) float s_mel[kFChunk * kUpMaxMel];         // [frames chunk][kUpMaxMel], zero padded
     const int m = blockIdx.y;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    float acc[kUpMaxMel];
+    const int k0 = blockIdx.x * 256 + threadIdx.x, k1 = k0 + 128;
+    float acc0[kUpMaxMel], acc1[kUpMaxMel];
 #pragma unroll
-    for (int i = 0; i < kUpMaxMel; ++i) acc[i] = 0.f;
+    for (int i = 0; i < kUpMaxMel; ++i) acc0[i] = acc1[i] = 0.f;
     float bsum = 0.f;
     const int n_total = T * n_group;
-    constexpr int kFChunk = 32;
     for (int b = blockIdx.z; b < batch; b += gridDim.z)
     for (int f0 = 0; f0 < frames; f0 += kFChunk) {
         __syncthreads();
-        for (int i = threadIdx.x; i < kFChunk * n_mel; i += blockDim.x) {
-            const int ff = i / n_mel, ci = i - ff * n_mel;
-            s_mel[i] = (f0 + ff < frames) ? mel[(static_cast<size_t>(b) * n_mel + ci) * frames + f0 + ff] : 0.f;
+        for (int i = threadIdx.x; i < kFChunk * kUpMaxMel; i += blockDim.x) {
+            const int ci = i / kFChunk, ff = i - ci * kFChunk;                 // consecutive threads read consecutive frames
+            s_mel[ff * kUpMaxMel + ci] = (ci < n_mel && f0 + ff < frames) ? mel[(static_cast<size_t>(b) * n_mel + ci) * frames + f0 + ff] : 0.f;
         }
         __syncthreads();
         for (int ff = 0; ff < kFChunk && f0 + ff < frames; ++ff) {
-            const int n = stride * (f0 + ff) + k;
-            if (k < ksize && n < n_total) {
-                const float g = g_cond[(static_cast<size_t>(b) * T + n / n_group) * ld + m * n_group + n % n_group];
-                if (k < stride) bsum += g;                     // every sample n is counted once (k < stride covers n = stride f + k)
-                const float* sm = s_mel + ff * n_mel;
+            const int n0 = stride * (f0 + ff) + k0, n1 = stride * (f0 + ff) + k1;
+            float g0 = 0.f, g1 = 0.f;
+            if (k0 < ksize && n0 < n_total) g0 = g_cond[(static_cast<size_t>(b) * T + n0 / n_group) * ld + m * n_group + n0 % n_group];
+            if (k1 < ksize && n1 < n_total) g1 = g_cond[(static_cast<size_t>(b) * T + n1 / n_group) * ld + m * n_group + n1 % n_group];
+            if (k0 < stride) bsum += g0;                       // every sample n = stride f + k, k < stride, counted once
+            if (k1 < stride) bsum += g1;
+            const float4* sm4 = reinterpret_cast<const float4*>(s_mel + ff * kUpMaxMel);
 #pragma unroll
-                for (int ci = 0; ci < kUpMaxMel; ++ci)
-                    if (ci < n_mel) acc[ci] = fmaf(sm[ci], g, acc[ci]);
+            for (int q = 0; q < kUpMaxMel / 4; ++q) {
+                const float4 v = sm4[q];
+                acc0[4 * q] = fmaf(v.x, g0, acc0[4 * q]);         acc1[4 * q] = fmaf(v.x, g1, acc1[4 * q]);
+                acc0[4 * q + 1] = fmaf(v.y, g0, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(v.y, g1, acc1[4 * q + 1]);
+                acc0[4 * q + 2] = fmaf(v.z, g0, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(v.z, g1, acc1[4 * q + 2]);
+                acc0[4 * q + 3] = fmaf(v.w, g0, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(v.w, g1, acc1[4 * q + 3]);
             }
         }
     }
-    if (k < ksize) {
-        for (int ci = 0; ci < n_mel; ++ci) atomicAdd(dw + (static_cast<size_t>(ci) * n_mel + m) * ksize + k, acc[ci]);
+#pragma unroll
+    for (int ci = 0; ci < kUpMaxMel; ++ci) {
+        if (ci < n_mel) {
+            if (k0 < ksize) atomicAdd(dw + (static_cast<size_t>(ci) * n_mel + m) * ksize + k0, acc0[ci]);
+            if (k1 < ksize) atomicAdd(dw + (static_cast<size_t>(ci) * n_mel + m) * ksize + k1, acc1[ci]);
+        }
     }
-    // db: block reduction of bsum
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
     if ((threadIdx.x & 31) == 0 && bsum != 0.f) atomicAdd(db + m, bsum);
@@ -389,9 +490,8 @@ int upsample_wgrad(const float* mel, const float* g_cond, float* dw, float* db, 
     WGB_REQUIRE(batch > 0 && frames > 0 && T > 0 && ld >= n_mel * n_group && ksize > 0 && stride > 0, "bad shape");
     WGB_CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(float) * n_mel * n_mel * ksize, stream));
     WGB_CUDA_TRY(cudaMemsetAsync(db, 0, sizeof(float) * n_mel, stream));
-    dim3 grid((ksize + 127) / 128, n_mel, batch < 4 ? batch : 4);
-    upsample_wgrad_kernel<<<grid, 128, 32 * n_mel * sizeof(float), stream>>>(mel, g_cond, dw, db, batch, n_mel, frames, T, ld,
-                                                                             ksize, stride, n_group);
+    dim3 grid((ksize + 255) / 256, n_mel, batch < 8 ? batch : 8);
+    upsample_wgrad_kernel<<<grid, 128, 0, stream>>>(mel, g_cond, dw, db, batch, n_mel, frames, T, ld, ksize, stride, n_group);
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }

@@ -66,6 +66,7 @@ struct TcParams {
                                   //        map_a1 (else map_a0) for segment s (split-bf16 hi/lo operands)
     int seg_shift0, seg_dshift;   // PLAIN  segment s reads A rows t + seg_shift0 + s*seg_dshift (conv taps; rows outside
                                   //        [0,T) are zero-filled by TMA = zero padding); 0, 0 for a plain GEMM
+    int seg_bstride;              // PLAIN  segment s reads utterance b + s*seg_bstride (segments stacked as [n_seg, B, T, C]); else 0
     int act;                      // PLAIN  DIR 0/1 epilogue: 0 none, 1 tanh, 2 relu
     const void* res;              // PLAIN  DIR 0/1: optional [B,T,N] tensor (fp32 for DIR 0, bf16 for DIR 1) added to the
                                   //        result before the store; may alias c_out (accumulate / residual update in place)
@@ -182,7 +183,8 @@ wn_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                         } else if constexpr (MODE == MODE_PLAIN || MODE == MODE_STFT_MEL) {
                             const int seg = kc / p.seg_chunks;
                             tma_load_3d(sa, ((p.seg_mask >> seg) & 1) ? &map_a1 : &map_a0, &full_bar[s],
-                                        (kc - seg * p.seg_chunks) * kBlockK, t0 + p.seg_shift0 + seg * p.seg_dshift, b);
+                                        (kc - seg * p.seg_chunks) * kBlockK, t0 + p.seg_shift0 + seg * p.seg_dshift,
+                                        b + seg * p.seg_bstride);
                         } else {
                             tma_load_3d(sa, &map_a0, &full_bar[s], (kc & 7) * kBlockK, t0, (kc >> 3) * p.batch + b);
                         }
@@ -671,10 +673,11 @@ int tc_conv1d_taps(const void* a, const void* w, const float* bias, void* c, int
 // General segmented GEMM behind the backward pass of the WN layers (training direction):
 //   out[b,t,n] = act(bias[n] + sum_s sum_c W[n][s*C + c] A_s[b, t + shift0 + s*dshift, c]) + res[b,t,n]
 // A_s = a1 when bit s of seg_mask is set, else a0 (both bf16 [B,T,C], C % 64 == 0); W bf16 [N][n_seg*C] (N % 256 == 0);
-// out / res fp32 (out_bf16 = 0) or bf16 [B,T,N]; res may be null or alias out.  Uses: data gradient of the dilated
+// out / res fp32 (out_bf16 = 0) or bf16 [B,T,N]; res may be null or alias out.  stacked = 1: a0 is [n_seg, B, T, C] and
+// segment s reads plane s (K-concatenation of several layers' tensors without copying them).  Uses: data gradient of the dilated
 // conv (taps as shifted segments + residual stream), of res_skip (segments [g_h | g_skip]), of cond (accumulating).
 int tc_gemm_seg(const void* a0, const void* a1, int n_seg, int seg_mask, const void* w, const float* bias, const void* res,
-                void* c, int out_bf16, int batch, int T, int N, int C, int shift0, int dshift, int act,
+                void* c, int out_bf16, int batch, int T, int N, int C, int shift0, int dshift, int act, int stacked,
                 cudaStream_t stream) {
     WGB_REQUIRE(a0 && w && c, "null pointer");
     WGB_REQUIRE(n_seg >= 1 && n_seg <= 31, "n_seg must be in 1..31 (got %d)", n_seg);
@@ -687,8 +690,10 @@ int tc_gemm_seg(const void* a0, const void* a1, int n_seg, int seg_mask, const v
     p.bias = bias; p.c_out = c; p.n_total = N; p.res = res;
     p.seg_chunks = C / kBlockK; p.seg_mask = seg_mask;
     p.seg_shift0 = shift0; p.seg_dshift = dshift; p.act = act;
+    WGB_REQUIRE(!stacked || seg_mask == 0, "stacked segments read a0 only");
+    p.seg_bstride = stacked ? batch : 0;                  // a0 is [n_seg, B, T, C]: segment s = plane s
     CUtensorMap ma0, ma1, mb;
-    if (int e = act_map(&ma0, a0, C, T, batch)) return e;
+    if (int e = act_map(&ma0, a0, C, T, stacked ? batch * n_seg : batch)) return e;
     if (int e = act_map(&ma1, a1 ? a1 : a0, C, T, batch)) return e;
     if (int e = weight_map(&mb, w, N, n_seg * C)) return e;
     return out_bf16 ? launch<MODE_PLAIN, 0, 1>(ma0, ma1, mb, ma0, p, stream) : launch<MODE_PLAIN, 0, 0>(ma0, ma1, mb, ma0, p, stream);

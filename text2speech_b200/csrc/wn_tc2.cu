@@ -88,6 +88,8 @@ struct Params {
     int skip_first;
     const float* bias;            // GATE [1024] packed order, RES [512]
     __nv_bfloat16* acts_out;      // GATE [B,T,512]
+    int seg_chunks, seg_shift0, seg_dshift;   // RES: K chunk kc reads A columns (kc % seg_chunks) * 64 of rows
+                                  //      t + seg_shift0 + (kc / seg_chunks) * seg_dshift (conv taps; plain GEMM: n_chunks, 0, 0)
     __nv_bfloat16* ts_out;        // GATE, training forward (optional): [B,T,1024] = tanh half | sigmoid half, original
                                   //       channel order (what the gate's backward needs; glow.py:33-40 under autograd)
     const float* w_end;           // SKIP_END [512][8] fp32 (rows >= 2*n_half zero)
@@ -290,7 +292,9 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                                 tma_load_3d_2sm(sa, &map_a1, bar, (kc - p.n_tap_chunks) * kBlockK, t0, b);
                             }
                         } else if constexpr (MODE == RES) {
-                            tma_load_3d_2sm(sa, &map_a0, bar, kc * kBlockK, t0, b);
+                            const int seg = kc / p.seg_chunks;
+                            tma_load_3d_2sm(sa, &map_a0, bar, (kc - seg * p.seg_chunks) * kBlockK,
+                                            t0 + p.seg_shift0 + seg * p.seg_dshift, b);
                         } else {
                             tma_load_3d_2sm(sa, &map_a0, bar, (kc & 7) * kBlockK, t0, (kc >> 3) * p.batch + b);
                         }
@@ -851,6 +855,7 @@ int tc2_wn_res(const void* acts, const void* w_res, const float* bias, const voi
     Params p{};
     if (int e = fill_common(p, batch, T)) return e;
     p.n_pass = skip_acc ? 3 : 2; p.ppi = 1; p.n_chunks = kNCh / kBlockK;
+    p.seg_chunks = p.n_chunks;
     p.bias = bias;
     p.skip_acc = skip_acc; p.skip_first = skip_first;
     CUtensorMap ma, mhi, mho, mw, mx;
@@ -865,6 +870,28 @@ int tc2_wn_res(const void* acts, const void* w_res, const float* bias, const voi
     if (int e = h_map(&mho, h_out, T, batch, h_batch_rows)) return e;
     if (int e = weight_half_map(&mw, w_res, kNCh, kNCh)) return e;
     return launch<RES, 0, 0>(ma, mhi, mw, mho, p, stream, skip_acc ? &mx : nullptr);
+}
+
+// Residual update fed by a dilated conv instead of a 1x1 (training direction: the data gradient of in_layers,
+// glow.py:159-160 under autograd):  h_out[b,t,:] = h_in[b,t,:] + bias + sum_tap W[:, tap*C : (tap+1)*C] a[b, t + (tap - (taps-1)/2) d, :]
+// a bf16 [B,T,C] (C % 64 == 0), w bf16 [512][taps*C], bias fp32 [512], h_in / h_out bf16 [B, h_batch_rows, 512] (may alias).
+int tc2_wn_res_taps(const void* a, const void* w, const float* bias, const void* h_in, void* h_out, int batch, int T,
+                    long long h_batch_rows, int C, int taps, int dilation, cudaStream_t stream) {
+    using namespace tc2;
+    WGB_REQUIRE(a && w && bias && h_in && h_out, "null pointer");
+    WGB_REQUIRE(h_batch_rows >= T, "h_batch_rows (%lld) must be >= T (%d)", h_batch_rows, T);
+    WGB_REQUIRE(C > 0 && C % kBlockK == 0 && taps >= 1 && taps % 2 == 1 && dilation >= 1, "bad conv shape (C=%d taps=%d)", C, taps);
+    Params p{};
+    if (int e = fill_common(p, batch, T)) return e;
+    p.n_pass = 2; p.ppi = 1; p.n_chunks = taps * C / kBlockK;
+    p.seg_chunks = C / kBlockK; p.seg_shift0 = -((taps - 1) / 2) * dilation; p.seg_dshift = dilation;
+    p.bias = bias;
+    CUtensorMap ma, mhi, mho, mw;
+    if (int e = act_map(&ma, a, C, T, batch)) return e;
+    if (int e = h_map(&mhi, h_in, T, batch, h_batch_rows)) return e;
+    if (int e = h_map(&mho, h_out, T, batch, h_batch_rows)) return e;
+    if (int e = weight_half_map(&mw, w, kNCh, taps * C)) return e;
+    return launch<RES, 0, 0>(ma, mhi, mw, mho, p, stream, nullptr);
 }
 
 int tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end, const float* b_end,

@@ -11,8 +11,11 @@
 // [0, T) by the tap offset are zero-filled by TMA (= the conv's zero padding); rows >= T of the last chunk of an
 // utterance are zero in G as well, so ragged T costs nothing.
 //
-// Tiling: one item = (m tile of 128, n tile of 256, tap, K split); K = all (utterance, 64-row chunk) pairs, split so
+// Tiling: one item = (m tile of 256, n tile of 256, tap, K split); K = all (utterance, 64-row chunk) pairs, split so
 // that the grid fills the SMs; partial sums leave through fp32 atomics (red.global.add) into dW (a few MB, L2 resident).
+// A 256 x 256 tile is two UMMA M = 128 accumulators (all 512 TMEM columns) fed by the same B chunk: 64 KB of operands
+// per 2 x (128 x 256 x 64) MACs = 128 B/clk/SM from L2 instead of the 192 B/clk of a 128 x 256 tile, which is what
+// bounds a single-CTA kernel here (the items are ~250 chunks long, so the un-overlapped epilogue is noise).
 // Warp roles as in wn_tc.cu: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -20,14 +23,14 @@
 namespace wgb {
 namespace wgrad {
 
-constexpr int kM = 128;
+constexpr int kM = 256;                         // two UMMA M = 128 halves
 constexpr int kN = 256;
 constexpr int kRows = 64;                       // K chunk = 64 time steps
 constexpr int kBox = 64 * kRows * 2;            // one {64 ch, 64 rows} box = 8 KB
-constexpr int kABytes = (kM / 64) * kBox;       // 16 KB
+constexpr int kABytes = (kM / 64) * kBox;       // 32 KB
 constexpr int kBBytes = (kN / 64) * kBox;       // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kThreads = 192;
 constexpr int kSmem = 1024 + kStages * kStageBytes + 256;
 
@@ -36,7 +39,12 @@ struct Params {
     int m_tiles, n_tiles, taps, dilation;
     int ca, cb;
     float* out;                                 // [taps][ca][cb] fp32
+    int vec_ok;                                 // out 16 B aligned and cb % 4 == 0: vector reds allowed
 };
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 // MN-major SW128 operand: LBO = distance between 64-element blocks along M/N, SBO = distance between 8-row K groups
 __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -68,10 +76,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
-        }
+        mbar_init(&tfull_bar[0], 1);
+        mbar_init(&tempty_bar[0], 4);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -116,17 +122,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     } else if (warp == 1) {
         if (lane == 0) {
             // kind::f16, D fp32, A/B bf16, both MN-major (bits 15, 16)
-            constexpr uint32_t idesc = umma_idesc_bf16_f32(kM, kN) | (1u << 15) | (1u << 16);
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(128, kN) | (1u << 15) | (1u << 16);
             int s = 0;
             uint32_t ph = 0, acc_it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
                 const int split = item / tiles;
                 const int c_begin = split * p.chunks_per_split;
                 const int c_end = min(c_begin + p.chunks_per_split, p.chunks_total);
-                const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-                mbar_wait(&tempty_bar[as], aph ^ 1, 200 + as);
+                mbar_wait(&tempty_bar[0], (acc_it & 1) ^ 1, 200);
                 tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + as * kN;
                 for (int c = c_begin; c < c_end; ++c) {
                     mbar_wait(&full_bar[s], ph, 300 + s);
                     tc_fence_after_sync();
@@ -134,13 +138,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                     const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
                     for (int k = 0; k < kRows / 16; ++k) {     // 16 rows = two 8-row groups = 2048 B per UMMA
-                        umma_bf16_ss(d_tmem, umma_desc_sw128_mn(a_addr + k * 2048, kBox),
-                                     umma_desc_sw128_mn(b_addr + k * 2048, kBox), idesc, (c > c_begin) || (k != 0));
+                        const uint64_t db = umma_desc_sw128_mn(b_addr + k * 2048, kBox);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half)   // channels half*128 .. +127 of the m tile -> accumulator half
+                            umma_bf16_ss(tmem_base + half * kN, umma_desc_sw128_mn(a_addr + half * 2 * kBox + k * 2048, kBox),
+                                         db, idesc, (c > c_begin) || (k != 0));
                     }
                     umma_commit(&empty_bar[s]);
                     if (++s == kStages) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&tfull_bar[as]);
+                umma_commit(&tfull_bar[0]);
             }
         }
     } else {
@@ -154,27 +161,36 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             const int n_tile = (tile / p.m_tiles) % p.n_tiles;
             const int tap = tile / (p.m_tiles * p.n_tiles);
             const bool has_work = split * p.chunks_per_split < p.chunks_total;
-            const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-            mbar_wait(&tfull_bar[as], aph, 400 + as);
+            mbar_wait(&tfull_bar[0], acc_it & 1, 400);
             tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kN;
-            const int m = m_tile * kM + row;
-            float* dst = p.out + (static_cast<size_t>(tap) * p.ca + m) * p.cb + n_tile * kN;
             const int n_left = p.cb - n_tile * kN;
 #pragma unroll 1
-            for (int ch = 0; ch < 8; ++ch) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(taddr + ch * 32, v);
-                tmem_ld_wait();
-                if (has_work && m < p.ca) {
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * kN;
+                const int m = m_tile * kM + half * 128 + row;
+                float* dst = p.out + (static_cast<size_t>(tap) * p.ca + m) * p.cb + n_tile * kN;
+#pragma unroll 1
+                for (int ch = 0; ch < 8; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + ch * 32, v);
+                    tmem_ld_wait();
+                    if (has_work && m < p.ca) {
+                        if (ch * 32 + 32 <= n_left && p.vec_ok) {         // 8 x red.v4 instead of 32 scalar reds
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (ch * 32 + j < n_left) atomicAdd(dst + ch * 32 + j, __uint_as_float(v[j]));
+                            for (int j = 0; j < 32; j += 4)
+                                red_add_v4(dst + ch * 32 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                           __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (ch * 32 + j < n_left) atomicAdd(dst + ch * 32 + j, __uint_as_float(v[j]));
+                        }
+                    }
                 }
             }
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) mbar_arrive(&tempty_bar[0]);
         }
     }
 
@@ -205,9 +221,11 @@ int tc_wgrad(const void* g, const void* x, float* dw, int batch, int T, int ca, 
     p.n_tiles = ceil_div(cb, kN);
     p.taps = taps; p.dilation = dilation; p.ca = ca; p.cb = cb; p.out = dw;
     const int tiles = p.m_tiles * p.n_tiles * taps;
-    // enough K splits to give every SM about two items, but at least 16 chunks per item
-    int splits = ceil_div(2 * sm_count(), tiles);
+    // K splits so that one wave of items fills the SMs (every extra split costs a full tile of atomics), but at least
+    // 16 chunks per item
+    int splits = sm_count() / tiles;
     splits = splits < 1 ? 1 : splits;
+    p.vec_ok = (reinterpret_cast<uintptr_t>(dw) % 16 == 0 && cb % 4 == 0) ? 1 : 0;
     const int max_splits = p.chunks_total / 16 > 0 ? p.chunks_total / 16 : 1;
     if (splits > max_splits) splits = max_splits;
     p.chunks_per_split = ceil_div(p.chunks_total, splits);

@@ -11,8 +11,8 @@ kernel calls (no torch op touches an activation):
   backward  per flow, last to first: coupling + WN.end (wgb_coupling_bwd), then per layer, last to first:
               g_acts  = [g_h | g_skip] W_rs          wgb_tc_gemm_seg   (tcgen05, K = 1024)
               g_in    = gate'(g_acts, tanh, sigmoid) wgb_gate_bwd
-              g_h     = g_h + conv_in^T(g_in)        wgb_tc_gemm_seg   (three shifted taps + residual, K = 3072)
-              g_cond += g_in W_cond                  wgb_tc_gemm_seg   (fp32 accumulate)
+              g_h     = g_h + conv_in^T(g_in)        wgb_tc2_wn_res_taps (CTA pairs, three shifted taps, K = 3072)
+              (per flow) g_cond += [g_in_0 .. g_in_7] W_cond   wgb_tc_gemm_seg (K = 8192, one fp32 accumulate per flow)
               dW_in, dW_cond, dW_res                 wgb_tc_wgrad      (tcgen05, MN-major operands, K = B*T)
               biases, WN.end / skip / start weights  wgb_colsum_* / wgb_skinny_wgrad (+ 8 x 512 parameter algebra)
             then WN.start (wgb_start_bwd), the 1x1 conv (wgb_mix_bwd) and finally the upsampler (wgb_upsample_wgrad).
@@ -108,9 +108,9 @@ def _pack_flow(st: Dict[str, Tensor], k: int) -> Dict[str, object]:
     f["b_gate"] = b_gate[:, order].contiguous()
     # data-gradient operands: W^T with the taps mirrored (tap' = 2 - tap)
     f["wt_in"] = w_in.flip(3).permute(0, 2, 3, 1).reshape(N_LAYERS, N_CH, 3 * 2 * N_CH).to(bf).contiguous()
-    wt_cond = torch.zeros(N_LAYERS, N_COND_PAD, 2 * N_CH, device=dev, dtype=bf)
-    wt_cond[:, :N_COND] = w_cond.transpose(1, 2)
-    f["wt_cond"] = wt_cond
+    wt_cond = torch.zeros(N_COND_PAD, N_LAYERS, 2 * N_CH, device=dev, dtype=bf)       # [cond ch][layer][gate ch]: K = layer*1024 + o
+    wt_cond[:N_COND] = w_cond.permute(2, 0, 1)
+    f["wt_cond"] = wt_cond.reshape(N_COND_PAD, N_LAYERS * 2 * N_CH)
     w_rs = [st[p + f"res_skip_layers.{i}.weight"][:, :, 0] for i in range(N_LAYERS)]             # [1024|512, 512]
     b_rs = [st[p + f"res_skip_layers.{i}.bias"] for i in range(N_LAYERS)]
     f["w_res"] = [w_rs[i][:N_CH].to(bf).contiguous() for i in range(N_LAYERS - 1)]
@@ -200,6 +200,8 @@ def _backward(st: Dict[str, Tensor], sv: _Saved, n_flows: int, n_group: int, g_z
     g_skip = torch.empty((b, t, N_CH), device=dev, dtype=bf)
     g_h = torch.empty((b, t, N_CH), device=dev, dtype=bf)
     g_acts = torch.empty((b, t, N_CH), device=dev, dtype=bf)
+    zero_bias = torch.zeros(N_CH, device=dev, dtype=f32)
+    L = N_LAYERS
     for k in reversed(range(n_flows)):
         f, fs = sv.packs[k], sv.flows[k]
         p = f"WN.{k}."
@@ -208,64 +210,72 @@ def _backward(st: Dict[str, Tensor], sv: _Saved, n_flows: int, n_group: int, g_z
         base = 8 - c
         gls = g_log_s[k]
         gls = None if gls is None else gls.float().contiguous()
+        # per-flow gradient buffers: the kernels write straight into slices of these (no per-layer torch ops)
+        g_all = torch.empty((L, 8, N_CH), device=dev, dtype=f32)               # G_i = g_out^T acts_i
+        d_w_rs = torch.empty((L, 2 * N_CH, N_CH), device=dev, dtype=f32)       # rows 0..511 res, 512..1023 skip
+        db_rs = torch.empty((L, 2 * N_CH), device=dev, dtype=f32)
+        d_w_in = torch.empty((L, 3, 2 * N_CH, N_CH), device=dev, dtype=f32)    # [layer][tap][out][in]
+        db_in = torch.empty((L, 2 * N_CH), device=dev, dtype=f32)
+        d_w_cond = torch.empty((L, 2 * N_CH, N_COND), device=dev, dtype=f32)
+        small = torch.empty((3, 8, N_CH), device=dev, dtype=f32)               # [0] start weight, [1][0] start bias, [2] scratch
         _lib.call("wgb_coupling_bwd", g_x, fs.x_mix, fs.log_s, gls, f["w_end_t"], g_out, g_skip, b, t, N_CH, nh, s)
-        g_out_sum = torch.empty(8, device=dev, dtype=f32)
+        g_out_sum = small[2, 0, :8]
         _lib.call("wgb_colsum8_f32", g_out, g_out_sum, rows, 0, s)
-        grads[p + "end.bias"] = g_out_sum[:c].clone()
-        w_end = f["w_end"]                                                     # [c, 512]
-        d_w_end = torch.outer(g_out_sum[:c], f["b_skip_total"])
-        db_skip = w_end.t() @ g_out_sum[:c]                                    # the same for every layer's skip bias
-        for i in reversed(range(N_LAYERS)):
+        for i in reversed(range(L)):
             d = 2 ** i
-            last = i == N_LAYERS - 1
-            # skip rows of res_skip and WN.end through the 8 x 512 product G_i = g_out^T acts_i
-            g_i = torch.empty((8, N_CH), device=dev, dtype=f32)
-            _lib.call("wgb_skinny_wgrad", g_out, fs.acts[i], g_i, rows, N_CH, 0, s)
-            d_w_end = d_w_end + g_i[:c] @ f["w_skip_f32"][i].t()
-            d_w_skip = w_end.t() @ g_i[:c]                                     # [512, 512]
+            last = i == L - 1
+            _lib.call("wgb_skinny_wgrad", g_out, fs.acts[i], g_all[i], rows, N_CH, 0, s)
             if last:
                 _lib.call("wgb_tc_gemm_seg", g_skip, None, 1, 0, f["wt_rs"][i], None, None, g_acts, 1, b, t, N_CH, N_CH,
-                          0, 0, 0, s)
-                grads[p + f"res_skip_layers.{i}.weight"] = d_w_skip.unsqueeze(2)
-                grads[p + f"res_skip_layers.{i}.bias"] = db_skip.clone()
+                          0, 0, 0, 0, s)
             else:
                 _lib.call("wgb_tc_gemm_seg", g_h, g_skip, 2, 0b10, f["wt_rs"][i], None, None, g_acts, 1, b, t, N_CH, N_CH,
-                          0, 0, 0, s)
-                d_w_res = torch.empty((1, N_CH, N_CH), device=dev, dtype=f32)
-                _lib.call("wgb_tc_wgrad", g_h, fs.acts[i], d_w_res, b, t, N_CH, N_CH, 1, 1, 0, s)
-                db_res = torch.empty(N_CH, device=dev, dtype=f32)
-                _lib.call("wgb_colsum_bf16", g_h, db_res, rows, N_CH, 0, s)
-                grads[p + f"res_skip_layers.{i}.weight"] = torch.cat([d_w_res[0], d_w_skip], dim=0).unsqueeze(2)
-                grads[p + f"res_skip_layers.{i}.bias"] = torch.cat([db_res, db_skip])
+                          0, 0, 0, 0, s)
+                _lib.call("wgb_tc_wgrad", g_h, fs.acts[i], d_w_rs[i, :N_CH], b, t, N_CH, N_CH, 1, 1, 0, s)
+                _lib.call("wgb_colsum_bf16", g_h, db_rs[i, :N_CH], rows, N_CH, 0, s)
             g_in = fs.ts[i]                                                    # (tanh | sigmoid) -> gradient, in place
-            _lib.call("wgb_gate_bwd", g_acts, g_in, rows, N_CH, s)
-            db_in = torch.empty(2 * N_CH, device=dev, dtype=f32)
-            _lib.call("wgb_colsum_bf16", g_in, db_in, rows, 2 * N_CH, 0, s)
-            grads[p + f"in_layers.{i}.bias"] = db_in
-            grads[p + f"cond_layers.{i}.bias"] = db_in.clone()
-            d_w_in = torch.empty((3, 2 * N_CH, N_CH), device=dev, dtype=f32)
-            _lib.call("wgb_tc_wgrad", g_in, fs.h[i], d_w_in, b, t, 2 * N_CH, N_CH, 3, d, 0, s)
-            grads[p + f"in_layers.{i}.weight"] = d_w_in.permute(1, 2, 0).contiguous()
-            d_w_cond = torch.empty((1, 2 * N_CH, N_COND), device=dev, dtype=f32)
-            _lib.call("wgb_tc_wgrad", g_in, cond, d_w_cond, b, t, 2 * N_CH, N_COND, 1, 1, 0, s)
-            grads[p + f"cond_layers.{i}.weight"] = d_w_cond[0].unsqueeze(2)
-            _lib.call("wgb_tc_gemm_seg", g_in, None, 1, 0, f["wt_cond"][i], None, g_cond, g_cond, 0, b, t, N_COND_PAD,
-                      2 * N_CH, 0, 0, 0, s)
-            _lib.call("wgb_tc_gemm_seg", g_in, None, 3, 0, f["wt_in"][i], None, None if last else g_h, g_h, 1, b, t, N_CH,
-                      2 * N_CH, -d, d, 0, s)
-        grads[p + "end.weight"] = d_w_end.unsqueeze(2)
+            _lib.call("wgb_gate_bwd", g_acts, g_in, db_in[i], rows, N_CH, s)
+            _lib.call("wgb_tc_wgrad", g_in, fs.h[i], d_w_in[i], b, t, 2 * N_CH, N_CH, 3, d, 0, s)
+            _lib.call("wgb_tc_wgrad", g_in, cond, d_w_cond[i], b, t, 2 * N_CH, N_COND, 1, 1, 0, s)
+            if last:
+                g_h.zero_()
+            _lib.call("wgb_tc2_wn_res_taps", g_in, f["wt_in"][i], zero_bias, g_h, g_h, b, t, t, 2 * N_CH, 3, d, s)
+        # conditioning gradient of the whole flow: the eight layers' g_in (still in fs.ts) K-concatenated, one fp32
+        # read-modify-write of g_cond per flow
+        _lib.call("wgb_tc_gemm_seg", fs.ts, None, L, 0, f["wt_cond"], None, g_cond, g_cond, 0, b, t, N_COND_PAD,
+                  2 * N_CH, 0, 0, 0, 1, s)
         # WN.start (g_h is now the gradient of h_0)
-        db_start = torch.empty(N_CH, device=dev, dtype=f32)
-        _lib.call("wgb_colsum_bf16", g_h, db_start, rows, N_CH, 0, s)
-        grads[p + "start.bias"] = db_start
-        d_start = torch.empty((8, N_CH), device=dev, dtype=f32)
-        _lib.call("wgb_skinny_wgrad", fs.x_mix, g_h, d_start, rows, N_CH, 0, s)
-        grads[p + "start.weight"] = d_start[base: base + nh].t().contiguous().unsqueeze(2)
+        _lib.call("wgb_colsum_bf16", g_h, small[1, 0], rows, N_CH, 0, s)
+        _lib.call("wgb_skinny_wgrad", fs.x_mix, g_h, small[0], rows, N_CH, 0, s)
         _lib.call("wgb_start_bwd", g_x, g_h, f["w_start"], rows, N_CH, nh, s)
         # invertible 1x1 conv
         d_mix = torch.empty((8, 8), device=dev, dtype=f32)
         _lib.call("wgb_mix_bwd", g_x, fs.x_pre, f["w_mix"], d_mix, rows, c, s)
+        # parameter-space algebra (8 x 512 matrices): WN.end and the skip rows of res_skip through G_i
+        w_end = f["w_end"]                                                     # [c, 512]
+        w_skip = torch.stack(f["w_skip_f32"])                                  # [L, 512 (out), 512 (in)]
+        g_c = g_all[:, :c]                                                     # [L, c, 512]
+        d_w_end = torch.einsum("ijn,imn->jm", g_c, w_skip) + torch.outer(g_out_sum[:c], f["b_skip_total"])
+        d_w_skip = torch.einsum("jm,ijn->imn", w_end, g_c)                     # [L, 512, 512]
+        db_skip = w_end.t() @ g_out_sum[:c]
+        d_w_rs[: L - 1, N_CH:] = d_w_skip[: L - 1]
+        d_w_rs[L - 1, :N_CH] = d_w_skip[L - 1]
+        db_rs[: L - 1, N_CH:] = db_skip
+        db_rs[L - 1, :N_CH] = db_skip
+        d_w_in_p = d_w_in.permute(0, 2, 3, 1).contiguous()                     # [L, out, in, tap]
+        grads[p + "end.weight"] = d_w_end.unsqueeze(2)
+        grads[p + "end.bias"] = g_out_sum[:c].clone()
+        grads[p + "start.weight"] = small[0, base: base + nh].t().contiguous().unsqueeze(2)
+        grads[p + "start.bias"] = small[1, 0]
         grads[f"convinv.{k}.conv.weight"] = d_mix[:c, :c].contiguous().unsqueeze(2)
+        for i in range(L):
+            n_rs = 2 * N_CH if i < L - 1 else N_CH
+            grads[p + f"res_skip_layers.{i}.weight"] = d_w_rs[i, :n_rs].unsqueeze(2)
+            grads[p + f"res_skip_layers.{i}.bias"] = db_rs[i, :n_rs]
+            grads[p + f"in_layers.{i}.weight"] = d_w_in_p[i]
+            grads[p + f"in_layers.{i}.bias"] = db_in[i]
+            grads[p + f"cond_layers.{i}.weight"] = d_w_cond[i].unsqueeze(2)
+            grads[p + f"cond_layers.{i}.bias"] = db_in[i].clone()
         fs.h = fs.acts = fs.ts = None                                          # release this flow's activations
     up = sv.up
     ksize = up.up_stride * up.up_taps
@@ -356,11 +366,11 @@ class FusedAdam:
 
     def gather_grads(self) -> Tensor:
         """Copy every .grad into the flat gradient buffer (missing grads count as zero); returns that buffer."""
-        for p, gv in zip(self.params, self.views):
-            if p.grad is None:
-                gv.zero_()
-            else:
-                gv.copy_(p.grad)
+        have = [(gv, p.grad) for p, gv in zip(self.params, self.views) if p.grad is not None]
+        if len(have) != len(self.params):
+            self.grad.zero_()
+        if have:
+            torch._foreach_copy_([gv for gv, _ in have], [g for _, g in have])     # one batched launch sequence
         return self.grad
 
     def step(self, grad_scale: float = 1.0, gathered: bool = False):

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--samples", type=int, default=16000)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--breakdown", action="store_true", help="one extra step with CUDA events around every C-ABI call")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     cfg = syn.load_config()
@@ -55,12 +56,38 @@ def main():
         scale = allreduce_gradients(opt)
         opt.step(grad_scale=scale, gathered=True)
         if e: e[3].record()
-        losses.append(float(loss.detach()))
+        losses.append(loss.detach())          # no host sync inside the loop: the next step's launches overlap this one's kernels
     torch.cuda.synchronize()
+    losses = [float(v) for v in losses]
     fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
     bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
     optim = sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps
     total = fwd + bwd + optim
+    breakdown = None
+    if args.breakdown:
+        from text2speech_b200 import _lib
+        raw_call, events = _lib.call, []
+
+        def timed_call(name, *a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            raw_call(name, *a)
+            e1.record()
+            events.append((name, e0, e1))
+
+        _lib.call = timed_call
+        opt.zero_grad()
+        loss = crit(model((mel, audio)))
+        loss.backward()
+        opt.step(grad_scale=allreduce_gradients(opt), gathered=True)
+        torch.cuda.synchronize()
+        _lib.call = raw_call
+        agg = {}
+        for name, a, b in events:
+            n, ms = agg.get(name, (0, 0.0))
+            agg[name] = (n + 1, ms + a.elapsed_time(b))
+        breakdown = {k: {"launches": n, "total_ms": round(ms, 3), "avg_ms": round(ms / n, 4)}
+                     for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])}
     t = args.samples // 8
     flop_fwd = 522_190_848 * t * args.batch
     print(json.dumps({
@@ -73,6 +100,7 @@ def main():
                            "step": 3 * flop_fwd / (total * 1e-3) / 1e12},
         "loss_first_last": [losses[0], losses[-1]], "steps": args.steps, "warmup": args.warmup,
         "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+        "breakdown": breakdown,
     }))
 
 

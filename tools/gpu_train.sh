@@ -7,5 +7,5 @@ timeout 1200 python -m pytest tests/test_training.py -m gpu -q --timeout 900 -p 
 echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
 tail -40 gpurun_out/${TAG}_pytest.log
 if [ -f tools/bench_train.py ] && [ "${3:-}" = "bench" ]; then
-  timeout 900 python tools/bench_train.py > gpurun_out/${TAG}_bench.log 2>&1; tail -3 gpurun_out/${TAG}_bench.log
+  timeout 900 python tools/bench_train.py --breakdown > gpurun_out/${TAG}_bench.log 2>&1; tail -3 gpurun_out/${TAG}_bench.log
 fi
