@@ -325,6 +325,11 @@ WGB_API int wgb_upsample_wgrad(const float* mel, const float* g_cond, float* dw,
  * the gradient is multiplied by grad_scale first (1 / world_size after a sum all-reduce). */
 WGB_API int wgb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                           float eps, int step, float grad_scale, void* stream);
+/* The same step with the step counter on the device (incremented by the call): CUDA-graph replayable. */
+WGB_API int wgb_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                              float eps, int* step_dev, float grad_scale, void* stream);
+/* log|det W| of a c x c matrix (c <= 8) and (W^-1)^T = its gradient (glow.py:100): out[0], inv_t fp32 [c][c]. */
+WGB_API int wgb_logdet(const float* w, float* out, float* inv_t, int c, void* stream);
 
 #ifdef __cplusplus
 }

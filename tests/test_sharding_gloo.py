@@ -74,3 +74,33 @@ def test_multi_gpu_vocoder_refuses_cpu_only_hosts():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError):
         MultiGpuVocoder(torch.nn.Identity())
+
+
+def _grad_worker(rank, world, port, out_dir):
+    """Data-parallel gradient reduction of the training direction (waveglow/distributed.py:90-142): every rank ends up
+    with the SUM in its flat gradient buffer and the 1 / world_size scale to hand to the optimiser."""
+    from text2speech_b200.training import allreduce_gradients
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class FlatOptimizer:                       # the two members allreduce_gradients uses of FusedAdam
+        def __init__(self):
+            self.grad = torch.zeros(10)
+
+        def gather_grads(self):
+            self.grad.copy_(torch.arange(10, dtype=torch.float32) * (rank + 1))
+            return self.grad
+
+    opt = FlatOptimizer()
+    scale = allreduce_gradients(opt)
+    want = torch.arange(10, dtype=torch.float32) * sum(r + 1 for r in range(world))
+    ok = torch.equal(opt.grad, want) and abs(scale - 1.0 / world) < 1e-12
+    with open(os.path.join(out_dir, f"g{rank}.json"), "w") as f:
+        json.dump({"ok": bool(ok)}, f)
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_grad_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all(json.load(open(tmp_path / f"g{r}.json"))["ok"] for r in range(2))

@@ -369,3 +369,54 @@ def test_training_loop_with_fused_adam_and_flat_allreduce(lib):
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses      # a small enough step lowers the NLL
     moved = max(float((p.detach() - q).abs().max()) for p, q in zip(m.parameters(), before))
     assert 0.5 * lr <= moved <= 3.2 * lr, moved
+
+
+@pytest.mark.gpu
+def test_logdet_kernel_matches_torch(lib):
+    from text2speech_b200.training import _LogDet
+    g = torch.Generator().manual_seed(13)
+    for c in (8, 6, 4, 2):
+        w = torch.randn((c, c, 1), generator=g).to(DEV).requires_grad_(True)
+        w_ref = w.detach().clone().requires_grad_(True)
+        got = _LogDet.apply(w, 3.0)
+        want = 3.0 * torch.linalg.slogdet(w_ref.squeeze(-1))[1]
+        assert abs(float(got) - float(want)) <= 1e-5 * max(1.0, abs(float(want)))
+        got.backward()
+        want.backward()
+        assert util.rel_l2(w.grad.cpu(), w_ref.grad.cpu()) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_graphed_train_step_matches_eager(lib):
+    """The CUDA-graph replay of a whole step (forward, loss, backward, gradient gather, Adam) follows the eager loop."""
+    import text2speech_b200 as t2s
+    from text2speech_b200.training import FusedAdam, GraphedTrainStep
+    mel, wav = train_inputs()
+    mel, wav = mel.to(DEV), wav.to(DEV)
+    crit = t2s.WaveGlowLoss(SIGMA)
+    runs = []
+    for graphed in (False, True):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = t2s.WaveGlow(**train_config())
+        m.load_state_dict(_train_state())
+        m = m.to(DEV).train()
+        opt = FusedAdam(m.parameters(), lr=1e-6)
+        losses = []
+        if graphed:
+            step = GraphedTrainStep(m, opt, crit, mel.shape[0], mel.shape[1], mel.shape[2], wav.shape[1])
+            for _ in range(3):
+                losses.append(float(step(mel, wav)))
+            assert opt.step_count == 3 and int(opt.step_dev.item()) == 3
+        else:
+            for _ in range(3):
+                opt.zero_grad()
+                loss = crit(m((mel, wav)))
+                loss.backward()
+                opt.step()
+                losses.append(float(loss.detach()))
+        runs.append(losses)
+    eager, graph = runs
+    assert eager[-1] < eager[0] and graph[-1] < graph[0], runs
+    for a, b in zip(eager, graph):
+        assert abs(a - b) <= 0.02 * abs(eager[0]) + 1e-4, runs

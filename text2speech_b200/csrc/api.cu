@@ -69,6 +69,8 @@ int colsum8_f32(const float*, float*, long long, int, cudaStream_t);
 int mix_bwd(float*, const float*, const float*, float*, long long, int, cudaStream_t);
 int upsample_wgrad(const float*, const float*, float*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
 int adam_step(float*, const float*, float*, float*, long long, float, float, float, float, int, float, cudaStream_t);
+int adam_step_dev(float*, const float*, float*, float*, long long, float, float, float, float, int*, float, cudaStream_t);
+int logdet(const float*, float*, float*, int, cudaStream_t);
 // stft.cu
 int stft_reflect_pad(const float*, float*, int, int, int, long long, cudaStream_t);
 int stft_reflect_pad_split(const float*, void*, void*, int, int, int, long long, cudaStream_t);
@@ -330,4 +332,11 @@ WGB_API int wgb_adam_step(float* p, const float* g, float* m, float* v, long lon
 WGB_API int wgb_tc2_wn_res_taps(const void* a, const void* w, const float* bias, const void* h_in, void* h_out, int batch,
                                 int T, long long h_batch_rows, int C, int taps, int dilation, void* stream) {
     return tc2_wn_res_taps(a, w, bias, h_in, h_out, batch, T, h_batch_rows, C, taps, dilation, S(stream));
+}
+WGB_API int wgb_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                              float eps, int* step_dev, float grad_scale, void* stream) {
+    return adam_step_dev(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, grad_scale, S(stream));
+}
+WGB_API int wgb_logdet(const float* w, float* out, float* inv_t, int c, void* stream) {
+    return logdet(w, out, inv_t, c, S(stream));
 }

@@ -517,6 +517,84 @@ __global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g
     }
 }
 
+// The same update with the step counter on the device (CUDA-graph replay: nothing in the launch changes per step).
+__global__ void adam_tick_kernel(int* step) { *step += 1; }
+__global__ void adam_dev_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                float4* __restrict__ v, long long n4, float lr, float b1, float b2, float eps,
+                                const int* __restrict__ step, float grad_scale) {
+    const float st = static_cast<float>(*step);
+    const float bc1 = 1.f - powf(b1, st), bc2_sqrt = sqrtf(1.f - powf(b2, st));
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+        float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float gr = ga[e] * grad_scale;
+            ma[e] = b1 * ma[e] + (1.f - b1) * gr;
+            va[e] = b2 * va[e] + (1.f - b2) * gr * gr;
+            pa[e] -= (lr / bc1) * (ma[e] / (sqrtf(va[e]) / bc2_sqrt + eps));
+        }
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+}
+
+int adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                  int* step_dev, float grad_scale, cudaStream_t stream) {
+    WGB_REQUIRE(p && g && m && v && step_dev, "null pointer");
+    WGB_REQUIRE(n > 0 && n % 4 == 0, "n (%lld) must be a positive multiple of 4 (pad the flat buffer)", n);
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    adam_tick_kernel<<<1, 1, 0, stream>>>(step_dev);
+    adam_dev_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g),
+                                                                       reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
+                                                                       n / 4, lr, beta1, beta2, eps, step_dev, grad_scale);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ log|det W|
+// Invertible1x1Conv's log-determinant and its gradient (glow.py:100: torch.logdet(W); d logdet / dW = W^-T) for a
+// c x c matrix, c <= 8, by Gauss-Jordan elimination with partial pivoting in one thread (fp64 internally).
+// w fp32 [c][c]; out[0] = log|det W|; inv_t fp32 [c][c] = (W^-1)^T.
+__global__ void logdet_kernel(const float* __restrict__ w, float* __restrict__ out, float* __restrict__ inv_t, int c) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double a[8][16];
+    for (int i = 0; i < c; ++i)
+        for (int j = 0; j < c; ++j) {
+            a[i][j] = w[i * c + j];
+            a[i][c + j] = i == j ? 1.0 : 0.0;
+        }
+    double logdet = 0.0;
+    for (int col = 0; col < c; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < c; ++r)
+            if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
+        if (piv != col)
+            for (int j = 0; j < 2 * c; ++j) { const double t = a[col][j]; a[col][j] = a[piv][j]; a[piv][j] = t; }
+        const double d = a[col][col];
+        logdet += log(fabs(d));
+        const double inv = 1.0 / d;
+        for (int j = 0; j < 2 * c; ++j) a[col][j] *= inv;
+        for (int r = 0; r < c; ++r) {
+            if (r == col) continue;
+            const double f = a[r][col];
+            for (int j = 0; j < 2 * c; ++j) a[r][j] -= f * a[col][j];
+        }
+    }
+    out[0] = static_cast<float>(logdet);
+    for (int i = 0; i < c; ++i)
+        for (int j = 0; j < c; ++j) inv_t[j * c + i] = static_cast<float>(a[i][c + j]);
+}
+
+int logdet(const float* w, float* out, float* inv_t, int c, cudaStream_t stream) {
+    WGB_REQUIRE(w && out && inv_t, "null pointer");
+    WGB_REQUIRE(c >= 1 && c <= 8, "c must be in 1..8 (got %d)", c);
+    logdet_kernel<<<1, 32, 0, stream>>>(w, out, inv_t, c);
+    WGB_LAUNCH_CHECK();
+    return WGB_OK;
+}
+
 int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
               int step, float grad_scale, cudaStream_t stream) {
     WGB_REQUIRE(p && g && m && v, "null pointer");

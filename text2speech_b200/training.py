@@ -84,12 +84,23 @@ class _UpsampleOperands:
         self.w_up, self.b_up = w.to(torch.bfloat16), b
 
 
+_ORDER_CACHE: Dict[str, Tensor] = {}
+
+
+def _gate_order(dev) -> Tensor:
+    """gate_row_order on the device, cached (no host-to-device copy inside a step: CUDA-graph capturable)."""
+    key = str(dev)
+    if key not in _ORDER_CACHE:
+        _ORDER_CACHE[key] = gate_row_order(N_CH).to(dev)
+    return _ORDER_CACHE[key]
+
+
 def _pack_flow(st: Dict[str, Tensor], k: int) -> Dict[str, object]:
     """bf16 / fp32 kernel operands of flow k from the live fp32 weights (all on the device; runs every step)."""
     p = f"WN.{k}."
     dev = st[p + "start.weight"].device
     bf = torch.bfloat16
-    order = gate_row_order(N_CH).to(dev)
+    order = _gate_order(dev)
     f: Dict[str, object] = {}
     w_end = st[p + "end.weight"][:, :, 0]                                   # [2 n_half, 512]
     n_half = w_end.shape[0] // 2
@@ -316,6 +327,27 @@ class _Flow(torch.autograd.Function):
         return (None, None, None, None, None, *out)
 
 
+class _LogDet(torch.autograd.Function):
+    """scale * log|det W| for a c x c matrix, c <= 8 (glow.py:100) as one capturable kernel; backward = scale W^-T."""
+
+    @staticmethod
+    def forward(ctx, w, scale):
+        c = w.shape[0]
+        w2 = w.detach().float().reshape(c, c).contiguous()
+        out = torch.empty(1, device=w.device, dtype=torch.float32)
+        inv_t = torch.empty((c, c), device=w.device, dtype=torch.float32)
+        with torch.cuda.device(w.device):
+            _lib.call("wgb_logdet", w2, out, inv_t, c, _lib.stream_ptr())
+        ctx.save_for_backward(inv_t)
+        ctx.scale, ctx.shape = scale, w.shape
+        return out[0] * scale
+
+    @staticmethod
+    def backward(ctx, g):
+        (inv_t,) = ctx.saved_tensors
+        return (g * ctx.scale * inv_t).reshape(ctx.shape), None
+
+
 def forward_autograd(model, spect: Tensor, audio: Tensor):
     """WaveGlow.forward under autograd (glow.py:207-249): returns (z, log_s_list, log_det_W_list) whose backward fills
     the ``.grad`` of every model parameter."""
@@ -327,7 +359,7 @@ def forward_autograd(model, spect: Tensor, audio: Tensor):
     outs = _Flow.apply(names, model.n_flows, model.n_group, spect, audio, *weights)
     z, log_s_list = outs[0], list(outs[1:])
     bt = z.shape[0] * z.shape[2]
-    log_det = [bt * torch.logdet(model.convinv[k].conv.weight.squeeze(-1).float()) for k in range(model.n_flows)]   # glow.py:100
+    log_det = [_LogDet.apply(model.convinv[k].conv.weight, float(bt)) for k in range(model.n_flows)]   # glow.py:100
     return z, log_s_list, log_det
 
 
@@ -352,6 +384,7 @@ class FusedAdam:
         self.grad = torch.zeros(self.n, device=dev, dtype=torch.float32)
         self.m = torch.zeros(self.n, device=dev, dtype=torch.float32)
         self.v = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         off = 0
         self.views = []
         for p, sz, pt in zip(self.params, sizes, pitch):
@@ -374,12 +407,14 @@ class FusedAdam:
         return self.grad
 
     def step(self, grad_scale: float = 1.0, gathered: bool = False):
+        """The step counter lives on the device (incremented by the kernel), so a captured step replays correctly."""
         if not gathered:
             self.gather_grads()
         self.step_count += 1
         with torch.cuda.device(self.flat.device):
-            _lib.call("wgb_adam_step", self.flat, self.grad, self.m, self.v, self.n, float(self.lr), float(self.betas[0]),
-                      float(self.betas[1]), float(self.eps), self.step_count, float(grad_scale), _lib.stream_ptr())
+            _lib.call("wgb_adam_step_dev", self.flat, self.grad, self.m, self.v, self.n, float(self.lr),
+                      float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_dev, float(grad_scale),
+                      _lib.stream_ptr())
 
 
 def allreduce_gradients(optimizer: FusedAdam, group=None) -> float:
@@ -391,3 +426,55 @@ def allreduce_gradients(optimizer: FusedAdam, group=None) -> float:
         return 1.0
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return 1.0 / dist.get_world_size(group)
+
+
+class GraphedTrainStep:
+    """One training step (forward, criterion, backward, gradient gather [, Adam]) captured in a CUDA graph for a fixed
+    batch shape: the ~4000 launches of a step (this package's kernels plus the parameter-sized torch ops around them)
+    become one graph launch, which matters because the step is otherwise host-bound below ~32 x 16000 samples.
+
+        step = GraphedTrainStep(model, optimizer, criterion, batch, n_mel, frames, samples)
+        loss = step(mel, audio)            # copies the batch into the graph's static buffers, replays, returns the loss
+
+    With ``world_size > 1`` build it with ``include_optimizer=False``: the graph then ends after the gradient gather,
+    and the caller runs ``allreduce_gradients`` + ``optimizer.step(gathered=True)`` eagerly (two launches)."""
+
+    def __init__(self, model, optimizer: FusedAdam, criterion, batch: int, n_mel: int, frames: int, samples: int,
+                 include_optimizer: bool = True, warmup: int = 2):
+        dev = optimizer.flat.device
+        self.model, self.opt, self.include_optimizer = model, optimizer, include_optimizer
+        self.mel = torch.zeros((batch, n_mel, frames), device=dev, dtype=torch.float32)
+        self.audio = torch.zeros((batch, samples), device=dev, dtype=torch.float32)
+        # warm-up on a side stream (allocator, cudaFuncSetAttribute, lazy module init), restoring the training state
+        # afterwards so that building the graph does not count as training
+        keep = [t.clone() for t in (optimizer.flat, optimizer.m, optimizer.v, optimizer.step_dev)]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._one_step(criterion)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        optimizer.zero_grad()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._one_step(criterion)
+        for dst, src in zip((optimizer.flat, optimizer.m, optimizer.v, optimizer.step_dev), keep):
+            dst.copy_(src)
+        optimizer.step_count = int(keep[3].item())
+
+    def _one_step(self, criterion):
+        self.opt.zero_grad()
+        loss = criterion(self.model((self.mel, self.audio)))
+        loss.backward()
+        self.opt.gather_grads()
+        if self.include_optimizer:
+            self.opt.step(gathered=True)
+        return loss.detach()
+
+    def __call__(self, mel: Tensor, audio: Tensor) -> Tensor:
+        self.mel.copy_(mel, non_blocking=True)
+        self.audio.copy_(audio, non_blocking=True)
+        self.graph.replay()
+        if self.include_optimizer:
+            self.opt.step_count += 1
+        return self.loss

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--samples", type=int, default=16000)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--graph", action="store_true", help="replay the whole step from one CUDA graph (GraphedTrainStep)")
     ap.add_argument("--breakdown", action="store_true", help="one extra step with CUDA events around every C-ABI call")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -43,6 +44,32 @@ def main():
     g = torch.Generator().manual_seed(1)
     audio = (0.1 * torch.randn((args.batch, args.samples), generator=g)).clamp(-1, 1).to(dev)
     mel = syn.synthetic_mel(args.batch, frames, seed=0).to(dev)
+    if args.graph:
+        from text2speech_b200.training import GraphedTrainStep
+        step = GraphedTrainStep(model, opt, crit, args.batch, mel.shape[1], frames, args.samples)
+        losses = []
+        for _ in range(args.warmup):
+            step(mel, audio)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            losses.append(step(mel, audio).clone())
+        e1.record()
+        torch.cuda.synchronize()
+        total = e0.elapsed_time(e1) / args.steps
+        t = args.samples // 8
+        flop_fwd = 522_190_848 * t * args.batch
+        print(json.dumps({
+            "metric": "waveglow_train_step_ms", "value": total, "unit": "ms", "higher_is_better": False,
+            "config": {"workload": f"WaveGlow train step, batch {args.batch} x {args.samples} samples ({frames} frames), "
+                                   "config.json arch, weight norm, Adam; whole step replayed from one CUDA graph"},
+            "samples_per_s": args.batch * args.samples / (total * 1e-3),
+            "wn_gemm_tflops": {"step": 3 * flop_fwd / (total * 1e-3) / 1e12},
+            "loss_first_last": [float(losses[0]), float(losses[-1])], "steps": args.steps, "warmup": args.warmup,
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+        }))
+        return
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     losses = []
     for it in range(args.warmup + args.steps):
