@@ -291,6 +291,12 @@ WGB_API int wgb_tc_gemm_seg(const void* a0, const void* a1, int n_seg, int seg_m
  * [B,h_batch_rows,512] (h_in may alias h_out). */
 WGB_API int wgb_tc2_wn_res_taps(const void* a, const void* w, const float* bias, const void* h_in, void* h_out, int batch,
                                 int T, long long h_batch_rows, int C, int taps, int dilation, void* stream);
+/* The same kernel with a general segmented K: h_out = h_in + bias + sum_s W[:, s*C:(s+1)*C] A_s[b, t + shift0 + s*dshift, :],
+ * A_s = a1 if bit s of seg_mask else a0.  The res_skip data gradient g_acts = [g_h | g_skip] W_rs runs through it with
+ * h_in = zeros. */
+WGB_API int wgb_tc2_wn_res_seg(const void* a0, const void* a1, int n_seg, int seg_mask, const void* w, const float* bias,
+                               const void* h_in, void* h_out, int batch, int T, long long h_batch_rows, int C, int shift0,
+                               int dshift, void* stream);
 /* dw[tap][m][n] (+)= sum_{b,t} g[b,t,m] x[b, t + (tap - (taps-1)/2)*dilation, n] on tcgen05 with both operands
  * MN-major (no transposed copies).  g bf16 [B,T,ca] (ca % 64 == 0), x bf16 [B,T,cb] (cb % 8 == 0), dw fp32
  * [taps][ca][cb]; accumulate = 0 clears dw first.  Weight gradients of in_layers / cond_layers / res_skip_layers. */
@@ -301,9 +307,10 @@ WGB_API int wgb_tc_wgrad(const void* g, const void* x, float* dw, int batch, int
 WGB_API int wgb_gate_bwd(const void* g_acts, void* ts, float* db, long long rows, int n_ch, void* stream);
 /* Affine coupling + WN.end backward (glow.py:241-246): see csrc/train.cu.  g_x fp32 [rows,8] in/out, x_mix = flow state
  * before the coupling, log_s / g_log_s fp32 [B,n_half,T] (g_log_s may be NULL), w_end_t fp32 [n_ch][8];
- * g_out fp32 [rows,8], g_skip bf16 [rows,n_ch]. */
+ * g_out fp32 [rows,8], g_skip bf16 [rows,n_ch]; stack (optional) bf16 [rows,64] = hi/lo(g_out) | hi/lo(x_mix) | 1 | 0:
+ * the operand that lets wgb_tc_wgrad compute the <= 8-channel weight gradients and the bias column sums. */
 WGB_API int wgb_coupling_bwd(float* g_x, const float* x_mix, const float* log_s, const float* g_log_s, const float* w_end_t,
-                             float* g_out, void* g_skip, int batch, int T, int n_ch, int n_half, void* stream);
+                             float* g_out, void* g_skip, void* stack, int batch, int T, int n_ch, int n_half, void* stream);
 /* g_x[a0 channels] += g_h0 W_start (glow.py:156); w_start fp32 [n_ch][n_half]. */
 WGB_API int wgb_start_bwd(float* g_x, const void* g_h0, const float* w_start, long long rows, int n_ch, int n_half,
                           void* stream);

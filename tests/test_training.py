@@ -191,7 +191,9 @@ def test_pointwise_backward_kernels(lib):
     gx = g_x.to(DEV).clone()
     g_out = torch.empty((rows, 8), device=DEV)
     g_skip = torch.empty((rows, 512), device=DEV, dtype=torch.bfloat16)
-    lib.call("wgb_coupling_bwd", gx, x_mix.to(DEV), log_s.to(DEV), g_ls.to(DEV), w_end_t.to(DEV), g_out, g_skip, b, t, 512, nh, s)
+    stack = torch.empty((rows, 64), device=DEV, dtype=torch.bfloat16)
+    lib.call("wgb_coupling_bwd", gx, x_mix.to(DEV), log_s.to(DEV), g_ls.to(DEV), w_end_t.to(DEV), g_out, g_skip, stack, b, t,
+             512, nh, s)
     ls_rows = log_s.permute(0, 2, 1).reshape(rows, nh)
     gls_rows = g_ls.permute(0, 2, 1).reshape(rows, nh)
     ga1p = g_x[:, base + nh:]
@@ -203,6 +205,11 @@ def test_pointwise_backward_kernels(lib):
     assert util.rel_l2(g_out.cpu(), want_out) <= 1e-6
     assert util.rel_l2(gx.cpu(), want_gx) <= 1e-6
     assert util.rel_l2(g_skip.float().cpu(), want_out @ w_end_t.t()) <= 4e-3
+    # the [rows, 64] stack: hi + lo parts reproduce g_out / x_mix to fp32 accuracy, column 32 is one
+    st = stack.float().cpu()
+    assert util.rel_l2(st[:, 0:8] + st[:, 8:16], want_out) <= 2e-5
+    assert util.rel_l2(st[:, 16:24] + st[:, 24:32], x_mix) <= 2e-5
+    assert torch.equal(st[:, 32], torch.ones(rows)) and float(st[:, 33:].abs().max()) == 0.0
     # skinny reductions
     bb = torch.randn((rows, 512), generator=g).bfloat16()
     out = torch.empty((8, 512), device=DEV)

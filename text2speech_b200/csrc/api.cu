@@ -56,11 +56,13 @@ int audio_to_int16(const float*, void*, long long, float, cudaStream_t);
 // training direction: wn_tc2.cu, wn_tc.cu, wn_wgrad.cu, train.cu
 int tc2_wn_res_taps(const void*, const void*, const float*, const void*, void*, int, int, long long, int, int, int,
                     cudaStream_t);
+int tc2_wn_res_seg(const void*, const void*, int, int, const void*, const float*, const void*, void*, int, int, long long, int,
+                   int, int, cudaStream_t);
 int tc_gemm_seg(const void*, const void*, int, int, const void*, const float*, const void*, void*, int, int, int, int, int,
                 int, int, int, int, cudaStream_t);
 int tc_wgrad(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int gate_bwd(const void*, void*, float*, long long, int, cudaStream_t);
-int coupling_bwd(float*, const float*, const float*, const float*, const float*, float*, void*, int, int, int, int,
+int coupling_bwd(float*, const float*, const float*, const float*, const float*, float*, void*, void*, int, int, int, int,
                  cudaStream_t);
 int start_bwd(float*, const void*, const float*, long long, int, int, cudaStream_t);
 int skinny_wgrad(const float*, const void*, float*, long long, int, int, cudaStream_t);
@@ -301,8 +303,8 @@ WGB_API int wgb_gate_bwd(const void* g_acts, void* ts, float* db, long long rows
     return gate_bwd(g_acts, ts, db, rows, n_ch, S(stream));
 }
 WGB_API int wgb_coupling_bwd(float* g_x, const float* x_mix, const float* log_s, const float* g_log_s, const float* w_end_t,
-                             float* g_out, void* g_skip, int batch, int T, int n_ch, int n_half, void* stream) {
-    return coupling_bwd(g_x, x_mix, log_s, g_log_s, w_end_t, g_out, g_skip, batch, T, n_ch, n_half, S(stream));
+                             float* g_out, void* g_skip, void* stack, int batch, int T, int n_ch, int n_half, void* stream) {
+    return coupling_bwd(g_x, x_mix, log_s, g_log_s, w_end_t, g_out, g_skip, stack, batch, T, n_ch, n_half, S(stream));
 }
 WGB_API int wgb_start_bwd(float* g_x, const void* g_h0, const float* w_start, long long rows, int n_ch, int n_half,
                           void* stream) {
@@ -339,4 +341,9 @@ WGB_API int wgb_adam_step_dev(float* p, const float* g, float* m, float* v, long
 }
 WGB_API int wgb_logdet(const float* w, float* out, float* inv_t, int c, void* stream) {
     return logdet(w, out, inv_t, c, S(stream));
+}
+WGB_API int wgb_tc2_wn_res_seg(const void* a0, const void* a1, int n_seg, int seg_mask, const void* w, const float* bias,
+                               const void* h_in, void* h_out, int batch, int T, long long h_batch_rows, int C, int shift0,
+                               int dshift, void* stream) {
+    return tc2_wn_res_seg(a0, a1, n_seg, seg_mask, w, bias, h_in, h_out, batch, T, h_batch_rows, C, shift0, dshift, S(stream));
 }

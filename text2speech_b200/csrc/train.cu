@@ -103,7 +103,8 @@ int gate_bwd(const void* g_acts, void* ts, float* db, long long rows, int n_ch, 
 template <int NHALF>
 __global__ void coupling_bwd_kernel(float* __restrict__ g_x, const float* __restrict__ x_mix, const float* __restrict__ log_s,
                                     const float* __restrict__ g_ls, const float* __restrict__ w_end_t,
-                                    float* __restrict__ g_out, __nv_bfloat16* __restrict__ g_skip, int batch, int T, int n_ch) {
+                                    float* __restrict__ g_out, __nv_bfloat16* __restrict__ g_skip,
+                                    __nv_bfloat16* __restrict__ stack, int batch, int T, int n_ch) {
     constexpr int C = 2 * NHALF, BASE = 8 - C;
     const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -131,6 +132,25 @@ __global__ void coupling_bwd_kernel(float* __restrict__ g_x, const float* __rest
         *reinterpret_cast<float4*>(g_out + row * 8) = make_float4(go[0], go[1], go[2], go[3]);
         *reinterpret_cast<float4*>(g_out + row * 8 + 4) = make_float4(go[4], go[5], go[6], go[7]);
     }
+    if (stack != nullptr && lane < 8) {
+        // bf16 [rows, 64] operand that turns the skinny reductions into tensor-core weight-gradient GEMMs:
+        // [0..7] hi(g_out) [8..15] lo(g_out) [16..23] hi(x_mix) [24..31] lo(x_mix) [32] 1.0 (column sums) [33..63] 0
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (lane == j) v = go[j];
+        const float xm = x_mix[row * 8 + lane];
+        const __nv_bfloat16 gh = __float2bfloat16_rn(v), xh = __float2bfloat16_rn(xm);
+        __nv_bfloat16* sr = stack + row * 64;
+        sr[lane] = gh;
+        sr[8 + lane] = __float2bfloat16_rn(v - __bfloat162float(gh));
+        sr[16 + lane] = xh;
+        sr[24 + lane] = __float2bfloat16_rn(xm - __bfloat162float(xh));
+        sr[32 + lane] = __float2bfloat16_rn(lane == 0 ? 1.f : 0.f);
+        sr[40 + lane] = __float2bfloat16_rn(0.f);
+        sr[48 + lane] = __float2bfloat16_rn(0.f);
+        sr[56 + lane] = __float2bfloat16_rn(0.f);
+    }
     for (int c = lane * 2; c < n_ch; c += 64) {
         const float4* w0 = reinterpret_cast<const float4*>(w_end_t + static_cast<size_t>(c) * 8);
         float acc[2];
@@ -145,18 +165,19 @@ __global__ void coupling_bwd_kernel(float* __restrict__ g_x, const float* __rest
 }
 
 int coupling_bwd(float* g_x, const float* x_mix, const float* log_s, const float* g_ls, const float* w_end_t, float* g_out,
-                 void* g_skip, int batch, int T, int n_ch, int n_half, cudaStream_t stream) {
+                 void* g_skip, void* stack, int batch, int T, int n_ch, int n_half, cudaStream_t stream) {
     WGB_REQUIRE(g_x && x_mix && log_s && w_end_t && g_out && g_skip, "null pointer");
     WGB_REQUIRE(batch > 0 && T > 0 && n_ch % 64 == 0, "bad shape");
     WGB_REQUIRE(n_half >= 1 && n_half <= 4, "n_half must be in 1..4 (got %d)", n_half);
     const long long rows = static_cast<long long>(batch) * T;
     const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
     __nv_bfloat16* gs = static_cast<__nv_bfloat16*>(g_skip);
+    __nv_bfloat16* st = static_cast<__nv_bfloat16*>(stack);
     switch (n_half) {
-        case 1: coupling_bwd_kernel<1><<<grid, 256, 0, stream>>>(g_x, x_mix, log_s, g_ls, w_end_t, g_out, gs, batch, T, n_ch); break;
-        case 2: coupling_bwd_kernel<2><<<grid, 256, 0, stream>>>(g_x, x_mix, log_s, g_ls, w_end_t, g_out, gs, batch, T, n_ch); break;
-        case 3: coupling_bwd_kernel<3><<<grid, 256, 0, stream>>>(g_x, x_mix, log_s, g_ls, w_end_t, g_out, gs, batch, T, n_ch); break;
-        default: coupling_bwd_kernel<4><<<grid, 256, 0, stream>>>(g_x, x_mix, log_s, g_ls, w_end_t, g_out, gs, batch, T, n_ch); break;
+        case 1: coupling_bwd_kernel<1><<<grid, 256, 0, stream>>>(g_x, x_mix, log_s, g_ls, w_end_t, g_out, gs, st, batch, T, n_ch); break;
+        case 2: coupling_bwd_kernel<2><<<grid, 256, 0, stream>>>(g_x, x_mix, log_s, g_ls, w_end_t, g_out, gs, st, batch, T, n_ch); break;
+        case 3: coupling_bwd_kernel<3><<<grid, 256, 0, stream>>>(g_x, x_mix, log_s, g_ls, w_end_t, g_out, gs, st, batch, T, n_ch); break;
+        default: coupling_bwd_kernel<4><<<grid, 256, 0, stream>>>(g_x, x_mix, log_s, g_ls, w_end_t, g_out, gs, st, batch, T, n_ch); break;
     }
     WGB_LAUNCH_CHECK();
     return WGB_OK;

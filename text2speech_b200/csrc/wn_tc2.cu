@@ -88,6 +88,7 @@ struct Params {
     int skip_first;
     const float* bias;            // GATE [1024] packed order, RES [512]
     __nv_bfloat16* acts_out;      // GATE [B,T,512]
+    int seg_mask;                 // RES: bit s set -> K segment s reads the second operand tensor (map_x) instead of map_a0
     int seg_chunks, seg_shift0, seg_dshift;   // RES: K chunk kc reads A columns (kc % seg_chunks) * 64 of rows
                                   //      t + seg_shift0 + (kc / seg_chunks) * seg_dshift (conv taps; plain GEMM: n_chunks, 0, 0)
     __nv_bfloat16* ts_out;        // GATE, training forward (optional): [B,T,1024] = tanh half | sigmoid half, original
@@ -293,8 +294,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             }
                         } else if constexpr (MODE == RES) {
                             const int seg = kc / p.seg_chunks;
-                            tma_load_3d_2sm(sa, &map_a0, bar, (kc - seg * p.seg_chunks) * kBlockK,
-                                            t0 + p.seg_shift0 + seg * p.seg_dshift, b);
+                            tma_load_3d_2sm(sa, ((p.seg_mask >> seg) & 1) ? &map_x : &map_a0, bar,
+                                            (kc - seg * p.seg_chunks) * kBlockK, t0 + p.seg_shift0 + seg * p.seg_dshift, b);
                         } else {
                             tma_load_3d_2sm(sa, &map_a0, bar, (kc & 7) * kBlockK, t0, (kc >> 3) * p.batch + b);
                         }
@@ -872,26 +873,38 @@ int tc2_wn_res(const void* acts, const void* w_res, const float* bias, const voi
     return launch<RES, 0, 0>(ma, mhi, mw, mho, p, stream, skip_acc ? &mx : nullptr);
 }
 
-// Residual update fed by a dilated conv instead of a 1x1 (training direction: the data gradient of in_layers,
-// glow.py:159-160 under autograd):  h_out[b,t,:] = h_in[b,t,:] + bias + sum_tap W[:, tap*C : (tap+1)*C] a[b, t + (tap - (taps-1)/2) d, :]
-// a bf16 [B,T,C] (C % 64 == 0), w bf16 [512][taps*C], bias fp32 [512], h_in / h_out bf16 [B, h_batch_rows, 512] (may alias).
-int tc2_wn_res_taps(const void* a, const void* w, const float* bias, const void* h_in, void* h_out, int batch, int T,
-                    long long h_batch_rows, int C, int taps, int dilation, cudaStream_t stream) {
+// Residual update fed by a segmented K instead of a 1x1 (training direction: data gradients, glow.py:159-166 under
+// autograd):  h_out[b,t,:] = h_in[b,t,:] + bias + sum_s W[:, s*C : (s+1)*C] A_s[b, t + shift0 + s*dshift, :]
+// A_s = a1 if bit s of seg_mask else a0, bf16 [B,T,C] (C % 64 == 0); w bf16 [512][n_seg*C]; bias fp32 [512];
+// h_in / h_out bf16 [B, h_batch_rows, 512] (may alias).  Dilated taps = shifted segments of one tensor; the
+// res_skip data gradient = segments [g_h | g_skip] of two tensors.
+int tc2_wn_res_seg(const void* a0, const void* a1, int n_seg, int seg_mask, const void* w, const float* bias,
+                   const void* h_in, void* h_out, int batch, int T, long long h_batch_rows, int C, int shift0, int dshift,
+                   cudaStream_t stream) {
     using namespace tc2;
-    WGB_REQUIRE(a && w && bias && h_in && h_out, "null pointer");
+    WGB_REQUIRE(a0 && w && bias && h_in && h_out, "null pointer");
+    WGB_REQUIRE(seg_mask == 0 || a1 != nullptr, "seg_mask selects a1, which is null");
     WGB_REQUIRE(h_batch_rows >= T, "h_batch_rows (%lld) must be >= T (%d)", h_batch_rows, T);
-    WGB_REQUIRE(C > 0 && C % kBlockK == 0 && taps >= 1 && taps % 2 == 1 && dilation >= 1, "bad conv shape (C=%d taps=%d)", C, taps);
+    WGB_REQUIRE(C > 0 && C % kBlockK == 0 && n_seg >= 1 && n_seg <= 31, "bad segment shape (C=%d n_seg=%d)", C, n_seg);
     Params p{};
     if (int e = fill_common(p, batch, T)) return e;
-    p.n_pass = 2; p.ppi = 1; p.n_chunks = taps * C / kBlockK;
-    p.seg_chunks = C / kBlockK; p.seg_shift0 = -((taps - 1) / 2) * dilation; p.seg_dshift = dilation;
+    p.n_pass = 2; p.ppi = 1; p.n_chunks = n_seg * C / kBlockK;
+    p.seg_chunks = C / kBlockK; p.seg_shift0 = shift0; p.seg_dshift = dshift; p.seg_mask = seg_mask;
     p.bias = bias;
-    CUtensorMap ma, mhi, mho, mw;
-    if (int e = act_map(&ma, a, C, T, batch)) return e;
+    CUtensorMap ma, ma1, mhi, mho, mw;
+    if (int e = act_map(&ma, a0, C, T, batch)) return e;
+    if (int e = act_map(&ma1, a1 ? a1 : a0, C, T, batch)) return e;
     if (int e = h_map(&mhi, h_in, T, batch, h_batch_rows)) return e;
     if (int e = h_map(&mho, h_out, T, batch, h_batch_rows)) return e;
-    if (int e = weight_half_map(&mw, w, kNCh, taps * C)) return e;
-    return launch<RES, 0, 0>(ma, mhi, mw, mho, p, stream, nullptr);
+    if (int e = weight_half_map(&mw, w, kNCh, n_seg * C)) return e;
+    return launch<RES, 0, 0>(ma, mhi, mw, mho, p, stream, &ma1);
+}
+
+int tc2_wn_res_taps(const void* a, const void* w, const float* bias, const void* h_in, void* h_out, int batch, int T,
+                    long long h_batch_rows, int C, int taps, int dilation, cudaStream_t stream) {
+    WGB_REQUIRE(taps >= 1 && taps % 2 == 1 && dilation >= 1, "taps must be odd (got %d), dilation >= 1", taps);
+    return tc2_wn_res_seg(a, nullptr, taps, 0, w, bias, h_in, h_out, batch, T, h_batch_rows, C, -((taps - 1) / 2) * dilation,
+                          dilation, stream);
 }
 
 int tc2_wn_skip_end(const void* acts_all, int n_layers, const void* w_skip, const float* w_end, const float* b_end,

@@ -9,12 +9,12 @@ kernel calls (no torch op touches an activation):
             gate kernel additionally storing tanh | sigmoid; every layer's h, acts and (tanh | sigmoid) are kept in
             bf16, the flow state before / after each 1x1 conv in fp32  (~2.1 GB per flow at 32 x 16000 samples)
   backward  per flow, last to first: coupling + WN.end (wgb_coupling_bwd), then per layer, last to first:
-              g_acts  = [g_h | g_skip] W_rs          wgb_tc_gemm_seg   (tcgen05, K = 1024)
+              g_acts  = [g_h | g_skip] W_rs          wgb_tc2_wn_res_seg (CTA pairs, two operands as K segments, K = 1024)
               g_in    = gate'(g_acts, tanh, sigmoid) wgb_gate_bwd
               g_h     = g_h + conv_in^T(g_in)        wgb_tc2_wn_res_taps (CTA pairs, three shifted taps, K = 3072)
               (per flow) g_cond += [g_in_0 .. g_in_7] W_cond   wgb_tc_gemm_seg (K = 8192, one fp32 accumulate per flow)
               dW_in, dW_cond, dW_res                 wgb_tc_wgrad      (tcgen05, MN-major operands, K = B*T)
-              biases, WN.end / skip / start weights  wgb_colsum_* / wgb_skinny_wgrad (+ 8 x 512 parameter algebra)
+              biases, WN.end / skip / start weights  wgb_tc_wgrad against a [rows, 64] hi/lo stack (+ 8 x 512 parameter algebra)
             then WN.start (wgb_start_bwd), the 1x1 conv (wgb_mix_bwd) and finally the upsampler (wgb_upsample_wgrad).
 
 Weight norm (g, v) and log|det W| stay ordinary torch autograd on parameter-sized tensors around the Function, so the
@@ -212,6 +212,8 @@ def _backward(st: Dict[str, Tensor], sv: _Saved, n_flows: int, n_group: int, g_z
     g_h = torch.empty((b, t, N_CH), device=dev, dtype=bf)
     g_acts = torch.empty((b, t, N_CH), device=dev, dtype=bf)
     zero_bias = torch.zeros(N_CH, device=dev, dtype=f32)
+    zero_h = torch.zeros((b, t, N_CH), device=dev, dtype=bf)
+    stack = torch.empty((b, t, 64), device=dev, dtype=bf)                      # hi/lo(g_out) | hi/lo(x_mix) | 1 (wgb_coupling_bwd)
     L = N_LAYERS
     for k in reversed(range(n_flows)):
         f, fs = sv.packs[k], sv.flows[k]
@@ -222,28 +224,29 @@ def _backward(st: Dict[str, Tensor], sv: _Saved, n_flows: int, n_group: int, g_z
         gls = g_log_s[k]
         gls = None if gls is None else gls.float().contiguous()
         # per-flow gradient buffers: the kernels write straight into slices of these (no per-layer torch ops)
-        g_all = torch.empty((L, 8, N_CH), device=dev, dtype=f32)               # G_i = g_out^T acts_i
+        g_all = torch.empty((L, 64, N_CH), device=dev, dtype=f32)              # stack^T acts_i: rows 0..7 + 8..15 = G_i
+        r_all = torch.empty((L, 64, N_CH), device=dev, dtype=f32)              # stack^T g_h: row 32 = column sums of g_h
         d_w_rs = torch.empty((L, 2 * N_CH, N_CH), device=dev, dtype=f32)       # rows 0..511 res, 512..1023 skip
         db_rs = torch.empty((L, 2 * N_CH), device=dev, dtype=f32)
         d_w_in = torch.empty((L, 3, 2 * N_CH, N_CH), device=dev, dtype=f32)    # [layer][tap][out][in]
         db_in = torch.empty((L, 2 * N_CH), device=dev, dtype=f32)
         d_w_cond = torch.empty((L, 2 * N_CH, N_COND), device=dev, dtype=f32)
         small = torch.empty((3, 8, N_CH), device=dev, dtype=f32)               # [0] start weight, [1][0] start bias, [2] scratch
-        _lib.call("wgb_coupling_bwd", g_x, fs.x_mix, fs.log_s, gls, f["w_end_t"], g_out, g_skip, b, t, N_CH, nh, s)
+        _lib.call("wgb_coupling_bwd", g_x, fs.x_mix, fs.log_s, gls, f["w_end_t"], g_out, g_skip, stack, b, t, N_CH, nh, s)
         g_out_sum = small[2, 0, :8]
         _lib.call("wgb_colsum8_f32", g_out, g_out_sum, rows, 0, s)
         for i in reversed(range(L)):
             d = 2 ** i
             last = i == L - 1
-            _lib.call("wgb_skinny_wgrad", g_out, fs.acts[i], g_all[i], rows, N_CH, 0, s)
+            _lib.call("wgb_tc_wgrad", stack, fs.acts[i], g_all[i], b, t, 64, N_CH, 1, 1, 0, s)
             if last:
-                _lib.call("wgb_tc_gemm_seg", g_skip, None, 1, 0, f["wt_rs"][i], None, None, g_acts, 1, b, t, N_CH, N_CH,
-                          0, 0, 0, 0, s)
+                _lib.call("wgb_tc2_wn_res_seg", g_skip, None, 1, 0, f["wt_rs"][i], zero_bias, zero_h, g_acts, b, t, t, N_CH,
+                          0, 0, s)
             else:
-                _lib.call("wgb_tc_gemm_seg", g_h, g_skip, 2, 0b10, f["wt_rs"][i], None, None, g_acts, 1, b, t, N_CH, N_CH,
-                          0, 0, 0, 0, s)
+                _lib.call("wgb_tc2_wn_res_seg", g_h, g_skip, 2, 0b10, f["wt_rs"][i], zero_bias, zero_h, g_acts, b, t, t,
+                          N_CH, 0, 0, s)
                 _lib.call("wgb_tc_wgrad", g_h, fs.acts[i], d_w_rs[i, :N_CH], b, t, N_CH, N_CH, 1, 1, 0, s)
-                _lib.call("wgb_colsum_bf16", g_h, db_rs[i, :N_CH], rows, N_CH, 0, s)
+                _lib.call("wgb_tc_wgrad", stack, g_h, r_all[i], b, t, 64, N_CH, 1, 1, 0, s)       # row 32: bias gradient
             g_in = fs.ts[i]                                                    # (tanh | sigmoid) -> gradient, in place
             _lib.call("wgb_gate_bwd", g_acts, g_in, db_in[i], rows, N_CH, s)
             _lib.call("wgb_tc_wgrad", g_in, fs.h[i], d_w_in[i], b, t, 2 * N_CH, N_CH, 3, d, 0, s)
@@ -256,8 +259,7 @@ def _backward(st: Dict[str, Tensor], sv: _Saved, n_flows: int, n_group: int, g_z
         _lib.call("wgb_tc_gemm_seg", fs.ts, None, L, 0, f["wt_cond"], None, g_cond, g_cond, 0, b, t, N_COND_PAD,
                   2 * N_CH, 0, 0, 0, 1, s)
         # WN.start (g_h is now the gradient of h_0)
-        _lib.call("wgb_colsum_bf16", g_h, small[1, 0], rows, N_CH, 0, s)
-        _lib.call("wgb_skinny_wgrad", fs.x_mix, g_h, small[0], rows, N_CH, 0, s)
+        _lib.call("wgb_tc_wgrad", stack, g_h, r_all[L - 1], b, t, 64, N_CH, 1, 1, 0, s)       # rows 16..31: x_mix^T g_h0
         _lib.call("wgb_start_bwd", g_x, g_h, f["w_start"], rows, N_CH, nh, s)
         # invertible 1x1 conv
         d_mix = torch.empty((8, 8), device=dev, dtype=f32)
@@ -265,7 +267,9 @@ def _backward(st: Dict[str, Tensor], sv: _Saved, n_flows: int, n_group: int, g_z
         # parameter-space algebra (8 x 512 matrices): WN.end and the skip rows of res_skip through G_i
         w_end = f["w_end"]                                                     # [c, 512]
         w_skip = torch.stack(f["w_skip_f32"])                                  # [L, 512 (out), 512 (in)]
-        g_c = g_all[:, :c]                                                     # [L, c, 512]
+        g_c = g_all[:, :c] + g_all[:, 8: 8 + c]                                # [L, c, 512] (hi + lo parts of g_out)
+        db_rs[: L - 1, :N_CH] = r_all[: L - 1, 32]
+        d_start = r_all[L - 1, 16:24] + r_all[L - 1, 24:32]                    # [8, 512] = x_mix^T g_h0
         d_w_end = torch.einsum("ijn,imn->jm", g_c, w_skip) + torch.outer(g_out_sum[:c], f["b_skip_total"])
         d_w_skip = torch.einsum("jm,ijn->imn", w_end, g_c)                     # [L, 512, 512]
         db_skip = w_end.t() @ g_out_sum[:c]
@@ -276,8 +280,8 @@ def _backward(st: Dict[str, Tensor], sv: _Saved, n_flows: int, n_group: int, g_z
         d_w_in_p = d_w_in.permute(0, 2, 3, 1).contiguous()                     # [L, out, in, tap]
         grads[p + "end.weight"] = d_w_end.unsqueeze(2)
         grads[p + "end.bias"] = g_out_sum[:c].clone()
-        grads[p + "start.weight"] = small[0, base: base + nh].t().contiguous().unsqueeze(2)
-        grads[p + "start.bias"] = small[1, 0]
+        grads[p + "start.weight"] = d_start[base: base + nh].t().contiguous().unsqueeze(2)
+        grads[p + "start.bias"] = r_all[L - 1, 32].clone()
         grads[f"convinv.{k}.conv.weight"] = d_mix[:c, :c].contiguous().unsqueeze(2)
         for i in range(L):
             n_rs = 2 * N_CH if i < L - 1 else N_CH
