@@ -27,7 +27,7 @@ from .waveglow_oracle import (  # noqa: F401
     fold_weight_norm, folded_state, wn_layer, wn_stack, waveglow_infer, waveglow_forward,
     regroup_spect, upsample_spect, flow_channels,
 )
-from .postnet_oracle import postnet  # noqa: F401
+from .postnet_oracle import postnet, encoder_convs  # noqa: F401
 from .stft_oracle import (  # noqa: F401
     stft_bases, stft_transform, stft_inverse, window_sumsquare, mel_filterbank,
     mel_spectrogram, denoiser_bias_spec, denoise, griffin_lim, griffin_lim_initial_angles, pcm16,

@@ -27,3 +27,17 @@ def postnet(state: Dict[str, Tensor], x: Tensor, eps: float = 1e-5) -> Tensor:
         if i < n - 1:
             x = torch.tanh(x)                                                                  # modules.py:134
     return x
+
+
+def encoder_convs(state: Dict[str, Tensor], x: Tensor, eps: float = 1e-5) -> Tensor:
+    """Conv bank of the Tacotron-2 Encoder in eval mode (tacotron/tacotron.py:175-186 built, :211-212 run):
+    x [B, C, T] -> relu(batch_norm(conv(x))) per layer -> [B, C, T] (what is transposed and fed to the LSTM at :214-217)."""
+    n = 1 + max(int(k.split(".")[1]) for k in state if k.startswith("convolutions."))
+    for i in range(n):
+        p = f"convolutions.{i}."
+        w, b = state[p + "0.conv.weight"], state[p + "0.conv.bias"]
+        x = F.conv1d(x, w, b, padding=(w.shape[2] - 1) // 2)
+        x = F.batch_norm(x, state[p + "1.running_mean"], state[p + "1.running_var"], state[p + "1.weight"],
+                         state[p + "1.bias"], training=False, eps=eps)
+        x = torch.relu(x)                                                                      # tacotron.py:212
+    return x

@@ -95,3 +95,53 @@ def test_gpu_conv1d_taps_exact_integers():
                   act, _lib.stream_ptr())
         torch.cuda.synchronize()
         assert torch.equal(out.cpu().double(), want)
+
+
+# ---------------------------------------------------------------------------------------------------- Encoder conv bank
+ENC_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "encoder_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def encoder_golden():
+    with np.load(ENC_GOLD) as f:
+        return torch.from_numpy(f["conv_bank_out"]).permute(0, 2, 1).contiguous()     # -> [B, 512, T]
+
+
+def _encoder_input():
+    from tests.golden.make_golden_encoder import encoder_input
+    return encoder_input()
+
+
+def test_encoder_convs_oracle_matches_reference(encoder_golden):
+    """tacotron/tacotron.py:211-217 of the unmodified reference (captured at the LSTM's input) vs the oracle."""
+    sd = syn.synthetic_encoder_convs_state_dict(seed=78)
+    with torch.no_grad():
+        out = oracle.encoder_convs(sd, _encoder_input())
+    assert out.shape == encoder_golden.shape and util.rel_l2(out, encoder_golden) < 1e-6
+
+
+def test_encoder_convs_state_dict_layout():
+    from text2speech_b200.postnet import EncoderConvs
+    m = EncoderConvs(syn.DEFAULT_ENCODER_HPARAMS)
+    sd = syn.synthetic_encoder_convs_state_dict(seed=78)
+    assert set(m.state_dict()) == set(sd) and all(m.state_dict()[k].shape == sd[k].shape for k in sd)
+    m.load_state_dict(sd)
+    assert m.acts == [2, 2, 2] and len(m.convolutions) == 3
+    with pytest.raises(RuntimeError):
+        m.train()(_encoder_input())                               # inference-only
+
+
+@pytest.mark.gpu
+def test_gpu_encoder_convs_match_reference(encoder_golden):
+    from text2speech_b200.postnet import EncoderConvs
+    m = EncoderConvs(syn.DEFAULT_ENCODER_HPARAMS)
+    m.load_state_dict(syn.synthetic_encoder_convs_state_dict(seed=78))
+    m = m.cuda().eval()
+    x = _encoder_input().cuda()
+    m.mode = "fp32"
+    out32 = m(x).cpu()
+    assert out32.shape == encoder_golden.shape and util.rel_l2(out32, encoder_golden) <= 1e-5
+    m.mode = "bf16"
+    out16 = m(x).cpu()
+    assert util.snr_db(out16, encoder_golden) >= util.MIN_SNR_DB
+    assert float(out16.min()) >= 0.0                              # relu in the GEMM epilogue

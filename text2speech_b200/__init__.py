@@ -6,6 +6,7 @@ Drop-in module API (same names / signatures / state_dict layout as the reference
     STFT                                            (utils/stft.py)
     TacotronSTFT                                    (utils/layers.py)
     Postnet, ConvNorm                               (tacotron/modules.py:94-137,177-197; inference only)
+    EncoderConvs                                    (conv bank of tacotron/tacotron.py:175-186,211-212; inference only)
 All compute runs in hand-written CUDA behind the C ABI in include/waveglow_b200.h; there is no CPU
 fallback.  Importing the package does not need a GPU (the library is loaded on first use).
 """
@@ -14,8 +15,8 @@ from .glow import (WaveGlow, WN, Invertible1x1Conv, WaveGlowLoss, remove,      #
 from .denoiser import Denoiser                                                # noqa: F401
 from .stft import STFT                                                        # noqa: F401
 from .layers import TacotronSTFT                                              # noqa: F401
-from .postnet import Postnet, ConvNorm                                        # noqa: F401
+from .postnet import Postnet, EncoderConvs, ConvNorm                          # noqa: F401
 
 MAX_WAV_VALUE = 32768.0        # waveglow/mel2samp.py:40
 
-__all__ = ["WaveGlow", "WN", "Invertible1x1Conv", "WaveGlowLoss", "Denoiser", "STFT", "TacotronSTFT", "Postnet", "ConvNorm"]
+__all__ = ["WaveGlow", "WN", "Invertible1x1Conv", "WaveGlowLoss", "Denoiser", "STFT", "TacotronSTFT", "Postnet", "EncoderConvs", "ConvNorm"]

@@ -39,19 +39,20 @@ def _round_up(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
 
-class Postnet(torch.nn.Module):
-    def __init__(self, hparams):
+class _ConvBnStack(torch.nn.Module):
+    """``convolutions`` = ModuleList of Sequential(ConvNorm, BatchNorm1d) run as folded implicit GEMMs; ``acts[i]`` is
+    the activation after layer i (0 none, 1 tanh, 2 relu), applied in the GEMM epilogue."""
+
+    def __init__(self, chans, kernel_size, acts, gains):
         super().__init__()
-        n_mel, dim = hparams["n_mel_channels"], hparams["postnet_embedding_dim"]
-        k, n_conv = hparams["postnet_kernel_size"], hparams["postnet_n_convolutions"]
-        pad = int((k - 1) / 2)
+        pad = int((kernel_size - 1) / 2)
         self.convolutions = torch.nn.ModuleList()
-        chans = [n_mel] + [dim] * (n_conv - 1) + [n_mel]
-        for i in range(n_conv):
-            gain = "tanh" if i < n_conv - 1 else "linear"
+        for i in range(len(chans) - 1):
             self.convolutions.append(torch.nn.Sequential(
-                ConvNorm(chans[i], chans[i + 1], kernel_size=k, stride=1, padding=pad, dilation=1, w_init_gain=gain),
+                ConvNorm(chans[i], chans[i + 1], kernel_size=kernel_size, stride=1, padding=pad, dilation=1,
+                         w_init_gain=gains[i]),
                 torch.nn.BatchNorm1d(chans[i + 1])))
+        self.acts = list(acts)
         self.mode = "bf16"
         self._pack = None
 
@@ -89,11 +90,12 @@ class Postnet(torch.nn.Module):
 
     # ------------------------------------------------------------------ reference API
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x [B, n_mel, F] (CUDA) -> [B, n_mel, F]   (modules.py:132-137 in eval mode)."""
+        """x [B, C_in, F] (CUDA) -> [B, C_out, F]   (eval mode: BatchNorm running statistics, dropout = identity)."""
+        name = type(self).__name__
         if self.training:
-            raise RuntimeError("Postnet on the B200 kernels is inference-only (BatchNorm folded, no dropout): call .eval()")
+            raise RuntimeError(f"{name} on the B200 kernels is inference-only (BatchNorm folded, no dropout): call .eval()")
         if not x.is_cuda:
-            raise RuntimeError("Postnet needs a CUDA tensor on a B200; there is no CPU fallback")
+            raise RuntimeError(f"{name} needs a CUDA tensor on a B200; there is no CPU fallback")
         _lib.require_b200(x.device)
         with torch.cuda.device(x.device):
             return self._forward(x)
@@ -110,7 +112,7 @@ class Postnet(torch.nn.Module):
                 last = i == n - 1
                 out = torch.empty((b, f, ly["npad"]), device=x.device, dtype=torch.float32 if last else torch.bfloat16)
                 _lib.call("wgb_tc_conv1d", cur, ly["w"], ly["b"], out, 0 if last else 1, b, f, ly["npad"], ly["cp"],
-                          ly["taps"], 1, 0 if last else 1, s)
+                          ly["taps"], 1, self.acts[i], s)
                 cur = out
             return cur[:, :, : layers[-1]["c_out"]].permute(0, 2, 1).contiguous().to(x.dtype)
         cur = torch.zeros((b, f, layers[0]["cp"]), device=x.device, dtype=torch.float32)
@@ -122,7 +124,29 @@ class Postnet(torch.nn.Module):
                 _lib.call("wgb_sgemm_f32", cur, ly["w"][tap], ly["b"] if tap == 0 else None, out, 0, b, f, ly["c_out"],
                           ly["cp"], ly["cp"], f * ly["cp"], ly["cp"], ly["c_out"], f * ly["c_out"], tap - half,
                           int(tap > 0), s)
-            if i < n - 1:
-                _lib.call("wgb_act_f32", out, out.numel(), 1, s)
+            if self.acts[i]:
+                _lib.call("wgb_act_f32", out, out.numel(), self.acts[i], s)
             cur = out
         return cur.permute(0, 2, 1).contiguous().to(x.dtype)
+
+
+class Postnet(_ConvBnStack):
+    """tacotron/modules.py:94-137: five k = 5 convs, tanh after all but the last."""
+
+    def __init__(self, hparams):
+        n_mel, dim = hparams["n_mel_channels"], hparams["postnet_embedding_dim"]
+        k, n_conv = hparams["postnet_kernel_size"], hparams["postnet_n_convolutions"]
+        super().__init__([n_mel] + [dim] * (n_conv - 1) + [n_mel], k, [1] * (n_conv - 1) + [0],
+                         ["tanh"] * (n_conv - 1) + ["linear"])
+
+
+class EncoderConvs(_ConvBnStack):
+    """The three-conv bank of the Tacotron-2 Encoder (tacotron/tacotron.py:175-186 built, :197-198 / :211-212 run:
+    ``x = F.dropout(F.relu(conv(x)), 0.5, self.training)`` per layer), eval mode.  Same ``convolutions.{i}.{0.conv,1}.*``
+    state_dict keys as the reference Encoder, so ``load_state_dict(encoder.state_dict(), strict=False)`` picks the conv
+    bank out of a reference Encoder; the bidirectional LSTM that consumes the result (``x.transpose(1, 2)`` first,
+    tacotron.py:214-217) stays in reference PyTorch.  Input = embedded text [B, enc_conv_channels, T]."""
+
+    def __init__(self, hparams):
+        c, k, n = hparams["enc_conv_channels"], hparams["enc_conv_kernel_size"], hparams["enc_conv_num_layers"]
+        super().__init__([c] * (n + 1), k, [2] * n, ["relu"] * n)

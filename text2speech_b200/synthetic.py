@@ -135,18 +135,32 @@ DEFAULT_POSTNET_HPARAMS = {          # == hparams.py:18,146-148 of the reference
 }
 
 
+DEFAULT_ENCODER_HPARAMS = {          # == hparams.py:111-113 of the reference
+    "enc_conv_num_layers": 3, "enc_conv_kernel_size": 5, "enc_conv_channels": 512,
+}
+
+
+def synthetic_encoder_convs_state_dict(hparams: Optional[Dict] = None, seed: int = 78) -> "OrderedDict[str, torch.Tensor]":
+    """Random state of the Encoder's conv bank (tacotron/tacotron.py:175-186) in the reference key layout."""
+    hp = hparams or DEFAULT_ENCODER_HPARAMS
+    n, c = hp["enc_conv_num_layers"], hp["enc_conv_channels"]
+    return _conv_bn_state([c] * (n + 1), hp["enc_conv_kernel_size"], [math.sqrt(2.0)] * n, seed)
+
+
 def synthetic_postnet_state_dict(hparams: Optional[Dict] = None, seed: int = 77) -> "OrderedDict[str, torch.Tensor]":
     """Random Postnet ``state_dict`` in the reference layout (tacotron/modules.py:94-130): xavier-uniform conv weights
     (gain 5/3 before a tanh, 1 for the last layer), and NON-trivial BatchNorm affine parameters / running statistics so
     that folding the BatchNorm is exercised."""
     hp = hparams or DEFAULT_POSTNET_HPARAMS
     n_mel, dim, k, n = hp["n_mel_channels"], hp["postnet_embedding_dim"], hp["postnet_kernel_size"], hp["postnet_n_convolutions"]
-    chans = [n_mel] + [dim] * (n - 1) + [n_mel]
+    return _conv_bn_state([n_mel] + [dim] * (n - 1) + [n_mel], k, [5.0 / 3.0] * (n - 1) + [1.0], seed)
+
+
+def _conv_bn_state(chans, k, gains, seed) -> "OrderedDict[str, torch.Tensor]":
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
-    for i in range(n):
+    for i in range(len(chans) - 1):
         c_in, c_out = chans[i], chans[i + 1]
-        gain = 5.0 / 3.0 if i < n - 1 else 1.0
-        bound = gain * math.sqrt(6.0 / (c_in * k + c_out * k))
+        bound = gains[i] * math.sqrt(6.0 / (c_in * k + c_out * k))
         p = f"convolutions.{i}."
         sd[p + "0.conv.weight"] = _uniform((c_out, c_in, k), bound, seed, p + "w")
         sd[p + "0.conv.bias"] = _uniform((c_out,), 1.0 / math.sqrt(c_in * k), seed, p + "b")

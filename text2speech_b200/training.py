@@ -421,11 +421,12 @@ class FusedAdam:
                       _lib.stream_ptr())
 
 
-def allreduce_gradients(optimizer: FusedAdam, group=None) -> float:
+def allreduce_gradients(optimizer: FusedAdam, group=None, gathered: bool = False) -> float:
     """Data-parallel gradient reduction of waveglow/distributed.py:90-142 (flatten -> all_reduce -> divide by world
-    size) on the optimiser's flat buffer: ONE collective per step; returns the scale to hand to ``step``."""
+    size) on the optimiser's flat buffer: ONE collective per step; returns the scale to hand to ``step``.
+    ``gathered``: the flat buffer already holds this step's gradients (GraphedTrainStep gathers inside its graph)."""
     import torch.distributed as dist
-    flat = optimizer.gather_grads()
+    flat = optimizer.grad if gathered else optimizer.gather_grads()
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return 1.0
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
     ap.add_argument("--samples", type=int, default=16000)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--graph", action="store_true", help="forward + backward + gradient gather from one CUDA graph per rank")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -47,16 +48,25 @@ def main():
     audio = (0.1 * torch.randn((args.batch, args.samples), generator=g)).clamp(-1, 1).to(dev)
     mel = syn.synthetic_mel(args.batch, frames, seed=200 + rank).to(dev)
     step_ms, ar_ms, losses = [], [], []
+    graphed = None
+    if args.graph:
+        from text2speech_b200.training import GraphedTrainStep
+        graphed = GraphedTrainStep(model, opt, crit, args.batch, mel.shape[1], frames, args.samples, include_optimizer=False)
     for it in range(args.steps + 1):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         dist.barrier()
         torch.cuda.synchronize()
-        opt.zero_grad()
         e[0].record()
-        loss = crit(model((mel, audio)))
-        loss.backward()
-        e[1].record()
-        scale = allreduce_gradients(opt)
+        if graphed is not None:
+            loss = graphed(mel, audio)                            # ends with the flat gradient gathered
+            e[1].record()
+            scale = allreduce_gradients(opt, gathered=True)
+        else:
+            opt.zero_grad()
+            loss = crit(model((mel, audio)))
+            loss.backward()
+            e[1].record()
+            scale = allreduce_gradients(opt)
         e[2].record()
         opt.step(grad_scale=scale, gathered=True)
         e[3].record()
@@ -75,7 +85,7 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({"check": "ddp_train", "world": world, "per_gpu_batch": args.batch, "samples": args.samples,
-                          "params_identical_across_ranks": bool(same.item() == 1.0),
+                          "graph": bool(args.graph), "params_identical_across_ranks": bool(same.item() == 1.0),
                           "step_ms": float(t[0]), "grad_gather_plus_allreduce_ms": float(t[1]),
                           "flat_gradient_bytes": opt.n * 4,
                           "samples_per_s_all_gpus": world * args.batch * args.samples / (float(t[0]) * 1e-3),
