@@ -427,3 +427,39 @@ def test_graphed_train_step_matches_eager(lib):
     assert eager[-1] < eager[0] and graph[-1] < graph[0], runs
     for a, b in zip(eager, graph):
         assert abs(a - b) <= 0.02 * abs(eager[0]) + 1e-4, runs
+
+
+@pytest.mark.gpu
+def test_gradients_match_oracle_six_flows_ragged(lib):
+    """All three coupling widths of config.json (n_half 4, 3, 2), one utterance, audio shorter than 256 * frames
+    (trimmed upsample, glow.py:216-218) and a group-step count that is not a multiple of the 64-row K chunk:
+    every parameter gradient vs the CPU oracle under autograd (itself pinned to the reference by the 4-flow golden)."""
+    import text2speech_b200 as t2s
+    from oracle import waveglow_oracle as wo
+    cfg = dict(syn.load_config())
+    cfg.update(n_flows=6, n_early_every=2, n_early_size=2)
+    sd = syn.synthetic_state_dict(cfg, seed=91, end_std=0.05, weight_norm=True)
+    frames, n = 5, 5 * 256 - 72                                   # T = 151 group steps
+    mel = syn.synthetic_mel(1, frames, seed=31)
+    g = torch.Generator().manual_seed(32)
+    wav = (0.1 * torch.randn((1, n), generator=g)).clamp(-1, 1)
+    ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        z, log_s, log_det = wo.waveglow_forward(ref, mel, wav)
+        loss_ref = wo.waveglow_loss(z, log_s, log_det, SIGMA)
+        loss_ref.backward()
+        m = t2s.WaveGlow(**cfg)
+    m.load_state_dict(sd)
+    m = m.to(DEV).train()
+    loss = t2s.WaveGlowLoss(SIGMA)(m((mel.to(DEV), wav.to(DEV))))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 2e-3 * abs(float(loss_ref.detach())) + 1e-4
+    worst = {}
+    for name, p in m.named_parameters():
+        want = ref[name].grad
+        err = util.rel_l2(p.grad.cpu(), want)
+        kind = ".".join(name.split(".")[2:]) if name.startswith("WN") else name.split(".")[0]
+        worst[kind] = max(worst.get(kind, 0.0), err)
+        assert err <= 2e-2, (name, err)
+    print("six flows, worst relative error per parameter kind:", {k: round(v, 4) for k, v in sorted(worst.items())})
