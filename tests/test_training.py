@@ -463,3 +463,43 @@ def test_gradients_match_oracle_six_flows_ragged(lib):
         worst[kind] = max(worst.get(kind, 0.0), err)
         assert err <= 2e-2, (name, err)
     print("six flows, worst relative error per parameter kind:", {k: round(v, 4) for k, v in sorted(worst.items())})
+
+
+@pytest.mark.gpu
+def test_train_cli_checkpoints_and_resume(tmp_path, lib):
+    """waveglow/train.py's loop on three synthetic wav files: per-iteration losses, checkpoints in the reference's
+    format ({'model': pickled module, 'iteration', 'optimizer' (torch Adam layout), 'learning_rate'}), resume."""
+    from scipy.io.wavfile import write
+    from text2speech_b200 import train as t2s_train
+    from text2speech_b200.inference import load_waveglow
+    g = torch.Generator().manual_seed(40)
+    names = []
+    for i in range(3):
+        path = str(tmp_path / f"u{i}.wav")
+        write(path, 22050, (0.2 * torch.randn(9000 + 500 * i, generator=g)).clamp(-1, 1).mul(32767).short().numpy())
+        names.append(path)
+    flist = tmp_path / "train_files.txt"
+    flist.write_text("\n".join(names) + "\n")
+    data_config = dict(training_files=str(flist), segment_length=4096, sampling_rate=22050, filter_length=1024,
+                       hop_length=256, win_length=1024, mel_fmin=0.0, mel_fmax=8000.0)
+    out_dir = str(tmp_path / "ckpt")
+    common = dict(output_directory=out_dir, learning_rate=1e-5, sigma=1.0, iters_per_checkpoint=1, batch_size=2, seed=1234,
+                  waveglow_config=train_config(), data_config=data_config)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        losses = t2s_train.train(1, 0, "", epochs=2, checkpoint_path="", **common)
+        assert len(losses) == 2 and all(np.isfinite(losses))
+        ck = torch.load(os.path.join(out_dir, "waveglow_1"), map_location="cpu", weights_only=False)
+        assert ck["iteration"] == 1 and ck["learning_rate"] == 1e-5
+        assert set(ck["optimizer"]) == {"state", "param_groups"} and int(ck["optimizer"]["state"][0]["step"]) == 2
+        assert type(ck["model"]).__name__ == "WaveGlow"
+        # resume: one more epoch = one more iteration, Adam moments and step restored
+        more = t2s_train.train(1, 0, "", epochs=3, checkpoint_path=os.path.join(out_dir, "waveglow_1"), **common)
+        assert len(more) == 1 and np.isfinite(more[0])
+        ck2 = torch.load(os.path.join(out_dir, "waveglow_2"), map_location="cpu", weights_only=False)
+        assert ck2["iteration"] == 2 and int(ck2["optimizer"]["state"][0]["step"]) == 3
+        # the checkpoint is a vocoder checkpoint: the inference loader takes it
+        m = load_waveglow(os.path.join(out_dir, "waveglow_2")).to(DEV).eval()
+    mel = syn.synthetic_mel(1, 4, seed=1).to(DEV)
+    audio = m.infer(mel, sigma=0.6)
+    assert audio.shape == (1, 1024) and bool(torch.isfinite(audio).all())

@@ -401,6 +401,40 @@ class FusedAdam:
         for p in self.params:
             p.grad = None
 
+    # ------------------------------------------------------------------ checkpoints (torch.optim.Adam's format)
+    def state_dict(self):
+        """The layout ``torch.optim.Adam.state_dict()`` produces (train.py:57-62 stores it in the checkpoint)."""
+        state = {}
+        if self.step_count > 0:
+            for i, (p, gv) in enumerate(zip(self.params, self.views)):
+                off = gv.storage_offset()
+                sz = p.numel()
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.m[off: off + sz].view_as(p).detach().cpu().clone(),
+                            "exp_avg_sq": self.v[off: off + sz].view_as(p).detach().cpu().clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        """Accepts ``torch.optim.Adam`` state (of this class or of the reference's optimiser over the same parameters)."""
+        group = sd["param_groups"][0]
+        self.lr, self.betas, self.eps = group["lr"], tuple(group["betas"]), group["eps"]
+        if group.get("weight_decay", 0) or group.get("amsgrad", False):
+            raise ValueError("FusedAdam has no weight decay / amsgrad")
+        self.m.zero_()
+        self.v.zero_()
+        step = 0
+        for i, st in sd["state"].items():
+            i = int(i)
+            gv = self.views[i]
+            off, sz = gv.storage_offset(), self.params[i].numel()
+            self.m[off: off + sz].copy_(st["exp_avg"].reshape(-1))
+            self.v[off: off + sz].copy_(st["exp_avg_sq"].reshape(-1))
+            step = max(step, int(float(st["step"])))
+        self.step_count = step
+        self.step_dev.fill_(step)
+
     def gather_grads(self) -> Tensor:
         """Copy every .grad into the flat gradient buffer (missing grads count as zero); returns that buffer."""
         have = [(gv, p.grad) for p, gv in zip(self.params, self.views) if p.grad is not None]
