@@ -22,7 +22,7 @@ gate_bwd_kernel(const uint4* __restrict__ g_acts, uint4* ts, float* __restrict__
 #pragma unroll
     for (int e = 0; e < 8; ++e) sa[e] = sb[e] = 0.f;
     if (c < c8) {
-        constexpr int kBatch = 4;                               // rows in flight per thread (12 independent 16 B loads)
+        constexpr int kBatch = 8;                               // rows in flight per thread (24 independent 16 B loads)
 #pragma unroll 1
         for (long long rb = static_cast<long long>(blockIdx.x) * (4 * kBatch) + lane_r; rb < rows;
              rb += static_cast<long long>(gridDim.x) * (4 * kBatch)) {
@@ -85,7 +85,7 @@ int gate_bwd(const void* g_acts, void* ts, float* db, long long rows, int n_ch, 
     WGB_REQUIRE(rows > 0 && n_ch > 0 && n_ch % 8 == 0, "rows must be positive and n_ch a multiple of 8");
     if (db) WGB_CUDA_TRY(cudaMemsetAsync(db, 0, sizeof(float) * 2 * n_ch, stream));
     const int c8 = n_ch / 8;
-    long long blocks = (rows + 15) / 16;                    // few, long-lived blocks: one set of bias atomics per block
+    long long blocks = (rows + 31) / 32;                    // few, long-lived blocks: one set of bias atomics per block
     if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
     dim3 grid(static_cast<unsigned>(blocks), (c8 + 63) / 64);
     gate_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(g_acts), static_cast<uint4*>(ts), db, rows, c8);

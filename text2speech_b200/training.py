@@ -5,7 +5,7 @@ the drop-in ``WaveGlow`` exactly as on the reference: ``WaveGlow.forward`` route
 and returns tensors wired into one ``torch.autograd.Function`` whose forward and backward are sequences of C-ABI
 kernel calls (no torch op touches an activation):
 
-  forward   the inference kernels of engine.py in their un-composed form (tcgen05 gate / residual / skip GEMMs), the
+  forward   the inference kernels of engine.py on the cond tensor (tcgen05 gate / residual GEMMs, composed skip + end), the
             gate kernel additionally storing tanh | sigmoid; every layer's h, acts and (tanh | sigmoid) are kept in
             bf16, the flow state before / after each 1x1 conv in fp32  (~2.1 GB per flow at 32 x 16000 samples)
   backward  per flow, last to first: coupling + WN.end (wgb_coupling_bwd), then per layer, last to first:
@@ -131,7 +131,7 @@ def _pack_flow(st: Dict[str, Tensor], k: int) -> Dict[str, object]:
     b_skip = sum(b_rs[i][N_CH:] if i < N_LAYERS - 1 else b_rs[i] for i in range(N_LAYERS))
     f["w_skip_f32"] = w_skip
     f["b_skip_total"] = b_skip
-    f["w_skip"] = torch.cat(w_skip, dim=1).to(bf).contiguous()              # [512, 8*512]
+    w_skip_cat = torch.cat(w_skip, dim=1)                                   # [512, 8*512]
     w_end_t = torch.zeros(N_CH, 8, device=dev)
     w_end_t[:, :c] = w_end.t()
     f["w_end_t"] = w_end_t
@@ -139,6 +139,12 @@ def _pack_flow(st: Dict[str, Tensor], k: int) -> Dict[str, object]:
     b_end = torch.zeros(8, device=dev)
     b_end[:c] = st[p + "end.bias"] + w_end @ b_skip
     f["b_end"] = b_end
+    # WN.end composed with the skip GEMM (engine "skip16" path; packing.pack_skip_end16 on the device): [16, 8*512]
+    # bf16, rows 0..7 the hi parts of W_end W_skip, rows 8..15 the lo parts
+    comp = torch.zeros(8, w_skip_cat.shape[1], device=dev)
+    comp[:c] = w_end @ w_skip_cat
+    hi = comp.to(bf)
+    f["w_skip16"] = torch.cat([hi, (comp - hi.float()).to(bf)], dim=0).contiguous()
     return f
 
 
@@ -186,8 +192,8 @@ def _forward(st: Dict[str, Tensor], n_flows: int, n_group: int, mel: Tensor, aud
                 _lib.call("wgb_tc2_wn_res", fs.acts[i], f["w_res"][i], f["b_res"][i], fs.h[i], fs.h[i + 1], b, t, t,
                           None, None, 0, s)
         fs.log_s = torch.empty((b, nh, t), device=dev, dtype=torch.float32)
-        _lib.call("wgb_tc2_wn_skip_end", fs.acts, N_LAYERS, f["w_skip"], f["w_end_t"], f["b_end"], x, None, fs.log_s, b, t,
-                  nh, 1, None, None, 0, None, 0, s)
+        _lib.call("wgb_tc_wn_skip16_end", fs.acts, N_LAYERS, f["w_skip16"], f["b_end"], x, None, fs.log_s, b, t, nh, 1,
+                  None, None, 0, None, 0, None, None, s)
         log_s_list.append(fs.log_s)
         sv.flows.append(fs)
         sv.packs.append(f)
