@@ -72,6 +72,36 @@ def test_allreduce_gradients_is_identity_without_process_group():
     assert training.allreduce_gradients(Fake()) == 1.0
 
 
+def test_per_step_packing_matches_inference_packing():
+    """training._pack_flow (device-side, every step) builds the same gate / residual / composed-skip operands as
+    packing.PackedWaveGlow (host-side, once) and the mirrored-tap transposes the data gradients need."""
+    from text2speech_b200 import packing, training
+    cfg = train_config()
+    sd = packing.folded(syn.synthetic_state_dict(cfg, seed=5, end_std=0.05, weight_norm=True))
+    k = 2                                                          # n_half = 3
+    f = training._pack_flow(sd, k)
+    p = f"WN.{k}."
+    for i in (0, 7):
+        wg, bg = packing.pack_gate(sd[p + f"in_layers.{i}.weight"], sd[p + f"in_layers.{i}.bias"],
+                                   sd[p + f"cond_layers.{i}.weight"], sd[p + f"cond_layers.{i}.bias"])
+        assert torch.equal(f["w_gate"][i], wg.bfloat16()) and torch.equal(f["b_gate"][i], bg)
+        w_in = sd[p + f"in_layers.{i}.weight"].bfloat16()
+        wt = f["wt_in"][i].reshape(512, 3, 1024)                   # [c_in][tap'][c_out], tap' = 2 - tap
+        assert torch.equal(wt[:, 0], w_in[:, :, 2].t()) and torch.equal(wt[:, 2], w_in[:, :, 0].t())
+        w_cond = sd[p + f"cond_layers.{i}.weight"][:, :, 0].bfloat16()
+        assert torch.equal(f["wt_cond"][:640, i * 1024:(i + 1) * 1024], w_cond.t())
+    assert float(f["wt_cond"][640:].abs().max()) == 0.0
+    w_rs = [sd[p + f"res_skip_layers.{i}.weight"] for i in range(8)]
+    b_rs = [sd[p + f"res_skip_layers.{i}.bias"] for i in range(8)]
+    w_skip, b_skip = packing.pack_skip(w_rs, b_rs, 512)
+    w16 = packing.pack_skip_end16(w_skip, sd[p + "end.weight"])
+    got16 = f["w_skip16"].float()
+    assert util.rel_l2(got16[:8] + got16[8:], w16.float()[:8] + w16.float()[8:]) <= 5e-6   # hi + lo = the composed product (fp32 here, fp64 there)
+    _, _, b_fold = packing.pack_end(sd[p + "end.weight"], sd[p + "end.bias"], b_skip)
+    assert util.rel_l2(f["b_end"], b_fold) <= 1e-6
+    assert torch.equal(f["wt_rs"][3], w_rs[3][:, :, 0].t().bfloat16()) and f["n_half"] == 3
+
+
 # ---------------------------------------------------------------------------------------------------- GPU
 @pytest.fixture(scope="module")
 def lib():

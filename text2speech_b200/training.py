@@ -111,14 +111,17 @@ def _pack_flow(st: Dict[str, Tensor], k: int) -> Dict[str, object]:
     c = 2 * n_half
     mix[:c, :c] = st[f"convinv.{k}.conv.weight"][:, :, 0]
     f["w_mix"] = mix
-    w_in = torch.stack([st[p + f"in_layers.{i}.weight"] for i in range(N_LAYERS)])              # [8, 1024, 512, 3]
-    w_cond = torch.stack([st[p + f"cond_layers.{i}.weight"][:, :, 0] for i in range(N_LAYERS)])  # [8, 1024, 640]
+    # everything below is cast to bf16 FIRST, so the layout shuffles move half the bytes
+    w_in = torch.stack([st[p + f"in_layers.{i}.weight"].to(bf) for i in range(N_LAYERS)])             # [8, 1024, 512, 3]
+    w_cond = torch.stack([st[p + f"cond_layers.{i}.weight"][:, :, 0].to(bf) for i in range(N_LAYERS)])  # [8, 1024, 640]
     b_gate = torch.stack([st[p + f"in_layers.{i}.bias"] + st[p + f"cond_layers.{i}.bias"] for i in range(N_LAYERS)])
-    w_gate = torch.cat([w_in.permute(0, 1, 3, 2).reshape(N_LAYERS, 2 * N_CH, 3 * N_CH), w_cond], dim=2)
-    f["w_gate"] = w_gate[:, order].to(bf).contiguous()                      # [8, 1024, 2176] packed row order
+    w_gate = torch.empty((N_LAYERS, 2 * N_CH, 3 * N_CH + N_COND), device=dev, dtype=bf)               # packed row order
+    w_gate[:, :, : 3 * N_CH] = w_in[:, order].permute(0, 1, 3, 2).reshape(N_LAYERS, 2 * N_CH, 3 * N_CH)
+    w_gate[:, :, 3 * N_CH:] = w_cond[:, order]
+    f["w_gate"] = w_gate                                                    # [8, 1024, 2176]
     f["b_gate"] = b_gate[:, order].contiguous()
     # data-gradient operands: W^T with the taps mirrored (tap' = 2 - tap)
-    f["wt_in"] = w_in.flip(3).permute(0, 2, 3, 1).reshape(N_LAYERS, N_CH, 3 * 2 * N_CH).to(bf).contiguous()
+    f["wt_in"] = w_in.flip(3).permute(0, 2, 3, 1).reshape(N_LAYERS, N_CH, 3 * 2 * N_CH).contiguous()
     wt_cond = torch.zeros(N_COND_PAD, N_LAYERS, 2 * N_CH, device=dev, dtype=bf)       # [cond ch][layer][gate ch]: K = layer*1024 + o
     wt_cond[:N_COND] = w_cond.permute(2, 0, 1)
     f["wt_cond"] = wt_cond.reshape(N_COND_PAD, N_LAYERS * 2 * N_CH)
