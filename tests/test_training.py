@@ -112,7 +112,7 @@ def lib():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("ca,cb,taps,dil,b,t", [(1024, 512, 3, 4, 3, 200), (512, 512, 1, 1, 2, 333), (1024, 640, 1, 1, 2, 128),
-                                                (1024, 512, 3, 128, 2, 300)])
+                                                (1024, 512, 3, 128, 2, 300), (64, 512, 1, 1, 2, 1100), (192, 512, 1, 1, 1, 700)])
 def test_tc_wgrad_matches_torch(lib, ca, cb, taps, dil, b, t):
     g = torch.Generator().manual_seed(ca + cb + taps)
     gy = torch.randn((b, t, ca), generator=g).bfloat16()

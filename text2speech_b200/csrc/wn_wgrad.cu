@@ -100,6 +100,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                 const int n_tile = (tile / p.m_tiles) % p.n_tiles;
                 const int tap = tile / (p.m_tiles * p.n_tiles);
                 const int shift = (tap - (p.taps - 1) / 2) * p.dilation;
+                // skinny operands (ca = 64: the hi/lo stack) load and multiply only the 64-channel boxes that exist
+                const int a_boxes = min(kM / 64, (p.ca - m_tile * kM + 63) / 64);
                 const int c_begin = split * p.chunks_per_split;
                 const int c_end = min(c_begin + p.chunks_per_split, p.chunks_total);
                 for (int c = c_begin; c < c_end; ++c) {
@@ -108,10 +110,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                     mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
                     uint8_t* sa = smem + s * kStageBytes;
                     uint8_t* sb = sa + kABytes;
-                    mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                    mbar_arrive_expect_tx(&full_bar[s], a_boxes * kBox + kBBytes);
 #pragma unroll
                     for (int j = 0; j < kM / 64; ++j)
-                        tma_load_3d(sa + j * kBox, &map_a, &full_bar[s], m_tile * kM + j * 64, t0, b);
+                        if (j < a_boxes) tma_load_3d(sa + j * kBox, &map_a, &full_bar[s], m_tile * kM + j * 64, t0, b);
 #pragma unroll
                     for (int j = 0; j < kN / 64; ++j)
                         tma_load_3d(sb + j * kBox, &map_b, &full_bar[s], n_tile * kN + j * 64, t0 + shift, b);
@@ -127,6 +129,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             uint32_t ph = 0, acc_it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
                 const int split = item / tiles;
+                const int halves = (p.ca - ((item % tiles) % p.m_tiles) * kM) > 128 ? 2 : 1;
                 const int c_begin = split * p.chunks_per_split;
                 const int c_end = min(c_begin + p.chunks_per_split, p.chunks_total);
                 mbar_wait(&tempty_bar[0], (acc_it & 1) ^ 1, 200);
@@ -141,7 +144,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                         const uint64_t db = umma_desc_sw128_mn(b_addr + k * 2048, kBox);
 #pragma unroll
                         for (int half = 0; half < 2; ++half)   // channels half*128 .. +127 of the m tile -> accumulator half
-                            umma_bf16_ss(tmem_base + half * kN, umma_desc_sw128_mn(a_addr + half * 2 * kBox + k * 2048, kBox),
+                            if (half < halves) umma_bf16_ss(tmem_base + half * kN, umma_desc_sw128_mn(a_addr + half * 2 * kBox + k * 2048, kBox),
                                          db, idesc, (c > c_begin) || (k != 0));
                     }
                     umma_commit(&empty_bar[s]);
@@ -164,8 +167,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             mbar_wait(&tfull_bar[0], acc_it & 1, 400);
             tc_fence_after_sync();
             const int n_left = p.cb - n_tile * kN;
+            const int halves = (p.ca - m_tile * kM) > 128 ? 2 : 1;
 #pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < halves; ++half) {
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * kN;
                 const int m = m_tile * kM + half * 128 + row;
                 float* dst = p.out + (static_cast<size_t>(tap) * p.ca + m) * p.cb + n_tile * kN;
