@@ -106,9 +106,21 @@ __global__ void coupling_bwd_kernel(float* __restrict__ g_x, const float* __rest
                                     float* __restrict__ g_out, __nv_bfloat16* __restrict__ g_skip,
                                     __nv_bfloat16* __restrict__ stack, int batch, int T, int n_ch) {
     constexpr int C = 2 * NHALF, BASE = 8 - C;
-    const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (row >= static_cast<long long>(batch) * T) return;
+    // this lane's 16 channels (2 lane + 64 k, +1) of W_end, kept in registers across all rows of the warp (n_ch = 512)
+    float wreg[8][2][C];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const int c = lane * 2 + 64 * k + e;
+                wreg[k][e][j] = c < n_ch ? w_end_t[static_cast<size_t>(c) * 8 + j] : 0.f;
+            }
+    const long long n_rows = static_cast<long long>(batch) * T;
+    const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    for (long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += warps) {
     const int b = static_cast<int>(row / T), t = static_cast<int>(row - static_cast<long long>(b) * T);
     float go[8], ga1[NHALF];
 #pragma unroll
@@ -151,26 +163,29 @@ __global__ void coupling_bwd_kernel(float* __restrict__ g_x, const float* __rest
         sr[48 + lane] = __float2bfloat16_rn(0.f);
         sr[56 + lane] = __float2bfloat16_rn(0.f);
     }
-    for (int c = lane * 2; c < n_ch; c += 64) {
-        const float4* w0 = reinterpret_cast<const float4*>(w_end_t + static_cast<size_t>(c) * 8);
-        float acc[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const float4 wa = w0[2 * e], wb = w0[2 * e + 1];
-            acc[e] = go[0] * wa.x + go[1] * wa.y + go[2] * wa.z + go[3] * wa.w + go[4] * wb.x + go[5] * wb.y + go[6] * wb.z +
-                     go[7] * wb.w;
-        }
-        *reinterpret_cast<__nv_bfloat162*>(g_skip + row * n_ch + c) = __floats2bfloat162_rn(acc[0], acc[1]);
+    for (int k = 0; k < 8; ++k) {
+        const int c = lane * 2 + 64 * k;
+        float acc[2] = {0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int j = 0; j < C; ++j) acc[e] = fmaf(go[j], wreg[k][e][j], acc[e]);
+        if (c < n_ch) *reinterpret_cast<__nv_bfloat162*>(g_skip + row * n_ch + c) = __floats2bfloat162_rn(acc[0], acc[1]);
+    }
+    __syncwarp();
     }
 }
 
 int coupling_bwd(float* g_x, const float* x_mix, const float* log_s, const float* g_ls, const float* w_end_t, float* g_out,
                  void* g_skip, void* stack, int batch, int T, int n_ch, int n_half, cudaStream_t stream) {
     WGB_REQUIRE(g_x && x_mix && log_s && w_end_t && g_out && g_skip, "null pointer");
-    WGB_REQUIRE(batch > 0 && T > 0 && n_ch % 64 == 0, "bad shape");
+    WGB_REQUIRE(batch > 0 && T > 0 && n_ch % 64 == 0 && n_ch <= 512, "n_ch must be a multiple of 64, at most 512");
     WGB_REQUIRE(n_half >= 1 && n_half <= 4, "n_half must be in 1..4 (got %d)", n_half);
     const long long rows = static_cast<long long>(batch) * T;
-    const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+    const unsigned grid = static_cast<unsigned>(blocks);
     __nv_bfloat16* gs = static_cast<__nv_bfloat16*>(g_skip);
     __nv_bfloat16* st = static_cast<__nv_bfloat16*>(stack);
     switch (n_half) {
@@ -187,34 +202,48 @@ int coupling_bwd(float* g_x, const float* x_mix, const float* log_s, const float
 // h0 = W_start a0 + b (glow.py:156): g_x[a0 channels] += g_h0 W_start.  w_start fp32 [512][n_half]; one warp per row.
 __global__ void start_bwd_kernel(float* __restrict__ g_x, const __nv_bfloat16* __restrict__ g_h0,
                                  const float* __restrict__ w_start, long long rows, int n_ch, int n_half) {
-    const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = lane * 2; c < n_ch; c += 64) {
-        const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(g_h0 + row * n_ch + c));
+    float wreg[8][2][4];                                      // this lane's 16 channels of W_start (n_ch <= 512)
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = lane * 2 + 64 * k + e;
+                wreg[k][e][j] = (c < n_ch && j < n_half) ? w_start[static_cast<size_t>(c) * n_half + j] : 0.f;
+            }
+    const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    for (long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane * 2 + 64 * k;
+            if (c < n_ch) {
+                const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(g_h0 + row * n_ch + c));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] += g.x * wreg[k][0][j] + g.y * wreg[k][1][j];
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (j < n_half)
-                acc[j] += g.x * __ldg(w_start + static_cast<size_t>(c) * n_half + j) +
-                          g.y * __ldg(w_start + static_cast<size_t>(c + 1) * n_half + j);
-    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+            for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+        if (lane == 0) {
+            const int base = 8 - 2 * n_half;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-    if (lane == 0) {
-        const int base = 8 - 2 * n_half;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j < n_half) g_x[row * 8 + base + j] += acc[j];
+            for (int j = 0; j < 4; ++j)
+                if (j < n_half) g_x[row * 8 + base + j] += acc[j];
+        }
     }
 }
 
 int start_bwd(float* g_x, const void* g_h0, const float* w_start, long long rows, int n_ch, int n_half, cudaStream_t stream) {
     WGB_REQUIRE(g_x && g_h0 && w_start, "null pointer");
-    WGB_REQUIRE(rows > 0 && n_ch % 64 == 0 && n_half >= 1 && n_half <= 4, "bad shape");
-    start_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(g_x, static_cast<const __nv_bfloat16*>(g_h0),
+    WGB_REQUIRE(rows > 0 && n_ch % 64 == 0 && n_ch <= 512 && n_half >= 1 && n_half <= 4, "bad shape");
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+    start_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(g_x, static_cast<const __nv_bfloat16*>(g_h0),
                                                                                 w_start, rows, n_ch, n_half);
     WGB_LAUNCH_CHECK();
     return WGB_OK;
