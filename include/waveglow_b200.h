@@ -314,11 +314,6 @@ WGB_API int wgb_coupling_bwd(float* g_x, const float* x_mix, const float* log_s,
 /* g_x[a0 channels] += g_h0 W_start (glow.py:156); w_start fp32 [n_ch][n_half]. */
 WGB_API int wgb_start_bwd(float* g_x, const void* g_h0, const float* w_start, long long rows, int n_ch, int n_half,
                           void* stream);
-/* out[j][c] (+)= sum_r a[r][j] b[r][c]; a fp32 [rows,8], b bf16 [rows,n_ch], out fp32 [8][n_ch]. */
-WGB_API int wgb_skinny_wgrad(const float* a, const void* b, float* out, long long rows, int n_ch, int accumulate,
-                             void* stream);
-/* out[c] (+)= sum_r b[r][c] (bias gradients); b bf16 [rows,n_ch]. */
-WGB_API int wgb_colsum_bf16(const void* b, float* out, long long rows, int n_ch, int accumulate, void* stream);
 /* out[j] (+)= sum_r a[r][j]; a fp32 [rows,8]. */
 WGB_API int wgb_colsum8_f32(const float* a, float* out, long long rows, int accumulate, void* stream);
 /* Invertible 1x1 conv backward (glow.py:97-102): g_x <- W^T g_y on the last C channels (in place),

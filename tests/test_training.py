@@ -240,14 +240,14 @@ def test_pointwise_backward_kernels(lib):
     assert util.rel_l2(st[:, 0:8] + st[:, 8:16], want_out) <= 2e-5
     assert util.rel_l2(st[:, 16:24] + st[:, 24:32], x_mix) <= 2e-5
     assert torch.equal(st[:, 32], torch.ones(rows)) and float(st[:, 33:].abs().max()) == 0.0
-    # skinny reductions
+    # the same reductions the backward pass runs on the tensor cores: stack^T b -> rows 0..7 + 8..15 = g_out^T b,
+    # row 32 = column sums of b
     bb = torch.randn((rows, 512), generator=g).bfloat16()
-    out = torch.empty((8, 512), device=DEV)
-    lib.call("wgb_skinny_wgrad", g_out, bb.to(DEV), out, rows, 512, 0, s)
-    assert util.rel_l2(out.cpu(), want_out.double().t() @ bb.double()) <= 1e-5
-    cs = torch.empty(512, device=DEV)
-    lib.call("wgb_colsum_bf16", bb.to(DEV), cs, rows, 512, 0, s)
-    assert util.rel_l2(cs.cpu(), bb.double().sum(0)) <= 1e-5
+    prod = torch.empty((1, 64, 512), device=DEV)
+    lib.call("wgb_tc_wgrad", stack.view(b, t, 64), bb.to(DEV).view(b, t, 512), prod, b, t, 64, 512, 1, 1, 0, s)
+    prod = prod[0].cpu()
+    assert util.rel_l2(prod[0:8] + prod[8:16], want_out.double().t() @ bb.double()) <= 1e-5
+    assert util.rel_l2(prod[32], bb.double().sum(0)) <= 1e-5
     c8 = torch.empty(8, device=DEV)
     lib.call("wgb_colsum8_f32", g_out, c8, rows, 0, s)
     assert util.rel_l2(c8.cpu(), want_out.double().sum(0)) <= 1e-5

@@ -65,8 +65,6 @@ int gate_bwd(const void*, void*, float*, long long, int, cudaStream_t);
 int coupling_bwd(float*, const float*, const float*, const float*, const float*, float*, void*, void*, int, int, int, int,
                  cudaStream_t);
 int start_bwd(float*, const void*, const float*, long long, int, int, cudaStream_t);
-int skinny_wgrad(const float*, const void*, float*, long long, int, int, cudaStream_t);
-int colsum_bf16(const void*, float*, long long, int, int, cudaStream_t);
 int colsum8_f32(const float*, float*, long long, int, cudaStream_t);
 int mix_bwd(float*, const float*, const float*, float*, long long, int, cudaStream_t);
 int upsample_wgrad(const float*, const float*, float*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
@@ -309,13 +307,6 @@ WGB_API int wgb_coupling_bwd(float* g_x, const float* x_mix, const float* log_s,
 WGB_API int wgb_start_bwd(float* g_x, const void* g_h0, const float* w_start, long long rows, int n_ch, int n_half,
                           void* stream) {
     return start_bwd(g_x, g_h0, w_start, rows, n_ch, n_half, S(stream));
-}
-WGB_API int wgb_skinny_wgrad(const float* a, const void* b, float* out, long long rows, int n_ch, int accumulate,
-                             void* stream) {
-    return skinny_wgrad(a, b, out, rows, n_ch, accumulate, S(stream));
-}
-WGB_API int wgb_colsum_bf16(const void* b, float* out, long long rows, int n_ch, int accumulate, void* stream) {
-    return colsum_bf16(b, out, rows, n_ch, accumulate, S(stream));
 }
 WGB_API int wgb_colsum8_f32(const float* a, float* out, long long rows, int accumulate, void* stream) {
     return colsum8_f32(a, out, rows, accumulate, S(stream));

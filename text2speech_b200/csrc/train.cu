@@ -249,133 +249,9 @@ int start_bwd(float* g_x, const void* g_h0, const float* w_start, long long rows
     return WGB_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ skinny reductions
-// out[j][c] += sum_r a[r][j] * b[r][c]   (a fp32 [rows, 8], b bf16 [rows, n_ch]; out fp32 [8][n_ch]).
-// Weight gradients whose one side has <= 8 channels: WN.start (a = flow state, b = g_h0), WN.end composed with the
-// skip rows (a = g_out, b = the layer's gated activations).  One thread per 8 columns, 256 rows per block.
-__global__ void __launch_bounds__(256)
-skinny_wgrad_kernel(const float* __restrict__ a, const uint4* __restrict__ b, float* __restrict__ out, long long rows, int c8) {
-    __shared__ float s_acc[8][64 * 8];                         // [j][column within this block's 512-column slab]
-    const int col = threadIdx.x & 63, lane_r = threadIdx.x >> 6;
-    const int c = blockIdx.y * 64 + col;
-    for (int i = threadIdx.x; i < 8 * 512; i += 256) (&s_acc[0][0])[i] = 0.f;
-    __syncthreads();
-    float acc[8][8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
-    if (c < c8) {
-        constexpr int kBatch = 4;
-#pragma unroll 1
-        for (long long rb = static_cast<long long>(blockIdx.x) * (4 * kBatch) + lane_r; rb < rows;
-             rb += static_cast<long long>(gridDim.x) * (4 * kBatch)) {
-            uint4 v[kBatch];
-            float4 a0[kBatch], a1[kBatch];
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const long long r = rb + 4 * u;
-                const bool ok = r < rows;
-                v[u] = ok ? b[r * c8 + c] : make_uint4(0u, 0u, 0u, 0u);
-                a0[u] = ok ? __ldg(reinterpret_cast<const float4*>(a + r * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                a1[u] = ok ? __ldg(reinterpret_cast<const float4*>(a + r * 8) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const float av[8] = {a0[u].x, a0[u].y, a0[u].z, a0[u].w, a1[u].x, a1[u].y, a1[u].z, a1[u].w};
-                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-                float bv[8];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-                    bv[2 * e] = f.x;
-                    bv[2 * e + 1] = f.y;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(av[j], bv[e], acc[j][e]);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(&s_acc[j][col * 8 + e], acc[j][e]);       // 4-way (the row lanes)
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 8 * 512; i += 256) {
-        const int j = i >> 9, cc = blockIdx.y * 512 + (i & 511);
-        if (cc < c8 * 8) atomicAdd(out + static_cast<size_t>(j) * c8 * 8 + cc, s_acc[j][i & 511]);
-    }
-}
-
-int skinny_wgrad(const float* a, const void* b, float* out, long long rows, int n_ch, int accumulate, cudaStream_t stream) {
-    WGB_REQUIRE(a && b && out, "null pointer");
-    WGB_REQUIRE(rows > 0 && n_ch > 0 && n_ch % 8 == 0, "bad shape");
-    if (!accumulate) WGB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * 8 * n_ch, stream));
-    const int c8 = n_ch / 8;
-    long long blocks = (rows + 15) / 16;
-    if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
-    dim3 grid(static_cast<unsigned>(blocks), (c8 + 63) / 64);
-    skinny_wgrad_kernel<<<grid, 256, 0, stream>>>(a, static_cast<const uint4*>(b), out, rows, c8);
-    WGB_LAUNCH_CHECK();
-    return WGB_OK;
-}
-
-// out[c] += sum_r b[r][c]  (bias gradients; b bf16 [rows, n_ch]).  Block = 64 column groups x 4 row lanes, grid-stride.
-__global__ void __launch_bounds__(256)
-colsum_bf16_kernel(const uint4* __restrict__ b, float* __restrict__ out, long long rows, int c8) {
-    __shared__ float s_sum[3][64][8];
-    const int col = threadIdx.x & 63, lane_r = threadIdx.x >> 6;
-    const int c = blockIdx.y * 64 + col;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (c < c8) {
-        constexpr int kBatch = 8;
-#pragma unroll 1
-        for (long long rb = static_cast<long long>(blockIdx.x) * (4 * kBatch) + lane_r; rb < rows;
-             rb += static_cast<long long>(gridDim.x) * (4 * kBatch)) {
-            uint4 v[kBatch];
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const long long r = rb + 4 * u;
-                v[u] = r < rows ? b[r * c8 + c] : make_uint4(0u, 0u, 0u, 0u);
-            }
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-                    acc[2 * e] += f.x;
-                    acc[2 * e + 1] += f.y;
-                }
-            }
-        }
-    }
-    if (lane_r > 0) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) s_sum[lane_r - 1][col][e] = acc[e];
-    }
-    __syncthreads();
-    if (lane_r == 0 && c < c8) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(out + c * 8 + e, acc[e] + s_sum[0][col][e] + s_sum[1][col][e] + s_sum[2][col][e]);
-    }
-}
-
-int colsum_bf16(const void* b, float* out, long long rows, int n_ch, int accumulate, cudaStream_t stream) {
-    WGB_REQUIRE(b && out, "null pointer");
-    WGB_REQUIRE(rows > 0 && n_ch > 0 && n_ch % 8 == 0, "bad shape");
-    if (!accumulate) WGB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * n_ch, stream));
-    const int c8 = n_ch / 8;
-    long long blocks = (rows + 31) / 32;
-    if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
-    dim3 grid(static_cast<unsigned>(blocks), (c8 + 63) / 64);
-    colsum_bf16_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(b), out, rows, c8);
-    WGB_LAUNCH_CHECK();
-    return WGB_OK;
-}
-
+// ------------------------------------------------------------------------------------------------ small reductions
+// (The <= 8-channel weight gradients and the 512-channel bias sums run on the tensor cores: wgb_tc_wgrad against the
+// [rows, 64] hi/lo stack written by coupling_bwd_kernel.)
 // out[j] += sum_r a[r][j]  (a fp32 [rows, 8]; gradient of WN.end's bias)
 __global__ void colsum8_f32_kernel(const float* __restrict__ a, float* __restrict__ out, long long rows) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
