@@ -119,7 +119,14 @@ def train(num_gpus, rank, group_name, output_directory, epochs, learning_rate, s
                                 "{}/waveglow_{}".format(output_directory, iteration), waveglow_config)
             iteration += 1
             if max_iterations is not None and len(losses) >= max_iterations:
-                return losses
+                return _finish(num_gpus, losses)
+    return _finish(num_gpus, losses)
+
+
+def _finish(num_gpus, losses):
+    if num_gpus > 1 and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
     return losses
 
 
