@@ -240,9 +240,8 @@ def _backward(st: Dict[str, Tensor], sv: _Saved, n_flows: int, n_group: int, g_z
         d_w_in = torch.empty((L, 3, 2 * N_CH, N_CH), device=dev, dtype=f32)    # [layer][tap][out][in]
         db_in = torch.empty((L, 2 * N_CH), device=dev, dtype=f32)
         d_w_cond = torch.empty((L, 2 * N_CH, N_COND), device=dev, dtype=f32)
-        small = torch.empty((3, 8, N_CH), device=dev, dtype=f32)               # [0] start weight, [1][0] start bias, [2] scratch
         _lib.call("wgb_coupling_bwd", g_x, fs.x_mix, fs.log_s, gls, f["w_end_t"], g_out, g_skip, stack, b, t, N_CH, nh, s)
-        g_out_sum = small[2, 0, :8]
+        g_out_sum = torch.empty(8, device=dev, dtype=f32)                      # column sums of g_out = WN.end's bias gradient
         _lib.call("wgb_colsum8_f32", g_out, g_out_sum, rows, 0, s)
         for i in reversed(range(L)):
             d = 2 ** i
