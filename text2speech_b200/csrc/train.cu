@@ -356,52 +356,65 @@ int mix_bwd(float* g_x, const float* x_pre, const float* w, float* dw, long long
 //   dw[ci][m][k] = sum_{b,f} mel[b,ci,f] g_up[b, m, stride f + k],    db[m] = sum_{b,n} g_up[b,m,n]
 // One block per (m, 128 taps k); each thread owns one k and all ci (<= 80) accumulators.
 constexpr int kUpMaxMel = 80;
-// One block per (m, 256 taps): 128 threads, each owning taps k and k + 128 and all ci accumulators (mel values come as
-// broadcast LDS.128, one per 8 FMAs).
+constexpr int kUpCiTile = 40;                  // input channels per block (accumulators per thread: 2 taps x 40)
+// One block per (256 taps, m, ci tile x batch group): 128 threads, each owning taps k and k + 128 and 40 ci accumulators
+// per tap (mel values come as broadcast LDS.128, one per 8 FMAs; the next frame's two g values are fetched before the
+// current frame's FMAs).
 __global__ void __launch_bounds__(128)
 upsample_wgrad_kernel(const float* __restrict__ mel, const float* __restrict__ g_cond, float* __restrict__ dw,
                       float* __restrict__ db, int batch, int n_mel, int frames, int T, int ld, int ksize, int stride,
-                      int n_group) {
+                      int n_group, int ci_tiles) {
     constexpr int kFChunk = 32;
-    __shared__ __align__(16) float s_mel[kFChunk * kUpMaxMel];         // [frames chunk][kUpMaxMel], zero padded
+    __shared__ __align__(16) float s_mel[kFChunk * kUpCiTile];          // [frames chunk][ci tile], zero padded
     const int m = blockIdx.y;
+    const int ci0 = (blockIdx.z % ci_tiles) * kUpCiTile;
+    const int bz = blockIdx.z / ci_tiles, nbz = gridDim.z / ci_tiles;
     const int k0 = blockIdx.x * 256 + threadIdx.x, k1 = k0 + 128;
-    float acc0[kUpMaxMel], acc1[kUpMaxMel];
+    float acc0[kUpCiTile], acc1[kUpCiTile];
 #pragma unroll
-    for (int i = 0; i < kUpMaxMel; ++i) acc0[i] = acc1[i] = 0.f;
+    for (int i = 0; i < kUpCiTile; ++i) acc0[i] = acc1[i] = 0.f;
     float bsum = 0.f;
     const int n_total = T * n_group;
-    for (int b = blockIdx.z; b < batch; b += gridDim.z)
+    auto g_at = [&](int b, int f, int k) -> float {
+        const int n = stride * f + k;
+        if (f >= frames || k >= ksize || n >= n_total) return 0.f;
+        return g_cond[(static_cast<size_t>(b) * T + n / n_group) * ld + m * n_group + n % n_group];
+    };
+    for (int b = bz; b < batch; b += nbz)
     for (int f0 = 0; f0 < frames; f0 += kFChunk) {
         __syncthreads();
-        for (int i = threadIdx.x; i < kFChunk * kUpMaxMel; i += blockDim.x) {
-            const int ci = i / kFChunk, ff = i - ci * kFChunk;                 // consecutive threads read consecutive frames
-            s_mel[ff * kUpMaxMel + ci] = (ci < n_mel && f0 + ff < frames) ? mel[(static_cast<size_t>(b) * n_mel + ci) * frames + f0 + ff] : 0.f;
+        for (int i = threadIdx.x; i < kFChunk * kUpCiTile; i += blockDim.x) {
+            const int cl = i / kFChunk, ff = i - cl * kFChunk;                 // consecutive threads read consecutive frames
+            const int ci = ci0 + cl;
+            s_mel[ff * kUpCiTile + cl] = (ci < n_mel && f0 + ff < frames) ? mel[(static_cast<size_t>(b) * n_mel + ci) * frames + f0 + ff] : 0.f;
         }
         __syncthreads();
+        float g0 = g_at(b, f0, k0), g1 = g_at(b, f0, k1);
         for (int ff = 0; ff < kFChunk && f0 + ff < frames; ++ff) {
-            const int n0 = stride * (f0 + ff) + k0, n1 = stride * (f0 + ff) + k1;
-            float g0 = 0.f, g1 = 0.f;
-            if (k0 < ksize && n0 < n_total) g0 = g_cond[(static_cast<size_t>(b) * T + n0 / n_group) * ld + m * n_group + n0 % n_group];
-            if (k1 < ksize && n1 < n_total) g1 = g_cond[(static_cast<size_t>(b) * T + n1 / n_group) * ld + m * n_group + n1 % n_group];
-            if (k0 < stride) bsum += g0;                       // every sample n = stride f + k, k < stride, counted once
-            if (k1 < stride) bsum += g1;
-            const float4* sm4 = reinterpret_cast<const float4*>(s_mel + ff * kUpMaxMel);
+            const float g0n = g_at(b, f0 + ff + 1, k0), g1n = g_at(b, f0 + ff + 1, k1);      // prefetch the next frame
+            if (ci0 == 0) {                                    // every sample n = stride f + k, k < stride, counted once
+                if (k0 < stride) bsum += g0;
+                if (k1 < stride) bsum += g1;
+            }
+            const float4* sm4 = reinterpret_cast<const float4*>(s_mel + ff * kUpCiTile);
 #pragma unroll
-            for (int q = 0; q < kUpMaxMel / 4; ++q) {
+            for (int q = 0; q < kUpCiTile / 4; ++q) {
                 const float4 v = sm4[q];
                 acc0[4 * q] = fmaf(v.x, g0, acc0[4 * q]);         acc1[4 * q] = fmaf(v.x, g1, acc1[4 * q]);
                 acc0[4 * q + 1] = fmaf(v.y, g0, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(v.y, g1, acc1[4 * q + 1]);
                 acc0[4 * q + 2] = fmaf(v.z, g0, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(v.z, g1, acc1[4 * q + 2]);
                 acc0[4 * q + 3] = fmaf(v.w, g0, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(v.w, g1, acc1[4 * q + 3]);
             }
+            g0 = g0n;
+            g1 = g1n;
         }
     }
 #pragma unroll
-    for (int ci = 0; ci < kUpMaxMel; ++ci) {
+    for (int cl = 0; cl < kUpCiTile; ++cl) {
+        const int ci = ci0 + cl;
         if (ci < n_mel) {
-            if (k0 < ksize) atomicAdd(dw + (static_cast<size_t>(ci) * n_mel + m) * ksize + k0, acc0[ci]);
-            if (k1 < ksize) atomicAdd(dw + (static_cast<size_t>(ci) * n_mel + m) * ksize + k1, acc1[ci]);
+            if (k0 < ksize) atomicAdd(dw + (static_cast<size_t>(ci) * n_mel + m) * ksize + k0, acc0[cl]);
+            if (k1 < ksize) atomicAdd(dw + (static_cast<size_t>(ci) * n_mel + m) * ksize + k1, acc1[cl]);
         }
     }
 #pragma unroll
@@ -416,8 +429,10 @@ int upsample_wgrad(const float* mel, const float* g_cond, float* dw, float* db, 
     WGB_REQUIRE(batch > 0 && frames > 0 && T > 0 && ld >= n_mel * n_group && ksize > 0 && stride > 0, "bad shape");
     WGB_CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(float) * n_mel * n_mel * ksize, stream));
     WGB_CUDA_TRY(cudaMemsetAsync(db, 0, sizeof(float) * n_mel, stream));
-    dim3 grid((ksize + 255) / 256, n_mel, batch < 8 ? batch : 8);
-    upsample_wgrad_kernel<<<grid, 128, 0, stream>>>(mel, g_cond, dw, db, batch, n_mel, frames, T, ld, ksize, stride, n_group);
+    const int ci_tiles = (n_mel + kUpCiTile - 1) / kUpCiTile;
+    dim3 grid((ksize + 255) / 256, n_mel, ci_tiles * (batch < 8 ? batch : 8));   // measured: 8 batch groups 2.2 ms, 2 groups 2.7 ms
+    upsample_wgrad_kernel<<<grid, 128, 0, stream>>>(mel, g_cond, dw, db, batch, n_mel, frames, T, ld, ksize, stride, n_group,
+                                                    ci_tiles);
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }
