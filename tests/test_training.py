@@ -102,6 +102,47 @@ def test_per_step_packing_matches_inference_packing():
     assert torch.equal(f["wt_rs"][3], w_rs[3][:, :, 0].t().bfloat16()) and f["n_half"] == 3
 
 
+def test_effective_weights_cover_every_parameter():
+    """The flat (name, tensor) list handed to the autograd node names every weight / bias of the reference layout once,
+    and every model parameter (weight_g / weight_v included) is reachable from it through autograd."""
+    import text2speech_b200 as t2s
+    from text2speech_b200 import training
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = t2s.WaveGlow(**train_config())
+    names, tensors = training.effective_weights(m)
+    folded = set(syn.synthetic_state_dict(train_config(), weight_norm=False))
+    assert len(names) == len(set(names)) and set(names) == folded
+    total = sum((t.float() ** 2).sum() for t in tensors)
+    total.backward()
+    missing = [n for n, p in m.named_parameters() if p.grad is None]
+    assert not missing, missing[:5]
+    # weight norm is applied with autograd-visible ops: w = g v / ||v||
+    conv = m.WN[0].in_layers[0]
+    w = tensors[names.index("WN.0.in_layers.0.weight")]
+    v, g = conv.weight_v.detach(), conv.weight_g.detach()
+    want = v * (g / v.reshape(v.shape[0], -1).norm(dim=1).reshape(-1, 1, 1))
+    assert util.rel_l2(w.detach(), want) <= 1e-6
+
+
+def test_training_refuses_cpu():
+    """No CPU fallback in the training direction either."""
+    import text2speech_b200 as t2s
+    from text2speech_b200 import train as t2s_train
+    from text2speech_b200.training import FusedAdam
+    with pytest.raises(RuntimeError):
+        FusedAdam([torch.nn.Parameter(torch.zeros(4))])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = t2s.WaveGlow(**train_config()).train()
+    mel, wav = train_inputs()
+    with pytest.raises(RuntimeError):
+        m((mel, wav))
+    with pytest.raises(ValueError):
+        t2s_train.train(1, 0, "", "out", 1, 1e-4, 1.0, 10, 2, 1234, "", waveglow_config=train_config(), data_config={},
+                        fp16_run=True)
+
+
 # ---------------------------------------------------------------------------------------------------- GPU
 @pytest.fixture(scope="module")
 def lib():
