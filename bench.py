@@ -46,9 +46,9 @@ GATE_ENTRY_POINTS = ("wgb_tc_wn_gate", "wgb_tc2_wn_gate", "wgb_tc2_wn_gate_mel")
 # (ncu --set full, profiles/r01c_ncu_full_summary.csv: 6.667 + 1.791 GB); algorithmic bytes are
 # h 1 KB + cond 1.25 KB read + acts 1 KB written per group step = 5.84 GB.  Scales with the per-rank batch.
 GATE_DRAM_BYTES_PER_LAUNCH_B64 = {"wgb_tc2_wn_gate": 8.458e9,         # profiles/r01c_ncu_full_summary.csv
-                                  "wgb_tc2_wn_gate_mel": 4.02e9}      # profiles/r01l_ncu_full_summary.csv (2.24 + 1.78 GB;
-                                                                      # 3.49 + 1.78 GB for the launch captured in r01h)
-GATE_DRAM_SOURCE = "profiles/r01l_ncu_full_summary.csv (composed gate) / r01c (cond-tensor gate)"
+                                  "wgb_tc2_wn_gate_mel": 4.16e9}      # profiles/r01t_ncu_full_summary.csv (2.38 + 1.78 GB
+                                                                      # for the launch captured there; 2.24 + 1.78 GB in r01l)
+GATE_DRAM_SOURCE = "profiles/r01t_ncu_full_summary.csv (composed gate) / r01c (cond-tensor gate)"
 
 
 def workload_config(n_gpus):
