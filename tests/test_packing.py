@@ -184,3 +184,35 @@ def test_start_folded_into_first_in_layer():
         assert w0.shape == (1024, 64) and w0.dtype == torch.bfloat16
         got = _x_stack_rows(x, n_half).double() @ w0.double().t()
         assert util.rel_l2(got, want) < 3e-5, k
+
+
+@pytest.mark.parametrize("cond_path", ["mel", "cond"])
+def test_engine_host_sequence_on_emulated_kernels(monkeypatch, cond_path):
+    """The REAL engine.infer / engine.forward (kernel sequencing, padded frame layout and guard rows, composed
+    conditioning operands, first-layer fold, fused next-flow start / 1x1 mix) run on the CPU with every entry point
+    replaced by a torch stand-in of its contract (tests/emulate_engine.py), against the oracle."""
+    from tests import emulate_engine
+    from text2speech_b200 import engine
+    calls = emulate_engine.install(monkeypatch)
+    from text2speech_b200 import synthetic as syn
+    cfg = dict(syn.load_config())
+    cfg.update(n_flows=4, n_early_every=2, n_early_size=2)        # n_half 4, 4, 3, 3: keeps the CPU composition cheap
+    sd = syn.synthetic_state_dict(cfg, seed=1234, end_std=0.01)
+    pk = PackedWaveGlow(sd, 4, 8, 512, 8, "bf16", torch.device("cpu"), compose_cond=(cond_path == "mel"))
+    pk.cond_path = cond_path
+    mel, z, wav = util.golden_inputs(2, 6)
+    with torch.no_grad():
+        audio = engine.infer(pk, mel, z, util.SIGMA)
+        want = oracle.waveglow_infer(sd, mel, z, util.SIGMA)
+        assert audio.shape == want.shape and util.snr_db(audio, want) >= util.MIN_SNR_DB
+        if cond_path == "mel":
+            assert "wgb_tc2_wn_gate_mel0" in calls and "wgb_x_stack" in calls and "wgb_tc2_wn_gate" not in calls
+            assert calls.count("wgb_wn_start_padded") == 1                   # later flows: fused into the skip+end kernel
+        else:
+            assert "wgb_tc2_wn_gate_mel" not in calls and calls.count("wgb_tc2_wn_gate") == 32
+        # forward direction, audio shorter than 256 * frames (trimmed / partial last frame)
+        zf, log_s, log_det = engine.forward(pk, mel, wav[:, :-72])
+        zw, lsw, ldw = oracle.waveglow_forward(sd, mel, wav[:, :-72])
+        assert util.snr_db(zf, zw) >= util.MIN_SNR_DB
+        assert util.snr_db(log_s[-1], lsw[-1]) >= 25.0
+        assert all(abs(float(a) - float(b)) <= 1e-3 for a, b in zip(log_det, ldw))
