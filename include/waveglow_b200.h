@@ -31,6 +31,10 @@ extern "C" {
 #endif
 
 WGB_API int wgb_abi_version(void);
+/* hex SHA-256 of the sources (csrc + this header) the library was built from: the Python binding compares it with
+ * the tree it parses its prototypes from, so a stale library is rebuilt (or refused) instead of being called through
+ * newer prototypes. */
+WGB_API const char* wgb_source_hash(void);
 WGB_API const char* wgb_last_error(void);
 /* 0 iff `device` exists and is compute capability 10.x; selects nothing. */
 WGB_API int wgb_device_check(int device);
@@ -264,7 +268,8 @@ WGB_API int wgb_spec_set_magnitude(float* spec, const float* target, int batch, 
 WGB_API int wgb_stft_recombine(const float* mag, const float* phase, float* spec, int batch, int F, int cutoff, int cp,
                        void* stream);
 /* overlap-add + window-sum normalisation + xL/hop + trim (stft.py:105-128; audio_processing.py:7-48):
- * frames [B,F,L] -> out [B, hop*(F-1)]; win_sq = fp64 squared padded window [L]. */
+ * frames [B,F,L] -> out [B, hop*(F-1)]; win_sq = fp64 squared padded window [L], or NULL for the reference's
+ * window=None case (no envelope division and no L/hop scale, stft.py:111-125). */
 WGB_API int wgb_istft_overlap_add(const float* frames, const double* win_sq, float* out, int batch, int F, int L,
                           int hop, void* stream);
 
@@ -330,7 +335,8 @@ WGB_API int wgb_adam_step(float* p, const float* g, float* m, float* v, long lon
 /* The same step with the step counter on the device (incremented by the call): CUDA-graph replayable. */
 WGB_API int wgb_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                               float eps, int* step_dev, float grad_scale, void* stream);
-/* log|det W| of a c x c matrix (c <= 8) and (W^-1)^T = its gradient (glow.py:100): out[0], inv_t fp32 [c][c]. */
+/* torch.logdet(W) of a c x c matrix (c <= 8; NaN when det W < 0, as in the reference) and (W^-1)^T = its gradient
+ * (glow.py:100): out[0], inv_t fp32 [c][c]. */
 WGB_API int wgb_logdet(const float* w, float* out, float* inv_t, int c, void* stream);
 
 #ifdef __cplusplus

@@ -179,7 +179,7 @@ def upsample_wgrad(mel, g_cond, dw, db, b, n_mel, frames, t, ld, ksize, stride, 
 
 def logdet(w, out, inv_t, c, s):
     w2 = w.reshape(c, c).double()
-    out[0] = torch.linalg.slogdet(w2)[1].float()
+    out[0] = torch.logdet(w2).float()
     inv_t.copy_(torch.linalg.inv(w2).t().float())
 
 

@@ -26,6 +26,8 @@ from text2speech_b200 import synthetic as syn       # noqa: E402
 RECIPES = {                       # name -> synthetic_state_dict kwargs
     "bench": dict(seed=1234, end_std=0.01, gain=1.0),
     "stress": dict(seed=4321, end_std=0.01, gain=2.0),
+    # non-orthogonal invertible 1x1 convs (W^-1 != W^T, log det W != 0, two flows with det W < 0) and a stronger coupling
+    "skew": dict(seed=777, end_std=0.03, gain=1.0, mix="skew"),
 }
 SIGMA = 0.666
 TAP_FLOW = 11
@@ -131,6 +133,9 @@ def golden_stft(ref_stft, ref_layers, ref_denoiser, model, out):
         small = ref_stft.STFT(64, 16, 48)         # filter_length > win_length branch (stft.py:58-62)
         mag_s, ph_s = small.transform(y[:, :512])
         rec_s = small.inverse(mag_s, ph_s)
+        nowin = ref_stft.STFT(64, 16, 64, window=None)   # window=None: no envelope division, no L/hop scale (stft.py:111)
+        mag_n, ph_n = nowin.transform(y[:, :512])
+        rec_n = nowin.inverse(mag_n, ph_n)
     rows = np.array([0, 1, 2, 100, 256, 511, 512, 513, 514, 700, 1024, 1025])
     out["stft_rows"] = rows
     out["stft_forward_basis_rows"] = stft.forward_basis[rows, 0].numpy()
@@ -145,6 +150,8 @@ def golden_stft(ref_stft, ref_layers, ref_denoiser, model, out):
     out["denoised_s0p01"] = den_out2.numpy()
     out["small_mag"] = mag_s.numpy()
     out["small_recon"] = rec_s.numpy()
+    out["nowin_mag"] = mag_n.numpy()
+    out["nowin_recon"] = rec_n.numpy()
     from utils.audio_processing import window_sumsquare     # reference helper
     out["wss_17"] = window_sumsquare("hann", 17, hop_length=hop, win_length=win, n_fft=fl, dtype=np.float32)
 

@@ -90,6 +90,31 @@ def test_exact_packing_with_fp32_weights():
     assert util.rel_l2(got, want) < 2e-5
 
 
+def test_packed_mix_with_non_orthogonal_weights():
+    """'skew' recipe (W^-1 != W^T, log det W != 0, det W < 0 in flows 3 and 8): the packed inverse / forward mixes and
+    log_det_W through the kernels' data layout (emulated from the packed weights) against the oracle.  With the
+    orthogonal recipes a packer that returned W^T for W^-1 would pass; here it cannot."""
+    import math
+    sd = util.state_dict("skew")
+    pk = PackedWaveGlow(sd, 12, 8, 512, 8, "bf16", torch.device("cpu"))
+    mel, z, wav = util.golden_inputs(1, 3)
+    with torch.no_grad():
+        want = oracle.waveglow_infer(sd, mel, z, util.SIGMA)
+        got = emulate.infer(pk, mel, z, util.SIGMA, round_bf16=False)
+        assert util.snr_db(got, want) > 40.0
+        zr, lsr, ldr = oracle.waveglow_forward(sd, mel, wav)
+        zf, ls, ld = emulate.forward(pk, mel, wav, round_bf16=False)
+        assert util.snr_db(zf, zr) > 40.0
+    for k in range(12):
+        w, r = float(ldr[k]), ld[k]
+        assert math.isnan(r) == math.isnan(w) == (k in (3, 8))
+        if not math.isnan(w):
+            assert abs(w) > 10.0 and abs(r - w) <= 1e-5 * abs(w)
+    for fl in pk.flows:                          # transposing instead of inverting is now visibly wrong
+        c = 2 * fl["n_half"]
+        assert util.rel_l2(fl["w_mix_inv"][:c, :c], fl["w_mix"][:c, :c].t()) > 0.3
+
+
 def test_cond_mel_composition_matches_cond_layer_of_upsampled_mel():
     """pack_cond_mel: cond_layers[i](regroup(upsample(mel))) == per-phase (W_cond U_phase) . stack(mel[f-j]) + bias
     (the algebra behind wgb_tc2_wn_gate_mel; glow.py:252-258 + :161)."""

@@ -477,6 +477,70 @@ def test_training_loop_with_fused_adam_and_flat_allreduce(lib):
     assert 0.5 * lr <= moved <= 3.2 * lr, moved
 
 
+def test_packed_weight_cache_sees_raw_kernel_updates():
+    """FusedAdam rewrites the parameters with a raw kernel behind torch's version counters and data pointers; the packed
+    weights of WaveGlow are keyed on a generation counter that every such step bumps (CPU: the key logic only)."""
+    import text2speech_b200 as t2s
+    from text2speech_b200 import packing
+    cfg = train_config()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = t2s.WaveGlow(**cfg)
+    sig0 = m._signature()
+    assert m._signature() == sig0
+    packing.bump_param_generation()
+    assert m._signature() != sig0
+    import copy
+    m._pack_cache = {"dummy": (sig0, object())}
+    assert copy.deepcopy(m)._pack_cache == {}                 # copies / pickles carry parameters only
+
+
+@pytest.mark.gpu
+def test_infer_after_training_steps_uses_the_new_weights(lib):
+    """infer -> Adam step -> infer -> graphed step -> infer: every infer sees the current parameters (the packed-weight
+    cache used to be keyed on data_ptr / _version only, which FusedAdam's flat-buffer kernel never changes), and the
+    audio equals that of a freshly constructed model holding the same state."""
+    import text2speech_b200 as t2s
+    from text2speech_b200.training import FusedAdam, GraphedTrainStep
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = t2s.WaveGlow(**train_config())
+    m.load_state_dict(_train_state())
+    m = m.to(DEV).train()
+    opt = FusedAdam(m.parameters(), lr=1e-3)                 # large steps: the audio must move visibly
+    crit = t2s.WaveGlowLoss(SIGMA)
+    mel, wav = train_inputs()
+    mel, wav = mel.to(DEV), wav.to(DEV)
+    z = syn.synthetic_z(mel.shape[0], mel.shape[2], seed=5).to(DEV)
+
+    def sample():
+        m.eval()
+        with torch.no_grad():
+            out = m.infer(mel, sigma=SIGMA, z=z).clone()
+        m.train()
+        return out
+
+    def fresh():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            f = t2s.WaveGlow(**train_config())
+        f.load_state_dict({k: v.detach().clone() for k, v in m.state_dict().items()})
+        return f.to(DEV).eval().infer(mel, sigma=SIGMA, z=z)
+
+    a0 = sample()
+    opt.zero_grad()
+    crit(m((mel, wav))).backward()
+    opt.step()
+    a1 = sample()
+    assert not torch.equal(a1, a0) and util.snr_db(a1.cpu(), a0.cpu()) < 60.0
+    assert torch.equal(a1, fresh())
+    step = GraphedTrainStep(m, opt, crit, mel.shape[0], mel.shape[1], mel.shape[2], wav.shape[1])
+    step(mel, wav)
+    a2 = sample()
+    assert not torch.equal(a2, a1)
+    assert torch.equal(a2, fresh())
+
+
 @pytest.mark.gpu
 def test_logdet_kernel_matches_torch(lib):
     from text2speech_b200.training import _LogDet
@@ -484,12 +548,24 @@ def test_logdet_kernel_matches_torch(lib):
     for c in (8, 6, 4, 2):
         w = torch.randn((c, c, 1), generator=g).to(DEV).requires_grad_(True)
         w_ref = w.detach().clone().requires_grad_(True)
+        if float(torch.det(w_ref.detach().squeeze(-1))) < 0:
+            with torch.no_grad():
+                w[:, 0] = -w[:, 0]
+                w_ref[:, 0] = -w_ref[:, 0]
         got = _LogDet.apply(w, 3.0)
-        want = 3.0 * torch.linalg.slogdet(w_ref.squeeze(-1))[1]
+        want = 3.0 * torch.logdet(w_ref.squeeze(-1))
         assert abs(float(got) - float(want)) <= 1e-5 * max(1.0, abs(float(want)))
         got.backward()
         want.backward()
         assert util.rel_l2(w.grad.cpu(), w_ref.grad.cpu()) <= 1e-5
+        # det W < 0: torch.logdet (what glow.py:100 calls) is NaN, and so is the kernel
+        sign = float(torch.linalg.slogdet(w_ref.detach().squeeze(-1))[0])
+        flipped = w.detach().clone()
+        flipped[:, 0] = -flipped[:, 0]
+        for m, s in ((w.detach(), sign), (flipped, -sign)):
+            val = float(_LogDet.apply(m, 1.0))
+            assert np.isnan(val) == (s < 0), (c, s, val)
+            assert np.isnan(float(torch.logdet(m.squeeze(-1)))) == (s < 0)
 
 
 @pytest.mark.gpu

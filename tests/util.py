@@ -14,12 +14,33 @@ SIGMA = 0.666
 RECIPES = {                       # must match tests/golden/make_golden.py
     "bench": dict(seed=1234, end_std=0.01, gain=1.0),
     "stress": dict(seed=4321, end_std=0.01, gain=2.0),
+    # non-orthogonal invertible 1x1 convs (W^-1 != W^T, log det W != 0, two flows with det W < 0) and a stronger coupling
+    "skew": dict(seed=777, end_std=0.03, gain=1.0, mix="skew"),
 }
 # Tolerances (north_star): per-WN-layer relative L2 <= 2e-3 in BF16 mode, <= 1e-5 in the FP32
 # validation mode, end-to-end audio SNR >= 30 dB against reference FP32.
 TOL_LAYER_BF16 = 2e-3
 TOL_LAYER_FP32 = 1e-5
-MIN_SNR_DB = 30.0
+MIN_SNR_DB = 30.0                 # north_star's statement; the regression gates are the per-test floors below
+
+# Regression floors for the end-to-end BF16 tests, in dB: the value measured on a B200 (profiles/r02a_snr_measured.json,
+# written by a GPU run with WGB_SNR_LOG set) minus ~6 dB, never below north_star's 30 dB.  A kernel regression that costs
+# more than one bit of accuracy fails here long before the audio drops to 30 dB (the coupling is close to the identity
+# at end_std 0.01: zeroing whole sub-layers still clears 30 dB on the "bench" recipe).
+SNR_FLOORS = {
+}
+
+
+def assert_snr(key: str, x, ref) -> float:
+    """SNR of x against ref must clear SNR_FLOORS[key]; the measured value is appended to $WGB_SNR_LOG when set."""
+    snr = snr_db(x, ref)
+    log = os.environ.get("WGB_SNR_LOG")
+    if log:
+        with open(log, "a") as f:
+            f.write(f"{key}\t{snr:.2f}\n")
+    floor = max(MIN_SNR_DB, SNR_FLOORS.get(key, MIN_SNR_DB))
+    assert snr >= floor, (key, snr, floor)
+    return snr
 
 
 def load_golden():

@@ -52,8 +52,10 @@ def _load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            from . import build as _build
+        # a library built from other sources than this tree (whose header the prototypes below are parsed from) is
+        # rebuilt before it is loaded; without nvcc that raises instead of calling stale code through new prototypes
+        from . import build as _build
+        if _build.needs_build():
             _build.build()
         lib = ctypes.CDLL(LIB_PATH)
         for name, (ret, types) in parse_header().items():
@@ -61,8 +63,9 @@ def _load():
             fn.restype = ctypes.c_char_p if "char" in ret else ctypes.c_int
             fn.argtypes = [ctypes.c_void_p if t == "ptr" else _CTYPES[t] for t in types]
             _protos[name] = (fn, types)
-        if lib.wgb_abi_version() != 1:
-            raise RuntimeError("libwaveglow_b200.so ABI version mismatch; rebuild with python -m text2speech_b200.build")
+        if lib.wgb_abi_version() != 1 or lib.wgb_source_hash().decode() != _build.source_hash():
+            raise RuntimeError("libwaveglow_b200.so does not match this source tree; rebuild with "
+                               "python -m text2speech_b200.build --force")
         _lib = lib
         return lib
 

@@ -90,6 +90,12 @@ static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 extern "C" {
 
 WGB_API int wgb_abi_version(void) { return WGB_ABI_VERSION; }
+#ifndef WGB_SOURCE_HASH
+#define WGB_SOURCE_HASH "unknown"
+#endif
+// the marker prefix lets build.py read the hash out of the file without dlopen-ing a possibly stale library
+static const char kSourceHash[] = "WGB_SOURCE_HASH=" WGB_SOURCE_HASH;
+WGB_API const char* wgb_source_hash(void) { return kSourceHash + 16; }
 WGB_API const char* wgb_last_error(void) { return error_buffer(); }
 
 WGB_API int wgb_device_check(int device) {

@@ -343,11 +343,14 @@ int stft_recombine(const float* mag, const float* phase, float* spec, int batch,
 // Overlap-add of the per-frame inverse-basis outputs (the conv_transpose1d of stft.py:105-109),
 // window-sum normalisation where the envelope exceeds float32 tiny, x L/hop, and the L/2 trim
 // (stft.py:111-128).  The envelope is rebuilt per sample exactly like the host loop of
-// audio_processing.py:45-47 (frames ascending, float32 running sum of float64 squares).
+// audio_processing.py:45-47 (frames ascending, float32 running sum of float64 squares).  win_sq == NULL is the
+// reference's window=None case: neither the envelope division nor the L/hop scale is applied (both sit inside
+// ``if self.window is not None`` at stft.py:111-125).
 __global__ void istft_overlap_add_kernel(const float* __restrict__ frames, const double* __restrict__ win_sq,
                                          float* __restrict__ out, int F, int L, int hop, int n_out, long long total) {
     const int half = L / 2;
-    const float scale = static_cast<float>(L) / static_cast<float>(hop);
+    const bool windowed = win_sq != nullptr;
+    const float scale = windowed ? static_cast<float>(L) / static_cast<float>(hop) : 1.f;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long b = i / n_out;
@@ -360,7 +363,7 @@ __global__ void istft_overlap_add_kernel(const float* __restrict__ frames, const
         for (int f = f_lo; f <= f_hi; ++f) {
             const int r = n - f * hop;
             acc += frames[(b * F + f) * L + r];
-            env = static_cast<float>(static_cast<double>(env) + win_sq[r]);
+            if (windowed) env = static_cast<float>(static_cast<double>(env) + win_sq[r]);
         }
         if (env > 1.17549435e-38f) acc /= env;
         out[i] = acc * scale;
@@ -372,7 +375,8 @@ __global__ void istft_overlap_add_kernel(const float* __restrict__ frames, const
 __global__ void istft_overlap_add4_kernel(const float* __restrict__ frames, const double* __restrict__ win_sq,
                                           float* __restrict__ out, int F, int L, int hop, int n_out, long long total4) {
     const int half = L / 2;
-    const float scale = static_cast<float>(L) / static_cast<float>(hop);
+    const bool windowed = win_sq != nullptr;
+    const float scale = windowed ? static_cast<float>(L) / static_cast<float>(hop) : 1.f;
     const int per_row = n_out >> 2;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -388,8 +392,10 @@ __global__ void istft_overlap_add4_kernel(const float* __restrict__ frames, cons
             const int r = n - f * hop;
             const float4 v = *reinterpret_cast<const float4*>(frames + (b * F + f) * L + r);
             acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+            if (windowed) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) env[j] = static_cast<float>(static_cast<double>(env[j]) + win_sq[r + j]);
+                for (int j = 0; j < 4; ++j) env[j] = static_cast<float>(static_cast<double>(env[j]) + win_sq[r + j]);
+            }
         }
         float o[4];
 #pragma unroll
@@ -400,7 +406,7 @@ __global__ void istft_overlap_add4_kernel(const float* __restrict__ frames, cons
 
 int istft_overlap_add(const float* frames, const double* win_sq, float* out, int batch, int F, int L, int hop,
                       cudaStream_t stream) {
-    WGB_REQUIRE(frames && win_sq && out && batch > 0 && F > 1 && L > 0 && hop > 0, "bad arguments");
+    WGB_REQUIRE(frames && out && batch > 0 && F > 1 && L > 0 && hop > 0, "bad arguments");
     const int n_out = hop * (F - 1);
     if (hop % 4 == 0 && L % 8 == 0 && (reinterpret_cast<uintptr_t>(frames) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         const long long total4 = static_cast<long long>(batch) * (n_out >> 2);

@@ -497,7 +497,7 @@ int adam_step_dev(float* p, const float* g, float* m, float* v, long long n, flo
 // ------------------------------------------------------------------------------------------------ log|det W|
 // Invertible1x1Conv's log-determinant and its gradient (glow.py:100: torch.logdet(W); d logdet / dW = W^-T) for a
 // c x c matrix, c <= 8, by Gauss-Jordan elimination with partial pivoting in one thread (fp64 internally).
-// w fp32 [c][c]; out[0] = log|det W|; inv_t fp32 [c][c] = (W^-1)^T.
+// w fp32 [c][c]; out[0] = log det W (NaN when det W < 0, as torch.logdet returns); inv_t fp32 [c][c] = (W^-1)^T.
 __global__ void logdet_kernel(const float* __restrict__ w, float* __restrict__ out, float* __restrict__ inv_t, int c) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double a[8][16];
@@ -507,13 +507,17 @@ __global__ void logdet_kernel(const float* __restrict__ w, float* __restrict__ o
             a[i][c + j] = i == j ? 1.0 : 0.0;
         }
     double logdet = 0.0;
+    bool negative = false;
     for (int col = 0; col < c; ++col) {
         int piv = col;
         for (int r = col + 1; r < c; ++r)
             if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
-        if (piv != col)
+        if (piv != col) {
+            negative = !negative;
             for (int j = 0; j < 2 * c; ++j) { const double t = a[col][j]; a[col][j] = a[piv][j]; a[piv][j] = t; }
+        }
         const double d = a[col][col];
+        if (d < 0.0) negative = !negative;
         logdet += log(fabs(d));
         const double inv = 1.0 / d;
         for (int j = 0; j < 2 * c; ++j) a[col][j] *= inv;
@@ -523,7 +527,7 @@ __global__ void logdet_kernel(const float* __restrict__ w, float* __restrict__ o
             for (int j = 0; j < 2 * c; ++j) a[r][j] -= f * a[col][j];
         }
     }
-    out[0] = static_cast<float>(logdet);
+    out[0] = negative ? __int_as_float(0x7fc00000) : static_cast<float>(logdet);
     for (int i = 0; i < c; ++i)
         for (int j = 0; j < c; ++j) inv_t[j * c + i] = static_cast<float>(a[i][c + j]);
 }

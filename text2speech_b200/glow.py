@@ -25,7 +25,7 @@ from typing import Optional
 import torch
 
 from . import _lib, engine
-from .packing import PackedWaveGlow
+from .packing import PackedWaveGlow, param_generation
 
 
 def fused_add_tanh_sigmoid_multiply(input_a: torch.Tensor, input_b: torch.Tensor, n_channels) -> torch.Tensor:
@@ -117,6 +117,15 @@ class WN(torch.nn.Module):
             self.res_skip_layers.append(wn(torch.nn.Conv1d(n_channels, rs, 1), name="weight"))
         self._owner = None          # (WaveGlow, flow index), set by WaveGlow.__init__ / _attach
 
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_owner"] = None      # back-reference to the owning model: re-attached by WaveGlow.__setstate__
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self.__dict__.setdefault("_owner", None)
+
     def forward(self, forward_input):
         audio, spect = forward_input
         if self._owner is None:
@@ -160,6 +169,16 @@ class WaveGlow(torch.nn.Module):
         for k, wn in enumerate(self.WN):
             object.__setattr__(wn, "_owner", (self, k))
 
+    def __getstate__(self):
+        # torch.save(model) / copy.deepcopy(model) carry parameters only: the packed-weight cache (2+ GB of derived
+        # device tensors) is rebuilt on first use; WN._owner is restored by _attach.  weight_norm's cached non-leaf
+        # ``weight`` attributes are detached first (current torch refuses to deepcopy them; the kernels never read them)
+        from .convert_model import detach_weight_norm_cache
+        detach_weight_norm_cache(self)
+        state = self.__dict__.copy()
+        state["_pack_cache"] = {}
+        return state
+
     def __setstate__(self, state):          # pickled-module checkpoints (waveglow/inference.py:37)
         super().__setstate__(state)
         self.__dict__.setdefault("mode", "bf16")
@@ -179,7 +198,9 @@ class WaveGlow(torch.nn.Module):
                                "(config.json); use mode='fp32' for other shapes")
 
     def _signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # data_ptr / _version catch torch-side updates; the generation counter catches raw-kernel updates (FusedAdam
+        # re-points p.data at a flat buffer and steps it with wgb_adam_step_dev, which changes neither)
+        return (param_generation(),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _packed(self, device) -> PackedWaveGlow:
         _lib.require_b200(device)

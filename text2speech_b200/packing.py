@@ -131,16 +131,33 @@ def pack_skip_end_layers(w_skip: Tensor, w_end: Tensor, n_ch: int):
     return comp.float().reshape(8, layers, n_ch).permute(1, 2, 0).contiguous()
 
 
+# Parameter generation: bumped by every in-place weight update that torch's version counters cannot see (FusedAdam's
+# raw kernel over its flat buffer, CUDA-graph replays of a training step).  WaveGlow._signature() includes it, so packed
+# weights are rebuilt after training steps instead of silently going stale.
+_param_generation = [0]
+
+
+def bump_param_generation() -> int:
+    _param_generation[0] += 1
+    return _param_generation[0]
+
+
+def param_generation() -> int:
+    return _param_generation[0]
+
+
 def pack_mix(w: Tensor):
-    """convinv weight [C,C,1] -> (W [8,8] fp32, W^-1 [8,8] fp32 via fp64, log|det W| python float).
-    The reference inverts in fp32 and caches (glow.py:88-95); fp64 here is strictly more accurate."""
+    """convinv weight [C,C,1] -> (W [8,8] fp32, W^-1 [8,8] fp32 via fp64, log det W python float).
+    The reference inverts in fp32 and caches (glow.py:88-95); fp64 here is strictly more accurate.  log det W is
+    torch.logdet's (glow.py:100): NaN when det W < 0."""
     c = w.shape[0]
     w2 = w[:, :, 0].double()
     fwd = torch.zeros(8, 8, dtype=torch.float32)
     inv = torch.zeros(8, 8, dtype=torch.float32)
     fwd[:c, :c] = w2.float()
     inv[:c, :c] = torch.linalg.inv(w2).float()
-    return fwd, inv, float(torch.linalg.slogdet(w2)[1])
+    sign, logabs = torch.linalg.slogdet(w2)
+    return fwd, inv, float(logabs) if float(sign) > 0 else float("nan")
 
 
 def pack_upsample(w: Tensor, b: Tensor, n_group: int, ld_tap: int):

@@ -67,6 +67,8 @@ class MultiGpuVocoder:
         self.devices = [torch.device(d) for d in devices]
         self.replicas = []
         for i, d in enumerate(self.devices):
+            # WaveGlow.__getstate__ makes the copy carry parameters only (no packed-weight cache of device 0, no
+            # weight_norm non-leaf tensors), so weight-normed checkpoints replicate too
             replica = model if i == 0 else copy.deepcopy(model)
             self.replicas.append(replica.to(d).eval())
 

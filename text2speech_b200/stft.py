@@ -95,10 +95,10 @@ class STFT(torch.nn.Module):
                 fwd_paired = _split3(fwd[order]).to(device)
                 fwd, inv = _split3(fwd), _split3(inv)
             if self.window is not None:
-                sq = padded_window(self.window, self.win_length, length) ** 2
+                sq = torch.from_numpy(padded_window(self.window, self.win_length, length) ** 2).double().to(device)
             else:
-                sq = np.zeros(length)
-            self._pack = (key, fwd.to(device), inv.to(device), torch.from_numpy(sq).double().to(device), cp, fwd_paired)
+                sq = None          # window=None: no envelope division and no L/hop scale (stft.py:111-125)
+            self._pack = (key, fwd.to(device), inv.to(device), sq, cp, fwd_paired)
         return self._pack[1:5]
 
     def _paired_basis(self, device):

@@ -53,11 +53,16 @@ def _uniform(shape, bound, seed, key):
 
 
 def synthetic_state_dict(config: Optional[Dict] = None, seed: int = 1234, end_std: float = 0.01,
-                         gain: float = 1.0, weight_norm: bool = False) -> "OrderedDict[str, torch.Tensor]":
+                         gain: float = 1.0, weight_norm: bool = False,
+                         mix: str = "orthogonal") -> "OrderedDict[str, torch.Tensor]":
     """Random-init WaveGlow ``state_dict`` in the reference layout.
 
     weight_norm=False gives the layout after ``WaveGlow.remove_weightnorm`` (``*.weight``);
     True gives ``weight_g`` / ``weight_v`` pairs with g != ||v|| so that folding is exercised.
+    mix='orthogonal' is the reference's init of the invertible 1x1 convs (glow.py:73-80: W^-1 = W^T, log|det W| = 0);
+    mix='skew' scales the columns of that Q by U[0.5, 2] (a trained-model-like W: W^-1 != W^T, log|det W| != 0) and
+    flips the sign of one column in every flow k with k % 5 == 3, so those flows have det W < 0 (torch.logdet, which
+    glow.py:100 calls, returns NaN there; W^-1 is still well defined).
     """
     cfg = config or DEFAULT_WAVEGLOW_CONFIG
     n_mel, n_group = cfg["n_mel_channels"], cfg["n_group"]
@@ -104,6 +109,13 @@ def synthetic_state_dict(config: Optional[Dict] = None, seed: int = 1234, end_st
         q = torch.linalg.qr(torch.randn((c, c), generator=_gen(seed, f"convinv.{k}"), dtype=torch.float64))[0]
         if torch.det(q) < 0:
             q[:, 0] = -q[:, 0]
+        if mix == "skew":
+            scale = 0.5 + 1.5 * torch.rand((c,), generator=_gen(seed, f"convinv.{k}.scale"), dtype=torch.float64)
+            q = q * scale[None, :]
+            if k % 5 == 3:
+                q[:, 1] = -q[:, 1]
+        elif mix != "orthogonal":
+            raise ValueError(f"mix must be 'orthogonal' or 'skew', got {mix!r}")
         sd[f"convinv.{k}.conv.weight"] = q.float().reshape(c, c, 1)
     return sd
 

@@ -29,7 +29,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from .packing import gate_row_order, pack_upsample
+from .packing import bump_param_generation, gate_row_order, pack_upsample
 
 Tensor = torch.Tensor
 N_CH, N_COND, N_LAYERS = 512, 640, 8
@@ -457,6 +457,7 @@ class FusedAdam:
         if not gathered:
             self.gather_grads()
         self.step_count += 1
+        bump_param_generation()                 # the kernel rewrites the parameters behind torch's version counters
         with torch.cuda.device(self.flat.device):
             _lib.call("wgb_adam_step_dev", self.flat, self.grad, self.m, self.v, self.n, float(self.lr),
                       float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_dev, float(grad_scale),
@@ -524,4 +525,5 @@ class GraphedTrainStep:
         self.graph.replay()
         if self.include_optimizer:
             self.opt.step_count += 1
+            bump_param_generation()
         return self.loss
