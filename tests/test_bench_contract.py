@@ -20,6 +20,20 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "64 x" in d["config"]["workload"]
+    # the line says what it really ran: a bounded sample (one 80x100 mel per step), and it honours --steps / --warmup
+    assert "bounded sample" in d["config"]["workload"] and "1 x 80x100" in d["config"]["workload"]
+    assert d["config"]["sample_per_step"] == {"batch": 1, "frames": 100, "samples": 25600}
+    assert d["steps"] == 1 and d["warmup"] == 1 and d["steps_requested"] == 1
+
+
+def test_ncu_traffic_is_read_from_the_newest_profile():
+    sys.path.insert(0, ROOT)
+    import bench
+    traffic, src = bench.ncu_traffic("pair_kernel<3, 0, 0>", 64)
+    assert traffic and 2e9 < traffic < 8e9 and src.startswith("profiles/") and "_ncu_full_summary.csv" in src
+    half, _ = bench.ncu_traffic("pair_kernel<3, 0, 0>", 32)
+    assert abs(half - traffic / 2) < 1.0
+    assert bench.ncu_traffic("no_such_kernel", 64)[0] is None
 
 
 def test_reference_arm_non_zero_ranks_exit_silently():

@@ -250,23 +250,30 @@ class WaveGlow(torch.nn.Module):
             audio = engine.infer(pk, spect.float().contiguous(), z.to(spect.device).float().contiguous(), sigma)
         return audio.to(spect.dtype) if spect.dtype in (torch.float16, torch.bfloat16) else audio
 
-    def graphed_infer(self, batch: int, frames: int, sigma: float = 1.0):
+    def graphed_infer(self, batch: int, frames: int, sigma: float = 1.0, before_capture=None):
         """CUDA-graph replay of ``infer`` for a fixed shape (the ~210 kernel launches of one call become one graph
-        launch: worth ~7 % at batch 1, where launch gaps show).  Returns ``run(spect, z) -> audio``; spect / z are
-        copied into the graph's static buffers, the returned tensor is the graph's static output (clone it to keep it)."""
+        launch: worth ~7 % at batch 1 and a few % at batch 8, where launch gaps show).  Returns ``run(spect, z) ->
+        audio``; spect / z (device or pinned host tensors) are copied into the graph's static buffers, the returned
+        tensor is the graph's static output (clone it to keep it).  ``run.replay()`` replays on whatever the static
+        buffers hold.  ``before_capture`` (optional callable) runs after the eager warm-up, right before the capture
+        (bench.py arms its launch counter / event-record nodes there).  The captured graph holds the weights as packed
+        at capture time: re-create it after changing parameters."""
         device = self.upsample.weight.device
         pk = self._packed(device)
         t = frames * self.upsample.stride[0] // self.n_group
         spect_buf = torch.zeros((batch, self.upsample.in_channels, frames), device=device, dtype=torch.float32)
         z_buf = torch.zeros((batch, self.n_group, t), device=device, dtype=torch.float32)
-        side = torch.cuda.Stream(device=device)
-        side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side), torch.no_grad():
-            engine.infer(pk, spect_buf, z_buf, sigma)                 # warm-up outside the capture (allocator, func attrs)
-        torch.cuda.current_stream(device).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph), torch.no_grad():
-            out = engine.infer(pk, spect_buf, z_buf, sigma)
+        with torch.cuda.device(device):
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side), torch.no_grad():
+                engine.infer(pk, spect_buf, z_buf, sigma)             # warm-up outside the capture (allocator, func attrs)
+            torch.cuda.current_stream(device).wait_stream(side)
+            if before_capture is not None:
+                before_capture()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph), torch.no_grad():
+                out = engine.infer(pk, spect_buf, z_buf, sigma)
 
         def run(spect: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
             spect_buf.copy_(spect, non_blocking=True)
@@ -275,6 +282,8 @@ class WaveGlow(torch.nn.Module):
             return out
 
         run.graph = graph
+        run.replay = graph.replay
+        run.output = out
         return run
 
     @staticmethod
