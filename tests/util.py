@@ -28,6 +28,60 @@ MIN_SNR_DB = 30.0                 # north_star's statement; the regression gates
 # more than one bit of accuracy fails here long before the audio drops to 30 dB (the coupling is close to the identity
 # at end_std 0.01: zeroing whole sub-layers still clears 30 dB on the "bench" recipe).
 SNR_FLOORS = {
+    "cfg4_forward/log_s11": 35.0,
+    "cfg4_forward/z": 37.0,
+    "cfg5_denoiser": 93.0,
+    "first_layer_fold/False": 33.0,
+    "first_layer_fold/True": 33.0,
+    "first_layer_fold/agree": 32.0,
+    "forward_bf16/bench/z": 45.0,
+    "forward_bf16/bench/z_short": 45.0,
+    "forward_bf16/skew/z": 35.0,
+    "forward_bf16/skew/z_short": 38.0,
+    "forward_bf16_mel/z": 45.0,
+    "forward_bf16_mel/z_short": 45.0,
+    "full_utterance/bench": 54.0,
+    "infer_bf16/bench": 55.0,
+    "infer_bf16/skew": 49.0,
+    "infer_bf16/stress": 32.0,
+    "infer_bf16_mel/bench": 55.0,
+    "infer_bf16_mel/skew": 50.0,
+    "infer_bf16_mel/stress": 33.0,
+    "infer_bf16_mel_vs_cond/bench": 56.0,
+    "infer_bf16_mel_vs_cond/skew": 50.0,
+    "infer_bf16_mel_vs_cond/stress": 32.0,
+    "invertibility_full_utterance": 46.0,
+    "ragged/cond/1x1": 56.0,
+    "ragged/cond/2x33": 54.0,
+    "ragged/cond/5x2": 56.0,
+    "ragged/mel/1x1": 57.0,
+    "ragged/mel/2x33": 54.0,
+    "ragged/mel/5x2": 56.0,
+    "skip_paths/acc": 33.0,
+    "skip_paths/acc_vs_skip16": 33.0,
+    "skip_paths/pair": 33.0,
+    "skip_paths/res16": 33.0,
+    "skip_paths/res16_vs_skip16": 33.0,
+    "skip_paths/skip16": 33.0,
+    "skip_paths/skip16_vs_pair": 33.0,
+    "sweep/auto/1x129": 31.0,
+    "sweep/auto/1x7": 32.0,
+    "sweep/auto/2x64": 30.0,
+    "sweep/auto/3x13": 31.0,
+    "sweep/auto/4x128": 31.0,
+    "sweep/auto/5x31": 31.0,
+    "sweep/cond/1x129": 31.0,
+    "sweep/cond/1x7": 32.0,
+    "sweep/cond/2x64": 30.0,
+    "sweep/cond/3x13": 31.0,
+    "sweep/cond/4x128": 31.0,
+    "sweep/cond/5x31": 31.0,
+    "sweep/mel/1x129": 31.0,
+    "sweep/mel/1x7": 34.0,
+    "sweep/mel/2x64": 31.0,
+    "sweep/mel/3x13": 32.0,
+    "sweep/mel/4x128": 31.0,
+    "sweep/mel/5x31": 31.0,
 }
 
 
@@ -38,7 +92,9 @@ def assert_snr(key: str, x, ref) -> float:
     if log:
         with open(log, "a") as f:
             f.write(f"{key}\t{snr:.2f}\n")
-    floor = max(MIN_SNR_DB, SNR_FLOORS.get(key, MIN_SNR_DB))
+    if key not in SNR_FLOORS:
+        raise KeyError(f"no SNR floor for {key!r}: measure it (WGB_SNR_LOG) and add it to tests/util.py SNR_FLOORS")
+    floor = max(MIN_SNR_DB, SNR_FLOORS[key])
     assert snr >= floor, (key, snr, floor)
     return snr
 
