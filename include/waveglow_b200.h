@@ -199,6 +199,29 @@ WGB_API int wgb_tc_stft_denoise(const void* a_hi, const void* a_lo, const void* 
                                 float strength, void* hi_out, void* lo_out, int batch, int rows, int cutoff, int cp, int K,
                                 long long row_stride, long long batch_stride, void* stream);
 
+/* The same three STFT-family GEMMs on CTA pairs (tcgen05 cta_group::2, 5-6 stage ring, half the basis traffic per
+ * CTA) with an unpadded spectrum layout -- the defaults of TacotronSTFT.mel_spectrogram / Denoiser.forward when
+ * filter_length % 256 == 0 and hop % 8 == 0.  Im of bins 0 and L/2 is exactly zero in the reference's basis
+ * (stft.py:46-51), so the L/2 + 1 bins are L real numbers: w3_paired = split-bf16 forward basis [L][3L] whose pass p
+ * (256 rows) holds the Re rows of bins 128p..128p+127 followed by their Im rows, with the Re row of bin L/2 in the Im
+ * slot of bin 0 (L/256 passes instead of the five of the padded layout above).  a_hi / a_lo = reflect-padded signals
+ * as bf16 hi / lo parts [B, R*hop]: frame r of utterance b is flat row b*R + r of ONE frame axis over the batch.
+ *   wgb_tc2_stft_mel      layers.py:63-79 in one kernel; only the first n_pass passes run (the ones holding a bin with
+ *                         non-zero mel weight: 3 of 4 at 22.05 kHz / fmax 8 kHz); mel_table has L/2 + 1 entries
+ *                         (the last one = bin L/2); out fp32 [B, n_mel, frames].
+ *   wgb_tc2_stft_denoise  denoiser.py:36-38 + stft.py:102-103; hi_out / lo_out bf16 [B*frames][L]: columns 0..L/2-1
+ *                         Re of bins 0..L/2-1, column L/2 Re of bin L/2, columns L/2+1.. Im of bins 1..L/2-1 = the
+ *                         K operand of the inverse-basis GEMM (K = L instead of 2 * 640); bias_spec fp32 [L/2 + 1].
+ *   wgb_tc2_gemm_split3   C fp32 [rows][N] = (a_hi + a_lo)[rows][K] (W_hi + W_lo)^T, w3 = [W_hi | W_hi | W_lo] bf16
+ *                         [N][3K] (stft.py:105-109, the inverse-basis contraction); N % 256 == 0, K % 64 == 0. */
+WGB_API int wgb_tc2_stft_mel(const void* a_hi, const void* a_lo, const void* w3_paired, const void* mel_table, float* out,
+                             int batch, int frames, int R, int L, int hop, int n_pass, int n_mel, float clip, void* stream);
+WGB_API int wgb_tc2_stft_denoise(const void* a_hi, const void* a_lo, const void* w3_paired, const float* bias_spec,
+                                 float strength, void* hi_out, void* lo_out, int batch, int frames, int R, int L, int hop,
+                                 void* stream);
+WGB_API int wgb_tc2_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, float* c, long long rows, int N, int K,
+                                void* stream);
+
 /* ---------------------------------------------------------------- FP32 validation path (CUDA cores) */
 
 /* C[b][m][n] (+)= sum_k A[b][m+shift][k] W[n][k] + bias[n]; rows outside [0,M) read as zero, so a

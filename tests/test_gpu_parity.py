@@ -821,6 +821,58 @@ def check_phase(got, want, mag):
     assert np.all((edge < 1e-6) | (np.abs(edge - np.pi) < 1e-6))
 
 
+def test_tc2_gemm_split3_pair_kernel(lib):
+    """split-bf16 GEMM on CTA pairs (csrc/stft_tc2.cu, EPI_F32): ragged row count (a partial tile and an absent
+    second tile of the last pair), K = 3 x 192 and 3 x 1024, against fp64."""
+    g = torch.Generator().manual_seed(5)
+    for rows, N, K in ((300, 512, 192), (128 * 3 + 7, 1024, 1024)):
+        a = torch.randn(rows, K, generator=g)
+        w = torch.randn(N, K, generator=g) / 16
+        hi, w_hi = a.bfloat16(), w.bfloat16()
+        lo, w_lo = (a - hi.float()).bfloat16(), (w - w_hi.float()).bfloat16()
+        w3 = torch.cat([w_hi, w_hi, w_lo], 1).contiguous()
+        c = torch.full((rows, N), 7.0, device=DEV)
+        lib.call("wgb_tc2_gemm_split3", hi.to(DEV), lo.to(DEV), w3.to(DEV), c, rows, N, K, lib.stream_ptr())
+        torch.cuda.synchronize()
+        assert util.rel_l2(c.cpu(), a.double() @ w.double().t()) <= 2e-5, (rows, N, K)
+
+
+def test_stft_pair_kernels_against_one_cta_kernels_and_oracle(models, lib):
+    """The CTA-pair mel / denoiser kernels (unpadded spectrum layout, Nyquist bin in the Im slot of bin 0, flat frame
+    axis over the batch, only the passes with mel weight) against the one-CTA kernels with the padded layout and
+    against the CPU oracle -- ragged lengths, several utterances (frames that straddle two utterances are dropped)."""
+    import text2speech_b200 as t2s
+    m = models["bench"]
+    m.mode = "fp32"
+    den = t2s.Denoiser(m)
+    m.mode = "bf16"
+    fwd, inv = oracle.stft_bases(1024, 256, 1024)
+    for fmax in (8000.0, 11025.0):                          # 11025 = sr / 2: the Nyquist bin carries mel weight, 4 passes
+        taco = t2s.TacotronSTFT(1024, 256, 1024, 80, 22050, 0.0, fmax).to(DEV)
+        mb = torch.from_numpy(oracle.mel_filterbank(22050, 1024, 80, 0.0, fmax)).float()
+        for B, n in ((1, 1024), (3, 256 * 37 + 19), (5, 22050)):
+            y = syn.synthetic_waveforms(B, n, sr=22050, seed=B + n)
+            want = oracle.mel_spectrogram(y, fwd, mb, 256)
+            taco.stft_fn.pair = True
+            a = taco.mel_spectrogram(y.to(DEV))
+            taco.stft_fn.pair = False
+            b = taco.mel_spectrogram(y.to(DEV))
+            assert a.shape == b.shape == want.shape
+            assert float((a.cpu() - want).abs().max()) <= 1e-3, (fmax, B, n)
+            assert float((a - b).abs().max()) <= 2e-5, (fmax, B, n)
+    for B, n in ((1, 1024), (3, 256 * 37 + 19), (5, 22050)):
+        y = syn.synthetic_waveforms(B, n, sr=22050, seed=B + n)
+        for strength in (0.0, 0.1):
+            want = oracle.denoise(y, den.bias_spec.cpu(), strength, fwd, inv, 256, 1024)
+            den.stft.pair = True
+            a = den(y.to(DEV), strength)
+            den.stft.pair = False
+            b = den(y.to(DEV), strength)
+            den.stft.pair = True
+            assert a.shape == b.shape == want.shape
+            assert util.snr_db(a.cpu(), want) >= 80.0 and util.snr_db(a.cpu(), b.cpu()) >= 80.0, (B, n, strength)
+
+
 @pytest.mark.parametrize("precision", ["tc", "fp32"])
 def test_stft_transform_inverse(golden, lib, precision):
     import text2speech_b200 as t2s

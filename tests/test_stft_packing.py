@@ -1,0 +1,101 @@
+"""Host-side packing of the CTA-pair STFT kernels (csrc/stft_tc2.cu), emulated on the CPU from the PACKED operands:
+the unpadded spectrum layout (Re row of bin L/2 in the Im slot of bin 0), the matching inverse-basis K order and the
+mel table / pass count must reproduce the oracle's STFT, mel spectrogram and denoiser."""
+import numpy as np
+import torch
+
+import oracle
+from tests import util
+from text2speech_b200 import synthetic as syn
+from text2speech_b200.layers import TacotronSTFT
+from text2speech_b200.stft import STFT
+
+DC = syn.DEFAULT_DATA_CONFIG
+CPU = torch.device("cpu")
+
+
+def _unsplit(w3):
+    k = w3.shape[1] // 3
+    assert torch.equal(w3[:, :k], w3[:, k:2 * k])
+    return w3[:, :k].double() + w3[:, 2 * k:].double()
+
+
+def _frames(y, length, hop):
+    padded = torch.nn.functional.pad(y[:, None], (length // 2, length // 2), mode="reflect")[:, 0]
+    return padded.unfold(1, length, hop).double()                         # [B, F, L]
+
+
+def _spectrum_from_paired(s, length):
+    """paired GEMM output [.., L] -> (re [.., L/2+1], im [.., L/2+1]) as the kernels' epilogues read it."""
+    half = length // 2
+    re = torch.zeros(s.shape[:-1] + (half + 1,), dtype=s.dtype)
+    im = torch.zeros_like(re)
+    for p in range(length // 256):
+        re[..., 128 * p: 128 * (p + 1)] = s[..., 256 * p: 256 * p + 128]
+        im[..., 128 * p: 128 * (p + 1)] = s[..., 256 * p + 128: 256 * (p + 1)]
+    re[..., half] = im[..., 0]                                            # Nyquist rides in the Im slot of bin 0
+    im[..., 0] = 0.0
+    return re, im
+
+
+def test_pair_layout_reproduces_transform_mel_and_denoiser(golden):
+    length, hop = DC["filter_length"], DC["hop_length"]
+    stft = STFT(length, hop, DC["win_length"])
+    fwd3, inv3 = stft._pair_pack(CPU)
+    assert fwd3.shape == (length, 3 * length) and inv3.shape == (length, 3 * length) and fwd3.dtype == torch.bfloat16
+    y = syn.synthetic_waveforms(2, 4096, sr=DC["sampling_rate"], seed=5)
+    fr = _frames(y, length, hop)
+    re, im = _spectrum_from_paired(fr @ _unsplit(fwd3).t(), length)
+    mag = torch.sqrt(re * re + im * im).permute(0, 2, 1)
+    assert util.rel_l2(mag, golden["stft_mag"]) < 5e-6          # hi + lo of the bf16 split keep ~16 bits of the basis
+
+    # mel: table of L/2 + 1 entries, only the first n_pass passes of 128 bins are computed
+    taco = TacotronSTFT(length, hop, DC["win_length"], 80, DC["sampling_rate"], DC["mel_fmin"], DC["mel_fmax"])
+    table, n_pass = taco._mel_table_pair(CPU)
+    assert table.shape == (length // 2 + 1, 4) and n_pass == 3            # bins above 371 carry no weight at 8 kHz / 22.05 kHz
+    mag_used = mag.permute(0, 2, 1).clone()
+    mag_used[..., 128 * n_pass: length // 2] = 0.0                        # passes the kernel never runs (Nyquist is in pass 0)
+    acc = torch.zeros(mag_used.shape[:2] + (82,), dtype=torch.float64)
+    for k in range(length // 2 + 1):
+        m0 = int(table[k, 0])
+        acc[..., m0] += float(table[k, 1]) * mag_used[..., k]
+        acc[..., m0 + 1] += float(table[k, 2]) * mag_used[..., k]
+    mel = torch.log(torch.clamp(acc[..., :80], min=1e-5)).permute(0, 2, 1)
+    assert float((mel - torch.from_numpy(golden["mel"]).double()).abs().max()) < 1e-4
+
+    # denoiser: epilogue columns [Re 0..L/2-1 | Re L/2 | Im 1..L/2-1] against the packed inverse basis
+    bias = torch.from_numpy(golden["denoiser_bias_spec"]).double().reshape(-1)
+    for strength, key in ((0.1, "denoised_s0p1"), (0.01, "denoised_s0p01")):
+        m = torch.sqrt(re * re + im * im)
+        m2 = torch.clamp(m - bias * strength, min=0.0)
+        g = torch.where(m > 0, m2 / m.clamp_min(1e-300), torch.zeros_like(m))
+        re2 = torch.where(m > 0, re * g, m2)
+        im2 = im * g
+        half = length // 2
+        cols = torch.cat([re2[..., :half], re2[..., half:half + 1], im2[..., 1:half]], dim=-1)
+        assert cols.shape[-1] == length
+        out_fr = cols @ _unsplit(inv3).t()                                # [B, F, L]
+        frames = out_fr.shape[1]
+        total = hop * (frames - 1) + length
+        out = torch.zeros(out_fr.shape[0], total, dtype=torch.float64)
+        for f in range(frames):
+            out[:, f * hop: f * hop + length] += out_fr[:, f]
+        env = torch.from_numpy(oracle.window_sumsquare("hann", frames, hop, DC["win_length"], length)).double()
+        nz = env > np.finfo(np.float32).tiny
+        out[:, nz] = out[:, nz] / env[nz]
+        out = out * (length / hop)
+        out = out[:, length // 2: total - length // 2]
+        assert util.rel_l2(out[:, None], golden[key]) < 1e-5
+
+
+def test_pair_layout_nyquist_weight_is_honoured():
+    """A filterbank that reaches the Nyquist bin (fmax = sr / 2): its weight sits in the table's last entry, which the
+    kernel applies to the value in the Im slot of bin 0, and all four passes run."""
+    taco = TacotronSTFT(1024, 256, 1024, 80, 22050, 0.0, 11025.0)
+    table, n_pass = taco._mel_table_pair(CPU)
+    basis = taco.mel_basis
+    assert n_pass == 4
+    for k in (0, 1, 371, 511, 512):
+        m0 = int(table[k, 0])
+        assert float(table[k, 1]) == float(basis[m0, k])
+        assert float(table[k, 2]) == (float(basis[m0 + 1, k]) if m0 + 1 < 80 else 0.0)

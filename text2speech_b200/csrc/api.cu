@@ -15,6 +15,9 @@ int tc_gemm_split3(const void*, const void*, const void*, const float*, void*, i
                    cudaStream_t);
 int tc_conv1d_taps(const void*, const void*, const float*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
 int tc_stft_mag(const void*, const void*, const void*, void*, int, int, int, int, long long, long long, cudaStream_t);
+int tc2_stft_mel(const void*, const void*, const void*, const void*, float*, int, int, int, int, int, int, int, float, cudaStream_t);
+int tc2_stft_denoise(const void*, const void*, const void*, const float*, float, void*, void*, int, int, int, int, int, cudaStream_t);
+int tc2_gemm_split3(const void*, const void*, const void*, float*, long long, int, int, cudaStream_t);
 int tc_stft_mel(const void*, const void*, const void*, const void*, void*, int, int, int, int, long long, long long, int, float,
                 cudaStream_t);
 int tc_stft_denoise(const void*, const void*, const void*, const float*, float, void*, void*, int, int, int, int, int,
@@ -217,6 +220,20 @@ WGB_API int wgb_tc_stft_denoise(const void* a_hi, const void* a_lo, const void* 
                                 long long row_stride, long long batch_stride, void* stream) {
     return tc_stft_denoise(a_hi, a_lo, w3_paired, bias_spec, strength, hi_out, lo_out, batch, rows, cutoff, cp, K,
                            row_stride, batch_stride, S(stream));
+}
+
+WGB_API int wgb_tc2_stft_mel(const void* a_hi, const void* a_lo, const void* w3_paired, const void* mel_table, float* out,
+                             int batch, int frames, int R, int L, int hop, int n_pass, int n_mel, float clip, void* stream) {
+    return tc2_stft_mel(a_hi, a_lo, w3_paired, mel_table, out, batch, frames, R, L, hop, n_pass, n_mel, clip, S(stream));
+}
+WGB_API int wgb_tc2_stft_denoise(const void* a_hi, const void* a_lo, const void* w3_paired, const float* bias_spec,
+                                 float strength, void* hi_out, void* lo_out, int batch, int frames, int R, int L, int hop,
+                                 void* stream) {
+    return tc2_stft_denoise(a_hi, a_lo, w3_paired, bias_spec, strength, hi_out, lo_out, batch, frames, R, L, hop, S(stream));
+}
+WGB_API int wgb_tc2_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, float* c, long long rows, int N, int K,
+                                void* stream) {
+    return tc2_gemm_split3(a_hi, a_lo, w3, c, rows, N, K, S(stream));
 }
 
 WGB_API int wgb_sgemm_f32(const float* A, const float* W, const float* bias, void* C, int out_bf16, int batch, int M, int N,

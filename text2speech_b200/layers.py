@@ -64,8 +64,21 @@ class TacotronSTFT(torch.nn.Module):
                 tab[k, 0], tab[k, 1] = float(m0), basis[m0, k]
                 if nz.numel() == 2:
                     tab[k, 2] = basis[m0 + 1, k]
-            self._mel_tab = (key, tab.to(device) if ok else None)
+            # passes (of 128 bins) of the CTA-pair kernel that hold a bin with non-zero weight; its layout has exactly
+            # L/2 + 1 entries and the last bin (L/2) rides in pass 0
+            nz = torch.nonzero(tab[: max(cp - 1, 1), 1:3].abs().sum(1)).flatten()
+            n_pass = max(1, -(-(int(nz.max()) + 1) // 128)) if nz.numel() else 1
+            self._mel_tab = (key, tab.to(device) if ok else None, n_pass)
         return self._mel_tab[1]
+
+    def _mel_table_pair(self, device):
+        """(table [L/2 + 1] float4, n_pass) for wgb_tc2_stft_mel, or None (basis without the two-adjacent-filters
+        structure, more than 80 filters, or a filter length the kernel's shared-memory table cannot hold)."""
+        cutoff = self.stft_fn.cutoff
+        if cutoff - 1 > 512:
+            return None
+        tab = self._mel_table(device, cutoff)
+        return None if tab is None else (tab, self._mel_tab[2])
 
     def mel_spectrogram(self, y: torch.Tensor) -> torch.Tensor:
         """y [B, T] in [-1, 1] (CUDA) -> log-mel [B, n_mel_channels, T // hop + 1]."""
@@ -82,7 +95,11 @@ class TacotronSTFT(torch.nn.Module):
         s = _lib.stream_ptr()
         if self.stft_fn._use_tc():
             cp = self.stft_fn._packed(y.device)[3]
-            table = self._mel_table(y.device, cp) if self.fused else None
+            table = None
+            if self.fused:
+                table = self._mel_table_pair(y.device) if self.stft_fn._use_pair() else None
+                if table is None:
+                    table = self._mel_table(y.device, cp)
             if table is not None:             # STFT GEMM with |X|, the mel filterbank and log-clamp in its epilogue
                 return self.stft_fn._mel_fused(y, table, self.n_mel_channels, 1e-5)
             mag_cl, frames, cp = self.stft_fn._magnitude_cl(y)   # |X| straight from the STFT GEMM's epilogue

@@ -60,6 +60,9 @@ class STFT(torch.nn.Module):
         # 'tc': split-bf16 tcgen05 GEMMs (fp32-grade accuracy, needs filter_length % 256 == 0 and hop % 8 == 0);
         # 'fp32': CUDA-core FP32 GEMM (any shape).  'auto' picks 'tc' when the shape allows.
         self.precision = "auto"
+        # fused mel / denoiser paths: CTA-pair kernels with the unpadded spectrum layout (csrc/stft_tc2.cu) when True,
+        # the one-CTA kernels with the 640-bin padded layout (csrc/wn_tc.cu) when False (kept for A/B)
+        self.pair = True
 
     # ------------------------------------------------------------------ packed constants
     @property
@@ -98,12 +101,37 @@ class STFT(torch.nn.Module):
                 sq = torch.from_numpy(padded_window(self.window, self.win_length, length) ** 2).double().to(device)
             else:
                 sq = None          # window=None: no envelope division and no L/hop scale (stft.py:111-125)
-            self._pack = (key, fwd.to(device), inv.to(device), sq, cp, fwd_paired)
+            pair_pack = None
+            if tc:
+                # CTA-pair kernels: no padded bins.  Im of bins 0 and L/2 is exactly zero (stft.py:46-51), so the Re row of
+                # bin L/2 rides in the Im slot of bin 0: pass p = Re rows of bins 128p..128p+127, then their Im rows
+                half = length // 2
+                re, im = fb[:cutoff], fb[cutoff:]
+                paired = torch.empty(length, length, dtype=torch.float32)
+                for p in range(length // 256):
+                    paired[256 * p: 256 * p + 128] = re[128 * p: 128 * (p + 1)]
+                    paired[256 * p + 128: 256 * (p + 1)] = im[128 * p: 128 * (p + 1)]
+                paired[128] = re[half]
+                # inverse basis with the matching K order: [Re 0..L/2-1 | Re L/2 | Im 1..L/2-1]
+                inv2 = torch.empty(length, length, dtype=torch.float32)
+                inv2[:, :half] = ib[:half].t()
+                inv2[:, half] = ib[half]
+                inv2[:, half + 1:] = ib[cutoff + 1: cutoff + half].t()
+                pair_pack = (_split3(paired).to(device), _split3(inv2).to(device))
+            self._pack = (key, fwd.to(device), inv.to(device), sq, cp, fwd_paired, pair_pack)
         return self._pack[1:5]
 
     def _paired_basis(self, device):
         self._packed(device)
         return self._pack[5]
+
+    def _pair_pack(self, device):
+        """(forward basis, inverse basis) in the unpadded layout of the CTA-pair kernels, split-bf16 [L][3L] each."""
+        self._packed(device)
+        return self._pack[6]
+
+    def _use_pair(self) -> bool:
+        return self.pair and self._use_tc()
 
     # ------------------------------------------------------------------ device pipeline pieces
     def _spectrum(self, y: torch.Tensor):
@@ -129,10 +157,12 @@ class STFT(torch.nn.Module):
                   hop, ld_pad, length, 2 * cp, frames * 2 * cp, 0, 0, s)
         return spec, frames, cp
 
-    def _padded_split(self, y: torch.Tensor):
-        """reflect-padded signal as bf16 hi / lo parts [B, ld_pad] (operands of the tensor-core STFT GEMMs)."""
+    def _padded_split(self, y: torch.Tensor, whole_hops: bool = False):
+        """reflect-padded signal as bf16 hi / lo parts [B, ld_pad] (operands of the tensor-core STFT GEMMs).
+        whole_hops: pitch = a whole number of hops, so that the frames of the whole batch form ONE row axis (frame r of
+        utterance b = flat row b * ld_pad / hop + r) for the CTA-pair kernels."""
         b, n = y.shape
-        ld_pad = _round_up(n + self.filter_length, 8)
+        ld_pad = _round_up(n + self.filter_length, self.hop_length if whole_hops else 8)
         hi = torch.empty((b, ld_pad), device=y.device, dtype=torch.bfloat16)
         lo = torch.empty_like(hi)
         _lib.call("wgb_stft_reflect_pad_split", y, hi, lo, b, n, self.filter_length // 2, ld_pad, _lib.stream_ptr())
@@ -156,8 +186,14 @@ class STFT(torch.nn.Module):
         _, _, _, cp = self._packed(y.device)
         b, n = y.shape
         frames = n // self.hop_length + 1
-        hi, lo, ld_pad = self._padded_split(y)
         out = torch.empty((b, n_mel, frames), device=y.device, dtype=torch.float32)
+        if isinstance(mel_table, tuple):          # (table [L/2 + 1], n_pass): CTA-pair kernel, unpadded layout
+            hi, lo, ld_pad = self._padded_split(y, whole_hops=True)
+            _lib.call("wgb_tc2_stft_mel", hi, lo, self._pair_pack(y.device)[0], mel_table[0], out, b, frames,
+                      ld_pad // self.hop_length, self.filter_length, self.hop_length, mel_table[1], n_mel, float(clip),
+                      _lib.stream_ptr())
+            return out
+        hi, lo, ld_pad = self._padded_split(y)
         _lib.call("wgb_tc_stft_mel", hi, lo, self._paired_basis(y.device), mel_table, out, b, frames, cp,
                   self.filter_length, self.hop_length, ld_pad, n_mel, float(clip), _lib.stream_ptr())
         return out
@@ -171,6 +207,18 @@ class STFT(torch.nn.Module):
         length, hop = self.filter_length, self.hop_length
         frames = n // hop + 1
         s = _lib.stream_ptr()
+        if self._use_pair():                      # CTA-pair kernels, unpadded layout: K of the inverse GEMM = L
+            hi, lo, ld_pad = self._padded_split(y, whole_hops=True)
+            fwd2, inv2 = self._pair_pack(y.device)
+            shi = torch.empty((b * frames, length), device=y.device, dtype=torch.bfloat16)
+            slo = torch.empty_like(shi)
+            _lib.call("wgb_tc2_stft_denoise", hi, lo, fwd2, bias_spec, float(strength), shi, slo, b, frames, ld_pad // hop,
+                      length, hop, s)
+            fr = torch.empty((b, frames, length), device=y.device, dtype=torch.float32)
+            _lib.call("wgb_tc2_gemm_split3", shi, slo, inv2, fr, b * frames, length, length, s)
+            out = torch.empty((b, 1, hop * (frames - 1)), device=y.device, dtype=torch.float32)
+            _lib.call("wgb_istft_overlap_add", fr, win_sq, out, b, frames, length, hop, s)
+            return out
         hi, lo, ld_pad = self._padded_split(y)
         shi = torch.empty((b * frames, 2 * cp), device=y.device, dtype=torch.bfloat16)
         slo = torch.empty_like(shi)

@@ -1,0 +1,71 @@
+"""A/B of the STFT kernels at BASELINE configs[4] size (256 x 10 s waveforms): CTA-pair kernels with the unpadded
+layout (csrc/stft_tc2.cu, default) vs the one-CTA kernels with the 640-bin padded layout (csrc/wn_tc.cu).
+
+    python tools/bench_stft_ab.py [--out gpurun_out/stft_ab.json] [--once pair|single]   (--once: one call each, for ncu)
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import text2speech_b200 as t2s                     # noqa: E402
+from text2speech_b200 import synthetic as syn      # noqa: E402
+from tools.bench_configs import breakdown, timeit  # noqa: E402
+
+DEV = torch.device("cuda:0")
+STFT_FLOP = 2 * 1026 * 1024
+MEL_FLOP = 2 * 80 * 513
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "stft_ab.json"))
+    ap.add_argument("--once", default="")
+    args = ap.parse_args()
+    cfg = syn.load_config()
+    model = t2s.WaveGlow.remove_weightnorm(t2s.WaveGlow(**cfg))
+    model.load_state_dict(syn.synthetic_state_dict(cfg, seed=1234, end_std=0.01))
+    model = model.to(DEV).eval()
+    taco = t2s.TacotronSTFT(1024, 256, 1024, 80, 22050, 0.0, 8000.0).to(DEV)
+    den = t2s.Denoiser(model)
+    y = syn.synthetic_waveforms(256, 220160, sr=22050, seed=5).to(DEV)
+    frames = 256 * 861
+    if args.once:
+        taco.stft_fn.pair = den.stft.pair = args.once == "pair"
+        for _ in range(2):
+            taco._mel_spectrogram(y)
+            den(y, 0.01)
+        torch.cuda.synchronize()
+        return
+    out = {}
+    for pair in (True, False):
+        taco.stft_fn.pair = den.stft.pair = pair
+        rec = {}
+        med, best = timeit(lambda: taco._mel_spectrogram(y), warmup=3, iters=10)
+        rec["mel_ms"] = med
+        rec["mel_algorithmic_tflops"] = frames * (STFT_FLOP + MEL_FLOP) / (med * 1e-3) / 1e12
+        rec["mel_breakdown"] = breakdown(lambda: taco._mel_spectrogram(y))
+        med, best = timeit(lambda: den(y, 0.01), warmup=3, iters=10)
+        rec["denoiser_ms"] = med
+        rec["denoiser_algorithmic_tflops"] = frames * 2 * STFT_FLOP / (med * 1e-3) / 1e12
+        rec["denoiser_breakdown"] = breakdown(lambda: den(y, 0.01))
+        out["pair" if pair else "one_cta"] = rec
+    taco.stft_fn.pair = den.stft.pair = True
+    a = taco._mel_spectrogram(y)
+    d = den(y, 0.01)
+    taco.stft_fn.pair = den.stft.pair = False
+    out["max_abs_mel_diff"] = float((a - taco._mel_spectrogram(y)).abs().max())
+    d2 = den(y, 0.01)
+    out["denoiser_snr_pair_vs_one_cta_db"] = float(10 * torch.log10(d2.double().pow(2).sum() / (d - d2).double().pow(2).sum()))
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as f:
+        json.dump(out, f, indent=1)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
