@@ -847,9 +847,12 @@ def test_stft_pair_kernels_against_one_cta_kernels_and_oracle(models, lib):
     den = t2s.Denoiser(m)
     m.mode = "bf16"
     fwd, inv = oracle.stft_bases(1024, 256, 1024)
-    for fmax in (8000.0, 11025.0):                          # 11025 = sr / 2: the Nyquist bin carries mel weight, 4 passes
-        taco = t2s.TacotronSTFT(1024, 256, 1024, 80, 22050, 0.0, fmax).to(DEV)
-        mb = torch.from_numpy(oracle.mel_filterbank(22050, 1024, 80, 0.0, fmax)).float()
+    # 11025 = sr / 2: the Nyquist bin carries mel weight, 4 passes; 44800 (the class default, layers.py:44): filters
+    # narrower than a bin at the low end, so the table's filter index steps by two
+    for sr, fmax in ((22050, 8000.0), (22050, 11025.0), (44800, 8000.0)):
+        taco = t2s.TacotronSTFT(1024, 256, 1024, 80, sr, 0.0, fmax).to(DEV)
+        assert taco._mel_table_pair(torch.device(DEV)) is not None
+        mb = torch.from_numpy(oracle.mel_filterbank(sr, 1024, 80, 0.0, fmax)).float()
         for B, n in ((1, 1024), (3, 256 * 37 + 19), (5, 22050)):
             y = syn.synthetic_waveforms(B, n, sr=22050, seed=B + n)
             want = oracle.mel_spectrogram(y, fwd, mb, 256)
@@ -858,8 +861,8 @@ def test_stft_pair_kernels_against_one_cta_kernels_and_oracle(models, lib):
             taco.stft_fn.pair = False
             b = taco.mel_spectrogram(y.to(DEV))
             assert a.shape == b.shape == want.shape
-            assert float((a.cpu() - want).abs().max()) <= 1e-3, (fmax, B, n)
-            assert float((a - b).abs().max()) <= 2e-5, (fmax, B, n)
+            assert float((a.cpu() - want).abs().max()) <= 1e-3, (sr, fmax, B, n)
+            assert float((a - b).abs().max()) <= 2e-5, (sr, fmax, B, n)
     for B, n in ((1, 1024), (3, 256 * 37 + 19), (5, 22050)):
         y = syn.synthetic_waveforms(B, n, sr=22050, seed=B + n)
         for strength in (0.0, 0.1):

@@ -99,3 +99,50 @@ def test_pair_layout_nyquist_weight_is_honoured():
         m0 = int(table[k, 0])
         assert float(table[k, 1]) == float(basis[m0, k])
         assert float(table[k, 2]) == (float(basis[m0 + 1, k]) if m0 + 1 < 80 else 0.0)
+
+
+def _stream_mel(table, mag, n_pass, n_mel=80, clip=1e-5):
+    """The kernel's streaming form of the filterbank (csrc/stft_tc2.cu EPI_MEL) for one row of magnitudes [L/2 + 1]:
+    two running sums, a filter is emitted when the table's first-filter index moves past it, the Nyquist bin joins last."""
+    cp = table.shape[0] - 1
+    out = np.full(n_mel, np.nan)
+    cur, a0, a1 = 0, 0.0, 0.0
+    for k in range(128 * n_pass):
+        m0 = int(table[k, 0]) if (table[k, 1] != 0 or table[k, 2] != 0) else -1
+        if m0 > cur:
+            out[cur] = np.log(max(a0, clip))
+            if m0 == cur + 1:
+                a0 = a1
+            else:
+                out[cur + 1] = np.log(max(a1, clip))
+                out[cur + 2: m0] = np.log(clip)
+                a0 = 0.0
+            a1, cur = 0.0, m0
+        a0 += float(table[k, 1]) * mag[k]
+        a1 += float(table[k, 2]) * mag[k]
+    mn = int(table[cp, 0]) if (table[cp, 1] != 0 or table[cp, 2] != 0) else -1
+    for m in range(cur, n_mel):
+        v = a0 if m == cur else (a1 if m == cur + 1 else 0.0)
+        if m == mn:
+            v += float(table[cp, 1]) * mag[cp]
+        if m == mn + 1 and mn >= 0:
+            v += float(table[cp, 2]) * mag[cp]
+        out[m] = np.log(max(v, clip))
+    return out
+
+
+def test_streaming_filterbank_equals_dense_matmul():
+    g = np.random.default_rng(0)
+    for fmax, sr in ((8000.0, 22050), (11025.0, 22050), (7600.0, 16000), (8000.0, 44800)):
+        taco = TacotronSTFT(1024, 256, 1024, 80, sr, 0.0, fmax)
+        pair = taco._mel_table_pair(CPU)
+        assert pair is not None, (fmax, sr)
+        table, n_pass = pair
+        mag = np.abs(g.standard_normal(513)) + 0.01
+        want = np.log(np.maximum(taco.mel_basis.double().numpy() @ mag, 1e-5))
+        got = _stream_mel(table.double().numpy(), mag, n_pass)
+        assert not np.isnan(got).any() and np.abs(got - want).max() < 1e-6, (fmax, sr)
+    # a hand-edited basis without the structure is refused (the one-CTA kernel takes it)
+    taco = TacotronSTFT(1024, 256, 1024, 80, 22050, 0.0, 8000.0)
+    taco.mel_basis[5, 300] = 0.1
+    assert taco._mel_table_pair(CPU) is None

@@ -21,7 +21,9 @@
 //     number of 128-row tiles (4 %).
 //
 //   EPI_F32      C fp32 [rows, N]                                  (inverse-basis GEMM; generic split-bf16 GEMM)
-//   EPI_MEL      |X| -> sparse mel filterbank -> log(clamp)        (all of TacotronSTFT.mel_spectrogram, layers.py:63-79)
+//   EPI_MEL      |X| -> sparse mel filterbank -> log(clamp)        (all of TacotronSTFT.mel_spectrogram, layers.py:63-79);
+//                a bin feeds two adjacent triangular filters and the filter index never decreases, so each row keeps
+//                two running sums in registers and emits a filter the moment the table moves past it
 //   EPI_DENOISE  max(|X| - bias*strength, 0) e^{j arg X} as the bf16 hi/lo operands of the inverse GEMM
 //                                                                   (denoiser.py:36-38 + stft.py:102-103)
 #include "common.cuh"
@@ -41,16 +43,16 @@ constexpr int kBBytes = kHalfN * kBlockK * 2;       // 16 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 192;
-constexpr int kMelMax = 80;           // mel channels kept per row (+1 pad column: a bin feeds filters m0 and m0 + 1)
-constexpr int kMaxBins = 512;         // EPI_MEL: L/2 <= 512 (table of L/2 + 1 entries in shared memory)
+constexpr int kMaxBins = 512;         // EPI_MEL / EPI_DENOISE: L/2 <= 512 (per-bin table of L/2 + 1 entries in shared memory)
 
 enum Epi { EPI_F32 = 0, EPI_MEL = 1, EPI_DENOISE = 2 };
 
 template <int EPI>
 struct Smem {
-    static constexpr int kStages = EPI == EPI_MEL ? 5 : 6;
+    static constexpr int kStages = 6;
     static constexpr int kExtraOff = kStages * kStageBytes;
-    static constexpr int kExtraBytes = EPI == EPI_MEL ? kBlockM * (kMelMax + 1) * 4 + (kMaxBins + 1) * 16 : 0;
+    // MEL: the sparse filterbank table, one float4 per bin; DENOISE: bias * strength per bin
+    static constexpr int kExtraBytes = EPI == EPI_MEL ? (kMaxBins + 1) * 16 : (EPI == EPI_DENOISE ? (kMaxBins + 1) * 4 : 0);
     static constexpr int kBarOff = kExtraOff + ((kExtraBytes + 15) & ~15);
     static constexpr int kTotal = 1024 + kBarOff + 256;
 };
@@ -69,19 +71,32 @@ struct Params {
     __nv_bfloat16* lo_out;
     const float* spec_bias;       // EPI_DENOISE [cp + 1]
     float strength;
-    const float4* mel_table;      // EPI_MEL [cp + 1]: {first filter index (as float), weight in it, weight in the next, 0}
+    const float4* mel_table;      // EPI_MEL [cp + 1]: {first filter index (as float), weight in it, weight in the next, 0};
+                                  // over the bins with weight the index never decreases
     int n_mel;
     float mel_clip;
 };
 
 // Denoiser.forward on one bin (denoiser.py:36-38, stft.py:102-103): (re, im) -> max(|X| - bias*strength, 0) e^{j arg X}
-// without atan2 / cos / sin; |X| = 0 keeps the reference's atan2(0, 0) = 0 (cos 1, sin 0).
+// without atan2 / cos / sin: both parts are scaled by g = max(|X| - bs, 0) / |X| = max(1 - bs / |X|, 0), with 1 / |X| from
+// one rsqrt.approx (relative error 2^-22: the error of g is 2^-22 absolute, i.e. 2^-22 |X| on the output).  |X| = 0
+// (or a denormal |X|^2, flushed) keeps the reference's atan2(0, 0) = 0: Re = max(-bs, 0), Im = 0.
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void denoise_bin(float& re, float& im, float bias_s) {
-    const float mag = sqrtf(re * re + im * im);
-    const float m2 = fmaxf(mag - bias_s, 0.f);
-    const float g = mag > 0.f ? m2 / mag : 0.f;
-    re = mag > 0.f ? re * g : m2;
-    im = im * g;
+    const float m2 = fmaf(re, re, im * im);
+    const float g = fmaxf(fmaf(-bias_s, rsqrt_approx(m2), 1.f), 0.f);
+    const bool zero = !(m2 >= 1.17549435e-38f);
+    re = zero ? fmaxf(-bias_s, 0.f) : re * g;
+    im = zero ? 0.f : im * g;
 }
 
 template <int EPI>
@@ -119,9 +134,17 @@ stft_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_2sm(tmem_slot, kTmemCols);
-    if (EPI == EPI_MEL && warp >= 2) {
-        float4* tab = reinterpret_cast<float4*>(s_extra + kBlockM * (kMelMax + 1) * 4);
-        for (int i = threadIdx.x - 64; i <= p.cp; i += 128) tab[i] = p.mel_table[i];
+    if (EPI == EPI_MEL && warp >= 2) {          // table in shared memory; first filter index as int bits, -1 = no weight
+        float4* tab = reinterpret_cast<float4*>(s_extra);
+        for (int i = threadIdx.x - 64; i <= p.cp; i += 128) {
+            float4 e = p.mel_table[i];
+            e.x = __int_as_float((e.y != 0.f || e.z != 0.f) ? static_cast<int>(e.x) : -1);
+            tab[i] = e;
+        }
+    }
+    if (EPI == EPI_DENOISE && warp >= 2) {
+        float* bs = reinterpret_cast<float*>(s_extra);
+        for (int i = threadIdx.x - 64; i <= p.cp; i += 128) bs[i] = p.spec_bias[i] * p.strength;
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -202,16 +225,17 @@ stft_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             const bool live = tile < p.n_tiles && flat < p.rows_total && r < p.frames;
             const size_t grow = static_cast<size_t>(b) * p.frames + r;          // compact output row
 
+            // EPI_MEL: a bin feeds the filters m0 and m0 + 1, and m0 never decreases as the bins ascend, so a row needs
+            // two running sums: a0 (filter `cur`) and a1 (filter `cur + 1`).  When the table moves on to the next filter,
+            // filter `cur` is complete and leaves as log(max(., clip)); the state lives in registers across the passes.
+            int cur = 0;
+            float a0 = 0.f, a1 = 0.f, nyq = 0.f;
+            float* mel_out = nullptr;
+            if constexpr (EPI == EPI_MEL) mel_out = p.c_out + (static_cast<size_t>(b) * p.n_mel) * p.frames + r;
+
             for (int pp = 0; pp < p.ppi; ++pp, ++acc_it) {
                 const int pass = (item % groups) * p.ppi + pp;
                 const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-                float* acc = nullptr;
-                if constexpr (EPI == EPI_MEL) {
-                    acc = reinterpret_cast<float*>(s_extra) + row * (kMelMax + 1);      // stride 81: conflict-free
-                    if (pp == 0) {
-                        for (int m = 0; m <= kMelMax; ++m) acc[m] = 0.f;
-                    }
-                }
                 mbar_wait(&tfull_bar[as], aph, 400 + as);
                 tc_fence_after_sync();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBlockN;
@@ -232,10 +256,8 @@ stft_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                         }
                     }
                 } else if constexpr (EPI == EPI_MEL) {
-                    // columns 0..127 = Re of bins 128 pass .. +127, columns 128..255 = the matching Im (bin 0: Re of bin cp).
-                    // |X| per bin is scattered into this row's <= 80 mel accumulators in shared memory (a bin feeds at
-                    // most two adjacent triangular filters); log(max(., clip)) after the last pass.
-                    const float4* tab = reinterpret_cast<const float4*>(s_extra + kBlockM * (kMelMax + 1) * 4);
+                    // columns 0..127 = Re of bins 128 pass .. +127, columns 128..255 = the matching Im (bin 0: Re of bin cp)
+                    const float4* tab = reinterpret_cast<const float4*>(s_extra);
 #pragma unroll 1
                     for (int ch = 0; ch < 4; ++ch) {
                         uint32_t vr[32], vi[32];
@@ -246,29 +268,45 @@ stft_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float re = __uint_as_float(vr[j]), im = __uint_as_float(vi[j]);
-                            float mag;
-                            if (k0 + j == 0) {                                   // two real bins: DC here, Nyquist below
+                            float mag = sqrt_approx(fmaf(re, re, im * im));      // MUFU.SQRT, 2^-23 relative
+                            if (k0 + j == 0) {                                   // two real bins: DC here, Nyquist at the end
                                 mag = fabsf(re);
-                                const float4 en = tab[p.cp];
-                                const int mn = static_cast<int>(en.x);
-                                const float nyq = fabsf(im);
-                                acc[mn] = fmaf(en.y, nyq, acc[mn]);
-                                acc[mn + 1] = fmaf(en.z, nyq, acc[mn + 1]);
-                            } else {
-                                mag = sqrtf(re * re + im * im);
+                                nyq = fabsf(im);
                             }
                             const float4 e = tab[k0 + j];                        // warp-uniform: broadcast
-                            const int m0 = static_cast<int>(e.x);
-                            acc[m0] = fmaf(e.y, mag, acc[m0]);
-                            acc[m0 + 1] = fmaf(e.z, mag, acc[m0 + 1]);
+                            const int m0 = __float_as_int(e.x);
+                            if (m0 > cur) {                                      // warp-uniform: the table moved on
+                                if (live) mel_out[static_cast<size_t>(cur) * p.frames] = logf(fmaxf(a0, p.mel_clip));
+                                a0 = a1;
+                                if (m0 != cur + 1) {                             // narrow filters: a step of two or more
+                                    if (live) mel_out[static_cast<size_t>(cur + 1) * p.frames] = logf(fmaxf(a1, p.mel_clip));
+#pragma unroll 1
+                                    for (int m = cur + 2; m < m0; ++m)
+                                        if (live) mel_out[static_cast<size_t>(m) * p.frames] = logf(fmaxf(0.f, p.mel_clip));
+                                    a0 = 0.f;
+                                }
+                                a1 = 0.f;
+                                cur = m0;
+                            }
+                            a0 = fmaf(e.y, mag, a0);                             // bins without weight: m0 = -1, e.y = e.z = 0
+                            a1 = fmaf(e.z, mag, a1);
                         }
                     }
                     if (pp == p.ppi - 1 && live) {
-                        float* out = p.c_out + (static_cast<size_t>(b) * p.n_mel) * p.frames + r;
-                        for (int m = 0; m < p.n_mel; ++m) out[static_cast<size_t>(m) * p.frames] = logf(fmaxf(acc[m], p.mel_clip));
+                        // filters cur, cur + 1 still hold sums; the Nyquist bin (no lower than any other bin's filters)
+                        // joins here; filters above got no bin at all
+                        const float4 en = tab[p.cp];
+                        const int mn = __float_as_int(en.x);
+                        for (int m = cur; m < p.n_mel; ++m) {
+                            float v = m == cur ? a0 : (m == cur + 1 ? a1 : 0.f);
+                            if (m == mn) v = fmaf(en.y, nyq, v);
+                            if (m == mn + 1 && mn >= 0) v = fmaf(en.z, nyq, v);
+                            mel_out[static_cast<size_t>(m) * p.frames] = logf(fmaxf(v, p.mel_clip));
+                        }
                     }
                 } else {
                     const int cp = p.cp;
+                    const float* bs = reinterpret_cast<const float*>(s_extra);
 #pragma unroll 1
                     for (int ch = 0; ch < 4; ++ch) {
                         uint32_t vr[32], vi[32];
@@ -286,10 +324,10 @@ stft_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                                 const int k = k0 + j + e;
                                 if (k == 0) {                                    // DC and Nyquist: two real bins
                                     float z0 = 0.f, z1 = 0.f;
-                                    denoise_bin(re, z0, __ldg(p.spec_bias) * p.strength);
-                                    denoise_bin(im, z1, __ldg(p.spec_bias + cp) * p.strength);
+                                    denoise_bin(re, z0, bs[0]);
+                                    denoise_bin(im, z1, bs[cp]);
                                 } else {
-                                    denoise_bin(re, im, __ldg(p.spec_bias + k) * p.strength);
+                                    denoise_bin(re, im, bs[k]);                  // warp-uniform: broadcast
                                 }
                                 o[e] = re;
                                 o[2 + e] = im;
@@ -393,19 +431,20 @@ static int frame_maps(CUtensorMap* mhi, CUtensorMap* mlo, Params& p, const void*
 // TacotronSTFT.mel_spectrogram (layers.py:63-79) as one kernel.  a_hi / a_lo: reflect-padded signals, bf16 hi / lo parts,
 // [B, R * hop]; w3_paired bf16 [L][3L]: the forward basis in the paired order of this file (pass p: Re rows of bins
 // 128p..128p+127, then their Im rows, with the Re row of bin L/2 in the Im slot of bin 0), split [hi | hi | lo];
-// mel_table [L/2 + 1] float4 {first filter, w_first, w_next, 0}; n_pass: passes that hold a bin with non-zero weight;
-// out fp32 [B, n_mel, frames].
+// mel_table [L/2 + 1] float4 {first filter, w_first, w_next, 0} -- over the bins that carry weight the first-filter
+// index must not decrease (triangular filters overlapping pairwise; the packer checks it);
+// n_pass: passes that hold a bin with non-zero weight; out fp32 [B, n_mel, frames].
 int tc2_stft_mel(const void* a_hi, const void* a_lo, const void* w3_paired, const void* mel_table, float* out, int batch,
                  int frames, int R, int L, int hop, int n_pass, int n_mel, float clip, cudaStream_t stream) {
     using namespace stft2;
     WGB_REQUIRE(w3_paired && mel_table && out, "null pointer");
     WGB_REQUIRE(L / 2 <= kMaxBins, "filter_length (%d) above %d: use the one-CTA kernel", L, 2 * kMaxBins);
-    WGB_REQUIRE(n_mel >= 1 && n_mel <= kMelMax, "n_mel (%d) must be in 1..%d", n_mel, kMelMax);
+    WGB_REQUIRE(n_mel >= 1, "n_mel (%d) must be positive", n_mel);
     Params p{};
     CUtensorMap mhi, mlo, mw;
     if (int e = frame_maps(&mhi, &mlo, p, a_hi, a_lo, batch, frames, R, L, hop)) return e;
     WGB_REQUIRE(n_pass >= 1 && n_pass <= L / kBlockN, "n_pass (%d) must be in 1..%d", n_pass, L / kBlockN);
-    p.n_pass = n_pass; p.ppi = n_pass;                    // one CTA pair runs all passes of its tiles (accumulators in smem)
+    p.n_pass = n_pass; p.ppi = n_pass;                    // one CTA pair runs all passes of its tiles (running sums in registers)
     p.c_out = out; p.mel_table = static_cast<const float4*>(mel_table); p.n_mel = n_mel; p.mel_clip = clip;
     if (int e = basis_half_map(&mw, w3_paired, L, 3 * L)) return e;
     return launch<EPI_MEL>(mhi, mlo, mw, p, stream);
@@ -417,6 +456,7 @@ int tc2_stft_denoise(const void* a_hi, const void* a_lo, const void* w3_paired, 
                      void* hi_out, void* lo_out, int batch, int frames, int R, int L, int hop, cudaStream_t stream) {
     using namespace stft2;
     WGB_REQUIRE(w3_paired && bias_spec && hi_out && lo_out, "null pointer");
+    WGB_REQUIRE(L / 2 <= kMaxBins, "filter_length (%d) above %d: use the one-CTA kernel", L, 2 * kMaxBins);
     Params p{};
     CUtensorMap mhi, mlo, mw;
     if (int e = frame_maps(&mhi, &mlo, p, a_hi, a_lo, batch, frames, R, L, hop)) return e;

@@ -72,13 +72,25 @@ class TacotronSTFT(torch.nn.Module):
         return self._mel_tab[1]
 
     def _mel_table_pair(self, device):
-        """(table [L/2 + 1] float4, n_pass) for wgb_tc2_stft_mel, or None (basis without the two-adjacent-filters
-        structure, more than 80 filters, or a filter length the kernel's shared-memory table cannot hold)."""
+        """(table [L/2 + 1] float4, n_pass) for wgb_tc2_stft_mel, or None when the basis lacks the structure that kernel
+        streams over (a bin feeds at most two ADJACENT filters, and over the bins that carry weight -- the last bin L/2
+        included -- the first-filter index never decreases) or the filter is longer than its
+        shared-memory table (L/2 > 512); the one-CTA kernel, which scatters into per-row accumulators, takes those."""
         cutoff = self.stft_fn.cutoff
         if cutoff - 1 > 512:
             return None
         tab = self._mel_table(device, cutoff)
-        return None if tab is None else (tab, self._mel_tab[2])
+        if tab is None:
+            return None
+        cached = getattr(self, "_mel_pair_ok", None)
+        if cached is None or cached[0] is not tab:
+            t = tab.detach().cpu()
+            has = (t[:, 1] != 0) | (t[:, 2] != 0)
+            idx = t[:, 0][has].long()                  # first-filter index of the bins with weight, ascending bins
+            ok = idx.numel() > 0 and bool(((idx[1:] - idx[:-1]) >= 0).all())
+            self._mel_pair_ok = (tab, ok)
+            cached = self._mel_pair_ok
+        return (tab, self._mel_tab[2]) if cached[1] else None
 
     def mel_spectrogram(self, y: torch.Tensor) -> torch.Tensor:
         """y [B, T] in [-1, 1] (CUDA) -> log-mel [B, n_mel_channels, T // hop + 1]."""

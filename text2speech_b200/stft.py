@@ -131,7 +131,7 @@ class STFT(torch.nn.Module):
         return self._pack[6]
 
     def _use_pair(self) -> bool:
-        return self.pair and self._use_tc()
+        return self.pair and self._use_tc() and self.filter_length <= 1024      # per-bin tables of L/2 + 1 entries in smem
 
     # ------------------------------------------------------------------ device pipeline pieces
     def _spectrum(self, y: torch.Tensor):
