@@ -209,7 +209,8 @@ WGB_API int wgb_tc_stft_denoise(const void* a_hi, const void* a_lo, const void* 
  *   wgb_tc2_stft_mel      layers.py:63-79 in one kernel; only the first n_pass passes run (the ones holding a bin with
  *                         non-zero mel weight: 3 of 4 at 22.05 kHz / fmax 8 kHz); mel_table has L/2 + 1 entries
  *                         (the last one = bin L/2); out fp32 [B, n_mel, frames].
- *   wgb_tc2_stft_denoise  denoiser.py:36-38 + stft.py:102-103; hi_out / lo_out bf16 [B*frames][L]: columns 0..L/2-1
+ *   wgb_tc2_stft_denoise  denoiser.py:36-38 + stft.py:102-103; hi_out / lo_out bf16 [B][out_R][L] (out_R >= frames: row
+ *                         pitch per utterance; rows >= frames are not written): columns 0..L/2-1
  *                         Re of bins 0..L/2-1, column L/2 Re of bin L/2, columns L/2+1.. Im of bins 1..L/2-1 = the
  *                         K operand of the inverse-basis GEMM (K = L instead of 2 * 640); bias_spec fp32 [L/2 + 1].
  *   wgb_tc2_gemm_split3   C fp32 [rows][N] = (a_hi + a_lo)[rows][K] (W_hi + W_lo)^T, w3 = [W_hi | W_hi | W_lo] bf16
@@ -218,9 +219,19 @@ WGB_API int wgb_tc2_stft_mel(const void* a_hi, const void* a_lo, const void* w3_
                              int batch, int frames, int R, int L, int hop, int n_pass, int n_mel, float clip, void* stream);
 WGB_API int wgb_tc2_stft_denoise(const void* a_hi, const void* a_lo, const void* w3_paired, const float* bias_spec,
                                  float strength, void* hi_out, void* lo_out, int batch, int frames, int R, int L, int hop,
-                                 void* stream);
+                                 int out_R, void* stream);
 WGB_API int wgb_tc2_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, float* c, long long rows, int N, int K,
                                 void* stream);
+/* STFT.inverse's conv_transpose1d WITH its overlap-add, the window-sum normalisation, the L/hop scale and the L/2 trim
+ * (stft.py:105-128; audio_processing.py:7-48) as one CTA-pair GEMM: output block q (hop samples) = sum_j frame[q-j] W_j
+ * with W_j the j-th hop-wide slice of the inverse basis (a tap conv over the frame axis, K = taps * 3L, N = hop), so the
+ * [B, frames, L] intermediate never exists.  s_hi / s_lo bf16 [B][frames + taps - 1][L] (column order of
+ * wgb_tc2_stft_denoise; the last taps - 1 rows of every utterance ZERO), taps = L / hop; w_ola bf16 [hop][taps * 3L]
+ * (tap j: split-bf16 [hi | hi | lo] of inverse-basis samples j*hop .. (j+1)*hop-1); env_tab fp32 [2^taps][hop]: the
+ * window-sum envelope for every set of covering frames (bit j: frame q - j exists), accumulated like the reference's
+ * host loop, or NULL for window=None; out fp32 [B][hop * (frames - 1)].  hop % 256 == 0, L % hop == 0, L / hop <= 8. */
+WGB_API int wgb_tc2_istft_ola(const void* s_hi, const void* s_lo, const void* w_ola, const float* env_tab, float* out,
+                              int batch, int frames, int L, int hop, void* stream);
 
 /* ---------------------------------------------------------------- FP32 validation path (CUDA cores) */
 

@@ -868,12 +868,16 @@ def test_stft_pair_kernels_against_one_cta_kernels_and_oracle(models, lib):
         for strength in (0.0, 0.1):
             want = oracle.denoise(y, den.bias_spec.cpu(), strength, fwd, inv, 256, 1024)
             den.stft.pair = True
-            a = den(y.to(DEV), strength)
+            a = den(y.to(DEV), strength)                 # inverse GEMM with the overlap-add inside (wgb_tc2_istft_ola)
+            den.stft.fused_ola = False
+            c = den(y.to(DEV), strength)                 # inverse GEMM + overlap-add kernel
+            den.stft.fused_ola = True
             den.stft.pair = False
             b = den(y.to(DEV), strength)
             den.stft.pair = True
-            assert a.shape == b.shape == want.shape
+            assert a.shape == b.shape == c.shape == want.shape
             assert util.snr_db(a.cpu(), want) >= 80.0 and util.snr_db(a.cpu(), b.cpu()) >= 80.0, (B, n, strength)
+            assert util.snr_db(c.cpu(), want) >= 80.0 and util.snr_db(a.cpu(), c.cpu()) >= 100.0, (B, n, strength)
 
 
 @pytest.mark.parametrize("precision", ["tc", "fp32"])

@@ -41,7 +41,7 @@ def _spectrum_from_paired(s, length):
 def test_pair_layout_reproduces_transform_mel_and_denoiser(golden):
     length, hop = DC["filter_length"], DC["hop_length"]
     stft = STFT(length, hop, DC["win_length"])
-    fwd3, inv3 = stft._pair_pack(CPU)
+    fwd3, inv3, ola = stft._pair_pack(CPU)
     assert fwd3.shape == (length, 3 * length) and inv3.shape == (length, 3 * length) and fwd3.dtype == torch.bfloat16
     y = syn.synthetic_waveforms(2, 4096, sr=DC["sampling_rate"], seed=5)
     fr = _frames(y, length, hop)
@@ -86,6 +86,28 @@ def test_pair_layout_reproduces_transform_mel_and_denoiser(golden):
         out = out * (length / hop)
         out = out[:, length // 2: total - length // 2]
         assert util.rel_l2(out[:, None], golden[key]) < 1e-5
+        # the same through the overlap-add GEMM (wgb_tc2_istft_ola): block q = sum_j frame[q - j] W_j over zero-guarded
+        # rows, envelope row picked by the set of covering frames, scale, blocks inside the trimmed L/2 dropped
+        w_ola, env = ola
+        taps = length // hop
+        assert w_ola.shape == (hop, taps * 3 * length) and env.shape == (1 << taps, hop)
+        rp = frames + taps - 1
+        guarded = torch.zeros(cols.shape[0], rp, length, dtype=torch.float64)
+        guarded[:, :frames] = cols
+        blocks = torch.zeros(cols.shape[0], rp, hop, dtype=torch.float64)
+        for j in range(taps):
+            wj = _unsplit(w_ola[:, j * 3 * length: (j + 1) * 3 * length])            # [hop, L]
+            shifted = torch.zeros_like(guarded)
+            shifted[:, j:] = guarded[:, : rp - j]                                    # row q reads frame q - j
+            blocks += shifted @ wj.t()
+        got = torch.zeros(cols.shape[0], hop * (frames - 1), dtype=torch.float64)
+        for q in range(taps // 2, frames - 2 + taps - taps // 2 + 1):
+            mask = sum(1 << j for j in range(taps) if 0 <= q - j < frames)
+            e = env[mask].double()
+            blk = torch.where(e > np.finfo(np.float32).tiny, blocks[:, q] / e, blocks[:, q]) * (length / hop)
+            got[:, (q - taps // 2) * hop: (q - taps // 2 + 1) * hop] = blk
+        assert util.rel_l2(got[:, None], golden[key]) < 1e-5
+        assert util.rel_l2(got, out) < 1e-6
 
 
 def test_pair_layout_nyquist_weight_is_honoured():
@@ -146,3 +168,17 @@ def test_streaming_filterbank_equals_dense_matmul():
     taco = TacotronSTFT(1024, 256, 1024, 80, 22050, 0.0, 8000.0)
     taco.mel_basis[5, 300] = 0.1
     assert taco._mel_table_pair(CPU) is None
+
+
+def test_ola_envelope_table_equals_reference_window_sum():
+    """env[mask] of the overlap-add GEMM = audio_processing.py:7-48's window_sumsquare at the positions whose covering
+    frames are that set -- bit for bit (float32 running sum of float64 squares, frames ascending)."""
+    stft = STFT(1024, 256, 1024)
+    _, _, (w_ola, env) = stft._pair_pack(CPU)
+    frames, hop, taps = 9, 256, 4
+    wss = oracle.window_sumsquare("hann", frames, hop, 1024, 1024)           # [hop * (frames - 1) + L]
+    for q in range(frames + taps - 1):
+        mask = sum(1 << j for j in range(taps) if 0 <= q - j < frames)
+        assert np.array_equal(env[mask].numpy(), wss[q * hop: (q + 1) * hop]), q
+    nowin = STFT(1024, 256, 1024, window=None)
+    assert nowin._pair_pack(CPU)[2][1] is None

@@ -16,7 +16,9 @@ int tc_gemm_split3(const void*, const void*, const void*, const float*, void*, i
 int tc_conv1d_taps(const void*, const void*, const float*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
 int tc_stft_mag(const void*, const void*, const void*, void*, int, int, int, int, long long, long long, cudaStream_t);
 int tc2_stft_mel(const void*, const void*, const void*, const void*, float*, int, int, int, int, int, int, int, float, cudaStream_t);
-int tc2_stft_denoise(const void*, const void*, const void*, const float*, float, void*, void*, int, int, int, int, int, cudaStream_t);
+int tc2_stft_denoise(const void*, const void*, const void*, const float*, float, void*, void*, int, int, int, int, int, int,
+                     cudaStream_t);
+int tc2_istft_ola(const void*, const void*, const void*, const float*, float*, int, int, int, int, cudaStream_t);
 int tc2_gemm_split3(const void*, const void*, const void*, float*, long long, int, int, cudaStream_t);
 int tc_stft_mel(const void*, const void*, const void*, const void*, void*, int, int, int, int, long long, long long, int, float,
                 cudaStream_t);
@@ -228,8 +230,13 @@ WGB_API int wgb_tc2_stft_mel(const void* a_hi, const void* a_lo, const void* w3_
 }
 WGB_API int wgb_tc2_stft_denoise(const void* a_hi, const void* a_lo, const void* w3_paired, const float* bias_spec,
                                  float strength, void* hi_out, void* lo_out, int batch, int frames, int R, int L, int hop,
-                                 void* stream) {
-    return tc2_stft_denoise(a_hi, a_lo, w3_paired, bias_spec, strength, hi_out, lo_out, batch, frames, R, L, hop, S(stream));
+                                 int out_R, void* stream) {
+    return tc2_stft_denoise(a_hi, a_lo, w3_paired, bias_spec, strength, hi_out, lo_out, batch, frames, R, L, hop, out_R,
+                            S(stream));
+}
+WGB_API int wgb_tc2_istft_ola(const void* s_hi, const void* s_lo, const void* w_ola, const float* env_tab, float* out,
+                              int batch, int frames, int L, int hop, void* stream) {
+    return tc2_istft_ola(s_hi, s_lo, w_ola, env_tab, out, batch, frames, L, hop, S(stream));
 }
 WGB_API int wgb_tc2_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, float* c, long long rows, int N, int K,
                                 void* stream) {

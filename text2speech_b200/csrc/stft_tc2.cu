@@ -26,6 +26,11 @@
 //                two running sums in registers and emits a filter the moment the table moves past it
 //   EPI_DENOISE  max(|X| - bias*strength, 0) e^{j arg X} as the bf16 hi/lo operands of the inverse GEMM
 //                                                                   (denoiser.py:36-38 + stft.py:102-103)
+//   EPI_OLA      the inverse-basis conv_transpose1d INCLUDING its overlap-add (stft.py:105-128): a tile row is one
+//                hop-sized block of the output signal, block q = sum_j frame[q - j] W_j with W_j = the j-th hop-wide
+//                slice of the inverse basis -- a tap conv over the frame axis (K = taps x 3L, N = hop), so the sums
+//                are complete in TMEM and the epilogue applies the window-sum envelope, the L/hop scale and the L/2
+//                trim: the [B, frames, L] intermediate (0.9 GB at 256 x 10 s) and its overlap-add pass do not exist
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -45,7 +50,7 @@ constexpr int kTmemCols = 512;
 constexpr int kThreads = 192;
 constexpr int kMaxBins = 512;         // EPI_MEL / EPI_DENOISE: L/2 <= 512 (per-bin table of L/2 + 1 entries in shared memory)
 
-enum Epi { EPI_F32 = 0, EPI_MEL = 1, EPI_DENOISE = 2 };
+enum Epi { EPI_F32 = 0, EPI_MEL = 1, EPI_DENOISE = 2, EPI_OLA = 3 };
 
 template <int EPI>
 struct Smem {
@@ -64,6 +69,11 @@ struct Params {
                                   // outputs are indexed by the compact row b frames + r
     int n_pass, ppi, n_chunks;    // 256-column passes, passes per work item, K chunks (of the 3K split operand) per pass
     int seg_chunks;               // K / 64: chunk kc reads A segment kc / seg_chunks (hi, lo, hi), columns (kc % seg_chunks) * 64
+    int taps;                     // EPI_OLA: L / hop; chunk kc belongs to tap kc / (3 seg_chunks) and reads A rows t - tap
+                                  // (1 elsewhere: n_chunks = 3 seg_chunks, no shift)
+    int out_R;                    // EPI_DENOISE: row pitch per utterance of hi_out / lo_out (>= frames; EPI_OLA's guard rows)
+    const float* env_tab;         // EPI_OLA [2^taps][hop]: window-sum envelope per set of covering frames (NULL: window=None)
+    float ola_scale;              // EPI_OLA: L / hop (stft.py:125)
     int n_total;                  // EPI_F32: N (row pitch of c_out); EPI_DENOISE: L (row pitch of the hi / lo outputs)
     int cp;                       // EPI_MEL / EPI_DENOISE: L / 2 (bins 0 .. cp - 1 are (Re, Im) pairs, bin cp rides in Im slot 0)
     float* c_out;                 // EPI_F32 [rows, N]; EPI_MEL [B, n_mel, frames]
@@ -175,8 +185,10 @@ stft_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                         uint8_t* sb = sa + kABytes;
                         if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * kStageBytes);
                         const uint32_t bar = mapa_u32(&full_bar[s], 0);
-                        const int seg = kc / p.seg_chunks;                     // 0: A_hi, 1: A_lo, 2: A_hi
-                        tma_load_2d_2sm(sa, seg == 1 ? &map_lo : &map_hi, bar, (kc - seg * p.seg_chunks) * kBlockK, t0);
+                        const int tap = kc / (3 * p.seg_chunks);               // EPI_OLA: frame q - tap feeds block q
+                        const int rem = kc - tap * 3 * p.seg_chunks;
+                        const int seg = rem / p.seg_chunks;                    // 0: A_hi, 1: A_lo, 2: A_hi
+                        tma_load_2d_2sm(sa, seg == 1 ? &map_lo : &map_hi, bar, (rem - seg * p.seg_chunks) * kBlockK, t0 - tap);
                         tma_load_2d_2sm(sb, &map_w, bar, kc * kBlockK, pass * kBlockN + static_cast<int>(rank) * kHalfN);
                         if (++s == kStages) { s = 0; ph ^= 1; }
                     }
@@ -222,8 +234,10 @@ stft_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             const int flat = tile * kBlockM + row;
             const int b = flat / p.R;
             const int r = flat - b * p.R;
-            const bool live = tile < p.n_tiles && flat < p.rows_total && r < p.frames;
-            const size_t grow = static_cast<size_t>(b) * p.frames + r;          // compact output row
+            // EPI_OLA rows are output blocks: all R = frames + taps - 1 of them exist (the trim is applied below)
+            const bool live = tile < p.n_tiles && flat < p.rows_total && (EPI == EPI_OLA || r < p.frames);
+            // compact output row (EPI_DENOISE: with the pitch the overlap-add GEMM wants, guard rows between utterances)
+            const size_t grow = static_cast<size_t>(b) * (EPI == EPI_DENOISE ? p.out_R : p.frames) + r;
 
             // EPI_MEL: a bin feeds the filters m0 and m0 + 1, and m0 never decreases as the bins ascend, so a row needs
             // two running sums: a0 (filter `cur`) and a1 (filter `cur + 1`).  When the table moves on to the next filter,
@@ -253,6 +267,40 @@ stft_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                             for (int j = 0; j < 8; ++j)
                                 d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        }
+                    }
+                } else if constexpr (EPI == EPI_OLA) {
+                    // row = hop block q of utterance b (R = frames + taps - 1 blocks per utterance); the frames covering it
+                    // are q - j for the taps j with 0 <= q - j < frames: that set picks the envelope row (stft.py:111-121,
+                    // audio_processing.py:45-47); blocks inside the trimmed L/2 at both ends are not stored (stft.py:127-128)
+                    const int q_lo = p.taps >> 1;
+                    const bool keep = live && r >= q_lo && r <= p.frames - 2 + p.taps - q_lo;
+                    int mask = 0;
+                    for (int j = 0; j < p.taps; ++j) mask |= (r - j >= 0 && r - j < p.frames) ? (1 << j) : 0;
+                    const int hop = p.n_total;
+                    float* dst = p.c_out + static_cast<size_t>(b) * hop * (p.frames - 1) + static_cast<size_t>(r - q_lo) * hop +
+                                 pass * kBlockN;
+                    const float* env = p.env_tab ? p.env_tab + static_cast<size_t>(mask) * hop + pass * kBlockN : nullptr;
+#pragma unroll 1
+                    for (int ch = 0; ch < 8; ++ch) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + ch * 32, v);
+                        tmem_ld_wait();
+                        if (keep) {
+                            float o[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float a = __uint_as_float(v[j]);
+                                if (env) {
+                                    const float e = __ldg(env + ch * 32 + j);
+                                    if (e > 1.17549435e-38f) a /= e;
+                                    a *= p.ola_scale;
+                                }
+                                o[j] = a;
+                            }
+                            float4* d4 = reinterpret_cast<float4*>(dst + ch * 32);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) d4[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                         }
                     }
                 } else if constexpr (EPI == EPI_MEL) {
@@ -422,6 +470,7 @@ static int frame_maps(CUtensorMap* mhi, CUtensorMap* mlo, Params& p, const void*
     p.frames = frames;
     p.seg_chunks = L / kBlockK;
     p.n_chunks = 3 * p.seg_chunks;
+    p.taps = 1;
     p.cp = L / 2;
     return WGB_OK;
 }
@@ -453,14 +502,15 @@ int tc2_stft_mel(const void* a_hi, const void* a_lo, const void* w3_paired, cons
 // Denoiser.forward's transform + spectral subtraction (denoiser.py:36-38): writes the bf16 hi / lo operands
 // [B * frames, L] of the inverse-basis GEMM (column order of this file).  bias_spec fp32 [L/2 + 1].
 int tc2_stft_denoise(const void* a_hi, const void* a_lo, const void* w3_paired, const float* bias_spec, float strength,
-                     void* hi_out, void* lo_out, int batch, int frames, int R, int L, int hop, cudaStream_t stream) {
+                     void* hi_out, void* lo_out, int batch, int frames, int R, int L, int hop, int out_R, cudaStream_t stream) {
     using namespace stft2;
     WGB_REQUIRE(w3_paired && bias_spec && hi_out && lo_out, "null pointer");
     WGB_REQUIRE(L / 2 <= kMaxBins, "filter_length (%d) above %d: use the one-CTA kernel", L, 2 * kMaxBins);
     Params p{};
     CUtensorMap mhi, mlo, mw;
     if (int e = frame_maps(&mhi, &mlo, p, a_hi, a_lo, batch, frames, R, L, hop)) return e;
-    p.n_pass = L / kBlockN; p.ppi = 1; p.n_total = L;
+    WGB_REQUIRE(out_R >= frames, "out_R (%d) must be >= frames (%d)", out_R, frames);
+    p.n_pass = L / kBlockN; p.ppi = 1; p.n_total = L; p.out_R = out_R;
     p.hi_out = static_cast<__nv_bfloat16*>(hi_out); p.lo_out = static_cast<__nv_bfloat16*>(lo_out);
     p.spec_bias = bias_spec; p.strength = strength;
     if (int e = basis_half_map(&mw, w3_paired, L, 3 * L)) return e;
@@ -479,7 +529,7 @@ int tc2_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, float* c
     p.rows_total = static_cast<int>(rows);
     p.n_tiles = ceil_div(p.rows_total, kBlockM);
     p.R = p.rows_total; p.frames = p.rows_total;          // compact rows
-    p.seg_chunks = K / kBlockK; p.n_chunks = 3 * p.seg_chunks;
+    p.seg_chunks = K / kBlockK; p.n_chunks = 3 * p.seg_chunks; p.taps = 1;
     p.n_pass = N / kBlockN; p.ppi = 1; p.n_total = N;
     p.c_out = c;
     CUtensorMap mhi, mlo, mw;
@@ -487,6 +537,37 @@ int tc2_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, float* c
     if (int e = rows_map(&mlo, a_lo, K, rows, K)) return e;
     if (int e = basis_half_map(&mw, w3, N, 3 * K)) return e;
     return launch<EPI_F32>(mhi, mlo, mw, p, stream);
+}
+
+// STFT.inverse's conv_transpose1d + overlap-add + window-sum normalisation + L/hop scale + L/2 trim (stft.py:105-128) as
+// ONE GEMM.  s_hi / s_lo: recombined spectra as bf16 hi / lo parts [B, frames + taps - 1, L] (taps = L / hop) whose last
+// taps - 1 rows per utterance are ZERO (the frames before the first / after the last one); w_ola bf16 [hop][taps * 3L]:
+// tap j's columns = split-bf16 [hi | hi | lo] of the inverse basis rows n = j hop .. (j + 1) hop - 1; env_tab fp32
+// [2^taps][hop] = the window-sum envelope for every set of covering frames (bit j set: frame q - j exists), built by the
+// host exactly like audio_processing.py:45-47 accumulates it, or NULL for window=None (no division, no scale);
+// out fp32 [B, hop * (frames - 1)].  hop % 256 == 0, L % hop == 0, L / hop <= 8.
+int tc2_istft_ola(const void* s_hi, const void* s_lo, const void* w_ola, const float* env_tab, float* out, int batch,
+                  int frames, int L, int hop, cudaStream_t stream) {
+    using namespace stft2;
+    WGB_REQUIRE(s_hi && s_lo && w_ola && out, "null pointer");
+    WGB_REQUIRE(batch > 0 && frames > 1, "batch must be positive and frames > 1");
+    WGB_REQUIRE(L > 0 && L % kBlockK == 0 && hop > 0 && hop % kBlockN == 0 && L % hop == 0 && L / hop <= 8,
+                "need hop %% 256 == 0, filter_length %% hop == 0 and at most 8 taps (L=%d hop=%d)", L, hop);
+    const int taps = L / hop;
+    const long long rows = static_cast<long long>(batch) * (frames + taps - 1);
+    WGB_REQUIRE(rows < (1ll << 31) - 1024, "too many frames");
+    Params p{};
+    p.rows_total = static_cast<int>(rows);
+    p.n_tiles = ceil_div(p.rows_total, kBlockM);
+    p.R = frames + taps - 1; p.frames = frames;
+    p.seg_chunks = L / kBlockK; p.taps = taps; p.n_chunks = taps * 3 * p.seg_chunks;
+    p.n_pass = hop / kBlockN; p.ppi = 1; p.n_total = hop;
+    p.c_out = out; p.env_tab = env_tab; p.ola_scale = static_cast<float>(L) / static_cast<float>(hop);
+    CUtensorMap mhi, mlo, mw;
+    if (int e = rows_map(&mhi, s_hi, L, rows, L)) return e;
+    if (int e = rows_map(&mlo, s_lo, L, rows, L)) return e;
+    if (int e = basis_half_map(&mw, w_ola, hop, taps * 3 * L)) return e;
+    return launch<EPI_OLA>(mhi, mlo, mw, p, stream);
 }
 
 }  // namespace wgb

@@ -63,6 +63,8 @@ class STFT(torch.nn.Module):
         # fused mel / denoiser paths: CTA-pair kernels with the unpadded spectrum layout (csrc/stft_tc2.cu) when True,
         # the one-CTA kernels with the 640-bin padded layout (csrc/wn_tc.cu) when False (kept for A/B)
         self.pair = True
+        # Denoiser: inverse GEMM with the overlap-add inside (wgb_tc2_istft_ola) instead of GEMM + overlap-add kernel
+        self.fused_ola = True
 
     # ------------------------------------------------------------------ packed constants
     @property
@@ -117,7 +119,25 @@ class STFT(torch.nn.Module):
                 inv2[:, :half] = ib[:half].t()
                 inv2[:, half] = ib[half]
                 inv2[:, half + 1:] = ib[cutoff + 1: cutoff + half].t()
-                pair_pack = (_split3(paired).to(device), _split3(inv2).to(device))
+                ola = None
+                taps = length // self.hop_length
+                if self.hop_length % 256 == 0 and length % self.hop_length == 0 and taps <= 8:
+                    # inverse GEMM with the overlap-add inside (wgb_tc2_istft_ola): tap j = inverse-basis samples
+                    # j*hop .. (j+1)*hop-1 as a [hop, 3L] split-bf16 block; envelope per set of covering frames, summed
+                    # like the reference's host loop (float32 += float64, frames ascending = taps descending)
+                    hop = self.hop_length
+                    w_ola = torch.cat([_split3(inv2[j * hop: (j + 1) * hop]) for j in range(taps)], dim=1).contiguous()
+                    env = None
+                    if self.window is not None:
+                        sq64 = padded_window(self.window, self.win_length, length).astype(np.float64) ** 2
+                        env = np.zeros((1 << taps, hop), dtype=np.float32)
+                        for mask in range(1 << taps):
+                            for j in reversed(range(taps)):
+                                if (mask >> j) & 1:
+                                    env[mask] = (env[mask].astype(np.float64) + sq64[j * hop: (j + 1) * hop]).astype(np.float32)
+                        env = torch.from_numpy(env).to(device)
+                    ola = (w_ola.to(device), env)
+                pair_pack = (_split3(paired).to(device), _split3(inv2).to(device), ola)
             self._pack = (key, fwd.to(device), inv.to(device), sq, cp, fwd_paired, pair_pack)
         return self._pack[1:5]
 
@@ -126,7 +146,9 @@ class STFT(torch.nn.Module):
         return self._pack[5]
 
     def _pair_pack(self, device):
-        """(forward basis, inverse basis) in the unpadded layout of the CTA-pair kernels, split-bf16 [L][3L] each."""
+        """(forward basis, inverse basis, overlap-add pack) in the unpadded layout of the CTA-pair kernels: the bases as
+        split-bf16 [L][3L]; the pack = (tap-sliced inverse basis [hop][taps*3L], envelope table [2^taps][hop] or None
+        for window=None), or None when hop % 256 != 0."""
         self._packed(device)
         return self._pack[6]
 
@@ -209,14 +231,26 @@ class STFT(torch.nn.Module):
         s = _lib.stream_ptr()
         if self._use_pair():                      # CTA-pair kernels, unpadded layout: K of the inverse GEMM = L
             hi, lo, ld_pad = self._padded_split(y, whole_hops=True)
-            fwd2, inv2 = self._pair_pack(y.device)
+            fwd2, inv2, ola = self._pair_pack(y.device)
+            out = torch.empty((b, 1, hop * (frames - 1)), device=y.device, dtype=torch.float32)
+            if ola is not None and self.fused_ola:
+                # inverse-basis GEMM with the overlap-add, envelope, scale and trim in it: the spectra carry taps - 1
+                # zero guard rows per utterance (the frames before the first / after the last one)
+                rp = frames + length // hop - 1
+                shi = torch.empty((b, rp, length), device=y.device, dtype=torch.bfloat16)
+                slo = torch.empty_like(shi)
+                shi[:, frames:].zero_()
+                slo[:, frames:].zero_()
+                _lib.call("wgb_tc2_stft_denoise", hi, lo, fwd2, bias_spec, float(strength), shi, slo, b, frames,
+                          ld_pad // hop, length, hop, rp, s)
+                _lib.call("wgb_tc2_istft_ola", shi, slo, ola[0], ola[1], out, b, frames, length, hop, s)
+                return out
             shi = torch.empty((b * frames, length), device=y.device, dtype=torch.bfloat16)
             slo = torch.empty_like(shi)
             _lib.call("wgb_tc2_stft_denoise", hi, lo, fwd2, bias_spec, float(strength), shi, slo, b, frames, ld_pad // hop,
-                      length, hop, s)
+                      length, hop, frames, s)
             fr = torch.empty((b, frames, length), device=y.device, dtype=torch.float32)
             _lib.call("wgb_tc2_gemm_split3", shi, slo, inv2, fr, b * frames, length, length, s)
-            out = torch.empty((b, 1, hop * (frames - 1)), device=y.device, dtype=torch.float32)
             _lib.call("wgb_istft_overlap_add", fr, win_sq, out, b, frames, length, hop, s)
             return out
         hi, lo, ld_pad = self._padded_split(y)

@@ -42,8 +42,9 @@ def main():
         torch.cuda.synchronize()
         return
     out = {}
-    for pair in (True, False):
+    for name, pair, fused in (("pair", True, True), ("pair_separate_overlap_add", True, False), ("one_cta", False, False)):
         taco.stft_fn.pair = den.stft.pair = pair
+        den.stft.fused_ola = fused
         rec = {}
         med, best = timeit(lambda: taco._mel_spectrogram(y), warmup=3, iters=10)
         rec["mel_ms"] = med
@@ -53,8 +54,8 @@ def main():
         rec["denoiser_ms"] = med
         rec["denoiser_algorithmic_tflops"] = frames * 2 * STFT_FLOP / (med * 1e-3) / 1e12
         rec["denoiser_breakdown"] = breakdown(lambda: den(y, 0.01))
-        out["pair" if pair else "one_cta"] = rec
-    taco.stft_fn.pair = den.stft.pair = True
+        out[name] = rec
+    taco.stft_fn.pair = den.stft.pair = den.stft.fused_ola = True
     a = taco._mel_spectrogram(y)
     d = den(y, 0.01)
     taco.stft_fn.pair = den.stft.pair = False
