@@ -380,6 +380,87 @@ def secondary_configs(model, dev, rank, world, barrier, reduce_max, peak):
     return out
 
 
+def measure_train(dev, rank, world, steps, warmup, barrier, reduce_max, peak, batch=32, samples=16000):
+    """Training direction (waveglow/train.py:108-124) at BASELINE.json configs[3]'s shape PER GPU: forward,
+    WaveGlowLoss, backward, Adam on `batch` x `samples`-sample segments, config.json architecture in weight-norm layout.
+    One GPU: the whole step replays from one CUDA graph (GraphedTrainStep).  N > 1 (weak scaling, data parallel): eager
+    steps with apply_gradient_allreduce -- one NCCL all-reduce per flow issued while the backward of the remaining flows
+    runs (waveglow/distributed.py:90-142's contract).  `e2e` adds the H2D copy of the batch from pinned host memory and a
+    D2H read of the loss every step."""
+    import warnings
+    import torch
+    import text2speech_b200 as t2s
+    from text2speech_b200 import synthetic as syn
+    from text2speech_b200.training import FusedAdam, GraphedTrainStep, apply_gradient_allreduce
+    sustained, burst, hbm = peak
+    cfg = syn.load_config()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = t2s.WaveGlow(**cfg)
+    model.load_state_dict(syn.synthetic_state_dict(cfg, seed=1234, end_std=0.01, weight_norm=True))
+    model = model.to(dev).train()
+    if world > 1:
+        model = apply_gradient_allreduce(model)
+    opt = FusedAdam(model.parameters(), lr=1e-4)
+    crit = t2s.WaveGlowLoss(1.0)
+    frames = samples // 256 + 1
+    g = torch.Generator().manual_seed(1 + rank)
+    audio_h = (0.1 * torch.randn((batch, samples), generator=g)).clamp(-1, 1).pin_memory()
+    mel_h = syn.synthetic_mel(batch, frames, seed=rank).pin_memory()
+    audio, mel = audio_h.to(dev), mel_h.to(dev)
+    loss_h = torch.zeros(1).pin_memory()
+    if world == 1:
+        graphed = GraphedTrainStep(model, opt, crit, batch, mel.shape[1], frames, samples)
+
+        def step(m, a):
+            return graphed(m, a)
+        how = "whole step (forward, loss, backward, gradient gather, Adam) replayed from one CUDA graph"
+    else:
+        def step(m, a):
+            opt.zero_grad()
+            loss = crit(model((m, a)))
+            loss.backward()
+            opt.step()
+            return loss.detach()
+        how = ("eager step; gradients averaged by apply_gradient_allreduce: one NCCL all-reduce per flow, overlapped with "
+               "the backward of the remaining flows")
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return reduce_max(e0.elapsed_time(e1) / steps)
+
+    losses = []
+    ms = timed(lambda: losses.append(step(mel, audio)))
+
+    def e2e_step():
+        m, a = mel_h.to(dev, non_blocking=True), audio_h.to(dev, non_blocking=True)
+        loss_h.copy_(step(m, a).reshape(1), non_blocking=True)
+    ms_e2e = timed(e2e_step)
+    torch.cuda.synchronize(dev)
+    flop_fwd = WN_FLOP_PER_STEP * (samples // 8) * batch
+    tf = 3 * flop_fwd / (ms * 1e-3) / 1e12                        # per GPU: forward + 2x backward (data + weight gradients)
+    out = {"config": f"WaveGlow train step (waveglow/train.py:108-124), {batch} x {samples} samples per GPU (BASELINE.json "
+                     f"configs[3] shape, {frames} mel frames), config.json arch, weight norm, FusedAdam, x{world} data parallel",
+           "how": how, "ms_per_step": ms, "samples_per_s": world * batch * samples / (ms * 1e-3),
+           "e2e_ms_per_step": ms_e2e, "e2e_samples_per_s": world * batch * samples / (ms_e2e * 1e-3),
+           "h2d_bytes_per_step": (mel_h.numel() + audio_h.numel()) * 4 * world, "d2h_bytes_per_step": 4 * world,
+           "wn_gemm_tflops_per_gpu": tf, "frac_bf16_sustained_per_gpu": tf / sustained,
+           "flop_accounting": "algorithmic conv FLOPs of the reference: forward 522.19 MFLOP per group step, backward 2x",
+           "loss_first_last": [float(losses[0]), float(losses[-1])],
+           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+    del model, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 
 def run_gpu_arm(args):
@@ -630,10 +711,13 @@ def run_gpu_arm(args):
     if not args.no_secondary:
         try:
             secondary = secondary_configs(model, dev, rank, world, barrier, reduce_max, (sustained, burst, hbm))
+            model.repack()                   # drop the packed inference weights (2.6 GB) before the training step
+            torch.cuda.empty_cache()
+            secondary["train_step"] = measure_train(dev, rank, world, 5, 3, barrier, reduce_max, (sustained, burst, hbm))
         except Exception as e:  # noqa: BLE001
             if world > 1:
                 raise
-            secondary = {"error": repr(e)[:400]}
+            secondary = dict(secondary or {}, error=repr(e)[:400])
     eager = None
     if rank == 0 and world == 1 and not args.no_gpu_baseline:
         try:
@@ -681,6 +765,52 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def run_train_arm(args):
+    """`--mode train`: the training step as the main line (same JSON contract; metric = training samples/s)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def reduce_max(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sustained, burst, hbm, peak_src = peaks()
+    with ClockSampler(local_rank) as clocks:
+        r = measure_train(dev, rank, world, args.steps, args.warmup, barrier, reduce_max, (sustained, burst, hbm))
+    if rank == 0:
+        line = {"metric": "waveglow_train_audio_samples_per_sec", "value": r["samples_per_s"], "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": r["config"], "step": r["how"],
+                           "l2": "no flush needed: a step streams ~30 GB of activations"},
+                "e2e": {"value": r["e2e_samples_per_s"], "unit": UNIT, "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": r["d2h_bytes_per_step"]},
+                "roofline": {"bound": "tensor", "achieved": r["wn_gemm_tflops_per_gpu"], "peak": sustained, "unit": "TFLOP/s",
+                             "frac": r["frac_bf16_sustained_per_gpu"], "traffic": None,
+                             "kernel": "whole step (forward + data-gradient + weight-gradient GEMMs), " + r["flop_accounting"],
+                             "peak_source": peak_src + ", bf16_tflops_sustained"},
+                "cpu_baseline": None, "detail": r, "clocks": clocks.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -692,10 +822,14 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip BASELINE.json configs 1, 3, 4")
     ap.add_argument("--no-graph", action="store_true", help="time eager infer calls instead of CUDA-graph replays (ncu runs)")
     ap.add_argument("--breakdown", action="store_true", help="add per-entry-point CUDA-event totals of one extra step")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer (default): the headline vocoding benchmark; train: the training step on 32 x 16 000 samples per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.mode == "train":
+        run_train_arm(args)
     else:
         run_gpu_arm(args)
 

@@ -104,3 +104,41 @@ def test_flat_gradient_allreduce_world2(tmp_path):
     port = _free_port()
     mp.spawn(_grad_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert all(json.load(open(tmp_path / f"g{r}.json"))["ok"] for r in range(2))
+
+
+def _reducer_worker(rank, world, port, out_dir):
+    """_GradReducer (per-flow buckets of effective-weight gradients, reduced while the backward is still running) and
+    apply_gradient_allreduce's broadcast, on gloo: every rank ends with the MEAN of the ranks' gradients, in views of
+    the right shapes, for overlap on and off; parameters start identical to rank 0's."""
+    from text2speech_b200 import training
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    for overlap in (True, False):
+        red = training._GradReducer(None, overlap)
+        grads, want = {}, {}
+        for k in range(3):                                   # three "flows" with a few tensors each
+            names = []
+            for j, shape in enumerate([(4, 3, 1), (7,), (2, 5)]):
+                n = f"WN.{k}.t{j}"
+                base = torch.arange(float(torch.Size(shape).numel())).reshape(shape) + 10 * k + j
+                grads[n] = base * (rank + 1)
+                want[n] = base * sum(r + 1 for r in range(world)) / world
+                names.append(n)
+            red.add(grads, names)
+        red.finish(grads)
+        ok = ok and all(grads[n].shape == want[n].shape and torch.allclose(grads[n], want[n]) for n in want)
+    lin = torch.nn.Linear(3, 2)
+    with torch.no_grad():
+        lin.weight.fill_(float(rank + 1))
+    training.apply_gradient_allreduce(lin)
+    ok = ok and bool((lin.weight == 1.0).all()) and lin._dp_allreduce == (None, True)
+    with open(os.path.join(out_dir, f"r{rank}.json"), "w") as f:
+        json.dump({"ok": bool(ok)}, f)
+    dist.destroy_process_group()
+
+
+def test_per_flow_gradient_reducer_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_reducer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all(json.load(open(tmp_path / f"r{r}.json"))["ok"] for r in range(2))

@@ -8,8 +8,8 @@ signature, per-iteration log line and checkpoint dict (``{'model': <pickled Wave
 'learning_rate'}``, train.py:52-62) as the reference, so a checkpoint written here loads with
 ``waveglow/inference.py:37`` (``torch.load(path)['model']``) and with ``text2speech_b200.inference.load_waveglow``.
 What runs underneath (training.py): forward / backward through this package's kernels, ``FusedAdam`` (one kernel per
-step; its ``state_dict`` is ``torch.optim.Adam``'s format), and ONE flat-gradient all-reduce per step instead of
-distributed.py:90-142's per-parameter hooks.  The dataset's mel is computed on the GPU, hence ``num_workers=0``.
+step; its ``state_dict`` is ``torch.optim.Adam``'s format), and ``apply_gradient_allreduce`` (distributed.py:90-142's name
+and contract) with one NCCL all-reduce per flow, issued while the backward pass of the remaining flows runs.  The dataset's mel is computed on the GPU, hence ``num_workers=0``.
 """
 from __future__ import annotations
 
@@ -24,7 +24,7 @@ from torch.utils.data.distributed import DistributedSampler
 
 from .glow import WaveGlow, WaveGlowLoss
 from .mel2samp import Mel2Samp
-from .training import FusedAdam, allreduce_gradients
+from .training import FusedAdam, apply_gradient_allreduce
 
 
 def reduce_tensor(tensor: torch.Tensor, num_gpus: int) -> torch.Tensor:
@@ -73,8 +73,10 @@ def save_checkpoint(model, optimizer, learning_rate, iteration, filepath, wavegl
 def train(num_gpus, rank, group_name, output_directory, epochs, learning_rate, sigma, iters_per_checkpoint, batch_size,
           seed, checkpoint_path, waveglow_config, data_config, dist_config=None, fp16_run=False, with_tensorboard=False,
           max_iterations=None):
-    """train.py:64-140.  ``max_iterations`` (extra) stops early; ``fp16_run`` / ``with_tensorboard`` of later reference
-    revisions are accepted and must be False (GEMMs already run in bf16 with fp32 accumulation and fp32 master weights)."""
+    """train.py:64-140.  ``max_iterations`` (extra) stops early.  ``fp16_run`` / ``with_tensorboard`` do not exist in the
+    reference under /root/reference (waveglow/train.py and config.json:2-11 have neither; they belong to later upstream
+    revisions): they are accepted for config compatibility and must be False (the GEMMs already run in bf16 with fp32
+    accumulation and fp32 master weights, which is what upstream's fp16_run buys with apex)."""
     if fp16_run or with_tensorboard:
         raise ValueError("fp16_run / with_tensorboard are not supported")
     torch.manual_seed(seed)
@@ -83,6 +85,8 @@ def train(num_gpus, rank, group_name, output_directory, epochs, learning_rate, s
         init_distributed(rank, num_gpus, group_name, **(dist_config or {"dist_backend": "nccl", "dist_url": "env://"}))
     criterion = WaveGlowLoss(sigma)
     model = WaveGlow(**waveglow_config).cuda()
+    if num_gpus > 1:
+        model = apply_gradient_allreduce(model)            # train.py:75-76
     optimizer = FusedAdam(model.parameters(), lr=learning_rate)
     iteration = 0
     if checkpoint_path != "":
@@ -109,9 +113,8 @@ def train(num_gpus, rank, group_name, output_directory, epochs, learning_rate, s
             outputs = model((mel, audio))
             loss = criterion(outputs)
             reduced_loss = reduce_tensor(loss.data, num_gpus).item() if num_gpus > 1 else loss.item()
-            loss.backward()
-            scale = allreduce_gradients(optimizer)        # distributed.py:90-142 as one flat all-reduce
-            optimizer.step(grad_scale=scale, gathered=True)
+            loss.backward()                               # gradients leave averaged over the ranks (distributed.py:105-141),
+            optimizer.step()                              # reduced per flow while the backward was still running
             print("{}:\t{:.9f}".format(iteration, reduced_loss))
             losses.append(reduced_loss)
             if iteration % iters_per_checkpoint == 0 and rank == 0:

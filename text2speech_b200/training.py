@@ -206,8 +206,54 @@ def _forward(st: Dict[str, Tensor], n_flows: int, n_group: int, mel: Tensor, aud
 
 
 # ------------------------------------------------------------------------------------------------ backward
+class _GradReducer:
+    """Data-parallel reduction of the EFFECTIVE-weight gradients while the backward pass is still running
+    (waveglow/distributed.py:105-141 averages the parameter gradients once the whole backward is done).
+
+    The map from effective-weight gradients to parameter gradients (weight norm's backward, identity for the rest) is
+    linear with coefficients that are identical on every rank, so averaging dL/dw per flow and letting torch's weight-norm
+    backward run on the averages leaves exactly the averaged parameter gradients in ``.grad``.  Each flow's gradients are
+    packed into one flat bucket the moment the flow's backward is finished and all-reduced asynchronously on NCCL's own
+    stream (NVLink / NVSwitch), overlapping the remaining flows' kernels; ``finish`` waits, scales by 1 / world and hands
+    back views.  overlap=False issues the same buckets only at the end (the A/B reference)."""
+
+    def __init__(self, group, overlap: bool):
+        import torch.distributed as dist
+        self.dist, self.group, self.overlap = dist, group, overlap
+        self.world = dist.get_world_size(group)
+        self.pending = []          # (work, flat, [(name, shape, offset, numel)])
+        self.deferred = []
+
+    def add(self, grads: Dict[str, Tensor], names: Sequence[str]) -> None:
+        if self.world == 1:
+            return
+        metas, off = [], 0
+        for n in names:
+            g = grads[n]
+            metas.append((n, g.shape, off, g.numel()))
+            off += g.numel()
+        flat = torch.cat([grads[n].reshape(-1) for n in names])
+        if self.overlap:
+            self.pending.append((self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True),
+                                 flat, metas))
+        else:
+            self.deferred.append((flat, metas))
+
+    def finish(self, grads: Dict[str, Tensor]) -> None:
+        for flat, metas in self.deferred:
+            self.pending.append((self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True),
+                                 flat, metas))
+        self.deferred = []
+        for work, flat, metas in self.pending:
+            work.wait()                                   # the current stream waits for NCCL's
+            flat.mul_(1.0 / self.world)
+            for n, shape, off, numel in metas:
+                grads[n] = flat[off: off + numel].view(shape)
+        self.pending = []
+
+
 def _backward(st: Dict[str, Tensor], sv: _Saved, n_flows: int, n_group: int, g_z: Tensor,
-              g_log_s: Sequence[Optional[Tensor]]) -> Dict[str, Tensor]:
+              g_log_s: Sequence[Optional[Tensor]], reducer: Optional[_GradReducer] = None) -> Dict[str, Tensor]:
     b, t, cond = sv.b, sv.t, sv.cond
     rows = b * t
     dev = cond.device
@@ -300,6 +346,8 @@ def _backward(st: Dict[str, Tensor], sv: _Saved, n_flows: int, n_group: int, g_z
             grads[p + f"cond_layers.{i}.weight"] = d_w_cond[i].unsqueeze(2)
             grads[p + f"cond_layers.{i}.bias"] = db_in[i].clone()
         fs.h = fs.acts = fs.ts = None                                          # release this flow's activations
+        if reducer is not None:                                                # this flow's gradients are final: reduce
+            reducer.add(grads, [n for n in grads if n.startswith(p) or n == f"convinv.{k}.conv.weight"])
     up = sv.up
     ksize = up.up_stride * up.up_taps
     d_up = torch.empty((up.n_mel, up.n_mel, ksize), device=dev, dtype=f32)
@@ -308,6 +356,9 @@ def _backward(st: Dict[str, Tensor], sv: _Saved, n_flows: int, n_group: int, g_z
               n_group, s)
     grads["upsample.weight"] = d_up
     grads["upsample.bias"] = db_up
+    if reducer is not None:
+        reducer.add(grads, ["upsample.weight", "upsample.bias"])
+        reducer.finish(grads)
     return grads
 
 
@@ -315,8 +366,9 @@ class _Flow(torch.autograd.Function):
     """(mel, audio, *effective weights) -> (z, *log_s): the whole flow as one autograd node."""
 
     @staticmethod
-    def forward(ctx, names, n_flows, n_group, mel, audio, *weights):
+    def forward(ctx, names, n_flows, n_group, dp, mel, audio, *weights):
         st = {n: w.detach().float() for n, w in zip(names, weights)}
+        ctx.dp = dp
         with torch.cuda.device(mel.device):
             z, log_s_list, sv = _forward(st, n_flows, n_group, mel.detach().float().contiguous(),
                                          audio.detach().float().contiguous())
@@ -330,13 +382,18 @@ class _Flow(torch.autograd.Function):
             raise RuntimeError("the flow's saved activations were already consumed (backward twice?)")
         if g_z is None:
             g_z = torch.zeros((sv.b, ctx.n_group, sv.t), device=sv.cond.device)
+        reducer = None
+        if ctx.dp is not None:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(ctx.dp[0]) > 1:
+                reducer = _GradReducer(ctx.dp[0], ctx.dp[1])
         with torch.cuda.device(sv.cond.device):
-            grads = _backward(ctx.st, sv, ctx.n_flows, ctx.n_group, g_z, g_log_s)
+            grads = _backward(ctx.st, sv, ctx.n_flows, ctx.n_group, g_z, g_log_s, reducer)
         ctx.sv = None
         out = []
-        for n, need in zip(ctx.names, ctx.needs_input_grad[5:]):
+        for n, need in zip(ctx.names, ctx.needs_input_grad[6:]):
             out.append(grads[n] if need else None)
-        return (None, None, None, None, None, *out)
+        return (None, None, None, None, None, None, *out)
 
 
 class _LogDet(torch.autograd.Function):
@@ -368,7 +425,7 @@ def forward_autograd(model, spect: Tensor, audio: Tensor):
     model._check_supported()
     _lib.require_b200(spect.device)
     names, weights = effective_weights(model)
-    outs = _Flow.apply(names, model.n_flows, model.n_group, spect, audio, *weights)
+    outs = _Flow.apply(names, model.n_flows, model.n_group, getattr(model, "_dp_allreduce", None), spect, audio, *weights)
     z, log_s_list = outs[0], list(outs[1:])
     bt = z.shape[0] * z.shape[2]
     log_det = [_LogDet.apply(model.convinv[k].conv.weight, float(bt)) for k in range(model.n_flows)]   # glow.py:100
@@ -462,6 +519,26 @@ class FusedAdam:
             _lib.call("wgb_adam_step_dev", self.flat, self.grad, self.m, self.v, self.n, float(self.lr),
                       float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_dev, float(grad_scale),
                       _lib.stream_ptr())
+
+
+def apply_gradient_allreduce(module, group=None, overlap: bool = True):
+    """waveglow/distributed.py:90-142 for the drop-in WaveGlow (same name, same contract): broadcast rank 0's state to
+    every rank (:99-103), then make every ``loss.backward()`` leave gradients AVERAGED over the ranks in ``.grad``
+    (:105-141), so the training loop is the reference's: ``model = apply_gradient_allreduce(model)`` ...
+    ``loss.backward(); optimizer.step()``.  Instead of flattening all parameter gradients after the backward pass, each
+    flow's effective-weight gradients are all-reduced as soon as that flow's backward is done (``_GradReducer``), which
+    hides the collective behind the remaining flows.  The log-determinant term's gradient (B T W^-T per rank, identical
+    on every rank for equal per-rank batches, which the DistributedSampler + drop_last loader guarantees) needs no
+    reduction.  overlap=False: the same buckets, issued after the last flow."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("apply_gradient_allreduce needs an initialised process group (init_distributed)")
+    for p in module.state_dict().values():
+        if torch.is_tensor(p):
+            dist.broadcast(p, 0, group=group)
+    bump_param_generation()
+    module._dp_allreduce = (group, bool(overlap))
+    return module
 
 
 def allreduce_gradients(optimizer: FusedAdam, group=None, gathered: bool = False) -> float:

@@ -3,9 +3,12 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 \
         tools/check_ddp_train.py [--batch 8] [--samples 16000] [--steps 3]
 
-Every rank trains the same model on its own shard; the flat gradient buffer is summed with ONE NCCL all-reduce per step
-(NVLink) and Adam runs on every rank.  Checks that the parameters stay bit-identical across ranks and prints step /
-all-reduce times (device-timed, max over ranks).
+Every rank trains the same model on its own shard and Adam runs on every rank.  --reduce picks how the gradients meet:
+  flat      ONE NCCL all-reduce of the optimiser's flat gradient buffer after the backward pass (allreduce_gradients)
+  overlap   apply_gradient_allreduce(model): one all-reduce per flow of the effective-weight gradients, issued as soon as
+            that flow's backward is done, i.e. hidden behind the remaining flows (the reference's name and contract)
+  deferred  the same buckets, all issued after the last flow (what `overlap` is compared against)
+Checks that the parameters stay bit-identical across ranks and prints step times (device-timed, max over ranks).
 """
 from __future__ import annotations
 
@@ -21,7 +24,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import text2speech_b200 as t2s                                   # noqa: E402
 from text2speech_b200 import synthetic as syn                    # noqa: E402
-from text2speech_b200.training import FusedAdam, allreduce_gradients   # noqa: E402
+from text2speech_b200.training import FusedAdam, allreduce_gradients, apply_gradient_allreduce   # noqa: E402
 
 
 def main():
@@ -30,7 +33,10 @@ def main():
     ap.add_argument("--samples", type=int, default=16000)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--graph", action="store_true", help="forward + backward + gradient gather from one CUDA graph per rank")
+    ap.add_argument("--reduce", default="flat", choices=["flat", "overlap", "deferred"])
     args = ap.parse_args()
+    if args.graph and args.reduce != "flat":
+        raise SystemExit("--graph goes with --reduce flat (the per-flow collectives are issued eagerly)")
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -41,6 +47,8 @@ def main():
         model = t2s.WaveGlow(**cfg)
     model.load_state_dict(syn.synthetic_state_dict(cfg, seed=1234, end_std=0.01, weight_norm=True))
     model = model.to(dev).train()
+    if args.reduce != "flat":
+        model = apply_gradient_allreduce(model, overlap=args.reduce == "overlap")
     opt = FusedAdam(model.parameters(), lr=1e-6)
     crit = t2s.WaveGlowLoss(1.0)
     frames = args.samples // 256 + 1
@@ -64,9 +72,9 @@ def main():
         else:
             opt.zero_grad()
             loss = crit(model((mel, audio)))
-            loss.backward()
+            loss.backward()                                       # overlap / deferred: gradients leave averaged
             e[1].record()
-            scale = allreduce_gradients(opt)
+            scale = allreduce_gradients(opt) if args.reduce == "flat" else (opt.gather_grads(), 1.0)[1]
         e[2].record()
         opt.step(grad_scale=scale, gathered=True)
         e[3].record()
@@ -85,7 +93,7 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({"check": "ddp_train", "world": world, "per_gpu_batch": args.batch, "samples": args.samples,
-                          "graph": bool(args.graph), "params_identical_across_ranks": bool(same.item() == 1.0),
+                          "graph": bool(args.graph), "reduce": args.reduce, "params_identical_across_ranks": bool(same.item() == 1.0),
                           "step_ms": float(t[0]), "grad_gather_plus_allreduce_ms": float(t[1]),
                           "flat_gradient_bytes": opt.n * 4,
                           "samples_per_s_all_gpus": world * args.batch * args.samples / (float(t[0]) * 1e-3),
