@@ -561,8 +561,10 @@ class GraphedTrainStep:
         step = GraphedTrainStep(model, optimizer, criterion, batch, n_mel, frames, samples)
         loss = step(mel, audio)            # copies the batch into the graph's static buffers, replays, returns the loss
 
-    With ``world_size > 1`` build it with ``include_optimizer=False``: the graph then ends after the gradient gather,
-    and the caller runs ``allreduce_gradients`` + ``optimizer.step(gathered=True)`` eagerly (two launches)."""
+    With ``world_size > 1`` either wrap the model with ``apply_gradient_allreduce`` first (its per-flow NCCL all-reduces
+    are captured into the graph, overlapped with the backward pass exactly as in eager mode), or build the step with
+    ``include_optimizer=False``: the graph then ends after the gradient gather, and the caller runs
+    ``allreduce_gradients`` + ``optimizer.step(gathered=True)`` eagerly (two launches)."""
 
     def __init__(self, model, optimizer: FusedAdam, criterion, batch: int, n_mel: int, frames: int, samples: int,
                  include_optimizer: bool = True, warmup: int = 2):
@@ -581,7 +583,10 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         optimizer.zero_grad()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # a model under apply_gradient_allreduce issues NCCL collectives inside the step: they are captured with it;
+        # NCCL's watchdog thread polls events concurrently, which only the thread-local capture mode tolerates
+        mode = "thread_local" if getattr(model, "_dp_allreduce", None) is not None else "global"
+        with torch.cuda.graph(self.graph, capture_error_mode=mode):
             self.loss = self._one_step(criterion)
         for dst, src in zip((optimizer.flat, optimizer.m, optimizer.v, optimizer.step_dev), keep):
             dst.copy_(src)

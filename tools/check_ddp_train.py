@@ -35,8 +35,8 @@ def main():
     ap.add_argument("--graph", action="store_true", help="forward + backward + gradient gather from one CUDA graph per rank")
     ap.add_argument("--reduce", default="flat", choices=["flat", "overlap", "deferred"])
     args = ap.parse_args()
-    if args.graph and args.reduce != "flat":
-        raise SystemExit("--graph goes with --reduce flat (the per-flow collectives are issued eagerly)")
+    if args.graph and args.reduce == "deferred":
+        raise SystemExit("--graph goes with --reduce flat or overlap")
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -59,7 +59,9 @@ def main():
     graphed = None
     if args.graph:
         from text2speech_b200.training import GraphedTrainStep
-        graphed = GraphedTrainStep(model, opt, crit, args.batch, mel.shape[1], frames, args.samples, include_optimizer=False)
+        # overlap: the per-flow NCCL all-reduces and Adam are captured with the step; flat: the graph ends after the gather
+        graphed = GraphedTrainStep(model, opt, crit, args.batch, mel.shape[1], frames, args.samples,
+                                   include_optimizer=args.reduce == "overlap")
     for it in range(args.steps + 1):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         dist.barrier()
@@ -68,7 +70,7 @@ def main():
         if graphed is not None:
             loss = graphed(mel, audio)                            # ends with the flat gradient gathered
             e[1].record()
-            scale = allreduce_gradients(opt, gathered=True)
+            scale = allreduce_gradients(opt, gathered=True) if args.reduce == "flat" else None
         else:
             opt.zero_grad()
             loss = crit(model((mel, audio)))
@@ -76,7 +78,8 @@ def main():
             e[1].record()
             scale = allreduce_gradients(opt) if args.reduce == "flat" else (opt.gather_grads(), 1.0)[1]
         e[2].record()
-        opt.step(grad_scale=scale, gathered=True)
+        if scale is not None:
+            opt.step(grad_scale=scale, gathered=True)
         e[3].record()
         torch.cuda.synchronize()
         if it > 0:                                                # first iteration = warm-up (NCCL setup, allocator)
