@@ -383,15 +383,15 @@ def secondary_configs(model, dev, rank, world, barrier, reduce_max, peak):
 def measure_train(dev, rank, world, steps, warmup, barrier, reduce_max, peak, batch=32, samples=16000):
     """Training direction (waveglow/train.py:108-124) at BASELINE.json configs[3]'s shape PER GPU: forward,
     WaveGlowLoss, backward, Adam on `batch` x `samples`-sample segments, config.json architecture in weight-norm layout.
-    One GPU: the whole step replays from one CUDA graph (GraphedTrainStep).  N > 1 (weak scaling, data parallel): eager
-    steps with apply_gradient_allreduce -- one NCCL all-reduce per flow issued while the backward of the remaining flows
-    runs (waveglow/distributed.py:90-142's contract).  `e2e` adds the H2D copy of the batch from pinned host memory and a
-    D2H read of the loss every step."""
+    One GPU: the whole step replays from one CUDA graph (GraphedTrainStep).  N > 1 (weak scaling, data parallel): the
+    graph ends after the gradient gather and is followed by one flat NCCL all-reduce and Adam (the reduction of
+    waveglow/distributed.py:90-142).  `e2e` adds the H2D copy of the batch from pinned host memory and a D2H read of the
+    loss every step."""
     import warnings
     import torch
     import text2speech_b200 as t2s
     from text2speech_b200 import synthetic as syn
-    from text2speech_b200.training import FusedAdam, GraphedTrainStep, apply_gradient_allreduce
+    from text2speech_b200.training import FusedAdam, GraphedTrainStep, allreduce_gradients
     sustained, burst, hbm = peak
     cfg = syn.load_config()
     with warnings.catch_warnings():
@@ -399,8 +399,10 @@ def measure_train(dev, rank, world, steps, warmup, barrier, reduce_max, peak, ba
         model = t2s.WaveGlow(**cfg)
     model.load_state_dict(syn.synthetic_state_dict(cfg, seed=1234, end_std=0.01, weight_norm=True))
     model = model.to(dev).train()
-    if world > 1:
-        model = apply_gradient_allreduce(model)
+    if world > 1:                             # identical start on every rank (distributed.py:99-103)
+        import torch.distributed as dist
+        for p_ in model.state_dict().values():
+            dist.broadcast(p_, 0)
     opt = FusedAdam(model.parameters(), lr=1e-4)
     crit = t2s.WaveGlowLoss(1.0)
     frames = samples // 256 + 1
@@ -409,21 +411,21 @@ def measure_train(dev, rank, world, steps, warmup, barrier, reduce_max, peak, ba
     mel_h = syn.synthetic_mel(batch, frames, seed=rank).pin_memory()
     audio, mel = audio_h.to(dev), mel_h.to(dev)
     loss_h = torch.zeros(1).pin_memory()
+    # forward, loss, backward and gradient gather replay from one CUDA graph; alone on a GPU Adam is part of it, under data
+    # parallelism the flat gradient is all-reduced (ONE NCCL call over NVLink) and Adam stepped right after the replay --
+    # the fastest of the four variants measured (profiles/r02f_*, r02g_*, r02h_*)
+    graphed = GraphedTrainStep(model, opt, crit, batch, mel.shape[1], frames, samples, include_optimizer=world == 1)
     if world == 1:
-        graphed = GraphedTrainStep(model, opt, crit, batch, mel.shape[1], frames, samples)
-
         def step(m, a):
             return graphed(m, a)
         how = "whole step (forward, loss, backward, gradient gather, Adam) replayed from one CUDA graph"
     else:
         def step(m, a):
-            opt.zero_grad()
-            loss = crit(model((m, a)))
-            loss.backward()
-            opt.step()
-            return loss.detach()
-        how = ("eager step; gradients averaged by apply_gradient_allreduce: one NCCL all-reduce per flow, overlapped with "
-               "the backward of the remaining flows")
+            loss = graphed(m, a)
+            opt.step(grad_scale=allreduce_gradients(opt, gathered=True), gathered=True)
+            return loss
+        how = ("forward + loss + backward + gradient gather replayed from one CUDA graph, then ONE flat NCCL all-reduce "
+               "(1.07 GB, waveglow/distributed.py:105-129) and the fused Adam kernel")
 
     def timed(fn):
         for _ in range(warmup):

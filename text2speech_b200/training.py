@@ -561,10 +561,9 @@ class GraphedTrainStep:
         step = GraphedTrainStep(model, optimizer, criterion, batch, n_mel, frames, samples)
         loss = step(mel, audio)            # copies the batch into the graph's static buffers, replays, returns the loss
 
-    With ``world_size > 1`` either wrap the model with ``apply_gradient_allreduce`` first (its per-flow NCCL all-reduces
-    are captured into the graph, overlapped with the backward pass exactly as in eager mode), or build the step with
-    ``include_optimizer=False``: the graph then ends after the gradient gather, and the caller runs
-    ``allreduce_gradients`` + ``optimizer.step(gathered=True)`` eagerly (two launches)."""
+    With ``world_size > 1`` build it with ``include_optimizer=False``: the graph then ends after the gradient gather,
+    and the caller runs ``allreduce_gradients`` + ``optimizer.step(gathered=True)`` eagerly (two launches) -- the
+    fastest data-parallel step measured; the eager loop uses ``apply_gradient_allreduce``."""
 
     def __init__(self, model, optimizer: FusedAdam, criterion, batch: int, n_mel: int, frames: int, samples: int,
                  include_optimizer: bool = True, warmup: int = 2):
@@ -582,11 +581,14 @@ class GraphedTrainStep:
                 self._one_step(criterion)
         torch.cuda.current_stream(dev).wait_stream(side)
         optimizer.zero_grad()
+        if getattr(model, "_dp_allreduce", None) is not None:
+            # measured on 2 x B200 (profiles/r02g_*): capturing the per-flow NCCL all-reduces into the graph is SLOWER than
+            # graph + one flat all-reduce (120.2 vs 119.2 ms: the collectives' CTAs compete with the persistent GEMM CTAs
+            # for SMs) and the process group then hangs at teardown
+            raise RuntimeError("GraphedTrainStep on a model under apply_gradient_allreduce is not supported: build it "
+                               "with include_optimizer=False and call allreduce_gradients + optimizer.step after it")
         self.graph = torch.cuda.CUDAGraph()
-        # a model under apply_gradient_allreduce issues NCCL collectives inside the step: they are captured with it;
-        # NCCL's watchdog thread polls events concurrently, which only the thread-local capture mode tolerates
-        mode = "thread_local" if getattr(model, "_dp_allreduce", None) is not None else "global"
-        with torch.cuda.graph(self.graph, capture_error_mode=mode):
+        with torch.cuda.graph(self.graph):
             self.loss = self._one_step(criterion)
         for dst, src in zip((optimizer.flat, optimizer.m, optimizer.v, optimizer.step_dev), keep):
             dst.copy_(src)

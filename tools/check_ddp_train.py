@@ -35,8 +35,9 @@ def main():
     ap.add_argument("--graph", action="store_true", help="forward + backward + gradient gather from one CUDA graph per rank")
     ap.add_argument("--reduce", default="flat", choices=["flat", "overlap", "deferred"])
     args = ap.parse_args()
-    if args.graph and args.reduce == "deferred":
-        raise SystemExit("--graph goes with --reduce flat or overlap")
+    if args.graph and args.reduce != "flat":
+        raise SystemExit("--graph goes with --reduce flat (per-flow collectives captured into the graph were measured slower "
+                         "and hang the process group at teardown: profiles/r02g_*)")
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -59,9 +60,7 @@ def main():
     graphed = None
     if args.graph:
         from text2speech_b200.training import GraphedTrainStep
-        # overlap: the per-flow NCCL all-reduces and Adam are captured with the step; flat: the graph ends after the gather
-        graphed = GraphedTrainStep(model, opt, crit, args.batch, mel.shape[1], frames, args.samples,
-                                   include_optimizer=args.reduce == "overlap")
+        graphed = GraphedTrainStep(model, opt, crit, args.batch, mel.shape[1], frames, args.samples, include_optimizer=False)
     for it in range(args.steps + 1):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         dist.barrier()
