@@ -440,7 +440,7 @@ def measure_train(dev, rank, world, steps, warmup, barrier, reduce_max, peak, ba
         return reduce_max(e0.elapsed_time(e1) / steps)
 
     losses = []
-    ms = timed(lambda: losses.append(step(mel, audio)))
+    ms = timed(lambda: losses.append(step(mel, audio).clone()))
 
     def e2e_step():
         m, a = mel_h.to(dev, non_blocking=True), audio_h.to(dev, non_blocking=True)
