@@ -279,6 +279,10 @@ WGB_API int wgb_stft_reflect_pad(const float* y, float* ypad, int batch, int N, 
 /* reflect pad + split into bf16 hi/lo parts (operands of wgb_tc_gemm_split3); ld_pad % 8 == 0. */
 WGB_API int wgb_stft_reflect_pad_split(const float* y, void* hi, void* lo, int batch, int N, int half,
                                        long long ld_pad, void* stream);
+/* the same pass with the input-range asserts of TacotronSTFT.mel_spectrogram (layers.py:72-73: min(y) >= -1, max(y) <= 1)
+ * folded in: *range_flag (device int, zeroed by the caller) is set to 1 when a sample is outside [-1, 1] or NaN. */
+WGB_API int wgb_stft_reflect_pad_split_check(const float* y, void* hi, void* lo, int batch, int N, int half,
+                                             long long ld_pad, int* range_flag, void* stream);
 /* hi = bf16(src), lo = bf16(src - hi). */
 WGB_API int wgb_split_bf16(const float* src, void* hi, void* lo, long long n, void* stream);
 /* spec[B,F,2cp] -> magnitude/phase [B,cutoff,F] (stft.py:91-97), optional channels-last mag_cl[B,F,cp];

@@ -78,7 +78,7 @@ int adam_step_dev(float*, const float*, float*, float*, long long, float, float,
 int logdet(const float*, float*, float*, int, cudaStream_t);
 // stft.cu
 int stft_reflect_pad(const float*, float*, int, int, int, long long, cudaStream_t);
-int stft_reflect_pad_split(const float*, void*, void*, int, int, int, long long, cudaStream_t);
+int stft_reflect_pad_split(const float*, void*, void*, int, int, int, long long, int*, cudaStream_t);
 int split_bf16(const float*, void*, void*, long long, cudaStream_t);
 int stft_polar(const float*, float*, float*, float*, int, int, int, int, cudaStream_t);
 int mel_log(const float*, float*, int, int, int, float, cudaStream_t);
@@ -283,7 +283,12 @@ WGB_API int wgb_stft_reflect_pad(const float* y, float* ypad, int batch, int N, 
 }
 WGB_API int wgb_stft_reflect_pad_split(const float* y, void* hi, void* lo, int batch, int N, int half, long long ld_pad,
                                        void* stream) {
-    return stft_reflect_pad_split(y, hi, lo, batch, N, half, ld_pad, S(stream));
+    return stft_reflect_pad_split(y, hi, lo, batch, N, half, ld_pad, nullptr, S(stream));
+}
+WGB_API int wgb_stft_reflect_pad_split_check(const float* y, void* hi, void* lo, int batch, int N, int half, long long ld_pad,
+                                             int* range_flag, void* stream) {
+    WGB_REQUIRE(range_flag, "null range_flag");
+    return stft_reflect_pad_split(y, hi, lo, batch, N, half, ld_pad, range_flag, S(stream));
 }
 WGB_API int wgb_split_bf16(const float* src, void* hi, void* lo, long long n, void* stream) {
     return split_bf16(src, hi, lo, n, S(stream));

@@ -52,9 +52,11 @@ __device__ __forceinline__ void split_store(float v, __nv_bfloat16* hi, __nv_bfl
     lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+// range_flag (optional): set to 1 when a sample lies outside [-1, 1] or is NaN -- the two device-wide reductions and host
+// syncs of TacotronSTFT.mel_spectrogram's input asserts (layers.py:72-73) folded into this pass
 __global__ void reflect_pad_split_kernel(const float* __restrict__ y, __nv_bfloat16* __restrict__ hi,
                                          __nv_bfloat16* __restrict__ lo, int N, int half, long long ld_pad,
-                                         long long total) {
+                                         long long total, int* __restrict__ range_flag) {
     const int padded = N + 2 * half;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -67,6 +69,7 @@ __global__ void reflect_pad_split_kernel(const float* __restrict__ y, __nv_bfloa
             if (s >= N) s = 2 * (N - 1) - s;
             v = y[b * N + s];
         }
+        if (range_flag && !(v >= -1.f && v <= 1.f)) *range_flag = 1;
         split_store(v, hi, lo, i);
     }
 }
@@ -75,7 +78,7 @@ __global__ void reflect_pad_split_kernel(const float* __restrict__ y, __nv_bfloa
 // reflected reads at the two edges, one 16 B store per output array
 __global__ void reflect_pad_split8_kernel(const float* __restrict__ y, __nv_bfloat16* __restrict__ hi,
                                           __nv_bfloat16* __restrict__ lo, int N, int half, long long ld_pad,
-                                          long long total8) {
+                                          long long total8, int* __restrict__ range_flag) {
     const int padded = N + 2 * half;
     const long long per_row = ld_pad >> 3;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
@@ -98,6 +101,12 @@ __global__ void reflect_pad_split8_kernel(const float* __restrict__ y, __nv_bflo
                 v[j] = p < padded ? row[sidx] : 0.f;
             }
         }
+        if (range_flag) {
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ok = ok && (v[j] >= -1.f && v[j] <= 1.f);
+            if (!ok) *range_flag = 1;
+        }
         uint32_t h[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -112,19 +121,19 @@ __global__ void reflect_pad_split8_kernel(const float* __restrict__ y, __nv_bflo
 }
 
 int stft_reflect_pad_split(const float* y, void* hi, void* lo, int batch, int N, int half, long long ld_pad,
-                           cudaStream_t stream) {
+                           int* range_flag, cudaStream_t stream) {
     WGB_REQUIRE(y && hi && lo && batch > 0 && N > half, "reflect padding needs N > filter_length/2 (N=%d)", N);
     WGB_REQUIRE(ld_pad >= N + 2 * half && ld_pad % 8 == 0, "bad padded stride");
     if (N % 4 == 0 && half % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
         const long long total8 = static_cast<long long>(batch) * (ld_pad >> 3);
         reflect_pad_split8_kernel<<<grid_for(total8, 256), 256, 0, stream>>>(
-            y, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), N, half, ld_pad, total8);
+            y, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), N, half, ld_pad, total8, range_flag);
         WGB_LAUNCH_CHECK();
         return WGB_OK;
     }
     const long long total = static_cast<long long>(batch) * ld_pad;
     reflect_pad_split_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
-        y, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), N, half, ld_pad, total);
+        y, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), N, half, ld_pad, total, range_flag);
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }

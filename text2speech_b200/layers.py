@@ -93,15 +93,25 @@ class TacotronSTFT(torch.nn.Module):
         return (tab, self._mel_tab[2]) if cached[1] else None
 
     def mel_spectrogram(self, y: torch.Tensor) -> torch.Tensor:
-        """y [B, T] in [-1, 1] (CUDA) -> log-mel [B, n_mel_channels, T // hop + 1]."""
+        """y [B, T] in [-1, 1] (CUDA) -> log-mel [B, n_mel_channels, T // hop + 1].  The reference's two input asserts
+        (layers.py:72-73: min(y) >= -1, max(y) <= 1) raise AssertionError here too; on the fused tensor-core path they are
+        one flag written by the reflect-pad pass and read once, instead of two device-wide reductions with a host sync each."""
         if not y.is_cuda:
             raise RuntimeError("TacotronSTFT.mel_spectrogram needs a CUDA tensor on a B200; there is no CPU fallback")
-        assert torch.min(y.data) >= -1                                         # layers.py:72-73
-        assert torch.max(y.data) <= 1
         with torch.cuda.device(y.device):
+            if self.fused and self.stft_fn._use_tc() and y.dtype == torch.float32:
+                flag = torch.zeros(1, device=y.device, dtype=torch.int32)
+                out = self._mel_spectrogram(y, flag)
+                if int(flag.item()) != 0:
+                    assert torch.min(y.data) >= -1                             # layers.py:72-73
+                    assert torch.max(y.data) <= 1
+                    raise AssertionError("input outside [-1, 1]")              # NaN input
+                return out
+            assert torch.min(y.data) >= -1                                     # layers.py:72-73
+            assert torch.max(y.data) <= 1
             return self._mel_spectrogram(y)
 
-    def _mel_spectrogram(self, y: torch.Tensor) -> torch.Tensor:
+    def _mel_spectrogram(self, y: torch.Tensor, range_flag=None) -> torch.Tensor:
         y = y.float().contiguous()
         b = y.shape[0]
         s = _lib.stream_ptr()
@@ -113,7 +123,9 @@ class TacotronSTFT(torch.nn.Module):
                 if table is None:
                     table = self._mel_table(y.device, cp)
             if table is not None:             # STFT GEMM with |X|, the mel filterbank and log-clamp in its epilogue
-                return self.stft_fn._mel_fused(y, table, self.n_mel_channels, 1e-5)
+                return self.stft_fn._mel_fused(y, table, self.n_mel_channels, 1e-5, range_flag)
+            if range_flag is not None:        # un-fused fallback: the flag would stay unwritten -> check the slow way
+                assert torch.min(y.data) >= -1 and torch.max(y.data) <= 1
             mag_cl, frames, cp = self.stft_fn._magnitude_cl(y)   # |X| straight from the STFT GEMM's epilogue
         else:
             spec, frames, cp = self.stft_fn._spectrum(y)

@@ -179,7 +179,7 @@ class STFT(torch.nn.Module):
                   hop, ld_pad, length, 2 * cp, frames * 2 * cp, 0, 0, s)
         return spec, frames, cp
 
-    def _padded_split(self, y: torch.Tensor, whole_hops: bool = False):
+    def _padded_split(self, y: torch.Tensor, whole_hops: bool = False, range_flag=None):
         """reflect-padded signal as bf16 hi / lo parts [B, ld_pad] (operands of the tensor-core STFT GEMMs).
         whole_hops: pitch = a whole number of hops, so that the frames of the whole batch form ONE row axis (frame r of
         utterance b = flat row b * ld_pad / hop + r) for the CTA-pair kernels."""
@@ -187,7 +187,11 @@ class STFT(torch.nn.Module):
         ld_pad = _round_up(n + self.filter_length, self.hop_length if whole_hops else 8)
         hi = torch.empty((b, ld_pad), device=y.device, dtype=torch.bfloat16)
         lo = torch.empty_like(hi)
-        _lib.call("wgb_stft_reflect_pad_split", y, hi, lo, b, n, self.filter_length // 2, ld_pad, _lib.stream_ptr())
+        if range_flag is not None:        # int32 device flag, zeroed by the caller: set when a sample is outside [-1, 1]
+            _lib.call("wgb_stft_reflect_pad_split_check", y, hi, lo, b, n, self.filter_length // 2, ld_pad, range_flag,
+                      _lib.stream_ptr())
+        else:
+            _lib.call("wgb_stft_reflect_pad_split", y, hi, lo, b, n, self.filter_length // 2, ld_pad, _lib.stream_ptr())
         return hi, lo, ld_pad
 
     def _magnitude_cl(self, y: torch.Tensor):
@@ -202,7 +206,7 @@ class STFT(torch.nn.Module):
                   self.hop_length, ld_pad, _lib.stream_ptr())
         return mag, frames, cp
 
-    def _mel_fused(self, y: torch.Tensor, mel_table: torch.Tensor, n_mel: int, clip: float) -> torch.Tensor:
+    def _mel_fused(self, y: torch.Tensor, mel_table: torch.Tensor, n_mel: int, clip: float, range_flag=None) -> torch.Tensor:
         """y [B,N] -> log-mel [B, n_mel, F] in one GEMM kernel (TacotronSTFT.mel_spectrogram, layers.py:63-79)."""
         _lib.require_b200(y.device)
         _, _, _, cp = self._packed(y.device)
@@ -210,12 +214,12 @@ class STFT(torch.nn.Module):
         frames = n // self.hop_length + 1
         out = torch.empty((b, n_mel, frames), device=y.device, dtype=torch.float32)
         if isinstance(mel_table, tuple):          # (table [L/2 + 1], n_pass): CTA-pair kernel, unpadded layout
-            hi, lo, ld_pad = self._padded_split(y, whole_hops=True)
+            hi, lo, ld_pad = self._padded_split(y, whole_hops=True, range_flag=range_flag)
             _lib.call("wgb_tc2_stft_mel", hi, lo, self._pair_pack(y.device)[0], mel_table[0], out, b, frames,
                       ld_pad // self.hop_length, self.filter_length, self.hop_length, mel_table[1], n_mel, float(clip),
                       _lib.stream_ptr())
             return out
-        hi, lo, ld_pad = self._padded_split(y)
+        hi, lo, ld_pad = self._padded_split(y, range_flag=range_flag)
         _lib.call("wgb_tc_stft_mel", hi, lo, self._paired_basis(y.device), mel_table, out, b, frames, cp,
                   self.filter_length, self.hop_length, ld_pad, n_mel, float(clip), _lib.stream_ptr())
         return out
