@@ -74,7 +74,7 @@ def train(num_gpus, rank, group_name, output_directory, epochs, learning_rate, s
           seed, checkpoint_path, waveglow_config, data_config, dist_config=None, fp16_run=False, with_tensorboard=False,
           max_iterations=None):
     """train.py:64-140.  ``max_iterations`` (extra) stops early.  ``fp16_run`` / ``with_tensorboard`` do not exist in the
-    reference under /root/reference (waveglow/train.py and config.json:2-11 have neither; they belong to later upstream
+    reference tree this package mirrors (its waveglow/train.py and config.json:2-11 have neither; they belong to later upstream
     revisions): they are accepted for config compatibility and must be False (the GEMMs already run in bf16 with fp32
     accumulation and fp32 master weights, which is what upstream's fp16_run buys with apex)."""
     if fp16_run or with_tensorboard:
