@@ -36,6 +36,10 @@ WGB_API int wgb_abi_version(void);
  * newer prototypes. */
 WGB_API const char* wgb_source_hash(void);
 WGB_API const char* wgb_last_error(void);
+/* Process-wide experiment switches for A/B measurements (tools/bench_kernels.py); results never depend on them.
+ *   "gate_l2_hint"  wgb_tc2_wn_gate_mel*: bit 0 = weight tiles loaded with L2 evict_last priority, bit 1 = h taps with
+ *                   evict_first (default 0: measured no faster, profiles/r02k_kernel_ab_l2_hint.json) */
+WGB_API int wgb_set_tuning(const char* key, int value);
 /* 0 iff `device` exists and is compute capability 10.x; selects nothing. */
 WGB_API int wgb_device_check(int device);
 

@@ -99,6 +99,8 @@ def call(name: str, *args):
                 if not a.is_contiguous():
                     raise RuntimeError(f"{name}: tensor argument must be contiguous")
                 conv.append(a.data_ptr())
+            elif isinstance(a, (str, bytes)):                     # const char* (wgb_set_tuning's key)
+                conv.append(ctypes.c_char_p(a.encode() if isinstance(a, str) else a))
             else:
                 conv.append(int(a))
         else:

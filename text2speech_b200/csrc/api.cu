@@ -95,6 +95,7 @@ static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 extern "C" {
 
 WGB_API int wgb_abi_version(void) { return WGB_ABI_VERSION; }
+WGB_API int wgb_set_tuning(const char* key, int value) { return tuning_set(key, value); }
 #ifndef WGB_SOURCE_HASH
 #define WGB_SOURCE_HASH "unknown"
 #endif

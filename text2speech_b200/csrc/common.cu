@@ -1,6 +1,7 @@
 // Error buffer, device query and CUtensorMap encoding (driver entry point resolved at run time).
 #include "common.cuh"
 
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
@@ -58,6 +59,21 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(WGB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
     return WGB_OK;
+}
+
+static std::atomic<int> g_gate_l2_hint{0};
+
+int tuning_get(const char* key) {
+    if (std::strcmp(key, "gate_l2_hint") == 0) return g_gate_l2_hint.load(std::memory_order_relaxed);
+    return 0;
+}
+int tuning_set(const char* key, int value) {
+    if (!key) return fail(WGB_ERR_ARGUMENT, "null key");
+    if (std::strcmp(key, "gate_l2_hint") == 0) {
+        g_gate_l2_hint.store(value, std::memory_order_relaxed);
+        return WGB_OK;
+    }
+    return fail(WGB_ERR_ARGUMENT, "unknown tuning key '%s'", key);
 }
 
 int sm_count() {

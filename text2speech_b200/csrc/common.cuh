@@ -44,4 +44,8 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 int sm_count();   // SMs of the current device (cached)
 
+// process-wide experiment switches (wgb_set_tuning); unknown keys read as 0
+int tuning_get(const char* key);
+int tuning_set(const char* key, int value);
+
 }  // namespace wgb

@@ -73,6 +73,8 @@ struct Params {
     int n_pass, ppi, n_chunks, dilation;
     int frames, n_fblk;           // GATE_MEL: frames per tiled sequence (one utterance, or all of them in the padded
                                   // layout), 128-frame blocks per sequence
+    int l2_hint;                  // GATE_MEL, experiment (wgb_set_tuning "gate_l2_hint"): bit 0 weights evict_last,
+                                  // bit 1 h taps evict_first
     int n_tap_chunks;             // GATE_MEL: K chunks of the in_layers part: 24 (three dilated taps of h), or 1 when the
                                   // first layer reads the pre-stacked flow state instead (x_stack, see tc2_wn_gate_mel0)
     int f_pad, f_real;            // GATE_MEL padded layout: frame pitch per utterance (> f_real: guard frames of zeros
@@ -221,7 +223,11 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                                 // frames outside [0, F) are zero-filled by TMA = the conv's zero padding.  With one tap
                                 // chunk (pre-stacked first layer) q = phase: the row itself.
                                 const int q = phase + (p.n_tap_chunks == 1 ? 0 : ((kc >> 3) - 1) * p.dilation);
-                                tma_load_4d_2sm(sa, &map_a0, bar, (kc & 7) * kBlockK, q & (kPhases - 1), t0 + (q >> 5), b);
+                                if (p.l2_hint & 2)
+                                    tma_load_4d_2sm_hint(sa, &map_a0, bar, (kc & 7) * kBlockK, q & (kPhases - 1), t0 + (q >> 5), b,
+                                                         l2_policy_evict_first());
+                                else
+                                    tma_load_4d_2sm(sa, &map_a0, bar, (kc & 7) * kBlockK, q & (kPhases - 1), t0 + (q >> 5), b);
                             } else {
                                 tma_load_3d_2sm(sa, &map_a1, bar, (kc - p.n_tap_chunks) * kBlockK, t0, b);
                             }
@@ -233,7 +239,13 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             tma_load_3d_2sm(sa, &map_a0, bar, (kc & 7) * kBlockK, t0, (kc >> 3) * p.batch + b);
                         }
                         const int w_row = pass * kBlockN + static_cast<int>(rank) * kHalfN;
-                        if (is_mel(MODE) && kc >= p.n_tap_chunks)      // phase-specific composed conditioning weight [32*1024][320]
+                        if (is_mel(MODE) && (p.l2_hint & 1)) {         // experiment: weights with L2 evict_last priority
+                            if (kc >= p.n_tap_chunks)
+                                tma_load_2d_2sm_hint(sb, &map_c, bar, (kc - p.n_tap_chunks) * kBlockK, phase * (2 * kNCh) + w_row,
+                                                     l2_policy_evict_last());
+                            else
+                                tma_load_2d_2sm_hint(sb, &map_w, bar, kc * kBlockK, w_row, l2_policy_evict_last());
+                        } else if (is_mel(MODE) && kc >= p.n_tap_chunks)      // phase-specific composed conditioning weight [32*1024][320]
                             tma_load_2d_2sm(sb, &map_c, bar, (kc - p.n_tap_chunks) * kBlockK, phase * (2 * kNCh) + w_row);
                         else if (skinny)
                             tma_load_2d_2sm(sb, &map_x, bar, kc * kBlockK, static_cast<int>(rank) * 8);
@@ -729,6 +741,7 @@ static int gate_mel_launch(const void* a_taps, int tap_channels, int n_tap_chunk
     p.tiles_per_b = p.n_fblk;                       // "tiles" = 128-frame blocks; each is visited once per phase and pass
     p.n_tiles = p.batch * p.n_fblk;
     p.n_tap_chunks = n_tap_chunks;
+    p.l2_hint = tuning_get("gate_l2_hint");
     p.n_pass = 4 * kPhases; p.ppi = 1; p.n_chunks = n_tap_chunks + kMelK / kBlockK; p.dilation = dilation;
     p.bias = bias; p.acts_out = static_cast<__nv_bfloat16*>(acts);
     WGB_REQUIRE((w_comp == nullptr) == (skip_acc == nullptr), "w_comp and skip_acc go together");

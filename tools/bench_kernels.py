@@ -144,6 +144,19 @@ def main():
         variants.append(("wgb_tc2_wn_gate_mel padded d=128", gate_flop, (2048 + 20) * steps,
                          lambda: _lib.call("wgb_tc2_wn_gate_mel", h_pad, stack_pad, fl["w_gate"][2], fl["w_mel"][2],
                                            fl["b_mel"][2], acts_all[2], b, t, fp, 128, None, None, 0, s)))
+
+        # L2 eviction-priority hints on the gate kernel's TMA loads (wgb_set_tuning "gate_l2_hint"): 1 = weights evict_last,
+        # 2 = h taps evict_first, 3 = both; d = 1 and d = 128
+        def hinted(hint, d):
+            def run():
+                _lib.call("wgb_set_tuning", "gate_l2_hint", hint)
+                _lib.call("wgb_tc2_wn_gate_mel", h_pad, stack_pad, fl["w_gate"][2], fl["w_mel"][2], fl["b_mel"][2], acts_all[2],
+                          b, t, fp, d, None, None, 0, s)
+                _lib.call("wgb_set_tuning", "gate_l2_hint", 0)
+            return run
+        for d in (1, 128):
+            for hint in (0, 1, 2, 3, 0):
+                variants.append((f"wgb_tc2_wn_gate_mel padded d={d} l2_hint={hint}", gate_flop, (2048 + 20) * steps, hinted(hint, d)))
         skip_acc = torch.zeros((4, b * t, 8), device=DEV)
         variants.append(("wgb_tc2_wn_gate_mel padded + skip acc d=128", gate_flop, (2048 + 20 + 256) * steps,
                          lambda: _lib.call("wgb_tc2_wn_gate_mel", h_pad, stack_pad, fl["w_gate"][2], fl["w_mel"][2],
