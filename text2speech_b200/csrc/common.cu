@@ -61,16 +61,21 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     return WGB_OK;
 }
 
-static std::atomic<int> g_gate_l2_hint{0};
+static std::atomic<int> g_gate_l2_hint{0}, g_res_l2_hint{0};
 
 int tuning_get(const char* key) {
     if (std::strcmp(key, "gate_l2_hint") == 0) return g_gate_l2_hint.load(std::memory_order_relaxed);
+    if (std::strcmp(key, "res_l2_hint") == 0) return g_res_l2_hint.load(std::memory_order_relaxed);
     return 0;
 }
 int tuning_set(const char* key, int value) {
     if (!key) return fail(WGB_ERR_ARGUMENT, "null key");
     if (std::strcmp(key, "gate_l2_hint") == 0) {
         g_gate_l2_hint.store(value, std::memory_order_relaxed);
+        return WGB_OK;
+    }
+    if (std::strcmp(key, "res_l2_hint") == 0) {
+        g_res_l2_hint.store(value, std::memory_order_relaxed);
         return WGB_OK;
     }
     return fail(WGB_ERR_ARGUMENT, "unknown tuning key '%s'", key);

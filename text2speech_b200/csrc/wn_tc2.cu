@@ -73,8 +73,8 @@ struct Params {
     int n_pass, ppi, n_chunks, dilation;
     int frames, n_fblk;           // GATE_MEL: frames per tiled sequence (one utterance, or all of them in the padded
                                   // layout), 128-frame blocks per sequence
-    int l2_hint;                  // GATE_MEL, experiment (wgb_set_tuning "gate_l2_hint"): bit 0 weights evict_last,
-                                  // bit 1 h taps evict_first
+    int l2_hint;                  // GATE_MEL (wgb_set_tuning "gate_l2_hint"): bit 0 weights evict_last, bit 1 h taps
+                                  // evict_first, bit 2 mel_stack evict_last, bit 3 acts stores evict_first
     int n_tap_chunks;             // GATE_MEL: K chunks of the in_layers part: 24 (three dilated taps of h), or 1 when the
                                   // first layer reads the pre-stacked flow state instead (x_stack, see tc2_wn_gate_mel0)
     int f_pad, f_real;            // GATE_MEL padded layout: frame pitch per utterance (> f_real: guard frames of zeros
@@ -229,12 +229,20 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                                 else
                                     tma_load_4d_2sm(sa, &map_a0, bar, (kc & 7) * kBlockK, q & (kPhases - 1), t0 + (q >> 5), b);
                             } else {
-                                tma_load_3d_2sm(sa, &map_a1, bar, (kc - p.n_tap_chunks) * kBlockK, t0, b);
+                                if (p.l2_hint & 4)
+                                    tma_load_3d_2sm_hint(sa, &map_a1, bar, (kc - p.n_tap_chunks) * kBlockK, t0, b, l2_policy_evict_last());
+                                else
+                                    tma_load_3d_2sm(sa, &map_a1, bar, (kc - p.n_tap_chunks) * kBlockK, t0, b);
                             }
                         } else if constexpr (MODE == RES) {
                             const int seg = kc / p.seg_chunks;
-                            tma_load_3d_2sm(sa, ((p.seg_mask >> seg) & 1) ? &map_x : &map_a0, bar,
-                                            (kc - seg * p.seg_chunks) * kBlockK, t0 + p.seg_shift0 + seg * p.seg_dshift, b);
+                            if (p.l2_hint & 2)                             // activations are read once here: evict_first
+                                tma_load_3d_2sm_hint(sa, ((p.seg_mask >> seg) & 1) ? &map_x : &map_a0, bar,
+                                                     (kc - seg * p.seg_chunks) * kBlockK, t0 + p.seg_shift0 + seg * p.seg_dshift, b,
+                                                     l2_policy_evict_first());
+                            else
+                                tma_load_3d_2sm(sa, ((p.seg_mask >> seg) & 1) ? &map_x : &map_a0, bar,
+                                                (kc - seg * p.seg_chunks) * kBlockK, t0 + p.seg_shift0 + seg * p.seg_dshift, b);
                         } else {
                             tma_load_3d_2sm(sa, &map_a0, bar, (kc & 7) * kBlockK, t0, (kc >> 3) * p.batch + b);
                         }
@@ -249,6 +257,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             tma_load_2d_2sm(sb, &map_c, bar, (kc - p.n_tap_chunks) * kBlockK, phase * (2 * kNCh) + w_row);
                         else if (skinny)
                             tma_load_2d_2sm(sb, &map_x, bar, kc * kBlockK, static_cast<int>(rank) * 8);
+                        else if (MODE == RES && (p.l2_hint & 1))       // residual weights (512 KB) with evict_last priority
+                            tma_load_2d_2sm_hint(sb, &map_w, bar, kc * kBlockK, w_row, l2_policy_evict_last());
                         else
                             tma_load_2d_2sm(sb, &map_w, bar, kc * kBlockK, w_row);
                         if (++s == kStages) { s = 0; ph ^= 1; }
@@ -443,9 +453,17 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                         }
                         if (live) {
                             uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
+                            if (is_mel(MODE) && (p.l2_hint & 8)) {           // experiment: streaming stores (evict_first)
+                                const uint64_t pol = l2_policy_evict_first();
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                                for (int j = 0; j < 4; ++j)
+                                    st_global_v4_hint(d4 + j, make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2],
+                                                                         packed[4 * j + 3]), pol);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                            }
                         }
                         if constexpr (MODE == GATE) {
                             if (p.ts_out != nullptr && live) {     // training forward: keep tanh and sigmoid for the backward
@@ -802,6 +820,7 @@ int tc2_wn_res(const void* acts, const void* w_res, const float* bias, const voi
     Params p{};
     if (int e = fill_common(p, batch, T)) return e;
     p.n_pass = skip_acc ? 3 : 2; p.ppi = 1; p.n_chunks = kNCh / kBlockK;
+    p.l2_hint = tuning_get("res_l2_hint");
     p.seg_chunks = p.n_chunks;
     p.bias = bias;
     p.skip_acc = skip_acc; p.skip_first = skip_first;

@@ -86,6 +86,8 @@ def main():
     ap.add_argument("--frames", type=int, default=860)
     ap.add_argument("--seconds", type=float, default=1.5)
     ap.add_argument("--only", default="")
+    ap.add_argument("--hints", default="", help="comma list of gate_l2_hint values to A/B (default: 0,1,2,3,0 at d = 1 and 128)")
+    ap.add_argument("--hint-dilation", type=int, default=8)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernels.json"))
     args = ap.parse_args()
     b, t = args.batch, args.frames * 32
@@ -110,6 +112,14 @@ def main():
         variants.append((name, res_flop, 3072 * steps,
                          lambda name=name: _lib.call(name, acts_all[2], fl["w_res"][2], fl["b_res"][2], h0, h1, b, t,
                                                      *((t, None, None, 0) if name == "wgb_tc2_wn_res" else ()), s)))
+    def res_hinted(hint):
+        def run():
+            _lib.call("wgb_set_tuning", "res_l2_hint", hint)
+            _lib.call("wgb_tc2_wn_res", acts_all[2], fl["w_res"][2], fl["b_res"][2], h0, h1, b, t, t, None, None, 0, s)
+            _lib.call("wgb_set_tuning", "res_l2_hint", 0)
+        return run
+    for hint in (0, 1, 2, 3, 0):
+        variants.append((f"wgb_tc2_wn_res l2_hint={hint}", res_flop, 3072 * steps, res_hinted(hint)))
     skip_row = torch.zeros((b * t, 8), device=DEV)
     variants.append(("wgb_tc2_wn_res + skip pass", res_flop, 3136 * steps,
                      lambda: _lib.call("wgb_tc2_wn_res", acts_all[2], fl["w_res"][2], fl["b_res"][2], h0, h1, b, t, t,
@@ -154,8 +164,8 @@ def main():
                           b, t, fp, d, None, None, 0, s)
                 _lib.call("wgb_set_tuning", "gate_l2_hint", 0)
             return run
-        for d in (1, 128):
-            for hint in (0, 1, 2, 3, 0):
+        for d in (1, 128) if not args.hints else (args.hint_dilation,):
+            for hint in (0, 1, 2, 3, 0) if not args.hints else [int(v) for v in args.hints.split(",")]:
                 variants.append((f"wgb_tc2_wn_gate_mel padded d={d} l2_hint={hint}", gate_flop, (2048 + 20) * steps, hinted(hint, d)))
         skip_acc = torch.zeros((4, b * t, 8), device=DEV)
         variants.append(("wgb_tc2_wn_gate_mel padded + skip acc d=128", gate_flop, (2048 + 20 + 256) * steps,
