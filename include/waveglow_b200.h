@@ -36,9 +36,14 @@ WGB_API int wgb_abi_version(void);
  * newer prototypes. */
 WGB_API const char* wgb_source_hash(void);
 WGB_API const char* wgb_last_error(void);
-/* Process-wide experiment switches for A/B measurements (tools/bench_kernels.py); results never depend on them.
- *   "gate_l2_hint"  wgb_tc2_wn_gate_mel*: bit 0 = weight tiles loaded with L2 evict_last priority, bit 1 = h taps with
- *                   evict_first (default 0: measured no faster, profiles/r02k_kernel_ab_l2_hint.json) */
+/* Process-wide tuning switches, A/B-measured with tools/bench_kernels.py; results never depend on them.
+ *   "gate_l2_hint"  gate kernels (wgb_tc2_wn_gate, wgb_tc2_wn_gate_mel*): bit 0 = weight tiles TMA-loaded with L2
+ *                   evict_last priority (DEFAULT 1: 5.27 vs 5.58 ms per launch at 64 x 10 s, the weights no longer lose
+ *                   their L2 lines to the activations streaming through; profiles/r02k_l2_hint_ab.json), bit 1 = h taps
+ *                   with evict_first (slower: 6.0 ms), bit 2 = mel_stack evict_last, bit 3 = acts stores evict_first
+ *   "res_l2_hint"   wgb_tc2_wn_res*: bit 0 = weights evict_last, bit 1 = activations evict_first (default 0: 1.20 ms
+ *                   either way for bit 0, 1.26 ms with bit 1)
+ *   "stft_l2_hint"  wgb_tc2_stft_* / wgb_tc2_istft_ola / wgb_tc2_gemm_split3: bit 0 = basis tiles evict_last */
 WGB_API int wgb_set_tuning(const char* key, int value);
 /* 0 iff `device` exists and is compute capability 10.x; selects nothing. */
 WGB_API int wgb_device_check(int device);

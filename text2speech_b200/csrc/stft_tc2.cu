@@ -64,6 +64,7 @@ struct Smem {
 
 struct Params {
     int n_tiles;                  // 128-row tiles over the flat row axis
+    int l2_hint;                  // wgb_set_tuning "stft_l2_hint": bit 0 = basis tiles evict_last
     int rows_total;               // flat rows
     int R, frames;                // flat row = b R + r; it is a real row iff r < frames (R == frames: compact rows);
                                   // outputs are indexed by the compact row b frames + r
@@ -189,7 +190,11 @@ stft_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                         const int rem = kc - tap * 3 * p.seg_chunks;
                         const int seg = rem / p.seg_chunks;                    // 0: A_hi, 1: A_lo, 2: A_hi
                         tma_load_2d_2sm(sa, seg == 1 ? &map_lo : &map_hi, bar, (rem - seg * p.seg_chunks) * kBlockK, t0 - tap);
-                        tma_load_2d_2sm(sb, &map_w, bar, kc * kBlockK, pass * kBlockN + static_cast<int>(rank) * kHalfN);
+                        if (p.l2_hint & 1)          // basis tiles (6 MB, re-read by every pair) with evict_last priority
+                            tma_load_2d_2sm_hint(sb, &map_w, bar, kc * kBlockK, pass * kBlockN + static_cast<int>(rank) * kHalfN,
+                                                 l2_policy_evict_last());
+                        else
+                            tma_load_2d_2sm(sb, &map_w, bar, kc * kBlockK, pass * kBlockN + static_cast<int>(rank) * kHalfN);
                         if (++s == kStages) { s = 0; ph ^= 1; }
                     }
                 }
@@ -490,6 +495,7 @@ int tc2_stft_mel(const void* a_hi, const void* a_lo, const void* w3_paired, cons
     WGB_REQUIRE(L / 2 <= kMaxBins, "filter_length (%d) above %d: use the one-CTA kernel", L, 2 * kMaxBins);
     WGB_REQUIRE(n_mel >= 1, "n_mel (%d) must be positive", n_mel);
     Params p{};
+    p.l2_hint = tuning_get("stft_l2_hint");
     CUtensorMap mhi, mlo, mw;
     if (int e = frame_maps(&mhi, &mlo, p, a_hi, a_lo, batch, frames, R, L, hop)) return e;
     WGB_REQUIRE(n_pass >= 1 && n_pass <= L / kBlockN, "n_pass (%d) must be in 1..%d", n_pass, L / kBlockN);
@@ -507,6 +513,7 @@ int tc2_stft_denoise(const void* a_hi, const void* a_lo, const void* w3_paired, 
     WGB_REQUIRE(w3_paired && bias_spec && hi_out && lo_out, "null pointer");
     WGB_REQUIRE(L / 2 <= kMaxBins, "filter_length (%d) above %d: use the one-CTA kernel", L, 2 * kMaxBins);
     Params p{};
+    p.l2_hint = tuning_get("stft_l2_hint");
     CUtensorMap mhi, mlo, mw;
     if (int e = frame_maps(&mhi, &mlo, p, a_hi, a_lo, batch, frames, R, L, hop)) return e;
     WGB_REQUIRE(out_R >= frames, "out_R (%d) must be >= frames (%d)", out_R, frames);
@@ -526,6 +533,7 @@ int tc2_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, float* c
     WGB_REQUIRE(rows > 0 && rows < (1ll << 31) - 1024, "bad row count");
     WGB_REQUIRE(N > 0 && N % kBlockN == 0 && K > 0 && K % kBlockK == 0, "N must be a multiple of 256 and K of 64 (N=%d K=%d)", N, K);
     Params p{};
+    p.l2_hint = tuning_get("stft_l2_hint");
     p.rows_total = static_cast<int>(rows);
     p.n_tiles = ceil_div(p.rows_total, kBlockM);
     p.R = p.rows_total; p.frames = p.rows_total;          // compact rows
@@ -557,6 +565,7 @@ int tc2_istft_ola(const void* s_hi, const void* s_lo, const void* w_ola, const f
     const long long rows = static_cast<long long>(batch) * (frames + taps - 1);
     WGB_REQUIRE(rows < (1ll << 31) - 1024, "too many frames");
     Params p{};
+    p.l2_hint = tuning_get("stft_l2_hint");
     p.rows_total = static_cast<int>(rows);
     p.n_tiles = ceil_div(p.rows_total, kBlockM);
     p.R = frames + taps - 1; p.frames = frames;

@@ -73,8 +73,9 @@ struct Params {
     int n_pass, ppi, n_chunks, dilation;
     int frames, n_fblk;           // GATE_MEL: frames per tiled sequence (one utterance, or all of them in the padded
                                   // layout), 128-frame blocks per sequence
-    int l2_hint;                  // GATE_MEL (wgb_set_tuning "gate_l2_hint"): bit 0 weights evict_last, bit 1 h taps
-                                  // evict_first, bit 2 mel_stack evict_last, bit 3 acts stores evict_first
+    int l2_hint;                  // wgb_set_tuning "gate_l2_hint" / "res_l2_hint": bit 0 weights evict_last (all modes);
+                                  // GATE_MEL bit 1 h taps evict_first, bit 2 mel_stack evict_last, bit 3 acts stores
+                                  // evict_first; RES bit 1 activations evict_first
     int n_tap_chunks;             // GATE_MEL: K chunks of the in_layers part: 24 (three dilated taps of h), or 1 when the
                                   // first layer reads the pre-stacked flow state instead (x_stack, see tc2_wn_gate_mel0)
     int f_pad, f_real;            // GATE_MEL padded layout: frame pitch per utterance (> f_real: guard frames of zeros
@@ -247,20 +248,22 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             tma_load_3d_2sm(sa, &map_a0, bar, (kc & 7) * kBlockK, t0, (kc >> 3) * p.batch + b);
                         }
                         const int w_row = pass * kBlockN + static_cast<int>(rank) * kHalfN;
-                        if (is_mel(MODE) && (p.l2_hint & 1)) {         // experiment: weights with L2 evict_last priority
-                            if (kc >= p.n_tap_chunks)
+                        // weight tiles are re-read by every CTA pair for the whole launch while activations stream through
+                        // L2 once: bit 0 of l2_hint gives them evict_last priority (measured: profiles/r02k_l2_hint_ab.json)
+                        const bool w_last = (p.l2_hint & 1) != 0;
+                        if (is_mel(MODE) && kc >= p.n_tap_chunks) {     // phase-specific composed conditioning weight [32*1024][320]
+                            if (w_last)
                                 tma_load_2d_2sm_hint(sb, &map_c, bar, (kc - p.n_tap_chunks) * kBlockK, phase * (2 * kNCh) + w_row,
                                                      l2_policy_evict_last());
                             else
-                                tma_load_2d_2sm_hint(sb, &map_w, bar, kc * kBlockK, w_row, l2_policy_evict_last());
-                        } else if (is_mel(MODE) && kc >= p.n_tap_chunks)      // phase-specific composed conditioning weight [32*1024][320]
-                            tma_load_2d_2sm(sb, &map_c, bar, (kc - p.n_tap_chunks) * kBlockK, phase * (2 * kNCh) + w_row);
-                        else if (skinny)
+                                tma_load_2d_2sm(sb, &map_c, bar, (kc - p.n_tap_chunks) * kBlockK, phase * (2 * kNCh) + w_row);
+                        } else if (skinny) {
                             tma_load_2d_2sm(sb, &map_x, bar, kc * kBlockK, static_cast<int>(rank) * 8);
-                        else if (MODE == RES && (p.l2_hint & 1))       // residual weights (512 KB) with evict_last priority
+                        } else if (w_last) {
                             tma_load_2d_2sm_hint(sb, &map_w, bar, kc * kBlockK, w_row, l2_policy_evict_last());
-                        else
+                        } else {
                             tma_load_2d_2sm(sb, &map_w, bar, kc * kBlockK, w_row);
+                        }
                         if (++s == kStages) { s = 0; ph ^= 1; }
                     }
                 }
@@ -722,6 +725,7 @@ int tc2_wn_gate(const void* h, const void* cond, const void* w_packed, const flo
     Params p{};
     if (int e = fill_common(p, batch, T)) return e;
     p.n_pass = 4; p.ppi = 1; p.n_chunks = (3 * kNCh + kNCond) / kBlockK; p.dilation = dilation;
+    p.l2_hint = tuning_get("gate_l2_hint") & 1;
     p.bias = bias; p.acts_out = static_cast<__nv_bfloat16*>(acts); p.ts_out = static_cast<__nv_bfloat16*>(ts);
     CUtensorMap mh, mc, mw;
     if (int e = act_map(&mh, h, kNCh, T, batch)) return e;
@@ -854,6 +858,7 @@ int tc2_wn_res_seg(const void* a0, const void* a1, int n_seg, int seg_mask, cons
     Params p{};
     if (int e = fill_common(p, batch, T)) return e;
     p.n_pass = 2; p.ppi = 1; p.n_chunks = n_seg * C / kBlockK;
+    p.l2_hint = tuning_get("res_l2_hint");
     p.seg_chunks = C / kBlockK; p.seg_shift0 = shift0; p.seg_dshift = dshift; p.seg_mask = seg_mask;
     p.bias = bias;
     CUtensorMap ma, ma1, mhi, mho, mw;

@@ -112,6 +112,15 @@ def main():
         variants.append((name, res_flop, 3072 * steps,
                          lambda name=name: _lib.call(name, acts_all[2], fl["w_res"][2], fl["b_res"][2], h0, h1, b, t,
                                                      *((t, None, None, 0) if name == "wgb_tc2_wn_res" else ()), s)))
+    def gate_hinted(hint, d):
+        def run():
+            _lib.call("wgb_set_tuning", "gate_l2_hint", hint)
+            _lib.call("wgb_tc2_wn_gate", h0, cond, fl["w_gate"][2], fl["b_gate"][2], acts_all[2], b, t, d, s)
+            _lib.call("wgb_set_tuning", "gate_l2_hint", 1)
+        return run
+    for hint in (0, 1, 0, 1):
+        variants.append((f"wgb_tc2_wn_gate d=8 l2_hint={hint}", gate_flop, 3328 * steps, gate_hinted(hint, 8)))
+
     def res_hinted(hint):
         def run():
             _lib.call("wgb_set_tuning", "res_l2_hint", hint)
@@ -162,7 +171,7 @@ def main():
                 _lib.call("wgb_set_tuning", "gate_l2_hint", hint)
                 _lib.call("wgb_tc2_wn_gate_mel", h_pad, stack_pad, fl["w_gate"][2], fl["w_mel"][2], fl["b_mel"][2], acts_all[2],
                           b, t, fp, d, None, None, 0, s)
-                _lib.call("wgb_set_tuning", "gate_l2_hint", 0)
+                _lib.call("wgb_set_tuning", "gate_l2_hint", 1)
             return run
         for d in (1, 128) if not args.hints else (args.hint_dilation,):
             for hint in (0, 1, 2, 3, 0) if not args.hints else [int(v) for v in args.hints.split(",")]:

@@ -25,6 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "stft_ab.json"))
     ap.add_argument("--once", default="")
+    ap.add_argument("--l2-hints", default="", help="comma list of stft_l2_hint values to A/B on the CTA-pair kernels instead")
     args = ap.parse_args()
     cfg = syn.load_config()
     model = t2s.WaveGlow.remove_weightnorm(t2s.WaveGlow(**cfg))
@@ -42,6 +43,19 @@ def main():
         torch.cuda.synchronize()
         return
     out = {}
+    if args.l2_hints:
+        from text2speech_b200 import _lib
+        for i, hint in enumerate(int(v) for v in args.l2_hints.split(",")):
+            _lib.call("wgb_set_tuning", "stft_l2_hint", hint)
+            rec = {"stft_l2_hint": hint}
+            rec["mel_ms"], _ = timeit(lambda: taco._mel_spectrogram(y), warmup=3, iters=20)
+            rec["denoiser_ms"], _ = timeit(lambda: den(y, 0.01), warmup=3, iters=20)
+            out[f"run{i}_hint{hint}"] = rec
+            print(json.dumps(rec), flush=True)
+        _lib.call("wgb_set_tuning", "stft_l2_hint", 0)
+        with open(args.out, "w") as f:
+            json.dump(out, f, indent=1)
+        return
     for name, pair, fused in (("pair", True, True), ("pair_separate_overlap_add", True, False), ("one_cta", False, False)):
         taco.stft_fn.pair = den.stft.pair = pair
         den.stft.fused_ola = fused
