@@ -242,6 +242,31 @@ WGB_API int wgb_tc2_gemm_split3(const void* a_hi, const void* a_lo, const void* 
 WGB_API int wgb_tc2_istft_ola(const void* s_hi, const void* s_lo, const void* w_ola, const float* env_tab, float* out,
                               int batch, int frames, int L, int hop, void* stream);
 
+/* ---------------------------------------------------------------- butterfly STFT (stock bases, filter_length 1024)
+ * The reference's forward_basis is window * [cos; -sin](2 pi k n / L) and inverse_basis its pseudo-inverse times the window
+ * (stft.py:46-60): a real DFT pair.  For those bases the two fused paths below compute the same thing as 1024-point real
+ * FFTs in fp32 (one warp per frame, 512-point complex FFT in registers + one shared-memory exchange buffer): 0.05 MFLOP per
+ * frame instead of the 2.1 MFLOP dense contraction, the signal read once from HBM and only the result written.  The host
+ * (stft.py / layers.py) takes these paths only when the module's basis buffers still equal the constructor's.
+ *
+ * TacotronSTFT.mel_spectrogram (layers.py:63-79; stft.py:79-97): y fp32 [B][n] -> out fp32 [B][n_mel][n / hop + 1] =
+ * log(clamp(mel_basis |STFT(y)|, clip)).  window fp32 [1024] (zero-padded window, ones for window=None).  The filterbank
+ * arrives as bands: mel_w = the rows of mel_basis over their non-zero spans, packed; mel_parts int32
+ * [32][parts_per_lane][4] = {first bin, number of bins, offset into mel_w, filter} lists, per lane of a warp, the pieces of
+ * rows that lane sums (count 0 = unused slot).  Every filter is covered by at most TWO pieces, so the two shared-memory
+ * adds that rebuild it commute: results are independent of scheduling.  range_flag (optional int32) is set to 1 when a
+ * sample is outside [-1, 1] or NaN (layers.py:72-73).  n > 512, n_mel <= 128, parts_per_lane <= 16, mel_w_total <= 4096. */
+WGB_API int wgb_fft_stft_mel(const float* y, const float* window, const void* mel_parts, int parts_per_lane,
+                             const float* mel_w, int mel_w_total, float* out, int batch, int n, int hop, int n_mel,
+                             float clip, int* range_flag, void* stream);
+/* Denoiser.forward (denoiser.py:35-40) = STFT.transform, clamp(|X| - bias_spec * strength, 0) with the phase kept,
+ * STFT.inverse (stft.py:99-130: overlap-add, window-sum normalisation, L/hop scale, L/2 trim) in ONE kernel: a warp walks a
+ * run of consecutive frames and holds the overlap-add in registers.  y fp32 [B][n]; bias_spec fp32 [513]; env_tab fp32
+ * [16][hop] as for wgb_tc2_istft_ola (NULL for window=None: no normalisation and no scale); out fp32 [B][hop * (n / hop)].
+ * hop must be 256 (= L / 4, the Denoiser's n_overlap = 4). */
+WGB_API int wgb_fft_denoise(const float* y, const float* window, const float* bias_spec, float strength,
+                            const float* env_tab, float* out, int batch, int n, int hop, void* stream);
+
 /* ---------------------------------------------------------------- FP32 validation path (CUDA cores) */
 
 /* C[b][m][n] (+)= sum_k A[b][m+shift][k] W[n][k] + bias[n]; rows outside [0,M) read as zero, so a

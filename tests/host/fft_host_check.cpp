@@ -9,15 +9,14 @@
 using namespace wgb::fft;
 
 static void fft512_warp(cf v[32][16]) {
-    static cf buf[kBufElems];
+    static cf buf_a[kBufA], buf_b[kBufB];
     LaneTw tw[32];
-    cf w[32][16];
     for (int l = 0; l < 32; ++l) lane_twiddles(l, tw[l]);
-    for (int l = 0; l < 32; ++l) stage1(l, tw[l], v[l], buf);
-    for (int l = 0; l < 32; ++l) stage2_load(l, tw[l], w[l], buf);
-    for (int i = 0; i < kBufElems; ++i) buf[i] = cf{NAN, NAN};      // every element stage 3 reads must be rewritten
-    for (int l = 0; l < 32; ++l) stage2_store(l, w[l], buf);
-    for (int l = 0; l < 32; ++l) stage3(l, v[l], buf);
+    for (int i = 0; i < kBufA; ++i) buf_a[i] = cf{NAN, NAN};        // every element a later stage reads must be written
+    for (int i = 0; i < kBufB; ++i) buf_b[i] = cf{NAN, NAN};
+    for (int l = 0; l < 32; ++l) stage1(l, tw[l], v[l], buf_a);
+    for (int l = 0; l < 32; ++l) stage2(l, tw[l], buf_a, buf_b);
+    for (int l = 0; l < 32; ++l) stage3(l, v[l], buf_b);
 }
 
 int main() {

@@ -558,21 +558,28 @@ def test_infer_shape_sweep_all_paths_agree(models, B, F):
 
 @pytest.mark.parametrize("n", [513, 1000, 4096 + 17, 22050])
 def test_stft_mel_denoiser_length_sweep(models, lib, n):
-    """Lengths that are not multiples of the hop: tensor-core STFT paths against the FP32 CUDA-core paths."""
+    """Lengths that are not multiples of the hop (odd ones too): the butterfly path (default) and the tensor-core
+    dense-basis path against the FP32 CUDA-core path."""
     import text2speech_b200 as t2s
     y = syn.synthetic_waveforms(3, n, sr=22050, seed=n).to(DEV)
     taco = t2s.TacotronSTFT(1024, 256, 1024, 80, 22050, 0.0, 8000.0).to(DEV)
     a = taco.mel_spectrogram(y)
+    taco.stft_fn.algorithm = "gemm"
+    g = taco.mel_spectrogram(y)
     taco.stft_fn.precision = "fp32"
     b = taco.mel_spectrogram(y)
-    assert a.shape == b.shape == (3, 80, n // 256 + 1) and float((a - b).abs().max()) <= 1e-3
+    assert a.shape == g.shape == b.shape == (3, 80, n // 256 + 1)
+    assert float((a - b).abs().max()) <= 1e-3 and float((g - b).abs().max()) <= 1e-3
     m = models["bench"]
     m.mode = "bf16"
     den = t2s.Denoiser(m)
+    d_fft = den(y, 0.05)
+    den.stft.algorithm = "gemm"
     d_tc = den(y, 0.05)
     den.stft.precision = "fp32"
     d_32 = den(y, 0.05)
-    assert d_tc.shape == d_32.shape == (3, 1, 256 * (n // 256)) and util.rel_l2(d_tc.cpu(), d_32.cpu()) <= 1e-4
+    assert d_fft.shape == d_tc.shape == d_32.shape == (3, 1, 256 * (n // 256))
+    assert util.rel_l2(d_tc.cpu(), d_32.cpu()) <= 1e-4 and util.rel_l2(d_fft.cpu(), d_32.cpu()) <= 1e-4
 
 
 def test_first_layer_fold_agrees(models, golden, monkeypatch):
@@ -845,12 +852,14 @@ def test_stft_pair_kernels_against_one_cta_kernels_and_oracle(models, lib):
     m = models["bench"]
     m.mode = "fp32"
     den = t2s.Denoiser(m)
+    den.stft.algorithm = "gemm"
     m.mode = "bf16"
     fwd, inv = oracle.stft_bases(1024, 256, 1024)
     # 11025 = sr / 2: the Nyquist bin carries mel weight, 4 passes; 44800 (the class default, layers.py:44): filters
     # narrower than a bin at the low end, so the table's filter index steps by two
     for sr, fmax in ((22050, 8000.0), (22050, 11025.0), (44800, 8000.0)):
         taco = t2s.TacotronSTFT(1024, 256, 1024, 80, sr, 0.0, fmax).to(DEV)
+        taco.stft_fn.algorithm = "gemm"
         assert taco._mel_table_pair(torch.device(DEV)) is not None
         mb = torch.from_numpy(oracle.mel_filterbank(sr, 1024, 80, 0.0, fmax)).float()
         for B, n in ((1, 1024), (3, 256 * 37 + 19), (5, 22050)):
@@ -878,6 +887,111 @@ def test_stft_pair_kernels_against_one_cta_kernels_and_oracle(models, lib):
             assert a.shape == b.shape == c.shape == want.shape
             assert util.snr_db(a.cpu(), want) >= 80.0 and util.snr_db(a.cpu(), b.cpu()) >= 80.0, (B, n, strength)
             assert util.snr_db(c.cpu(), want) >= 80.0 and util.snr_db(a.cpu(), c.cpu()) >= 100.0, (B, n, strength)
+
+
+def test_fft_stft_kernels_against_oracle(models, lib):
+    """The butterfly kernels (csrc/fft.cu: wgb_fft_stft_mel, wgb_fft_denoise) against the CPU oracle's conv-basis STFT and
+    against the tensor-core dense-basis kernels: signals shorter than one filter (every frame reflect-padded), odd and
+    ragged lengths, several utterances (tile / run boundaries inside an utterance at 300+ frames), three filterbanks
+    (fmax = sr / 2 puts weight on the Nyquist bin), strengths 0 / 0.1 / huge (every bin clamped to zero)."""
+    import text2speech_b200 as t2s
+    m = models["bench"]
+    m.mode = "fp32"
+    den = t2s.Denoiser(m)
+    m.mode = "bf16"
+    assert den.stft._fft_pack(torch.device(DEV)) is not None
+    fwd, inv = oracle.stft_bases(1024, 256, 1024)
+    shapes = ((1, 513), (1, 1024), (2, 1531), (3, 256 * 37 + 19), (5, 22050), (2, 256 * 331 + 255))
+    for sr, fmax in ((22050, 8000.0), (22050, 11025.0), (44800, 8000.0)):
+        taco = t2s.TacotronSTFT(1024, 256, 1024, 80, sr, 0.0, fmax).to(DEV)
+        mb = torch.from_numpy(oracle.mel_filterbank(sr, 1024, 80, 0.0, fmax)).float()
+        for B, n in shapes:
+            y = syn.synthetic_waveforms(B, n, sr=22050, seed=B + n)
+            want = oracle.mel_spectrogram(y, fwd, mb, 256)
+            calls = []
+            raw = lib.call
+            lib.call = lambda name, *a: (calls.append(name), raw(name, *a))[1]
+            try:
+                a = taco.mel_spectrogram(y.to(DEV))
+            finally:
+                lib.call = raw
+            assert calls == ["wgb_fft_stft_mel"], calls
+            taco.stft_fn.algorithm = "gemm"
+            g = taco.mel_spectrogram(y.to(DEV))
+            taco.stft_fn.algorithm = "auto"
+            assert a.shape == want.shape
+            assert float((a.cpu() - want).abs().max()) <= 1e-3, (sr, fmax, B, n)      # log of quiet bins (the golden test's bound)
+            assert util.rel_l2(a.cpu(), want) <= 5e-6, (sr, fmax, B, n)
+            assert float((a - g).abs().max()) <= 2e-3, (sr, fmax, B, n)             # each within 1e-3 of the oracle
+    for B, n in shapes:
+        y = syn.synthetic_waveforms(B, n, sr=22050, seed=B + n)
+        for strength in (0.0, 0.1, 1e6):
+            want = oracle.denoise(y, den.bias_spec.cpu(), strength, fwd, inv, 256, 1024)
+            a = den(y.to(DEV), strength)
+            den.stft.algorithm = "gemm"
+            g = den(y.to(DEV), strength)
+            den.stft.algorithm = "auto"
+            assert a.shape == g.shape == want.shape
+            if strength > 1e3:
+                assert float(a.abs().max()) <= 1e-6 and float(want.abs().max()) <= 1e-6
+                continue
+            assert util.snr_db(a.cpu(), want) >= 100.0, (B, n, strength, util.snr_db(a.cpu(), want))
+            assert util.snr_db(a.cpu(), g.cpu()) >= 80.0, (B, n, strength)
+
+
+def test_fft_stft_other_windows_and_hops(lib):
+    """Butterfly mel kernel at hops other than L / 4 (incl. one that is not a multiple of 8) and with win_length <
+    filter_length; butterfly denoiser with window=None (no envelope division, no L / hop scale: stft.py:111-125)."""
+    import text2speech_b200 as t2s
+    y = syn.synthetic_waveforms(2, 9000, sr=22050, seed=3)
+    for hop, win_length in ((256, 800), (200, 1024), (300, 1024), (512, 1024)):
+        taco = t2s.TacotronSTFT(1024, hop, win_length, 80, 22050, 0.0, 8000.0).to(DEV)
+        assert taco.stft_fn._fft_pack(torch.device(DEV)) is not None
+        fwd, _ = oracle.stft_bases(1024, hop, win_length)
+        mb = torch.from_numpy(oracle.mel_filterbank(22050, 1024, 80, 0.0, 8000.0)).float()
+        want = oracle.mel_spectrogram(y, fwd, mb, hop)
+        got = taco.mel_spectrogram(y.to(DEV))
+        assert got.shape == want.shape and float((got.cpu() - want).abs().max()) <= 1e-3, (hop, win_length)
+        assert util.rel_l2(got.cpu(), want) <= 5e-6, (hop, win_length)
+    bias = torch.rand(513) * 0.05
+    for window, win_length in (("hann", 1024), ("hann", 800), (None, 1024)):
+        stft = t2s.STFT(1024, 256, win_length, window=window).to(DEV)
+        fwd, inv = oracle.stft_bases(1024, 256, win_length, window=window)
+        mag, phase = oracle.stft_transform(y, fwd, 256)
+        want = oracle.stft_inverse(torch.clamp(mag - bias.reshape(1, 513, 1) * 0.5, 0.0), phase, inv, 256, win_length,
+                                   window=window)
+        got = stft._denoised_fft(y.to(DEV), bias.to(DEV), 0.5)
+        assert got is not None and got.shape == want.shape
+        assert util.snr_db(got.cpu(), want) >= 100.0, (window, win_length, util.snr_db(got.cpu(), want))
+
+
+def test_fft_stft_range_flag_and_edited_bases(lib):
+    """layers.py:72-73 on the butterfly path: one sample outside [-1, 1] anywhere (first, last, around hop boundaries, in the
+    tail that only the last frame covers) or a NaN raises AssertionError; in-range input does not.  A forward_basis that is no
+    longer the constructor's sends the call to the dense-basis kernels, which honour the edit."""
+    import text2speech_b200 as t2s
+    taco = t2s.TacotronSTFT(1024, 256, 1024, 80, 22050, 0.0, 8000.0).to(DEV)
+    n = 256 * 9 + 200
+    y = (syn.synthetic_waveforms(2, n, sr=22050, seed=4) * 0.5).to(DEV)
+    taco.mel_spectrogram(y)
+    for b, pos, val in ((0, 0, 1.5), (1, n - 1, -1.5), (0, 127, 1.01), (1, 128, 1.01), (0, 256 * 4 + 129, -2.0),
+                        (1, 256 * 9 + 199, 3.0), (0, 256 * 9 + 1, float("nan")), (1, 700, float("inf"))):
+        bad = y.clone()
+        bad[b, pos] = val
+        with pytest.raises(AssertionError):
+            taco.mel_spectrogram(bad)
+    edge = y.clone()
+    edge[0, 5], edge[1, n - 3] = 1.0, -1.0                              # the closed interval is allowed
+    taco.mel_spectrogram(edge)
+    ref = taco.mel_spectrogram(y)
+    with torch.no_grad():
+        taco.stft_fn.forward_basis[3] *= 2.0                            # bin 3 twice as loud
+    assert taco.stft_fn._fft_pack(torch.device(DEV)) is None
+    louder = taco.mel_spectrogram(y)
+    assert float((louder - ref).abs().max()) > 1e-2
+    taco.stft_fn.algorithm = "fft"
+    with pytest.raises(RuntimeError):
+        taco.mel_spectrogram(y)
 
 
 @pytest.mark.parametrize("precision", ["tc", "fp32"])
@@ -1001,11 +1115,14 @@ def cfg5_waves():
     return syn.synthetic_waveforms(256, 220160, sr=DC["sampling_rate"], seed=5)
 
 
-def test_cfg5_mel_spectrogram_full_size_against_oracle(lib, cfg5_waves):
-    """TacotronSTFT.mel_spectrogram on all 256 x 10 s waveforms in one call; utterances are independent, so rows
-    0 / 101 / 255 of the batch are compared with the CPU oracle run on those rows alone."""
+@pytest.mark.parametrize("algorithm", ["auto", "gemm"])
+def test_cfg5_mel_spectrogram_full_size_against_oracle(lib, cfg5_waves, algorithm):
+    """TacotronSTFT.mel_spectrogram on all 256 x 10 s waveforms in one call (butterfly kernel = the default, and the
+    tensor-core dense-basis kernel); utterances are independent, so rows 0 / 101 / 255 of the batch are compared with the
+    CPU oracle run on those rows alone."""
     import text2speech_b200 as t2s
     taco = t2s.TacotronSTFT(1024, 256, 1024, 80, DC["sampling_rate"], DC["mel_fmin"], DC["mel_fmax"]).to(DEV)
+    taco.stft_fn.algorithm = algorithm
     mel = taco.mel_spectrogram(cfg5_waves.to(DEV))
     assert mel.shape == (256, 80, 861) and bool(torch.isfinite(mel).all())
     fwd, _ = oracle.stft_bases(1024, 256, 1024)
@@ -1017,13 +1134,16 @@ def test_cfg5_mel_spectrogram_full_size_against_oracle(lib, cfg5_waves):
     assert util.rel_l2(got, want) <= 1e-5
 
 
-def test_cfg5_denoiser_full_size_against_oracle(models, lib, cfg5_waves):
-    """Denoiser(strength 0.01) on all 256 x 10 s waveforms against the CPU oracle on three rows (bias_spec from the
-    FP32-mode model, which matches the reference's to 1e-4)."""
+@pytest.mark.parametrize("algorithm", ["auto", "gemm"])
+def test_cfg5_denoiser_full_size_against_oracle(models, lib, cfg5_waves, algorithm):
+    """Denoiser(strength 0.01) on all 256 x 10 s waveforms (butterfly kernel = the default, and the tensor-core dense-basis
+    kernels) against the CPU oracle on three rows (bias_spec from the FP32-mode model, which matches the reference's to
+    1e-4)."""
     import text2speech_b200 as t2s
     m = models["bench"]
     m.mode = "fp32"
     den = t2s.Denoiser(m)
+    den.stft.algorithm = algorithm
     m.mode = "bf16"
     out = den(cfg5_waves.to(DEV), strength=0.01)
     assert out.shape == (256, 1, 220160) and bool(torch.isfinite(out).all())

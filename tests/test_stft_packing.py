@@ -182,3 +182,109 @@ def test_ola_envelope_table_equals_reference_window_sum():
         assert np.array_equal(env[mask].numpy(), wss[q * hop: (q + 1) * hop]), q
     nowin = STFT(1024, 256, 1024, window=None)
     assert nowin._pair_pack(CPU)[2][1] is None
+
+
+# ------------------------------------------------------------------------------------ butterfly path (csrc/fft.cu)
+
+def _fft_mel_emulated(y, win, parts, weights, n_mel, hop, clip=1e-5):
+    """What wgb_fft_stft_mel computes, from ITS operands: reflect-indexed frames x window -> real FFT -> |X| -> the
+    filterbank as pieces (lane, slot) -> {first bin, bins, weight offset, filter} added per filter -> log(clamp)."""
+    fr = _frames(y, 1024, hop) * win.double()
+    mag = torch.fft.rfft(fr, dim=-1).abs()                                 # [B, F, 513]
+    out = torch.zeros(mag.shape[0], n_mel, mag.shape[1], dtype=torch.float64)
+    for first, count, off, m in parts.reshape(-1, 4).tolist():
+        if count > 0:
+            out[:, m] += (mag[..., first: first + count] * weights[off: off + count].double()).sum(-1)
+    return torch.log(torch.clamp(out, min=clip))
+
+
+def _fft_denoise_emulated(y, win, env, bias, strength, hop, scale):
+    """What wgb_fft_denoise computes: per frame rfft -> clamp(|X| - bias * strength, 0) with the phase kept -> irfft x
+    window / scale; output block q (hop samples of the padded time line) = taps j = 3..0 of frames q - j, normalised with
+    the envelope row of the set of existing frames, scaled by L / hop; blocks 2 .. frames are kept (L/2 trim)."""
+    length = 1024
+    fr = _frames(y, length, hop) * win.double()
+    X = torch.fft.rfft(fr, dim=-1)
+    mag = X.abs()
+    g = torch.where(mag > 0, torch.clamp(mag - bias.double() * strength, min=0.0) / mag.clamp_min(1e-300), torch.zeros_like(mag))
+    X = X * g
+    x = torch.fft.irfft(X, n=length, dim=-1) * win.double() / scale       # [B, F, L]
+    B, F, _ = x.shape
+    out = torch.zeros(B, 1, hop * (F - 1), dtype=torch.float64)
+    for q in range(2, F + 1):
+        acc = torch.zeros(B, hop, dtype=torch.float64)
+        mask = 0
+        for j in (3, 2, 1, 0):                                            # oldest frame first, as the register pipeline
+            r = q - j
+            if 0 <= r < F:
+                acc = acc + x[:, r, j * hop: (j + 1) * hop]
+                mask |= 1 << j
+        if env is not None:
+            e = env[mask].double()
+            acc = torch.where(e > np.finfo(np.float32).tiny, acc / e, acc) * scale
+        out[:, 0, (q - 2) * hop: (q - 1) * hop] = acc
+    return out
+
+
+def test_fft_path_operands_reproduce_the_oracle():
+    """Host side of the butterfly path on the CPU: the stock-basis test, the window / envelope tables of STFT._fft_pack
+    and the banded mel rows of TacotronSTFT._mel_rows, pushed through a torch.fft emulation of the kernels' arithmetic,
+    reproduce the oracle's conv-basis mel spectrogram and denoiser (ragged length, window shorter than the filter,
+    window=None)."""
+    y = syn.synthetic_waveforms(2, 256 * 11 + 77, sr=DC["sampling_rate"], seed=9)
+    bias = torch.rand(513, generator=torch.Generator().manual_seed(1)) * 0.05
+    for window, win_length, hop in (("hann", 1024, 256), ("hann", 800, 256), (None, 1024, 256), ("hann", 1024, 200)):
+        stft = STFT(1024, hop, win_length, window=window)
+        pack = stft._fft_pack(CPU)
+        assert pack is not None
+        win, env = pack
+        fwd, inv = oracle.stft_bases(1024, hop, win_length, window=window)
+        if window is not None:
+            taco = TacotronSTFT(1024, hop, win_length, 80, DC["sampling_rate"], DC["mel_fmin"], DC["mel_fmax"])
+            parts, weights, per_lane = taco._mel_parts(CPU)
+            assert parts.dtype == torch.int32 and parts.shape == (32, per_lane, 4) and per_lane <= 16
+            assert int(parts[..., 1].sum()) == weights.numel() <= 4096
+            pieces_per_filter = torch.bincount(parts[..., 3][parts[..., 1] > 0].flatten().long(), minlength=80)
+            assert int(pieces_per_filter.max()) <= 2                      # two partial sums commute: order-independent
+            load = parts[..., 1].sum(1)
+            assert int(load.max()) <= 1.5 * weights.numel() / 32 + 8       # balanced across the lanes
+            mb = torch.from_numpy(oracle.mel_filterbank(DC["sampling_rate"], 1024, 80, DC["mel_fmin"], DC["mel_fmax"])).float()
+            want = oracle.mel_spectrogram(y, fwd, mb, hop)
+            got = _fft_mel_emulated(y, win, parts, weights, 80, hop)
+            assert float((got - want).abs().max()) <= 2e-4, (window, win_length, hop)
+        if hop * 4 == 1024:
+            mag, phase = oracle.stft_transform(y, fwd, hop)
+            want = oracle.stft_inverse(torch.clamp(mag - bias.reshape(1, 513, 1) * 0.5, 0.0), phase, inv, hop, win_length,
+                                       window=window)
+            assert (env is None) == (window is None)
+            got = _fft_denoise_emulated(y, win, env, bias, 0.5, hop, 1024 / hop)
+            assert got.shape == want.shape and util.snr_db(got, want) >= 100.0, (window, win_length)
+
+
+def test_fft_path_refuses_edited_or_foreign_bases():
+    """The butterfly kernels assume the constructor's real-DFT pair: an edited buffer, a basis of another filter length, a
+    forced precision or algorithm = 'gemm' all leave the call on the dense-basis kernels; the reference's own bases
+    (np.fft.fft(eye) / pinv, what a reference checkpoint would carry) are recognised as stock."""
+    stft = STFT(1024, 256, 1024)
+    assert stft._fft_pack(CPU) is not None
+    fwd, inv = oracle.stft_bases(1024, 256, 1024)                          # the reference's construction (stft.py:45-66)
+    stft.forward_basis.copy_(fwd)
+    stft.inverse_basis.copy_(inv)
+    assert stft._fft_pack(CPU) is not None
+    stft.inverse_basis[5, 0, 100] += 1e-4
+    assert stft._fft_pack(CPU) is None
+    stft = STFT(1024, 256, 1024)
+    stft.precision = "fp32"
+    assert stft._fft_pack(CPU) is None
+    stft.precision, stft.algorithm = "auto", "gemm"
+    assert stft._fft_pack(CPU) is None
+    assert STFT(512, 128, 512)._fft_pack(CPU) is None
+    stft = STFT(1024, 256, 1024)
+    with torch.no_grad():
+        stft.forward_basis[3] *= 2.0
+    stft.algorithm = "fft"
+    try:
+        stft._fft_pack(CPU)
+        raise AssertionError("algorithm='fft' must insist")
+    except RuntimeError:
+        pass

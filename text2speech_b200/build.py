@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libwaveglow_b200.so")
-SOURCES = ["api.cu", "common.cu", "wn_tc.cu", "wn_tc2.cu", "wn_skip16.cu", "ref_f32.cu", "flow.cu", "stft.cu", "stft_tc2.cu", "wn_wgrad.cu", "train.cu"]
+SOURCES = ["api.cu", "common.cu", "wn_tc.cu", "wn_tc2.cu", "wn_skip16.cu", "ref_f32.cu", "flow.cu", "stft.cu", "stft_tc2.cu", "fft.cu", "wn_wgrad.cu", "train.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static",

@@ -19,6 +19,8 @@ int tc2_stft_mel(const void*, const void*, const void*, const void*, float*, int
 int tc2_stft_denoise(const void*, const void*, const void*, const float*, float, void*, void*, int, int, int, int, int, int,
                      cudaStream_t);
 int tc2_istft_ola(const void*, const void*, const void*, const float*, float*, int, int, int, int, cudaStream_t);
+int fft_stft_mel(const float*, const float*, const void*, int, const float*, int, float*, int, int, int, int, float, int*, cudaStream_t);
+int fft_denoise(const float*, const float*, const float*, float, const float*, float*, int, int, int, cudaStream_t);
 int tc2_gemm_split3(const void*, const void*, const void*, float*, long long, int, int, cudaStream_t);
 int tc_stft_mel(const void*, const void*, const void*, const void*, void*, int, int, int, int, long long, long long, int, float,
                 cudaStream_t);
@@ -238,6 +240,16 @@ WGB_API int wgb_tc2_stft_denoise(const void* a_hi, const void* a_lo, const void*
 WGB_API int wgb_tc2_istft_ola(const void* s_hi, const void* s_lo, const void* w_ola, const float* env_tab, float* out,
                               int batch, int frames, int L, int hop, void* stream) {
     return tc2_istft_ola(s_hi, s_lo, w_ola, env_tab, out, batch, frames, L, hop, S(stream));
+}
+WGB_API int wgb_fft_stft_mel(const float* y, const float* window, const void* mel_parts, int parts_per_lane,
+                             const float* mel_w, int mel_w_total, float* out, int batch, int n, int hop, int n_mel,
+                             float clip, int* range_flag, void* stream) {
+    return fft_stft_mel(y, window, mel_parts, parts_per_lane, mel_w, mel_w_total, out, batch, n, hop, n_mel, clip, range_flag,
+                        S(stream));
+}
+WGB_API int wgb_fft_denoise(const float* y, const float* window, const float* bias_spec, float strength,
+                            const float* env_tab, float* out, int batch, int n, int hop, void* stream) {
+    return fft_denoise(y, window, bias_spec, strength, env_tab, out, batch, n, hop, S(stream));
 }
 WGB_API int wgb_tc2_gemm_split3(const void* a_hi, const void* a_lo, const void* w3, float* c, long long rows, int N, int K,
                                 void* stream) {

@@ -7,9 +7,9 @@
 //
 //   512 = 8 x 8 x 8:   n = n0 + 8 n1 + 64 n2,   k = k2 + 8 k1 + 64 k0
 //   stage 1  A[n0,n1,k2] = sum_n2 z[n] W8^(n2 k2)                       lane owns (n0,n1) = lane + 32u, u = 0,1
-//            * W64^(n1 k2)                                      -> smem [n0 + 8 n1 + 72 k2]
+//            * W64^(n1 k2)                                      -> smem A [n0 + 8 n1 + 72 k2]
 //   stage 2  B[n0,k1,k2] = sum_n1 A' W8^(n1 k1)                         lane owns (n0,k2) = lane + 32u
-//            * W512^(n0 (k2 + 8 k1))                            -> smem [k2 + 8 k1 + 66 n0]
+//            * W512^(n0 (k2 + 8 k1))                            -> smem B [k2 + 8 k1 + 66 n0]
 //   stage 3  Z[k] = sum_n0 B' W8^(n0 k0)                                lane owns (k2,k1) = lane + 32u
 //   A lane starts with z[lane + 32 j] and ends with Z[lane + 32 j], j = 0..15 (j = u + 2 n2 on the way in, u + 2 k0 on
 //   the way out), so consecutive lanes touch consecutive addresses of the signal, and the partner bin 512 - k of the
@@ -31,7 +31,9 @@ struct cf {
     float x, y;
 };
 
-constexpr int kBufElems = 576;          // cf per warp: 8 rows of pitch 72 (stage 1 -> 2); 8 rows of pitch 66 fit inside
+constexpr int kBufA = 576;              // cf per warp, first exchange (stage 1 -> 2): 8 rows of pitch 72
+constexpr int kBufB = 528;              // second exchange (stage 2 -> 3): 8 rows of pitch 66
+constexpr int kBufElems = kBufA + kBufB;
 constexpr float kSqrtHalf = 0.70710678118654752440f;
 
 WGB_FFT_HD cf cmul(cf a, cf b) { return cf{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
@@ -111,8 +113,9 @@ WGB_FFT_HD cf w32(int j) {
     return cf{c[j], -s[j]};
 }
 
-// ---- the three stages.  v[16]: this lane's values; buf: the warp's kBufElems exchange buffer.  A warp-wide barrier goes
-// between stage1 / stage2_load, stage2_load / stage2_store, stage2_store / stage3, and after stage3 before buf is reused.
+// ---- the three stages.  v[16]: this lane's values; buf_a / buf_b: the warp's two exchange buffers (kBufA, kBufB).  A
+// warp-wide barrier goes between stage1 / stage2 and between stage2 / stage3; with two buffers nothing else is needed between
+// back-to-back transforms (a buffer is rewritten only after a barrier that every lane reaches after its last read of it).
 WGB_FFT_HD void stage1(int lane, const LaneTw& t, const cf* v, cf* buf) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -129,30 +132,21 @@ WGB_FFT_HD void stage1(int lane, const LaneTw& t, const cf* v, cf* buf) {
         }
     }
 }
-WGB_FFT_HD void stage2_load(int lane, const LaneTw& t, cf* w, const cf* buf) {          // w[16]: (u, k1) -> w[8 u + k1]
+WGB_FFT_HD void stage2(int lane, const LaneTw& t, const cf* buf_a, cf* buf_b) {
     const int n0 = lane & 7;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         const int k2 = (lane >> 3) + 4 * u;
         cf a[8];
 #pragma unroll
-        for (int n1 = 0; n1 < 8; ++n1) a[n1] = buf[n0 + 8 * n1 + 72 * k2];
+        for (int n1 = 0; n1 < 8; ++n1) a[n1] = buf_a[n0 + 8 * n1 + 72 * k2];
         dft8(a);
 #pragma unroll
         for (int k1 = 0; k1 < 8; ++k1) {
             cf x = cmul(a[k1], t.s2[k1]);
             if (u) x = cmul(x, t.s2u);
-            w[8 * u + k1] = x;
+            buf_b[k2 + 8 * k1 + 66 * n0] = x;
         }
-    }
-}
-WGB_FFT_HD void stage2_store(int lane, const cf* w, cf* buf) {
-    const int n0 = lane & 7;
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int k2 = (lane >> 3) + 4 * u;
-#pragma unroll
-        for (int k1 = 0; k1 < 8; ++k1) buf[k2 + 8 * k1 + 66 * n0] = w[8 * u + k1];
     }
 }
 WGB_FFT_HD void stage3(int lane, cf* v, const cf* buf) {

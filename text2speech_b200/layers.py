@@ -92,6 +92,51 @@ class TacotronSTFT(torch.nn.Module):
             cached = self._mel_pair_ok
         return (tab, self._mel_tab[2]) if cached[1] else None
 
+    def _mel_parts(self, device):
+        """mel_basis as balanced bands for wgb_fft_stft_mel: (parts int32 [32, P, 4] = {first bin, bins, offset into the
+        packed weights, filter} per lane of a warp, packed weights fp32 = the rows of mel_basis over their non-zero spans),
+        or None when the basis is too dense for the kernel's shared-memory tables.  A row wider than the average load of
+        a lane is cut into two halves (never more: two partial sums commute, so the result stays order-independent); the
+        pieces are dealt to the 32 lanes longest-first onto the least loaded lane."""
+        key = (str(device), self.mel_basis.data_ptr(), self.mel_basis._version)
+        cached = getattr(self, "_mel_parts_pack", None)
+        if cached is None or cached[0] != key:
+            basis = self.mel_basis.detach().float().cpu()
+            n_mel, n_bins = basis.shape
+            spans, vals, off = [], [], 0
+            for m in range(n_mel):
+                nz = torch.nonzero(basis[m]).flatten()
+                lo, cnt = (int(nz[0]), int(nz[-1]) - int(nz[0]) + 1) if nz.numel() else (0, 0)
+                spans.append((lo, cnt, off))
+                vals.append(basis[m, lo: lo + cnt])
+                off += cnt
+            pack = None
+            if n_mel <= 128 and off <= 4096 and n_bins == self.stft_fn.cutoff:
+                target = max(8, -(-off // 32))
+                pieces = []
+                for m, (lo, cnt, o) in enumerate(spans):
+                    if cnt > target:
+                        h = (cnt + 1) // 2
+                        pieces += [(h, lo, o, m), (cnt - h, lo + h, o + h, m)]
+                    elif cnt > 0:
+                        pieces.append((cnt, lo, o, m))
+                lanes, load = [[] for _ in range(32)], [0] * 32
+                for cnt, lo, o, m in sorted(pieces, reverse=True):
+                    i = min(range(32), key=lambda j: (load[j], j))
+                    lanes[i].append([lo, cnt, o, m])
+                    load[i] += cnt + 4                  # + the fixed cost of a piece (table read, shared-memory add)
+                per_lane = max(1, max(len(x) for x in lanes))
+                if per_lane <= 16:
+                    table = torch.zeros((32, per_lane, 4), dtype=torch.int32)
+                    for i, lst in enumerate(lanes):
+                        for q, piece in enumerate(lst):
+                            table[i, q] = torch.tensor(piece, dtype=torch.int32)
+                    w = torch.cat(vals) if off else torch.zeros(1)
+                    pack = (table.contiguous().to(device), w.contiguous().to(device), per_lane)
+            self._mel_parts_pack = (key, pack)
+            cached = self._mel_parts_pack
+        return cached[1]
+
     def mel_spectrogram(self, y: torch.Tensor) -> torch.Tensor:
         """y [B, T] in [-1, 1] (CUDA) -> log-mel [B, n_mel_channels, T // hop + 1].  The reference's two input asserts
         (layers.py:72-73: min(y) >= -1, max(y) <= 1) raise AssertionError here too; on the fused tensor-core path they are
@@ -115,6 +160,10 @@ class TacotronSTFT(torch.nn.Module):
         y = y.float().contiguous()
         b = y.shape[0]
         s = _lib.stream_ptr()
+        if self.fused:                        # stock STFT bases: FFT, |X|, filterbank and log-clamp in one butterfly kernel
+            out = self.stft_fn._mel_fft(y, self._mel_parts(y.device), self.n_mel_channels, 1e-5, range_flag)
+            if out is not None:
+                return out
         if self.stft_fn._use_tc():
             cp = self.stft_fn._packed(y.device)[3]
             table = None

@@ -65,6 +65,11 @@ class STFT(torch.nn.Module):
         self.pair = True
         # Denoiser: inverse GEMM with the overlap-add inside (wgb_tc2_istft_ola) instead of GEMM + overlap-add kernel
         self.fused_ola = True
+        # 'auto': the fused mel / denoiser paths run as butterflies (csrc/fft.cu: 1024-point real FFTs, one warp per frame)
+        # whenever the basis buffers are still the constructor's real-DFT pair, filter_length is 1024 and precision is
+        # 'auto', else as the dense-basis contractions; 'gemm' forces the contractions (A/B, validation); 'fft' insists
+        self.algorithm = "auto"
+        self._fft = None
 
     # ------------------------------------------------------------------ packed constants
     @property
@@ -151,6 +156,81 @@ class STFT(torch.nn.Module):
         for window=None), or None when hop % 256 != 0."""
         self._packed(device)
         return self._pack[6]
+
+    def _fft_pack(self, device):
+        """(window fp32 [L] on device, overlap-add envelope table [2^taps][hop] or None) for the butterfly kernels, or None
+        when they do not apply.  They assume what stft.py:46-60 builds: forward_basis = window * [cos; -sin](2 pi k n / L)
+        and inverse_basis = its pseudo-inverse, which for this basis is the inverse real DFT c_k / (L scale) * [cos; -sin]
+        (c = 1 for bins 0 and L/2, else 2) times the window.  Buffers that were edited or loaded from elsewhere are compared
+        with those closed forms (1e-6 of the largest entry); anything else goes to the dense-basis kernels."""
+        if self.algorithm == "gemm" or self.precision != "auto" or self.filter_length != 1024:
+            if self.algorithm == "fft":
+                raise RuntimeError("the butterfly STFT kernels need filter_length 1024 and precision 'auto'")
+            return None
+        key = (str(device), self.forward_basis.data_ptr(), self.forward_basis._version,
+               self.inverse_basis.data_ptr(), self.inverse_basis._version)
+        if self._fft is None or self._fft[0] != key:
+            length, cutoff = self.filter_length, self.cutoff
+            if self.window is not None:
+                win = padded_window(self.window, self.win_length, length).astype(np.float32)
+            else:
+                win = np.ones(length, dtype=np.float32)
+            kn = (np.outer(np.arange(cutoff), np.arange(length)) % length) * (2.0 * np.pi / length)
+            basis = np.concatenate([np.cos(kn), -np.sin(kn)], axis=0)
+            c = np.full((cutoff, 1), 2.0)
+            c[0] = c[-1] = 1.0
+            inv = np.concatenate([c, c], axis=0) * basis / (length * (length / self.hop_length))
+            fb = self.forward_basis.detach().float().cpu().numpy()[:, 0]
+            ib = self.inverse_basis.detach().float().cpu().numpy()[:, 0]
+            stock = (fb.shape == basis.shape and ib.shape == inv.shape
+                     and float(np.abs(fb - basis.astype(np.float32) * win).max()) <= 1e-6
+                     and float(np.abs(ib - inv.astype(np.float32) * win).max()) <= 1e-6 * float(np.abs(inv).max()))
+            pack = None
+            if stock:
+                env = None
+                taps = length // self.hop_length
+                if self.window is not None and length % self.hop_length == 0 and taps <= 8:
+                    # window-sum envelope per set of covering frames, summed like the reference's host loop
+                    # (audio_processing.py:45-47: float32 += float64, frames ascending = taps descending)
+                    hop = self.hop_length
+                    sq64 = win.astype(np.float64) ** 2
+                    tab = np.zeros((1 << taps, hop), dtype=np.float32)
+                    for mask in range(1 << taps):
+                        for j in reversed(range(taps)):
+                            if (mask >> j) & 1:
+                                tab[mask] = (tab[mask].astype(np.float64) + sq64[j * hop: (j + 1) * hop]).astype(np.float32)
+                    env = torch.from_numpy(tab).to(device)
+                pack = (torch.from_numpy(win).to(device), env)
+            self._fft = (key, pack)
+        if self._fft[1] is None and self.algorithm == "fft":
+            raise RuntimeError("the butterfly STFT kernels need the constructor's basis buffers")
+        return self._fft[1]
+
+    def _denoised_fft(self, y: torch.Tensor, bias_spec: torch.Tensor, strength: float):
+        """Denoiser.forward as ONE butterfly kernel (wgb_fft_denoise), or None when that path does not apply."""
+        pack = self._fft_pack(y.device)
+        if pack is None or self.hop_length * 4 != self.filter_length or y.shape[1] <= self.filter_length // 2:
+            return None
+        _lib.require_b200(y.device)
+        b, n = y.shape
+        frames = n // self.hop_length + 1
+        out = torch.empty((b, 1, self.hop_length * (frames - 1)), device=y.device, dtype=torch.float32)
+        _lib.call("wgb_fft_denoise", y, pack[0], bias_spec, float(strength), pack[1] if self.window is not None else None,
+                  out, b, n, self.hop_length, _lib.stream_ptr())
+        return out
+
+    def _mel_fft(self, y: torch.Tensor, mel_pack, n_mel: int, clip: float, range_flag=None):
+        """TacotronSTFT.mel_spectrogram as ONE butterfly kernel (wgb_fft_stft_mel), or None when that path does not
+        apply.  mel_pack = (parts int32 [32, P, 4], packed weights fp32, P) from TacotronSTFT._mel_parts."""
+        pack = self._fft_pack(y.device)
+        if pack is None or mel_pack is None or y.shape[1] <= self.filter_length // 2:
+            return None
+        _lib.require_b200(y.device)
+        b, n = y.shape
+        out = torch.empty((b, n_mel, n // self.hop_length + 1), device=y.device, dtype=torch.float32)
+        _lib.call("wgb_fft_stft_mel", y, pack[0], mel_pack[0], mel_pack[2], mel_pack[1], mel_pack[1].numel(), out, b, n,
+                  self.hop_length, n_mel, float(clip), range_flag, _lib.stream_ptr())
+        return out
 
     def _use_pair(self) -> bool:
         return self.pair and self._use_tc() and self.filter_length <= 1024      # per-bin tables of L/2 + 1 entries in smem

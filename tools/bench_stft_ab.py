@@ -1,7 +1,7 @@
 """A/B of the STFT kernels at BASELINE configs[4] size (256 x 10 s waveforms): CTA-pair kernels with the unpadded
 layout (csrc/stft_tc2.cu, default) vs the one-CTA kernels with the 640-bin padded layout (csrc/wn_tc.cu).
 
-    python tools/bench_stft_ab.py [--out gpurun_out/stft_ab.json] [--once pair|single]   (--once: one call each, for ncu)
+    python tools/bench_stft_ab.py [--out gpurun_out/stft_ab.json] [--once fft|pair|single]   (--once: one call each, for ncu)
 """
 import argparse
 import json
@@ -36,7 +36,8 @@ def main():
     y = syn.synthetic_waveforms(256, 220160, sr=22050, seed=5).to(DEV)
     frames = 256 * 861
     if args.once:
-        taco.stft_fn.pair = den.stft.pair = args.once == "pair"
+        taco.stft_fn.pair = den.stft.pair = args.once != "single"
+        taco.stft_fn.algorithm = den.stft.algorithm = "auto" if args.once == "fft" else "gemm"
         for _ in range(2):
             taco._mel_spectrogram(y)
             den(y, 0.01)
@@ -56,7 +57,9 @@ def main():
         with open(args.out, "w") as f:
             json.dump(out, f, indent=1)
         return
-    for name, pair, fused in (("pair", True, True), ("pair_separate_overlap_add", True, False), ("one_cta", False, False)):
+    for name, algo, pair, fused in (("fft", "auto", True, True), ("pair", "gemm", True, True),
+                                    ("pair_separate_overlap_add", "gemm", True, False), ("one_cta", "gemm", False, False)):
+        taco.stft_fn.algorithm = den.stft.algorithm = algo
         taco.stft_fn.pair = den.stft.pair = pair
         den.stft.fused_ola = fused
         rec = {}
@@ -70,8 +73,14 @@ def main():
         rec["denoiser_breakdown"] = breakdown(lambda: den(y, 0.01))
         out[name] = rec
     taco.stft_fn.pair = den.stft.pair = den.stft.fused_ola = True
+    taco.stft_fn.algorithm = den.stft.algorithm = "auto"
+    a_fft = taco._mel_spectrogram(y)
+    d_fft = den(y, 0.01)
+    taco.stft_fn.algorithm = den.stft.algorithm = "gemm"
     a = taco._mel_spectrogram(y)
     d = den(y, 0.01)
+    out["max_abs_mel_diff_fft_vs_pair"] = float((a - a_fft).abs().max())
+    out["denoiser_snr_fft_vs_pair_db"] = float(10 * torch.log10(d.double().pow(2).sum() / (d - d_fft).double().pow(2).sum()))
     taco.stft_fn.pair = den.stft.pair = False
     out["max_abs_mel_diff"] = float((a - taco._mel_spectrogram(y)).abs().max())
     d2 = den(y, 0.01)
