@@ -251,13 +251,14 @@ WGB_API int wgb_tc2_istft_ola(const void* s_hi, const void* s_lo, const void* w_
  *
  * TacotronSTFT.mel_spectrogram (layers.py:63-79; stft.py:79-97): y fp32 [B][n] -> out fp32 [B][n_mel][n / hop + 1] =
  * log(clamp(mel_basis |STFT(y)|, clip)).  window fp32 [1024] (zero-padded window, ones for window=None).  The filterbank
- * arrives as bands: mel_w = the rows of mel_basis over their non-zero spans, packed; mel_parts int32
- * [32][parts_per_lane][4] = {first bin, number of bins, offset into mel_w, filter} lists, per lane of a warp, the pieces of
- * rows that lane sums (count 0 = unused slot).  Every filter is covered by at most TWO pieces, so the two shared-memory
- * adds that rebuild it commute: results are independent of scheduling.  range_flag (optional int32) is set to 1 when a
- * sample is outside [-1, 1] or NaN (layers.py:72-73).  n > 512, n_mel <= 128, parts_per_lane <= 16, mel_w_total <= 4096. */
-WGB_API int wgb_fft_stft_mel(const float* y, const float* window, const void* mel_parts, int parts_per_lane,
-                             const float* mel_w, int mel_w_total, float* out, int batch, int n, int hop, int n_mel,
+ * arrives as PIECES of 8 consecutive bins starting at a multiple of 4: mel_w fp32 [n_pieces][8] holds the piece's weights
+ * (zero outside the filter's span and past bin 512); mel_slots int32 [32][slots_per_lane][4] = {first bin / 4, piece,
+ * filter to emit after this piece or -1, 1 if this piece starts a filter} lists, per lane of a warp, the pieces that lane
+ * sums.  All pieces of a filter sit consecutively in ONE lane, so every filter is summed in a fixed order by one thread;
+ * unused slots name an all-zero piece and emit nothing.  range_flag (optional int32) is set to 1 when a sample is outside
+ * [-1, 1] or NaN (layers.py:72-73).  n > 512, n_mel <= 128, slots_per_lane <= 24, n_pieces <= 512. */
+WGB_API int wgb_fft_stft_mel(const float* y, const float* window, const void* mel_slots, int slots_per_lane,
+                             const float* mel_w, int n_pieces, float* out, int batch, int n, int hop, int n_mel,
                              float clip, int* range_flag, void* stream);
 /* Denoiser.forward (denoiser.py:35-40) = STFT.transform, clamp(|X| - bias_spec * strength, 0) with the phase kept,
  * STFT.inverse (stft.py:99-130: overlap-add, window-sum normalisation, L/hop scale, L/2 trim) in ONE kernel: a warp walks a

@@ -186,15 +186,23 @@ def test_ola_envelope_table_equals_reference_window_sum():
 
 # ------------------------------------------------------------------------------------ butterfly path (csrc/fft.cu)
 
-def _fft_mel_emulated(y, win, parts, weights, n_mel, hop, clip=1e-5):
-    """What wgb_fft_stft_mel computes, from ITS operands: reflect-indexed frames x window -> real FFT -> |X| -> the
-    filterbank as pieces (lane, slot) -> {first bin, bins, weight offset, filter} added per filter -> log(clamp)."""
+def _fft_mel_emulated(y, win, slots, weights, n_mel, hop, clip=1e-5):
+    """What wgb_fft_stft_mel computes, from ITS operands: reflect-indexed frames x window -> real FFT -> |X| (zeros past
+    bin 512) -> per lane, the slots in order: sum restarts on a filter's first piece, a piece = 8 bins from 4 * slot[0]
+    times weights[slot[1]], the running sum is the filter's value after its last piece -> log(clamp)."""
     fr = _frames(y, 1024, hop) * win.double()
     mag = torch.fft.rfft(fr, dim=-1).abs()                                 # [B, F, 513]
-    out = torch.zeros(mag.shape[0], n_mel, mag.shape[1], dtype=torch.float64)
-    for first, count, off, m in parts.reshape(-1, 4).tolist():
-        if count > 0:
-            out[:, m] += (mag[..., first: first + count] * weights[off: off + count].double()).sum(-1)
+    mag = torch.cat([mag, torch.zeros(mag.shape[:2] + (15,), dtype=mag.dtype)], dim=-1)      # the kernel's 528-entry buffer
+    out = torch.full((mag.shape[0], n_mel, mag.shape[1]), float("nan"), dtype=torch.float64)
+    for lane in range(32):
+        total = torch.zeros(mag.shape[:2], dtype=torch.float64)
+        for bin4, piece, emit, first in slots[lane].tolist():
+            if first:
+                total = torch.zeros_like(total)
+            total = total + (mag[..., 4 * bin4: 4 * bin4 + 8] * weights[piece].double()).sum(-1)
+            if emit >= 0:
+                assert torch.isnan(out[:, emit]).all()                     # every filter is emitted exactly once
+                out[:, emit] = total
     return torch.log(torch.clamp(out, min=clip))
 
 
@@ -241,16 +249,15 @@ def test_fft_path_operands_reproduce_the_oracle():
         fwd, inv = oracle.stft_bases(1024, hop, win_length, window=window)
         if window is not None:
             taco = TacotronSTFT(1024, hop, win_length, 80, DC["sampling_rate"], DC["mel_fmin"], DC["mel_fmax"])
-            parts, weights, per_lane = taco._mel_parts(CPU)
-            assert parts.dtype == torch.int32 and parts.shape == (32, per_lane, 4) and per_lane <= 16
-            assert int(parts[..., 1].sum()) == weights.numel() <= 4096
-            pieces_per_filter = torch.bincount(parts[..., 3][parts[..., 1] > 0].flatten().long(), minlength=80)
-            assert int(pieces_per_filter.max()) <= 2                      # two partial sums commute: order-independent
-            load = parts[..., 1].sum(1)
-            assert int(load.max()) <= 1.5 * weights.numel() / 32 + 8       # balanced across the lanes
+            slots, weights, per_lane = taco._mel_slots(CPU)
+            assert slots.dtype == torch.int32 and slots.shape == (32, per_lane, 4) and per_lane <= 24
+            assert weights.shape[1] == 8 and weights.shape[0] <= 512 and float(weights[0].abs().max()) == 0.0
+            assert int(slots[..., 0].max()) * 4 + 8 <= 528                # the last piece stays inside the |X| buffer
+            assert sorted(slots[..., 2][slots[..., 2] >= 0].tolist()) == list(range(80))
+            assert per_lane <= 2 + weights.shape[0] // 32                  # balanced across the lanes
             mb = torch.from_numpy(oracle.mel_filterbank(DC["sampling_rate"], 1024, 80, DC["mel_fmin"], DC["mel_fmax"])).float()
             want = oracle.mel_spectrogram(y, fwd, mb, hop)
-            got = _fft_mel_emulated(y, win, parts, weights, 80, hop)
+            got = _fft_mel_emulated(y, win, slots, weights, 80, hop)
             assert float((got - want).abs().max()) <= 2e-4, (window, win_length, hop)
         if hop * 4 == 1024:
             mag, phase = oracle.stft_transform(y, fwd, hop)

@@ -241,10 +241,10 @@ WGB_API int wgb_tc2_istft_ola(const void* s_hi, const void* s_lo, const void* w_
                               int batch, int frames, int L, int hop, void* stream) {
     return tc2_istft_ola(s_hi, s_lo, w_ola, env_tab, out, batch, frames, L, hop, S(stream));
 }
-WGB_API int wgb_fft_stft_mel(const float* y, const float* window, const void* mel_parts, int parts_per_lane,
-                             const float* mel_w, int mel_w_total, float* out, int batch, int n, int hop, int n_mel,
+WGB_API int wgb_fft_stft_mel(const float* y, const float* window, const void* mel_slots, int slots_per_lane,
+                             const float* mel_w, int n_pieces, float* out, int batch, int n, int hop, int n_mel,
                              float clip, int* range_flag, void* stream) {
-    return fft_stft_mel(y, window, mel_parts, parts_per_lane, mel_w, mel_w_total, out, batch, n, hop, n_mel, clip, range_flag,
+    return fft_stft_mel(y, window, mel_slots, slots_per_lane, mel_w, n_pieces, out, batch, n, hop, n_mel, clip, range_flag,
                         S(stream));
 }
 WGB_API int wgb_fft_denoise(const float* y, const float* window, const float* bias_spec, float strength,

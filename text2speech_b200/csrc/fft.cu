@@ -29,8 +29,9 @@ constexpr int kMelThreads = kMelWarps * 32;   // prefetched into registers)
 constexpr int kDnWarps = 12;              // denoise: the same (the register file is split over 4 schedulers: 3 warps each)
 constexpr int kDnThreads = kDnWarps * 32;
 constexpr int kMaxMel = 128;
-constexpr int kMaxMelW = 4096;            // packed filter weights (floats)
-constexpr int kMaxParts = 16;             // filterbank pieces per lane
+constexpr int kMaxPieces = 512;           // filterbank pieces of 8 bins
+constexpr int kMaxSlots = 24;             // pieces per lane
+constexpr int kMagPad = 528;              // |X| buffer: bins 0..512, then zeros that the last pieces may read
 
 __device__ __forceinline__ int reflect_index(int p, int n) {          // np.pad(mode='reflect'), |overhang| < n
     p = p < 0 ? -p : p;
@@ -133,12 +134,12 @@ __device__ __forceinline__ void irfft_split(int lane, const LaneTw& tw, cf* v, f
 struct MelParams {
     const float* y;            // [B, n]
     const float* window;       // [1024] (the window zero-padded to the filter length; ones for window=None)
-    const int4* mel_parts;     // [32][parts_per_lane] {first bin, bins, offset into mel_w, filter}: the pieces of mel_basis rows
-                               // lane l sums; a filter is cut into at most TWO pieces, so the two shared-memory adds that
-                               // rebuild it commute and the result does not depend on their order
-    int parts_per_lane;
-    const float* mel_w;        // packed rows of mel_basis over their non-zero spans
-    int mel_w_total;
+    const int4* mel_slots;     // [32][slots_per_lane] {float4 index into |X|, piece, filter to emit or -1, first piece of a filter}:
+                               // the filterbank as 8-bin pieces (4-bin aligned, zero-padded weights); a lane sums ALL pieces of
+                               // the filters it owns, in order, so no two lanes ever add into the same filter
+    int slots_per_lane;
+    const float4* mel_w;       // [n_pieces][2]: the 8 weights of each piece
+    int n_pieces;
     float* out;                // [B, n_mel, frames]
     int batch, n, frames, hop, n_mel;
     float clip;
@@ -150,43 +151,38 @@ __global__ void __launch_bounds__(kMelThreads, 1) fft_mel_kernel(const MelParams
     extern __shared__ __align__(16) unsigned char smem[];
     cf* bufs = reinterpret_cast<cf*>(smem);                                         // [kMelWarps][kBufElems]
     float2* win2 = reinterpret_cast<float2*>(bufs + kMelWarps * kBufElems);         // [512]
-    int4* parts = reinterpret_cast<int4*>(win2 + kHalf);                            // [32][parts_per_lane]
-    float* mw = reinterpret_cast<float*>(parts + 32 * kMaxParts);                   // [mel_w_total]
+    int4* slots = reinterpret_cast<int4*>(win2 + kHalf);                            // [32][slots_per_lane]
+    float4* mw = reinterpret_cast<float4*>(slots + 32 * kMaxSlots);                 // [n_pieces][2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < kHalf; i += kMelThreads) win2[i] = make_float2(p.window[2 * i], p.window[2 * i + 1]);
-    for (int i = threadIdx.x; i < 32 * p.parts_per_lane; i += kMelThreads) parts[i] = p.mel_parts[i];
-    for (int i = threadIdx.x; i < p.mel_w_total; i += kMelThreads) mw[i] = p.mel_w[i];
+    for (int i = threadIdx.x; i < 32 * p.slots_per_lane; i += kMelThreads) slots[i] = p.mel_slots[i];
+    for (int i = threadIdx.x; i < 2 * p.n_pieces; i += kMelThreads) mw[i] = p.mel_w[i];
     __syncthreads();
 
     LaneTw tw;
     lane_twiddles(lane, tw);
     cf* buf_a = bufs + warp * kBufElems;
     cf* buf_b = buf_a + kBufA;
-    float* mag = reinterpret_cast<float*>(buf_a);              // [513] |X|, then [kMaxMel] filter sums: buffer A is free once
-    float* acc = mag + kHalf + 3;                              // every lane is past stage 2
+    float* mag = reinterpret_cast<float*>(buf_a);              // [kMagPad] |X| (zeros past bin 512), then [kMaxMel] filter sums:
+    float* acc = mag + kMagPad;                                // buffer A is free once every lane is past stage 2
     bool bad = false;
 
     // warps walk the frames of the whole batch in flat order, a stride of all resident warps apart: at any moment an SM
     // works on consecutive frames, whose samples overlap (L1 / L2 hits), and no warp ever waits for another
-    const long long total = static_cast<long long>(p.batch) * p.frames;
-    const long long stride = static_cast<long long>(gridDim.x) * kMelWarps;
-    long long f = static_cast<long long>(blockIdx.x) * kMelWarps + warp;
+    const int stride = static_cast<int>(gridDim.x) * kMelWarps;
+    int b = 0, r = static_cast<int>(blockIdx.x) * kMelWarps + warp;           // (utterance, frame) of this warp's current frame
+    while (r >= p.frames) { r -= p.frames; ++b; }
     float2 nx[16];
-    if (f < total) {
-        const int b = static_cast<int>(f / p.frames), r = static_cast<int>(f % p.frames);
-        issue_frame_loads(p.y + static_cast<size_t>(b) * p.n, p.n, r * p.hop - kHalf, lane, nx);
-    }
-    for (; f < total; f += stride) {
-        const int b = static_cast<int>(f / p.frames), r = static_cast<int>(f % p.frames);
+    if (b < p.batch) issue_frame_loads(p.y + static_cast<size_t>(b) * p.n, p.n, r * p.hop - kHalf, lane, nx);
+    while (b < p.batch) {
         cf v[16];
         bad = window_frame<CHECK>(nx, win2, lane, r == 0 || r == p.frames - 1 || p.hop > 256, v) || bad;
         stage1(lane, tw, v, buf_a);
-        if (f + stride < total) {                                                  // v is dead until stage 3: fetch ahead
-            const long long fn = f + stride;
-            const int bn = static_cast<int>(fn / p.frames), rn = static_cast<int>(fn % p.frames);
+        int bn = b, rn = r + stride;                                                // the frame after this one
+        while (rn >= p.frames) { rn -= p.frames; ++bn; }
+        if (bn < p.batch)                                                           // v is dead until stage 3: fetch ahead
             issue_frame_loads(p.y + static_cast<size_t>(bn) * p.n, p.n, rn * p.hop - kHalf, lane, nx);
-        }
         __syncwarp();
         stage2(lane, tw, buf_a, buf_b);
         __syncwarp();
@@ -194,17 +190,19 @@ __global__ void __launch_bounds__(kMelThreads, 1) fft_mel_kernel(const MelParams
         const float nyq = rfft_split(lane, tw, v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) mag[lane + 32 * j] = sqrt_approx(v[j].x * v[j].x + v[j].y * v[j].y);      // stft.py:94
-        if (lane == 0) mag[kHalf] = fabsf(nyq);
-        for (int m = lane; m < p.n_mel; m += 32) acc[m] = 0.f;
+        if (lane < kMagPad - kHalf) mag[kHalf + lane] = lane == 0 ? fabsf(nyq) : 0.f;
         __syncwarp();
-        for (int q = 0; q < p.parts_per_lane; ++q) {                                // layers.py:77
-            const int4 part = parts[lane * p.parts_per_lane + q];
-            if (part.y > 0) {
-                const float* w = mw + part.z;
-                const float* a = mag + part.x;
-                float sum = 0.f;
-                for (int k = 0; k < part.y; ++k) sum = fmaf(w[k], a[k], sum);
-                atomicAdd(acc + part.w, sum);
+        {                                                                           // layers.py:77
+            const float4* mag4 = reinterpret_cast<const float4*>(mag);
+            float sum = 0.f;
+            for (int q = 0; q < p.slots_per_lane; ++q) {
+                const int4 slot = slots[lane * p.slots_per_lane + q];
+                const float4 a0 = mag4[slot.x], a1 = mag4[slot.x + 1];
+                const float4 w0 = mw[2 * slot.y], w1 = mw[2 * slot.y + 1];
+                const float s0 = fmaf(a0.w, w0.w, fmaf(a0.z, w0.z, fmaf(a0.y, w0.y, a0.x * w0.x)));
+                const float s1 = fmaf(a1.w, w1.w, fmaf(a1.z, w1.z, fmaf(a1.y, w1.y, a1.x * w1.x)));
+                sum = (slot.w ? 0.f : sum) + (s0 + s1);
+                if (slot.z >= 0) acc[slot.z] = sum;
             }
         }
         __syncwarp();
@@ -213,6 +211,8 @@ __global__ void __launch_bounds__(kMelThreads, 1) fft_mel_kernel(const MelParams
         float* ob = p.out + static_cast<size_t>(b) * p.n_mel * p.frames + r;
         for (int m = lane; m < p.n_mel; m += 32) ob[static_cast<size_t>(m) * p.frames] = logf(fmaxf(acc[m], p.clip));   // :78
         __syncwarp();
+        b = bn;
+        r = rn;
     }
     if (CHECK && bad) atomicOr(p.range_flag, 1);
 }
@@ -344,27 +344,28 @@ static int check_common(const float* y, const float* window, int batch, int n, i
     return WGB_OK;
 }
 
-int fft_stft_mel(const float* y, const float* window, const void* mel_parts, int parts_per_lane, const float* mel_w,
-                 int mel_w_total, float* out, int batch, int n, int hop, int n_mel, float clip, int* range_flag,
+int fft_stft_mel(const float* y, const float* window, const void* mel_slots, int slots_per_lane, const float* mel_w,
+                 int n_pieces, float* out, int batch, int n, int hop, int n_mel, float clip, int* range_flag,
                  cudaStream_t stream) {
     using namespace fftk;
     if (int e = check_common(y, window, batch, n, hop)) return e;
-    WGB_REQUIRE(mel_parts && mel_w && out, "null pointer");
+    WGB_REQUIRE(mel_slots && mel_w && out, "null pointer");
     WGB_REQUIRE(n_mel >= 1 && n_mel <= kMaxMel, "n_mel (%d) must be in 1..%d", n_mel, kMaxMel);
-    WGB_REQUIRE(parts_per_lane >= 1 && parts_per_lane <= kMaxParts, "parts_per_lane (%d) must be in 1..%d", parts_per_lane,
-                kMaxParts);
-    WGB_REQUIRE(mel_w_total >= 0 && mel_w_total <= kMaxMelW, "packed mel weights (%d) exceed %d", mel_w_total, kMaxMelW);
+    WGB_REQUIRE(slots_per_lane >= 1 && slots_per_lane <= kMaxSlots, "slots_per_lane (%d) must be in 1..%d", slots_per_lane,
+                kMaxSlots);
+    WGB_REQUIRE(n_pieces >= 1 && n_pieces <= kMaxPieces, "n_pieces (%d) must be in 1..%d", n_pieces, kMaxPieces);
     MelParams p{};
-    p.y = y; p.window = window; p.mel_parts = static_cast<const int4*>(mel_parts); p.parts_per_lane = parts_per_lane;
-    p.mel_w = mel_w; p.mel_w_total = mel_w_total;
+    p.y = y; p.window = window; p.mel_slots = static_cast<const int4*>(mel_slots); p.slots_per_lane = slots_per_lane;
+    p.mel_w = reinterpret_cast<const float4*>(mel_w); p.n_pieces = n_pieces;
     p.out = out; p.batch = batch; p.n = n; p.frames = n / hop + 1; p.hop = hop; p.n_mel = n_mel; p.clip = clip;
     p.range_flag = range_flag;
-    const int smem = kMelWarps * kBufElems * 8 + kHalf * 8 + 32 * kMaxParts * 16 + mel_w_total * 4;
+    const int smem = kMelWarps * kBufElems * 8 + kHalf * 8 + 32 * kMaxSlots * 16 + n_pieces * 32;
     auto kern = range_flag ? fft_mel_kernel<true> : fft_mel_kernel<false>;
     WGB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 1;
     WGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMelThreads, smem));
     const long long resident = static_cast<long long>(sm_count()) * (per_sm > 0 ? per_sm : 1);
+    WGB_REQUIRE(static_cast<long long>(batch) * p.frames < 0x40000000LL, "too many frames");
     const long long want = (static_cast<long long>(batch) * p.frames + kMelWarps - 1) / kMelWarps;
     kern<<<static_cast<unsigned>(want < resident ? want : resident), kMelThreads, smem, stream>>>(p);
     WGB_LAUNCH_CHECK();

@@ -92,49 +92,56 @@ class TacotronSTFT(torch.nn.Module):
             cached = self._mel_pair_ok
         return (tab, self._mel_tab[2]) if cached[1] else None
 
-    def _mel_parts(self, device):
-        """mel_basis as balanced bands for wgb_fft_stft_mel: (parts int32 [32, P, 4] = {first bin, bins, offset into the
-        packed weights, filter} per lane of a warp, packed weights fp32 = the rows of mel_basis over their non-zero spans),
-        or None when the basis is too dense for the kernel's shared-memory tables.  A row wider than the average load of
-        a lane is cut into two halves (never more: two partial sums commute, so the result stays order-independent); the
-        pieces are dealt to the 32 lanes longest-first onto the least loaded lane."""
+    def _mel_slots(self, device):
+        """mel_basis for wgb_fft_stft_mel: (slots int32 [32, S, 4], piece weights fp32 [n_pieces, 8], S), or None when the
+        basis does not fit the kernel's shared-memory tables.  A filter's non-zero span is covered by pieces of 8 bins
+        that start at multiples of 4 (two aligned 16-byte reads of |X| each; weights zero outside the span); whole
+        filters are dealt to the 32 lanes of a warp, most pieces first onto the least loaded lane, and a lane's slots list
+        its filters' pieces in order: {first bin / 4, piece, filter to emit after this piece or -1, starts a filter}.
+        Piece 0 is all zeros: filters without any weight emit it (log(clip), like the reference's matmul), and it pads
+        the shorter lanes."""
         key = (str(device), self.mel_basis.data_ptr(), self.mel_basis._version)
-        cached = getattr(self, "_mel_parts_pack", None)
+        cached = getattr(self, "_mel_slots_pack", None)
         if cached is None or cached[0] != key:
             basis = self.mel_basis.detach().float().cpu()
             n_mel, n_bins = basis.shape
-            spans, vals, off = [], [], 0
-            for m in range(n_mel):
-                nz = torch.nonzero(basis[m]).flatten()
-                lo, cnt = (int(nz[0]), int(nz[-1]) - int(nz[0]) + 1) if nz.numel() else (0, 0)
-                spans.append((lo, cnt, off))
-                vals.append(basis[m, lo: lo + cnt])
-                off += cnt
             pack = None
-            if n_mel <= 128 and off <= 4096 and n_bins == self.stft_fn.cutoff:
-                target = max(8, -(-off // 32))
-                pieces = []
-                for m, (lo, cnt, o) in enumerate(spans):
-                    if cnt > target:
-                        h = (cnt + 1) // 2
-                        pieces += [(h, lo, o, m), (cnt - h, lo + h, o + h, m)]
-                    elif cnt > 0:
-                        pieces.append((cnt, lo, o, m))
+            if n_mel <= 128 and n_bins == self.stft_fn.cutoff and n_bins == 513:
+                weights = [torch.zeros(8)]
+                filters = []                                   # (number of pieces, filter, [(bin4, piece), ...])
+                padded = torch.zeros((n_mel, 544))
+                padded[:, :n_bins] = basis
+                for m in range(n_mel):
+                    nz = torch.nonzero(basis[m]).flatten()
+                    if nz.numel() == 0:
+                        filters.append((1, m, [(0, 0)]))
+                        continue
+                    lo, hi = int(nz[0]), int(nz[-1]) + 1
+                    pieces = []
+                    for start in range(lo // 4 * 4, hi, 8):
+                        w = padded[m, start: start + 8].clone()
+                        w[: max(lo - start, 0)] = 0.0
+                        if hi - start < 8:
+                            w[hi - start:] = 0.0
+                        pieces.append((start // 4, len(weights)))
+                        weights.append(w)
+                    filters.append((len(pieces), m, pieces))
                 lanes, load = [[] for _ in range(32)], [0] * 32
-                for cnt, lo, o, m in sorted(pieces, reverse=True):
+                for cnt, m, pieces in sorted(filters, key=lambda f: (-f[0], f[1])):
                     i = min(range(32), key=lambda j: (load[j], j))
-                    lanes[i].append([lo, cnt, o, m])
-                    load[i] += cnt + 4                  # + the fixed cost of a piece (table read, shared-memory add)
-                per_lane = max(1, max(len(x) for x in lanes))
-                if per_lane <= 16:
+                    for q, (bin4, piece) in enumerate(pieces):
+                        lanes[i].append([bin4, piece, m if q == cnt - 1 else -1, 1 if q == 0 else 0])
+                    load[i] += cnt
+                per_lane = max(load)
+                if per_lane <= 24 and len(weights) <= 512:
                     table = torch.zeros((32, per_lane, 4), dtype=torch.int32)
+                    table[:, :, 2] = -1                       # padding slots: the zero piece, nothing emitted
                     for i, lst in enumerate(lanes):
-                        for q, piece in enumerate(lst):
-                            table[i, q] = torch.tensor(piece, dtype=torch.int32)
-                    w = torch.cat(vals) if off else torch.zeros(1)
-                    pack = (table.contiguous().to(device), w.contiguous().to(device), per_lane)
-            self._mel_parts_pack = (key, pack)
-            cached = self._mel_parts_pack
+                        for q, slot in enumerate(lst):
+                            table[i, q] = torch.tensor(slot, dtype=torch.int32)
+                    pack = (table.contiguous().to(device), torch.stack(weights).contiguous().to(device), per_lane)
+            self._mel_slots_pack = (key, pack)
+            cached = self._mel_slots_pack
         return cached[1]
 
     def mel_spectrogram(self, y: torch.Tensor) -> torch.Tensor:
@@ -161,7 +168,7 @@ class TacotronSTFT(torch.nn.Module):
         b = y.shape[0]
         s = _lib.stream_ptr()
         if self.fused:                        # stock STFT bases: FFT, |X|, filterbank and log-clamp in one butterfly kernel
-            out = self.stft_fn._mel_fft(y, self._mel_parts(y.device), self.n_mel_channels, 1e-5, range_flag)
+            out = self.stft_fn._mel_fft(y, self._mel_slots(y.device), self.n_mel_channels, 1e-5, range_flag)
             if out is not None:
                 return out
         if self.stft_fn._use_tc():
