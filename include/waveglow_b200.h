@@ -43,7 +43,10 @@ WGB_API const char* wgb_last_error(void);
  *                   with evict_first (slower: 6.0 ms), bit 2 = mel_stack evict_last, bit 3 = acts stores evict_first
  *   "res_l2_hint"   wgb_tc2_wn_res*: bit 0 = weights evict_last, bit 1 = activations evict_first (default 0: 1.20 ms
  *                   either way for bit 0, 1.26 ms with bit 1)
- *   "stft_l2_hint"  wgb_tc2_stft_* / wgb_tc2_istft_ola / wgb_tc2_gemm_split3: bit 0 = basis tiles evict_last */
+ *   "stft_l2_hint"  wgb_tc2_stft_* / wgb_tc2_istft_ola / wgb_tc2_gemm_split3: bit 0 = basis tiles evict_last (default 0:
+ *                   no effect, profiles/r02l_stft_l2_hint_ab.json)
+ *   "fft_mel_warps" wgb_fft_stft_mel: 12 (default; 168 registers per thread) or 16 (128 registers, small spills) warps
+ *                   per CTA, one CTA per SM */
 WGB_API int wgb_set_tuning(const char* key, int value);
 /* 0 iff `device` exists and is compute capability 10.x; selects nothing. */
 WGB_API int wgb_device_check(int device);

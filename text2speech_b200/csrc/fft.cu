@@ -24,8 +24,8 @@ using namespace fft;
 
 constexpr int kL = 1024;
 constexpr int kHalf = kL / 2;
-constexpr int kMelWarps = 12;             // one CTA per SM: 12 warps x 168 registers (the next frame's samples are
-constexpr int kMelThreads = kMelWarps * 32;   // prefetched into registers)
+// mel: one CTA per SM of 12 warps x 168 registers (default; the next frame's samples are prefetched into registers) or of
+// 16 warps x 128 registers with a few spills (wgb_set_tuning "fft_mel_warps" = 16, A/B)
 constexpr int kDnWarps = 12;              // denoise: the same (the register file is split over 4 schedulers: 3 warps each)
 constexpr int kDnThreads = kDnWarps * 32;
 constexpr int kMaxMel = 128;
@@ -146,8 +146,9 @@ struct MelParams {
     int* range_flag;           // optional: set to 1 when a sample is outside [-1, 1] or NaN (layers.py:72-73)
 };
 
-template <bool CHECK>
-__global__ void __launch_bounds__(kMelThreads, 1) fft_mel_kernel(const MelParams p) {
+template <bool CHECK, int kMelWarps>
+__global__ void __launch_bounds__(kMelWarps * 32, 1) fft_mel_kernel(const MelParams p) {
+    constexpr int kMelThreads = kMelWarps * 32;
     extern __shared__ __align__(16) unsigned char smem[];
     cf* bufs = reinterpret_cast<cf*>(smem);                                         // [kMelWarps][kBufElems]
     float2* win2 = reinterpret_cast<float2*>(bufs + kMelWarps * kBufElems);         // [512]
@@ -359,15 +360,17 @@ int fft_stft_mel(const float* y, const float* window, const void* mel_slots, int
     p.mel_w = reinterpret_cast<const float4*>(mel_w); p.n_pieces = n_pieces;
     p.out = out; p.batch = batch; p.n = n; p.frames = n / hop + 1; p.hop = hop; p.n_mel = n_mel; p.clip = clip;
     p.range_flag = range_flag;
-    const int smem = kMelWarps * kBufElems * 8 + kHalf * 8 + 32 * kMaxSlots * 16 + n_pieces * 32;
-    auto kern = range_flag ? fft_mel_kernel<true> : fft_mel_kernel<false>;
+    WGB_REQUIRE(static_cast<long long>(batch) * p.frames < 0x40000000LL, "too many frames");
+    const int warps = tuning_get("fft_mel_warps") == 16 ? 16 : 12;
+    const int smem = warps * kBufElems * 8 + kHalf * 8 + 32 * kMaxSlots * 16 + n_pieces * 32;
+    void (*kern)(MelParams) = warps == 16 ? (range_flag ? fft_mel_kernel<true, 16> : fft_mel_kernel<false, 16>)
+                                          : (range_flag ? fft_mel_kernel<true, 12> : fft_mel_kernel<false, 12>);
     WGB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 1;
-    WGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMelThreads, smem));
+    WGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
     const long long resident = static_cast<long long>(sm_count()) * (per_sm > 0 ? per_sm : 1);
-    WGB_REQUIRE(static_cast<long long>(batch) * p.frames < 0x40000000LL, "too many frames");
-    const long long want = (static_cast<long long>(batch) * p.frames + kMelWarps - 1) / kMelWarps;
-    kern<<<static_cast<unsigned>(want < resident ? want : resident), kMelThreads, smem, stream>>>(p);
+    const long long want = (static_cast<long long>(batch) * p.frames + warps - 1) / warps;
+    kern<<<static_cast<unsigned>(want < resident ? want : resident), warps * 32, smem, stream>>>(p);
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }

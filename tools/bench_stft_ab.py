@@ -57,8 +57,11 @@ def main():
         with open(args.out, "w") as f:
             json.dump(out, f, indent=1)
         return
-    for name, algo, pair, fused in (("fft", "auto", True, True), ("pair", "gemm", True, True),
+    from text2speech_b200 import _lib
+    for name, algo, pair, fused in (("fft", "auto", True, True), ("fft_mel_16_warps", "auto", True, True),
+                                    ("fft_again", "auto", True, True), ("pair", "gemm", True, True),
                                     ("pair_separate_overlap_add", "gemm", True, False), ("one_cta", "gemm", False, False)):
+        _lib.call("wgb_set_tuning", "fft_mel_warps", 16 if name == "fft_mel_16_warps" else 12)
         taco.stft_fn.algorithm = den.stft.algorithm = algo
         taco.stft_fn.pair = den.stft.pair = pair
         den.stft.fused_ola = fused
