@@ -965,6 +965,34 @@ def test_fft_stft_other_windows_and_hops(lib):
         assert util.snr_db(got.cpu(), want) >= 100.0, (window, win_length, util.snr_db(got.cpu(), want))
 
 
+def test_fft_kernels_write_only_their_output(models, lib):
+    """compute-sanitizer is closed on this GPU pool, so the bounds of the butterfly kernels' stores are checked by hand:
+    the outputs sit inside larger buffers pre-filled with a sentinel, called through the C ABI at ragged shapes (signal
+    shorter than a filter, odd length, a last partial hop, batch > 1), and every byte outside the output must survive."""
+    import text2speech_b200 as t2s
+    dev = torch.device(DEV)
+    taco = t2s.TacotronSTFT(1024, 256, 1024, 80, 22050, 0.0, 8000.0).to(DEV)
+    stft = taco.stft_fn
+    win, env = stft._fft_pack(dev)
+    slots, weights, per_lane = taco._mel_slots(dev)
+    bias = (torch.rand(513) * 0.05).to(DEV)
+    guard, sentinel = 4096, -12345.0
+    for B, n in ((1, 513), (2, 777), (3, 256 * 9 + 255), (2, 256 * 40)):
+        y = (syn.synthetic_waveforms(B, n, sr=22050, seed=n) * 0.9).to(DEV).contiguous()
+        frames = n // 256 + 1
+        for kind, size in (("mel", B * 80 * frames), ("denoise", B * 256 * (frames - 1))):
+            big = torch.full((guard + size + guard,), sentinel, device=DEV, dtype=torch.float32)
+            out = big[guard: guard + size]
+            if kind == "mel":
+                lib.call("wgb_fft_stft_mel", y, win, slots, per_lane, weights, weights.shape[0], out, B, n, 256, 80, 1e-5, None,
+                         lib.stream_ptr())
+            else:
+                lib.call("wgb_fft_denoise", y, win, bias, 0.1, env, out, B, n, 256, lib.stream_ptr())
+            torch.cuda.synchronize()
+            assert bool((big[:guard] == sentinel).all()) and bool((big[guard + size:] == sentinel).all()), (kind, B, n)
+            assert bool(torch.isfinite(out).all()) and not bool((out == sentinel).any()), (kind, B, n)
+
+
 def test_fft_stft_range_flag_and_edited_bases(lib):
     """layers.py:72-73 on the butterfly path: one sample outside [-1, 1] anywhere (first, last, around hop boundaries, in the
     tail that only the last frame covers) or a NaN raises AssertionError; in-range input does not.  A forward_basis that is no
