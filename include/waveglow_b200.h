@@ -45,6 +45,10 @@ WGB_API const char* wgb_last_error(void);
  *                   either way for bit 0, 1.26 ms with bit 1)
  *   "stft_l2_hint"  wgb_tc2_stft_* / wgb_tc2_istft_ola / wgb_tc2_gemm_split3: bit 0 = basis tiles evict_last (default 0:
  *                   no effect, profiles/r02l_stft_l2_hint_ab.json)
+ *   "pdl"           1 (default): the persistent WN kernels (wgb_tc2_wn_*, wgb_tc_wn_skip16_end, wgb_x_stack) are launched
+ *                   with programmatic stream serialization: a kernel's CTAs start on an SM as soon as the previous kernel's
+ *                   CTA there has exited and run their prologue while its slowest CTAs finish; they wait for the previous
+ *                   grid's completion before their first access to activations.  0: plain stream order.
  *   "fft_mel_warps" wgb_fft_stft_mel: 12 (default; 168 registers per thread) or 16 (128 registers, small spills) warps
  *                   per CTA, one CTA per SM */
 WGB_API int wgb_set_tuning(const char* key, int value);

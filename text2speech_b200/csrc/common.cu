@@ -61,13 +61,14 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     return WGB_OK;
 }
 
-static std::atomic<int> g_gate_l2_hint{1}, g_res_l2_hint{0}, g_stft_l2_hint{0}, g_fft_mel_warps{12};
+static std::atomic<int> g_gate_l2_hint{1}, g_res_l2_hint{0}, g_stft_l2_hint{0}, g_fft_mel_warps{12}, g_pdl{1};
 
 int tuning_get(const char* key) {
     if (std::strcmp(key, "gate_l2_hint") == 0) return g_gate_l2_hint.load(std::memory_order_relaxed);
     if (std::strcmp(key, "res_l2_hint") == 0) return g_res_l2_hint.load(std::memory_order_relaxed);
     if (std::strcmp(key, "stft_l2_hint") == 0) return g_stft_l2_hint.load(std::memory_order_relaxed);
     if (std::strcmp(key, "fft_mel_warps") == 0) return g_fft_mel_warps.load(std::memory_order_relaxed);
+    if (std::strcmp(key, "pdl") == 0) return g_pdl.load(std::memory_order_relaxed);
     return 0;
 }
 int tuning_set(const char* key, int value) {
@@ -86,6 +87,10 @@ int tuning_set(const char* key, int value) {
     }
     if (std::strcmp(key, "fft_mel_warps") == 0) {
         g_fft_mel_warps.store(value, std::memory_order_relaxed);
+        return WGB_OK;
+    }
+    if (std::strcmp(key, "pdl") == 0) {
+        g_pdl.store(value, std::memory_order_relaxed);
         return WGB_OK;
     }
     return fail(WGB_ERR_ARGUMENT, "unknown tuning key '%s'", key);

@@ -48,4 +48,32 @@ int sm_count();   // SMs of the current device (cached)
 int tuning_get(const char* key);
 int tuning_set(const char* key, int value);
 
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// -- as far as SM resources allow -- once every CTA of the kernel before it in the stream has executed
+// pdl_launch_dependents() (or exited); it must execute pdl_wait() before touching anything that kernel reads or writes:
+// the wait returns when the earlier grid has completed and its memory is visible.  Both are no-ops for a kernel launched
+// without the attribute / without a dependent.  The persistent WN kernels trigger at their first instruction, so the next
+// kernel's CTAs arrive on an SM the moment this kernel's CTA there exits and run their prologue (barrier init, TMEM
+// allocation, tensor-map prefetch, bias staging) while the slowest CTAs of this one are still finishing.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// <<<>>> with the programmatic-dependent-launch attribute when wgb_set_tuning("pdl") is on (default) and the kernel is
+// one of those that call pdl_wait() before their first dependent access
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = tuning_get("pdl") ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace wgb

@@ -124,6 +124,8 @@ int flow_mix(float* x, const float* w, long long rows, int C, cudaStream_t strea
 // the K = 64 operand of wgb_tc2_wn_gate_mel0: WN.start folded into in_layers[0] (glow.py:156,160).
 __global__ void x_stack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int T, long long rows,
                                long long out_batch_rows, int n_half) {
+    pdl_launch_dependents();
+    pdl_wait();                       // x comes from the kernel before this one
     const int base = 8 - 2 * n_half;
     for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < rows;
          r += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -165,8 +167,8 @@ __global__ void x_stack_kernel(const float* __restrict__ x, __nv_bfloat16* __res
 int x_stack(const float* x, void* out, int batch, int T, long long out_batch_rows, int n_half, cudaStream_t stream) {
     WGB_REQUIRE(x && out && batch > 0 && T > 0 && out_batch_rows >= T && n_half >= 1 && n_half <= 4, "bad arguments");
     const long long rows = static_cast<long long>(batch) * T;
-    x_stack_kernel<<<grid_for(rows, 128), 128, 0, stream>>>(x, static_cast<__nv_bfloat16*>(out), T, rows, out_batch_rows,
-                                                           n_half);
+    WGB_CUDA_TRY(launch_pdl(x_stack_kernel, grid_for(rows, 128), 128, 0, stream, x, static_cast<__nv_bfloat16*>(out), T, rows,
+                            out_batch_rows, n_half));
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }

@@ -63,6 +63,7 @@ skip16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();          // the next kernel may queue up behind this persistent grid right away
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -88,6 +89,7 @@ skip16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                       // everything above touched only weights; activations and the flow state start here
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -256,7 +258,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p,
     auto kern = skip16_kernel<NHALF, DIR>;
     WGB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-    kern<<<grid, kThreads, kSmemTotal, stream>>>(ma, mw, p);
+    WGB_CUDA_TRY(launch_pdl(kern, grid, kThreads, kSmemTotal, stream, ma, mw, p));
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }

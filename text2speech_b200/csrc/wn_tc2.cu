@@ -133,6 +133,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
+    pdl_launch_dependents();          // persistent grid: the next kernel may queue up behind this one right away
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a0);
@@ -180,6 +181,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     cluster_sync_all();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                       // everything above touched only weights / biases; activations start here
 
     const int n_pairs = gridDim.x >> 1;
     const int pair_id = blockIdx.x >> 1;
@@ -709,7 +711,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     const int n_items = ((p.n_tiles + 1) / 2) * (p.n_pass / p.ppi);
     int pairs = sm_count() / 2;
     if (n_items < pairs) pairs = n_items;
-    kern<<<2 * pairs, MODE == RES ? kThreadsRes : kThreads, smem, stream>>>(a0, a1, w, c, x ? *x : a0, p);
+    WGB_CUDA_TRY(launch_pdl(kern, 2 * pairs, MODE == RES ? kThreadsRes : kThreads, smem, stream, a0, a1, w, c, x ? *x : a0, p));
     WGB_LAUNCH_CHECK();
     return WGB_OK;
 }
