@@ -3,15 +3,20 @@
 // bases.  The reference's forward_basis is window * [cos; -sin](2 pi k n / L) and its inverse_basis the pseudo-inverse of that
 // (stft.py:46-60), i.e. a real DFT / inverse real DFT: 10 N log2 N = 0.05 MFLOP per frame as butterflies against 2.1 MFLOP
 // as a dense-basis contraction (x3 for fp32-grade accuracy on the bf16 tensor pipe).  These kernels are the HBM-side answer
-// to the tensor-core STFT kernels of stft_tc2.cu: the signal is read once, nothing but the result is written.
+// to the tensor-core STFT kernels of stft_tc2.cu: the signal is read from DRAM once, nothing but the result is written.
 //
-// One warp = one frame at a time: 1024 windowed samples -> 512-point complex FFT in registers + one 4.6 KB shared-memory
-// exchange buffer (fft_core.cuh) -> real-FFT split by warp shuffles.
-//   mel      |X| -> shared memory -> banded mel filterbank (each lane sums whole filters) -> log(clamp) -> a 32-frame output
-//            tile in shared memory, written as coalesced rows of out [B, n_mel, F]
-//   denoise  spectral subtraction on the lane's own bins -> inverse split -> the same FFT -> windowed frame; a warp walks
-//            a run of consecutive frames and keeps the overlap-add in REGISTERS: the lane's samples 2 (lane + 32 j) + {0,1} of
-//            frame r and samples of frame r + 1 that overlap them differ by j -> j - 4 in the same lane (hop = L / 4)
+// One warp = one frame at a time: 1024 windowed samples -> 512-point complex FFT in registers + two small shared-memory
+// exchange buffers (fft_core.cuh) -> real-FFT split by warp shuffles.  Warps are persistent and independent (no block-level
+// barrier after the tables are staged); the NEXT frame's samples are loaded into the registers that are dead between stage 1
+// and stage 3 of the current one, so no warp ever waits for global memory.
+//   mel      warps walk the flat frame axis of the batch a stride of all resident warps apart (an SM always works on
+//            consecutive, overlapping frames); |X| -> shared memory -> mel filterbank as 8-bin pieces, every filter summed by
+//            one lane in a fixed order -> log(clamp) -> 4-byte stores into out [B, n_mel, F] that merge in L2 with the
+//            neighbouring warps' frames
+//   denoise  spectral subtraction on the lane's own bins -> inverse split -> the same butterfly code again (a 2-trip loop:
+//            one copy in the instruction cache) -> windowed frame; a warp walks a run of consecutive frames and keeps the
+//            overlap-add in REGISTERS: the lane's samples 2 (lane + 32 j) + {0,1} of frame r and the samples of frame r + 1
+//            that overlap them differ by j -> j - 4 in the same lane (hop = L / 4)
 // L = 1024 only (the config's filter length); other shapes, and hand-edited bases, stay on the dense-basis kernels.
 #include "common.cuh"
 #include "fft_core.cuh"
