@@ -4,7 +4,8 @@
 
 One block per kernel: total SASS instructions and the counts of the mnemonics that prove what the kernel is built
 from -- tcgen05 MMA (UTCHMMA / UTCQMMA...), TMEM loads (LDTM), TMEM alloc (UTCATOMSWS...), TMA (UTMALDG / UTMASTG /
-UTMAPF), mbarrier traffic (SYNCS), tcgen05.commit (UTCBAR), MUFU (tanh / ex2), legacy tensor ops (HMMA: must be 0).
+UTMAPF), mbarrier traffic (SYNCS), tcgen05.commit (UTCBAR), MUFU (tanh / ex2), legacy tensor ops (HMMA: must be 0),
+programmatic dependent launch (PREEXIT = griddepcontrol.launch_dependents, ACQBULK = griddepcontrol.wait).
 """
 import collections
 import os
@@ -16,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "text2speech_b200", "libwaveglow_b200.so")
 INTEREST = ("UTCHMMA", "UTCQMMA", "UTCOMMA", "UTCIMMA", "LDTM", "STTM", "UTCATOMSWS", "UTCBAR", "UTCCP", "UTMALDG", "UTMASTG",
             "UTMAPF", "UTMACCTL", "UTMACMDFLUSH", "SYNCS", "MUFU.TANH", "MUFU.EX2", "MUFU.RCP", "HMMA", "IMMA", "DMMA", "FFMA",
-            "LDG", "STG", "LDS", "STS", "RED", "ATOM", "BAR.SYNC", "UCGABAR")
+            "LDG", "STG", "LDS", "STS", "RED", "ATOM", "BAR.SYNC", "UCGABAR", "SHFL", "PREEXIT", "ACQBULK")
 
 
 def main():
