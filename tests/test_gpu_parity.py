@@ -1059,13 +1059,21 @@ def test_stft_without_window(golden, lib):
     assert util.rel_l2(stft.inverse(mag, phase).cpu(), golden["nowin_recon"]) <= 1e-4
 
 
-@pytest.mark.parametrize("precision", ["tc", "fp32"])
+@pytest.mark.parametrize("precision", ["auto", "tc", "fp32"])
 def test_mel_spectrogram(golden, lib, precision):
+    """Against the unmodified reference's mel (golden file): 'auto' = the default path (butterfly kernel), 'tc' = tensor-core
+    dense-basis kernels, 'fp32' = CUDA-core validation path."""
     import text2speech_b200 as t2s
     taco = t2s.TacotronSTFT(1024, 256, 1024, 80, DC["sampling_rate"], DC["mel_fmin"], DC["mel_fmax"]).to(DEV)
     taco.stft_fn.precision = precision
     y = syn.synthetic_waveforms(2, 4096, sr=DC["sampling_rate"], seed=5).to(DEV)
-    mel = taco.mel_spectrogram(y)
+    calls, raw = [], lib.call
+    lib.call = lambda name, *a: (calls.append(name), raw(name, *a))[1]
+    try:
+        mel = taco.mel_spectrogram(y)
+    finally:
+        lib.call = raw
+    assert (calls == ["wgb_fft_stft_mel"]) == (precision == "auto"), calls
     assert mel.shape == (2, 80, 17)
     assert float((mel.cpu() - torch.from_numpy(golden["mel"])).abs().max()) <= 1e-3
     if precision == "tc":                     # fused single-kernel path (default) vs separate mel matmul / log kernels
@@ -1093,10 +1101,13 @@ def test_denoiser(models, golden, lib):
     assert den.bias_spec.shape == (1, 513, 1)
     assert util.rel_l2(den.bias_spec.cpu(), golden["denoiser_bias_spec"]) <= 1e-4
     y = syn.synthetic_waveforms(2, 4096, sr=DC["sampling_rate"], seed=5).to(DEV)
-    for s, key in ((0.1, "denoised_s0p1"), (0.01, "denoised_s0p01")):
-        out = den(y, strength=s)
-        assert out.shape == (2, 1, 4096)
-        assert util.snr_db(out.cpu(), golden[key]) >= 60.0
+    for algorithm in ("auto", "gemm"):         # butterfly kernel (default) and tensor-core dense-basis kernels vs the reference
+        den.stft.algorithm = algorithm
+        for s, key in ((0.1, "denoised_s0p1"), (0.01, "denoised_s0p01")):
+            out = den(y, strength=s)
+            assert out.shape == (2, 1, 4096)
+            assert util.snr_db(out.cpu(), golden[key]) >= 60.0, (algorithm, key)
+    den.stft.algorithm = "auto"
     m.mode = "bf16"
     den16 = t2s.Denoiser(m)                                             # bias from the tensor-core path
     assert util.rel_l2(den16.bias_spec.cpu(), golden["denoiser_bias_spec"]) <= 2e-2
