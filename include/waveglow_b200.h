@@ -262,11 +262,13 @@ WGB_API int wgb_tc2_istft_ola(const void* s_hi, const void* s_lo, const void* w_
  * (zero outside the filter's span and past bin 512); mel_slots int32 [32][slots_per_lane][4] = {first bin / 4, piece,
  * filter to emit after this piece or -1, 1 if this piece starts a filter} lists, per lane of a warp, the pieces that lane
  * sums.  All pieces of a filter sit consecutively in ONE lane, so every filter is summed in a fixed order by one thread;
- * unused slots name an all-zero piece and emit nothing.  range_flag (optional int32) is set to 1 when a sample is outside
- * [-1, 1] or NaN (layers.py:72-73).  n > 512, n_mel <= 128, slots_per_lane <= 24, n_pieces <= 512. */
+ * unused slots name an all-zero piece and emit nothing.  bins_used = one past the last bin any piece with weight covers
+ * (513 = all; at most 384 lets the kernel skip the upper quarter of the spectrum, which the usual 8 kHz filterbank never
+ * reads).  range_flag (optional int32) is set to 1 when a sample is outside [-1, 1] or NaN (layers.py:72-73).  n > 512,
+ * n_mel <= 128, slots_per_lane <= 24, n_pieces <= 512. */
 WGB_API int wgb_fft_stft_mel(const float* y, const float* window, const void* mel_slots, int slots_per_lane,
-                             const float* mel_w, int n_pieces, float* out, int batch, int n, int hop, int n_mel,
-                             float clip, int* range_flag, void* stream);
+                             const float* mel_w, int n_pieces, int bins_used, float* out, int batch, int n, int hop,
+                             int n_mel, float clip, int* range_flag, void* stream);
 /* Denoiser.forward (denoiser.py:35-40) = STFT.transform, clamp(|X| - bias_spec * strength, 0) with the phase kept,
  * STFT.inverse (stft.py:99-130: overlap-add, window-sum normalisation, L/hop scale, L/2 trim) in ONE kernel: a warp walks a
  * run of consecutive frames and holds the overlap-add in registers.  y fp32 [B][n]; bias_spec fp32 [513]; env_tab fp32

@@ -974,7 +974,7 @@ def test_fft_kernels_write_only_their_output(models, lib):
     taco = t2s.TacotronSTFT(1024, 256, 1024, 80, 22050, 0.0, 8000.0).to(DEV)
     stft = taco.stft_fn
     win, env = stft._fft_pack(dev)
-    slots, weights, per_lane = taco._mel_slots(dev)
+    slots, weights, per_lane, bins_used = taco._mel_slots(dev)
     bias = (torch.rand(513) * 0.05).to(DEV)
     guard, sentinel = 4096, -12345.0
     for B, n in ((1, 513), (2, 777), (3, 256 * 9 + 255), (2, 256 * 40)):
@@ -984,8 +984,8 @@ def test_fft_kernels_write_only_their_output(models, lib):
             big = torch.full((guard + size + guard,), sentinel, device=DEV, dtype=torch.float32)
             out = big[guard: guard + size]
             if kind == "mel":
-                lib.call("wgb_fft_stft_mel", y, win, slots, per_lane, weights, weights.shape[0], out, B, n, 256, 80, 1e-5, None,
-                         lib.stream_ptr())
+                lib.call("wgb_fft_stft_mel", y, win, slots, per_lane, weights, weights.shape[0], bins_used, out, B, n, 256, 80,
+                         1e-5, None, lib.stream_ptr())
             else:
                 lib.call("wgb_fft_denoise", y, win, bias, 0.1, env, out, B, n, 256, lib.stream_ptr())
             torch.cuda.synchronize()

@@ -234,6 +234,10 @@ def _fft_denoise_emulated(y, win, env, bias, strength, hop, scale):
     return out
 
 
+def mb_check(taco):
+    return taco.mel_basis.abs().sum(0)
+
+
 def test_fft_path_operands_reproduce_the_oracle():
     """Host side of the butterfly path on the CPU: the stock-basis test, the window / envelope tables of STFT._fft_pack
     and the banded mel rows of TacotronSTFT._mel_rows, pushed through a torch.fft emulation of the kernels' arithmetic,
@@ -249,7 +253,8 @@ def test_fft_path_operands_reproduce_the_oracle():
         fwd, inv = oracle.stft_bases(1024, hop, win_length, window=window)
         if window is not None:
             taco = TacotronSTFT(1024, hop, win_length, 80, DC["sampling_rate"], DC["mel_fmin"], DC["mel_fmax"])
-            slots, weights, per_lane = taco._mel_slots(CPU)
+            slots, weights, per_lane, bins_used = taco._mel_slots(CPU)
+            assert bins_used == 376 and int(torch.nonzero(mb_check(taco)).max()) < bins_used     # 8 kHz at 22.05 kHz: bin 371
             assert slots.dtype == torch.int32 and slots.shape == (32, per_lane, 4) and per_lane <= 24
             assert weights.shape[1] == 8 and weights.shape[0] <= 512 and float(weights[0].abs().max()) == 0.0
             assert int(slots[..., 0].max()) * 4 + 8 <= 528                # the last piece stays inside the |X| buffer

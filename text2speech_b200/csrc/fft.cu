@@ -111,14 +111,16 @@ __device__ __forceinline__ cf partner_of(const cf* v, int j, int lane) {
     return p;
 }
 
-// Z (v) -> X in place; returns X[512] (meaningful in lane 0)
+// Z (v) -> X in place for the bins k = lane + 32 j with j < J_USED (compile time; the others keep Z: the mel filterbank
+// at 22.05 kHz / 8 kHz reads bins 0..371 only); returns X[512] (meaningful in lane 0)
+template <int J_USED = 16>
 __device__ __forceinline__ float rfft_split(int lane, const LaneTw& tw, cf* v) {
     const float nyq = v[0].x - v[0].y;
-    cf x[16];
+    cf x[J_USED];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) x[j] = rfft_bin(v[j], partner_of(v, j, lane), cmul(tw.post, w32(j)));
+    for (int j = 0; j < J_USED; ++j) x[j] = rfft_bin(v[j], partner_of(v, j, lane), cmul(tw.post, w32(j)));
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = x[j];
+    for (int j = 0; j < J_USED; ++j) v[j] = x[j];
     return nyq;
 }
 
@@ -151,7 +153,7 @@ struct MelParams {
     int* range_flag;           // optional: set to 1 when a sample is outside [-1, 1] or NaN (layers.py:72-73)
 };
 
-template <bool CHECK, int kMelWarps>
+template <bool CHECK, int kMelWarps, int J_USED>
 __global__ void __launch_bounds__(kMelWarps * 32, 1) fft_mel_kernel(const MelParams p) {
     constexpr int kMelThreads = kMelWarps * 32;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -193,9 +195,10 @@ __global__ void __launch_bounds__(kMelWarps * 32, 1) fft_mel_kernel(const MelPar
         stage2(lane, tw, buf_a, buf_b);
         __syncwarp();
         stage3(lane, v, buf_b);
-        const float nyq = rfft_split(lane, tw, v);
+        const float nyq = rfft_split<J_USED>(lane, tw, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) mag[lane + 32 * j] = sqrt_approx(v[j].x * v[j].x + v[j].y * v[j].y);      // stft.py:94
+        for (int j = 0; j < 16; ++j)                                                // stft.py:94; bins nobody reads stay zero
+            mag[lane + 32 * j] = j < J_USED ? sqrt_approx(v[j].x * v[j].x + v[j].y * v[j].y) : 0.f;
         if (lane < kMagPad - kHalf) mag[kHalf + lane] = lane == 0 ? fabsf(nyq) : 0.f;
         __syncwarp();
         {                                                                           // layers.py:77
@@ -351,7 +354,7 @@ static int check_common(const float* y, const float* window, int batch, int n, i
 }
 
 int fft_stft_mel(const float* y, const float* window, const void* mel_slots, int slots_per_lane, const float* mel_w,
-                 int n_pieces, float* out, int batch, int n, int hop, int n_mel, float clip, int* range_flag,
+                 int n_pieces, int bins_used, float* out, int batch, int n, int hop, int n_mel, float clip, int* range_flag,
                  cudaStream_t stream) {
     using namespace fftk;
     if (int e = check_common(y, window, batch, n, hop)) return e;
@@ -360,6 +363,7 @@ int fft_stft_mel(const float* y, const float* window, const void* mel_slots, int
     WGB_REQUIRE(slots_per_lane >= 1 && slots_per_lane <= kMaxSlots, "slots_per_lane (%d) must be in 1..%d", slots_per_lane,
                 kMaxSlots);
     WGB_REQUIRE(n_pieces >= 1 && n_pieces <= kMaxPieces, "n_pieces (%d) must be in 1..%d", n_pieces, kMaxPieces);
+    WGB_REQUIRE(bins_used >= 1 && bins_used <= kHalf + 1, "bins_used (%d) must be in 1..%d", bins_used, kHalf + 1);
     MelParams p{};
     p.y = y; p.window = window; p.mel_slots = static_cast<const int4*>(mel_slots); p.slots_per_lane = slots_per_lane;
     p.mel_w = reinterpret_cast<const float4*>(mel_w); p.n_pieces = n_pieces;
@@ -368,8 +372,13 @@ int fft_stft_mel(const float* y, const float* window, const void* mel_slots, int
     WGB_REQUIRE(static_cast<long long>(batch) * p.frames < 0x40000000LL, "too many frames");
     const int warps = tuning_get("fft_mel_warps") == 16 ? 16 : 12;
     const int smem = warps * kBufElems * 8 + kHalf * 8 + 32 * kMaxSlots * 16 + n_pieces * 32;
-    void (*kern)(MelParams) = warps == 16 ? (range_flag ? fft_mel_kernel<true, 16> : fft_mel_kernel<false, 16>)
-                                          : (range_flag ? fft_mel_kernel<true, 12> : fft_mel_kernel<false, 12>);
+    // bins 0 .. 383 suffice for the usual filterbanks (fmax 8 kHz at 22.05 kHz ends at bin 371): the real-FFT split and the
+    // magnitudes of the upper quarter are then compiled out (bin 512, the Nyquist bin, is always computed)
+    const bool quarter = bins_used <= 384 && warps == 12;
+    void (*kern)(MelParams) =
+        warps == 16 ? (range_flag ? fft_mel_kernel<true, 16, 16> : fft_mel_kernel<false, 16, 16>)
+        : quarter   ? (range_flag ? fft_mel_kernel<true, 12, 12> : fft_mel_kernel<false, 12, 12>)
+                    : (range_flag ? fft_mel_kernel<true, 12, 16> : fft_mel_kernel<false, 12, 16>);
     WGB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 1;
     WGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));

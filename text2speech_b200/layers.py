@@ -93,7 +93,8 @@ class TacotronSTFT(torch.nn.Module):
         return (tab, self._mel_tab[2]) if cached[1] else None
 
     def _mel_slots(self, device):
-        """mel_basis for wgb_fft_stft_mel: (slots int32 [32, S, 4], piece weights fp32 [n_pieces, 8], S), or None when the
+        """mel_basis for wgb_fft_stft_mel: (slots int32 [32, S, 4], piece weights fp32 [n_pieces, 8], S, bins the pieces
+        with weight reach), or None when the
         basis does not fit the kernel's shared-memory tables.  A filter's non-zero span is covered by pieces of 8 bins
         that start at multiples of 4 (two aligned 16-byte reads of |X| each; weights zero outside the span); whole
         filters are dealt to the 32 lanes of a warp, most pieces first onto the least loaded lane, and a lane's slots list
@@ -139,7 +140,9 @@ class TacotronSTFT(torch.nn.Module):
                     for i, lst in enumerate(lanes):
                         for q, slot in enumerate(lst):
                             table[i, q] = torch.tensor(slot, dtype=torch.int32)
-                    pack = (table.contiguous().to(device), torch.stack(weights).contiguous().to(device), per_lane)
+                    bins_used = max([4 * bin4 + 8 for _, _, pieces in filters for bin4, piece in pieces if piece] + [1])
+                    pack = (table.contiguous().to(device), torch.stack(weights).contiguous().to(device), per_lane,
+                            min(bins_used, n_bins))
             self._mel_slots_pack = (key, pack)
             cached = self._mel_slots_pack
         return cached[1]
