@@ -258,17 +258,18 @@ WGB_API int wgb_tc2_istft_ola(const void* s_hi, const void* s_lo, const void* w_
  *
  * TacotronSTFT.mel_spectrogram (layers.py:63-79; stft.py:79-97): y fp32 [B][n] -> out fp32 [B][n_mel][n / hop + 1] =
  * log(clamp(mel_basis |STFT(y)|, clip)).  window fp32 [1024] (zero-padded window, ones for window=None).  The filterbank
- * arrives as PIECES of 8 consecutive bins starting at a multiple of 4: mel_w fp32 [n_pieces][8] holds the piece's weights
- * (zero outside the filter's span and past bin 512); mel_slots int32 [32][slots_per_lane][4] = {first bin / 4, piece,
- * filter to emit after this piece or -1, 1 if this piece starts a filter} lists, per lane of a warp, the pieces that lane
- * sums.  All pieces of a filter sit consecutively in ONE lane, so every filter is summed in a fixed order by one thread;
- * unused slots name an all-zero piece and emit nothing.  bins_used = one past the last bin any piece with weight covers
- * (513 = all; at most 384 lets the kernel skip the upper quarter of the spectrum, which the usual 8 kHz filterbank never
- * reads).  range_flag (optional int32) is set to 1 when a sample is outside [-1, 1] or NaN (layers.py:72-73).  n > 512,
- * n_mel <= 128, slots_per_lane <= 24, n_pieces <= 512. */
+ * arrives as PIECES of 8 consecutive bins starting at a multiple of 4, dealt to the 32 lanes of a warp: lane l sums the
+ * pieces [q][l], q = 0 .. slots_per_lane - 1, in order.  mel_slots int32 [slots_per_lane][32] = first bin / 4 | (filter to
+ * emit after this piece + 1) << 8 | (1 if the piece starts a filter) << 16; mel_w fp32 [slots_per_lane][2][32][4] = the
+ * piece's 8 weights as two float4 with the lanes innermost (zero outside the filter's span and past bin 512).  All pieces
+ * of a filter sit consecutively in ONE lane, so every filter is summed in a fixed order by one thread; unused slots carry
+ * zero weights and emit nothing.  bins_used = one past the last bin any piece with weight covers (513 = all; at most 384
+ * lets the kernel skip the upper quarter of the spectrum, which the usual 8 kHz filterbank never reads).  range_flag
+ * (optional int32) is set to 1 when a sample is outside [-1, 1] or NaN (layers.py:72-73).  n > 512, n_mel <= 128,
+ * slots_per_lane <= 16. */
 WGB_API int wgb_fft_stft_mel(const float* y, const float* window, const void* mel_slots, int slots_per_lane,
-                             const float* mel_w, int n_pieces, int bins_used, float* out, int batch, int n, int hop,
-                             int n_mel, float clip, int* range_flag, void* stream);
+                             const float* mel_w, int bins_used, float* out, int batch, int n, int hop, int n_mel,
+                             float clip, int* range_flag, void* stream);
 /* Denoiser.forward (denoiser.py:35-40) = STFT.transform, clamp(|X| - bias_spec * strength, 0) with the phase kept,
  * STFT.inverse (stft.py:99-130: overlap-add, window-sum normalisation, L/hop scale, L/2 trim) in ONE kernel: a warp walks a
  * run of consecutive frames and holds the overlap-add in registers.  y fp32 [B][n]; bias_spec fp32 [513]; env_tab fp32

@@ -984,8 +984,8 @@ def test_fft_kernels_write_only_their_output(models, lib):
             big = torch.full((guard + size + guard,), sentinel, device=DEV, dtype=torch.float32)
             out = big[guard: guard + size]
             if kind == "mel":
-                lib.call("wgb_fft_stft_mel", y, win, slots, per_lane, weights, weights.shape[0], bins_used, out, B, n, 256, 80,
-                         1e-5, None, lib.stream_ptr())
+                lib.call("wgb_fft_stft_mel", y, win, slots, per_lane, weights, bins_used, out, B, n, 256, 80, 1e-5, None,
+                         lib.stream_ptr())
             else:
                 lib.call("wgb_fft_denoise", y, win, bias, 0.1, env, out, B, n, 256, lib.stream_ptr())
             torch.cuda.synchronize()

@@ -188,18 +188,20 @@ def test_ola_envelope_table_equals_reference_window_sum():
 
 def _fft_mel_emulated(y, win, slots, weights, n_mel, hop, clip=1e-5):
     """What wgb_fft_stft_mel computes, from ITS operands: reflect-indexed frames x window -> real FFT -> |X| (zeros past
-    bin 512) -> per lane, the slots in order: sum restarts on a filter's first piece, a piece = 8 bins from 4 * slot[0]
-    times weights[slot[1]], the running sum is the filter's value after its last piece -> log(clamp)."""
+    bin 512) -> per lane, the slots [q][lane] in order: sum restarts on a filter's first piece, a piece = 8 bins from
+    4 * (word & 255) times weights[q, :, lane], the running sum is the filter's value after its last piece -> log(clamp)."""
     fr = _frames(y, 1024, hop) * win.double()
     mag = torch.fft.rfft(fr, dim=-1).abs()                                 # [B, F, 513]
     mag = torch.cat([mag, torch.zeros(mag.shape[:2] + (15,), dtype=mag.dtype)], dim=-1)      # the kernel's 528-entry buffer
     out = torch.full((mag.shape[0], n_mel, mag.shape[1]), float("nan"), dtype=torch.float64)
     for lane in range(32):
         total = torch.zeros(mag.shape[:2], dtype=torch.float64)
-        for bin4, piece, emit, first in slots[lane].tolist():
+        for q in range(slots.shape[0]):
+            word = int(slots[q, lane])
+            bin4, emit, first = word & 255, ((word >> 8) & 255) - 1, word >> 16
             if first:
                 total = torch.zeros_like(total)
-            total = total + (mag[..., 4 * bin4: 4 * bin4 + 8] * weights[piece].double()).sum(-1)
+            total = total + (mag[..., 4 * bin4: 4 * bin4 + 8] * weights[q, :, lane].reshape(8).double()).sum(-1)
             if emit >= 0:
                 assert torch.isnan(out[:, emit]).all()                     # every filter is emitted exactly once
                 out[:, emit] = total
@@ -255,11 +257,13 @@ def test_fft_path_operands_reproduce_the_oracle():
             taco = TacotronSTFT(1024, hop, win_length, 80, DC["sampling_rate"], DC["mel_fmin"], DC["mel_fmax"])
             slots, weights, per_lane, bins_used = taco._mel_slots(CPU)
             assert bins_used == 376 and int(torch.nonzero(mb_check(taco)).max()) < bins_used     # 8 kHz at 22.05 kHz: bin 371
-            assert slots.dtype == torch.int32 and slots.shape == (32, per_lane, 4) and per_lane <= 24
-            assert weights.shape[1] == 8 and weights.shape[0] <= 512 and float(weights[0].abs().max()) == 0.0
-            assert int(slots[..., 0].max()) * 4 + 8 <= 528                # the last piece stays inside the |X| buffer
-            assert sorted(slots[..., 2][slots[..., 2] >= 0].tolist()) == list(range(80))
-            assert per_lane <= 2 + weights.shape[0] // 32                  # balanced across the lanes
+            assert slots.dtype == torch.int32 and slots.shape == (per_lane, 32) and per_lane <= 16
+            assert weights.shape == (per_lane, 2, 32, 4)
+            assert int((slots & 255).max()) * 4 + 8 <= 528                # the last piece stays inside the |X| buffer
+            emitted = ((slots >> 8) & 255).flatten()
+            assert sorted((emitted[emitted > 0] - 1).tolist()) == list(range(80))
+            used = int(((weights.abs().sum((1, 3)) > 0) | (((slots >> 8) & 255) > 0)).sum())
+            assert per_lane <= 2 + used // 32                              # balanced across the lanes
             mb = torch.from_numpy(oracle.mel_filterbank(DC["sampling_rate"], 1024, 80, DC["mel_fmin"], DC["mel_fmax"])).float()
             want = oracle.mel_spectrogram(y, fwd, mb, hop)
             got = _fft_mel_emulated(y, win, slots, weights, 80, hop)

@@ -19,7 +19,7 @@ int tc2_stft_mel(const void*, const void*, const void*, const void*, float*, int
 int tc2_stft_denoise(const void*, const void*, const void*, const float*, float, void*, void*, int, int, int, int, int, int,
                      cudaStream_t);
 int tc2_istft_ola(const void*, const void*, const void*, const float*, float*, int, int, int, int, cudaStream_t);
-int fft_stft_mel(const float*, const float*, const void*, int, const float*, int, int, float*, int, int, int, int, float, int*, cudaStream_t);
+int fft_stft_mel(const float*, const float*, const void*, int, const float*, int, float*, int, int, int, int, float, int*, cudaStream_t);
 int fft_denoise(const float*, const float*, const float*, float, const float*, float*, int, int, int, cudaStream_t);
 int tc2_gemm_split3(const void*, const void*, const void*, float*, long long, int, int, cudaStream_t);
 int tc_stft_mel(const void*, const void*, const void*, const void*, void*, int, int, int, int, long long, long long, int, float,
@@ -242,10 +242,10 @@ WGB_API int wgb_tc2_istft_ola(const void* s_hi, const void* s_lo, const void* w_
     return tc2_istft_ola(s_hi, s_lo, w_ola, env_tab, out, batch, frames, L, hop, S(stream));
 }
 WGB_API int wgb_fft_stft_mel(const float* y, const float* window, const void* mel_slots, int slots_per_lane,
-                             const float* mel_w, int n_pieces, int bins_used, float* out, int batch, int n, int hop,
-                             int n_mel, float clip, int* range_flag, void* stream) {
-    return fft_stft_mel(y, window, mel_slots, slots_per_lane, mel_w, n_pieces, bins_used, out, batch, n, hop, n_mel, clip,
-                        range_flag, S(stream));
+                             const float* mel_w, int bins_used, float* out, int batch, int n, int hop, int n_mel,
+                             float clip, int* range_flag, void* stream) {
+    return fft_stft_mel(y, window, mel_slots, slots_per_lane, mel_w, bins_used, out, batch, n, hop, n_mel, clip, range_flag,
+                        S(stream));
 }
 WGB_API int wgb_fft_denoise(const float* y, const float* window, const float* bias_spec, float strength,
                             const float* env_tab, float* out, int batch, int n, int hop, void* stream) {

@@ -34,8 +34,7 @@ constexpr int kHalf = kL / 2;
 constexpr int kDnWarps = 12;              // denoise: the same (the register file is split over 4 schedulers: 3 warps each)
 constexpr int kDnThreads = kDnWarps * 32;
 constexpr int kMaxMel = 128;
-constexpr int kMaxPieces = 512;           // filterbank pieces of 8 bins
-constexpr int kMaxSlots = 24;             // pieces per lane
+constexpr int kMaxSlots = 16;             // filterbank pieces (of 8 bins) per lane
 constexpr int kMagPad = 528;              // |X| buffer: bins 0..512, then zeros that the last pieces may read
 
 __device__ __forceinline__ int reflect_index(int p, int n) {          // np.pad(mode='reflect'), |overhang| < n
@@ -141,12 +140,13 @@ __device__ __forceinline__ void irfft_split(int lane, const LaneTw& tw, cf* v, f
 struct MelParams {
     const float* y;            // [B, n]
     const float* window;       // [1024] (the window zero-padded to the filter length; ones for window=None)
-    const int4* mel_slots;     // [32][slots_per_lane] {float4 index into |X|, piece, filter to emit or -1, first piece of a filter}:
-                               // the filterbank as 8-bin pieces (4-bin aligned, zero-padded weights); a lane sums ALL pieces of
-                               // the filters it owns, in order, so no two lanes ever add into the same filter
+    const int* mel_slots;      // [slots_per_lane][32] packed {first bin / 4 | (filter to emit + 1) << 8 | starts a filter << 16}: the
+                               // filterbank as 8-bin pieces (4-bin aligned, zero-padded weights); lane l sums the pieces
+                               // [q][l], q = 0 .., in order: ALL pieces of the filters it owns, so no two lanes ever add
+                               // into the same filter
     int slots_per_lane;
-    const float4* mel_w;       // [n_pieces][2]: the 8 weights of each piece
-    int n_pieces;
+    const float4* mel_w;       // [slots_per_lane][2][32]: the 8 weights of piece [q][l] as two float4, lanes innermost
+                               // (conflict-free shared-memory reads)
     float* out;                // [B, n_mel, frames]
     int batch, n, frames, hop, n_mel;
     float clip;
@@ -159,13 +159,13 @@ __global__ void __launch_bounds__(kMelWarps * 32, 1) fft_mel_kernel(const MelPar
     extern __shared__ __align__(16) unsigned char smem[];
     cf* bufs = reinterpret_cast<cf*>(smem);                                         // [kMelWarps][kBufElems]
     float2* win2 = reinterpret_cast<float2*>(bufs + kMelWarps * kBufElems);         // [512]
-    int4* slots = reinterpret_cast<int4*>(win2 + kHalf);                            // [32][slots_per_lane]
-    float4* mw = reinterpret_cast<float4*>(slots + 32 * kMaxSlots);                 // [n_pieces][2]
+    float4* mw = reinterpret_cast<float4*>(win2 + kHalf);                           // [slots_per_lane][2][32]
+    int* slots = reinterpret_cast<int*>(mw + kMaxSlots * 64);                       // [slots_per_lane][32]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < kHalf; i += kMelThreads) win2[i] = make_float2(p.window[2 * i], p.window[2 * i + 1]);
     for (int i = threadIdx.x; i < 32 * p.slots_per_lane; i += kMelThreads) slots[i] = p.mel_slots[i];
-    for (int i = threadIdx.x; i < 2 * p.n_pieces; i += kMelThreads) mw[i] = p.mel_w[i];
+    for (int i = threadIdx.x; i < 64 * p.slots_per_lane; i += kMelThreads) mw[i] = p.mel_w[i];
     __syncthreads();
 
     LaneTw tw;
@@ -205,13 +205,15 @@ __global__ void __launch_bounds__(kMelWarps * 32, 1) fft_mel_kernel(const MelPar
             const float4* mag4 = reinterpret_cast<const float4*>(mag);
             float sum = 0.f;
             for (int q = 0; q < p.slots_per_lane; ++q) {
-                const int4 slot = slots[lane * p.slots_per_lane + q];
-                const float4 a0 = mag4[slot.x], a1 = mag4[slot.x + 1];
-                const float4 w0 = mw[2 * slot.y], w1 = mw[2 * slot.y + 1];
+                const int slot = slots[q * 32 + lane];
+                const float4* a = mag4 + (slot & 255);
+                const float4 a0 = a[0], a1 = a[1];
+                const float4 w0 = mw[q * 64 + lane], w1 = mw[q * 64 + 32 + lane];
                 const float s0 = fmaf(a0.w, w0.w, fmaf(a0.z, w0.z, fmaf(a0.y, w0.y, a0.x * w0.x)));
                 const float s1 = fmaf(a1.w, w1.w, fmaf(a1.z, w1.z, fmaf(a1.y, w1.y, a1.x * w1.x)));
-                sum = (slot.w ? 0.f : sum) + (s0 + s1);
-                if (slot.z >= 0) acc[slot.z] = sum;
+                sum = ((slot >> 16) ? 0.f : sum) + (s0 + s1);
+                const int emit = ((slot >> 8) & 255) - 1;
+                if (emit >= 0) acc[emit] = sum;
             }
         }
         __syncwarp();
@@ -354,7 +356,7 @@ static int check_common(const float* y, const float* window, int batch, int n, i
 }
 
 int fft_stft_mel(const float* y, const float* window, const void* mel_slots, int slots_per_lane, const float* mel_w,
-                 int n_pieces, int bins_used, float* out, int batch, int n, int hop, int n_mel, float clip, int* range_flag,
+                 int bins_used, float* out, int batch, int n, int hop, int n_mel, float clip, int* range_flag,
                  cudaStream_t stream) {
     using namespace fftk;
     if (int e = check_common(y, window, batch, n, hop)) return e;
@@ -362,16 +364,15 @@ int fft_stft_mel(const float* y, const float* window, const void* mel_slots, int
     WGB_REQUIRE(n_mel >= 1 && n_mel <= kMaxMel, "n_mel (%d) must be in 1..%d", n_mel, kMaxMel);
     WGB_REQUIRE(slots_per_lane >= 1 && slots_per_lane <= kMaxSlots, "slots_per_lane (%d) must be in 1..%d", slots_per_lane,
                 kMaxSlots);
-    WGB_REQUIRE(n_pieces >= 1 && n_pieces <= kMaxPieces, "n_pieces (%d) must be in 1..%d", n_pieces, kMaxPieces);
     WGB_REQUIRE(bins_used >= 1 && bins_used <= kHalf + 1, "bins_used (%d) must be in 1..%d", bins_used, kHalf + 1);
     MelParams p{};
-    p.y = y; p.window = window; p.mel_slots = static_cast<const int4*>(mel_slots); p.slots_per_lane = slots_per_lane;
-    p.mel_w = reinterpret_cast<const float4*>(mel_w); p.n_pieces = n_pieces;
+    p.y = y; p.window = window; p.mel_slots = static_cast<const int*>(mel_slots); p.slots_per_lane = slots_per_lane;
+    p.mel_w = reinterpret_cast<const float4*>(mel_w);
     p.out = out; p.batch = batch; p.n = n; p.frames = n / hop + 1; p.hop = hop; p.n_mel = n_mel; p.clip = clip;
     p.range_flag = range_flag;
     WGB_REQUIRE(static_cast<long long>(batch) * p.frames < 0x40000000LL, "too many frames");
     const int warps = tuning_get("fft_mel_warps") == 16 ? 16 : 12;
-    const int smem = warps * kBufElems * 8 + kHalf * 8 + 32 * kMaxSlots * 16 + n_pieces * 32;
+    const int smem = warps * kBufElems * 8 + kHalf * 8 + kMaxSlots * (64 * 16 + 32 * 4);
     // bins 0 .. 383 suffice for the usual filterbanks (fmax 8 kHz at 22.05 kHz ends at bin 371): the real-FFT split and the
     // magnitudes of the upper quarter are then compiled out (bin 512, the Nyquist bin, is always computed)
     const bool quarter = bins_used <= 384 && warps == 12;

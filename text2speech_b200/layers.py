@@ -93,14 +93,13 @@ class TacotronSTFT(torch.nn.Module):
         return (tab, self._mel_tab[2]) if cached[1] else None
 
     def _mel_slots(self, device):
-        """mel_basis for wgb_fft_stft_mel: (slots int32 [32, S, 4], piece weights fp32 [n_pieces, 8], S, bins the pieces
-        with weight reach), or None when the
-        basis does not fit the kernel's shared-memory tables.  A filter's non-zero span is covered by pieces of 8 bins
-        that start at multiples of 4 (two aligned 16-byte reads of |X| each; weights zero outside the span); whole
-        filters are dealt to the 32 lanes of a warp, most pieces first onto the least loaded lane, and a lane's slots list
-        its filters' pieces in order: {first bin / 4, piece, filter to emit after this piece or -1, starts a filter}.
-        Piece 0 is all zeros: filters without any weight emit it (log(clip), like the reference's matmul), and it pads
-        the shorter lanes."""
+        """mel_basis for wgb_fft_stft_mel: (slots int32 [S, 32], piece weights fp32 [S, 2, 32, 4], S, bins the pieces with
+        weight reach), or None when the basis does not fit the kernel's tables.  A filter's non-zero span is covered by
+        pieces of 8 bins that start at multiples of 4 (two aligned 16-byte reads of |X| each; weights zero outside the span);
+        whole filters are dealt to the 32 lanes of a warp, most pieces first onto the least loaded lane, and lane l's
+        slots [q][l] list its filters' pieces in order, packed as first bin / 4 | (filter to emit after this piece + 1) << 8
+        | (starts a filter) << 16.  Filters without any weight get one all-zero piece (they emit log(clip), like the
+        reference's matmul); unused slots have zero weights and emit nothing."""
         key = (str(device), self.mel_basis.data_ptr(), self.mel_basis._version)
         cached = getattr(self, "_mel_slots_pack", None)
         if cached is None or cached[0] != key:
@@ -108,14 +107,14 @@ class TacotronSTFT(torch.nn.Module):
             n_mel, n_bins = basis.shape
             pack = None
             if n_mel <= 128 and n_bins == self.stft_fn.cutoff and n_bins == 513:
-                weights = [torch.zeros(8)]
-                filters = []                                   # (number of pieces, filter, [(bin4, piece), ...])
+                filters = []                                   # (number of pieces, filter, [(bin4, weights[8]), ...])
                 padded = torch.zeros((n_mel, 544))
                 padded[:, :n_bins] = basis
+                bins_used = 1
                 for m in range(n_mel):
                     nz = torch.nonzero(basis[m]).flatten()
                     if nz.numel() == 0:
-                        filters.append((1, m, [(0, 0)]))
+                        filters.append((1, m, [(0, torch.zeros(8))]))
                         continue
                     lo, hi = int(nz[0]), int(nz[-1]) + 1
                     pieces = []
@@ -124,25 +123,24 @@ class TacotronSTFT(torch.nn.Module):
                         w[: max(lo - start, 0)] = 0.0
                         if hi - start < 8:
                             w[hi - start:] = 0.0
-                        pieces.append((start // 4, len(weights)))
-                        weights.append(w)
+                        pieces.append((start // 4, w))
+                        bins_used = max(bins_used, start + 8)
                     filters.append((len(pieces), m, pieces))
                 lanes, load = [[] for _ in range(32)], [0] * 32
                 for cnt, m, pieces in sorted(filters, key=lambda f: (-f[0], f[1])):
                     i = min(range(32), key=lambda j: (load[j], j))
-                    for q, (bin4, piece) in enumerate(pieces):
-                        lanes[i].append([bin4, piece, m if q == cnt - 1 else -1, 1 if q == 0 else 0])
+                    for q, (bin4, w) in enumerate(pieces):
+                        lanes[i].append((bin4 | ((m + 1 if q == cnt - 1 else 0) << 8) | ((1 if q == 0 else 0) << 16), w))
                     load[i] += cnt
                 per_lane = max(load)
-                if per_lane <= 24 and len(weights) <= 512:
-                    table = torch.zeros((32, per_lane, 4), dtype=torch.int32)
-                    table[:, :, 2] = -1                       # padding slots: the zero piece, nothing emitted
+                if per_lane <= 16:
+                    table = torch.zeros((per_lane, 32), dtype=torch.int32)
+                    weights = torch.zeros((per_lane, 2, 32, 4), dtype=torch.float32)
                     for i, lst in enumerate(lanes):
-                        for q, slot in enumerate(lst):
-                            table[i, q] = torch.tensor(slot, dtype=torch.int32)
-                    bins_used = max([4 * bin4 + 8 for _, _, pieces in filters for bin4, piece in pieces if piece] + [1])
-                    pack = (table.contiguous().to(device), torch.stack(weights).contiguous().to(device), per_lane,
-                            min(bins_used, n_bins))
+                        for q, (word, w) in enumerate(lst):
+                            table[q, i] = word
+                            weights[q, 0, i], weights[q, 1, i] = w[:4], w[4:]
+                    pack = (table.contiguous().to(device), weights.contiguous().to(device), per_lane, min(bins_used, n_bins))
             self._mel_slots_pack = (key, pack)
             cached = self._mel_slots_pack
         return cached[1]

@@ -221,15 +221,15 @@ class STFT(torch.nn.Module):
 
     def _mel_fft(self, y: torch.Tensor, mel_pack, n_mel: int, clip: float, range_flag=None):
         """TacotronSTFT.mel_spectrogram as ONE butterfly kernel (wgb_fft_stft_mel), or None when that path does not
-        apply.  mel_pack = (slots int32 [32, S, 4], piece weights fp32 [n_pieces, 8], S, bins_used) from TacotronSTFT._mel_slots."""
+        apply.  mel_pack = (slots int32 [S, 32], piece weights fp32 [S, 2, 32, 4], S, bins_used) from TacotronSTFT._mel_slots."""
         pack = self._fft_pack(y.device)
         if pack is None or mel_pack is None or y.shape[1] <= self.filter_length // 2:
             return None
         _lib.require_b200(y.device)
         b, n = y.shape
         out = torch.empty((b, n_mel, n // self.hop_length + 1), device=y.device, dtype=torch.float32)
-        _lib.call("wgb_fft_stft_mel", y, pack[0], mel_pack[0], mel_pack[2], mel_pack[1], mel_pack[1].shape[0], mel_pack[3],
-                  out, b, n, self.hop_length, n_mel, float(clip), range_flag, _lib.stream_ptr())
+        _lib.call("wgb_fft_stft_mel", y, pack[0], mel_pack[0], mel_pack[2], mel_pack[1], mel_pack[3], out, b, n,
+                  self.hop_length, n_mel, float(clip), range_flag, _lib.stream_ptr())
         return out
 
     def _use_pair(self) -> bool:
